@@ -1,0 +1,1287 @@
+/*
+ * edge_oracle.cpp -- CPU oracle (TEST INFRASTRUCTURE ONLY, see edge_oracle.h).
+ *
+ * Restates, with the reference's per-edge operation order, the hot path of
+ * Exawind/nalu-wind's edge-based CVFEM assembly.  Reference citations are
+ * relative to /root/reference.  Build: `make -C oracle` (g++ -O2
+ * -ffp-contract=off so results are plain IEEE double, reproducible across
+ * hosts).
+ */
+#include "edge_oracle.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <set>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+constexpr int kMaxDim = 3;
+constexpr int kMaxRhs = 2 * kMaxDim;
+
+/* include/edge_kernels/EdgeKernelUtils.h:18-24 */
+inline double
+van_leer(double dqm, double dqp, double eps)
+{
+  return (2.0 * (dqm * dqp + std::fabs(dqm * dqp))) /
+         ((dqm + dqp) * (dqm + dqp) + eps);
+}
+
+} // namespace
+
+/* ------------------------------------------------------------------ */
+/*  sinks                                                              */
+/* ------------------------------------------------------------------ */
+
+struct orc_applier
+{
+  virtual ~orc_applier() {}
+  /* lhs: row-major n x n with n = nEnt*ldDof, rhs: n */
+  virtual void apply(
+    int nEnt, const int32_t* nodes, const double* rhs, const double* lhs,
+    int n) = 0;
+};
+
+namespace {
+
+/* unit_tests/UnitTestLinearSystem.h:42-72 */
+struct DenseApplier : orc_applier
+{
+  int64_t nNodes;
+  int numDof;
+  std::vector<double> lhs_, rhs_;
+  DenseApplier(int64_t nn, int nd) : nNodes(nn), numDof(nd)
+  {
+    const size_t n = size_t(nn) * nd;
+    lhs_.assign(n * n, 0.0);
+    rhs_.assign(n, 0.0);
+  }
+  void apply(
+    int nEnt, const int32_t* nodes, const double* rhs, const double* lhs,
+    int n) override
+  {
+    const size_t N = size_t(nNodes) * numDof;
+    for (int i = 0; i < nEnt; ++i) {
+      const size_t ioff = size_t(nodes[i]) * numDof;
+      for (int d = 0; d < numDof; ++d)
+        rhs_[ioff + d] += rhs[i * numDof + d];
+    }
+    for (int i = 0; i < nEnt; ++i) {
+      const size_t ioff = size_t(nodes[i]) * numDof;
+      for (int j = 0; j < nEnt; ++j) {
+        const size_t joff = size_t(nodes[j]) * numDof;
+        for (int d = 0; d < numDof; ++d) {
+          const int ii = i * numDof + d;
+          const int jj = j * numDof + d;
+          lhs_[(ioff + d) * N + (joff + d)] += lhs[ii * n + jj];
+        }
+      }
+    }
+  }
+};
+
+} // namespace
+
+/* ------------------------------------------------------------------ */
+/*  hypre-IJ style graph                                               */
+/* ------------------------------------------------------------------ */
+
+struct orc_graph
+{
+  int numDof;
+  int64_t iLower, iUpper; /* inclusive, already scaled by numDof */
+  int64_t numRows;
+
+  /* host graph containers, as in HypreLinearSystem.h */
+  std::vector<std::vector<int64_t>> columnsOwned;
+  std::vector<unsigned> rowCountOwned;
+  std::map<int64_t, std::vector<int64_t>> columnsShared;
+  std::map<int64_t, unsigned> rowCountShared;
+  std::set<int64_t> skippedRows;
+
+  /* finalized */
+  int64_t numRowsOwned = 0, nnzOwned = 0, numRowsShared = 0, nnzShared = 0;
+  std::vector<int64_t> rowStartOwned, rowStartShared;
+  std::vector<int64_t> cols, rows;
+  std::vector<int64_t> rowIndicesShared;
+  std::vector<int64_t> periodicRowsOwned;
+  std::unordered_map<int64_t, int64_t> mapShared;
+};
+
+extern "C" orc_graph*
+orc_graph_create(int num_dof, int64_t i_lower, int64_t i_upper)
+{
+  /* beginLinearSystemConstruction: src/HypreLinearSystem.C:97-208.
+   * iLower_/iUpper_ are node offsets * numDof, iUpper inclusive. */
+  auto* g = new orc_graph;
+  g->numDof = num_dof;
+  g->iLower = i_lower;
+  g->iUpper = i_upper;
+  g->numRows = i_upper - i_lower + 1;
+  g->columnsOwned.resize(g->numRows);
+  g->rowCountOwned.assign(g->numRows, 0u);
+  return g;
+}
+
+extern "C" void
+orc_graph_destroy(orc_graph* g)
+{
+  delete g;
+}
+
+extern "C" void
+orc_graph_set_skipped(orc_graph* g, const int64_t* rows, int64_t n)
+{
+  for (int64_t i = 0; i < n; ++i)
+    g->skippedRows.insert(rows[i]);
+}
+
+namespace {
+
+/* fill_owned_shared_data_structures_1DoF: src/HypreLinearSystem.C:211-236 */
+void
+fill_1dof(orc_graph* g, unsigned numNodes, const std::vector<int64_t>& hids)
+{
+  for (unsigned i = 0; i < numNodes; ++i) {
+    const int64_t hid = hids[i];
+    if (hid >= g->iLower && hid <= g->iUpper) {
+      const int64_t lid = hid - g->iLower;
+      g->rowCountOwned[lid]++;
+      auto& c = g->columnsOwned[lid];
+      c.insert(c.end(), hids.begin(), hids.end());
+    } else {
+      auto it = g->rowCountShared.find(hid);
+      if (it != g->rowCountShared.end()) {
+        it->second++;
+        auto& c = g->columnsShared.at(hid);
+        c.insert(c.end(), hids.begin(), hids.end());
+      } else {
+        g->rowCountShared.insert(std::make_pair(hid, 1u));
+        g->columnsShared.insert(std::make_pair(hid, hids));
+      }
+    }
+  }
+}
+
+/* fill_owned_shared_data_structures: src/HypreLinearSystem.C:238-269 */
+void
+fill_ndof(
+  orc_graph* g,
+  unsigned numNodes,
+  const std::vector<int64_t>& hids,
+  const std::vector<int64_t>& columns)
+{
+  for (unsigned i = 0; i < numNodes; ++i) {
+    const int64_t hid = hids[i];
+    for (int d = 0; d < g->numDof; ++d) {
+      const int64_t HID = hid * g->numDof + d;
+      if (HID >= g->iLower && HID <= g->iUpper) {
+        const int64_t lid = HID - g->iLower;
+        g->rowCountOwned[lid]++;
+        auto& c = g->columnsOwned[lid];
+        c.insert(c.end(), columns.begin(), columns.end());
+      } else {
+        auto it = g->rowCountShared.find(HID);
+        if (it != g->rowCountShared.end()) {
+          it->second++;
+          auto& c = g->columnsShared.at(HID);
+          c.insert(c.end(), columns.begin(), columns.end());
+        } else {
+          g->rowCountShared.insert(std::make_pair(HID, 1u));
+          g->columnsShared.insert(std::make_pair(HID, columns));
+        }
+      }
+    }
+  }
+}
+
+void
+graph_add_entities(
+  orc_graph* g,
+  int64_t nEnt,
+  unsigned nodesPerEnt,
+  const int32_t* entNodes,
+  const int64_t* node_hid)
+{
+  std::vector<int64_t> hids(nodesPerEnt);
+  std::vector<int64_t> columns(nodesPerEnt * g->numDof);
+  for (int64_t k = 0; k < nEnt; ++k) {
+    for (unsigned i = 0; i < nodesPerEnt; ++i) {
+      hids[i] = node_hid[entNodes[k * nodesPerEnt + i]];
+      /* fill_hids_columns: :271-283 */
+      for (int d = 0; d < g->numDof; ++d)
+        columns[i * g->numDof + d] = hids[i] * g->numDof + d;
+    }
+    if (g->numDof == 1)
+      fill_1dof(g, nodesPerEnt, hids);
+    else
+      fill_ndof(g, nodesPerEnt, hids, columns);
+  }
+}
+
+/* sort + scan-unique as in :1044-1054 */
+int64_t
+push_sorted_unique(std::vector<int64_t> columns, std::vector<int64_t>& out)
+{
+  std::sort(columns.begin(), columns.end());
+  int64_t count = 1;
+  int64_t col = columns[0];
+  for (size_t i = 1; i < columns.size(); ++i) {
+    if (columns[i] != col) {
+      out.push_back(col);
+      col = columns[i];
+      count++;
+    }
+  }
+  out.push_back(col);
+  return count;
+}
+
+} // namespace
+
+extern "C" void
+orc_graph_add_edges(
+  orc_graph* g,
+  int64_t n_edges,
+  const int32_t* edge_nodes,
+  const int64_t* node_hid)
+{
+  /* buildEdgeToNodeGraph: src/HypreLinearSystem.C:412-478 */
+  graph_add_entities(g, n_edges, 2, edge_nodes, node_hid);
+}
+
+extern "C" void
+orc_graph_add_nodes(
+  orc_graph* g, int64_t n_nodes, const int32_t* nodes, const int64_t* node_hid)
+{
+  /* buildNodeGraph: src/HypreLinearSystem.C:286-340 */
+  graph_add_entities(g, n_nodes, 1, nodes, node_hid);
+}
+
+extern "C" void
+orc_graph_finalize(orc_graph* g)
+{
+  /* buildCoeffApplierDeviceOwnedDataStructures: :999-1137 (no overset) */
+  std::vector<int64_t> colsOwned, countOwned;
+  g->periodicRowsOwned.clear();
+  for (int64_t j = g->iLower; j <= g->iUpper; ++j) {
+    const int64_t jShift = j - g->iLower;
+    int64_t cnt = 1;
+    const auto& columns = g->columnsOwned[jShift];
+    if (g->skippedRows.find(j) != g->skippedRows.end()) {
+      colsOwned.push_back(j); /* Dirichlet row: diagonal only */
+    } else if (columns.size() == 0) {
+      colsOwned.push_back(j); /* untouched row == periodic slave */
+      g->periodicRowsOwned.push_back(j);
+    } else if (columns.size() == 1) {
+      colsOwned.push_back(j);
+    } else {
+      cnt = push_sorted_unique(columns, colsOwned);
+    }
+    countOwned.push_back(cnt);
+  }
+  g->numRowsOwned = (int64_t)countOwned.size();
+  g->nnzOwned = (int64_t)colsOwned.size();
+  g->rowStartOwned.assign(g->numRowsOwned + 1, 0);
+  for (int64_t i = 0; i < g->numRowsOwned; ++i)
+    g->rowStartOwned[i + 1] = g->rowStartOwned[i] + countOwned[i];
+
+  /* buildCoeffApplierDeviceSharedDataStructures: :1143-1236 */
+  std::vector<int64_t> colsShared, countShared;
+  g->rowIndicesShared.clear();
+  for (auto it = g->rowCountShared.begin(); it != g->rowCountShared.end();
+       ++it) {
+    const int64_t hid = it->first;
+    const auto& columns = g->columnsShared[hid];
+    int64_t cnt = 1;
+    if (g->skippedRows.find(hid) != g->skippedRows.end()) {
+      continue;
+    } else if (columns.size() == 1) {
+      colsShared.push_back(hid);
+    } else if (columns.size() > 1) {
+      cnt = push_sorted_unique(columns, colsShared);
+    } else
+      continue;
+    g->rowIndicesShared.push_back(hid);
+    countShared.push_back(cnt);
+  }
+  g->numRowsShared = (int64_t)g->rowIndicesShared.size();
+  g->nnzShared = (int64_t)colsShared.size();
+  g->rowStartShared.assign(g->numRowsShared + 1, 0);
+  g->mapShared.clear();
+  for (int64_t i = 0; i < g->numRowsShared; ++i) {
+    g->rowStartShared[i + 1] = g->rowStartShared[i] + countShared[i];
+    g->mapShared[g->rowIndicesShared[i]] = i; /* init_shared_map :1233 */
+  }
+
+  /* computeRowSizes: :956-993 -- monolithic cols / rows arrays, owned first */
+  g->cols.clear();
+  g->cols.insert(g->cols.end(), colsOwned.begin(), colsOwned.end());
+  g->cols.insert(g->cols.end(), colsShared.begin(), colsShared.end());
+  g->rows.assign(g->cols.size(), 0);
+  int64_t k = 0;
+  for (int64_t i = 0; i < g->numRowsOwned; ++i)
+    for (int64_t j = 0; j < countOwned[i]; ++j)
+      g->rows[k++] = g->iLower + i;
+  k = g->nnzOwned;
+  for (int64_t i = 0; i < g->numRowsShared; ++i)
+    for (int64_t j = 0; j < countShared[i]; ++j)
+      g->rows[k++] = g->rowIndicesShared[i];
+
+  /* :1319-1330 the host containers are cleared for the next build */
+  for (auto& c : g->columnsOwned)
+    c.clear();
+  std::fill(g->rowCountOwned.begin(), g->rowCountOwned.end(), 0u);
+  g->columnsShared.clear();
+  g->rowCountShared.clear();
+}
+
+extern "C" int64_t
+orc_graph_size(const orc_graph* g, int what)
+{
+  switch (what) {
+  case ORC_G_NUM_ROWS_OWNED:
+    return g->numRowsOwned;
+  case ORC_G_NNZ_OWNED:
+    return g->nnzOwned;
+  case ORC_G_NUM_ROWS_SHARED:
+    return g->numRowsShared;
+  case ORC_G_NNZ_SHARED:
+    return g->nnzShared;
+  case ORC_G_NUM_PERIODIC_ROWS:
+    return (int64_t)g->periodicRowsOwned.size();
+  }
+  return -1;
+}
+
+extern "C" void
+orc_graph_copy(const orc_graph* g, int what, int64_t* out)
+{
+  const std::vector<int64_t>* v = nullptr;
+  switch (what) {
+  case ORC_G_ROW_START_OWNED:
+    v = &g->rowStartOwned;
+    break;
+  case ORC_G_ROW_START_SHARED:
+    v = &g->rowStartShared;
+    break;
+  case ORC_G_COLS:
+    v = &g->cols;
+    break;
+  case ORC_G_ROWS:
+    v = &g->rows;
+    break;
+  case ORC_G_ROW_INDICES_SHARED:
+    v = &g->rowIndicesShared;
+    break;
+  case ORC_G_PERIODIC_ROWS:
+    v = &g->periodicRowsOwned;
+    break;
+  }
+  if (v && !v->empty())
+    std::memcpy(out, v->data(), v->size() * sizeof(int64_t));
+}
+
+/* ------------------------------------------------------------------ */
+/*  hypre coefficient applier                                          */
+/* ------------------------------------------------------------------ */
+
+namespace {
+
+struct HypreApplier : orc_applier
+{
+  const orc_graph* g;
+  std::vector<int64_t> nodeHid;
+  int uvwDim; /* 0: HypreLinSysCoeffApplier; >0: UVW with that many rhs */
+  int nRhs;
+  int64_t totalRows;
+  std::vector<double> values, rhs;       /* rhs column-major [totalRows][nRhs] */
+  std::vector<double> absValues, absRhs; /* |.| scatter, tolerance scale */
+  bool logOn = false;
+  int64_t logCalls = 0, callNo = 0;
+  int logN = 0;
+  std::vector<int64_t> logSlots, logRhs;
+
+  HypreApplier(const orc_graph* gg, const int64_t* hid, int64_t nn, int uvw)
+    : g(gg), nodeHid(hid, hid + nn), uvwDim(uvw)
+  {
+    nRhs = uvw > 0 ? uvw : 1;
+    totalRows = g->numRowsOwned + g->numRowsShared;
+    reset();
+  }
+
+  /* resetCoeffApplierData: src/HypreLinearSystem.C:1386-1430 */
+  void reset()
+  {
+    values.assign(g->cols.size(), 0.0);
+    rhs.assign(size_t(totalRows) * nRhs, 0.0);
+    absValues.assign(g->cols.size(), 0.0);
+    absRhs.assign(size_t(totalRows) * nRhs, 0.0);
+    for (int64_t hid : g->periodicRowsOwned) {
+      const int64_t matIndex = g->rowStartOwned[hid - g->iLower];
+      values[matIndex] = 1.0;
+      absValues[matIndex] = 1.0;
+      for (int d = 0; d < nRhs; ++d)
+        rhs[size_t(d) * totalRows + (hid - g->iLower)] = 0.0;
+    }
+    callNo = 0;
+  }
+
+  /* HypreLinSysCoeffApplier::sort, :1960-2055: for N==2 a single
+   * compare-exchange, N<=4 fixed networks, else bubble sort; all are stable
+   * orderings of distinct ids, restated here as one stable insertion sort
+   * (ids within one entity set are distinct unless periodic aliasing, where
+   * the relative order of equal ids follows the strict '>' comparisons). */
+  static void sort_ids(int64_t* ids, int* perm, unsigned N)
+  {
+    if (N == 2) {
+      if (ids[0] > ids[1]) {
+        std::swap(ids[0], ids[1]);
+        std::swap(perm[0], perm[1]);
+      }
+      return;
+    }
+    for (unsigned i = 0; i + 1 < N; ++i)
+      for (unsigned j = 0; j + 1 < N - i; ++j)
+        if (ids[j] > ids[j + 1]) {
+          std::swap(ids[j], ids[j + 1]);
+          std::swap(perm[j], perm[j + 1]);
+        }
+  }
+
+  void log_slot(int n, int ii, int kk, int64_t idx)
+  {
+    if (logOn && callNo < logCalls)
+      logSlots[(size_t(callNo) * n + ii) * n + kk] = idx;
+  }
+  void log_rhs(int n, int ii, int64_t idx)
+  {
+    if (logOn && callNo < logCalls)
+      logRhs[size_t(callNo) * n + ii] = idx;
+  }
+
+  void add_rhs(int64_t row, int d, double v)
+  {
+    rhs[size_t(d) * totalRows + row] += v;
+    absRhs[size_t(d) * totalRows + row] += std::fabs(v);
+  }
+  void add_val(int64_t idx, double v)
+  {
+    values[idx] += v;
+    absValues[idx] += std::fabs(v);
+  }
+
+  /* sum_into_1DoF: src/HypreLinearSystem.C:2165-2239 */
+  void sum_into_1dof(
+    unsigned nEnt, const int32_t* nodes, const double* r, const double* lhs,
+    int n)
+  {
+    int64_t localIds[8];
+    int perm[8];
+    for (unsigned i = 0; i < nEnt; ++i) {
+      localIds[i] = nodeHid[nodes[i]];
+      perm[i] = int(i);
+    }
+    sort_ids(localIds, perm, nEnt);
+    const int64_t memShift = g->nnzOwned;
+    for (unsigned i = 0; i < nEnt; ++i) {
+      const int64_t hid = localIds[i];
+      if (g->skippedRows.count(hid))
+        continue;
+      const int ii = perm[i];
+      const double* cur = &lhs[ii * n];
+      if (hid >= g->iLower && hid <= g->iUpper) {
+        const int64_t index = hid - g->iLower;
+        int64_t matIndex = g->rowStartOwned[index];
+        for (unsigned k = 0; k < nEnt; ++k) {
+          const int64_t col = localIds[k];
+          while (g->cols[matIndex] < col)
+            matIndex++;
+          const int kk = perm[k];
+          add_val(matIndex, cur[kk]);
+          log_slot(n, ii, kk, matIndex);
+          matIndex++;
+        }
+        add_rhs(index, 0, r[ii]);
+        log_rhs(n, ii, index);
+      } else {
+        auto it = g->mapShared.find(hid);
+        if (it == g->mapShared.end())
+          continue;
+        const int64_t index = it->second;
+        int64_t matIndex = g->rowStartShared[index] + memShift;
+        for (unsigned k = 0; k < nEnt; ++k) {
+          const int64_t col = localIds[k];
+          while (g->cols[matIndex] < col)
+            matIndex++;
+          const int kk = perm[k];
+          add_val(matIndex, cur[kk]);
+          log_slot(n, ii, kk, matIndex);
+          matIndex++;
+        }
+        /* rhs_row_start_shared_(index) == index (one rhs slot per row) */
+        const int64_t rhsIndex = index + (g->iUpper - g->iLower + 1);
+        add_rhs(rhsIndex, 0, r[ii]);
+        log_rhs(n, ii, rhsIndex);
+      }
+    }
+  }
+
+  /* sum_into: src/HypreLinearSystem.C:2059-2161 */
+  void sum_into_ndof(
+    unsigned nEnt, const int32_t* nodes, const double* r, const double* lhs,
+    int n)
+  {
+    const unsigned numDof = unsigned(g->numDof);
+    const unsigned numRows = nEnt * numDof;
+    int64_t localIds[4 * kMaxDim];
+    int perm[4 * kMaxDim];
+    for (unsigned i = 0; i < nEnt; ++i) {
+      const int64_t hid = nodeHid[nodes[i]];
+      for (unsigned d = 0; d < numDof; ++d) {
+        const unsigned lid = i * numDof + d;
+        localIds[lid] = hid * numDof + d;
+        perm[lid] = int(lid);
+      }
+    }
+    sort_ids(localIds, perm, numRows);
+    const int64_t memShift = g->nnzOwned;
+    for (unsigned i = 0; i < nEnt; ++i) {
+      const unsigned ix = i * numDof;
+      int64_t hid = localIds[ix];
+      /* quirk: only the first dof's row id is tested (:2095-2099) */
+      if (g->skippedRows.count(hid))
+        continue;
+      if (hid >= g->iLower && hid <= g->iUpper) {
+        for (unsigned d = 0; d < numDof; ++d) {
+          const unsigned ir = ix + d;
+          hid = localIds[ir];
+          const int ii = perm[ir];
+          const double* cur = &lhs[ii * n];
+          const int64_t index = hid - g->iLower;
+          int64_t matIndex = g->rowStartOwned[index];
+          for (unsigned k = 0; k < numRows; ++k) {
+            const int64_t col = localIds[k];
+            while (g->cols[matIndex] < col)
+              matIndex++;
+            const int kk = perm[k];
+            add_val(matIndex, cur[kk]);
+            log_slot(n, ii, kk, matIndex);
+          }
+          add_rhs(index, 0, r[ii]);
+          log_rhs(n, ii, index);
+        }
+      } else {
+        for (unsigned d = 0; d < numDof; ++d) {
+          const unsigned ir = ix + d;
+          hid = localIds[ir];
+          const int ii = perm[ir];
+          const double* cur = &lhs[ii * n];
+          auto it = g->mapShared.find(hid);
+          if (it == g->mapShared.end())
+            continue;
+          const int64_t index = it->second;
+          int64_t matIndex = g->rowStartShared[index] + memShift;
+          for (unsigned k = 0; k < numRows; ++k) {
+            const int64_t col = localIds[k];
+            while (g->cols[matIndex] < col)
+              matIndex++;
+            const int kk = perm[k];
+            add_val(matIndex, cur[kk]);
+            log_slot(n, ii, kk, matIndex);
+          }
+          const int64_t rhsIndex = index + (g->iUpper - g->iLower + 1);
+          add_rhs(rhsIndex, 0, r[ii]);
+          log_rhs(n, ii, rhsIndex);
+        }
+      }
+    }
+  }
+
+  /* HypreUVWLinSysCoeffApplier::sum_into:
+   * src/HypreUVWLinearSystem.C:695-767.  lhs is the full
+   * (nEnt*nDim)^2 block; only entries (i*nDim, k*nDim) reach the matrix. */
+  void sum_into_uvw(
+    unsigned nEnt, const int32_t* nodes, const double* r, const double* lhs,
+    int n)
+  {
+    const unsigned nDim = unsigned(uvwDim);
+    int64_t localIds[8];
+    int perm[8];
+    for (unsigned i = 0; i < nEnt; ++i) {
+      localIds[i] = nodeHid[nodes[i]];
+      perm[i] = int(i * nDim);
+    }
+    sort_ids(localIds, perm, nEnt);
+    const int64_t memShift = g->nnzOwned;
+    for (unsigned i = 0; i < nEnt; ++i) {
+      const int ix = perm[i];
+      const int64_t hid = localIds[i];
+      if (g->skippedRows.count(hid))
+        continue;
+      int64_t index, matIndex, rhsIndex;
+      if (hid >= g->iLower && hid <= g->iUpper) {
+        index = hid - g->iLower;
+        matIndex = g->rowStartOwned[index];
+        rhsIndex = index;
+      } else {
+        auto it = g->mapShared.find(hid);
+        if (it == g->mapShared.end())
+          continue;
+        index = it->second;
+        matIndex = g->rowStartShared[index] + memShift;
+        rhsIndex = index + (g->iUpper - g->iLower + 1);
+      }
+      for (unsigned k = 0; k < nEnt; ++k) {
+        const int64_t col = localIds[k];
+        while (g->cols[matIndex] < col)
+          matIndex++;
+        add_val(matIndex, lhs[ix * n + perm[k]]);
+        log_slot(int(nEnt), ix / int(nDim), perm[k] / int(nDim), matIndex);
+        matIndex++;
+      }
+      for (unsigned d = 0; d < nDim; ++d)
+        add_rhs(rhsIndex, int(d), r[ix + int(d)]);
+      log_rhs(int(nEnt), ix / int(nDim), rhsIndex);
+    }
+  }
+
+  /* HypreLinSysCoeffApplier::operator(): :2241-2260 */
+  void apply(
+    int nEnt, const int32_t* nodes, const double* r, const double* lhs,
+    int n) override
+  {
+    if (uvwDim > 0)
+      sum_into_uvw(unsigned(nEnt), nodes, r, lhs, n);
+    else if (g->numDof == 1)
+      sum_into_1dof(unsigned(nEnt), nodes, r, lhs, n);
+    else
+      sum_into_ndof(unsigned(nEnt), nodes, r, lhs, n);
+    callNo++;
+  }
+};
+
+} // namespace
+
+extern "C" orc_applier*
+orc_applier_dense_create(int64_t n_nodes, int num_dof)
+{
+  return new DenseApplier(n_nodes, num_dof);
+}
+
+extern "C" void
+orc_applier_dense_get(const orc_applier* a, double* lhs, double* rhs)
+{
+  auto* d = static_cast<const DenseApplier*>(a);
+  std::memcpy(lhs, d->lhs_.data(), d->lhs_.size() * sizeof(double));
+  std::memcpy(rhs, d->rhs_.data(), d->rhs_.size() * sizeof(double));
+}
+
+extern "C" orc_applier*
+orc_applier_hypre_create(
+  const orc_graph* g, const int64_t* node_hid, int64_t n_nodes, int uvw_ndim)
+{
+  return new HypreApplier(g, node_hid, n_nodes, uvw_ndim);
+}
+
+extern "C" void
+orc_applier_hypre_reset(orc_applier* a)
+{
+  static_cast<HypreApplier*>(a)->reset();
+}
+
+extern "C" void
+orc_applier_hypre_get(const orc_applier* a, double* values, double* rhs)
+{
+  auto* h = static_cast<const HypreApplier*>(a);
+  if (values && !h->values.empty())
+    std::memcpy(values, h->values.data(), h->values.size() * sizeof(double));
+  if (rhs && !h->rhs.empty())
+    std::memcpy(rhs, h->rhs.data(), h->rhs.size() * sizeof(double));
+}
+
+extern "C" void
+orc_applier_hypre_get_abs(const orc_applier* a, double* values, double* rhs)
+{
+  auto* h = static_cast<const HypreApplier*>(a);
+  if (values && !h->absValues.empty())
+    std::memcpy(
+      values, h->absValues.data(), h->absValues.size() * sizeof(double));
+  if (rhs && !h->absRhs.empty())
+    std::memcpy(rhs, h->absRhs.data(), h->absRhs.size() * sizeof(double));
+}
+
+extern "C" void
+orc_applier_hypre_enable_log(orc_applier* a, int64_t n_calls)
+{
+  auto* h = static_cast<HypreApplier*>(a);
+  h->logOn = true;
+  h->logCalls = n_calls;
+  const int n = h->uvwDim > 0 ? 2 : 2 * h->g->numDof;
+  h->logN = n;
+  h->logSlots.assign(size_t(n_calls) * n * n, -1);
+  h->logRhs.assign(size_t(n_calls) * n, -1);
+}
+
+extern "C" void
+orc_applier_hypre_get_log(
+  const orc_applier* a, int64_t* slots, int64_t* rhs_index)
+{
+  auto* h = static_cast<const HypreApplier*>(a);
+  std::memcpy(slots, h->logSlots.data(), h->logSlots.size() * sizeof(int64_t));
+  std::memcpy(
+    rhs_index, h->logRhs.data(), h->logRhs.size() * sizeof(int64_t));
+}
+
+extern "C" void
+orc_applier_destroy(orc_applier* a)
+{
+  delete a;
+}
+
+/* ------------------------------------------------------------------ */
+/*  Peclet function                                                    */
+/* ------------------------------------------------------------------ */
+
+extern "C" double
+orc_peclet_eval(const orc_peclet* f, double pecnum)
+{
+  if (f->form == ORC_PECLET_CLASSIC) {
+    /* ClassicPecletFunction::execute, src/PecletFunction.C:41-45 (A_ unused) */
+    const double modPeclet = f->a * pecnum;
+    return modPeclet * modPeclet / (5.0 + modPeclet * modPeclet);
+  }
+  /* TanhFunction::execute, src/PecletFunction.C:68-71 */
+  return 0.50 * (1.0 + std::tanh((pecnum - f->a) / f->b));
+}
+
+/* ------------------------------------------------------------------ */
+/*  MdotEdgeAlg                                                        */
+/* ------------------------------------------------------------------ */
+
+extern "C" void
+orc_mdot_edge(
+  int ndim,
+  int64_t n_edges,
+  const int32_t* edge_nodes,
+  const double* coords,
+  const double* velocity,
+  const double* gpdx,
+  const double* density,
+  const double* pressure,
+  const double* udiag,
+  const double* edge_area,
+  double noc_fac,
+  double interp_together,
+  double* mdot)
+{
+  /* src/ngp_algorithms/MdotEdgeAlg.C:117-190 */
+  const double om_interp = 1.0 - interp_together;
+  for (int64_t e = 0; e < n_edges; ++e) {
+    double av[kMaxDim];
+    for (int d = 0; d < ndim; ++d)
+      av[d] = edge_area[e * ndim + d];
+    const int64_t nL = edge_nodes[2 * e], nR = edge_nodes[2 * e + 1];
+    const double pressureL = pressure[nL], pressureR = pressure[nR];
+    const double densityL = density[nL], densityR = density[nR];
+    const double udiagL = udiag[nL], udiagR = udiag[nR];
+    const double projTimeScale = 0.5 * (1.0 / udiagL + 1.0 / udiagR);
+    const double rhoIp = 0.5 * (densityL + densityR);
+    double axdx = 0.0, asq = 0.0;
+    for (int d = 0; d < ndim; ++d) {
+      const double dxj = coords[nR * ndim + d] - coords[nL * ndim + d];
+      asq += av[d] * av[d];
+      axdx += av[d] * dxj;
+    }
+    const double inv_axdx = 1.0 / axdx;
+    double tmdot = -projTimeScale * (pressureR - pressureL) * asq * inv_axdx;
+    for (int d = 0; d < ndim; ++d) {
+      const double dxj = coords[nR * ndim + d] - coords[nL * ndim + d];
+      const double kxj = av[d] - asq * inv_axdx * dxj;
+      const double rhoUjIp = 0.5 * (densityR * velocity[nR * ndim + d] +
+                                    densityL * velocity[nL * ndim + d]);
+      const double ujIp =
+        0.5 * (velocity[nR * ndim + d] + velocity[nL * ndim + d]);
+      const double GjIp =
+        0.5 * (gpdx[nR * ndim + d] / udiagR + gpdx[nL * ndim + d] / udiagL);
+      tmdot +=
+        (interp_together * rhoUjIp + om_interp * rhoIp * ujIp + GjIp) * av[d] -
+        kxj * GjIp * noc_fac;
+    }
+    mdot[e] = tmdot;
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/*  MomentumEdgePecletAlg                                              */
+/* ------------------------------------------------------------------ */
+
+extern "C" void
+orc_peclet_edge(
+  int ndim,
+  int64_t n_edges,
+  const int32_t* edge_nodes,
+  const double* coords,
+  const double* vrtm,
+  const double* density,
+  const double* viscosity,
+  const orc_peclet* pf,
+  double eps,
+  double* pecnum_out,
+  double* pecfac)
+{
+  /* src/edge_kernels/MomentumEdgePecletAlg.C:74-101 */
+  for (int64_t e = 0; e < n_edges; ++e) {
+    double udotx = 0.0;
+    const int64_t nL = edge_nodes[2 * e], nR = edge_nodes[2 * e + 1];
+    const double diffIp =
+      0.5 * (viscosity[nL] / density[nL] + viscosity[nR] / density[nR]);
+    for (int d = 0; d < ndim; ++d) {
+      const double dxj = coords[nR * ndim + d] - coords[nL * ndim + d];
+      udotx += 0.5 * dxj * (vrtm[nR * ndim + d] + vrtm[nL * ndim + d]);
+    }
+    const double pecnum = std::fabs(udotx) / (diffIp + eps);
+    if (pecnum_out)
+      pecnum_out[e] = pecnum;
+    pecfac[e] = orc_peclet_eval(pf, pecnum);
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/*  NodalGradEdgeAlg                                                   */
+/* ------------------------------------------------------------------ */
+
+extern "C" void
+orc_nodal_grad_edge(
+  int dim1,
+  int dim2,
+  int64_t n_edges,
+  const int32_t* edge_nodes,
+  const double* phi,
+  const double* edge_area,
+  const double* dual_vol,
+  double* grad)
+{
+  /* src/ngp_algorithms/NodalGradEdgeAlg.C:85-109; the atomic adds of
+   * include/ngp_utils/NgpFieldOps.h:84 become serial adds in edge order. */
+  const int gsz = dim1 * dim2;
+  for (int64_t e = 0; e < n_edges; ++e) {
+    double av[kMaxDim];
+    for (int d = 0; d < dim2; ++d)
+      av[d] = edge_area[e * dim2 + d];
+    const int64_t nL = edge_nodes[2 * e], nR = edge_nodes[2 * e + 1];
+    const double invVolL = 1.0 / dual_vol[nL];
+    const double invVolR = 1.0 / dual_vol[nR];
+    int counter = 0;
+    for (int i = 0; i < dim1; ++i) {
+      const double phiIp = 0.5 * (phi[nL * dim1 + i] + phi[nR * dim1 + i]);
+      for (int j = 0; j < dim2; ++j) {
+        const double ajPhiIp = av[j] * phiIp;
+        grad[nL * gsz + counter] += ajPhiIp * invVolL;
+        grad[nR * gsz + counter] -= ajPhiIp * invVolR;
+        counter++;
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/*  ContinuityEdgeSolverAlg                                            */
+/* ------------------------------------------------------------------ */
+
+extern "C" void
+orc_continuity_edge(
+  int ndim,
+  int64_t n_edges,
+  const int32_t* edge_nodes,
+  const double* coords,
+  const double* velocity,
+  const double* gpdx,
+  const double* density,
+  const double* pressure,
+  const double* udiag,
+  const double* edge_area,
+  const orc_continuity_opts* o,
+  orc_applier* sink)
+{
+  /* shell: include/AssembleEdgeSolverAlgorithm.h:72-98
+   * body:  src/edge_kernels/ContinuityEdgeSolverAlg.C:37-60, 109-194 */
+  const double nocFac = o->noc_fac;
+  const double tauScale = o->dt / o->gamma1;
+  const double interpTogether = o->interp_together;
+  const double om_interpTogether = 1.0 - interpTogether;
+  const double solveInc = o->solve_incompressible;
+  const double om_solveInc = 1.0 - solveInc;
+
+  for (int64_t e = 0; e < n_edges; ++e) {
+    double lhs[4] = {0.0, 0.0, 0.0, 0.0};
+    double rhs[2] = {0.0, 0.0};
+    double av[kMaxDim];
+    for (int d = 0; d < ndim; ++d)
+      av[d] = edge_area[e * ndim + d];
+    const int32_t nodes[2] = {edge_nodes[2 * e], edge_nodes[2 * e + 1]};
+    const int64_t nL = nodes[0], nR = nodes[1];
+
+    const double pressureL = pressure[nL], pressureR = pressure[nR];
+    const double densityL = density[nL], densityR = density[nR];
+    const double udiagL = udiag[nL], udiagR = udiag[nR];
+    const double projTimeScale = 0.5 * (1.0 / udiagL + 1.0 / udiagR);
+    const double rhoIp = 0.5 * (densityL + densityR);
+    const double denScale = (1.0 / rhoIp) * solveInc + om_solveInc;
+
+    double axdx = 0.0, asq = 0.0;
+    for (int d = 0; d < ndim; ++d) {
+      const double dxj = coords[nR * ndim + d] - coords[nL * ndim + d];
+      asq += av[d] * av[d];
+      axdx += av[d] * dxj;
+    }
+    const double inv_axdx = 1.0 / axdx;
+
+    double tmdot = -projTimeScale * (pressureR - pressureL) * asq * inv_axdx;
+    for (int d = 0; d < ndim; ++d) {
+      const double dxj = coords[nR * ndim + d] - coords[nL * ndim + d];
+      const double kxj = av[d] - asq * inv_axdx * dxj;
+      const double rhoUjIp = 0.5 * (densityR * velocity[nR * ndim + d] +
+                                    densityL * velocity[nL * ndim + d]);
+      const double ujIp =
+        0.5 * (velocity[nR * ndim + d] + velocity[nL * ndim + d]);
+      const double GjIp = 0.5 * (gpdx[nR * ndim + d] / (udiagR) +
+                                 gpdx[nL * ndim + d] / (udiagL));
+      tmdot += (interpTogether * rhoUjIp + om_interpTogether * rhoIp * ujIp +
+                GjIp) *
+                 av[d] -
+               kxj * GjIp * nocFac;
+    }
+    tmdot /= tauScale;
+    tmdot *= denScale;
+    const double lhsfac = -asq * inv_axdx * projTimeScale * denScale / tauScale;
+
+    lhs[0] = -lhsfac;
+    lhs[1] = +lhsfac;
+    rhs[0] = -tmdot;
+    lhs[2] = +lhsfac;
+    lhs[3] = -lhsfac;
+    rhs[1] = tmdot;
+
+    sink->apply(2, nodes, rhs, lhs, 2);
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/*  ScalarEdgeSolverAlg                                                */
+/* ------------------------------------------------------------------ */
+
+extern "C" void
+orc_scalar_edge(
+  int ndim,
+  int64_t n_edges,
+  const int32_t* edge_nodes,
+  const double* coords,
+  const double* vrtm,
+  const double* q,
+  const double* dqdx,
+  const double* density,
+  const double* diff_flux_coeff,
+  const double* edge_area,
+  const double* mdot_f,
+  const orc_scalar_opts* o,
+  orc_applier* sink)
+{
+  /* src/edge_kernels/ScalarEdgeSolverAlg.C:55-70, 85-205 */
+  const double eps = o->eps;
+  const double alpha = o->alpha;
+  const double alphaUpw = o->alpha_upw;
+  const double hoUpwind = o->ho_upwind;
+  const double relaxFac = o->relax_fac;
+  const bool useLimiter = o->use_limiter != 0;
+  const double om_alpha = 1.0 - alpha;
+  const double om_alphaUpw = 1.0 - alphaUpw;
+
+  for (int64_t e = 0; e < n_edges; ++e) {
+    double lhs[4] = {0.0, 0.0, 0.0, 0.0};
+    double rhs[2] = {0.0, 0.0};
+    double av[kMaxDim];
+    for (int d = 0; d < ndim; ++d)
+      av[d] = edge_area[e * ndim + d];
+    const int32_t nodes[2] = {edge_nodes[2 * e], edge_nodes[2 * e + 1]};
+    const int64_t nL = nodes[0], nR = nodes[1];
+
+    const double mdot = mdot_f[e];
+    const double densityL = density[nL], densityR = density[nR];
+    const double qNp1L = q[nL], qNp1R = q[nR];
+    const double viscosityL = diff_flux_coeff[nL];
+    const double viscosityR = diff_flux_coeff[nR];
+    const double viscIp = 0.5 * (viscosityL + viscosityR);
+    const double diffIp =
+      0.5 * (viscosityL / densityL + viscosityR / densityR);
+
+    double axdx = 0.0, asq = 0.0, udotx = 0.0;
+    for (int d = 0; d < ndim; ++d) {
+      const double dxj = coords[nR * ndim + d] - coords[nL * ndim + d];
+      asq += av[d] * av[d];
+      axdx += av[d] * dxj;
+      udotx += 0.5 * dxj * (vrtm[nR * ndim + d] + vrtm[nL * ndim + d]);
+    }
+    const double inv_axdx = 1.0 / axdx;
+
+    double dqL = 0.0, dqR = 0.0, nonOrth = 0.0;
+    for (int d = 0; d < ndim; ++d) {
+      const double dxj = (coords[nR * ndim + d] - coords[nL * ndim + d]);
+      dqL += 0.5 * dxj * dqdx[nL * ndim + d];
+      dqR += 0.5 * dxj * dqdx[nR * ndim + d];
+      const double kxj = av[d] - asq * inv_axdx * dxj;
+      nonOrth +=
+        -viscIp * kxj * 0.5 * (dqdx[nR * ndim + d] + dqdx[nL * ndim + d]);
+    }
+
+    const double pecnum = std::fabs(udotx) / (diffIp + eps);
+    const double pecfac = orc_peclet_eval(&o->pf, pecnum);
+    const double om_pecfac = 1.0 - pecfac;
+
+    double limitL = 1.0, limitR = 1.0;
+    if (useLimiter) {
+      const double dq = qNp1R - qNp1L;
+      const double dqML = 4.0 * dqL - dq;
+      const double dqMR = 4.0 * dqR - dq;
+      limitL = van_leer(dqML, dq, eps);
+      limitR = van_leer(dqMR, dq, eps);
+    }
+
+    const double qIpL = qNp1L + dqL * hoUpwind * limitL;
+    const double qIpR = qNp1R - dqR * hoUpwind * limitR;
+
+    const double lhsfac = -viscIp * asq * inv_axdx;
+    const double diffFlux = lhsfac * (qNp1R - qNp1L) + nonOrth;
+
+    lhs[0] = -lhsfac / relaxFac;
+    lhs[1] = lhsfac;
+    rhs[0] = -diffFlux;
+    lhs[2] = lhsfac;
+    lhs[3] = -lhsfac / relaxFac;
+    rhs[1] = diffFlux;
+
+    const double qIp = 0.5 * (qNp1R + qNp1L);
+    const double qUpw = (mdot > 0) ? (alphaUpw * qIpL + om_alphaUpw * qIp)
+                                   : (alphaUpw * qIpR + om_alphaUpw * qIp);
+    const double qHatL = (alpha * qIpL + om_alpha * qIp);
+    const double qHatR = (alpha * qIpR + om_alpha * qIp);
+    const double qCds = 0.5 * (qHatL + qHatR);
+
+    const double adv_flux = mdot * (pecfac * qUpw + om_pecfac * qCds);
+    rhs[0] -= adv_flux;
+    rhs[1] += adv_flux;
+
+    double alhsfac = 0.5 * (mdot + std::fabs(mdot)) * pecfac * alphaUpw +
+                     0.5 * alpha * om_pecfac * mdot;
+    lhs[0] += alhsfac / relaxFac;
+    lhs[2] -= alhsfac;
+
+    alhsfac = 0.5 * (mdot - std::fabs(mdot)) * pecfac * alphaUpw +
+              0.5 * alpha * om_pecfac * mdot;
+    lhs[3] -= alhsfac / relaxFac;
+    lhs[1] += alhsfac;
+
+    alhsfac = 0.5 * mdot * (pecfac * om_alphaUpw + om_pecfac * om_alpha);
+    lhs[0] += alhsfac / relaxFac;
+    lhs[1] += alhsfac;
+    lhs[2] -= alhsfac;
+    lhs[3] -= alhsfac / relaxFac;
+
+    sink->apply(2, nodes, rhs, lhs, 2);
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/*  MomentumEdgeSolverAlg                                              */
+/* ------------------------------------------------------------------ */
+
+extern "C" void
+orc_momentum_edge(
+  int ndim,
+  int64_t n_edges,
+  const int32_t* edge_nodes,
+  const double* coords,
+  const double* vel,
+  const double* dudx,
+  const double* viscosity,
+  const double* density,
+  const double* node_mask,
+  const double* edge_area,
+  const double* mdot_f,
+  const double* pecfac_f,
+  const orc_momentum_opts* o,
+  orc_applier* sink,
+  double* udiag_accum)
+{
+  /* src/edge_kernels/MomentumEdgeSolverAlg.C:70-88, 105-312 with
+   * has_vof == 0 (mdot == massFlowRate, density_upwinding_factor == 1). */
+  const double eps = o->eps;
+  const double includeDivU = o->include_divu;
+  const double alpha = o->alpha;
+  const double alphaUpw = o->alpha_upw;
+  const double hoUpwind = o->ho_upwind;
+  const double relaxFacU = o->relax_fac;
+  const bool useLimiter = o->use_limiter != 0;
+  const double om_alpha = 1.0 - alpha;
+  const double om_alphaUpw = 1.0 - alphaUpw;
+  const double density_upwinding_factor = 1.0;
+  const int n = 2 * ndim;
+  (void)density; /* only read by the VOF branch (:178-192), has_vof == 0 */
+
+  for (int64_t e = 0; e < n_edges; ++e) {
+    double lhs[kMaxRhs * kMaxRhs];
+    double rhs[kMaxRhs];
+    for (int i = 0; i < n * n; ++i)
+      lhs[i] = 0.0;
+    for (int i = 0; i < n; ++i)
+      rhs[i] = 0.0;
+#define LHS(r, c) lhs[(r) * n + (c)]
+
+    double av[kMaxDim];
+    for (int d = 0; d < ndim; ++d)
+      av[d] = edge_area[e * ndim + d];
+    const int32_t nodes[2] = {edge_nodes[2 * e], edge_nodes[2 * e + 1]};
+    const int64_t nL = nodes[0], nR = nodes[1];
+    const double* xL = &coords[nL * ndim];
+    const double* xR = &coords[nR * ndim];
+    const double* uL = &vel[nL * ndim];
+    const double* uR = &vel[nR * ndim];
+    const double* gL = &dudx[nL * ndim * ndim];
+    const double* gR = &dudx[nR * ndim * ndim];
+
+    const double mdot = mdot_f[e];
+    const double viscosityL = viscosity[nL], viscosityR = viscosity[nR];
+    const double viscIp = 0.5 * (viscosityL + viscosityR);
+
+    double axdx = 0.0, asq = 0.0;
+    for (int d = 0; d < ndim; ++d) {
+      const double dxj = xR[d] - xL[d];
+      asq += av[d] * av[d];
+      axdx += av[d] * dxj;
+    }
+    const double inv_axdx = 1.0 / axdx;
+
+    double duL[kMaxDim], duR[kMaxDim];
+    for (int i = 0; i < ndim; ++i) {
+      const int offset = i * ndim;
+      duL[i] = 0.0;
+      duR[i] = 0.0;
+      for (int j = 0; j < ndim; ++j) {
+        const double dxj = 0.5 * (xR[j] - xL[j]);
+        duL[i] += dxj * gL[offset + j];
+        duR[i] += dxj * gR[offset + j];
+      }
+    }
+
+    double limitL[kMaxDim] = {1.0, 1.0, 1.0};
+    double limitR[kMaxDim] = {1.0, 1.0, 1.0};
+    if (useLimiter) {
+      for (int d = 0; d < ndim; ++d) {
+        const double du = uR[d] - uL[d];
+        const double duML = 4.0 * duL[d] - du;
+        const double duMR = 4.0 * duR[d] - du;
+        limitL[d] = van_leer(duML, du, eps);
+        limitR[d] = van_leer(duMR, du, eps);
+      }
+    }
+
+    const double pecfac = pecfac_f[e];
+    const double om_pecfac = 1.0 - pecfac;
+
+    double uIpL[kMaxDim], uIpR[kMaxDim];
+    for (int d = 0; d < ndim; ++d) {
+      uIpL[d] = uL[d] + duL[d] * hoUpwind * limitL[d] * density_upwinding_factor;
+      uIpR[d] = uR[d] - duR[d] * hoUpwind * limitR[d] * density_upwinding_factor;
+    }
+
+    double duidxj[kMaxDim][kMaxDim];
+    for (int i = 0; i < ndim; ++i) {
+      const double dui = uR[i] - uL[i];
+      const int offset = i * ndim;
+      double gjuidx = 0.0;
+      for (int j = 0; j < ndim; ++j) {
+        const double dxj = xR[j] - xL[j];
+        const double gjui = 0.5 * (gR[offset + j] + gL[offset + j]);
+        gjuidx += gjui * dxj;
+      }
+      for (int j = 0; j < ndim; ++j) {
+        const double gjui = 0.5 * (gR[offset + j] + gL[offset + j]);
+        duidxj[i][j] = gjui + (dui - gjuidx) * av[j] * inv_axdx;
+      }
+    }
+
+    const double dlhsfac = -viscIp * asq * inv_axdx;
+
+    for (int i = 0; i < ndim; ++i) {
+      const int rowL = i;
+      const int rowR = i + ndim;
+
+      const double uiIp = 0.5 * (uR[i] + uL[i]);
+      const double uiUpw = (mdot > 0.0)
+                             ? (alphaUpw * uIpL[i] + om_alphaUpw * uiIp)
+                             : (alphaUpw * uIpR[i] + om_alphaUpw * uiIp);
+      const double uiHatL = (alpha * uIpL[i] + om_alpha * uiIp);
+      const double uiHatR = (alpha * uIpR[i] + om_alpha * uiIp);
+      const double uiCds = 0.5 * (uiHatL + uiHatR);
+
+      const double adv_flux = mdot * (pecfac * uiUpw + om_pecfac * uiCds);
+
+      double diff_flux = 0.0;
+      for (int j = 0; j < ndim; ++j)
+        diff_flux += duidxj[j][j];
+      diff_flux *= 2.0 / 3.0 * viscIp * av[i] * includeDivU;
+      for (int j = 0; j < ndim; ++j)
+        diff_flux += -viscIp * (duidxj[i][j] + duidxj[j][i]) * av[j];
+
+      const double maskNode = std::fmin(node_mask[nL], node_mask[nR]);
+      const double total_flux = adv_flux + diff_flux * maskNode;
+
+      rhs[rowL] -= total_flux;
+      rhs[rowR] += total_flux;
+
+      double alhsfac = 0.5 * (mdot + std::fabs(mdot)) * pecfac * alphaUpw +
+                       0.5 * alpha * om_pecfac * mdot;
+      LHS(rowL, rowL) += alhsfac / relaxFacU;
+      LHS(rowR, rowL) -= alhsfac;
+
+      alhsfac = 0.5 * (mdot - std::fabs(mdot)) * pecfac * alphaUpw +
+                0.5 * alpha * om_pecfac * mdot;
+      LHS(rowR, rowR) -= alhsfac / relaxFacU;
+      LHS(rowL, rowR) += alhsfac;
+
+      alhsfac = 0.5 * mdot * (pecfac * om_alphaUpw + om_pecfac * om_alpha);
+      LHS(rowL, rowL) += alhsfac / relaxFacU;
+      LHS(rowL, rowR) += alhsfac;
+      LHS(rowR, rowL) -= alhsfac;
+      LHS(rowR, rowR) -= alhsfac / relaxFacU;
+
+      LHS(rowL, rowL) -= dlhsfac / relaxFacU;
+      LHS(rowL, rowR) += dlhsfac;
+      LHS(rowR, rowL) += dlhsfac;
+      LHS(rowR, rowR) -= dlhsfac / relaxFacU;
+
+      for (int j = 0; j < ndim; ++j) {
+        const double lhsfacNS = -viscIp * av[i] * av[j] * inv_axdx;
+        const int colL = j;
+        const int colR = j + ndim;
+        LHS(rowL, colL) -= lhsfacNS / relaxFacU;
+        LHS(rowL, colR) += lhsfacNS;
+        LHS(rowR, colL) += lhsfacNS;
+        LHS(rowR, colR) -= lhsfacNS / relaxFacU;
+      }
+    }
+
+    /* NGPApplyCoeff::operator(): src/SolverAlgorithm.C:132-151 */
+    if (udiag_accum) {
+      for (int i = 0; i < 2; ++i) {
+        const int ix = i * ndim;
+        udiag_accum[nodes[i]] += LHS(ix, ix);
+      }
+    }
+    sink->apply(2, nodes, rhs, lhs, n);
+#undef LHS
+  }
+}

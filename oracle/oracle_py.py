@@ -1,0 +1,310 @@
+"""ctypes binding of the CPU oracle (oracle/libedge_oracle.so).
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product
+(nalu-wind_b200/, include/) never imports this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_f64p = C.POINTER(C.c_double)
+
+
+class Peclet(C.Structure):
+    _fields_ = [("form", C.c_int), ("a", C.c_double), ("b", C.c_double)]
+
+
+class ContinuityOpts(C.Structure):
+    _fields_ = [("dt", C.c_double), ("gamma1", C.c_double),
+                ("noc_fac", C.c_double), ("interp_together", C.c_double),
+                ("solve_incompressible", C.c_double)]
+
+
+class ScalarOpts(C.Structure):
+    _fields_ = [("alpha", C.c_double), ("alpha_upw", C.c_double),
+                ("ho_upwind", C.c_double), ("relax_fac", C.c_double),
+                ("use_limiter", C.c_int), ("eps", C.c_double), ("pf", Peclet)]
+
+
+class MomentumOpts(C.Structure):
+    _fields_ = [("include_divu", C.c_double), ("alpha", C.c_double),
+                ("alpha_upw", C.c_double), ("ho_upwind", C.c_double),
+                ("relax_fac", C.c_double), ("use_limiter", C.c_int),
+                ("eps", C.c_double)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libedge_oracle.so")
+    src = [os.path.join(_HERE, f) for f in ("edge_oracle.cpp", "edge_oracle.h")]
+    stale = (not os.path.exists(so)) or any(
+        os.path.getmtime(s) > os.path.getmtime(so) for s in src)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    L = C.CDLL(build())
+    vp = C.c_void_p
+    L.orc_peclet_eval.restype = C.c_double
+    L.orc_peclet_eval.argtypes = [C.POINTER(Peclet), C.c_double]
+    L.orc_applier_dense_create.restype = vp
+    L.orc_applier_dense_create.argtypes = [C.c_int64, C.c_int]
+    L.orc_applier_dense_get.argtypes = [vp, c_f64p, c_f64p]
+    L.orc_graph_create.restype = vp
+    L.orc_graph_create.argtypes = [C.c_int, C.c_int64, C.c_int64]
+    L.orc_graph_destroy.argtypes = [vp]
+    L.orc_graph_set_skipped.argtypes = [vp, c_i64p, C.c_int64]
+    L.orc_graph_add_edges.argtypes = [vp, C.c_int64, c_i32p, c_i64p]
+    L.orc_graph_add_nodes.argtypes = [vp, C.c_int64, c_i32p, c_i64p]
+    L.orc_graph_finalize.argtypes = [vp]
+    L.orc_graph_size.restype = C.c_int64
+    L.orc_graph_size.argtypes = [vp, C.c_int]
+    L.orc_graph_copy.argtypes = [vp, C.c_int, c_i64p]
+    L.orc_applier_hypre_create.restype = vp
+    L.orc_applier_hypre_create.argtypes = [vp, c_i64p, C.c_int64, C.c_int]
+    L.orc_applier_hypre_reset.argtypes = [vp]
+    L.orc_applier_hypre_get.argtypes = [vp, c_f64p, c_f64p]
+    L.orc_applier_hypre_get_abs.argtypes = [vp, c_f64p, c_f64p]
+    L.orc_applier_hypre_enable_log.argtypes = [vp, C.c_int64]
+    L.orc_applier_hypre_get_log.argtypes = [vp, c_i64p, c_i64p]
+    L.orc_applier_destroy.argtypes = [vp]
+    L.orc_mdot_edge.argtypes = [
+        C.c_int, C.c_int64, c_i32p] + [c_f64p] * 7 + [
+        C.c_double, C.c_double, c_f64p]
+    L.orc_peclet_edge.argtypes = [
+        C.c_int, C.c_int64, c_i32p] + [c_f64p] * 4 + [
+        C.POINTER(Peclet), C.c_double, c_f64p, c_f64p]
+    L.orc_nodal_grad_edge.argtypes = [
+        C.c_int, C.c_int, C.c_int64, c_i32p] + [c_f64p] * 4
+    L.orc_continuity_edge.argtypes = [
+        C.c_int, C.c_int64, c_i32p] + [c_f64p] * 7 + [
+        C.POINTER(ContinuityOpts), vp]
+    L.orc_scalar_edge.argtypes = [
+        C.c_int, C.c_int64, c_i32p] + [c_f64p] * 8 + [
+        C.POINTER(ScalarOpts), vp]
+    L.orc_momentum_edge.argtypes = [
+        C.c_int, C.c_int64, c_i32p] + [c_f64p] * 9 + [
+        C.POINTER(MomentumOpts), vp, c_f64p]
+    _LIB = L
+    return L
+
+
+def _f(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(c_f64p)
+
+
+def _i32(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(c_i32p)
+
+
+def _i64(a):
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    return a, a.ctypes.data_as(c_i64p)
+
+
+def peclet(form="classic", a=0.0, b=1.0):
+    return Peclet(0 if form == "classic" else 1, float(a), float(b))
+
+
+class DenseSink:
+    """TestLinearSystem (unit_tests/UnitTestLinearSystem.h)."""
+
+    def __init__(self, n_nodes, num_dof):
+        self.n = n_nodes * num_dof
+        self.h = lib().orc_applier_dense_create(n_nodes, num_dof)
+
+    def get(self):
+        lhs = np.zeros((self.n, self.n))
+        rhs = np.zeros(self.n)
+        lib().orc_applier_dense_get(self.h, lhs.ctypes.data_as(c_f64p),
+                                    rhs.ctypes.data_as(c_f64p))
+        return lhs, rhs
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_applier_destroy(self.h)
+            self.h = None
+
+
+class Graph:
+    """HypreLinearSystem graph (oracle restatement)."""
+
+    def __init__(self, num_dof, i_lower, i_upper):
+        self.num_dof = num_dof
+        self.i_lower, self.i_upper = int(i_lower), int(i_upper)
+        self.h = lib().orc_graph_create(num_dof, int(i_lower), int(i_upper))
+
+    def set_skipped(self, rows):
+        r, p = _i64(rows)
+        lib().orc_graph_set_skipped(self.h, p, len(r))
+
+    def add_edges(self, edge_nodes, node_hid):
+        en, pe = _i32(edge_nodes)
+        nh, ph = _i64(node_hid)
+        lib().orc_graph_add_edges(self.h, en.size // 2, pe, ph)
+
+    def add_nodes(self, nodes, node_hid):
+        nn, pn = _i32(nodes)
+        nh, ph = _i64(node_hid)
+        lib().orc_graph_add_nodes(self.h, nn.size, pn, ph)
+
+    def finalize(self):
+        L = lib()
+        L.orc_graph_finalize(self.h)
+        sz = lambda w: int(L.orc_graph_size(self.h, w))
+        self.num_rows_owned = sz(0)
+        self.nnz_owned = sz(1)
+        self.num_rows_shared = sz(2)
+        self.nnz_shared = sz(3)
+        self.num_periodic = sz(4)
+
+        def cp(what, n):
+            out = np.zeros(n, dtype=np.int64)
+            if n:
+                L.orc_graph_copy(self.h, what, out.ctypes.data_as(c_i64p))
+            return out
+        self.row_start_owned = cp(0, self.num_rows_owned + 1)
+        self.row_start_shared = cp(1, self.num_rows_shared + 1)
+        self.cols = cp(2, self.nnz_owned + self.nnz_shared)
+        self.rows = cp(3, self.nnz_owned + self.nnz_shared)
+        self.row_indices_shared = cp(4, self.num_rows_shared)
+        self.periodic_rows = cp(5, self.num_periodic)
+        return self
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_graph_destroy(self.h)
+            self.h = None
+
+
+class HypreSink:
+    """HypreLinSysCoeffApplier / HypreUVWLinSysCoeffApplier (oracle)."""
+
+    def __init__(self, graph, node_hid, uvw_ndim=0):
+        self.graph = graph
+        self.uvw_ndim = uvw_ndim
+        nh, ph = _i64(node_hid)
+        self.h = lib().orc_applier_hypre_create(graph.h, ph, len(nh), uvw_ndim)
+        self.nrhs = uvw_ndim if uvw_ndim > 0 else 1
+        self.total_rows = graph.num_rows_owned + graph.num_rows_shared
+        self.nnz = graph.nnz_owned + graph.nnz_shared
+        self._log_calls = 0
+
+    def reset(self):
+        lib().orc_applier_hypre_reset(self.h)
+
+    def enable_log(self, n_calls):
+        self._log_calls = n_calls
+        lib().orc_applier_hypre_enable_log(self.h, n_calls)
+
+    def get_log(self):
+        n = 2 if self.uvw_ndim > 0 else 2 * self.graph.num_dof
+        slots = np.zeros((self._log_calls, n, n), dtype=np.int64)
+        ridx = np.zeros((self._log_calls, n), dtype=np.int64)
+        lib().orc_applier_hypre_get_log(
+            self.h, slots.ctypes.data_as(c_i64p), ridx.ctypes.data_as(c_i64p))
+        return slots, ridx
+
+    def _get(self, fn):
+        vals = np.zeros(self.nnz)
+        rhs = np.zeros((self.nrhs, self.total_rows))  # column-major (row, d)
+        fn(self.h, vals.ctypes.data_as(c_f64p), rhs.ctypes.data_as(c_f64p))
+        return vals, rhs
+
+    def get(self):
+        return self._get(lib().orc_applier_hypre_get)
+
+    def get_abs(self):
+        return self._get(lib().orc_applier_hypre_get_abs)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_applier_destroy(self.h)
+            self.h = None
+
+
+def mdot_edge(ndim, edge_nodes, coords, vel, gpdx, rho, p, udiag, area,
+              noc_fac=1.0, interp_together=1.0):
+    en, pe = _i32(edge_nodes)
+    ne = en.size // 2
+    arrs = [_f(x) for x in (coords, vel, gpdx, rho, p, udiag, area)]
+    out = np.zeros(ne)
+    lib().orc_mdot_edge(ndim, ne, pe, *[a[1] for a in arrs],
+                        float(noc_fac), float(interp_together),
+                        out.ctypes.data_as(c_f64p))
+    return out
+
+
+def peclet_edge(ndim, edge_nodes, coords, vrtm, rho, visc, pf, eps=1e-16):
+    en, pe = _i32(edge_nodes)
+    ne = en.size // 2
+    arrs = [_f(x) for x in (coords, vrtm, rho, visc)]
+    pn = np.zeros(ne)
+    pfac = np.zeros(ne)
+    lib().orc_peclet_edge(ndim, ne, pe, *[a[1] for a in arrs], C.byref(pf),
+                          float(eps), pn.ctypes.data_as(c_f64p),
+                          pfac.ctypes.data_as(c_f64p))
+    return pn, pfac
+
+
+def nodal_grad_edge(dim1, dim2, edge_nodes, phi, area, dual_vol, n_nodes):
+    en, pe = _i32(edge_nodes)
+    ne = en.size // 2
+    arrs = [_f(x) for x in (phi, area, dual_vol)]
+    grad = np.zeros((n_nodes, dim1 * dim2))
+    lib().orc_nodal_grad_edge(dim1, dim2, ne, pe, *[a[1] for a in arrs],
+                              grad.ctypes.data_as(c_f64p))
+    return grad
+
+
+def continuity_edge(ndim, edge_nodes, coords, vel, gpdx, rho, p, udiag, area,
+                    sink, dt=1.0, gamma1=1.0, noc_fac=1.0,
+                    interp_together=1.0, solve_incompressible=0.0):
+    en, pe = _i32(edge_nodes)
+    arrs = [_f(x) for x in (coords, vel, gpdx, rho, p, udiag, area)]
+    o = ContinuityOpts(dt, gamma1, noc_fac, interp_together,
+                       solve_incompressible)
+    lib().orc_continuity_edge(ndim, en.size // 2, pe, *[a[1] for a in arrs],
+                              C.byref(o), sink.h)
+
+
+def scalar_edge(ndim, edge_nodes, coords, vrtm, q, dqdx, rho, dflux, area,
+                mdot, sink, alpha=0.0, alpha_upw=1.0, ho_upwind=1.0,
+                relax_fac=1.0, use_limiter=False, eps=1e-16, pf=None):
+    en, pe = _i32(edge_nodes)
+    arrs = [_f(x) for x in (coords, vrtm, q, dqdx, rho, dflux, area, mdot)]
+    o = ScalarOpts(alpha, alpha_upw, ho_upwind, relax_fac,
+                   1 if use_limiter else 0, eps, pf or peclet())
+    lib().orc_scalar_edge(ndim, en.size // 2, pe, *[a[1] for a in arrs],
+                          C.byref(o), sink.h)
+
+
+def momentum_edge(ndim, edge_nodes, coords, vel, dudx, visc, rho, mask, area,
+                  mdot, pecfac, sink, include_divu=0.0, alpha=0.0,
+                  alpha_upw=1.0, ho_upwind=1.0, relax_fac=1.0,
+                  use_limiter=False, eps=1e-16, udiag_accum=None):
+    en, pe = _i32(edge_nodes)
+    arrs = [_f(x) for x in (coords, vel, dudx, visc, rho, mask, area, mdot,
+                            pecfac)]
+    o = MomentumOpts(include_divu, alpha, alpha_upw, ho_upwind, relax_fac,
+                     1 if use_limiter else 0, eps)
+    ud = None
+    if udiag_accum is not None:
+        assert udiag_accum.dtype == np.float64 and udiag_accum.flags.c_contiguous
+        ud = udiag_accum.ctypes.data_as(c_f64p)
+    lib().orc_momentum_edge(ndim, en.size // 2, pe, *[a[1] for a in arrs],
+                            C.byref(o), sink.h, ud)
