@@ -1,0 +1,371 @@
+/*
+ * nalu_edge_b200.h -- C ABI of the B200-native edge-based CVFEM assembly path.
+ *
+ * Drop-in boundary for the hot path of Exawind/nalu-wind (citations relative to
+ * the nalu-wind source tree): the edge algorithms
+ *   MdotEdgeAlg, NodalGradEdgeAlg, MomentumEdgePecletAlg,
+ *   ContinuityEdgeSolverAlg, ScalarEdgeSolverAlg, MomentumEdgeSolverAlg
+ * and the LinearSystem / CoeffApplier assembly surface of HypreLinearSystem and
+ * HypreUVWLinearSystem.  Plain C, opaque handles, plain pointers and sizes; no
+ * C++/torch types.  The C++ shim classes that keep the reference's names live
+ * in nalu-wind_b200/host/ and call only this header.
+ *
+ * Conventions
+ *  - every function returns nw_status (0 == NW_OK); nw_last_error() gives the
+ *    message of the last failure on the calling thread (the reference throws
+ *    std::runtime_error / STK_ThrowRequire on the host and never reports device
+ *    errors; here host-side misuse is an error code, never a silent fallback).
+ *  - there is NO CPU fallback: every compute entry point fails with
+ *    NW_ERR_CUDA if no CUDA device is usable.
+ *  - host arrays use the reference's field layout: entity-major,
+ *    component-minor (f[entity*ncomp + comp]); nodes are indexed by the
+ *    caller's local node index (0..n_nodes), edges by the caller's edge order
+ *    (the order of the STK edge buckets the reference loops over).
+ *  - one CUDA stream per context; calls are asynchronous on that stream unless
+ *    they return data to the host.  No host-side concurrency on one context
+ *    (same rule as the reference's LinearSystem).
+ */
+#ifndef NALU_EDGE_B200_H
+#define NALU_EDGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  NW_OK = 0,
+  NW_ERR_ARG = 1,   /* bad argument / inconsistent sizes */
+  NW_ERR_CUDA = 2,  /* CUDA runtime failure or no device */
+  NW_ERR_STATE = 3, /* call out of order (e.g. assemble before finalize) */
+  NW_ERR_COMM = 4,  /* NCCL failure / communicator missing */
+  NW_ERR_LIMIT = 5  /* a plan limit was exceeded */
+} nw_status;
+
+typedef struct nw_ctx nw_ctx;       /* device + stream + communicator */
+typedef struct nw_mesh nw_mesh;     /* one rank's mesh partition + fields */
+typedef struct nw_linsys nw_linsys; /* LinearSystem: graph + values */
+
+const char* nw_last_error(void);
+/* library / ABI version: major*1000 + minor */
+int nw_version(void);
+
+/* ------------------------------------------------------------------ */
+/* context                                                             */
+/* ------------------------------------------------------------------ */
+
+/* replaces Kokkos::initialize + hypre_initialize for this path (nalu.C:83-86) */
+int nw_ctx_create(int cuda_device, nw_ctx** out);
+int nw_ctx_destroy(nw_ctx* ctx);
+/* fence: Kokkos::fence() equivalent on the context's stream */
+int nw_ctx_sync(nw_ctx* ctx);
+/* cudaStream_t of the context (as void*) so callers can order their own work */
+void* nw_ctx_stream(nw_ctx* ctx);
+
+/* Multi-GPU: one process per GPU.  The communicator replaces the MPI
+ * communicator STK/hypre use (stk::mesh::parallel_sum,
+ * HYPRE_IJMatrixAssemble).  unique_id is the 128-byte ncclUniqueId, produced
+ * on rank 0 by nw_comm_unique_id and distributed by the caller (MPI_Bcast,
+ * torch.distributed, a file ...). */
+#define NW_UNIQUE_ID_BYTES 128
+int nw_comm_unique_id(void* unique_id_out);
+int nw_ctx_comm_init(nw_ctx* ctx, const void* unique_id, int nranks, int rank);
+
+/* ------------------------------------------------------------------ */
+/* mesh partition                                                      */
+/* ------------------------------------------------------------------ */
+
+typedef struct {
+  int32_t ndim;   /* 2 or 3 (meta.spatial_dimension()) */
+  int32_t rank;   /* bulk.parallel_rank() */
+  int32_t nranks; /* bulk.parallel_size() */
+  int64_t n_nodes; /* local nodes: owned + shared (+ periodic slaves) */
+  int64_t n_edges; /* locally-owned edges: the selector of
+                      AssembleEdgeSolverAlgorithm.h:56-58 */
+  /* [2*n_edges] (nodeL, nodeR) local node indices, in the reference's edge
+   * order and orientation (STK: nodes of an edge in ascending global id) */
+  const int32_t* edge_nodes;
+  /* [n_nodes] Realm::hypreGlobalId_ with periodic slaves already carrying the
+   * master's id (HypreLinearSystem::get_entity_hypre_id,
+   * src/HypreLinearSystem.C:2460-2470) */
+  const int64_t* node_hypre_id;
+  /* [n_nodes] the node's own row id before periodic resolution (only differs
+   * from node_hypre_id for periodic slaves); NULL == same as node_hypre_id */
+  const int64_t* node_own_hypre_id;
+  /* [nranks+1] Realm::hypreOffsets_ (src/Realm.C:3620-3626): rank r owns rows
+   * [offsets[r], offsets[r+1]) */
+  const int64_t* hypre_offsets;
+  /* [n_nodes*ndim] coordinates; used for the locality tiling and registered
+   * as the nodal field "coordinates" */
+  const double* coords;
+  /* target nodes per tile; 0 = library default */
+  int32_t tile_nodes;
+} nw_mesh_desc;
+
+int nw_mesh_create(nw_ctx* ctx, const nw_mesh_desc* desc, nw_mesh** out);
+int nw_mesh_destroy(nw_mesh* mesh);
+
+typedef struct {
+  int64_t n_nodes, n_edges;
+  int64_t n_tiles;
+  int64_t n_tile_edges;     /* edges incl. the copies cut edges get per tile */
+  int64_t n_halo_nodes;     /* sum over tiles of staged non-owned nodes */
+  int64_t max_tile_nodes, max_tile_staged, max_tile_edges, max_tile_halfedges;
+  int64_t plan_bytes_device; /* integer plan arrays resident in HBM */
+} nw_mesh_stats;
+int nw_mesh_get_stats(const nw_mesh* mesh, nw_mesh_stats* out);
+
+/* ---- fields (replaces the stk::mesh::NgpField the lambdas capture) ---- */
+
+typedef enum { NW_NODE = 0, NW_EDGE = 1 } nw_entity_rank;
+
+/* Registers (or finds) a field by the reference's field name, e.g.
+ * "velocity", "pressure", "density", "dpdx", "dudx", "momentum_diag",
+ * "viscosity", "dual_nodal_volume", "edge_area_vector", "mass_flow_rate",
+ * "peclet_factor", "abl_wall_no_slip_wall_func_node_mask", "turbulent_ke" ...
+ * Storage is zero-initialised. */
+int nw_field_register(
+  nw_mesh* mesh, const char* name, int entity_rank, int ncomp, int* field_id);
+int nw_field_find(const nw_mesh* mesh, const char* name, int* field_id);
+/* host (pageable or pinned) -> device, reference layout; asynchronous on the
+ * context stream when the host buffer is pinned */
+int nw_field_upload(nw_mesh* mesh, int field_id, const double* host);
+/* device -> host, reference layout; synchronises the stream */
+int nw_field_download(nw_mesh* mesh, int field_id, double* host);
+/* fill every component with a constant (stk::mesh::field_fill) */
+int nw_field_fill(nw_mesh* mesh, int field_id, double value);
+/* Device view of the internal storage: component c of internal entity i is at
+ * base[c*stride + i]; internal numbering via nw_mesh_get_node_permutation. */
+int nw_field_device_view(
+  nw_mesh* mesh, int field_id, double** base, int64_t* stride);
+/* perm[i] = caller's local node index of internal slot i, or -1 for a padding
+ * slot; n_slots >= n_nodes */
+int nw_mesh_get_node_permutation(
+  const nw_mesh* mesh, int64_t* n_slots, int32_t* perm /* may be NULL */);
+
+
+/* ---- shared-node exchange lists (multi-rank) ----
+ * A node is identified across ranks by its own hypre row id.  With a
+ * communicator attached (nw_ctx_comm_init before nw_mesh_create) the lists are
+ * exchanged automatically; otherwise the caller moves them with its own
+ * transport: for every peer, get_send on the sharer -> set_recv on the owner,
+ * then commit on every rank.  Replaces the STK comm lists behind
+ * stk::mesh::parallel_sum / copy_owned_to_shared. */
+int nw_mesh_halo_send_count(const nw_mesh* mesh, int peer, int64_t* n);
+int nw_mesh_halo_get_send(const nw_mesh* mesh, int peer, int64_t* own_hids);
+int nw_mesh_halo_set_recv(
+  nw_mesh* mesh, int peer, int64_t n, const int64_t* own_hids);
+int nw_mesh_halo_commit(nw_mesh* mesh);
+/* stk::mesh::parallel_sum(bulk, {field}) for a nodal field: every sharer ends
+ * with the sum over all ranks' copies (owner adds in ascending rank order,
+ * then owner -> sharers).  Single rank: no-op. */
+int nw_field_parallel_sum(nw_mesh* mesh, int field_id);
+
+/* ------------------------------------------------------------------ */
+/* edge algorithms without a linear system                             */
+/* ------------------------------------------------------------------ */
+
+typedef enum { NW_PECLET_CLASSIC = 0, NW_PECLET_TANH = 1 } nw_peclet_form;
+typedef struct {
+  int32_t form; /* nw_peclet_form (EquationSystem::ngp_create_peclet_function,
+                   include/EquationSystem.h:399-417) */
+  double a;     /* classic: hybrid factor; tanh: transition c1 */
+  double b;     /* classic: unused;        tanh: width c2 */
+} nw_peclet_fn;
+
+typedef struct {
+  double noc_fac;         /* realm.get_noc_usage("pressure") ? 1 : 0 */
+  double interp_together; /* realm.get_mdot_interp() */
+} nw_mdot_opts;
+/* MdotEdgeAlg::execute (src/ngp_algorithms/MdotEdgeAlg.C:43-194); reads
+ * coordinates, velocity, dpdx, density, pressure, momentum_diag,
+ * edge_area_vector; writes the edge field mass_flow_rate. */
+int nw_mdot_edge(nw_mesh* mesh, const nw_mdot_opts* opts);
+
+typedef struct {
+  nw_peclet_fn pf;
+  double eps; /* MomentumEdgePecletAlg::eps_ = 1e-16 */
+} nw_peclet_opts;
+/* MomentumEdgePecletAlg::execute (src/edge_kernels/MomentumEdgePecletAlg.C:49-102);
+ * reads coordinates, velocity, density, viscosity_field; writes peclet_factor. */
+int nw_peclet_edge(
+  nw_mesh* mesh, int viscosity_field, const nw_peclet_opts* opts);
+
+/* NodalGradAlgDriver::execute for the interior edge algorithm
+ * (src/ngp_algorithms/NodalGradAlgDriver.C:30-72 +
+ *  NodalGradEdgeAlg.C:58-111): grad = 0; grad += edge contributions; then the
+ * shared-node sum over ranks (stk::mesh::parallel_sum) when a communicator is
+ * attached.  phi has dim1 components (1 or ndim), grad dim1*ndim. */
+int nw_nodal_grad_edge(nw_mesh* mesh, int phi_field, int grad_field);
+
+/* ------------------------------------------------------------------ */
+/* linear system (LinearSystem / HypreLinearSystem / HypreUVWLinearSystem) */
+/* ------------------------------------------------------------------ */
+
+typedef enum {
+  NW_LINSYS_HYPRE = 0,    /* HypreLinearSystem, numDof rows per node */
+  NW_LINSYS_HYPRE_UVW = 1 /* HypreUVWLinearSystem: scalar graph, ndim RHS */
+} nw_linsys_kind;
+
+/* LinearSystem::create (src/LinearSystem.C:117-159) */
+int nw_linsys_create(
+  nw_mesh* mesh, int kind, int num_dof, nw_linsys** out);
+int nw_linsys_destroy(nw_linsys* ls);
+/* skippedRows_ (Dirichlet rows, global row ids); call before finalize */
+int nw_linsys_set_skipped_rows(nw_linsys* ls, const int64_t* rows, int64_t n);
+/* LinearSystem::buildEdgeToNodeGraph (src/HypreLinearSystem.C:412-478) over
+ * the mesh's owned edges */
+int nw_linsys_build_edge_to_node_graph(nw_linsys* ls);
+/* LinearSystem::finalizeLinearSystem (src/HypreLinearSystem.C:819-880): CSR
+ * arrays, edge->slot map, device plans */
+int nw_linsys_finalize(nw_linsys* ls);
+
+typedef struct {
+  int64_t i_lower, i_upper; /* inclusive owned row range (iLower_, iUpper_) */
+  int64_t num_rows_owned, num_nonzeros_owned;
+  int64_t num_rows_shared, num_nonzeros_shared;
+  int64_t num_periodic_rows; /* periodic_bc_rows_owned_ */
+  int32_t num_rhs;           /* columns of rhs_dev_: 1, or ndim for UVW */
+  int32_t block;             /* rows (== cols) of the per-edge block: 2*numDof
+                                (UVW: 2) */
+} nw_linsys_sizes;
+int nw_linsys_get_sizes(const nw_linsys* ls, nw_linsys_sizes* out);
+
+/* Integer structures for bit-exact comparison with the reference
+ * (src/HypreLinearSystem.C:999-1236, 883-993).  Any output may be NULL. */
+int nw_linsys_get_graph(
+  const nw_linsys* ls,
+  int64_t* mat_row_start_owned,  /* [num_rows_owned+1] */
+  int64_t* mat_row_start_shared, /* [num_rows_shared+1] */
+  int64_t* cols,                 /* [nnz_owned+nnz_shared] cols_host_ */
+  int64_t* rows,                 /* [nnz_owned+nnz_shared] rows_host_ */
+  int64_t* row_indices_shared,   /* [num_rows_shared] ascending */
+  int64_t* periodic_rows_owned); /* [num_periodic_rows] */
+/* edge -> CSR slot map: for edge e (caller's order) and local block entry
+ * (ii,kk), slots[(e*block + ii)*block + kk] is the index into the value array
+ * that HypreLinSysCoeffApplier::sum_into{,_1DoF} / the UVW applier would add
+ * lhs(ii,kk) to (after its sort + column walk), or -1 when that row is
+ * skipped / absent.  rhs_rows[e*block + ii] is the row of rhs_dev_. */
+int nw_linsys_get_edge_slots(
+  const nw_linsys* ls, int64_t* slots, int64_t* rhs_rows);
+
+/* LinearSystem::zeroSystem + resetCoeffApplierData
+ * (src/HypreLinearSystem.C:1892-1933, 1386-1430): values = 0, rhs = 0,
+ * periodic-slave rows diag 1 / rhs 0. */
+int nw_linsys_zero(nw_linsys* ls);
+
+typedef enum {
+  NW_SCATTER_SEGMENTED = 0, /* default: deterministic tile kernel, row-sorted
+                               segmented warp-shuffle reduction, no atomics */
+  NW_SCATTER_ATOMIC = 1     /* warp-aggregated fp64 atomicAdd variant */
+} nw_scatter_mode;
+int nw_linsys_set_scatter_mode(nw_linsys* ls, int mode);
+
+typedef struct {
+  double dt, gamma1;           /* tauScale = dt / gamma1 */
+  double noc_fac;              /* get_noc_usage("pressure") */
+  double interp_together;      /* get_mdot_interp() */
+  double solve_incompressible; /* get_incompressible_solve() */
+} nw_continuity_opts;
+/* ContinuityEdgeSolverAlg::execute incl. the CoeffApplier scatter
+ * (src/edge_kernels/ContinuityEdgeSolverAlg.C:37-195). */
+int nw_assemble_continuity_edge(nw_linsys* ls, const nw_continuity_opts* opts);
+
+typedef struct {
+  double alpha, alpha_upw, ho_upwind, relax_fac;
+  int32_t use_limiter;
+  double eps; /* 1e-16 */
+  nw_peclet_fn pf;
+} nw_scalar_opts;
+/* ScalarEdgeSolverAlg::execute (src/edge_kernels/ScalarEdgeSolverAlg.C:55-206)
+ * for scalar q with gradient dqdx and diffusive-flux coefficient field. */
+int nw_assemble_scalar_edge(
+  nw_linsys* ls,
+  int q_field,
+  int dqdx_field,
+  int diff_flux_coeff_field,
+  const nw_scalar_opts* opts);
+
+typedef struct {
+  double include_divu, alpha, alpha_upw, ho_upwind, relax_fac;
+  int32_t use_limiter;
+  double eps; /* 1e-16 */
+  /* fuse MomentumEdgePecletAlg into the kernel instead of reading the
+   * peclet_factor edge field; pf/pec_eps only used then */
+  int32_t fuse_peclet;
+  nw_peclet_fn pf;
+  double pec_eps;
+  /* NGPApplyCoeff::extract_diagonal (src/SolverAlgorithm.C:87-105): nodal
+   * field that accumulates lhs(i*ndim, i*ndim) of both end nodes, or -1 */
+  int32_t diag_field;
+} nw_momentum_opts;
+/* MomentumEdgeSolverAlg::execute (src/edge_kernels/MomentumEdgeSolverAlg.C:70-313)
+ * into a NW_LINSYS_HYPRE_UVW system (x-x entries + ndim RHS,
+ * src/HypreUVWLinearSystem.C:695-767) or a monolithic NW_LINSYS_HYPRE system
+ * with num_dof == ndim (src/HypreLinearSystem.C:2059-2161). */
+int nw_assemble_momentum_edge(
+  nw_linsys* ls, int viscosity_field, const nw_momentum_opts* opts);
+
+/* Generic CoeffApplier entry (include/LinearSystem.h:62-70) for callers that
+ * computed their own per-entity blocks on the device: n_entities entities of
+ * nodes_per_entity nodes (local node indices, device pointer), lhs
+ * [n_entities][n][n] row-major and rhs [n_entities][n] with
+ * n = nodes_per_entity*numDof (device pointers).  Uses fp64 atomics. */
+int nw_linsys_sum_into(
+  nw_linsys* ls,
+  int64_t n_entities,
+  int nodes_per_entity,
+  const int32_t* d_entity_nodes,
+  const double* d_lhs,
+  const double* d_rhs);
+
+
+/* ---- shared-row exchange structure (multi-rank) ----
+ * The rows of the shared tail destined to one owner form one contiguous
+ * segment (rows ascending, ranks own contiguous row ranges), sent in place.
+ * With a communicator the structure is exchanged inside nw_linsys_finalize;
+ * otherwise: send_info / get_send on the sender -> set_recv on the owner ->
+ * commit on every rank.  Received (row, col) pairs that the owner's local
+ * graph does not contain (the edge lives on the sender) get one slot each in a
+ * COO extension behind the reference-layout arrays: values[nnz_owned +
+ * nnz_shared + x], rows/cols from nw_linsys_get_extra -- the hand-off to
+ * HYPRE_IJMatrixAddToValues2 then needs no off-rank rows at all. */
+int nw_linsys_halo_send_info(
+  const nw_linsys* ls, int peer, int64_t* n_rows, int64_t* n_vals);
+int nw_linsys_halo_get_send(
+  const nw_linsys* ls, int peer, int64_t* rows, int64_t* row_lens,
+  int64_t* cols);
+int nw_linsys_halo_set_recv(
+  nw_linsys* ls, int peer, int64_t n_rows, const int64_t* rows,
+  const int64_t* row_lens, const int64_t* cols);
+int nw_linsys_halo_commit(nw_linsys* ls);
+/* destination of every received value / rhs entry (bit-exact halo lists) */
+int nw_linsys_halo_get_recv_slots(
+  const nw_linsys* ls, int peer, int64_t* n_vals, int64_t* val_slots,
+  int64_t* n_rows, int64_t* rhs_rows);
+int nw_linsys_get_extra(
+  const nw_linsys* ls, int64_t* n_extra, int64_t* rows, int64_t* cols);
+
+/* LinearSystem::loadComplete (src/HypreLinearSystem.C:1848-1889): the
+ * shared-row halo sum.  Single rank: no-op. */
+int nw_linsys_load_complete(nw_linsys* ls);
+
+/* Device pointers in exactly the layout the reference hands to
+ * HYPRE_IJMatrixSetValues2 / AddToValues2 and HYPRE_IJVectorSetValues
+ * (src/HypreLinearSystem.C:1572-1590, 1665-1673): values[nnz_owned+nnz_shared],
+ * rhs column-major [(rows_owned+rows_shared) x num_rhs]. */
+int nw_linsys_device_arrays(
+  nw_linsys* ls, double** values, double** rhs, int64_t* rhs_stride);
+/* copy to host; either may be NULL; synchronises */
+int nw_linsys_get_values(nw_linsys* ls, double* values, double* rhs);
+/* sum of squares of the owned part of every rhs column (device reduction,
+ * deterministic); feeds the nonlinear residual norm
+ * (src/HypreLinearSystem.C:2534, 2611-2638).  out[num_rhs]. */
+int nw_linsys_rhs_norm2(nw_linsys* ls, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

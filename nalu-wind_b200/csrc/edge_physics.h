@@ -1,0 +1,463 @@
+/*
+ * edge_physics.h -- per-edge arithmetic of the nalu-wind edge kernels, written
+ * for registers: every function takes the two end-node states by value-struct
+ * and returns the compact per-edge result the row reduction needs.
+ *
+ * Operation order follows the reference lambdas so that results agree with the
+ * reference to rounding (tolerance 1e-12 relative, see tests/):
+ *   continuity_edge / mdot_edge : src/edge_kernels/ContinuityEdgeSolverAlg.C:109-194,
+ *                                 src/ngp_algorithms/MdotEdgeAlg.C:117-190
+ *   scalar_edge                 : src/edge_kernels/ScalarEdgeSolverAlg.C:85-205
+ *   momentum_edge               : src/edge_kernels/MomentumEdgeSolverAlg.C:105-312
+ *   peclet_edge                 : src/edge_kernels/MomentumEdgePecletAlg.C:74-101
+ *   peclet_eval                 : src/PecletFunction.C:41-45, 68-71
+ *   van_leer                    : include/edge_kernels/EdgeKernelUtils.h:18-24
+ *
+ * NW_HD is __host__ __device__ under nvcc and empty under g++ (the plan
+ * emulator used by the CPU test-suite compiles this header with g++).
+ */
+#ifndef NW_EDGE_PHYSICS_H
+#define NW_EDGE_PHYSICS_H
+
+#include <math.h>
+
+#include "nw_types.h"
+
+#if defined(__CUDACC__)
+#define NW_HD __host__ __device__ __forceinline__
+#else
+#define NW_HD inline
+#endif
+
+namespace nw {
+
+NW_HD double
+peclet_eval(const nw_peclet_fn& f, double pecnum)
+{
+  if (f.form == NW_PECLET_CLASSIC) {
+    const double modPeclet = f.a * pecnum;
+    return modPeclet * modPeclet / (5.0 + modPeclet * modPeclet);
+  }
+  return 0.50 * (1.0 + tanh((pecnum - f.a) / f.b));
+}
+
+NW_HD double
+van_leer(double dqm, double dqp, double eps)
+{
+  return (2.0 * (dqm * dqp + fabs(dqm * dqp))) /
+         ((dqm + dqp) * (dqm + dqp) + eps);
+}
+
+/* ---- node state bundles (what each kernel stages per node) ---- */
+
+template <int ND>
+struct ContNode /* continuity + mdot: 3*ND + 3 doubles */
+{
+  double x[ND], u[ND], g[ND], rho, p, ud;
+};
+static const int kContNodeComps3 = 12;
+
+template <int ND>
+struct ScalNode /* scalar: 3*ND + 3 doubles */
+{
+  double x[ND], v[ND], dq[ND], q, rho, mu;
+};
+
+template <int ND>
+struct MomNode /* momentum: 2*ND + ND*ND + 3 doubles */
+{
+  double x[ND], u[ND], g[ND * ND], mu, rho, mask;
+};
+
+template <int ND>
+struct PecNode
+{
+  double x[ND], v[ND], rho, mu;
+};
+
+/* ---- mdot / continuity ---- */
+
+template <int ND>
+struct MdotCore
+{
+  double tmdot;         /* un-scaled edge mass flow rate (MdotEdgeAlg) */
+  double asq_inv_axdx;  /* asq * inv_axdx */
+  double projTimeScale;
+  double rhoIp;
+};
+
+template <int ND>
+NW_HD MdotCore<ND>
+mdot_core(
+  const ContNode<ND>& L,
+  const ContNode<ND>& R,
+  const double* av,
+  double nocFac,
+  double interpTogether)
+{
+  const double om_interpTogether = 1.0 - interpTogether;
+  MdotCore<ND> r;
+  r.projTimeScale = 0.5 * (1.0 / L.ud + 1.0 / R.ud);
+  r.rhoIp = 0.5 * (L.rho + R.rho);
+  double axdx = 0.0, asq = 0.0;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const double dxj = R.x[d] - L.x[d];
+    asq += av[d] * av[d];
+    axdx += av[d] * dxj;
+  }
+  const double inv_axdx = 1.0 / axdx;
+  double tmdot = -r.projTimeScale * (R.p - L.p) * asq * inv_axdx;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const double dxj = R.x[d] - L.x[d];
+    const double kxj = av[d] - asq * inv_axdx * dxj;
+    const double rhoUjIp = 0.5 * (R.rho * R.u[d] + L.rho * L.u[d]);
+    const double ujIp = 0.5 * (R.u[d] + L.u[d]);
+    const double GjIp = 0.5 * (R.g[d] / R.ud + L.g[d] / L.ud);
+    tmdot += (interpTogether * rhoUjIp + om_interpTogether * r.rhoIp * ujIp +
+              GjIp) *
+               av[d] -
+             kxj * GjIp * nocFac;
+  }
+  r.tmdot = tmdot;
+  r.asq_inv_axdx = asq * inv_axdx;
+  return r;
+}
+
+/* result: res[0] = lhsfac, res[1] = tmdot (scaled).
+ * lhs = [[-f, +f], [+f, -f]], rhs = [-m, +m]. */
+template <int ND>
+NW_HD void
+continuity_edge(
+  const ContNode<ND>& L,
+  const ContNode<ND>& R,
+  const double* av,
+  const nw_continuity_opts& o,
+  double& lhsfac,
+  double& tmdot_out)
+{
+  const double tauScale = o.dt / o.gamma1;
+  const double solveInc = o.solve_incompressible;
+  const double om_solveInc = 1.0 - solveInc;
+  MdotCore<ND> c = mdot_core<ND>(L, R, av, o.noc_fac, o.interp_together);
+  const double denScale = (1.0 / c.rhoIp) * solveInc + om_solveInc;
+  double tmdot = c.tmdot;
+  tmdot /= tauScale;
+  tmdot *= denScale;
+  /* -asq * inv_axdx * projTimeScale * denScale / tauScale, left to right */
+  lhsfac = -c.asq_inv_axdx * c.projTimeScale * denScale / tauScale;
+  tmdot_out = tmdot;
+}
+
+/* ---- Peclet factor ---- */
+
+template <int ND>
+NW_HD double
+peclet_number(const PecNode<ND>& L, const PecNode<ND>& R, double eps)
+{
+  double udotx = 0.0;
+  const double diffIp = 0.5 * (L.mu / L.rho + R.mu / R.rho);
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const double dxj = R.x[d] - L.x[d];
+    udotx += 0.5 * dxj * (R.v[d] + L.v[d]);
+  }
+  return fabs(udotx) / (diffIp + eps);
+}
+
+/* ---- scalar ---- */
+
+/* result: a[4] = lhs(0,0),lhs(0,1),lhs(1,0),lhs(1,1); flux: rhs = [-flux,+flux] */
+template <int ND>
+NW_HD void
+scalar_edge(
+  const ScalNode<ND>& L,
+  const ScalNode<ND>& R,
+  const double* av,
+  double mdot,
+  const nw_scalar_opts& o,
+  double* a,
+  double& flux)
+{
+  const double eps = o.eps;
+  const double alpha = o.alpha;
+  const double alphaUpw = o.alpha_upw;
+  const double hoUpwind = o.ho_upwind;
+  const double relaxFac = o.relax_fac;
+  const double om_alpha = 1.0 - alpha;
+  const double om_alphaUpw = 1.0 - alphaUpw;
+
+  const double viscIp = 0.5 * (L.mu + R.mu);
+  const double diffIp = 0.5 * (L.mu / L.rho + R.mu / R.rho);
+
+  double axdx = 0.0, asq = 0.0, udotx = 0.0;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const double dxj = R.x[d] - L.x[d];
+    asq += av[d] * av[d];
+    axdx += av[d] * dxj;
+    udotx += 0.5 * dxj * (R.v[d] + L.v[d]);
+  }
+  const double inv_axdx = 1.0 / axdx;
+
+  double dqL = 0.0, dqR = 0.0, nonOrth = 0.0;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const double dxj = R.x[d] - L.x[d];
+    dqL += 0.5 * dxj * L.dq[d];
+    dqR += 0.5 * dxj * R.dq[d];
+    const double kxj = av[d] - asq * inv_axdx * dxj;
+    nonOrth += -viscIp * kxj * 0.5 * (R.dq[d] + L.dq[d]);
+  }
+
+  const double pecnum = fabs(udotx) / (diffIp + eps);
+  const double pecfac = peclet_eval(o.pf, pecnum);
+  const double om_pecfac = 1.0 - pecfac;
+
+  double limitL = 1.0, limitR = 1.0;
+  if (o.use_limiter) {
+    const double dq = R.q - L.q;
+    const double dqML = 4.0 * dqL - dq;
+    const double dqMR = 4.0 * dqR - dq;
+    limitL = van_leer(dqML, dq, eps);
+    limitR = van_leer(dqMR, dq, eps);
+  }
+
+  const double qIpL = L.q + dqL * hoUpwind * limitL;
+  const double qIpR = R.q - dqR * hoUpwind * limitR;
+
+  const double lhsfac = -viscIp * asq * inv_axdx;
+  const double diffFlux = lhsfac * (R.q - L.q) + nonOrth;
+
+  double a00 = -lhsfac / relaxFac;
+  double a01 = lhsfac;
+  double a10 = lhsfac;
+  double a11 = -lhsfac / relaxFac;
+
+  const double qIp = 0.5 * (R.q + L.q);
+  const double qUpw = (mdot > 0) ? (alphaUpw * qIpL + om_alphaUpw * qIp)
+                                 : (alphaUpw * qIpR + om_alphaUpw * qIp);
+  const double qHatL = (alpha * qIpL + om_alpha * qIp);
+  const double qHatR = (alpha * qIpR + om_alpha * qIp);
+  const double qCds = 0.5 * (qHatL + qHatR);
+  const double adv_flux = mdot * (pecfac * qUpw + om_pecfac * qCds);
+
+  /* rhs(0) = -diffFlux - adv_flux, rhs(1) = diffFlux + adv_flux; negation is
+   * exact, so one number carries both. */
+  flux = diffFlux + adv_flux;
+
+  double alhsfac = 0.5 * (mdot + fabs(mdot)) * pecfac * alphaUpw +
+                   0.5 * alpha * om_pecfac * mdot;
+  a00 += alhsfac / relaxFac;
+  a10 -= alhsfac;
+
+  alhsfac = 0.5 * (mdot - fabs(mdot)) * pecfac * alphaUpw +
+            0.5 * alpha * om_pecfac * mdot;
+  a11 -= alhsfac / relaxFac;
+  a01 += alhsfac;
+
+  alhsfac = 0.5 * mdot * (pecfac * om_alphaUpw + om_pecfac * om_alpha);
+  a00 += alhsfac / relaxFac;
+  a01 += alhsfac;
+  a10 -= alhsfac;
+  a11 -= alhsfac / relaxFac;
+
+  a[0] = a00;
+  a[1] = a01;
+  a[2] = a10;
+  a[3] = a11;
+}
+
+/* ---- momentum ---- */
+
+/* Per-edge momentum result.  The 2ND x 2ND block the reference builds is
+ *   lhs(rowL(i), colL(j)) = d_ij * sLL - NS_ij / relax
+ *   lhs(rowL(i), colR(j)) = d_ij * sLR + NS_ij
+ *   lhs(rowR(i), colL(j)) = d_ij * sRL + NS_ij
+ *   lhs(rowR(i), colR(j)) = d_ij * sRR - NS_ij / relax
+ * with NS_ij = -viscIp * av[i] * av[j] * inv_axdx, accumulated in the
+ * reference's order (same-component terms first, then the NS terms for
+ * j = 0..ND-1).  flux[i]: rhs(rowL(i)) = -flux[i], rhs(rowR(i)) = +flux[i]. */
+template <int ND>
+struct MomResult
+{
+  double sLL, sLR, sRL, sRR; /* same-component advection+diffusion part */
+  double flux[ND];
+  double viscIp, inv_axdx;
+};
+
+template <int ND>
+NW_HD void
+momentum_edge(
+  const MomNode<ND>& L,
+  const MomNode<ND>& R,
+  const double* av,
+  double mdot,
+  double pecfac,
+  const nw_momentum_opts& o,
+  MomResult<ND>& res)
+{
+  const double eps = o.eps;
+  const double includeDivU = o.include_divu;
+  const double alpha = o.alpha;
+  const double alphaUpw = o.alpha_upw;
+  const double hoUpwind = o.ho_upwind;
+  const double relaxFacU = o.relax_fac;
+  const double om_alpha = 1.0 - alpha;
+  const double om_alphaUpw = 1.0 - alphaUpw;
+  const double density_upwinding_factor = 1.0; /* has_vof == 0 */
+
+  const double viscIp = 0.5 * (L.mu + R.mu);
+
+  double axdx = 0.0, asq = 0.0;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const double dxj = R.x[d] - L.x[d];
+    asq += av[d] * av[d];
+    axdx += av[d] * dxj;
+  }
+  const double inv_axdx = 1.0 / axdx;
+
+  double duL[ND], duR[ND];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    duL[i] = 0.0;
+    duR[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      const double dxj = 0.5 * (R.x[j] - L.x[j]);
+      duL[i] += dxj * L.g[i * ND + j];
+      duR[i] += dxj * R.g[i * ND + j];
+    }
+  }
+
+  double limitL[ND], limitR[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    limitL[d] = 1.0;
+    limitR[d] = 1.0;
+  }
+  if (o.use_limiter) {
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      const double du = R.u[d] - L.u[d];
+      const double duML = 4.0 * duL[d] - du;
+      const double duMR = 4.0 * duR[d] - du;
+      limitL[d] = van_leer(duML, du, eps);
+      limitR[d] = van_leer(duMR, du, eps);
+    }
+  }
+
+  const double om_pecfac = 1.0 - pecfac;
+
+  double uIpL[ND], uIpR[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    uIpL[d] = L.u[d] + duL[d] * hoUpwind * limitL[d] * density_upwinding_factor;
+    uIpR[d] = R.u[d] - duR[d] * hoUpwind * limitR[d] * density_upwinding_factor;
+  }
+
+  double duidxj[ND][ND];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    const double dui = R.u[i] - L.u[i];
+    double gjuidx = 0.0;
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      const double dxj = R.x[j] - L.x[j];
+      const double gjui = 0.5 * (R.g[i * ND + j] + L.g[i * ND + j]);
+      gjuidx += gjui * dxj;
+    }
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      const double gjui = 0.5 * (R.g[i * ND + j] + L.g[i * ND + j]);
+      duidxj[i][j] = gjui + (dui - gjuidx) * av[j] * inv_axdx;
+    }
+  }
+
+  const double dlhsfac = -viscIp * asq * inv_axdx;
+  const double maskNode = fmin(L.mask, R.mask);
+
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    const double uiIp = 0.5 * (R.u[i] + L.u[i]);
+    const double uiUpw = (mdot > 0.0)
+                           ? (alphaUpw * uIpL[i] + om_alphaUpw * uiIp)
+                           : (alphaUpw * uIpR[i] + om_alphaUpw * uiIp);
+    const double uiHatL = (alpha * uIpL[i] + om_alpha * uiIp);
+    const double uiHatR = (alpha * uIpR[i] + om_alpha * uiIp);
+    const double uiCds = 0.5 * (uiHatL + uiHatR);
+    const double adv_flux = mdot * (pecfac * uiUpw + om_pecfac * uiCds);
+
+    double diff_flux = 0.0;
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+      diff_flux += duidxj[j][j];
+    diff_flux *= 2.0 / 3.0 * viscIp * av[i] * includeDivU;
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+      diff_flux += -viscIp * (duidxj[i][j] + duidxj[j][i]) * av[j];
+
+    res.flux[i] = adv_flux + diff_flux * maskNode;
+  }
+
+  /* same-component Jacobian terms: identical for every i, accumulated in the
+   * reference's order onto a zeroed entry (AssembleEdgeSolverAlgorithm.h:89) */
+  double sLL = 0.0, sLR = 0.0, sRL = 0.0, sRR = 0.0;
+  double alhsfac = 0.5 * (mdot + fabs(mdot)) * pecfac * alphaUpw +
+                   0.5 * alpha * om_pecfac * mdot;
+  sLL += alhsfac / relaxFacU;
+  sRL -= alhsfac;
+
+  alhsfac = 0.5 * (mdot - fabs(mdot)) * pecfac * alphaUpw +
+            0.5 * alpha * om_pecfac * mdot;
+  sRR -= alhsfac / relaxFacU;
+  sLR += alhsfac;
+
+  alhsfac = 0.5 * mdot * (pecfac * om_alphaUpw + om_pecfac * om_alpha);
+  sLL += alhsfac / relaxFacU;
+  sLR += alhsfac;
+  sRL -= alhsfac;
+  sRR -= alhsfac / relaxFacU;
+
+  sLL -= dlhsfac / relaxFacU;
+  sLR += dlhsfac;
+  sRL += dlhsfac;
+  sRR -= dlhsfac / relaxFacU;
+
+  res.sLL = sLL;
+  res.sLR = sLR;
+  res.sRL = sRL;
+  res.sRR = sRR;
+  res.viscIp = viscIp;
+  res.inv_axdx = inv_axdx;
+}
+
+/* entry (i,j) of the four ND x ND sub-blocks, reference accumulation order:
+ * for row component i the j-loop adds NS_i0, NS_i1, NS_i2 in turn, and the
+ * same-component part was added before the j-loop (MomentumEdgeSolverAlg.C:275-310). */
+template <int ND>
+NW_HD void
+momentum_block_entry(
+  const MomResult<ND>& r,
+  const double* av,
+  double relaxFacU,
+  int i,
+  int j,
+  double& LL,
+  double& LR,
+  double& RL,
+  double& RR)
+{
+  const double lhsfacNS = -r.viscIp * av[i] * av[j] * r.inv_axdx;
+  const double s = (i == j) ? 1.0 : 0.0;
+  LL = s * r.sLL - lhsfacNS / relaxFacU;
+  LR = s * r.sLR + lhsfacNS;
+  RL = s * r.sRL + lhsfacNS;
+  RR = s * r.sRR - lhsfacNS / relaxFacU;
+}
+
+} // namespace nw
+
+#endif

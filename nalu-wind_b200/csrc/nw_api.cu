@@ -1,0 +1,1195 @@
+/*
+ * nw_api.cu -- implementation of the C ABI declared in include/nalu_edge_b200.h.
+ * Host logic only; the kernels are in nw_kernels.cu, the plan builder in
+ * plan.cpp, the communicator in nw_comm.cpp.
+ */
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+#include "nw_comm.h"
+#include "nw_internal.h"
+
+namespace nw {
+
+static thread_local std::string g_err;
+
+void
+set_error(const std::string& m)
+{
+  g_err = m;
+}
+
+static int
+fail(int code, const std::string& m)
+{
+  g_err = m;
+  return code;
+}
+
+#define NW_CUDA(expr)                                                        \
+  do {                                                                       \
+    cudaError_t _e = (expr);                                                 \
+    if (_e != cudaSuccess)                                                   \
+      return fail(                                                           \
+        NW_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
+  } while (0)
+
+#define NW_TRY(body)                                                         \
+  try {                                                                      \
+    body                                                                     \
+  } catch (const std::exception& ex) {                                       \
+    return fail(NW_ERR_ARG, ex.what());                                      \
+  }
+
+static int
+need_device(const nw_ctx* ctx, const char* what)
+{
+  if (!ctx || ctx->device < 0)
+    return fail(
+      NW_ERR_CUDA, std::string(what) +
+                     ": no CUDA device (host-only context); this library has "
+                     "no CPU fallback");
+  return NW_OK;
+}
+
+template <class T>
+static int
+upload(DevBuf& b, const std::vector<T>& v, cudaStream_t s, int64_t* acc)
+{
+  NW_CUDA(b.alloc(v.size() * sizeof(T)));
+  if (!v.empty())
+    NW_CUDA(cudaMemcpyAsync(
+      b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  if (acc)
+    *acc += (int64_t)(v.size() * sizeof(T));
+  return NW_OK;
+}
+
+static inline int
+even_up(int v)
+{
+  return (v + 1) & ~1;
+}
+
+} // namespace nw
+
+using namespace nw;
+
+extern "C" const char*
+nw_last_error(void)
+{
+  return g_err.c_str();
+}
+
+extern "C" int
+nw_version(void)
+{
+  return 1000;
+}
+
+/* ------------------------------------------------------------------ */
+/*  context                                                            */
+/* ------------------------------------------------------------------ */
+
+extern "C" int
+nw_ctx_create(int cuda_device, nw_ctx** out)
+{
+  if (!out)
+    return fail(NW_ERR_ARG, "nw_ctx_create: out is NULL");
+  auto* c = new nw_ctx;
+  c->device = cuda_device;
+  if (cuda_device >= 0) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || cuda_device >= n) {
+      delete c;
+      return fail(
+        NW_ERR_CUDA,
+        std::string("nw_ctx_create: CUDA device not available: ") +
+          (e != cudaSuccess ? cudaGetErrorString(e) : "index out of range"));
+    }
+    e = cudaSetDevice(cuda_device);
+    if (e == cudaSuccess)
+      e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete c;
+      return fail(
+        NW_ERR_CUDA,
+        std::string("nw_ctx_create: ") + cudaGetErrorString(e));
+    }
+  }
+  *out = c;
+  return NW_OK;
+}
+
+extern "C" int
+nw_ctx_destroy(nw_ctx* ctx)
+{
+  if (!ctx)
+    return NW_OK;
+  comm_destroy(ctx->comm);
+  if (ctx->stream)
+    cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return NW_OK;
+}
+
+extern "C" int
+nw_ctx_sync(nw_ctx* ctx)
+{
+  if (int rc = need_device(ctx, "nw_ctx_sync"))
+    return rc;
+  NW_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NW_OK;
+}
+
+extern "C" void*
+nw_ctx_stream(nw_ctx* ctx)
+{
+  return ctx ? (void*)ctx->stream : nullptr;
+}
+
+extern "C" int
+nw_comm_unique_id(void* unique_id_out)
+{
+  std::string err;
+  if (!comm_unique_id(unique_id_out, err))
+    return fail(NW_ERR_COMM, "nw_comm_unique_id: " + err);
+  return NW_OK;
+}
+
+extern "C" int
+nw_ctx_comm_init(nw_ctx* ctx, const void* unique_id, int nranks, int rank)
+{
+  if (int rc = need_device(ctx, "nw_ctx_comm_init"))
+    return rc;
+  NW_CUDA(cudaSetDevice(ctx->device));
+  std::string err;
+  if (!comm_init(ctx->comm, unique_id, nranks, rank, err))
+    return fail(NW_ERR_COMM, "nw_ctx_comm_init: " + err);
+  return NW_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/*  mesh                                                               */
+/* ------------------------------------------------------------------ */
+
+static int mesh_halo_prepare(nw_mesh* mesh, const int64_t* ownHid);
+static int mesh_halo_auto(nw_mesh* mesh);
+
+static int
+mesh_upload_plan(nw_mesh* m)
+{
+  cudaStream_t s = m->ctx->stream;
+  MeshPlan& p = m->plan;
+  int64_t& acc = m->planBytes;
+  int rc;
+  if ((rc = upload(m->dTiles, p.tiles, s, &acc)) ||
+      (rc = upload(m->dHalo, p.haloNodes, s, &acc)) ||
+      (rc = upload(m->dLr, p.lr, s, &acc)) ||
+      (rc = upload(m->dHeNode, p.heNode, s, &acc)) ||
+      (rc = upload(m->dWarpNode, p.warpSplitNode, s, &acc)) ||
+      (rc = upload(m->dPrimary, p.tileEdgePrimary, s, &acc)) ||
+      (rc = upload(m->dNodeOfSlot, p.nodeOfSlot, s, &acc)) ||
+      (rc = upload(m->dTileEdgeSrc, p.tileEdgeSrc, s, &acc)) ||
+      (rc = upload(m->dPrimarySlot, p.primarySlotOfEdge, s, &acc)))
+    return rc;
+  NW_CUDA(cudaStreamSynchronize(s));
+  MeshPlanDev& d = m->dev;
+  d.tiles = m->dTiles.as<TileHdr>();
+  d.haloNodes = m->dHalo.as<int32_t>();
+  d.lr = m->dLr.as<uint32_t>();
+  d.heNode = m->dHeNode.as<uint32_t>();
+  d.warpSplitNode = m->dWarpNode.as<int32_t>();
+  d.primary = m->dPrimary.as<uint8_t>();
+  return NW_OK;
+}
+
+extern "C" int
+nw_mesh_create(nw_ctx* ctx, const nw_mesh_desc* desc, nw_mesh** out)
+{
+  if (!ctx || !desc || !out)
+    return fail(NW_ERR_ARG, "nw_mesh_create: NULL argument");
+  auto m = std::make_unique<nw_mesh>();
+  m->ctx = ctx;
+  MeshInput in;
+  in.ndim = desc->ndim;
+  in.rank = desc->rank;
+  in.nranks = desc->nranks;
+  in.nNodes = desc->n_nodes;
+  in.nEdges = desc->n_edges;
+  in.edgeNodes = desc->edge_nodes;
+  in.nodeHid = desc->node_hypre_id;
+  in.nodeOwnHid = desc->node_own_hypre_id;
+  in.hypreOffsets = desc->hypre_offsets;
+  in.coords = desc->coords;
+  in.tileNodes = desc->tile_nodes;
+  NW_TRY(build_mesh_plan(in, m->plan);)
+  MeshPlanDev& d = m->dev;
+  d.nTiles = (int)m->plan.nTiles;
+  d.ndim = m->plan.ndim;
+  d.maxStaged = even_up((int)m->plan.maxTileStaged);
+  d.maxTileEdges = (int)m->plan.maxTileEdges;
+  d.maxTileNodes = (int)m->plan.maxTileNodes;
+  if (ctx->device >= 0) {
+    NW_CUDA(cudaSetDevice(ctx->device));
+    if (int rc = mesh_upload_plan(m.get()))
+      return rc;
+  }
+  if (desc->nranks > 1) {
+    const int64_t* own =
+      desc->node_own_hypre_id ? desc->node_own_hypre_id : desc->node_hypre_id;
+    for (int64_t n = 0; n < desc->n_nodes; ++n)
+      if (own[n] >= m->plan.iLowerNode && own[n] <= m->plan.iUpperNode)
+        m->ownedNodeOfHid[own[n]] = (int32_t)n;
+    if (int rc = mesh_halo_prepare(m.get(), own))
+      return rc;
+  }
+  nw_mesh* raw = m.release();
+  /* the coordinates field comes with the mesh (realm.get_coordinates_name()) */
+  int fid = -1;
+  int rc = nw_field_register(raw, "coordinates", NW_NODE, desc->ndim, &fid);
+  if (rc == NW_OK && ctx->device >= 0)
+    rc = nw_field_upload(raw, fid, desc->coords);
+  if (rc != NW_OK) {
+    delete raw;
+    return rc;
+  }
+  *out = raw;
+  return NW_OK;
+}
+
+extern "C" int
+nw_mesh_destroy(nw_mesh* mesh)
+{
+  delete mesh;
+  return NW_OK;
+}
+
+extern "C" int
+nw_mesh_get_stats(const nw_mesh* mesh, nw_mesh_stats* out)
+{
+  if (!mesh || !out)
+    return fail(NW_ERR_ARG, "nw_mesh_get_stats: NULL argument");
+  const MeshPlan& p = mesh->plan;
+  out->n_nodes = p.nNodes;
+  out->n_edges = p.nEdges;
+  out->n_tiles = p.nTiles;
+  int64_t te = 0;
+  for (const TileHdr& h : p.tiles)
+    te += h.nEdges;
+  out->n_tile_edges = te;
+  out->n_halo_nodes = p.totalHalo;
+  out->max_tile_nodes = p.maxTileNodes;
+  out->max_tile_staged = p.maxTileStaged;
+  out->max_tile_edges = p.maxTileEdges;
+  out->max_tile_halfedges = p.maxTileHalf;
+  out->plan_bytes_device = mesh->planBytes;
+  return NW_OK;
+}
+
+extern "C" int
+nw_mesh_get_node_permutation(
+  const nw_mesh* mesh, int64_t* n_slots, int32_t* perm)
+{
+  if (!mesh || !n_slots)
+    return fail(NW_ERR_ARG, "nw_mesh_get_node_permutation: NULL argument");
+  *n_slots = mesh->plan.nSlots;
+  if (perm)
+    std::memcpy(
+      perm, mesh->plan.nodeOfSlot.data(), mesh->plan.nSlots * sizeof(int32_t));
+  return NW_OK;
+}
+
+/* ---- fields ---- */
+
+extern "C" int
+nw_field_register(
+  nw_mesh* mesh, const char* name, int entity_rank, int ncomp, int* field_id)
+{
+  if (!mesh || !name || !field_id)
+    return fail(NW_ERR_ARG, "nw_field_register: NULL argument");
+  if (ncomp < 1 || ncomp > 9)
+    return fail(NW_ERR_ARG, "nw_field_register: ncomp must be 1..9");
+  if (entity_rank != NW_NODE && entity_rank != NW_EDGE)
+    return fail(NW_ERR_ARG, "nw_field_register: bad entity rank");
+  auto it = mesh->fieldByName.find(name);
+  if (it != mesh->fieldByName.end()) {
+    nw_field_t& f = *mesh->fields[it->second];
+    if (f.rank != entity_rank || f.ncomp != ncomp)
+      return fail(
+        NW_ERR_ARG, std::string("nw_field_register: field '") + name +
+                      "' already registered with another shape");
+    *field_id = it->second;
+    return NW_OK;
+  }
+  auto f = std::make_unique<nw_field_t>();
+  f->name = name;
+  f->rank = entity_rank;
+  f->ncomp = ncomp;
+  f->stride =
+    entity_rank == NW_NODE ? mesh->plan.nSlots : mesh->plan.nTileEdgeSlots;
+  if (mesh->ctx->device >= 0) {
+    NW_CUDA(cudaSetDevice(mesh->ctx->device));
+    NW_CUDA(f->buf.alloc(sizeof(double) * f->stride * ncomp));
+    NW_CUDA(cudaMemsetAsync(
+      f->buf.p, 0, sizeof(double) * f->stride * ncomp, mesh->ctx->stream));
+  }
+  *field_id = (int)mesh->fields.size();
+  mesh->fieldByName[name] = *field_id;
+  mesh->fields.push_back(std::move(f));
+  return NW_OK;
+}
+
+extern "C" int
+nw_field_find(const nw_mesh* mesh, const char* name, int* field_id)
+{
+  if (!mesh || !name || !field_id)
+    return fail(NW_ERR_ARG, "nw_field_find: NULL argument");
+  auto it = mesh->fieldByName.find(name);
+  if (it == mesh->fieldByName.end())
+    return fail(
+      NW_ERR_ARG, std::string("field '") + name + "' is not registered");
+  *field_id = it->second;
+  return NW_OK;
+}
+
+static nw_field_t*
+get_field(nw_mesh* mesh, int id)
+{
+  if (!mesh || id < 0 || id >= (int)mesh->fields.size())
+    return nullptr;
+  return mesh->fields[id].get();
+}
+
+static int
+ensure_scratch(nw_mesh* mesh, size_t bytes)
+{
+  if (mesh->scratch.bytes < bytes) {
+    /* wait for earlier users of the old scratch before freeing it */
+    NW_CUDA(cudaStreamSynchronize(mesh->ctx->stream));
+    NW_CUDA(mesh->scratch.alloc(bytes));
+  }
+  return NW_OK;
+}
+
+extern "C" int
+nw_field_upload(nw_mesh* mesh, int field_id, const double* host)
+{
+  nw_field_t* f = get_field(mesh, field_id);
+  if (!f || !host)
+    return fail(NW_ERR_ARG, "nw_field_upload: bad field id or NULL buffer");
+  if (int rc = need_device(mesh->ctx, "nw_field_upload"))
+    return rc;
+  cudaStream_t s = mesh->ctx->stream;
+  const int64_t nEnt = f->rank == NW_NODE ? mesh->plan.nNodes : mesh->plan.nEdges;
+  const size_t bytes = sizeof(double) * nEnt * f->ncomp;
+  if (int rc = ensure_scratch(mesh, bytes))
+    return rc;
+  NW_CUDA(cudaMemcpyAsync(mesh->scratch.p, host, bytes, cudaMemcpyHostToDevice, s));
+  if (f->rank == NW_NODE)
+    NW_CUDA(launch_node_gather(
+      mesh->scratch.as<double>(), f->ncomp, mesh->dNodeOfSlot.as<int32_t>(),
+      f->stride, f->buf.as<double>(), s));
+  else
+    NW_CUDA(launch_edge_gather(
+      mesh->scratch.as<double>(), f->ncomp, mesh->dTileEdgeSrc.as<int32_t>(),
+      f->stride, f->buf.as<double>(), s));
+  return NW_OK;
+}
+
+extern "C" int
+nw_field_download(nw_mesh* mesh, int field_id, double* host)
+{
+  nw_field_t* f = get_field(mesh, field_id);
+  if (!f || !host)
+    return fail(NW_ERR_ARG, "nw_field_download: bad field id or NULL buffer");
+  if (int rc = need_device(mesh->ctx, "nw_field_download"))
+    return rc;
+  cudaStream_t s = mesh->ctx->stream;
+  const int64_t nEnt = f->rank == NW_NODE ? mesh->plan.nNodes : mesh->plan.nEdges;
+  const size_t bytes = sizeof(double) * nEnt * f->ncomp;
+  if (int rc = ensure_scratch(mesh, bytes))
+    return rc;
+  if (f->rank == NW_NODE)
+    NW_CUDA(launch_node_scatter(
+      f->buf.as<double>(), f->ncomp, mesh->dNodeOfSlot.as<int32_t>(), f->stride,
+      mesh->scratch.as<double>(), s));
+  else
+    NW_CUDA(launch_edge_scatter(
+      f->buf.as<double>(), f->ncomp, mesh->dPrimarySlot.as<int32_t>(),
+      mesh->plan.nEdges, f->stride, mesh->scratch.as<double>(), s));
+  NW_CUDA(cudaMemcpyAsync(host, mesh->scratch.p, bytes, cudaMemcpyDeviceToHost, s));
+  NW_CUDA(cudaStreamSynchronize(s));
+  return NW_OK;
+}
+
+extern "C" int
+nw_field_fill(nw_mesh* mesh, int field_id, double value)
+{
+  nw_field_t* f = get_field(mesh, field_id);
+  if (!f)
+    return fail(NW_ERR_ARG, "nw_field_fill: bad field id");
+  if (int rc = need_device(mesh->ctx, "nw_field_fill"))
+    return rc;
+  NW_CUDA(launch_fill(
+    f->buf.as<double>(), f->stride * f->ncomp, value, mesh->ctx->stream));
+  return NW_OK;
+}
+
+extern "C" int
+nw_field_device_view(
+  nw_mesh* mesh, int field_id, double** base, int64_t* stride)
+{
+  nw_field_t* f = get_field(mesh, field_id);
+  if (!f || !base || !stride)
+    return fail(NW_ERR_ARG, "nw_field_device_view: bad argument");
+  if (int rc = need_device(mesh->ctx, "nw_field_device_view"))
+    return rc;
+  *base = f->buf.as<double>();
+  *stride = f->stride;
+  return NW_OK;
+}
+
+/* ---- helpers to bind fields by the reference's names ---- */
+
+static int
+bind(
+  nw_mesh* mesh, const char* name, int rank, int ncomp, const double** comps)
+{
+  auto it = mesh->fieldByName.find(name);
+  if (it == mesh->fieldByName.end())
+    return fail(
+      NW_ERR_STATE, std::string("required field '") + name +
+                      "' is not registered (get_field_ordinal would throw)");
+  nw_field_t& f = *mesh->fields[it->second];
+  if (f.rank != rank || f.ncomp != ncomp)
+    return fail(
+      NW_ERR_STATE, std::string("field '") + name + "' has the wrong shape");
+  for (int c = 0; c < ncomp; ++c)
+    comps[c] = f.buf.as<double>() + (int64_t)c * f.stride;
+  return NW_OK;
+}
+
+static int
+bind_id(nw_mesh* mesh, int id, int rank, int ncomp, const double** comps)
+{
+  nw_field_t* f = get_field(mesh, id);
+  if (!f)
+    return fail(NW_ERR_ARG, "bad field id");
+  if (f->rank != rank || f->ncomp != ncomp)
+    return fail(
+      NW_ERR_ARG, std::string("field '") + f->name + "' has the wrong shape");
+  for (int c = 0; c < ncomp; ++c)
+    comps[c] = f->buf.as<double>() + (int64_t)c * f->stride;
+  return NW_OK;
+}
+
+static int
+bind_edge_common(nw_mesh* mesh, EdgeComps& ec, bool mdot, bool pec)
+{
+  const int nd = mesh->plan.ndim;
+  ec = EdgeComps();
+  const double* a[3] = {nullptr, nullptr, nullptr};
+  if (int rc = bind(mesh, "edge_area_vector", NW_EDGE, nd, a))
+    return rc;
+  for (int d = 0; d < 3; ++d)
+    ec.area[d] = a[d];
+  if (mdot)
+    if (int rc = bind(mesh, "mass_flow_rate", NW_EDGE, 1, &ec.mdot))
+      return rc;
+  if (pec)
+    if (int rc = bind(mesh, "peclet_factor", NW_EDGE, 1, &ec.pecfac))
+      return rc;
+  return NW_OK;
+}
+
+/* continuity / mdot node bundle: x, u, dpdx, rho, p, udiag */
+static int
+bind_cont_nodes(nw_mesh* mesh, NodeComps& nc)
+{
+  const int nd = mesh->plan.ndim;
+  int rc;
+  if ((rc = bind(mesh, "coordinates", NW_NODE, nd, &nc.c[0])) ||
+      (rc = bind(mesh, "velocity", NW_NODE, nd, &nc.c[nd])) ||
+      (rc = bind(mesh, "dpdx", NW_NODE, nd, &nc.c[2 * nd])) ||
+      (rc = bind(mesh, "density", NW_NODE, 1, &nc.c[3 * nd])) ||
+      (rc = bind(mesh, "pressure", NW_NODE, 1, &nc.c[3 * nd + 1])) ||
+      (rc = bind(mesh, "momentum_diag", NW_NODE, 1, &nc.c[3 * nd + 2])))
+    return rc;
+  return NW_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/*  edge algorithms without a linear system                            */
+/* ------------------------------------------------------------------ */
+
+extern "C" int
+nw_mdot_edge(nw_mesh* mesh, const nw_mdot_opts* opts)
+{
+  if (!mesh || !opts)
+    return fail(NW_ERR_ARG, "nw_mdot_edge: NULL argument");
+  if (int rc = need_device(mesh->ctx, "nw_mdot_edge"))
+    return rc;
+  NodeComps nc;
+  EdgeComps ec;
+  if (int rc = bind_cont_nodes(mesh, nc))
+    return rc;
+  if (int rc = bind_edge_common(mesh, ec, false, false))
+    return rc;
+  const double* out = nullptr;
+  if (int rc = bind(mesh, "mass_flow_rate", NW_EDGE, 1, &out))
+    return rc;
+  NW_CUDA(launch_mdot_tile(
+    mesh->dev, nc, ec, const_cast<double*>(out), *opts, mesh->ctx->stream));
+  return NW_OK;
+}
+
+extern "C" int
+nw_peclet_edge(nw_mesh* mesh, int viscosity_field, const nw_peclet_opts* opts)
+{
+  if (!mesh || !opts)
+    return fail(NW_ERR_ARG, "nw_peclet_edge: NULL argument");
+  if (int rc = need_device(mesh->ctx, "nw_peclet_edge"))
+    return rc;
+  const int nd = mesh->plan.ndim;
+  NodeComps nc;
+  int rc;
+  if ((rc = bind(mesh, "coordinates", NW_NODE, nd, &nc.c[0])) ||
+      (rc = bind(mesh, "velocity", NW_NODE, nd, &nc.c[nd])) ||
+      (rc = bind(mesh, "density", NW_NODE, 1, &nc.c[2 * nd])) ||
+      (rc = bind_id(mesh, viscosity_field, NW_NODE, 1, &nc.c[2 * nd + 1])))
+    return rc;
+  const double* out = nullptr;
+  if ((rc = bind(mesh, "peclet_factor", NW_EDGE, 1, &out)))
+    return rc;
+  NW_CUDA(launch_peclet_tile(
+    mesh->dev, nc, const_cast<double*>(out), *opts, mesh->ctx->stream));
+  return NW_OK;
+}
+
+static int node_halo_sum(nw_mesh* mesh, nw_field_t* f);
+
+extern "C" int
+nw_nodal_grad_edge(nw_mesh* mesh, int phi_field, int grad_field)
+{
+  if (!mesh)
+    return fail(NW_ERR_ARG, "nw_nodal_grad_edge: NULL mesh");
+  if (int rc = need_device(mesh->ctx, "nw_nodal_grad_edge"))
+    return rc;
+  nw_field_t* phi = get_field(mesh, phi_field);
+  nw_field_t* grad = get_field(mesh, grad_field);
+  const int nd = mesh->plan.ndim;
+  if (!phi || !grad || phi->rank != NW_NODE || grad->rank != NW_NODE)
+    return fail(NW_ERR_ARG, "nw_nodal_grad_edge: bad field id");
+  /* NodalGradEdgeAlg constructor checks, src/ngp_algorithms/NodalGradEdgeAlg.C:24-55 */
+  if (!(phi->ncomp == 1 || phi->ncomp == nd) ||
+      grad->ncomp != phi->ncomp * nd)
+    return fail(
+      NW_ERR_ARG,
+      "nw_nodal_grad_edge: phi must be a scalar or vector field and grad "
+      "must have dim1*ndim components");
+  NodeComps nc;
+  for (int c = 0; c < phi->ncomp; ++c)
+    nc.c[c] = phi->buf.as<double>() + (int64_t)c * phi->stride;
+  const double* vol = nullptr;
+  EdgeComps ec;
+  int rc;
+  if ((rc = bind(mesh, "dual_nodal_volume", NW_NODE, 1, &vol)) ||
+      (rc = bind_edge_common(mesh, ec, false, false)))
+    return rc;
+  double* out[9];
+  for (int c = 0; c < grad->ncomp; ++c)
+    out[c] = grad->buf.as<double>() + (int64_t)c * grad->stride;
+  NW_CUDA(launch_grad_tile(
+    mesh->dev, phi->ncomp, nc, vol, ec, out, mesh->ctx->stream));
+  if (mesh->plan.nranks > 1)
+    return node_halo_sum(mesh, grad);
+  return NW_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/*  linear system                                                      */
+/* ------------------------------------------------------------------ */
+
+extern "C" int
+nw_linsys_create(nw_mesh* mesh, int kind, int num_dof, nw_linsys** out)
+{
+  if (!mesh || !out)
+    return fail(NW_ERR_ARG, "nw_linsys_create: NULL argument");
+  if (kind != NW_LINSYS_HYPRE && kind != NW_LINSYS_HYPRE_UVW)
+    return fail(NW_ERR_ARG, "nw_linsys_create: unknown kind");
+  if (kind == NW_LINSYS_HYPRE && !(num_dof == 1 || num_dof == mesh->plan.ndim))
+    return fail(NW_ERR_ARG, "nw_linsys_create: num_dof must be 1 or ndim");
+  auto* ls = new nw_linsys;
+  ls->mesh = mesh;
+  ls->kind = kind;
+  ls->numDof = kind == NW_LINSYS_HYPRE_UVW ? 1 : num_dof;
+  ls->nRhs = kind == NW_LINSYS_HYPRE_UVW ? mesh->plan.ndim : 1;
+  *out = ls;
+  return NW_OK;
+}
+
+extern "C" int
+nw_linsys_destroy(nw_linsys* ls)
+{
+  delete ls;
+  return NW_OK;
+}
+
+extern "C" int
+nw_linsys_set_skipped_rows(nw_linsys* ls, const int64_t* rows, int64_t n)
+{
+  if (!ls || (n > 0 && !rows))
+    return fail(NW_ERR_ARG, "nw_linsys_set_skipped_rows: NULL argument");
+  if (ls->finalized)
+    return fail(NW_ERR_STATE, "nw_linsys_set_skipped_rows: already finalized");
+  ls->skipped.assign(rows, rows + n);
+  return NW_OK;
+}
+
+extern "C" int
+nw_linsys_build_edge_to_node_graph(nw_linsys* ls)
+{
+  if (!ls)
+    return fail(NW_ERR_ARG, "nw_linsys_build_edge_to_node_graph: NULL");
+  ls->graphBuilt = true;
+  return NW_OK;
+}
+
+static int
+linsys_upload(nw_linsys* ls)
+{
+  nw_mesh* m = ls->mesh;
+  cudaStream_t s = m->ctx->stream;
+  NW_CUDA(cudaSetDevice(m->ctx->device));
+  const Graph& g = ls->g;
+  const int64_t nnz = g.nnzOwned + g.nnzShared + ls->nExtra;
+  const int64_t rows = g.numRowsLocal();
+  NW_CUDA(ls->dValues.alloc(sizeof(double) * (nnz + 2)));
+  NW_CUDA(ls->dRhs.alloc(sizeof(double) * (rows * ls->nRhs + 2)));
+  ls->dev.values = ls->dValues.as<double>();
+  ls->dev.rhs = ls->dRhs.as<double>();
+  ls->dev.rhsStride = rows;
+  int rc;
+  if (ls->lp.usable) {
+    if ((rc = upload(ls->dLsTiles, ls->lp.tiles, s, nullptr)) ||
+        (rc = upload(ls->dEntInfo, ls->lp.entInfo, s, nullptr)) ||
+        (rc = upload(ls->dEntRhsRow, ls->lp.entRhsRow, s, nullptr)) ||
+        (rc = upload(ls->dHe, ls->lp.he, s, nullptr)) ||
+        (rc = upload(ls->dWarp, ls->lp.warpSplit, s, nullptr)) ||
+        (rc = upload(ls->dRuns, ls->lp.runs, s, nullptr)))
+      return rc;
+    ls->dev.tiles = ls->dLsTiles.as<LsTileHdr>();
+    ls->dev.entInfo = ls->dEntInfo.as<EntInfo>();
+    ls->dev.entRhsRow = ls->dEntRhsRow.as<int32_t>();
+    ls->dev.he = ls->dHe.as<uint32_t>();
+    ls->dev.warpSplit = ls->dWarp.as<int32_t>();
+    ls->dev.runs = ls->dRuns.as<Run>();
+    ls->dev.maxTileNnz = (int)ls->lp.maxTileNnz;
+    ls->dev.maxTileEnts = (int)ls->lp.maxTileEnts;
+    /* rows the tiles do not write */
+    std::vector<uint8_t> isPer(ls->lp.uncoveredRows.size(), 0);
+    for (size_t i = 0; i < isPer.size(); ++i) {
+      const int64_t r = ls->lp.uncoveredRows[i];
+      if (r < g.numRowsOwned)
+        isPer[i] = std::binary_search(
+          g.periodicRowsOwned.begin(), g.periodicRowsOwned.end(), g.iLower + r);
+    }
+    if ((rc = upload(ls->dUncovered, ls->lp.uncoveredRows, s, nullptr)) ||
+        (rc = upload(ls->dUncoveredPeriodic, isPer, s, nullptr)))
+      return rc;
+  }
+  {
+    std::vector<int64_t> rowPtr(rows + 1);
+    for (int64_t r = 0; r < rows; ++r)
+      rowPtr[r] = g.rowPtr(r);
+    rowPtr[rows] = g.nnzOwned + g.nnzShared;
+    if ((rc = upload(ls->dRowPtr, rowPtr, s, nullptr)))
+      return rc;
+    std::vector<int64_t> per(g.periodicRowsOwned.size());
+    for (size_t i = 0; i < per.size(); ++i)
+      per[i] = g.rowStartOwned[g.periodicRowsOwned[i] - g.iLower];
+    if ((rc = upload(ls->dPeriodicRows, per, s, nullptr)))
+      return rc;
+  }
+  const int nPartial = 296;
+  NW_CUDA(ls->dNormPartial.alloc(sizeof(double) * nPartial * ls->nRhs));
+  NW_CUDA(ls->dNormOut.alloc(sizeof(double) * 8));
+  NW_CUDA(cudaStreamSynchronize(s));
+  return NW_OK;
+}
+
+static int linsys_build_halo(nw_linsys* ls);
+
+extern "C" int
+nw_linsys_finalize(nw_linsys* ls)
+{
+  if (!ls)
+    return fail(NW_ERR_ARG, "nw_linsys_finalize: NULL");
+  if (!ls->graphBuilt)
+    return fail(
+      NW_ERR_STATE, "nw_linsys_finalize: buildEdgeToNodeGraph not called");
+  if (ls->finalized)
+    return NW_OK;
+  NW_TRY(build_graph(ls->mesh->plan, ls->kind, ls->numDof, ls->skipped, ls->g);
+         build_ls_plan(ls->mesh->plan, ls->g, ls->lp);)
+  if (ls->g.nnzOwned + ls->g.nnzShared >= (int64_t(1) << 31) - 8)
+    return fail(
+      NW_ERR_LIMIT, "nw_linsys_finalize: more than 2^31 nonzeros per rank");
+  if (ls->mesh->plan.nranks > 1)
+    if (int rc = linsys_build_halo(ls))
+      return rc;
+  if (ls->mesh->ctx->device >= 0)
+    if (int rc = linsys_upload(ls))
+      return rc;
+  ls->finalized = true;
+  ls->state = NW_LS_UNSET;
+  return NW_OK;
+}
+
+extern "C" int
+nw_linsys_get_sizes(const nw_linsys* ls, nw_linsys_sizes* out)
+{
+  if (!ls || !out)
+    return fail(NW_ERR_ARG, "nw_linsys_get_sizes: NULL argument");
+  if (!ls->finalized)
+    return fail(NW_ERR_STATE, "nw_linsys_get_sizes: not finalized");
+  const Graph& g = ls->g;
+  out->i_lower = g.iLower;
+  out->i_upper = g.iUpper;
+  out->num_rows_owned = g.numRowsOwned;
+  out->num_nonzeros_owned = g.nnzOwned;
+  out->num_rows_shared = g.numRowsShared;
+  out->num_nonzeros_shared = g.nnzShared;
+  out->num_periodic_rows = (int64_t)g.periodicRowsOwned.size();
+  out->num_rhs = ls->nRhs;
+  out->block = g.block;
+  return NW_OK;
+}
+
+template <class T>
+static void
+copy_out(T* dst, const std::vector<T>& v)
+{
+  if (dst && !v.empty())
+    std::memcpy(dst, v.data(), v.size() * sizeof(T));
+}
+
+extern "C" int
+nw_linsys_get_graph(
+  const nw_linsys* ls,
+  int64_t* mat_row_start_owned,
+  int64_t* mat_row_start_shared,
+  int64_t* cols,
+  int64_t* rows,
+  int64_t* row_indices_shared,
+  int64_t* periodic_rows_owned)
+{
+  if (!ls)
+    return fail(NW_ERR_ARG, "nw_linsys_get_graph: NULL");
+  if (!ls->finalized)
+    return fail(NW_ERR_STATE, "nw_linsys_get_graph: not finalized");
+  const Graph& g = ls->g;
+  copy_out(mat_row_start_owned, g.rowStartOwned);
+  copy_out(mat_row_start_shared, g.rowStartShared);
+  copy_out(cols, g.cols);
+  copy_out(rows, g.rows);
+  copy_out(row_indices_shared, g.rowIndicesShared);
+  copy_out(periodic_rows_owned, g.periodicRowsOwned);
+  return NW_OK;
+}
+
+extern "C" int
+nw_linsys_get_edge_slots(
+  const nw_linsys* ls, int64_t* slots, int64_t* rhs_rows)
+{
+  if (!ls)
+    return fail(NW_ERR_ARG, "nw_linsys_get_edge_slots: NULL");
+  if (!ls->finalized)
+    return fail(NW_ERR_STATE, "nw_linsys_get_edge_slots: not finalized");
+  copy_out(slots, ls->g.edgeSlots);
+  copy_out(rhs_rows, ls->g.edgeRhsRows);
+  return NW_OK;
+}
+
+static int
+ls_ready(nw_linsys* ls, const char* what)
+{
+  if (!ls)
+    return fail(NW_ERR_ARG, std::string(what) + ": NULL linear system");
+  if (int rc = need_device(ls->mesh->ctx, what))
+    return rc;
+  if (!ls->finalized)
+    return fail(
+      NW_ERR_STATE,
+      std::string(what) + ": finalizeLinearSystem has not been called");
+  return NW_OK;
+}
+
+/* turn a lazy zero into real zeros (atomic kernels and sum_into accumulate) */
+static int
+materialize_zero(nw_linsys* ls)
+{
+  cudaStream_t s = ls->mesh->ctx->stream;
+  const Graph& g = ls->g;
+  const int64_t nnz = g.nnzOwned + g.nnzShared + ls->nExtra;
+  NW_CUDA(cudaMemsetAsync(ls->dValues.p, 0, sizeof(double) * nnz, s));
+  NW_CUDA(cudaMemsetAsync(
+    ls->dRhs.p, 0, sizeof(double) * g.numRowsLocal() * ls->nRhs, s));
+  /* periodic-slave rows: diagonal 1 (src/HypreLinearSystem.C:1420-1428) */
+  const int64_t np = (int64_t)g.periodicRowsOwned.size();
+  if (np > 0) {
+    /* dPeriodicRows holds the value offsets of those diagonals */
+    std::vector<double> ones(np, 1.0);
+    if (int rc = ensure_scratch(ls->mesh, sizeof(double) * np))
+      return rc;
+    NW_CUDA(cudaMemcpyAsync(
+      ls->mesh->scratch.p, ones.data(), sizeof(double) * np,
+      cudaMemcpyHostToDevice, s));
+    NW_CUDA(cudaStreamSynchronize(s));
+    /* scatter: dst[idx[i]] += src[i] on zeroed memory */
+    NW_CUDA(launch_unpack_add(
+      ls->mesh->scratch.as<double>(), ls->dPeriodicRows.as<int64_t>(), np,
+      ls->dValues.as<double>(), s));
+  }
+  ls->state = NW_LS_ACCUM;
+  return NW_OK;
+}
+
+extern "C" int
+nw_linsys_zero(nw_linsys* ls)
+{
+  if (int rc = ls_ready(ls, "nw_linsys_zero"))
+    return rc;
+  /* The zero-fill is deferred: the tile kernels write every row exactly once,
+   * so a following segmented assembly needs no memset at all. */
+  ls->state = NW_LS_LAZY_ZERO;
+  return NW_OK;
+}
+
+extern "C" int
+nw_linsys_set_scatter_mode(nw_linsys* ls, int mode)
+{
+  if (!ls || (mode != NW_SCATTER_SEGMENTED && mode != NW_SCATTER_ATOMIC))
+    return fail(NW_ERR_ARG, "nw_linsys_set_scatter_mode: bad argument");
+  ls->mode = mode;
+  return NW_OK;
+}
+
+static int
+build_atomic_map(nw_linsys* ls)
+{
+  if (ls->atomicBuilt)
+    return NW_OK;
+  const MeshPlan& mp = ls->mesh->plan;
+  const Graph& g = ls->g;
+  const int nb = g.block;
+  const int64_t S = mp.nTileEdgeSlots;
+  std::vector<int32_t> slots(size_t(S) * nb * nb, -1);
+  std::vector<int32_t> rows(size_t(S) * nb, -1);
+  for (int64_t e = 0; e < mp.nEdges; ++e) {
+    const int64_t s = mp.primarySlotOfEdge[e];
+    for (int i = 0; i < nb * nb; ++i)
+      slots[size_t(s) * nb * nb + i] =
+        (int32_t)g.edgeSlots[size_t(e) * nb * nb + i];
+    for (int i = 0; i < nb; ++i)
+      rows[size_t(s) * nb + i] = (int32_t)g.edgeRhsRows[size_t(e) * nb + i];
+  }
+  cudaStream_t st = ls->mesh->ctx->stream;
+  int rc;
+  if ((rc = upload(ls->dASlots, slots, st, nullptr)) ||
+      (rc = upload(ls->dARhsRows, rows, st, nullptr)))
+    return rc;
+  NW_CUDA(cudaStreamSynchronize(st));
+  ls->atomicBuilt = true;
+  return NW_OK;
+}
+
+/* after a tile assembly on a lazily-zeroed system: initialise the rows no tile
+ * owns (Dirichlet rows, periodic-slave rows) */
+static int
+finish_tile_assembly(nw_linsys* ls)
+{
+  cudaStream_t s = ls->mesh->ctx->stream;
+  NW_CUDA(launch_row_init(
+    ls->dUncovered.as<int32_t>(), (int)ls->lp.uncoveredRows.size(),
+    ls->dRowPtr.as<int64_t>(), ls->dUncoveredPeriodic.as<uint8_t>(),
+    ls->dev.values, ls->dev.rhs, ls->dev.rhsStride, ls->nRhs, s));
+  if (ls->nExtra > 0)
+    NW_CUDA(cudaMemsetAsync(
+      ls->dev.values + ls->g.nnzOwned + ls->g.nnzShared, 0,
+      sizeof(double) * ls->nExtra, s));
+  ls->state = NW_LS_ACCUM;
+  return NW_OK;
+}
+
+/* decide the path for an edge assembly; returns 1 for the tile kernel */
+static int
+use_tile_path(nw_linsys* ls, bool needsDiagExtract, int* rcOut)
+{
+  *rcOut = NW_OK;
+  const bool tile = ls->mode == NW_SCATTER_SEGMENTED && ls->lp.usable &&
+                    ls->state == NW_LS_LAZY_ZERO && !needsDiagExtract;
+  if (tile)
+    return 1;
+  if (ls->state != NW_LS_ACCUM)
+    if ((*rcOut = materialize_zero(ls)))
+      return 0;
+  *rcOut = build_atomic_map(ls);
+  return 0;
+}
+
+extern "C" int
+nw_assemble_continuity_edge(nw_linsys* ls, const nw_continuity_opts* opts)
+{
+  if (int rc = ls_ready(ls, "nw_assemble_continuity_edge"))
+    return rc;
+  if (!opts)
+    return fail(NW_ERR_ARG, "nw_assemble_continuity_edge: NULL options");
+  if (ls->numDof != 1 || ls->kind != NW_LINSYS_HYPRE)
+    return fail(
+      NW_ERR_ARG, "nw_assemble_continuity_edge: needs a 1-dof hypre system");
+  nw_mesh* mesh = ls->mesh;
+  NodeComps nc;
+  EdgeComps ec;
+  int rc;
+  if ((rc = bind_cont_nodes(mesh, nc)) ||
+      (rc = bind_edge_common(mesh, ec, false, false)))
+    return rc;
+  cudaStream_t s = mesh->ctx->stream;
+  if (use_tile_path(ls, false, &rc)) {
+    NW_CUDA(launch_continuity_tile(mesh->dev, ls->dev, nc, ec, *opts, s));
+    return finish_tile_assembly(ls);
+  }
+  if (rc)
+    return rc;
+  AtomicMapDev am{ls->dASlots.as<int32_t>(), ls->dARhsRows.as<int32_t>()};
+  NW_CUDA(launch_continuity_atomic(mesh->dev, ls->dev, am, nc, ec, *opts, s));
+  return NW_OK;
+}
+
+extern "C" int
+nw_assemble_scalar_edge(
+  nw_linsys* ls,
+  int q_field,
+  int dqdx_field,
+  int diff_flux_coeff_field,
+  const nw_scalar_opts* opts)
+{
+  if (int rc = ls_ready(ls, "nw_assemble_scalar_edge"))
+    return rc;
+  if (!opts)
+    return fail(NW_ERR_ARG, "nw_assemble_scalar_edge: NULL options");
+  if (ls->numDof != 1 || ls->kind != NW_LINSYS_HYPRE)
+    return fail(
+      NW_ERR_ARG, "nw_assemble_scalar_edge: needs a 1-dof hypre system");
+  nw_mesh* mesh = ls->mesh;
+  const int nd = mesh->plan.ndim;
+  NodeComps nc;
+  EdgeComps ec;
+  int rc;
+  /* x, vrtm, dqdx, q, rho, dflux */
+  if ((rc = bind(mesh, "coordinates", NW_NODE, nd, &nc.c[0])) ||
+      (rc = bind(mesh, "velocity", NW_NODE, nd, &nc.c[nd])) ||
+      (rc = bind_id(mesh, dqdx_field, NW_NODE, nd, &nc.c[2 * nd])) ||
+      (rc = bind_id(mesh, q_field, NW_NODE, 1, &nc.c[3 * nd])) ||
+      (rc = bind(mesh, "density", NW_NODE, 1, &nc.c[3 * nd + 1])) ||
+      (rc = bind_id(mesh, diff_flux_coeff_field, NW_NODE, 1, &nc.c[3 * nd + 2])) ||
+      (rc = bind_edge_common(mesh, ec, true, false)))
+    return rc;
+  cudaStream_t s = mesh->ctx->stream;
+  if (use_tile_path(ls, false, &rc)) {
+    NW_CUDA(launch_scalar_tile(mesh->dev, ls->dev, nc, ec, *opts, s));
+    return finish_tile_assembly(ls);
+  }
+  if (rc)
+    return rc;
+  AtomicMapDev am{ls->dASlots.as<int32_t>(), ls->dARhsRows.as<int32_t>()};
+  NW_CUDA(launch_scalar_atomic(mesh->dev, ls->dev, am, nc, ec, *opts, s));
+  return NW_OK;
+}
+
+extern "C" int
+nw_assemble_momentum_edge(
+  nw_linsys* ls, int viscosity_field, const nw_momentum_opts* opts)
+{
+  if (int rc = ls_ready(ls, "nw_assemble_momentum_edge"))
+    return rc;
+  if (!opts)
+    return fail(NW_ERR_ARG, "nw_assemble_momentum_edge: NULL options");
+  nw_mesh* mesh = ls->mesh;
+  const int nd = mesh->plan.ndim;
+  const bool uvw = ls->kind == NW_LINSYS_HYPRE_UVW;
+  if (!uvw && ls->numDof != nd)
+    return fail(
+      NW_ERR_ARG,
+      "nw_assemble_momentum_edge: needs a UVW system or numDof == ndim");
+  NodeComps nc;
+  EdgeComps ec;
+  int rc;
+  /* x, u, dudx, visc, rho, mask */
+  if ((rc = bind(mesh, "coordinates", NW_NODE, nd, &nc.c[0])) ||
+      (rc = bind(mesh, "velocity", NW_NODE, nd, &nc.c[nd])) ||
+      (rc = bind(mesh, "dudx", NW_NODE, nd * nd, &nc.c[2 * nd])) ||
+      (rc = bind_id(mesh, viscosity_field, NW_NODE, 1, &nc.c[2 * nd + nd * nd])) ||
+      (rc = bind(mesh, "density", NW_NODE, 1, &nc.c[2 * nd + nd * nd + 1])) ||
+      (rc = bind(
+         mesh, "abl_wall_no_slip_wall_func_node_mask", NW_NODE, 1,
+         &nc.c[2 * nd + nd * nd + 2])) ||
+      (rc = bind_edge_common(mesh, ec, true, !opts->fuse_peclet)))
+    return rc;
+  double* diagOut = nullptr;
+  if (opts->diag_field >= 0) {
+    const double* dp = nullptr;
+    if ((rc = bind_id(mesh, opts->diag_field, NW_NODE, 1, &dp)))
+      return rc;
+    diagOut = const_cast<double*>(dp);
+  }
+  cudaStream_t s = mesh->ctx->stream;
+  if (uvw) {
+    if (use_tile_path(ls, diagOut != nullptr, &rc)) {
+      NW_CUDA(launch_momentum_uvw_tile(
+        mesh->dev, ls->dev, nc, ec, *opts, nullptr, s));
+      return finish_tile_assembly(ls);
+    }
+    if (rc)
+      return rc;
+    AtomicMapDev am{ls->dASlots.as<int32_t>(), ls->dARhsRows.as<int32_t>()};
+    NW_CUDA(launch_momentum_uvw_atomic(
+      mesh->dev, ls->dev, am, nc, ec, *opts, diagOut, s));
+    return NW_OK;
+  }
+  /* monolithic: atomic scatter of the full block */
+  if (ls->state != NW_LS_ACCUM)
+    if ((rc = materialize_zero(ls)))
+      return rc;
+  if ((rc = build_atomic_map(ls)))
+    return rc;
+  NW_CUDA(launch_momentum_mono_atomic(
+    mesh->dev, ls->dASlots.as<int32_t>(), ls->dARhsRows.as<int32_t>(),
+    ls->dev.values, ls->dev.rhs, nc, ec, *opts, diagOut, s));
+  return NW_OK;
+}
+
+static int
+build_dev_graph(nw_linsys* ls)
+{
+  if (ls->devGraphBuilt)
+    return NW_OK;
+  cudaStream_t s = ls->mesh->ctx->stream;
+  const Graph& g = ls->g;
+  int rc;
+  if ((rc = upload(ls->dRowStartOwned, g.rowStartOwned, s, nullptr)) ||
+      (rc = upload(ls->dRowStartShared, g.rowStartShared, s, nullptr)) ||
+      (rc = upload(ls->dRowIndicesShared, g.rowIndicesShared, s, nullptr)) ||
+      (rc = upload(ls->dCols, g.cols, s, nullptr)) ||
+      (rc = upload(ls->dSkipped, g.skippedRows, s, nullptr)) ||
+      (rc = upload(ls->dNodeHid, ls->mesh->plan.nodeHid, s, nullptr)))
+    return rc;
+  NW_CUDA(cudaStreamSynchronize(s));
+  ls->devGraphBuilt = true;
+  return NW_OK;
+}
+
+extern "C" int
+nw_linsys_sum_into(
+  nw_linsys* ls,
+  int64_t n_entities,
+  int nodes_per_entity,
+  const int32_t* d_entity_nodes,
+  const double* d_lhs,
+  const double* d_rhs)
+{
+  if (int rc = ls_ready(ls, "nw_linsys_sum_into"))
+    return rc;
+  if (n_entities < 0 || nodes_per_entity < 1 || nodes_per_entity > 8 ||
+      (n_entities > 0 && (!d_entity_nodes || !d_lhs || !d_rhs)))
+    return fail(NW_ERR_ARG, "nw_linsys_sum_into: bad argument");
+  int rc;
+  if (ls->state != NW_LS_ACCUM)
+    if ((rc = materialize_zero(ls)))
+      return rc;
+  if ((rc = build_dev_graph(ls)))
+    return rc;
+  const Graph& g = ls->g;
+  NW_CUDA(launch_sum_into(
+    n_entities, nodes_per_entity, ls->numDof, d_entity_nodes,
+    ls->dNodeHid.as<int64_t>(), d_lhs, d_rhs, g.iLower, g.iUpper,
+    g.numRowsOwned, g.nnzOwned, ls->dRowStartOwned.as<int64_t>(),
+    ls->dRowStartShared.as<int64_t>(), ls->dRowIndicesShared.as<int64_t>(),
+    g.numRowsShared, ls->dCols.as<int64_t>(), ls->dSkipped.as<int64_t>(),
+    (int64_t)g.skippedRows.size(),
+    ls->kind == NW_LINSYS_HYPRE_UVW ? ls->mesh->plan.ndim : 0, ls->dev.values,
+    ls->dev.rhs, ls->dev.rhsStride, ls->mesh->ctx->stream));
+  return NW_OK;
+}
+
+extern "C" int
+nw_linsys_device_arrays(
+  nw_linsys* ls, double** values, double** rhs, int64_t* rhs_stride)
+{
+  if (int rc = ls_ready(ls, "nw_linsys_device_arrays"))
+    return rc;
+  if (ls->state == NW_LS_LAZY_ZERO)
+    if (int rc = materialize_zero(ls))
+      return rc;
+  if (values)
+    *values = ls->dev.values;
+  if (rhs)
+    *rhs = ls->dev.rhs;
+  if (rhs_stride)
+    *rhs_stride = ls->dev.rhsStride;
+  return NW_OK;
+}
+
+extern "C" int
+nw_linsys_get_values(nw_linsys* ls, double* values, double* rhs)
+{
+  if (int rc = ls_ready(ls, "nw_linsys_get_values"))
+    return rc;
+  if (ls->state == NW_LS_LAZY_ZERO)
+    if (int rc = materialize_zero(ls))
+      return rc;
+  cudaStream_t s = ls->mesh->ctx->stream;
+  const Graph& g = ls->g;
+  if (values)
+    NW_CUDA(cudaMemcpyAsync(
+      values, ls->dev.values,
+      sizeof(double) * (g.nnzOwned + g.nnzShared + ls->nExtra),
+      cudaMemcpyDeviceToHost, s));
+  if (rhs)
+    NW_CUDA(cudaMemcpyAsync(
+      rhs, ls->dev.rhs, sizeof(double) * g.numRowsLocal() * ls->nRhs,
+      cudaMemcpyDeviceToHost, s));
+  NW_CUDA(cudaStreamSynchronize(s));
+  return NW_OK;
+}
+
+extern "C" int
+nw_linsys_rhs_norm2(nw_linsys* ls, double* out)
+{
+  if (int rc = ls_ready(ls, "nw_linsys_rhs_norm2"))
+    return rc;
+  if (!out)
+    return fail(NW_ERR_ARG, "nw_linsys_rhs_norm2: NULL output");
+  if (ls->state == NW_LS_LAZY_ZERO)
+    if (int rc = materialize_zero(ls))
+      return rc;
+  cudaStream_t s = ls->mesh->ctx->stream;
+  NW_CUDA(launch_norm2(
+    ls->dev.rhs, ls->g.numRowsOwned, ls->dev.rhsStride, ls->nRhs,
+    ls->dNormPartial.as<double>(), 296, ls->dNormOut.as<double>(), s));
+  NW_CUDA(cudaMemcpyAsync(
+    out, ls->dNormOut.p, sizeof(double) * ls->nRhs, cudaMemcpyDeviceToHost, s));
+  NW_CUDA(cudaStreamSynchronize(s));
+  return NW_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/*  multi-rank halo (see nw_halo.cu)                                   */
+/* ------------------------------------------------------------------ */
+
+#include "nw_halo.inc"

@@ -1,0 +1,175 @@
+/*
+ * nw_internal.h -- handle definitions behind the opaque C-ABI types.
+ */
+#ifndef NW_INTERNAL_H
+#define NW_INTERNAL_H
+
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "nw_kernels.cuh"
+#include "plan.h"
+
+namespace nw {
+
+void set_error(const std::string& m);
+
+/* device buffer with RAII */
+struct DevBuf
+{
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes)
+  {
+    o.p = nullptr;
+    o.bytes = 0;
+  }
+  DevBuf& operator=(DevBuf&& o) noexcept
+  {
+    if (this != &o) {
+      release();
+      p = o.p;
+      bytes = o.bytes;
+      o.p = nullptr;
+      o.bytes = 0;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release()
+  {
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  cudaError_t alloc(size_t n)
+  {
+    release();
+    if (n == 0)
+      n = 16;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess)
+      bytes = n;
+    return e;
+  }
+  template <class T>
+  T* as() const
+  {
+    return static_cast<T*>(p);
+  }
+};
+
+/* NCCL, bound at run time (dlopen) so the library loads on hosts without it */
+struct NcclApi;
+struct Comm
+{
+  void* comm = nullptr; /* ncclComm_t */
+  int nranks = 1, rank = 0;
+};
+
+} // namespace nw
+
+struct nw_ctx
+{
+  int device = -1; /* < 0: host-only context (plan building, no compute) */
+  cudaStream_t stream = nullptr;
+  nw::Comm comm;
+};
+
+struct nw_field_t
+{
+  std::string name;
+  int rank = NW_NODE;
+  int ncomp = 1;
+  int64_t stride = 0; /* entities incl. padding */
+  nw::DevBuf buf;
+};
+
+/* neighbour exchange lists of one mesh (nodal fields) */
+struct nw_node_halo
+{
+  bool built = false;
+  std::vector<int> peers; /* ascending rank */
+  /* as a sharer: my non-owned nodes grouped by owner */
+  std::vector<std::vector<int32_t>> ghostSlots; /* per peer: internal slots */
+  std::vector<std::vector<int64_t>> ghostHids;  /* per peer: row ids sent */
+  /* as the owner: my owned nodes other ranks hold copies of */
+  std::vector<std::vector<int32_t>> ownedSlots; /* per peer */
+  std::vector<nw::DevBuf> dGhostIdx, dOwnedIdx; /* int64 slot lists */
+  nw::DevBuf sendBuf, recvBuf;
+};
+
+struct nw_mesh
+{
+  nw_ctx* ctx = nullptr;
+  nw::MeshPlan plan;
+  nw::MeshPlanDev dev;
+  nw::DevBuf dTiles, dHalo, dLr, dHeNode, dWarpNode, dPrimary, dNodeOfSlot,
+    dTileEdgeSrc, dPrimarySlot;
+  nw::DevBuf scratch; /* staging for field upload / download */
+  std::vector<std::unique_ptr<nw_field_t>> fields;
+  std::map<std::string, int> fieldByName;
+  nw_node_halo halo;
+  std::map<int64_t, int32_t> ownedNodeOfHid; /* own row id -> local node */
+  int64_t planBytes = 0;
+};
+
+enum nw_ls_state { NW_LS_UNSET = 0, NW_LS_LAZY_ZERO = 1, NW_LS_ACCUM = 2 };
+
+struct nw_linsys
+{
+  nw_mesh* mesh = nullptr;
+  int kind = NW_LINSYS_HYPRE;
+  int numDof = 1;
+  int nRhs = 1;
+  bool graphBuilt = false, finalized = false;
+  std::vector<int64_t> skipped;
+  nw::Graph g;
+  nw::LsPlan lp;
+  nw::LsPlanDev dev;
+  int mode = NW_SCATTER_SEGMENTED;
+  int state = NW_LS_UNSET;
+
+  nw::DevBuf dLsTiles, dEntInfo, dEntRhsRow, dHe, dWarp, dRuns;
+  nw::DevBuf dValues, dRhs;
+  nw::DevBuf dUncovered, dUncoveredPeriodic, dRowPtr;
+  nw::DevBuf dPeriodicRows;
+  /* atomic variant maps (lazy) */
+  bool atomicBuilt = false;
+  nw::DevBuf dASlots, dARhsRows;
+  /* device copy of the graph for nw_linsys_sum_into (lazy) */
+  bool devGraphBuilt = false;
+  nw::DevBuf dRowStartOwned, dRowStartShared, dRowIndicesShared, dCols,
+    dSkipped, dNodeHid;
+  nw::DevBuf dNormPartial, dNormOut;
+
+  /* shared-row halo (multi-rank) */
+  struct Peer
+  {
+    int rank = -1;
+    /* send: contiguous segment of my shared tail */
+    int64_t sendRow0 = 0, sendRows = 0, sendVal0 = 0, sendVals = 0;
+    /* recv: structure received at finalize, destination slots in my arrays */
+    std::vector<int64_t> recvRows, recvRowLens, recvCols;
+    std::vector<int64_t> recvValSlot, recvRhsRow;
+    nw::DevBuf dRecvValSlot, dRecvRhsRow;
+    int64_t recvVals = 0, recvNRows = 0;
+  };
+  std::vector<Peer> peers;
+  bool haloBuilt = false;
+  nw::DevBuf haloRecv;
+  /* columns received for owned rows that the local graph does not have:
+   * (row, col) pairs appended after the reference-layout arrays */
+  int64_t nExtra = 0;
+  std::vector<int64_t> extraRows, extraCols;
+};
+
+#endif

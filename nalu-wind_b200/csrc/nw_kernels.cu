@@ -1,0 +1,1622 @@
+/*
+ * nw_kernels.cu -- hand-written sm_100a kernels of the edge assembly path.
+ *
+ * Tile kernels (default, deterministic):  one CTA per locality tile.
+ *   stage : the tile's own node range of every SoA field component is pulled
+ *           into shared memory by TMA bulk copies (cp.async.bulk + mbarrier
+ *           complete_tx); the halo nodes of the tile are gathered by the
+ *           threads (they hit L2: neighbouring tiles run close in time);
+ *   phase1: one thread per tile-edge evaluates the edge physics from shared
+ *           memory (edge data is streamed coalesced from HBM) and leaves a
+ *           compact per-edge result in shared memory;
+ *   phase2: the tile's row-sorted half-edge list is reduced with a segmented
+ *           warp-shuffle scan; segment tails deposit diagonal / rhs sums into
+ *           the row staging buffer, every lane writes its own off-diagonal;
+ *   phase3: the staged rows are copied out in contiguous runs -- each matrix
+ *           value and rhs entry is written exactly once, no atomics, no
+ *           zero-fill pass (replaces resetCoeffApplierData's deep_copy(0) and
+ *           the column walk + atomic_add of sum_into,
+ *           src/HypreLinearSystem.C:1386-1430, 2165-2239).
+ * Atomic kernels (comparison variant): same tiles, direct global gathers,
+ *   warp-aggregated fp64 atomicAdd through a precomputed integer slot map.
+ */
+#include "nw_kernels.cuh"
+
+#include <stdint.h>
+
+#include "edge_physics.h"
+
+namespace nw {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+/* ------------------------------------------------------------------ */
+/*  TMA bulk copy + mbarrier (PTX)                                     */
+/* ------------------------------------------------------------------ */
+
+__device__ __forceinline__ uint32_t
+smem_u32(const void* p)
+{
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void
+mbar_init(uint64_t* bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(count)
+               : "memory");
+  /* make the initialised barrier visible to the async (TMA) proxy */
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void
+mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile(
+    "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+    "r"(bytes)
+    : "memory");
+}
+
+__device__ __forceinline__ void
+mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  } while (!done);
+}
+
+/* 1-D bulk copy global -> shared, completion signalled on an mbarrier.
+ * bytes % 16 == 0, both addresses 16-byte aligned.  SASS: UBLKCP. */
+__device__ __forceinline__ void
+tma_load_1d(void* dstSmem, const void* srcGmem, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile(
+    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+    "[%0], [%1], %2, [%3];" ::"r"(smem_u32(dstSmem)),
+    "l"(srcGmem), "r"(bytes), "r"(smem_u32(bar))
+    : "memory");
+}
+
+/* Stage NC node components of one tile: own range by TMA, halo by gather.
+ * s_node[c*stride + i]; i < nOwnPad own, nOwnPad + k halo k. */
+template <int NC>
+__device__ __forceinline__ void
+stage_nodes(
+  double* s_node,
+  int stride,
+  const NodeComps& nc,
+  const TileHdr& h,
+  const int32_t* __restrict__ haloNodes,
+  uint64_t* bar)
+{
+  if (threadIdx.x == 0)
+    mbar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = (uint32_t)h.nOwnPad * 8u;
+    mbar_expect_tx(bar, bytes * NC);
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      tma_load_1d(s_node + c * stride, nc.c[c] + h.node0, bytes, bar);
+  }
+  const int32_t* halo = haloNodes + h.haloPtr;
+  for (int k = threadIdx.x; k < h.nHalo; k += blockDim.x) {
+    const int32_t g = __ldg(halo + k);
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      s_node[c * stride + h.nOwnPad + k] = __ldg(nc.c[c] + g);
+  }
+  mbar_wait(bar, 0);
+  __syncthreads();
+}
+
+template <int NV>
+__device__ __forceinline__ void
+seg_scan(double (&v)[NV], uint32_t key, int lane)
+{
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t k2 = __shfl_up_sync(kFull, key, d);
+    const bool take = (lane >= d) && (k2 == key);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const double t = __shfl_up_sync(kFull, v[i], d);
+      if (take)
+        v[i] += t;
+    }
+  }
+}
+
+__device__ __forceinline__ bool
+seg_tail(uint32_t key, int lane)
+{
+  const uint32_t kn = __shfl_down_sync(kFull, key, 1);
+  return (lane == 31) || (kn != key);
+}
+
+__device__ __forceinline__ int
+even_up_i(int v)
+{
+  return (v + 1) & ~1;
+}
+
+/* ------------------------------------------------------------------ */
+/*  physics policies                                                   */
+/* ------------------------------------------------------------------ */
+
+/* A policy provides
+ *   NC    staged node components            NRES  doubles per edge result
+ *   NR    rhs columns                       Opts  option struct
+ *   compute(ld, l, r, av, mdot, pecfac, o, res)   phase 1
+ *   contrib(side, res, diag, off, rhs)            phase 2
+ * Node component order for each policy is fixed here and mirrored by
+ * nw_api.cu when it fills NodeComps. */
+
+template <int ND>
+struct ContinuityP
+{
+  static constexpr int NC = 3 * ND + 3; /* x, u, dpdx, rho, p, udiag */
+  static constexpr int NRES = 2;
+  static constexpr int NR = 1;
+  static constexpr bool kNeedsMdot = false;
+  static constexpr bool kNeedsPec = false;
+  using Opts = nw_continuity_opts;
+  template <class LD>
+  __device__ __forceinline__ static void
+  load(const LD& ld, int i, ContNode<ND>& n)
+  {
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      n.x[d] = ld(d, i);
+      n.u[d] = ld(ND + d, i);
+      n.g[d] = ld(2 * ND + d, i);
+    }
+    n.rho = ld(3 * ND, i);
+    n.p = ld(3 * ND + 1, i);
+    n.ud = ld(3 * ND + 2, i);
+  }
+  template <class LD>
+  __device__ __forceinline__ static void compute(
+    const LD& ld, int l, int r, const double* av, double, double,
+    const Opts& o, double* res)
+  {
+    ContNode<ND> L, R;
+    load(ld, l, L);
+    load(ld, r, R);
+    continuity_edge<ND>(L, R, av, o, res[0], res[1]);
+  }
+  __device__ __forceinline__ static void contrib(
+    uint32_t side, const double* res, double& diag, double& off, double* rhs)
+  {
+    diag = -res[0];
+    off = res[0];
+    rhs[0] = side ? res[1] : -res[1];
+  }
+  __device__ __forceinline__ static void block(
+    const double* res, double& LL, double& LR, double& RL, double& RR,
+    double* flux)
+  {
+    LL = -res[0];
+    LR = res[0];
+    RL = res[0];
+    RR = -res[0];
+    flux[0] = res[1];
+  }
+};
+
+template <int ND>
+struct ScalarP
+{
+  static constexpr int NC = 3 * ND + 3; /* x, vrtm, dqdx, q, rho, dflux */
+  static constexpr int NRES = 5;
+  static constexpr int NR = 1;
+  static constexpr bool kNeedsMdot = true;
+  static constexpr bool kNeedsPec = false;
+  using Opts = nw_scalar_opts;
+  template <class LD>
+  __device__ __forceinline__ static void
+  load(const LD& ld, int i, ScalNode<ND>& n)
+  {
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      n.x[d] = ld(d, i);
+      n.v[d] = ld(ND + d, i);
+      n.dq[d] = ld(2 * ND + d, i);
+    }
+    n.q = ld(3 * ND, i);
+    n.rho = ld(3 * ND + 1, i);
+    n.mu = ld(3 * ND + 2, i);
+  }
+  template <class LD>
+  __device__ __forceinline__ static void compute(
+    const LD& ld, int l, int r, const double* av, double mdot, double,
+    const Opts& o, double* res)
+  {
+    ScalNode<ND> L, R;
+    load(ld, l, L);
+    load(ld, r, R);
+    scalar_edge<ND>(L, R, av, mdot, o, res, res[4]);
+  }
+  __device__ __forceinline__ static void contrib(
+    uint32_t side, const double* res, double& diag, double& off, double* rhs)
+  {
+    diag = side ? res[3] : res[0];
+    off = side ? res[2] : res[1];
+    rhs[0] = side ? res[4] : -res[4];
+  }
+  __device__ __forceinline__ static void block(
+    const double* res, double& LL, double& LR, double& RL, double& RR,
+    double* flux)
+  {
+    LL = res[0];
+    LR = res[1];
+    RL = res[2];
+    RR = res[3];
+    flux[0] = res[4];
+  }
+};
+
+template <int ND>
+struct MomentumUvwP
+{
+  /* x, u, dudx, visc, rho, mask */
+  static constexpr int NC = 2 * ND + ND * ND + 3;
+  static constexpr int NRES = 4 + ND;
+  static constexpr int NR = ND;
+  static constexpr bool kNeedsMdot = true;
+  static constexpr bool kNeedsPec = true;
+  using Opts = nw_momentum_opts;
+  template <class LD>
+  __device__ __forceinline__ static void
+  load(const LD& ld, int i, MomNode<ND>& n)
+  {
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      n.x[d] = ld(d, i);
+      n.u[d] = ld(ND + d, i);
+    }
+#pragma unroll
+    for (int d = 0; d < ND * ND; ++d)
+      n.g[d] = ld(2 * ND + d, i);
+    n.mu = ld(2 * ND + ND * ND, i);
+    n.rho = ld(2 * ND + ND * ND + 1, i);
+    n.mask = ld(2 * ND + ND * ND + 2, i);
+  }
+  template <class LD>
+  __device__ __forceinline__ static void compute(
+    const LD& ld, int l, int r, const double* av, double mdot, double pecfac,
+    const Opts& o, double* res)
+  {
+    MomNode<ND> L, R;
+    load(ld, l, L);
+    load(ld, r, R);
+    if (o.fuse_peclet) {
+      /* MomentumEdgePecletAlg fused (src/edge_kernels/MomentumEdgePecletAlg.C:74-101) */
+      PecNode<ND> pl, pr;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        pl.x[d] = L.x[d];
+        pr.x[d] = R.x[d];
+        pl.v[d] = L.u[d];
+        pr.v[d] = R.u[d];
+      }
+      pl.rho = L.rho;
+      pr.rho = R.rho;
+      pl.mu = L.mu;
+      pr.mu = R.mu;
+      pecfac = peclet_eval(o.pf, peclet_number<ND>(pl, pr, o.pec_eps));
+    }
+    MomResult<ND> m;
+    momentum_edge<ND>(L, R, av, mdot, pecfac, o, m);
+    /* HypreUVWLinSysCoeffApplier keeps only the x-x entries
+     * (src/HypreUVWLinearSystem.C:738) */
+    momentum_block_entry<ND>(
+      m, av, o.relax_fac, 0, 0, res[0], res[1], res[2], res[3]);
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+      res[4 + d] = m.flux[d];
+  }
+  __device__ __forceinline__ static void contrib(
+    uint32_t side, const double* res, double& diag, double& off, double* rhs)
+  {
+    diag = side ? res[3] : res[0];
+    off = side ? res[2] : res[1];
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+      rhs[d] = side ? res[4 + d] : -res[4 + d];
+  }
+  __device__ __forceinline__ static void block(
+    const double* res, double& LL, double& LR, double& RL, double& RR,
+    double* flux)
+  {
+    LL = res[0];
+    LR = res[1];
+    RL = res[2];
+    RR = res[3];
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+      flux[d] = res[4 + d];
+  }
+};
+
+/* shared-memory loader */
+struct SmemLd
+{
+  const double* s;
+  int stride;
+  __device__ __forceinline__ double operator()(int c, int i) const
+  {
+    return s[c * stride + i];
+  }
+};
+/* global loader through the read-only path */
+struct GmemLd
+{
+  const NodeComps* nc;
+  __device__ __forceinline__ double operator()(int c, int i) const
+  {
+    return __ldg(nc->c[c] + i);
+  }
+};
+
+/* ------------------------------------------------------------------ */
+/*  linear-system tile kernel                                          */
+/* ------------------------------------------------------------------ */
+
+template <class P, int ND>
+__global__ void __launch_bounds__(kTileThreads) ls_tile_kernel(
+  const MeshPlanDev mp,
+  const LsPlanDev lp,
+  const NodeComps nc,
+  const EdgeComps ec,
+  const typename P::Opts o)
+{
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t bar;
+
+  const TileHdr h = mp.tiles[blockIdx.x];
+  const LsTileHdr lh = lp.tiles[blockIdx.x];
+  const int stride = even_up_i(h.nOwnPad + h.nHalo);
+  const int resStride = even_up_i(mp.maxTileEdges);
+  const int entStride = even_up_i(lp.maxTileEnts);
+
+  double* s_node = smem;
+  double* s_res = s_node + (size_t)P::NC * mp.maxStaged;
+  double* s_vals = s_res + (size_t)P::NRES * resStride;
+  double* s_rhs = s_vals + even_up_i(lp.maxTileNnz);
+
+  stage_nodes<P::NC>(s_node, stride, nc, h, mp.haloNodes, &bar);
+
+  /* zero the row staging (diagonal and rhs are accumulated by segment tails) */
+  for (int i = threadIdx.x; i < lh.nnz; i += blockDim.x)
+    s_vals[i] = 0.0;
+  for (int i = threadIdx.x; i < P::NR * entStride; i += blockDim.x)
+    s_rhs[i] = 0.0;
+
+  /* ---- phase 1: per-edge physics ---- */
+  {
+    const SmemLd ld{s_node, stride};
+    const uint32_t* lr = mp.lr + h.edge0;
+    for (int j = threadIdx.x; j < h.nEdges; j += blockDim.x) {
+      const uint32_t v = __ldg(lr + j);
+      const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
+      double av[ND];
+#pragma unroll
+      for (int d = 0; d < ND; ++d)
+        av[d] = __ldg(ec.area[d] + h.edge0 + j);
+      double mdot = 0.0, pecfac = 0.0;
+      if (P::kNeedsMdot)
+        mdot = __ldg(ec.mdot + h.edge0 + j);
+      if (P::kNeedsPec && ec.pecfac)
+        pecfac = __ldg(ec.pecfac + h.edge0 + j);
+      double res[P::NRES];
+      P::compute(ld, l, r, av, mdot, pecfac, o, res);
+#pragma unroll
+      for (int k = 0; k < P::NRES; ++k)
+        s_res[k * resStride + j] = res[k];
+    }
+  }
+  __syncthreads();
+
+  /* ---- phase 2: row-sorted segmented reduction ---- */
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int32_t* split = lp.warpSplit + lh.warpPtr;
+    const int ws = __ldg(split + warp), we = __ldg(split + warp + 1);
+    const uint32_t* he = lp.he + lh.hePtr;
+    const EntInfo* ents = lp.entInfo + lh.entPtr;
+    for (int base = ws; base < we; base += 32) {
+      const int idx = base + lane;
+      const bool valid = idx < we;
+      const uint32_t hv = valid ? __ldg(he + idx) : 0u;
+      const uint32_t ent = he_ent(hv);
+      const uint32_t key = valid ? ent : 0xffffffffu;
+      double acc[1 + P::NR];
+      double off = 0.0;
+      EntInfo ei;
+      ei.base = 0;
+      ei.diagK = 0;
+      ei.nnz = 0;
+      if (valid) {
+        const int j = (int)he_edge(hv);
+        double res[P::NRES];
+#pragma unroll
+        for (int k = 0; k < P::NRES; ++k)
+          res[k] = s_res[k * resStride + j];
+        P::contrib(he_side(hv), res, acc[0], off, &acc[1]);
+        ei = ents[ent];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 1 + P::NR; ++k)
+          acc[k] = 0.0;
+      }
+      seg_scan<1 + P::NR>(acc, key, lane);
+      const bool tail = seg_tail(key, lane);
+      if (valid) {
+        if (hv & kHeDup)
+          atomicAdd(&s_vals[ei.base + he_k(hv)], off);
+        else
+          s_vals[ei.base + he_k(hv)] = off;
+        if (tail) {
+          s_vals[ei.base + ei.diagK] += acc[0];
+#pragma unroll
+          for (int d = 0; d < P::NR; ++d)
+            s_rhs[d * entStride + ent] += acc[1 + d];
+        }
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  /* ---- phase 3: copy-out, every value written exactly once ---- */
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Run* runs = lp.runs + lh.runPtr;
+    for (int q = warp; q < lh.nRuns; q += kTileThreads / 32) {
+      const Run rn = runs[q];
+      double* dst = lp.values + rn.go;
+      for (int k = lane; k < rn.len; k += 32)
+        dst[k] = s_vals[rn.so + k];
+    }
+    const int32_t* rows = lp.entRhsRow + lh.entPtr;
+    for (int i = threadIdx.x; i < lh.nEnts; i += blockDim.x) {
+      const int64_t row = __ldg(rows + i);
+#pragma unroll
+      for (int d = 0; d < P::NR; ++d)
+        lp.rhs[(int64_t)d * lp.rhsStride + row] = s_rhs[d * entStride + i];
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/*  linear-system atomic kernel (comparison variant)                   */
+/* ------------------------------------------------------------------ */
+
+__device__ __forceinline__ int
+global_slot(const TileHdr& h, const int32_t* haloNodes, int local)
+{
+  return local < h.nOwnPad ? h.node0 + local
+                           : __ldg(haloNodes + h.haloPtr + (local - h.nOwnPad));
+}
+
+template <class P, int ND>
+__global__ void __launch_bounds__(kTileThreads) ls_atomic_kernel(
+  const MeshPlanDev mp,
+  const LsPlanDev lp,
+  const AtomicMapDev am,
+  const NodeComps nc,
+  const EdgeComps ec,
+  const typename P::Opts o,
+  double* diagOut)
+{
+  const TileHdr h = mp.tiles[blockIdx.x];
+  const GmemLd ld{&nc};
+  const int lane = threadIdx.x & 31;
+  const int nIter = (h.nEdges + blockDim.x - 1) / blockDim.x;
+  for (int it = 0; it < nIter; ++it) {
+    const int j = it * blockDim.x + threadIdx.x;
+    const int64_t es = (int64_t)h.edge0 + j;
+    const bool valid = (j < h.nEdges) && mp.primary[es];
+    double LL = 0, LR = 0, RL = 0, RR = 0;
+    double flux[P::NR];
+#pragma unroll
+    for (int d = 0; d < P::NR; ++d)
+      flux[d] = 0.0;
+    int sLL = -1, sLR = -1, sRL = -1, sRR = -1, rowL = -1, rowR = -1;
+    int gl = 0, gr = 0;
+    if (valid) {
+      const uint32_t v = __ldg(mp.lr + es);
+      gl = global_slot(h, mp.haloNodes, (int)(v & 0xffffu));
+      gr = global_slot(h, mp.haloNodes, (int)(v >> 16));
+      double av[ND];
+#pragma unroll
+      for (int d = 0; d < ND; ++d)
+        av[d] = __ldg(ec.area[d] + es);
+      double mdot = 0.0, pecfac = 0.0;
+      if (P::kNeedsMdot)
+        mdot = __ldg(ec.mdot + es);
+      if (P::kNeedsPec && ec.pecfac)
+        pecfac = __ldg(ec.pecfac + es);
+      double res[P::NRES];
+      P::compute(ld, gl, gr, av, mdot, pecfac, o, res);
+      P::block(res, LL, LR, RL, RR, flux);
+      const int4 s4 = __ldg(reinterpret_cast<const int4*>(am.slots) + es);
+      sLL = s4.x;
+      sLR = s4.y;
+      sRL = s4.z;
+      sRR = s4.w;
+      const int2 r2 = __ldg(reinterpret_cast<const int2*>(am.rhsRows) + es);
+      rowL = r2.x;
+      rowR = r2.y;
+    }
+    /* warp aggregation of the L-row sums: tile-edges are sorted by L node, so
+     * lanes hitting the same diagonal slot are adjacent */
+    double acc[1 + P::NR];
+    acc[0] = LL;
+#pragma unroll
+    for (int d = 0; d < P::NR; ++d)
+      acc[1 + d] = -flux[d];
+    const uint32_t key = (uint32_t)sLL;
+    seg_scan<1 + P::NR>(acc, key, lane);
+    const bool tail = seg_tail(key, lane);
+    if (valid) {
+      if (tail && sLL >= 0) {
+        atomicAdd(lp.values + sLL, acc[0]);
+#pragma unroll
+        for (int d = 0; d < P::NR; ++d)
+          atomicAdd(lp.rhs + (int64_t)d * lp.rhsStride + rowL, acc[1 + d]);
+      }
+      if (sLR >= 0)
+        atomicAdd(lp.values + sLR, LR);
+      if (sRL >= 0)
+        atomicAdd(lp.values + sRL, RL);
+      if (sRR >= 0) {
+        atomicAdd(lp.values + sRR, RR);
+#pragma unroll
+        for (int d = 0; d < P::NR; ++d)
+          atomicAdd(lp.rhs + (int64_t)d * lp.rhsStride + rowR, flux[d]);
+      }
+      if (diagOut) {
+        /* NGPApplyCoeff::extract_diagonal (src/SolverAlgorithm.C:87-105) */
+        atomicAdd(diagOut + gl, LL);
+        atomicAdd(diagOut + gr, RR);
+      }
+    }
+  }
+}
+
+/* monolithic momentum: full 2ND x 2ND block through the slot map */
+template <int ND>
+__global__ void __launch_bounds__(kTileThreads) momentum_mono_atomic_kernel(
+  const MeshPlanDev mp,
+  const int32_t* __restrict__ slots,
+  const int32_t* __restrict__ rhsRows,
+  double* values,
+  double* rhs,
+  const NodeComps nc,
+  const EdgeComps ec,
+  const nw_momentum_opts o,
+  double* diagOut)
+{
+  using P = MomentumUvwP<ND>;
+  constexpr int NB = 2 * ND;
+  const TileHdr h = mp.tiles[blockIdx.x];
+  const GmemLd ld{&nc};
+  for (int j = threadIdx.x; j < h.nEdges; j += blockDim.x) {
+    const int64_t es = (int64_t)h.edge0 + j;
+    if (!mp.primary[es])
+      continue;
+    const uint32_t v = __ldg(mp.lr + es);
+    const int gl = global_slot(h, mp.haloNodes, (int)(v & 0xffffu));
+    const int gr = global_slot(h, mp.haloNodes, (int)(v >> 16));
+    double av[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+      av[d] = __ldg(ec.area[d] + es);
+    const double mdot = __ldg(ec.mdot + es);
+    double pecfac = ec.pecfac ? __ldg(ec.pecfac + es) : 0.0;
+    MomNode<ND> L, R;
+    P::load(ld, gl, L);
+    P::load(ld, gr, R);
+    if (o.fuse_peclet) {
+      PecNode<ND> pl, pr;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        pl.x[d] = L.x[d];
+        pr.x[d] = R.x[d];
+        pl.v[d] = L.u[d];
+        pr.v[d] = R.u[d];
+      }
+      pl.rho = L.rho;
+      pr.rho = R.rho;
+      pl.mu = L.mu;
+      pr.mu = R.mu;
+      pecfac = peclet_eval(o.pf, peclet_number<ND>(pl, pr, o.pec_eps));
+    }
+    MomResult<ND> m;
+    momentum_edge<ND>(L, R, av, mdot, pecfac, o, m);
+    const int32_t* sl = slots + es * (NB * NB);
+    const int32_t* rr = rhsRows + es * NB;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) {
+#pragma unroll
+      for (int jj = 0; jj < ND; ++jj) {
+        double LL, LR, RL, RR;
+        momentum_block_entry<ND>(m, av, o.relax_fac, i, jj, LL, LR, RL, RR);
+        const int a = sl[i * NB + jj], b = sl[i * NB + ND + jj];
+        const int c = sl[(ND + i) * NB + jj], d = sl[(ND + i) * NB + ND + jj];
+        if (a >= 0)
+          atomicAdd(values + a, LL);
+        if (b >= 0)
+          atomicAdd(values + b, LR);
+        if (c >= 0)
+          atomicAdd(values + c, RL);
+        if (d >= 0)
+          atomicAdd(values + d, RR);
+        if (diagOut && i == 0 && jj == 0) {
+          atomicAdd(diagOut + gl, LL);
+          atomicAdd(diagOut + gr, RR);
+        }
+      }
+      if (rr[i] >= 0)
+        atomicAdd(rhs + rr[i], -m.flux[i]);
+      if (rr[ND + i] >= 0)
+        atomicAdd(rhs + rr[ND + i], m.flux[i]);
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/*  mdot / peclet tile kernels (no reduction)                          */
+/* ------------------------------------------------------------------ */
+
+template <int ND>
+__global__ void __launch_bounds__(kTileThreads) mdot_tile_kernel(
+  const MeshPlanDev mp,
+  const NodeComps nc,
+  const EdgeComps ec,
+  double* __restrict__ mdotOut,
+  const nw_mdot_opts o)
+{
+  using P = ContinuityP<ND>;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const TileHdr h = mp.tiles[blockIdx.x];
+  const int stride = even_up_i(h.nOwnPad + h.nHalo);
+  stage_nodes<P::NC>(smem, stride, nc, h, mp.haloNodes, &bar);
+  const SmemLd ld{smem, stride};
+  const uint32_t* lr = mp.lr + h.edge0;
+  for (int j = threadIdx.x; j < h.nEdges; j += blockDim.x) {
+    const uint32_t v = __ldg(lr + j);
+    const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
+    double av[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+      av[d] = __ldg(ec.area[d] + h.edge0 + j);
+    ContNode<ND> L, R;
+    P::load(ld, l, L);
+    P::load(ld, r, R);
+    const MdotCore<ND> c =
+      mdot_core<ND>(L, R, av, o.noc_fac, o.interp_together);
+    mdotOut[h.edge0 + j] = c.tmdot;
+  }
+}
+
+template <int ND>
+__global__ void __launch_bounds__(kTileThreads) peclet_tile_kernel(
+  const MeshPlanDev mp,
+  const NodeComps nc, /* x, v, rho, mu */
+  double* __restrict__ pecfacOut,
+  const nw_peclet_opts o)
+{
+  constexpr int NC = 2 * ND + 2;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const TileHdr h = mp.tiles[blockIdx.x];
+  const int stride = even_up_i(h.nOwnPad + h.nHalo);
+  stage_nodes<NC>(smem, stride, nc, h, mp.haloNodes, &bar);
+  const SmemLd ld{smem, stride};
+  const uint32_t* lr = mp.lr + h.edge0;
+  for (int j = threadIdx.x; j < h.nEdges; j += blockDim.x) {
+    const uint32_t v = __ldg(lr + j);
+    const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
+    PecNode<ND> L, R;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      L.x[d] = ld(d, l);
+      R.x[d] = ld(d, r);
+      L.v[d] = ld(ND + d, l);
+      R.v[d] = ld(ND + d, r);
+    }
+    L.rho = ld(2 * ND, l);
+    R.rho = ld(2 * ND, r);
+    L.mu = ld(2 * ND + 1, l);
+    R.mu = ld(2 * ND + 1, r);
+    pecfacOut[h.edge0 + j] = peclet_eval(o.pf, peclet_number<ND>(L, R, o.eps));
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/*  nodal gradient                                                     */
+/* ------------------------------------------------------------------ */
+
+struct GradOut
+{
+  double* c[9];
+};
+
+/* NodalGradEdgeAlg (src/ngp_algorithms/NodalGradEdgeAlg.C:85-109) with the
+ * zero-fill of NodalGradAlgDriver::pre_work fused: every owned node's
+ * gradient is written once. */
+template <int D1, int ND>
+__global__ void __launch_bounds__(kTileThreads) grad_tile_kernel(
+  const MeshPlanDev mp,
+  const NodeComps phi,
+  const double* __restrict__ dualVol,
+  const EdgeComps ec,
+  const GradOut out)
+{
+  constexpr int NV = D1 * ND;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const TileHdr h = mp.tiles[blockIdx.x];
+  const int stride = even_up_i(h.nOwnPad + h.nHalo);
+  const int outStride = even_up_i(mp.maxTileNodes);
+  double* s_phi = smem;
+  double* s_out = smem + (size_t)D1 * mp.maxStaged;
+  stage_nodes<D1>(s_phi, stride, phi, h, mp.haloNodes, &bar);
+  for (int i = threadIdx.x; i < NV * outStride; i += blockDim.x)
+    s_out[i] = 0.0;
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int32_t* split = mp.warpSplitNode + h.warpPtrNode;
+  const int ws = __ldg(split + warp), we = __ldg(split + warp + 1);
+  const uint32_t* he = mp.heNode + h.hePtrNode;
+  for (int base = ws; base < we; base += 32) {
+    const int idx = base + lane;
+    const bool valid = idx < we;
+    const uint32_t hv = valid ? __ldg(he + idx) : 0u;
+    const uint32_t ent = he_ent(hv);
+    const uint32_t key = valid ? ent : 0xffffffffu;
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      acc[k] = 0.0;
+    if (valid) {
+      const int j = (int)he_edge(hv);
+      const uint32_t v = __ldg(mp.lr + h.edge0 + j);
+      const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
+      const double invVol = 1.0 / __ldg(dualVol + h.node0 + ent);
+      const double sgn = he_side(hv) ? -1.0 : 1.0;
+      double av[ND];
+#pragma unroll
+      for (int d = 0; d < ND; ++d)
+        av[d] = __ldg(ec.area[d] + h.edge0 + j);
+#pragma unroll
+      for (int i = 0; i < D1; ++i) {
+        const double phiIp = 0.5 * (s_phi[i * stride + l] + s_phi[i * stride + r]);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+          const double ajPhiIp = av[d] * phiIp;
+          acc[i * ND + d] = sgn * (ajPhiIp * invVol);
+        }
+      }
+    }
+    seg_scan<NV>(acc, key, lane);
+    if (valid && seg_tail(key, lane)) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+        s_out[k * outStride + ent] += acc[k];
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < h.nOwn; i += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      out.c[k][h.node0 + i] = s_out[k * outStride + i];
+  }
+}
+
+/* atomic comparison variant: grad must be zeroed beforehand */
+template <int D1, int ND>
+__global__ void __launch_bounds__(kTileThreads) grad_atomic_kernel(
+  const MeshPlanDev mp,
+  const NodeComps phi,
+  const double* __restrict__ dualVol,
+  const EdgeComps ec,
+  const GradOut out)
+{
+  const TileHdr h = mp.tiles[blockIdx.x];
+  for (int j = threadIdx.x; j < h.nEdges; j += blockDim.x) {
+    const int64_t es = (int64_t)h.edge0 + j;
+    if (!mp.primary[es])
+      continue;
+    const uint32_t v = __ldg(mp.lr + es);
+    const int gl = global_slot(h, mp.haloNodes, (int)(v & 0xffffu));
+    const int gr = global_slot(h, mp.haloNodes, (int)(v >> 16));
+    const double invVolL = 1.0 / __ldg(dualVol + gl);
+    const double invVolR = 1.0 / __ldg(dualVol + gr);
+#pragma unroll
+    for (int i = 0; i < D1; ++i) {
+      const double phiIp = 0.5 * (__ldg(phi.c[i] + gl) + __ldg(phi.c[i] + gr));
+#pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        const double ajPhiIp = __ldg(ec.area[d] + es) * phiIp;
+        atomicAdd(out.c[i * ND + d] + gl, ajPhiIp * invVolL);
+        atomicAdd(out.c[i * ND + d] + gr, -(ajPhiIp * invVolR));
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/*  utility kernels                                                    */
+/* ------------------------------------------------------------------ */
+
+__global__ void
+node_gather_kernel(
+  const double* __restrict__ src,
+  int ncomp,
+  const int32_t* __restrict__ nodeOfSlot,
+  int64_t nSlots,
+  double* __restrict__ dst)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nSlots)
+    return;
+  const int32_t n = nodeOfSlot[i];
+  for (int c = 0; c < ncomp; ++c)
+    dst[(int64_t)c * nSlots + i] = (n >= 0) ? src[(int64_t)n * ncomp + c] : 0.0;
+}
+
+__global__ void
+node_scatter_kernel(
+  const double* __restrict__ src,
+  int ncomp,
+  const int32_t* __restrict__ nodeOfSlot,
+  int64_t nSlots,
+  double* __restrict__ dst)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nSlots)
+    return;
+  const int32_t n = nodeOfSlot[i];
+  if (n < 0)
+    return;
+  for (int c = 0; c < ncomp; ++c)
+    dst[(int64_t)n * ncomp + c] = src[(int64_t)c * nSlots + i];
+}
+
+__global__ void
+edge_scatter_kernel(
+  const double* __restrict__ src,
+  int ncomp,
+  const int32_t* __restrict__ primarySlot,
+  int64_t nEdges,
+  int64_t slotStride,
+  double* __restrict__ dst)
+{
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nEdges)
+    return;
+  const int32_t s = primarySlot[e];
+  for (int c = 0; c < ncomp; ++c)
+    dst[e * ncomp + c] = src[(int64_t)c * slotStride + s];
+}
+
+__global__ void
+fill_kernel(double* p, int64_t n, double v)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    p[i] = v;
+}
+
+__global__ void
+row_init_kernel(
+  const int32_t* __restrict__ rows,
+  int nRows,
+  const int64_t* __restrict__ rowPtr,
+  const uint8_t* __restrict__ isPeriodic,
+  double* values,
+  double* rhs,
+  int64_t rhsStride,
+  int nRhs)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nRows)
+    return;
+  const int32_t r = rows[i];
+  const int64_t a = rowPtr[r], b = rowPtr[r + 1];
+  for (int64_t k = a; k < b; ++k)
+    values[k] = 0.0;
+  if (isPeriodic[i])
+    values[a] = 1.0;
+  for (int d = 0; d < nRhs; ++d)
+    rhs[(int64_t)d * rhsStride + r] = 0.0;
+}
+
+/* fixed-shape two-level reduction: deterministic for a given (n, nPartial) */
+__global__ void __launch_bounds__(256) norm2_partial_kernel(
+  const double* __restrict__ rhs, int64_t n, int64_t stride, double* partial)
+{
+  __shared__ double sm[256];
+  const int d = blockIdx.y;
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t a = (int64_t)blockIdx.x * per;
+  const int64_t b = a + per < n ? a + per : n;
+  double s = 0.0;
+  for (int64_t i = a + threadIdx.x; i < b; i += 256) {
+    const double v = rhs[(int64_t)d * stride + i];
+    s += v * v;
+  }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w)
+      sm[threadIdx.x] += sm[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    partial[(int64_t)d * gridDim.x + blockIdx.x] = sm[0];
+}
+
+__global__ void __launch_bounds__(256)
+norm2_final_kernel(const double* __restrict__ partial, int nPartial, double* out)
+{
+  __shared__ double sm[256];
+  const int d = blockIdx.x;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nPartial; i += 256)
+    s += partial[(int64_t)d * nPartial + i];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w)
+      sm[threadIdx.x] += sm[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    out[d] = sm[0];
+}
+
+__device__ __forceinline__ int64_t
+lower_bound_dev(const int64_t* a, int64_t n, int64_t v)
+{
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (a[mid] < v)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+/* Generic CoeffApplier::operator() (include/LinearSystem.h:62-70): one thread
+ * per entity; the reference's sort + linear column walk becomes a binary
+ * search per entry (same destination, see tests/test_graph_parity.py). */
+__global__ void
+sum_into_kernel(
+  int64_t nEnt,
+  int npe,
+  int numDof,
+  const int32_t* __restrict__ entNodes,
+  const int64_t* __restrict__ nodeHid,
+  const double* __restrict__ lhs,
+  const double* __restrict__ rhsIn,
+  int64_t iLower,
+  int64_t iUpper,
+  int64_t nRowsOwned,
+  int64_t nnzOwned,
+  const int64_t* __restrict__ rowStartOwned,
+  const int64_t* __restrict__ rowStartShared,
+  const int64_t* __restrict__ rowIndicesShared,
+  int64_t nRowsShared,
+  const int64_t* __restrict__ cols,
+  const int64_t* __restrict__ skipped,
+  int64_t nSkipped,
+  int uvwDim,
+  double* values,
+  double* rhs,
+  int64_t rhsStride)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nEnt)
+    return;
+  const int ld = uvwDim > 0 ? uvwDim : numDof; /* dofs per node in lhs/rhs */
+  const int n = npe * ld;
+  const double* L = lhs + t * (int64_t)n * n;
+  const double* R = rhsIn + t * (int64_t)n;
+  for (int i = 0; i < npe; ++i) {
+    const int64_t hid = nodeHid[entNodes[t * npe + i]];
+    const int64_t first = hid * numDof;
+    if (nSkipped) {
+      const int64_t p = lower_bound_dev(skipped, nSkipped, first);
+      if (p < nSkipped && skipped[p] == first)
+        continue;
+    }
+    for (int d = 0; d < numDof; ++d) {
+      const int64_t row = first + d;
+      int64_t base, len, lrow;
+      if (row >= iLower && row <= iUpper) {
+        lrow = row - iLower;
+        base = rowStartOwned[lrow];
+        len = rowStartOwned[lrow + 1] - base;
+      } else {
+        const int64_t p = lower_bound_dev(rowIndicesShared, nRowsShared, row);
+        if (p >= nRowsShared || rowIndicesShared[p] != row)
+          continue;
+        lrow = nRowsOwned + p;
+        base = nnzOwned + rowStartShared[p];
+        len = rowStartShared[p + 1] - rowStartShared[p];
+      }
+      const int ii = uvwDim > 0 ? i * uvwDim : i * numDof + d;
+      for (int k = 0; k < npe; ++k) {
+        const int64_t hk = nodeHid[entNodes[t * npe + k]];
+        for (int dd = 0; dd < numDof; ++dd) {
+          const int64_t col = hk * numDof + dd;
+          const int64_t p = lower_bound_dev(cols + base, len, col);
+          if (p < len && cols[base + p] == col) {
+            const int kk = uvwDim > 0 ? k * uvwDim : k * numDof + dd;
+            atomicAdd(values + base + p, L[ii * n + kk]);
+          }
+        }
+      }
+      if (uvwDim > 0) {
+        for (int q = 0; q < uvwDim; ++q)
+          atomicAdd(rhs + (int64_t)q * rhsStride + lrow, R[ii + q]);
+      } else
+        atomicAdd(rhs + lrow, R[ii]);
+    }
+  }
+}
+
+__global__ void
+pack_kernel(
+  const double* __restrict__ src,
+  const int64_t* __restrict__ idx,
+  int64_t n,
+  double* __restrict__ dst)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    dst[i] = src[idx[i]];
+}
+
+/* idx entries are unique within one call (one slot per received entry of one
+ * neighbour), so a plain read-modify-write is race-free and the sum order is
+ * the fixed neighbour order of the caller */
+__global__ void
+unpack_add_kernel(
+  const double* __restrict__ src,
+  const int64_t* __restrict__ idx,
+  int64_t n,
+  double* dst)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && idx[i] >= 0)
+    dst[idx[i]] += src[i];
+}
+
+__global__ void
+scatter_assign_kernel(
+  const double* __restrict__ src,
+  const int64_t* __restrict__ idx,
+  int64_t n,
+  double* dst)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && idx[i] >= 0)
+    dst[idx[i]] = src[i];
+}
+
+template <class K>
+cudaError_t
+set_smem(K kernel, size_t bytes)
+{
+  if (bytes > 48 * 1024)
+    return cudaFuncSetAttribute(
+      kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return cudaSuccess;
+}
+
+inline int
+even_up_h(int v)
+{
+  return (v + 1) & ~1;
+}
+
+template <class P>
+size_t
+ls_tile_smem(const MeshPlanDev& mp, const LsPlanDev& lp)
+{
+  return sizeof(double) *
+         ((size_t)P::NC * mp.maxStaged +
+          (size_t)P::NRES * even_up_h(mp.maxTileEdges) +
+          (size_t)even_up_h(lp.maxTileNnz) +
+          (size_t)P::NR * even_up_h(lp.maxTileEnts));
+}
+
+template <class P, int ND>
+cudaError_t
+launch_ls_tile(
+  const MeshPlanDev& mp,
+  const LsPlanDev& lp,
+  const NodeComps& nc,
+  const EdgeComps& ec,
+  const typename P::Opts& o,
+  cudaStream_t s)
+{
+  const size_t bytes = ls_tile_smem<P>(mp, lp);
+  if (bytes > 227 * 1024)
+    return cudaErrorInvalidConfiguration;
+  cudaError_t e = set_smem(ls_tile_kernel<P, ND>, bytes);
+  if (e != cudaSuccess)
+    return e;
+  ls_tile_kernel<P, ND><<<mp.nTiles, kTileThreads, bytes, s>>>(mp, lp, nc, ec, o);
+  return cudaGetLastError();
+}
+
+template <class P, int ND>
+cudaError_t
+launch_ls_atomic(
+  const MeshPlanDev& mp,
+  const LsPlanDev& lp,
+  const AtomicMapDev& am,
+  const NodeComps& nc,
+  const EdgeComps& ec,
+  const typename P::Opts& o,
+  double* diagOut,
+  cudaStream_t s)
+{
+  ls_atomic_kernel<P, ND>
+    <<<mp.nTiles, kTileThreads, 0, s>>>(mp, lp, am, nc, ec, o, diagOut);
+  return cudaGetLastError();
+}
+
+inline int
+blocks_for(int64_t n, int bs)
+{
+  return (int)((n + bs - 1) / bs);
+}
+
+} // namespace
+
+/* ------------------------------------------------------------------ */
+/*  launchers                                                          */
+/* ------------------------------------------------------------------ */
+
+cudaError_t
+launch_mdot_tile(
+  const MeshPlanDev& mp,
+  const NodeComps& nc,
+  const EdgeComps& ec,
+  double* mdotOut,
+  nw_mdot_opts o,
+  cudaStream_t s)
+{
+  cudaError_t e;
+  if (mp.ndim == 3) {
+    const size_t bytes = sizeof(double) * ContinuityP<3>::NC * mp.maxStaged;
+    if ((e = set_smem(mdot_tile_kernel<3>, bytes)) != cudaSuccess)
+      return e;
+    mdot_tile_kernel<3>
+      <<<mp.nTiles, kTileThreads, bytes, s>>>(mp, nc, ec, mdotOut, o);
+  } else {
+    const size_t bytes = sizeof(double) * ContinuityP<2>::NC * mp.maxStaged;
+    if ((e = set_smem(mdot_tile_kernel<2>, bytes)) != cudaSuccess)
+      return e;
+    mdot_tile_kernel<2>
+      <<<mp.nTiles, kTileThreads, bytes, s>>>(mp, nc, ec, mdotOut, o);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_peclet_tile(
+  const MeshPlanDev& mp,
+  const NodeComps& nc,
+  double* pecfacOut,
+  nw_peclet_opts o,
+  cudaStream_t s)
+{
+  cudaError_t e;
+  if (mp.ndim == 3) {
+    const size_t bytes = sizeof(double) * 8 * mp.maxStaged;
+    if ((e = set_smem(peclet_tile_kernel<3>, bytes)) != cudaSuccess)
+      return e;
+    peclet_tile_kernel<3>
+      <<<mp.nTiles, kTileThreads, bytes, s>>>(mp, nc, pecfacOut, o);
+  } else {
+    const size_t bytes = sizeof(double) * 6 * mp.maxStaged;
+    if ((e = set_smem(peclet_tile_kernel<2>, bytes)) != cudaSuccess)
+      return e;
+    peclet_tile_kernel<2>
+      <<<mp.nTiles, kTileThreads, bytes, s>>>(mp, nc, pecfacOut, o);
+  }
+  return cudaGetLastError();
+}
+
+namespace {
+template <int D1, int ND>
+cudaError_t
+launch_grad_tile_t(
+  const MeshPlanDev& mp,
+  const NodeComps& phi,
+  const double* dualVol,
+  const EdgeComps& ec,
+  double* const* gradOut,
+  cudaStream_t s)
+{
+  GradOut go;
+  for (int k = 0; k < D1 * ND; ++k)
+    go.c[k] = gradOut[k];
+  const size_t bytes =
+    sizeof(double) * ((size_t)D1 * mp.maxStaged +
+                      (size_t)D1 * ND * even_up_h(mp.maxTileNodes));
+  cudaError_t e = set_smem(grad_tile_kernel<D1, ND>, bytes);
+  if (e != cudaSuccess)
+    return e;
+  grad_tile_kernel<D1, ND>
+    <<<mp.nTiles, kTileThreads, bytes, s>>>(mp, phi, dualVol, ec, go);
+  return cudaGetLastError();
+}
+template <int D1, int ND>
+cudaError_t
+launch_grad_atomic_t(
+  const MeshPlanDev& mp,
+  const NodeComps& phi,
+  const double* dualVol,
+  const EdgeComps& ec,
+  double* const* gradOut,
+  cudaStream_t s)
+{
+  GradOut go;
+  for (int k = 0; k < D1 * ND; ++k)
+    go.c[k] = gradOut[k];
+  grad_atomic_kernel<D1, ND>
+    <<<mp.nTiles, kTileThreads, 0, s>>>(mp, phi, dualVol, ec, go);
+  return cudaGetLastError();
+}
+} // namespace
+
+cudaError_t
+launch_grad_tile(
+  const MeshPlanDev& mp,
+  int dim1,
+  const NodeComps& phi,
+  const double* dualVol,
+  const EdgeComps& ec,
+  double* const* gradOut,
+  cudaStream_t s)
+{
+  if (mp.ndim == 3)
+    return dim1 == 1
+             ? launch_grad_tile_t<1, 3>(mp, phi, dualVol, ec, gradOut, s)
+             : launch_grad_tile_t<3, 3>(mp, phi, dualVol, ec, gradOut, s);
+  return dim1 == 1 ? launch_grad_tile_t<1, 2>(mp, phi, dualVol, ec, gradOut, s)
+                   : launch_grad_tile_t<2, 2>(mp, phi, dualVol, ec, gradOut, s);
+}
+
+cudaError_t
+launch_grad_atomic(
+  const MeshPlanDev& mp,
+  int dim1,
+  const NodeComps& phi,
+  const double* dualVol,
+  const EdgeComps& ec,
+  double* const* gradOut,
+  cudaStream_t s)
+{
+  if (mp.ndim == 3)
+    return dim1 == 1
+             ? launch_grad_atomic_t<1, 3>(mp, phi, dualVol, ec, gradOut, s)
+             : launch_grad_atomic_t<3, 3>(mp, phi, dualVol, ec, gradOut, s);
+  return dim1 == 1
+           ? launch_grad_atomic_t<1, 2>(mp, phi, dualVol, ec, gradOut, s)
+           : launch_grad_atomic_t<2, 2>(mp, phi, dualVol, ec, gradOut, s);
+}
+
+cudaError_t
+launch_continuity_tile(
+  const MeshPlanDev& mp,
+  const LsPlanDev& lp,
+  const NodeComps& nc,
+  const EdgeComps& ec,
+  nw_continuity_opts o,
+  cudaStream_t s)
+{
+  return mp.ndim == 3
+           ? launch_ls_tile<ContinuityP<3>, 3>(mp, lp, nc, ec, o, s)
+           : launch_ls_tile<ContinuityP<2>, 2>(mp, lp, nc, ec, o, s);
+}
+
+cudaError_t
+launch_scalar_tile(
+  const MeshPlanDev& mp,
+  const LsPlanDev& lp,
+  const NodeComps& nc,
+  const EdgeComps& ec,
+  nw_scalar_opts o,
+  cudaStream_t s)
+{
+  return mp.ndim == 3 ? launch_ls_tile<ScalarP<3>, 3>(mp, lp, nc, ec, o, s)
+                      : launch_ls_tile<ScalarP<2>, 2>(mp, lp, nc, ec, o, s);
+}
+
+cudaError_t
+launch_momentum_uvw_tile(
+  const MeshPlanDev& mp,
+  const LsPlanDev& lp,
+  const NodeComps& nc,
+  const EdgeComps& ec,
+  nw_momentum_opts o,
+  double* /*diagOut*/,
+  cudaStream_t s)
+{
+  return mp.ndim == 3
+           ? launch_ls_tile<MomentumUvwP<3>, 3>(mp, lp, nc, ec, o, s)
+           : launch_ls_tile<MomentumUvwP<2>, 2>(mp, lp, nc, ec, o, s);
+}
+
+cudaError_t
+launch_continuity_atomic(
+  const MeshPlanDev& mp,
+  const LsPlanDev& lp,
+  const AtomicMapDev& am,
+  const NodeComps& nc,
+  const EdgeComps& ec,
+  nw_continuity_opts o,
+  cudaStream_t s)
+{
+  return mp.ndim == 3
+           ? launch_ls_atomic<ContinuityP<3>, 3>(mp, lp, am, nc, ec, o, nullptr, s)
+           : launch_ls_atomic<ContinuityP<2>, 2>(mp, lp, am, nc, ec, o, nullptr, s);
+}
+
+cudaError_t
+launch_scalar_atomic(
+  const MeshPlanDev& mp,
+  const LsPlanDev& lp,
+  const AtomicMapDev& am,
+  const NodeComps& nc,
+  const EdgeComps& ec,
+  nw_scalar_opts o,
+  cudaStream_t s)
+{
+  return mp.ndim == 3
+           ? launch_ls_atomic<ScalarP<3>, 3>(mp, lp, am, nc, ec, o, nullptr, s)
+           : launch_ls_atomic<ScalarP<2>, 2>(mp, lp, am, nc, ec, o, nullptr, s);
+}
+
+cudaError_t
+launch_momentum_uvw_atomic(
+  const MeshPlanDev& mp,
+  const LsPlanDev& lp,
+  const AtomicMapDev& am,
+  const NodeComps& nc,
+  const EdgeComps& ec,
+  nw_momentum_opts o,
+  double* diagOut,
+  cudaStream_t s)
+{
+  return mp.ndim == 3
+           ? launch_ls_atomic<MomentumUvwP<3>, 3>(mp, lp, am, nc, ec, o, diagOut, s)
+           : launch_ls_atomic<MomentumUvwP<2>, 2>(mp, lp, am, nc, ec, o, diagOut, s);
+}
+
+cudaError_t
+launch_momentum_mono_atomic(
+  const MeshPlanDev& mp,
+  const int32_t* slots,
+  const int32_t* rhsRows,
+  double* values,
+  double* rhs,
+  const NodeComps& nc,
+  const EdgeComps& ec,
+  nw_momentum_opts o,
+  double* diagOut,
+  cudaStream_t s)
+{
+  if (mp.ndim == 3)
+    momentum_mono_atomic_kernel<3><<<mp.nTiles, kTileThreads, 0, s>>>(
+      mp, slots, rhsRows, values, rhs, nc, ec, o, diagOut);
+  else
+    momentum_mono_atomic_kernel<2><<<mp.nTiles, kTileThreads, 0, s>>>(
+      mp, slots, rhsRows, values, rhs, nc, ec, o, diagOut);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_node_gather(
+  const double* srcAos,
+  int ncomp,
+  const int32_t* nodeOfSlot,
+  int64_t nSlots,
+  double* dstSoa,
+  cudaStream_t s)
+{
+  node_gather_kernel<<<blocks_for(nSlots, 256), 256, 0, s>>>(
+    srcAos, ncomp, nodeOfSlot, nSlots, dstSoa);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_node_scatter(
+  const double* srcSoa,
+  int ncomp,
+  const int32_t* nodeOfSlot,
+  int64_t nSlots,
+  double* dstAos,
+  cudaStream_t s)
+{
+  node_scatter_kernel<<<blocks_for(nSlots, 256), 256, 0, s>>>(
+    srcSoa, ncomp, nodeOfSlot, nSlots, dstAos);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_edge_gather(
+  const double* srcAos,
+  int ncomp,
+  const int32_t* tileEdgeSrc,
+  int64_t nSlots,
+  double* dstSoa,
+  cudaStream_t s)
+{
+  /* same access pattern as the node gather: slot -> source entity */
+  node_gather_kernel<<<blocks_for(nSlots, 256), 256, 0, s>>>(
+    srcAos, ncomp, tileEdgeSrc, nSlots, dstSoa);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_edge_scatter(
+  const double* srcSoa,
+  int ncomp,
+  const int32_t* primarySlotOfEdge,
+  int64_t nEdges,
+  int64_t slotStride,
+  double* dstAos,
+  cudaStream_t s)
+{
+  if (nEdges == 0)
+    return cudaSuccess;
+  edge_scatter_kernel<<<blocks_for(nEdges, 256), 256, 0, s>>>(
+    srcSoa, ncomp, primarySlotOfEdge, nEdges, slotStride, dstAos);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_fill(double* p, int64_t n, double v, cudaStream_t s)
+{
+  if (n == 0)
+    return cudaSuccess;
+  fill_kernel<<<blocks_for(n, 256), 256, 0, s>>>(p, n, v);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_row_init(
+  const int32_t* rows,
+  int nRows,
+  const int64_t* rowPtr,
+  const uint8_t* isPeriodic,
+  double* values,
+  double* rhs,
+  int64_t rhsStride,
+  int nRhs,
+  cudaStream_t s)
+{
+  if (nRows == 0)
+    return cudaSuccess;
+  row_init_kernel<<<blocks_for(nRows, 128), 128, 0, s>>>(
+    rows, nRows, rowPtr, isPeriodic, values, rhs, rhsStride, nRhs);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_norm2(
+  const double* rhs,
+  int64_t n,
+  int64_t stride,
+  int nRhs,
+  double* partial,
+  int nPartial,
+  double* out,
+  cudaStream_t s)
+{
+  dim3 grid(nPartial, nRhs);
+  norm2_partial_kernel<<<grid, 256, 0, s>>>(rhs, n, stride, partial);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return e;
+  norm2_final_kernel<<<nRhs, 256, 0, s>>>(partial, nPartial, out);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_sum_into(
+  int64_t nEnt,
+  int npe,
+  int numDof,
+  const int32_t* entNodes,
+  const int64_t* nodeHid,
+  const double* lhs,
+  const double* rhsIn,
+  int64_t iLower,
+  int64_t iUpper,
+  int64_t nRowsOwned,
+  int64_t nnzOwned,
+  const int64_t* rowStartOwned,
+  const int64_t* rowStartShared,
+  const int64_t* rowIndicesShared,
+  int64_t nRowsShared,
+  const int64_t* cols,
+  const int64_t* skipped,
+  int64_t nSkipped,
+  int uvwDim,
+  double* values,
+  double* rhs,
+  int64_t rhsStride,
+  cudaStream_t s)
+{
+  if (nEnt == 0)
+    return cudaSuccess;
+  sum_into_kernel<<<blocks_for(nEnt, 128), 128, 0, s>>>(
+    nEnt, npe, numDof, entNodes, nodeHid, lhs, rhsIn, iLower, iUpper,
+    nRowsOwned, nnzOwned, rowStartOwned, rowStartShared, rowIndicesShared,
+    nRowsShared, cols, skipped, nSkipped, uvwDim, values, rhs, rhsStride);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_pack(
+  const double* src, const int64_t* idx, int64_t n, double* dst, cudaStream_t s)
+{
+  if (n == 0)
+    return cudaSuccess;
+  pack_kernel<<<blocks_for(n, 256), 256, 0, s>>>(src, idx, n, dst);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_scatter_assign(
+  const double* src, const int64_t* idx, int64_t n, double* dst, cudaStream_t s)
+{
+  if (n == 0)
+    return cudaSuccess;
+  scatter_assign_kernel<<<blocks_for(n, 256), 256, 0, s>>>(src, idx, n, dst);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_unpack_add(
+  const double* src, const int64_t* idx, int64_t n, double* dst, cudaStream_t s)
+{
+  if (n == 0)
+    return cudaSuccess;
+  unpack_add_kernel<<<blocks_for(n, 256), 256, 0, s>>>(src, idx, n, dst);
+  return cudaGetLastError();
+}
+
+} // namespace nw

@@ -1,0 +1,154 @@
+/*
+ * nw_kernels.cuh -- launch interface between the C-ABI layer (nw_api.cu) and
+ * the sm_100a kernels (nw_kernels.cu).
+ */
+#ifndef NW_KERNELS_CUH
+#define NW_KERNELS_CUH
+
+#include <cuda_runtime.h>
+
+#include "nw_types.h"
+
+namespace nw {
+
+constexpr int kMaxNodeComps = 20;
+
+struct MeshPlanDev
+{
+  const TileHdr* tiles = nullptr;
+  const int32_t* haloNodes = nullptr;
+  const uint32_t* lr = nullptr;
+  const uint32_t* heNode = nullptr;
+  const int32_t* warpSplitNode = nullptr;
+  const uint8_t* primary = nullptr;
+  int nTiles = 0;
+  int ndim = 3;
+  int maxStaged = 0;   /* max over tiles of even(nOwnPad + nHalo) */
+  int maxTileEdges = 0;
+  int maxTileNodes = 0;
+};
+
+struct LsPlanDev
+{
+  const LsTileHdr* tiles = nullptr;
+  const EntInfo* entInfo = nullptr;
+  const int32_t* entRhsRow = nullptr;
+  const uint32_t* he = nullptr;
+  const int32_t* warpSplit = nullptr;
+  const Run* runs = nullptr;
+  int maxTileNnz = 0;
+  int maxTileEnts = 0;
+  double* values = nullptr;
+  double* rhs = nullptr;
+  int64_t rhsStride = 0; /* rows_owned + rows_shared */
+};
+
+/* atomic-variant slot map, per tile-edge slot */
+struct AtomicMapDev
+{
+  const int32_t* slots = nullptr;   /* [nTileEdgeSlots][4]: LL, LR, RL, RR */
+  const int32_t* rhsRows = nullptr; /* [nTileEdgeSlots][2] */
+};
+
+/* node component pointers (SoA, internal numbering) */
+struct NodeComps
+{
+  const double* c[kMaxNodeComps];
+};
+struct EdgeComps
+{
+  const double* area[3];
+  const double* mdot;
+  const double* pecfac;
+};
+
+/* every launcher returns the cudaError_t of the launch */
+cudaError_t launch_mdot_tile(
+  const MeshPlanDev& mp, const NodeComps& nc, const EdgeComps& ec,
+  double* mdotOut, nw_mdot_opts o, cudaStream_t s);
+cudaError_t launch_peclet_tile(
+  const MeshPlanDev& mp, const NodeComps& nc, double* pecfacOut,
+  nw_peclet_opts o, cudaStream_t s);
+cudaError_t launch_grad_tile(
+  const MeshPlanDev& mp, int dim1, const NodeComps& phi, const double* dualVol,
+  const EdgeComps& ec, double* const* gradOut /* dim1*ndim comps */,
+  cudaStream_t s);
+
+cudaError_t launch_continuity_tile(
+  const MeshPlanDev& mp, const LsPlanDev& lp, const NodeComps& nc,
+  const EdgeComps& ec, nw_continuity_opts o, cudaStream_t s);
+cudaError_t launch_scalar_tile(
+  const MeshPlanDev& mp, const LsPlanDev& lp, const NodeComps& nc,
+  const EdgeComps& ec, nw_scalar_opts o, cudaStream_t s);
+cudaError_t launch_momentum_uvw_tile(
+  const MeshPlanDev& mp, const LsPlanDev& lp, const NodeComps& nc,
+  const EdgeComps& ec, nw_momentum_opts o, double* diagOut, cudaStream_t s);
+
+/* atomic variants (accumulate into values / rhs) */
+cudaError_t launch_continuity_atomic(
+  const MeshPlanDev& mp, const LsPlanDev& lp, const AtomicMapDev& am,
+  const NodeComps& nc, const EdgeComps& ec, nw_continuity_opts o,
+  cudaStream_t s);
+cudaError_t launch_scalar_atomic(
+  const MeshPlanDev& mp, const LsPlanDev& lp, const AtomicMapDev& am,
+  const NodeComps& nc, const EdgeComps& ec, nw_scalar_opts o, cudaStream_t s);
+cudaError_t launch_momentum_uvw_atomic(
+  const MeshPlanDev& mp, const LsPlanDev& lp, const AtomicMapDev& am,
+  const NodeComps& nc, const EdgeComps& ec, nw_momentum_opts o,
+  double* diagOut, cudaStream_t s);
+/* monolithic momentum (numDof == ndim): 2ndim x 2ndim blocks through the
+ * per-edge slot map [nTileEdgeSlots][4*ndim*ndim] */
+cudaError_t launch_momentum_mono_atomic(
+  const MeshPlanDev& mp, const int32_t* slots, const int32_t* rhsRows,
+  double* values, double* rhs, const NodeComps& nc, const EdgeComps& ec,
+  nw_momentum_opts o, double* diagOut, cudaStream_t s);
+cudaError_t launch_grad_atomic(
+  const MeshPlanDev& mp, int dim1, const NodeComps& phi, const double* dualVol,
+  const EdgeComps& ec, double* const* gradOut, cudaStream_t s);
+
+/* utility kernels */
+cudaError_t launch_node_gather(   /* AoS caller order -> SoA internal */
+  const double* srcAos, int ncomp, const int32_t* nodeOfSlot, int64_t nSlots,
+  double* dstSoa, cudaStream_t s);
+cudaError_t launch_node_scatter(  /* SoA internal -> AoS caller order */
+  const double* srcSoa, int ncomp, const int32_t* nodeOfSlot, int64_t nSlots,
+  double* dstAos, cudaStream_t s);
+cudaError_t launch_edge_gather(
+  const double* srcAos, int ncomp, const int32_t* tileEdgeSrc, int64_t nSlots,
+  double* dstSoa, cudaStream_t s);
+cudaError_t launch_edge_scatter(
+  const double* srcSoa, int ncomp, const int32_t* primarySlotOfEdge,
+  int64_t nEdges, int64_t slotStride, double* dstAos, cudaStream_t s);
+cudaError_t launch_fill(double* p, int64_t n, double v, cudaStream_t s);
+/* rows no tile writes: values zero (periodic rows: diagonal 1), rhs zero */
+cudaError_t launch_row_init(
+  const int32_t* rows, int nRows, const int64_t* rowPtr /* [R+1] */,
+  const uint8_t* isPeriodic, double* values, double* rhs, int64_t rhsStride,
+  int nRhs, cudaStream_t s);
+/* deterministic sum of squares of rhs[d*stride + (0..n)] for each d */
+cudaError_t launch_norm2(
+  const double* rhs, int64_t n, int64_t stride, int nRhs, double* partial,
+  int nPartial, double* out, cudaStream_t s);
+/* generic CoeffApplier entry: binary-search column lookup + atomics */
+cudaError_t launch_sum_into(
+  int64_t nEnt, int npe, int numDof, const int32_t* entNodes,
+  const int64_t* nodeHid, const double* lhs, const double* rhsIn,
+  int64_t iLower, int64_t iUpper, int64_t nRowsOwned, int64_t nnzOwned,
+  const int64_t* rowStartOwned, const int64_t* rowStartShared,
+  const int64_t* rowIndicesShared, int64_t nRowsShared, const int64_t* cols,
+  const int64_t* skipped, int64_t nSkipped, int uvwDim, double* values,
+  double* rhs, int64_t rhsStride, cudaStream_t s);
+/* halo exchange helpers */
+cudaError_t launch_pack(
+  const double* src, const int64_t* idx, int64_t n, double* dst,
+  cudaStream_t s);
+cudaError_t launch_scatter_assign(
+  const double* src, const int64_t* idx, int64_t n, double* dst,
+  cudaStream_t s);
+cudaError_t launch_unpack_add(
+  const double* src, const int64_t* idx, int64_t n, double* dst,
+  cudaStream_t s);
+
+} // namespace nw
+
+#endif

@@ -1,0 +1,584 @@
+/*
+ * nw_emul.cpp -- CPU walk-through of the tile plans (TEST INFRASTRUCTURE ONLY;
+ * lives under tests/, is never linked into the product library).
+ *
+ * The CUDA tile kernels cannot run in the build container (no GPU).  This file
+ * replays their phases sequentially on the host -- same plan arrays, same
+ * record decoding, same physics header (csrc/edge_physics.h) -- so that the
+ * CPU test-suite can check the plan builder and the restated arithmetic against
+ * the oracle before any GPU time is spent.  It compiles plan.cpp directly.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "edge_physics.h"
+#include "plan.h"
+
+using namespace nw;
+
+namespace {
+
+struct Emu
+{
+  MeshPlan mp;
+  Graph g;
+  LsPlan lp;
+  bool hasLs = false;
+  std::string err;
+};
+
+/* SoA internal storage of a node field given in caller AoS layout */
+std::vector<double>
+to_slots(const MeshPlan& mp, const double* aos, int ncomp)
+{
+  std::vector<double> s(size_t(mp.nSlots) * ncomp, 0.0);
+  for (int64_t i = 0; i < mp.nSlots; ++i) {
+    const int32_t n = mp.nodeOfSlot[i];
+    if (n < 0)
+      continue;
+    for (int c = 0; c < ncomp; ++c)
+      s[size_t(c) * mp.nSlots + i] = aos[size_t(n) * ncomp + c];
+  }
+  return s;
+}
+
+std::vector<double>
+edge_to_slots(const MeshPlan& mp, const double* aos, int ncomp)
+{
+  std::vector<double> s(size_t(mp.nTileEdgeSlots) * ncomp, 0.0);
+  for (int64_t i = 0; i < mp.nTileEdgeSlots; ++i) {
+    const int32_t e = mp.tileEdgeSrc[i];
+    if (e < 0)
+      continue;
+    for (int c = 0; c < ncomp; ++c)
+      s[size_t(c) * mp.nTileEdgeSlots + i] = aos[size_t(e) * ncomp + c];
+  }
+  return s;
+}
+
+/* stage one tile: returns staged[c*stride + local] */
+struct Staged
+{
+  std::vector<double> s;
+  int stride;
+  double operator()(int c, int i) const { return s[size_t(c) * stride + i]; }
+};
+
+Staged
+stage(const MeshPlan& mp, const TileHdr& h, const std::vector<const double*>& comps)
+{
+  Staged st;
+  st.stride = (h.nOwnPad + h.nHalo + 1) & ~1;
+  st.s.assign(size_t(st.stride) * comps.size(), 0.0);
+  for (size_t c = 0; c < comps.size(); ++c) {
+    for (int i = 0; i < h.nOwnPad; ++i)
+      st.s[c * st.stride + i] = comps[c][h.node0 + i];
+    for (int k = 0; k < h.nHalo; ++k)
+      st.s[c * st.stride + h.nOwnPad + k] =
+        comps[c][mp.haloNodes[h.haloPtr + k]];
+  }
+  return st;
+}
+
+} // namespace
+
+extern "C" {
+
+void*
+emu_create(
+  int ndim,
+  int rank,
+  int nranks,
+  int64_t nNodes,
+  int64_t nEdges,
+  const int32_t* edgeNodes,
+  const int64_t* hid,
+  const int64_t* ownHid,
+  const int64_t* offsets,
+  const double* coords,
+  int tileNodes)
+{
+  Emu* e = new Emu;
+  try {
+    MeshInput in;
+    in.ndim = ndim;
+    in.rank = rank;
+    in.nranks = nranks;
+    in.nNodes = nNodes;
+    in.nEdges = nEdges;
+    in.edgeNodes = edgeNodes;
+    in.nodeHid = hid;
+    in.nodeOwnHid = ownHid;
+    in.hypreOffsets = offsets;
+    in.coords = coords;
+    in.tileNodes = tileNodes;
+    build_mesh_plan(in, e->mp);
+  } catch (const std::exception& ex) {
+    e->err = ex.what();
+  }
+  return e;
+}
+
+const char*
+emu_error(void* h)
+{
+  return static_cast<Emu*>(h)->err.c_str();
+}
+
+void
+emu_destroy(void* h)
+{
+  delete static_cast<Emu*>(h);
+}
+
+int
+emu_build_linsys(
+  void* h, int kind, int numDof, const int64_t* skipped, int64_t nSkipped)
+{
+  Emu* e = static_cast<Emu*>(h);
+  try {
+    std::vector<int64_t> sk(skipped, skipped + nSkipped);
+    build_graph(e->mp, kind, numDof, sk, e->g);
+    build_ls_plan(e->mp, e->g, e->lp);
+    e->hasLs = true;
+  } catch (const std::exception& ex) {
+    e->err = ex.what();
+    return 1;
+  }
+  if (!e->lp.usable) {
+    e->err = "tile plan unusable: " + e->lp.whyNot;
+    return 2;
+  }
+  return 0;
+}
+
+/* plan invariants; returns 0 or writes a message */
+int
+emu_check_plan(void* h)
+{
+  Emu* e = static_cast<Emu*>(h);
+  const MeshPlan& mp = e->mp;
+  auto bad = [&](const std::string& m) {
+    e->err = m;
+    return 1;
+  };
+  std::vector<int> seen(mp.nNodes, 0);
+  for (int64_t t = 0; t < mp.nTiles; ++t) {
+    const TileHdr& hd = mp.tiles[t];
+    if (hd.node0 & 1)
+      return bad("tile node0 not even");
+    if (hd.edge0 & 1)
+      return bad("tile edge0 not even");
+    for (int i = 0; i < hd.nOwn; ++i) {
+      const int32_t n = mp.nodeOfSlot[hd.node0 + i];
+      if (n < 0 || mp.tileOfNode[n] != t)
+        return bad("slot/tile mismatch");
+      seen[n]++;
+    }
+    for (int k = 1; k < hd.nHalo; ++k)
+      if (mp.haloNodes[hd.haloPtr + k] <= mp.haloNodes[hd.haloPtr + k - 1])
+        return bad("halo list not strictly ascending");
+    /* every tile-edge decodes back to its source edge */
+    for (int j = 0; j < hd.nEdges; ++j) {
+      const int32_t src = mp.tileEdgeSrc[hd.edge0 + j];
+      const uint32_t v = mp.lr[hd.edge0 + j];
+      const int l = v & 0xffff, r = v >> 16;
+      auto gslot = [&](int loc) {
+        return loc < hd.nOwnPad ? hd.node0 + loc
+                                : mp.haloNodes[hd.haloPtr + loc - hd.nOwnPad];
+      };
+      if (mp.nodeOfSlot[gslot(l)] != mp.edgeNodes[2 * src] ||
+          mp.nodeOfSlot[gslot(r)] != mp.edgeNodes[2 * src + 1])
+        return bad("lr record does not decode to the edge's nodes");
+    }
+    /* half-edges sorted by entity, warp split at entity boundaries */
+    const uint32_t* he = mp.heNode.data() + hd.hePtrNode;
+    for (int q = 1; q < hd.nHalfNode; ++q)
+      if (he_ent(he[q]) < he_ent(he[q - 1]))
+        return bad("node half-edges not sorted");
+    const int32_t* sp = mp.warpSplitNode.data() + hd.warpPtrNode;
+    if (sp[0] != 0 || sp[kMaxWarps] != hd.nHalfNode)
+      return bad("warp split endpoints");
+    for (int w = 1; w < kMaxWarps; ++w) {
+      if (sp[w] < sp[w - 1])
+        return bad("warp split not monotone");
+      if (sp[w] > 0 && sp[w] < hd.nHalfNode &&
+          he_ent(he[sp[w]]) == he_ent(he[sp[w] - 1]))
+        return bad("warp split inside an entity");
+    }
+  }
+  for (int64_t n = 0; n < mp.nNodes; ++n)
+    if (seen[n] != 1)
+      return bad("node not owned by exactly one tile");
+  for (int64_t ed = 0; ed < mp.nEdges; ++ed) {
+    const int32_t p = mp.primarySlotOfEdge[ed];
+    if (p < 0 || mp.tileEdgeSrc[p] != ed || !mp.tileEdgePrimary[p])
+      return bad("primary slot map broken");
+    const int32_t tL = mp.tileOfNode[mp.edgeNodes[2 * ed]];
+    const int32_t tR = mp.tileOfNode[mp.edgeNodes[2 * ed + 1]];
+    if ((tL != tR) != (mp.secondSlotOfEdge[ed] >= 0))
+      return bad("cut edge must have exactly two copies");
+  }
+  if (e->hasLs) {
+    const LsPlan& lp = e->lp;
+    const Graph& g = e->g;
+    std::vector<int> cov(g.numRowsLocal(), 0);
+    for (int64_t t = 0; t < mp.nTiles; ++t) {
+      const LsTileHdr& lh = lp.tiles[t];
+      int64_t so = 0;
+      for (int i = 0; i < lh.nEnts; ++i) {
+        const EntInfo& ei = lp.entInfo[lh.entPtr + i];
+        const int64_t r = lp.entRhsRow[lh.entPtr + i];
+        cov[r]++;
+        if (ei.base != so || ei.nnz != g.rowLen(r))
+          return bad("ent staging layout");
+        so += ei.nnz;
+      }
+      if (so != lh.nnz)
+        return bad("tile nnz");
+      int64_t covered = 0;
+      for (int q = 0; q < lh.nRuns; ++q) {
+        const Run& rn = lp.runs[lh.runPtr + q];
+        if (rn.so != covered)
+          return bad("runs not contiguous in staging");
+        covered += rn.len;
+      }
+      if (covered != lh.nnz)
+        return bad("runs do not cover the staging");
+      const uint32_t* he = lp.he.data() + lh.hePtr;
+      for (int q = 1; q < lh.nHalf; ++q)
+        if (he_ent(he[q]) < he_ent(he[q - 1]))
+          return bad("row half-edges not sorted");
+      const int32_t* sp = lp.warpSplit.data() + lh.warpPtr;
+      for (int w = 1; w < kMaxWarps; ++w)
+        if (sp[w] > 0 && sp[w] < lh.nHalf &&
+            he_ent(he[sp[w]]) == he_ent(he[sp[w] - 1]))
+          return bad("ls warp split inside a row");
+    }
+    for (int32_t r : lp.uncoveredRows)
+      cov[r]++;
+    for (int64_t r = 0; r < g.numRowsLocal(); ++r)
+      if (cov[r] != 1)
+        return bad("row not covered exactly once");
+  }
+  return 0;
+}
+
+/* ---- emulated kernels: all fields in caller AoS layout ---- */
+
+/* kind: 0 continuity, 1 scalar, 2 momentum-UVW.  values/rhs sized like the
+ * product's arrays; emulates a tile assembly on a lazily zeroed system. */
+int
+emu_assemble(
+  void* h,
+  int kind,
+  const double* const* nodeFields, /* per policy, AoS */
+  const int* nodeNcomp,
+  int nNodeFields,
+  const double* area,
+  const double* mdot,
+  const double* pecfac,
+  const void* opts,
+  double* values,
+  double* rhs)
+{
+  Emu* e = static_cast<Emu*>(h);
+  if (!e->hasLs || !e->lp.usable) {
+    e->err = "no usable linear-system plan";
+    return 1;
+  }
+  const MeshPlan& mp = e->mp;
+  const Graph& g = e->g;
+  const LsPlan& lp = e->lp;
+  constexpr int ND = 3;
+  if (mp.ndim != 3) {
+    e->err = "emulator handles ndim == 3";
+    return 1;
+  }
+  std::vector<std::vector<double>> store;
+  std::vector<const double*> comps;
+  for (int f = 0; f < nNodeFields; ++f) {
+    store.push_back(to_slots(mp, nodeFields[f], nodeNcomp[f]));
+  }
+  for (int f = 0; f < nNodeFields; ++f)
+    for (int c = 0; c < nodeNcomp[f]; ++c)
+      comps.push_back(store[f].data() + size_t(c) * mp.nSlots);
+  std::vector<double> sArea = edge_to_slots(mp, area, ND);
+  std::vector<double> sMdot, sPec;
+  if (mdot)
+    sMdot = edge_to_slots(mp, mdot, 1);
+  if (pecfac)
+    sPec = edge_to_slots(mp, pecfac, 1);
+  const int NR = kind == 2 ? ND : 1;
+  const int NRES = kind == 0 ? 2 : (kind == 1 ? 5 : 4 + ND);
+  const int64_t rows = g.numRowsLocal();
+  const int64_t S = mp.nTileEdgeSlots;
+
+  /* lazy zero semantics: nothing is pre-zeroed; poison to catch gaps */
+  const int64_t nnz = g.nnzOwned + g.nnzShared;
+  for (int64_t i = 0; i < nnz; ++i)
+    values[i] = NAN;
+  for (int64_t i = 0; i < rows * NR; ++i)
+    rhs[i] = NAN;
+
+  for (int64_t t = 0; t < mp.nTiles; ++t) {
+    const TileHdr& hd = mp.tiles[t];
+    const LsTileHdr& lh = lp.tiles[t];
+    Staged st = stage(mp, hd, comps);
+    std::vector<double> res(size_t(NRES) * hd.nEdges);
+    /* phase 1 */
+    for (int j = 0; j < hd.nEdges; ++j) {
+      const uint32_t v = mp.lr[hd.edge0 + j];
+      const int l = v & 0xffff, r = v >> 16;
+      double av[ND];
+      for (int d = 0; d < ND; ++d)
+        av[d] = sArea[size_t(d) * S + hd.edge0 + j];
+      double out[8];
+      if (kind == 0) {
+        ContNode<ND> L, R;
+        auto ld = [&](int i, ContNode<ND>& n) {
+          for (int d = 0; d < ND; ++d) {
+            n.x[d] = st(d, i);
+            n.u[d] = st(ND + d, i);
+            n.g[d] = st(2 * ND + d, i);
+          }
+          n.rho = st(3 * ND, i);
+          n.p = st(3 * ND + 1, i);
+          n.ud = st(3 * ND + 2, i);
+        };
+        ld(l, L);
+        ld(r, R);
+        continuity_edge<ND>(
+          L, R, av, *static_cast<const nw_continuity_opts*>(opts), out[0],
+          out[1]);
+      } else if (kind == 1) {
+        ScalNode<ND> L, R;
+        auto ld = [&](int i, ScalNode<ND>& n) {
+          for (int d = 0; d < ND; ++d) {
+            n.x[d] = st(d, i);
+            n.v[d] = st(ND + d, i);
+            n.dq[d] = st(2 * ND + d, i);
+          }
+          n.q = st(3 * ND, i);
+          n.rho = st(3 * ND + 1, i);
+          n.mu = st(3 * ND + 2, i);
+        };
+        ld(l, L);
+        ld(r, R);
+        scalar_edge<ND>(
+          L, R, av, sMdot[hd.edge0 + j],
+          *static_cast<const nw_scalar_opts*>(opts), out, out[4]);
+      } else {
+        const nw_momentum_opts& o = *static_cast<const nw_momentum_opts*>(opts);
+        MomNode<ND> L, R;
+        auto ld = [&](int i, MomNode<ND>& n) {
+          for (int d = 0; d < ND; ++d) {
+            n.x[d] = st(d, i);
+            n.u[d] = st(ND + d, i);
+          }
+          for (int d = 0; d < ND * ND; ++d)
+            n.g[d] = st(2 * ND + d, i);
+          n.mu = st(2 * ND + ND * ND, i);
+          n.rho = st(2 * ND + ND * ND + 1, i);
+          n.mask = st(2 * ND + ND * ND + 2, i);
+        };
+        ld(l, L);
+        ld(r, R);
+        double pf = pecfac ? sPec[hd.edge0 + j] : 0.0;
+        if (o.fuse_peclet) {
+          PecNode<ND> pl, pr;
+          for (int d = 0; d < ND; ++d) {
+            pl.x[d] = L.x[d];
+            pr.x[d] = R.x[d];
+            pl.v[d] = L.u[d];
+            pr.v[d] = R.u[d];
+          }
+          pl.rho = L.rho;
+          pr.rho = R.rho;
+          pl.mu = L.mu;
+          pr.mu = R.mu;
+          pf = peclet_eval(o.pf, peclet_number<ND>(pl, pr, o.pec_eps));
+        }
+        MomResult<ND> m;
+        momentum_edge<ND>(L, R, av, sMdot[hd.edge0 + j], pf, o, m);
+        momentum_block_entry<ND>(
+          m, av, o.relax_fac, 0, 0, out[0], out[1], out[2], out[3]);
+        for (int d = 0; d < ND; ++d)
+          out[4 + d] = m.flux[d];
+      }
+      for (int k = 0; k < NRES; ++k)
+        res[size_t(k) * hd.nEdges + j] = out[k];
+    }
+    /* phase 2: half-edges in plan order, warp by warp, chunk by chunk (the
+     * sum order differs from the GPU's shuffle tree only by rounding) */
+    std::vector<double> sVals(lh.nnz, 0.0), sRhs(size_t(NR) * lh.nEnts, 0.0);
+    const uint32_t* he = lp.he.data() + lh.hePtr;
+    for (int q = 0; q < lh.nHalf; ++q) {
+      const uint32_t hv = he[q];
+      if (!(hv & kHeValid)) {
+        e->err = "invalid half-edge inside the list";
+        return 1;
+      }
+      const int j = he_edge(hv), side = he_side(hv), ent = he_ent(hv);
+      const EntInfo& ei = lp.entInfo[lh.entPtr + ent];
+      double r_[8];
+      for (int k = 0; k < NRES; ++k)
+        r_[k] = res[size_t(k) * hd.nEdges + j];
+      double diag, off, rr[3];
+      if (kind == 0) {
+        diag = -r_[0];
+        off = r_[0];
+        rr[0] = side ? r_[1] : -r_[1];
+      } else {
+        diag = side ? r_[3] : r_[0];
+        off = side ? r_[2] : r_[1];
+        for (int d = 0; d < NR; ++d)
+          rr[d] = side ? r_[4 + d] : -r_[4 + d];
+      }
+      if (he_k(hv) >= ei.nnz || he_k(hv) == ei.diagK) {
+        e->err = "half-edge slot out of row";
+        return 1;
+      }
+      if (hv & kHeDup)
+        sVals[ei.base + he_k(hv)] += off;
+      else
+        sVals[ei.base + he_k(hv)] = off;
+      sVals[ei.base + ei.diagK] += diag;
+      for (int d = 0; d < NR; ++d)
+        sRhs[size_t(d) * lh.nEnts + ent] += rr[d];
+    }
+    /* phase 3 */
+    for (int q = 0; q < lh.nRuns; ++q) {
+      const Run& rn = lp.runs[lh.runPtr + q];
+      for (int k = 0; k < rn.len; ++k)
+        values[rn.go + k] = sVals[rn.so + k];
+    }
+    for (int i = 0; i < lh.nEnts; ++i)
+      for (int d = 0; d < NR; ++d)
+        rhs[size_t(d) * rows + lp.entRhsRow[lh.entPtr + i]] =
+          sRhs[size_t(d) * lh.nEnts + i];
+  }
+  /* row init of the rows no tile writes */
+  for (int32_t r : lp.uncoveredRows) {
+    const int64_t a = g.rowPtr(r), len = g.rowLen(r);
+    for (int64_t k = 0; k < len; ++k)
+      values[a + k] = 0.0;
+    if (r < g.numRowsOwned &&
+        std::binary_search(
+          g.periodicRowsOwned.begin(), g.periodicRowsOwned.end(),
+          g.iLower + r))
+      values[a] = 1.0;
+    for (int d = 0; d < NR; ++d)
+      rhs[size_t(d) * rows + r] = 0.0;
+  }
+  return 0;
+}
+
+/* nodal gradient through the node-keyed half-edge lists; grad AoS out */
+int
+emu_nodal_grad(
+  void* h, int dim1, const double* phi, const double* area, const double* vol,
+  double* grad)
+{
+  Emu* e = static_cast<Emu*>(h);
+  const MeshPlan& mp = e->mp;
+  constexpr int ND = 3;
+  std::vector<double> sPhi = to_slots(mp, phi, dim1);
+  std::vector<double> sVol = to_slots(mp, vol, 1);
+  std::vector<double> sArea = edge_to_slots(mp, area, ND);
+  const int64_t S = mp.nTileEdgeSlots;
+  const int NV = dim1 * ND;
+  for (int64_t t = 0; t < mp.nTiles; ++t) {
+    const TileHdr& hd = mp.tiles[t];
+    std::vector<const double*> comps;
+    for (int c = 0; c < dim1; ++c)
+      comps.push_back(sPhi.data() + size_t(c) * mp.nSlots);
+    Staged st = stage(mp, hd, comps);
+    std::vector<double> out(size_t(NV) * hd.nOwn, 0.0);
+    const uint32_t* he = mp.heNode.data() + hd.hePtrNode;
+    for (int q = 0; q < hd.nHalfNode; ++q) {
+      const uint32_t hv = he[q];
+      const int j = he_edge(hv), ent = he_ent(hv);
+      const uint32_t v = mp.lr[hd.edge0 + j];
+      const int l = v & 0xffff, r = v >> 16;
+      const double invVol = 1.0 / sVol[hd.node0 + ent];
+      const double sgn = he_side(hv) ? -1.0 : 1.0;
+      for (int i = 0; i < dim1; ++i) {
+        const double phiIp = 0.5 * (st(i, l) + st(i, r));
+        for (int d = 0; d < ND; ++d) {
+          const double ajPhiIp = sArea[size_t(d) * S + hd.edge0 + j] * phiIp;
+          out[size_t(i * ND + d) * hd.nOwn + ent] += sgn * (ajPhiIp * invVol);
+        }
+      }
+    }
+    for (int i = 0; i < hd.nOwn; ++i) {
+      const int32_t n = mp.nodeOfSlot[hd.node0 + i];
+      for (int k = 0; k < NV; ++k)
+        grad[size_t(n) * NV + k] = out[size_t(k) * hd.nOwn + i];
+    }
+  }
+  return 0;
+}
+
+/* mdot per edge (caller order) through the tile-edge lists; both copies of a
+ * cut edge must agree bit for bit */
+int
+emu_mdot(
+  void* h, const double* const* nodeFields, const int* nodeNcomp,
+  int nNodeFields, const double* area, double nocFac, double interp,
+  double* mdotOut)
+{
+  Emu* e = static_cast<Emu*>(h);
+  const MeshPlan& mp = e->mp;
+  constexpr int ND = 3;
+  std::vector<std::vector<double>> store;
+  std::vector<const double*> comps;
+  for (int f = 0; f < nNodeFields; ++f)
+    store.push_back(to_slots(mp, nodeFields[f], nodeNcomp[f]));
+  for (int f = 0; f < nNodeFields; ++f)
+    for (int c = 0; c < nodeNcomp[f]; ++c)
+      comps.push_back(store[f].data() + size_t(c) * mp.nSlots);
+  std::vector<double> sArea = edge_to_slots(mp, area, ND);
+  const int64_t S = mp.nTileEdgeSlots;
+  std::vector<double> slots(S, 0.0);
+  for (int64_t t = 0; t < mp.nTiles; ++t) {
+    const TileHdr& hd = mp.tiles[t];
+    Staged st = stage(mp, hd, comps);
+    for (int j = 0; j < hd.nEdges; ++j) {
+      const uint32_t v = mp.lr[hd.edge0 + j];
+      const int l = v & 0xffff, r = v >> 16;
+      double av[ND];
+      for (int d = 0; d < ND; ++d)
+        av[d] = sArea[size_t(d) * S + hd.edge0 + j];
+      ContNode<ND> L, R;
+      auto ld = [&](int i, ContNode<ND>& n) {
+        for (int d = 0; d < ND; ++d) {
+          n.x[d] = st(d, i);
+          n.u[d] = st(ND + d, i);
+          n.g[d] = st(2 * ND + d, i);
+        }
+        n.rho = st(3 * ND, i);
+        n.p = st(3 * ND + 1, i);
+        n.ud = st(3 * ND + 2, i);
+      };
+      ld(l, L);
+      ld(r, R);
+      slots[hd.edge0 + j] = mdot_core<ND>(L, R, av, nocFac, interp).tmdot;
+    }
+  }
+  for (int64_t ed = 0; ed < mp.nEdges; ++ed) {
+    const int32_t p = mp.primarySlotOfEdge[ed], s2 = mp.secondSlotOfEdge[ed];
+    if (s2 >= 0 && std::memcmp(&slots[p], &slots[s2], sizeof(double)) != 0) {
+      e->err = "the two copies of a cut edge disagree";
+      return 1;
+    }
+    mdotOut[ed] = slots[p];
+  }
+  return 0;
+}
+
+} // extern "C"

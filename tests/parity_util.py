@@ -1,0 +1,353 @@
+"""Shared helpers of the parity tests: build a synthetic case, run the CPU
+oracle on it, and compare against the product (CUDA through the C ABI) or the
+CPU plan walk-through (tests/emul).  Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import oracle_py as orc  # noqa: E402
+import __graft_entry__ as graft  # noqa: E402
+
+TOL = 1.0e-12  # north_star: every fp64 matrix / RHS entry within relative 1e-12
+
+DT, GAMMA1 = 0.5, 1.5
+
+
+def pkg():
+    return graft.load_package()
+
+
+def scaled_err(got, ref, scale):
+    """max |got-ref| / (TOL * scale): < 1 passes.  `scale` is the oracle's sum of
+    |contributions| of the entry (a rigorous cancellation-aware magnitude), with
+    |ref| as a floor."""
+    got, ref, scale = np.asarray(got), np.asarray(ref), np.asarray(scale)
+    if got.shape != ref.shape:
+        return float("inf")
+    if not np.all(np.isfinite(got)):
+        return float("inf")
+    s = np.maximum(np.maximum(scale, np.abs(ref)), 1e-300)
+    if got.size == 0:
+        return 0.0
+    return float(np.max(np.abs(got - ref) / (TOL * s)))
+
+
+class Case:
+    """generated hex box + synthetic state (one rank)"""
+
+    def __init__(self, dims=(12, 10, 8), lengths=None, periodic=(False, False),
+                 warp=0.0, zstretch=1.0, nranks=1, rank=0, shuffle_bucket=0):
+        P = pkg()
+        synth = __import__("nalu_wind_b200.synth", fromlist=["state"])
+        self.box = P.BoxMesh(*dims, lengths=lengths, periodic=periodic,
+                             warp=warp, zstretch=zstretch, nranks=nranks,
+                             rank=rank, shuffle_bucket=shuffle_bucket)
+        b = self.box
+        L = lengths if lengths else tuple(float(d) for d in dims)
+        self.lengths = L
+        pg = None
+        if any(periodic):
+            # periodic master's global id: own_hid differs from hid on slaves;
+            # use the resolved row id as the noise key (identical on aliases)
+            pg = b.hid.astype(np.int64) + 1
+        self.fields = synth.state(b.coords, b.gid, L, DT, GAMMA1,
+                                  periodic_gid=pg)
+        self.fields["dual_nodal_volume"] = b.vol
+        self.edges = b.edges
+        self.area = b.area
+        self.n_nodes, self.n_edges = b.n_nodes, b.n_edges
+
+    # ---- oracle side ----
+    def oracle_graph(self, num_dof=1, skipped=()):
+        b = self.box
+        lo = int(b.offsets[b.rank]) * num_dof
+        hi = int(b.offsets[b.rank + 1]) * num_dof - 1
+        g = orc.Graph(num_dof, lo, hi)
+        if len(skipped):
+            g.set_skipped(skipped)
+        g.add_edges(self.edges, b.hid)
+        return g.finalize()
+
+    def oracle_mdot(self):
+        f = self.fields
+        return orc.mdot_edge(3, self.edges, self.box.coords, f["velocity"],
+                             f["dpdx"], f["density"], f["pressure"],
+                             f["momentum_diag"], self.area, 1.0, 1.0)
+
+    def oracle_pecfac(self, pf):
+        f = self.fields
+        return orc.peclet_edge(3, self.edges, self.box.coords, f["velocity"],
+                               f["density"], f["viscosity"], pf)[1]
+
+
+MOM_OPTS = dict(include_divu=0.0, alpha=0.0, alpha_upw=1.0, ho_upwind=1.0,
+                relax_fac=0.7, use_limiter=True)
+SCAL_OPTS = dict(alpha=0.0, alpha_upw=1.0, ho_upwind=1.0, relax_fac=0.9,
+                 use_limiter=True)
+CONT_OPTS = dict(dt=DT, gamma1=GAMMA1, noc_fac=1.0, interp_together=1.0,
+                 solve_incompressible=0.0)
+
+
+def oracle_continuity(case, g):
+    f, b = case.fields, case.box
+    s = orc.HypreSink(g, b.hid)
+    orc.continuity_edge(3, case.edges, b.coords, f["velocity"], f["dpdx"],
+                        f["density"], f["pressure"], f["momentum_diag"],
+                        case.area, s, **CONT_OPTS)
+    return s
+
+
+def oracle_scalar(case, g, mdot, q="turbulent_ke", dq="dkdx",
+                  mu="effective_viscosity_tke", pf=None):
+    f, b = case.fields, case.box
+    s = orc.HypreSink(g, b.hid)
+    orc.scalar_edge(3, case.edges, b.coords, f["velocity"], f[q], f[dq],
+                    f["density"], f[mu], case.area, mdot, s,
+                    pf=pf or orc.peclet("tanh", 2.0, 1.0), **SCAL_OPTS)
+    return s
+
+
+def oracle_momentum(case, g, mdot, pecfac, uvw=True, udiag=None):
+    f, b = case.fields, case.box
+    s = orc.HypreSink(g, b.hid, uvw_ndim=3 if uvw else 0)
+    orc.momentum_edge(3, case.edges, b.coords, f["velocity"], f["dudx"],
+                      f["viscosity"], f["density"],
+                      f["abl_wall_no_slip_wall_func_node_mask"], case.area,
+                      mdot, pecfac, s, udiag_accum=udiag, **MOM_OPTS)
+    return s
+
+
+# ---------------------------------------------------------------------------
+# CPU plan walk-through (tests/emul)
+# ---------------------------------------------------------------------------
+_emu = None
+
+
+def emu_lib():
+    global _emu
+    if _emu is None:
+        subprocess.check_call(["make", "-C", os.path.join(HERE, "emul"), "-s"])
+        L = C.CDLL(os.path.join(HERE, "emul", "libnw_emul.so"))
+        vp = C.c_void_p
+        L.emu_create.restype = vp
+        L.emu_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64,
+                                 C.c_int64, vp, vp, vp, vp, vp, C.c_int]
+        L.emu_error.restype = C.c_char_p
+        L.emu_error.argtypes = [vp]
+        L.emu_destroy.argtypes = [vp]
+        L.emu_build_linsys.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int64]
+        L.emu_check_plan.argtypes = [vp]
+        L.emu_assemble.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, vp,
+                                   vp, vp, vp]
+        L.emu_nodal_grad.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+        L.emu_mdot.argtypes = [vp, vp, vp, C.c_int, vp, C.c_double,
+                               C.c_double, vp]
+        _emu = L
+    return _emu
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+class Emu:
+    def __init__(self, case, tile_nodes=64):
+        b = case.box
+        self.case = case
+        L = emu_lib()
+        self._keep = [np.ascontiguousarray(b.edges), b.hid, b.own_hid,
+                      b.offsets, b.coords]
+        self.h = L.emu_create(3, b.rank, b.nranks, b.n_nodes, b.n_edges,
+                              *[_p(a) for a in self._keep], tile_nodes)
+        err = L.emu_error(self.h).decode()
+        assert err == "", err
+
+    def build_linsys(self, kind=0, num_dof=1, skipped=()):
+        sk = np.ascontiguousarray(skipped, dtype=np.int64)
+        rc = emu_lib().emu_build_linsys(self.h, kind, num_dof, _p(sk), sk.size)
+        assert rc == 0, emu_lib().emu_error(self.h).decode()
+
+    def check_plan(self):
+        rc = emu_lib().emu_check_plan(self.h)
+        assert rc == 0, emu_lib().emu_error(self.h).decode()
+
+    def _fields(self, names):
+        arrs = [np.ascontiguousarray(self.case.fields[n] if n != "coordinates"
+                                     else self.case.box.coords,
+                                     dtype=np.float64) for n in names]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        nc = np.array([a.size // self.case.n_nodes for a in arrs],
+                      dtype=np.int32)
+        return arrs, ptrs, nc
+
+    def assemble(self, kind, names, opts, nnz, rows, nrhs, mdot=None,
+                 pecfac=None):
+        arrs, ptrs, nc = self._fields(names)
+        vals = np.zeros(nnz)
+        rhs = np.zeros((nrhs, rows))
+        area = np.ascontiguousarray(self.case.area)
+        rc = emu_lib().emu_assemble(
+            self.h, kind, C.cast(ptrs, C.c_void_p), _p(nc), len(arrs),
+            _p(area), _p(mdot), _p(pecfac), C.cast(C.byref(opts), C.c_void_p),
+            _p(vals), _p(rhs))
+        assert rc == 0, emu_lib().emu_error(self.h).decode()
+        return vals, rhs
+
+    def nodal_grad(self, phi, dim1):
+        phi = np.ascontiguousarray(phi, dtype=np.float64)
+        out = np.zeros((self.case.n_nodes, dim1 * 3))
+        area = np.ascontiguousarray(self.case.area)
+        vol = np.ascontiguousarray(self.case.fields["dual_nodal_volume"])
+        rc = emu_lib().emu_nodal_grad(self.h, dim1, _p(phi), _p(area), _p(vol),
+                                      _p(out))
+        assert rc == 0
+        return out
+
+    def mdot(self):
+        arrs, ptrs, nc = self._fields(CONT_FIELDS)
+        out = np.zeros(self.case.n_edges)
+        area = np.ascontiguousarray(self.case.area)
+        rc = emu_lib().emu_mdot(self.h, C.cast(ptrs, C.c_void_p), _p(nc),
+                                len(arrs), _p(area), 1.0, 1.0, _p(out))
+        assert rc == 0, emu_lib().emu_error(self.h).decode()
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            emu_lib().emu_destroy(self.h)
+            self.h = None
+
+
+CONT_FIELDS = ["coordinates", "velocity", "dpdx", "density", "pressure",
+               "momentum_diag"]
+SCAL_FIELDS = ["coordinates", "velocity", "dkdx", "turbulent_ke", "density",
+               "effective_viscosity_tke"]
+MOM_FIELDS = ["coordinates", "velocity", "dudx", "viscosity", "density",
+              "abl_wall_no_slip_wall_func_node_mask"]
+
+
+# ---------------------------------------------------------------------------
+# product (CUDA) side
+# ---------------------------------------------------------------------------
+
+def upload_state(P, mesh, case, extra_edge=None):
+    for name, arr in case.fields.items():
+        mesh.put(name, P.NW_NODE, arr)
+    mesh.put("edge_area_vector", P.NW_EDGE, case.area)
+    mesh.register("mass_flow_rate", P.NW_EDGE, 1)
+    mesh.register("peclet_factor", P.NW_EDGE, 1)
+    for k, v in (extra_edge or {}).items():
+        mesh.put(k, P.NW_EDGE, v)
+
+
+def run_lowmach_case(P, ctx, dims=(12, 10, 8), tile_nodes=64, mode=None,
+                     **case_kw):
+    """The full low-Mach sweep on one rank through the C ABI, compared with the
+    oracle.  Returns {name: scaled error} (every value must be < 1)."""
+    case = Case(dims=dims, **case_kw)
+    mesh = case.box.make_mesh(ctx, tile_nodes=tile_nodes)
+    upload_state(P, mesh, case)
+    res = {}
+    pf = P.peclet_fn("classic", 1.0)
+    opf = orc.peclet("classic", 1.0)
+
+    # K1 mdot
+    mesh.mdot_edge(1.0, 1.0)
+    mdot = mesh.download("mass_flow_rate")
+    omdot = case.oracle_mdot()
+    f = case.fields
+    res["mdot"] = scaled_err(mdot, omdot, np.abs(omdot) + 1e-3 * np.max(np.abs(omdot)))
+    # K9 peclet
+    mesh.peclet_edge("viscosity", pf)
+    pec = mesh.download("peclet_factor")
+    opec = case.oracle_pecfac(opf)
+    res["peclet"] = scaled_err(pec, opec, np.ones_like(opec))
+    # feed the oracle's edge fields back so later kernels see identical bits
+    mesh.upload("mass_flow_rate", omdot)
+    mesh.upload("peclet_factor", opec)
+
+    # K2 gradients
+    for phi, grad, d1 in (("pressure", "dpdx_out", 1), ("velocity", "dudx_out", 3)):
+        mesh.register(grad, P.NW_NODE, d1 * 3)
+        mesh.nodal_grad_edge(phi, grad)
+        got = mesh.download(grad)
+        ref = orc.nodal_grad_edge(d1, 3, case.edges, f[phi], case.area,
+                                  f["dual_nodal_volume"], case.n_nodes)
+        mag = orc.nodal_grad_edge(d1, 3, case.edges, np.abs(f[phi]),
+                                  np.abs(case.area), f["dual_nodal_volume"],
+                                  case.n_nodes)
+        # |.| version over-counts signs of R contributions: use abs of terms
+        mag = np.abs(mag) + np.max(np.abs(ref)) * 1e-3
+        res["grad_" + phi] = scaled_err(got.reshape(ref.shape), ref, mag)
+
+    g = case.oracle_graph()
+    # K4 continuity
+    ls = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE, 1)
+    if mode is not None:
+        ls.set_scatter_mode(mode)
+    ls.buildEdgeToNodeGraph()
+    ls.finalizeLinearSystem()
+    ls.zeroSystem()
+    ls.assemble_continuity_edge(**CONT_OPTS)
+    ls.loadComplete()
+    vals, rhs = ls.values()
+    o = oracle_continuity(case, g)
+    ov, orhs = o.get()
+    av, arhs = o.get_abs()
+    res["continuity_lhs"] = scaled_err(vals, ov, av)
+    res["continuity_rhs"] = scaled_err(rhs, orhs, arhs)
+    n2 = ls.rhs_norm2()
+    res["continuity_norm"] = scaled_err(
+        n2, np.sum(orhs[:, :g.num_rows_owned] ** 2, axis=1),
+        1e3 * np.sum(arhs[:, :g.num_rows_owned] ** 2, axis=1))
+    ls.close()
+
+    # K5 scalar
+    ls = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE, 1)
+    if mode is not None:
+        ls.set_scatter_mode(mode)
+    ls.buildEdgeToNodeGraph()
+    ls.finalizeLinearSystem()
+    ls.zeroSystem()
+    ls.assemble_scalar_edge("turbulent_ke", "dkdx", "effective_viscosity_tke",
+                            pf=P.peclet_fn("tanh", 2.0, 1.0), **SCAL_OPTS)
+    vals, rhs = ls.values()
+    o = oracle_scalar(case, g, omdot)
+    ov, orhs = o.get()
+    av, arhs = o.get_abs()
+    res["scalar_lhs"] = scaled_err(vals, ov, av)
+    res["scalar_rhs"] = scaled_err(rhs, orhs, arhs)
+    ls.close()
+
+    # K3 momentum, segregated UVW
+    ls = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE_UVW, 3)
+    if mode is not None:
+        ls.set_scatter_mode(mode)
+    ls.buildEdgeToNodeGraph()
+    ls.finalizeLinearSystem()
+    ls.zeroSystem()
+    ls.assemble_momentum_edge("viscosity", **MOM_OPTS)
+    vals, rhs = ls.values()
+    o = oracle_momentum(case, g, omdot, opec, uvw=True)
+    ov, orhs = o.get()
+    av, arhs = o.get_abs()
+    res["momentum_uvw_lhs"] = scaled_err(vals, ov, av)
+    res["momentum_uvw_rhs"] = scaled_err(rhs, orhs, arhs)
+    # fused Peclet variant must give the same system
+    ls.zeroSystem()
+    ls.assemble_momentum_edge("viscosity", fuse_peclet=True, pf=pf, **MOM_OPTS)
+    vals, rhs = ls.values()
+    res["momentum_fused_lhs"] = scaled_err(vals, ov, av)
+    res["momentum_fused_rhs"] = scaled_err(rhs, orhs, arhs)
+    ls.close()
+    mesh.close()
+    return res
