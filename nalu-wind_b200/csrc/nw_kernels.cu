@@ -24,6 +24,8 @@
 
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "edge_physics.h"
 
 namespace nw {
@@ -378,7 +380,7 @@ struct GmemLd
 /* ------------------------------------------------------------------ */
 
 template <class P, int ND>
-__global__ void __launch_bounds__(kTileThreads) ls_tile_kernel(
+__global__ void __launch_bounds__(kTileThreads, 2) ls_tile_kernel(
   const MeshPlanDev mp,
   const LsPlanDev lp,
   const NodeComps nc,
@@ -394,18 +396,16 @@ __global__ void __launch_bounds__(kTileThreads) ls_tile_kernel(
   const int resStride = even_up_i(mp.maxTileEdges);
   const int entStride = even_up_i(lp.maxTileEnts);
 
+  /* [ node stage | edge results ]; the row staging of phases 2-3 reuses the
+   * node stage, which is dead once phase 1 is over */
+  const int nodeRegion = max(
+    P::NC * mp.maxStaged, even_up_i(lp.maxTileNnz) + P::NR * entStride);
   double* s_node = smem;
-  double* s_res = s_node + (size_t)P::NC * mp.maxStaged;
-  double* s_vals = s_res + (size_t)P::NRES * resStride;
+  double* s_res = s_node + nodeRegion;
+  double* s_vals = s_node;
   double* s_rhs = s_vals + even_up_i(lp.maxTileNnz);
 
   stage_nodes<P::NC>(s_node, stride, nc, h, mp.haloNodes, &bar);
-
-  /* zero the row staging (diagonal and rhs are accumulated by segment tails) */
-  for (int i = threadIdx.x; i < lh.nnz; i += blockDim.x)
-    s_vals[i] = 0.0;
-  for (int i = threadIdx.x; i < P::NR * entStride; i += blockDim.x)
-    s_rhs[i] = 0.0;
 
   /* ---- phase 1: per-edge physics ---- */
   {
@@ -430,6 +430,13 @@ __global__ void __launch_bounds__(kTileThreads) ls_tile_kernel(
         s_res[k * resStride + j] = res[k];
     }
   }
+  __syncthreads();
+
+  /* zero the row staging (diagonal and rhs are accumulated by segment tails) */
+  for (int i = threadIdx.x; i < lh.nnz; i += blockDim.x)
+    s_vals[i] = 0.0;
+  for (int i = threadIdx.x; i < P::NR * entStride; i += blockDim.x)
+    s_rhs[i] = 0.0;
   __syncthreads();
 
   /* ---- phase 2: row-sorted segmented reduction ---- */
@@ -1149,11 +1156,11 @@ template <class P>
 size_t
 ls_tile_smem(const MeshPlanDev& mp, const LsPlanDev& lp)
 {
+  const size_t nodeRegion = std::max<size_t>(
+    (size_t)P::NC * mp.maxStaged,
+    (size_t)even_up_h(lp.maxTileNnz) + (size_t)P::NR * even_up_h(lp.maxTileEnts));
   return sizeof(double) *
-         ((size_t)P::NC * mp.maxStaged +
-          (size_t)P::NRES * even_up_h(mp.maxTileEdges) +
-          (size_t)even_up_h(lp.maxTileNnz) +
-          (size_t)P::NR * even_up_h(lp.maxTileEnts));
+         (nodeRegion + (size_t)P::NRES * even_up_h(mp.maxTileEdges));
 }
 
 template <class P, int ND>

@@ -17,6 +17,34 @@
 #include <unordered_map>
 #include <vector>
 
+/* Threading.  Default 1 thread: the plain serial loop ("Kokkos Serial"), which is
+ * what the golden fixtures pin.  With orc_set_num_threads(n > 1) the edge loops
+ * run under OpenMP and every scatter add becomes an `omp atomic`, the analogue
+ * of the reference's OpenMP build (Kokkos::atomic_add); used only to time the
+ * CPU baseline on all host cores. */
+static int g_threads = 1;
+extern "C" void
+orc_set_num_threads(int n)
+{
+  g_threads = n < 1 ? 1 : n;
+}
+extern "C" int
+orc_get_num_threads(void)
+{
+  return g_threads;
+}
+static inline void
+add_to(double& dst, double v)
+{
+  if (g_threads > 1) {
+#pragma omp atomic
+    dst += v;
+  } else
+    dst += v;
+}
+#define ORC_EDGE_LOOP \
+  _Pragma("omp parallel for schedule(static) if (g_threads > 1) num_threads(g_threads)")
+
 namespace {
 
 constexpr int kMaxDim = 3;
@@ -67,7 +95,7 @@ struct DenseApplier : orc_applier
     for (int i = 0; i < nEnt; ++i) {
       const size_t ioff = size_t(nodes[i]) * numDof;
       for (int d = 0; d < numDof; ++d)
-        rhs_[ioff + d] += rhs[i * numDof + d];
+        add_to(rhs_[ioff + d], rhs[i * numDof + d]);
     }
     for (int i = 0; i < nEnt; ++i) {
       const size_t ioff = size_t(nodes[i]) * numDof;
@@ -76,7 +104,7 @@ struct DenseApplier : orc_applier
         for (int d = 0; d < numDof; ++d) {
           const int ii = i * numDof + d;
           const int jj = j * numDof + d;
-          lhs_[(ioff + d) * N + (joff + d)] += lhs[ii * n + jj];
+          add_to(lhs_[(ioff + d) * N + (joff + d)], lhs[ii * n + jj]);
         }
       }
     }
@@ -454,24 +482,24 @@ struct HypreApplier : orc_applier
 
   void log_slot(int n, int ii, int kk, int64_t idx)
   {
-    if (logOn && callNo < logCalls)
+    if (logOn && g_threads == 1 && callNo < logCalls)
       logSlots[(size_t(callNo) * n + ii) * n + kk] = idx;
   }
   void log_rhs(int n, int ii, int64_t idx)
   {
-    if (logOn && callNo < logCalls)
+    if (logOn && g_threads == 1 && callNo < logCalls)
       logRhs[size_t(callNo) * n + ii] = idx;
   }
 
   void add_rhs(int64_t row, int d, double v)
   {
-    rhs[size_t(d) * totalRows + row] += v;
-    absRhs[size_t(d) * totalRows + row] += std::fabs(v);
+    add_to(rhs[size_t(d) * totalRows + row], v);
+    add_to(absRhs[size_t(d) * totalRows + row], std::fabs(v));
   }
   void add_val(int64_t idx, double v)
   {
-    values[idx] += v;
-    absValues[idx] += std::fabs(v);
+    add_to(values[idx], v);
+    add_to(absValues[idx], std::fabs(v));
   }
 
   /* sum_into_1DoF: src/HypreLinearSystem.C:2165-2239 */
@@ -660,7 +688,8 @@ struct HypreApplier : orc_applier
       sum_into_1dof(unsigned(nEnt), nodes, r, lhs, n);
     else
       sum_into_ndof(unsigned(nEnt), nodes, r, lhs, n);
-    callNo++;
+    if (g_threads == 1)
+      callNo++;
   }
 };
 
@@ -780,6 +809,7 @@ orc_mdot_edge(
 {
   /* src/ngp_algorithms/MdotEdgeAlg.C:117-190 */
   const double om_interp = 1.0 - interp_together;
+  ORC_EDGE_LOOP
   for (int64_t e = 0; e < n_edges; ++e) {
     double av[kMaxDim];
     for (int d = 0; d < ndim; ++d)
@@ -834,6 +864,7 @@ orc_peclet_edge(
   double* pecfac)
 {
   /* src/edge_kernels/MomentumEdgePecletAlg.C:74-101 */
+  ORC_EDGE_LOOP
   for (int64_t e = 0; e < n_edges; ++e) {
     double udotx = 0.0;
     const int64_t nL = edge_nodes[2 * e], nR = edge_nodes[2 * e + 1];
@@ -868,6 +899,7 @@ orc_nodal_grad_edge(
   /* src/ngp_algorithms/NodalGradEdgeAlg.C:85-109; the atomic adds of
    * include/ngp_utils/NgpFieldOps.h:84 become serial adds in edge order. */
   const int gsz = dim1 * dim2;
+  ORC_EDGE_LOOP
   for (int64_t e = 0; e < n_edges; ++e) {
     double av[kMaxDim];
     for (int d = 0; d < dim2; ++d)
@@ -880,8 +912,8 @@ orc_nodal_grad_edge(
       const double phiIp = 0.5 * (phi[nL * dim1 + i] + phi[nR * dim1 + i]);
       for (int j = 0; j < dim2; ++j) {
         const double ajPhiIp = av[j] * phiIp;
-        grad[nL * gsz + counter] += ajPhiIp * invVolL;
-        grad[nR * gsz + counter] -= ajPhiIp * invVolR;
+        add_to(grad[nL * gsz + counter], ajPhiIp * invVolL);
+        add_to(grad[nR * gsz + counter], -(ajPhiIp * invVolR));
         counter++;
       }
     }
@@ -916,6 +948,7 @@ orc_continuity_edge(
   const double solveInc = o->solve_incompressible;
   const double om_solveInc = 1.0 - solveInc;
 
+  ORC_EDGE_LOOP
   for (int64_t e = 0; e < n_edges; ++e) {
     double lhs[4] = {0.0, 0.0, 0.0, 0.0};
     double rhs[2] = {0.0, 0.0};
@@ -1000,6 +1033,7 @@ orc_scalar_edge(
   const double om_alpha = 1.0 - alpha;
   const double om_alphaUpw = 1.0 - alphaUpw;
 
+  ORC_EDGE_LOOP
   for (int64_t e = 0; e < n_edges; ++e) {
     double lhs[4] = {0.0, 0.0, 0.0, 0.0};
     double rhs[2] = {0.0, 0.0};
@@ -1131,6 +1165,7 @@ orc_momentum_edge(
   const int n = 2 * ndim;
   (void)density; /* only read by the VOF branch (:178-192), has_vof == 0 */
 
+  ORC_EDGE_LOOP
   for (int64_t e = 0; e < n_edges; ++e) {
     double lhs[kMaxRhs * kMaxRhs];
     double rhs[kMaxRhs];
@@ -1278,7 +1313,7 @@ orc_momentum_edge(
     if (udiag_accum) {
       for (int i = 0; i < 2; ++i) {
         const int ix = i * ndim;
-        udiag_accum[nodes[i]] += LHS(ix, ix);
+        add_to(udiag_accum[nodes[i]], LHS(ix, ix));
       }
     }
     sink->apply(2, nodes, rhs, lhs, n);

@@ -30,6 +30,10 @@
 extern "C" {
 #endif
 
+/* threads used by the edge loops (default 1 == serial, deterministic) */
+void orc_set_num_threads(int n);
+int orc_get_num_threads(void);
+
 /* ---- Peclet blending function (src/PecletFunction.C:41-45, 68-71) ---- */
 enum { ORC_PECLET_CLASSIC = 0, ORC_PECLET_TANH = 1 };
 typedef struct {

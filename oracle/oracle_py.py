@@ -57,6 +57,8 @@ def lib():
         return _LIB
     L = C.CDLL(build())
     vp = C.c_void_p
+    L.orc_set_num_threads.argtypes = [C.c_int]
+    L.orc_get_num_threads.restype = C.c_int
     L.orc_peclet_eval.restype = C.c_double
     L.orc_peclet_eval.argtypes = [C.POINTER(Peclet), C.c_double]
     L.orc_applier_dense_create.restype = vp
@@ -114,6 +116,10 @@ def _i32(a):
 def _i64(a):
     a = np.ascontiguousarray(a, dtype=np.int64)
     return a, a.ctypes.data_as(c_i64p)
+
+
+def set_num_threads(n):
+    lib().orc_set_num_threads(int(n))
 
 
 def peclet(form="classic", a=0.0, b=1.0):

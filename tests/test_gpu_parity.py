@@ -1,0 +1,349 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the
+reference's golden vectors.  Needs a B200: `pytest -m gpu`.
+
+Tolerance (BASELINE.json north_star): every fp64 matrix / RHS entry within a
+relative 1e-12; 'relative' is taken against the entry's sum of |contributions|
+(the oracle computes it), which is the rigorous scale for entries that nearly
+cancel.  Integer structures (CSR graph, slot maps) are compared bit-exactly in
+tests/test_plan_cpu.py (no GPU needed) -- the same host code runs here."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_py as orc
+import parity_util as pu
+import unit_cube as uc
+
+pytestmark = pytest.mark.gpu
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden",
+                                "reference_golds.json")))
+
+
+@pytest.fixture(scope="module")
+def P():
+    return pu.pkg()
+
+
+@pytest.fixture(scope="module")
+def ctx(P):
+    c = P.Context(0)
+    yield c
+    c.close()
+
+
+def _cube_mesh(P, ctx, nz=1):
+    c, e = uc.mesh(nz)
+    n = len(c)
+    m = P.Mesh(ctx, 3, e, np.arange(n, dtype=np.int64), c, tile_nodes=8)
+    return m, c, e
+
+
+# ---------------------------------------------------------------------------
+# the reference's own golden vectors, through the CUDA path
+# ---------------------------------------------------------------------------
+
+def test_gold_mdot(P, ctx):
+    m, c, e = _cube_mesh(P, ctx)
+    n = len(c)
+    m.put("velocity", P.NW_NODE, np.full((n, 3), 10.0))
+    m.put("dpdx", P.NW_NODE, np.zeros((n, 3)))
+    m.put("density", P.NW_NODE, np.ones(n))
+    m.put("pressure", P.NW_NODE, np.zeros(n))
+    m.put("momentum_diag", P.NW_NODE, np.ones(n))
+    m.put("edge_area_vector", P.NW_EDGE, uc.edge_area(c, e))
+    m.register("mass_flow_rate", P.NW_EDGE, 1)
+    m.mdot_edge(1.0, 1.0)
+    mdot = m.download("mass_flow_rate")
+    assert np.max(np.abs(mdot - 2.5)) <= 1e-14  # UnitTestMdotAlg.C:66-77
+
+
+def test_gold_nodal_grad(P, ctx):
+    m, c, e = _cube_mesh(P, ctx)
+    n = len(c)
+    m.put("dual_nodal_volume", P.NW_NODE, np.full(n, 0.125))
+    m.put("edge_area_vector", P.NW_EDGE, uc.edge_area(c, e))
+    m.put("turbulent_ke", P.NW_NODE, 2 * c[:, 0] + 2 * c[:, 1] + 2 * c[:, 2])
+    m.register("dkdx", P.NW_NODE, 3)
+    m.nodal_grad_edge("turbulent_ke", "dkdx")
+    g = m.download("dkdx")
+    assert np.max(np.abs(g.ravel() - np.array(G["nodal_grad_scalar"]))) <= 1e-16
+    m.put("velocity", P.NW_NODE, 2.0 * c)
+    m.register("dudx", P.NW_NODE, 9)
+    m.nodal_grad_edge("velocity", "dudx")
+    g = m.download("dudx")
+    assert np.max(np.abs(g[:, [0, 4, 8]].ravel() -
+                         np.array(G["nodal_grad_vector_diag"]))) <= 1e-16
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_gold_continuity(P, ctx, mode):
+    m, c, e = _cube_mesh(P, ctx)
+    n = len(c)
+    m.put("velocity", P.NW_NODE, uc.velocity(c))
+    m.put("dpdx", P.NW_NODE, uc.dpdx(c))
+    m.put("density", P.NW_NODE, np.ones(n))
+    m.put("pressure", P.NW_NODE, uc.pressure(c))
+    m.put("momentum_diag", P.NW_NODE, np.ones(n))
+    m.put("edge_area_vector", P.NW_EDGE, uc.edge_area(c, e))
+    ls = P.LinearSystem(m)
+    ls.set_scatter_mode(mode)
+    ls.buildEdgeToNodeGraph()
+    ls.finalizeLinearSystem()
+    ls.zeroSystem()
+    ls.assemble_continuity_edge(dt=1.0, gamma1=1.0)
+    vals, rhs = ls.values()
+    g = ls.graph()
+    dense = np.zeros((n, n))
+    dense[g["rows"], g["cols"]] = vals
+    assert np.max(np.abs(rhs[0] - np.array(G["continuity_adv"]["rhs"]))) <= 1e-12
+    assert np.max(np.abs(dense - np.array(G["continuity_adv"]["lhs"]))) <= 1e-12
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_gold_scalar_csr(P, ctx, mode):
+    m, c, e = _cube_mesh(P, ctx)
+    n = len(c)
+    av = uc.edge_area(c, e)
+    z, rho, visc = uc.mixture_fraction_fields(c)
+    vel = uc.velocity(c)
+    m.put("velocity", P.NW_NODE, vel)
+    m.put("density", P.NW_NODE, rho)
+    m.put("mixture_fraction", P.NW_NODE, z)
+    m.put("dzdx", P.NW_NODE, np.zeros((n, 3)))
+    m.put("viscosity", P.NW_NODE, visc)
+    m.put("edge_area_vector", P.NW_EDGE, av)
+    m.put("mass_flow_rate", P.NW_EDGE, uc.fixture_mdot(e, vel, rho, av))
+    ls = P.LinearSystem(m)
+    ls.set_scatter_mode(mode)
+    ls.buildEdgeToNodeGraph()
+    ls.finalizeLinearSystem()
+    gold = G["scalar_adv_diff"]["serial"]
+    g = ls.graph()
+    assert g["row_start_owned"].tolist() == gold["rowOffsets"]
+    assert g["cols"].tolist() == gold["cols"]
+    ls.zeroSystem()
+    ls.assemble_scalar_edge("mixture_fraction", "dzdx", "viscosity", alpha=0.0,
+                            alpha_upw=0.0, ho_upwind=0.0, relax_fac=1.0,
+                            pf=P.peclet_fn("classic", 0.0))
+    vals, rhs = ls.values()
+    assert np.max(np.abs(vals - np.array(gold["vals"]))) <= 1e-12
+    assert np.max(np.abs(rhs[0] - np.array(gold["rhs"]))) <= 1e-12
+
+
+@pytest.mark.parametrize("kind", ["uvw", "mono"])
+def test_gold_momentum(P, ctx, kind):
+    """UnitTestMomentumAdvDiffEdge.C golds: the fake linear system keeps the
+    (d,d) component pairs; the monolithic CSR holds them at (3i+d, 3j+d), the
+    UVW system holds the d = 0 pairs + all three RHS."""
+    m, c, e = _cube_mesh(P, ctx)
+    n = len(c)
+    av = uc.edge_area(c, e)
+    vel, rho = uc.velocity(c), np.ones(n)
+    m.put("velocity", P.NW_NODE, vel)
+    m.put("dudx", P.NW_NODE, uc.dudx(c))
+    m.put("viscosity", P.NW_NODE, np.full(n, 0.1))
+    m.put("density", P.NW_NODE, rho)
+    m.put("abl_wall_no_slip_wall_func_node_mask", P.NW_NODE, np.ones(n))
+    m.put("edge_area_vector", P.NW_EDGE, av)
+    m.put("mass_flow_rate", P.NW_EDGE, uc.fixture_mdot(e, vel, rho, av))
+    m.put("peclet_factor", P.NW_EDGE, np.zeros(len(e)))
+    glhs = np.array(G["momentum_adv_diff"]["lhs"])
+    grhs = np.array(G["momentum_adv_diff"]["rhs"])
+    opts = dict(include_divu=0.0, alpha=0.0, alpha_upw=0.0, ho_upwind=0.0,
+                relax_fac=1.0)
+    if kind == "mono":
+        ls = P.LinearSystem(m, P.NW_LINSYS_HYPRE, 3)
+        ls.buildEdgeToNodeGraph()
+        ls.finalizeLinearSystem()
+        ls.zeroSystem()
+        ls.assemble_momentum_edge("viscosity", **opts)
+        vals, rhs = ls.values()
+        g = ls.graph()
+        same = (g["rows"] % 3) == (g["cols"] % 3)
+        got = np.zeros((3 * n, 3 * n))
+        got[g["rows"][same], g["cols"][same]] = vals[same]
+        assert np.max(np.abs(got - glhs)) <= 1e-12
+        assert np.max(np.abs(rhs[0] - grhs)) <= 1e-12
+    else:
+        for mode in (0, 1):
+            ls = P.LinearSystem(m, P.NW_LINSYS_HYPRE_UVW, 3)
+            ls.set_scatter_mode(mode)
+            ls.buildEdgeToNodeGraph()
+            ls.finalizeLinearSystem()
+            ls.zeroSystem()
+            ls.assemble_momentum_edge("viscosity", **opts)
+            vals, rhs = ls.values()
+            g = ls.graph()
+            got = np.zeros((n, n))
+            got[g["rows"], g["cols"]] = vals
+            assert np.max(np.abs(got - glhs[0::3, 0::3])) <= 1e-12
+            assert np.max(np.abs(rhs.T.ravel() - grhs)) <= 1e-12
+
+
+# ---------------------------------------------------------------------------
+# seeded synthetic cases against the oracle
+# ---------------------------------------------------------------------------
+
+SWEEP_CASES = [
+    dict(dims=(12, 10, 8), tile_nodes=64),
+    dict(dims=(12, 10, 8), tile_nodes=64, mode=1),
+    dict(dims=(20, 17, 13), tile_nodes=192),
+    dict(dims=(9, 7, 5), tile_nodes=32, periodic=(True, True),
+         lengths=(5000.0, 5000.0, 1000.0)),
+    dict(dims=(9, 7, 5), tile_nodes=32, periodic=(True, True),
+         lengths=(5000.0, 5000.0, 1000.0), mode=1),
+    dict(dims=(16, 12, 10), tile_nodes=100, warp=0.15, shuffle_bucket=512),
+    dict(dims=(14, 11, 40), tile_nodes=256, zstretch=1.15),
+    dict(dims=(1, 1, 1), tile_nodes=8),
+    dict(dims=(2, 1, 1), tile_nodes=1024),
+]
+
+
+@pytest.mark.parametrize("kw", SWEEP_CASES,
+                         ids=lambda c: "-".join("%s=%s" % kv for kv in sorted(c.items())))
+def test_lowmach_sweep_vs_oracle(P, ctx, kw):
+    res = pu.run_lowmach_case(P, ctx, **kw)
+    bad = {k: v for k, v in res.items() if not v < 1.0}
+    assert not bad, bad
+
+
+def test_monolithic_momentum_vs_oracle(P, ctx):
+    case = pu.Case(dims=(10, 9, 7))
+    mesh = case.box.make_mesh(ctx, tile_nodes=64)
+    pu.upload_state(P, mesh, case)
+    omdot = case.oracle_mdot()
+    opec = case.oracle_pecfac(orc.peclet("classic", 1.0))
+    mesh.upload("mass_flow_rate", omdot)
+    mesh.upload("peclet_factor", opec)
+    mesh.register("udiag_out", P.NW_NODE, 1)
+    ls = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE, 3)
+    ls.buildEdgeToNodeGraph()
+    ls.finalizeLinearSystem()
+    ls.zeroSystem()
+    ls.assemble_momentum_edge("viscosity", diag_field="udiag_out", **pu.MOM_OPTS)
+    vals, rhs = ls.values()
+    g = case.oracle_graph(num_dof=3)
+    ud = np.zeros(case.n_nodes)
+    o = pu.oracle_momentum(case, g, omdot, opec, uvw=False, udiag=ud)
+    ov, orhs = o.get()
+    av, arhs = o.get_abs()
+    assert pu.scaled_err(vals, ov, av) < 1
+    assert pu.scaled_err(rhs, orhs, arhs) < 1
+    # NGPApplyCoeff::extract_diagonal side channel
+    got = mesh.download("udiag_out")
+    assert pu.scaled_err(got, ud, np.abs(ud) + np.max(np.abs(ud)) * 1e-2) < 1
+
+
+def test_skipped_rows_and_accumulation(P, ctx):
+    """Dirichlet rows are left untouched; a second assembly without zeroSystem
+    accumulates (HypreLinearSystem.C:1394-1405: values are zeroed once per
+    loadComplete, several algorithms add into the same arrays)."""
+    case = pu.Case(dims=(8, 7, 6))
+    mesh = case.box.make_mesh(ctx, tile_nodes=48)
+    pu.upload_state(P, mesh, case)
+    skipped = np.array([0, 5, 17, 100, 311], dtype=np.int64)
+    g = case.oracle_graph(skipped=skipped)
+    o = pu.oracle_continuity(case, g)
+    ov, orhs = o.get()
+    av, arhs = o.get_abs()
+    for mode in (0, 1):
+        ls = P.LinearSystem(mesh)
+        ls.set_scatter_mode(mode)
+        ls.set_skipped_rows(skipped)
+        ls.buildEdgeToNodeGraph()
+        ls.finalizeLinearSystem()
+        ls.zeroSystem()
+        ls.assemble_continuity_edge(**pu.CONT_OPTS)
+        vals, rhs = ls.values()
+        assert pu.scaled_err(vals, ov, av) < 1
+        assert pu.scaled_err(rhs, orhs, arhs) < 1
+        ls.assemble_continuity_edge(**pu.CONT_OPTS)  # accumulate
+        vals2, rhs2 = ls.values()
+        assert pu.scaled_err(vals2, 2 * ov, 2 * av) < 1
+        assert pu.scaled_err(rhs2, 2 * orhs, 2 * arhs) < 1
+        ls.close()
+
+
+def test_no_silent_fallback(P, ctx):
+    """missing fields / wrong order are errors, never a fallback"""
+    case = pu.Case(dims=(3, 3, 3))
+    mesh = case.box.make_mesh(ctx)
+    with pytest.raises(P.NwError, match="not registered"):
+        mesh.mdot_edge()
+    ls = P.LinearSystem(mesh)
+    with pytest.raises(P.NwError):
+        ls.finalizeLinearSystem()  # buildEdgeToNodeGraph not called
+
+
+# ---------------------------------------------------------------------------
+# full BASELINE size: properties that do not need the oracle
+# ---------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def big(P, ctx):
+    n = int(os.environ.get("NW_TEST_BIG", "128"))
+    case = pu.Case(dims=(n, n, n))
+    mesh = case.box.make_mesh(ctx)
+    pu.upload_state(P, mesh, case)
+    mesh.mdot_edge()
+    mesh.peclet_edge("viscosity", P.peclet_fn("classic", 1.0))
+    return case, mesh
+
+
+def test_full_size_determinism_and_variants(P, ctx, big):
+    case, mesh = big
+    out = {}
+    for mode in (0, 0, 1):
+        ls = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE_UVW, 3)
+        ls.set_scatter_mode(mode)
+        ls.buildEdgeToNodeGraph()
+        ls.finalizeLinearSystem()
+        ls.zeroSystem()
+        ls.assemble_momentum_edge("viscosity", **pu.MOM_OPTS)
+        out.setdefault(mode, []).append(ls.values())
+        ls.close()
+    (v0, r0), (v1, r1) = out[0]
+    assert np.array_equal(v0, v1) and np.array_equal(r0, r1), \
+        "segmented reduction must be bitwise reproducible"
+    va, ra = out[1][0]
+    # atomic variant: same numbers up to summation order
+    scale_v = np.maximum(np.abs(v0), np.max(np.abs(v0)) * 1e-3)
+    scale_r = np.maximum(np.abs(r0), np.max(np.abs(r0)) * 1e-3)
+    assert pu.scaled_err(va, v0, scale_v) < 1
+    assert pu.scaled_err(ra, r0, scale_r) < 1
+
+
+def test_full_size_conservation(P, ctx, big):
+    """continuity: every 2x2 block is [[-f, f], [f, -f]] and rhs = [-m, +m], so
+    each matrix row sums to zero and the rhs sums to zero; diagonal > 0."""
+    case, mesh = big
+    ls = P.LinearSystem(mesh)
+    ls.buildEdgeToNodeGraph()
+    ls.finalizeLinearSystem()
+    ls.zeroSystem()
+    ls.assemble_continuity_edge(**pu.CONT_OPTS)
+    vals, rhs = ls.values()
+    g = ls.graph()
+    rs = g["row_start_owned"]
+    rowsum = np.add.reduceat(vals, rs[:-1])
+    rowabs = np.add.reduceat(np.abs(vals), rs[:-1])
+    assert np.max(np.abs(rowsum) / rowabs) < 1e-13
+    assert abs(np.sum(rhs)) <= 1e-12 * np.sum(np.abs(rhs))
+    diag = vals[np.flatnonzero(g["rows"] == g["cols"])]
+    assert np.all(diag > 0)
+    n2 = ls.rhs_norm2()
+    assert abs(n2[0] - np.sum(rhs[0] ** 2)) <= 1e-12 * n2[0]
+    # gradient of a linear field is exact at interior nodes
+    f = 3.0 * case.box.coords[:, 0] - 2.0 * case.box.coords[:, 1] + 0.5 * case.box.coords[:, 2]
+    mesh.put("lin", P.NW_NODE, f)
+    mesh.register("dlin", P.NW_NODE, 3)
+    mesh.nodal_grad_edge("lin", "dlin")
+    gl = mesh.download("dlin")
+    n = case.box.dims[0]
+    ijk = np.rint(case.box.coords).astype(int)
+    interior = np.all((ijk > 0) & (ijk < n), axis=1)
+    assert np.max(np.abs(gl[interior] - np.array([3.0, -2.0, 0.5]))) < 1e-10
+    ls.close()
