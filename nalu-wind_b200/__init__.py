@@ -179,6 +179,19 @@ def lib():
                                           C.POINTER(C.c_int64)]
     L.nw_linsys_get_values.argtypes = [vp, vp, vp]
     L.nw_linsys_rhs_norm2.argtypes = [vp, c_f64p]
+    L.nw_mesh_halo_send_count.argtypes = [vp, C.c_int, c_i64p]
+    L.nw_mesh_halo_get_send.argtypes = [vp, C.c_int, c_i64p]
+    L.nw_mesh_halo_set_recv.argtypes = [vp, C.c_int, C.c_int64, c_i64p]
+    L.nw_mesh_halo_commit.argtypes = [vp]
+    L.nw_field_parallel_sum.argtypes = [vp, C.c_int]
+    L.nw_linsys_halo_send_info.argtypes = [vp, C.c_int, c_i64p, c_i64p]
+    L.nw_linsys_halo_get_send.argtypes = [vp, C.c_int, c_i64p, c_i64p, c_i64p]
+    L.nw_linsys_halo_set_recv.argtypes = [vp, C.c_int, C.c_int64, c_i64p,
+                                          c_i64p, c_i64p]
+    L.nw_linsys_halo_commit.argtypes = [vp]
+    L.nw_linsys_halo_get_recv_slots.argtypes = [vp, C.c_int, c_i64p, c_i64p,
+                                                c_i64p, c_i64p]
+    L.nw_linsys_get_extra.argtypes = [vp, c_i64p, c_i64p, c_i64p]
     _lib = L
     return L
 
@@ -330,6 +343,26 @@ class Mesh:
         _chk(lib().nw_nodal_grad_edge(self.h, self.field_id(phi),
                                       self.field_id(grad)))
 
+    # --- shared-node exchange lists (caller-side transport) ---
+    def halo_send(self, peer):
+        n = C.c_int64()
+        _chk(lib().nw_mesh_halo_send_count(self.h, peer, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.int64)
+        _chk(lib().nw_mesh_halo_get_send(self.h, peer,
+                                         out.ctypes.data_as(c_i64p)))
+        return out
+
+    def halo_set_recv(self, peer, own_hids):
+        a = np.ascontiguousarray(own_hids, dtype=np.int64)
+        _chk(lib().nw_mesh_halo_set_recv(self.h, peer, a.size,
+                                         a.ctypes.data_as(c_i64p)))
+
+    def halo_commit(self):
+        _chk(lib().nw_mesh_halo_commit(self.h))
+
+    def parallel_sum(self, name):
+        _chk(lib().nw_field_parallel_sum(self.h, self.field_id(name)))
+
     def close(self):
         if self.h:
             lib().nw_mesh_destroy(self.h)
@@ -424,9 +457,55 @@ class LinearSystem:
     def loadComplete(self):
         _chk(lib().nw_linsys_load_complete(self.h))
 
+    # --- shared-row exchange structure (caller-side transport) ---
+    def halo_send(self, peer):
+        nr, nv = C.c_int64(), C.c_int64()
+        _chk(lib().nw_linsys_halo_send_info(self.h, peer, C.byref(nr),
+                                            C.byref(nv)))
+        rows = np.zeros(nr.value, dtype=np.int64)
+        lens = np.zeros(nr.value, dtype=np.int64)
+        cols = np.zeros(nv.value, dtype=np.int64)
+        _chk(lib().nw_linsys_halo_get_send(
+            self.h, peer, rows.ctypes.data_as(c_i64p),
+            lens.ctypes.data_as(c_i64p), cols.ctypes.data_as(c_i64p)))
+        return rows, lens, cols
+
+    def halo_set_recv(self, peer, rows, lens, cols):
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        lens = np.ascontiguousarray(lens, dtype=np.int64)
+        cols = np.ascontiguousarray(cols, dtype=np.int64)
+        _chk(lib().nw_linsys_halo_set_recv(
+            self.h, peer, rows.size, rows.ctypes.data_as(c_i64p),
+            lens.ctypes.data_as(c_i64p), cols.ctypes.data_as(c_i64p)))
+
+    def halo_commit(self):
+        _chk(lib().nw_linsys_halo_commit(self.h))
+
+    def halo_recv_slots(self, peer):
+        nv, nr = C.c_int64(), C.c_int64()
+        _chk(lib().nw_linsys_halo_get_recv_slots(
+            self.h, peer, C.byref(nv), None, C.byref(nr), None))
+        vs = np.zeros(nv.value, dtype=np.int64)
+        rr = np.zeros(nr.value, dtype=np.int64)
+        _chk(lib().nw_linsys_halo_get_recv_slots(
+            self.h, peer, C.byref(nv), vs.ctypes.data_as(c_i64p), C.byref(nr),
+            rr.ctypes.data_as(c_i64p)))
+        return vs, rr
+
+    def extra(self):
+        n = C.c_int64()
+        _chk(lib().nw_linsys_get_extra(self.h, C.byref(n), None, None))
+        rows = np.zeros(n.value, dtype=np.int64)
+        cols = np.zeros(n.value, dtype=np.int64)
+        _chk(lib().nw_linsys_get_extra(self.h, C.byref(n),
+                                       rows.ctypes.data_as(c_i64p),
+                                       cols.ctypes.data_as(c_i64p)))
+        return rows, cols
+
     def values(self):
         s = self.sizes
         nnz = s.num_nonzeros_owned + s.num_nonzeros_shared
+        nnz += self.extra()[0].size
         rows = s.num_rows_owned + s.num_rows_shared
         vals = np.zeros(nnz)
         rhs = np.zeros((s.num_rhs, rows))
