@@ -826,7 +826,9 @@ __global__ void __launch_bounds__(kTileThreads) grad_tile_kernel(
       }
     }
     seg_scan<NV>(acc, key, lane);
-    if (valid && seg_tail(key, lane)) {
+    /* the shuffle inside seg_tail needs every lane: never short-circuit it */
+    const bool tail = seg_tail(key, lane);
+    if (valid && tail) {
 #pragma unroll
       for (int k = 0; k < NV; ++k)
         s_out[k * outStride + ent] += acc[k];
