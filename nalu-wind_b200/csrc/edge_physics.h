@@ -31,21 +31,69 @@
 
 namespace nw {
 
+/* Reciprocal for the divisions of the edge kernels.  The FP64 pipe is the
+ * second roofline of this path, and nvcc's IEEE divide
+ * costs ~12 FP64 instructions plus a branchy slow path that zero numerators
+ * (limiter on a flat field) fall into.  On the device: MUFU.RCP64H seed
+ * (rel. error <= 2^-23) + two Newton steps = 1 MUFU + 4 DFMA, <= 2 ulp for
+ * normal-range arguments -- every denominator here (a.dx, rho, momentum_diag,
+ * dq^2 + 1e-16, D + 1e-16, relaxation factors) is normal-range for valid
+ * input; 0 / denormal / inf arguments give inf / NaN exactly where the
+ * reference's divide gives inf / NaN downstream.  The 1e-12 parity bar is
+ * three orders of magnitude above this.  Host (CPU walk-through): 1.0 / x. */
+NW_HD double
+nw_rcp(double x)
+{
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+#else
+  return 1.0 / x;
+#endif
+}
+
+/* exactly-rounded, never-contracted fp64 ops for the Peclet chain (see
+ * peclet_eval); g++ on baseline x86-64 does not contract either */
+#if defined(__CUDA_ARCH__)
+#define NW_XMUL(a, b) __dmul_rn((a), (b))
+#define NW_XADD(a, b) __dadd_rn((a), (b))
+#define NW_XDIV(a, b) __ddiv_rn((a), (b))
+#else
+#define NW_XMUL(a, b) ((a) * (b))
+#define NW_XADD(a, b) ((a) + (b))
+#define NW_XDIV(a, b) ((a) / (b))
+#endif
+
 NW_HD double
 peclet_eval(const nw_peclet_fn& f, double pecnum)
 {
   if (f.form == NW_PECLET_CLASSIC) {
-    const double modPeclet = f.a * pecnum;
-    return modPeclet * modPeclet / (5.0 + modPeclet * modPeclet);
+    /* Exactly-rounded, un-contracted arithmetic on purpose: at high Peclet
+     * number the factor is 1 - O(1e-11) and the kernels use (1 - pecfac), so a
+     * 1-ulp difference in pecfac (FMA contraction of 5 + m*m, or a reciprocal-
+     * multiply divide) shows up at ~1e-11 relative in off-diagonal entries.
+     * Worse, where 5/m^2 is about half an ulp of 1 the rounding of pecfac
+     * flips on any perturbation of the Peclet number, so the whole chain
+     * (peclet_number too) uses IEEE mul/add/div in the reference's order: the
+     * fused-Peclet path and the scalar kernel then see bit-identical factors
+     * to the MomentumEdgePecletAlg edge field (src/PecletFunction.C:41-45). */
+    const double modPeclet = NW_XMUL(f.a, pecnum);
+    const double m2 = NW_XMUL(modPeclet, modPeclet);
+    return NW_XDIV(m2, NW_XADD(5.0, m2));
   }
-  return 0.50 * (1.0 + tanh((pecnum - f.a) / f.b));
+  return 0.50 * (1.0 + tanh((pecnum - f.a) * nw_rcp(f.b)));
 }
 
 NW_HD double
 van_leer(double dqm, double dqp, double eps)
 {
-  return (2.0 * (dqm * dqp + fabs(dqm * dqp))) /
-         ((dqm + dqp) * (dqm + dqp) + eps);
+  return (2.0 * (dqm * dqp + fabs(dqm * dqp))) *
+         nw_rcp((dqm + dqp) * (dqm + dqp) + eps);
 }
 
 /* ---- node state bundles (what each kernel stages per node) ---- */
@@ -97,7 +145,11 @@ mdot_core(
 {
   const double om_interpTogether = 1.0 - interpTogether;
   MdotCore<ND> r;
-  r.projTimeScale = 0.5 * (1.0 / L.ud + 1.0 / R.ud);
+  /* one reciprocal per node instead of a divide per use: differs from the
+   * reference's g/udiag by <= 1 ulp per term, far inside the 1e-12 bar, and
+   * removes 2*ND fp64 divides (the FP64 pipe is the second roofline here) */
+  const double invUdL = nw_rcp(L.ud), invUdR = nw_rcp(R.ud);
+  r.projTimeScale = 0.5 * (invUdL + invUdR);
   r.rhoIp = 0.5 * (L.rho + R.rho);
   double axdx = 0.0, asq = 0.0;
 #pragma unroll
@@ -106,7 +158,7 @@ mdot_core(
     asq += av[d] * av[d];
     axdx += av[d] * dxj;
   }
-  const double inv_axdx = 1.0 / axdx;
+  const double inv_axdx = nw_rcp(axdx);
   double tmdot = -r.projTimeScale * (R.p - L.p) * asq * inv_axdx;
 #pragma unroll
   for (int d = 0; d < ND; ++d) {
@@ -114,7 +166,7 @@ mdot_core(
     const double kxj = av[d] - asq * inv_axdx * dxj;
     const double rhoUjIp = 0.5 * (R.rho * R.u[d] + L.rho * L.u[d]);
     const double ujIp = 0.5 * (R.u[d] + L.u[d]);
-    const double GjIp = 0.5 * (R.g[d] / R.ud + L.g[d] / L.ud);
+    const double GjIp = 0.5 * (R.g[d] * invUdR + L.g[d] * invUdL);
     tmdot += (interpTogether * rhoUjIp + om_interpTogether * r.rhoIp * ujIp +
               GjIp) *
                av[d] -
@@ -137,16 +189,16 @@ continuity_edge(
   double& lhsfac,
   double& tmdot_out)
 {
-  const double tauScale = o.dt / o.gamma1;
   const double solveInc = o.solve_incompressible;
   const double om_solveInc = 1.0 - solveInc;
   MdotCore<ND> c = mdot_core<ND>(L, R, av, o.noc_fac, o.interp_together);
-  const double denScale = (1.0 / c.rhoIp) * solveInc + om_solveInc;
+  const double denScale = nw_rcp(c.rhoIp) * solveInc + om_solveInc;
+  const double invTauScale = o.gamma1 * nw_rcp(o.dt); /* 1 / (dt / gamma1) */
   double tmdot = c.tmdot;
-  tmdot /= tauScale;
+  tmdot *= invTauScale;
   tmdot *= denScale;
   /* -asq * inv_axdx * projTimeScale * denScale / tauScale, left to right */
-  lhsfac = -c.asq_inv_axdx * c.projTimeScale * denScale / tauScale;
+  lhsfac = -c.asq_inv_axdx * c.projTimeScale * denScale * invTauScale;
   tmdot_out = tmdot;
 }
 
@@ -157,13 +209,15 @@ NW_HD double
 peclet_number(const PecNode<ND>& L, const PecNode<ND>& R, double eps)
 {
   double udotx = 0.0;
-  const double diffIp = 0.5 * (L.mu / L.rho + R.mu / R.rho);
+  const double diffIp =
+    NW_XMUL(0.5, NW_XADD(NW_XDIV(L.mu, L.rho), NW_XDIV(R.mu, R.rho)));
 #pragma unroll
   for (int d = 0; d < ND; ++d) {
     const double dxj = R.x[d] - L.x[d];
-    udotx += 0.5 * dxj * (R.v[d] + L.v[d]);
+    udotx = NW_XADD(
+      udotx, NW_XMUL(NW_XMUL(0.5, dxj), NW_XADD(R.v[d], L.v[d])));
   }
-  return fabs(udotx) / (diffIp + eps);
+  return NW_XDIV(fabs(udotx), NW_XADD(diffIp, eps));
 }
 
 /* ---- scalar ---- */
@@ -184,22 +238,20 @@ scalar_edge(
   const double alpha = o.alpha;
   const double alphaUpw = o.alpha_upw;
   const double hoUpwind = o.ho_upwind;
-  const double relaxFac = o.relax_fac;
+  const double invRelax = nw_rcp(o.relax_fac); /* warp-uniform */
   const double om_alpha = 1.0 - alpha;
   const double om_alphaUpw = 1.0 - alphaUpw;
 
   const double viscIp = 0.5 * (L.mu + R.mu);
-  const double diffIp = 0.5 * (L.mu / L.rho + R.mu / R.rho);
 
-  double axdx = 0.0, asq = 0.0, udotx = 0.0;
+  double axdx = 0.0, asq = 0.0;
 #pragma unroll
   for (int d = 0; d < ND; ++d) {
     const double dxj = R.x[d] - L.x[d];
     asq += av[d] * av[d];
     axdx += av[d] * dxj;
-    udotx += 0.5 * dxj * (R.v[d] + L.v[d]);
   }
-  const double inv_axdx = 1.0 / axdx;
+  const double inv_axdx = nw_rcp(axdx);
 
   double dqL = 0.0, dqR = 0.0, nonOrth = 0.0;
 #pragma unroll
@@ -211,8 +263,21 @@ scalar_edge(
     nonOrth += -viscIp * kxj * 0.5 * (R.dq[d] + L.dq[d]);
   }
 
-  const double pecnum = fabs(udotx) / (diffIp + eps);
-  const double pecfac = peclet_eval(o.pf, pecnum);
+  /* ScalarEdgeSolverAlg.C:128-143: same Peclet number as the momentum Peclet
+   * algorithm, with D = diffFluxCoeff / rho */
+  PecNode<ND> pl, pr;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    pl.x[d] = L.x[d];
+    pr.x[d] = R.x[d];
+    pl.v[d] = L.v[d];
+    pr.v[d] = R.v[d];
+  }
+  pl.rho = L.rho;
+  pr.rho = R.rho;
+  pl.mu = L.mu;
+  pr.mu = R.mu;
+  const double pecfac = peclet_eval(o.pf, peclet_number<ND>(pl, pr, eps));
   const double om_pecfac = 1.0 - pecfac;
 
   double limitL = 1.0, limitR = 1.0;
@@ -230,10 +295,10 @@ scalar_edge(
   const double lhsfac = -viscIp * asq * inv_axdx;
   const double diffFlux = lhsfac * (R.q - L.q) + nonOrth;
 
-  double a00 = -lhsfac / relaxFac;
+  double a00 = -lhsfac * invRelax;
   double a01 = lhsfac;
   double a10 = lhsfac;
-  double a11 = -lhsfac / relaxFac;
+  double a11 = -lhsfac * invRelax;
 
   const double qIp = 0.5 * (R.q + L.q);
   const double qUpw = (mdot > 0) ? (alphaUpw * qIpL + om_alphaUpw * qIp)
@@ -249,19 +314,19 @@ scalar_edge(
 
   double alhsfac = 0.5 * (mdot + fabs(mdot)) * pecfac * alphaUpw +
                    0.5 * alpha * om_pecfac * mdot;
-  a00 += alhsfac / relaxFac;
+  a00 += alhsfac * invRelax;
   a10 -= alhsfac;
 
   alhsfac = 0.5 * (mdot - fabs(mdot)) * pecfac * alphaUpw +
             0.5 * alpha * om_pecfac * mdot;
-  a11 -= alhsfac / relaxFac;
+  a11 -= alhsfac * invRelax;
   a01 += alhsfac;
 
   alhsfac = 0.5 * mdot * (pecfac * om_alphaUpw + om_pecfac * om_alpha);
-  a00 += alhsfac / relaxFac;
+  a00 += alhsfac * invRelax;
   a01 += alhsfac;
   a10 -= alhsfac;
-  a11 -= alhsfac / relaxFac;
+  a11 -= alhsfac * invRelax;
 
   a[0] = a00;
   a[1] = a01;
@@ -303,7 +368,7 @@ momentum_edge(
   const double alpha = o.alpha;
   const double alphaUpw = o.alpha_upw;
   const double hoUpwind = o.ho_upwind;
-  const double relaxFacU = o.relax_fac;
+  const double invRelaxU = nw_rcp(o.relax_fac); /* warp-uniform */
   const double om_alpha = 1.0 - alpha;
   const double om_alphaUpw = 1.0 - alphaUpw;
   const double density_upwinding_factor = 1.0; /* has_vof == 0 */
@@ -317,7 +382,7 @@ momentum_edge(
     asq += av[d] * av[d];
     axdx += av[d] * dxj;
   }
-  const double inv_axdx = 1.0 / axdx;
+  const double inv_axdx = nw_rcp(axdx);
 
   double duL[ND], duR[ND];
 #pragma unroll
@@ -407,24 +472,24 @@ momentum_edge(
   double sLL = 0.0, sLR = 0.0, sRL = 0.0, sRR = 0.0;
   double alhsfac = 0.5 * (mdot + fabs(mdot)) * pecfac * alphaUpw +
                    0.5 * alpha * om_pecfac * mdot;
-  sLL += alhsfac / relaxFacU;
+  sLL += alhsfac * invRelaxU;
   sRL -= alhsfac;
 
   alhsfac = 0.5 * (mdot - fabs(mdot)) * pecfac * alphaUpw +
             0.5 * alpha * om_pecfac * mdot;
-  sRR -= alhsfac / relaxFacU;
+  sRR -= alhsfac * invRelaxU;
   sLR += alhsfac;
 
   alhsfac = 0.5 * mdot * (pecfac * om_alphaUpw + om_pecfac * om_alpha);
-  sLL += alhsfac / relaxFacU;
+  sLL += alhsfac * invRelaxU;
   sLR += alhsfac;
   sRL -= alhsfac;
-  sRR -= alhsfac / relaxFacU;
+  sRR -= alhsfac * invRelaxU;
 
-  sLL -= dlhsfac / relaxFacU;
+  sLL -= dlhsfac * invRelaxU;
   sLR += dlhsfac;
   sRL += dlhsfac;
-  sRR -= dlhsfac / relaxFacU;
+  sRR -= dlhsfac * invRelaxU;
 
   res.sLL = sLL;
   res.sLR = sLR;
@@ -452,10 +517,11 @@ momentum_block_entry(
 {
   const double lhsfacNS = -r.viscIp * av[i] * av[j] * r.inv_axdx;
   const double s = (i == j) ? 1.0 : 0.0;
-  LL = s * r.sLL - lhsfacNS / relaxFacU;
+  const double invRelaxU = nw_rcp(relaxFacU);
+  LL = s * r.sLL - lhsfacNS * invRelaxU;
   LR = s * r.sLR + lhsfacNS;
   RL = s * r.sRL + lhsfacNS;
-  RR = s * r.sRR - lhsfacNS / relaxFacU;
+  RR = s * r.sRR - lhsfacNS * invRelaxU;
 }
 
 } // namespace nw

@@ -189,8 +189,8 @@ mesh_upload_plan(nw_mesh* m)
   if ((rc = upload(m->dTiles, p.tiles, s, &acc)) ||
       (rc = upload(m->dHalo, p.haloNodes, s, &acc)) ||
       (rc = upload(m->dLr, p.lr, s, &acc)) ||
-      (rc = upload(m->dHeNode, p.heNode, s, &acc)) ||
-      (rc = upload(m->dWarpNode, p.warpSplitNode, s, &acc)) ||
+      (rc = upload(m->dHeNode, p.heNodeEll, s, &acc)) ||
+      (rc = upload(m->dWarpNode, p.sliceOffNode, s, &acc)) ||
       (rc = upload(m->dPrimary, p.tileEdgePrimary, s, &acc)) ||
       (rc = upload(m->dNodeOfSlot, p.nodeOfSlot, s, &acc)) ||
       (rc = upload(m->dTileEdgeSrc, p.tileEdgeSrc, s, &acc)) ||
@@ -201,8 +201,8 @@ mesh_upload_plan(nw_mesh* m)
   d.tiles = m->dTiles.as<TileHdr>();
   d.haloNodes = m->dHalo.as<int32_t>();
   d.lr = m->dLr.as<uint32_t>();
-  d.heNode = m->dHeNode.as<uint32_t>();
-  d.warpSplitNode = m->dWarpNode.as<int32_t>();
+  d.heNodeEll = m->dHeNode.as<uint32_t>();
+  d.sliceOffNode = m->dWarpNode.as<int32_t>();
   d.primary = m->dPrimary.as<uint8_t>();
   return NW_OK;
 }
@@ -233,6 +233,7 @@ nw_mesh_create(nw_ctx* ctx, const nw_mesh_desc* desc, nw_mesh** out)
   d.maxStaged = even_up((int)m->plan.maxTileStaged);
   d.maxTileEdges = (int)m->plan.maxTileEdges;
   d.maxTileNodes = (int)m->plan.maxTileNodes;
+  d.maxTileEllNode = (int)m->plan.maxTileEllNode;
   if (ctx->device >= 0) {
     NW_CUDA(cudaSetDevice(ctx->device));
     if (int rc = mesh_upload_plan(m.get()))
@@ -678,18 +679,20 @@ linsys_upload(nw_linsys* ls)
     if ((rc = upload(ls->dLsTiles, ls->lp.tiles, s, nullptr)) ||
         (rc = upload(ls->dEntInfo, ls->lp.entInfo, s, nullptr)) ||
         (rc = upload(ls->dEntRhsRow, ls->lp.entRhsRow, s, nullptr)) ||
-        (rc = upload(ls->dHe, ls->lp.he, s, nullptr)) ||
-        (rc = upload(ls->dWarp, ls->lp.warpSplit, s, nullptr)) ||
+        (rc = upload(ls->dHe, ls->lp.heEll, s, nullptr)) ||
+        (rc = upload(ls->dWarp, ls->lp.sliceOff, s, nullptr)) ||
         (rc = upload(ls->dRuns, ls->lp.runs, s, nullptr)))
       return rc;
     ls->dev.tiles = ls->dLsTiles.as<LsTileHdr>();
     ls->dev.entInfo = ls->dEntInfo.as<EntInfo>();
     ls->dev.entRhsRow = ls->dEntRhsRow.as<int32_t>();
-    ls->dev.he = ls->dHe.as<uint32_t>();
-    ls->dev.warpSplit = ls->dWarp.as<int32_t>();
+    ls->dev.heEll = ls->dHe.as<uint32_t>();
+    ls->dev.sliceOff = ls->dWarp.as<int32_t>();
     ls->dev.runs = ls->dRuns.as<Run>();
     ls->dev.maxTileNnz = (int)ls->lp.maxTileNnz;
     ls->dev.maxTileEnts = (int)ls->lp.maxTileEnts;
+    ls->dev.maxTileEll = (int)ls->lp.maxTileEll;
+    ls->dev.maxTileRuns = (int)ls->lp.maxTileRuns;
     /* rows the tiles do not write */
     std::vector<uint8_t> isPer(ls->lp.uncoveredRows.size(), 0);
     for (size_t i = 0; i < isPer.size(); ++i) {

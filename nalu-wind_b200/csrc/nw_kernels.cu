@@ -9,9 +9,14 @@
  *   phase1: one thread per tile-edge evaluates the edge physics from shared
  *           memory (edge data is streamed coalesced from HBM) and leaves a
  *           compact per-edge result in shared memory;
- *   phase2: the tile's row-sorted half-edge list is reduced with a segmented
- *           warp-shuffle scan; segment tails deposit diagonal / rhs sums into
- *           the row staging buffer, every lane writes its own off-diagonal;
+ *   phase2: row-sorted reduction, one thread per matrix row: the row's
+ *           half-edges come from the sliced-ELL list (one coalesced record per
+ *           lane and step, staged by a TMA bulk copy), diagonal and rhs are
+ *           summed in registers in list order (deterministic), every
+ *           off-diagonal is stored once into the row staging buffer.  (Round-1
+ *           profile: the segmented warp-shuffle scan this replaces was 45 % of
+ *           all issued instructions, profiles/r01a_*; it survives only as the
+ *           warp aggregation of the atomic comparison variant);
  *   phase3: the staged rows are copied out in contiguous runs -- each matrix
  *           value and rhs entry is written exactly once, no atomics, no
  *           zero-fill pass (replaces resetCoeffApplierData's deep_copy(0) and
@@ -94,7 +99,46 @@ tma_load_1d(void* dstSmem, const void* srcGmem, uint32_t bytes, uint64_t* bar)
 }
 
 /* Stage NC node components of one tile: own range by TMA, halo by gather.
- * s_node[c*stride + i]; i < nOwnPad own, nOwnPad + k halo k. */
+ * s_node[c*stride + i]; i < nOwnPad own, nOwnPad + k halo k.  The caller has
+ * initialised `bar` (count 1) and synchronised the CTA. */
+template <int NC>
+__device__ __forceinline__ void
+stage_nodes_issue(
+  double* s_node,
+  int stride,
+  const NodeComps& nc,
+  const TileHdr& h,
+  uint64_t* bar)
+{
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = (uint32_t)h.nOwnPad * 8u;
+    mbar_expect_tx(bar, bytes * NC);
+    if (bytes) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        tma_load_1d(s_node + c * stride, nc.c[c] + h.node0, bytes, bar);
+    }
+  }
+}
+
+template <int NC>
+__device__ __forceinline__ void
+stage_halo_gather(
+  double* s_node,
+  int stride,
+  const NodeComps& nc,
+  const TileHdr& h,
+  const int32_t* __restrict__ haloNodes)
+{
+  const int32_t* halo = haloNodes + h.haloPtr;
+  for (int k = threadIdx.x; k < h.nHalo; k += blockDim.x) {
+    const int32_t g = __ldg(halo + k);
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      s_node[c * stride + h.nOwnPad + k] = __ldg(nc.c[c] + g);
+  }
+}
+
 template <int NC>
 __device__ __forceinline__ void
 stage_nodes(
@@ -108,22 +152,16 @@ stage_nodes(
   if (threadIdx.x == 0)
     mbar_init(bar, 1);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const uint32_t bytes = (uint32_t)h.nOwnPad * 8u;
-    mbar_expect_tx(bar, bytes * NC);
-#pragma unroll
-    for (int c = 0; c < NC; ++c)
-      tma_load_1d(s_node + c * stride, nc.c[c] + h.node0, bytes, bar);
-  }
-  const int32_t* halo = haloNodes + h.haloPtr;
-  for (int k = threadIdx.x; k < h.nHalo; k += blockDim.x) {
-    const int32_t g = __ldg(halo + k);
-#pragma unroll
-    for (int c = 0; c < NC; ++c)
-      s_node[c * stride + h.nOwnPad + k] = __ldg(nc.c[c] + g);
-  }
+  stage_nodes_issue<NC>(s_node, stride, nc, h, bar);
+  stage_halo_gather<NC>(s_node, stride, nc, h, haloNodes);
   mbar_wait(bar, 0);
   __syncthreads();
+}
+
+__device__ __forceinline__ uint32_t
+round16(uint32_t bytes)
+{
+  return (bytes + 15u) & ~15u;
 }
 
 template <int NV>
@@ -172,6 +210,7 @@ template <int ND>
 struct ContinuityP
 {
   static constexpr int NC = 3 * ND + 3; /* x, u, dpdx, rho, p, udiag */
+  static constexpr int kMinBlocks = 3;  /* <= 85 registers: 3 CTAs per SM */
   static constexpr int NRES = 2;
   static constexpr int NR = 1;
   static constexpr bool kNeedsMdot = false;
@@ -201,12 +240,16 @@ struct ContinuityP
     load(ld, r, R);
     continuity_edge<ND>(L, R, av, o, res[0], res[1]);
   }
+  /* contribution of edge j to the row of its `side` node, read from the
+   * phase-1 results s_res[k * rs + j] */
   __device__ __forceinline__ static void contrib(
-    uint32_t side, const double* res, double& diag, double& off, double* rhs)
+    uint32_t side, const double* s_res, int rs, int j, double& diag,
+    double& off, double* rhs)
   {
-    diag = -res[0];
-    off = res[0];
-    rhs[0] = side ? res[1] : -res[1];
+    const double f = s_res[j], m = s_res[rs + j];
+    diag = -f;
+    off = f;
+    rhs[0] = side ? m : -m;
   }
   __device__ __forceinline__ static void block(
     const double* res, double& LL, double& LR, double& RL, double& RR,
@@ -224,6 +267,7 @@ template <int ND>
 struct ScalarP
 {
   static constexpr int NC = 3 * ND + 3; /* x, vrtm, dqdx, q, rho, dflux */
+  static constexpr int kMinBlocks = 2;
   static constexpr int NRES = 5;
   static constexpr int NR = 1;
   static constexpr bool kNeedsMdot = true;
@@ -254,11 +298,15 @@ struct ScalarP
     scalar_edge<ND>(L, R, av, mdot, o, res, res[4]);
   }
   __device__ __forceinline__ static void contrib(
-    uint32_t side, const double* res, double& diag, double& off, double* rhs)
+    uint32_t side, const double* s_res, int rs, int j, double& diag,
+    double& off, double* rhs)
   {
-    diag = side ? res[3] : res[0];
-    off = side ? res[2] : res[1];
-    rhs[0] = side ? res[4] : -res[4];
+    /* L row: (a00, a01, -flux); R row: (a11, a10, +flux) */
+    const double* p = s_res + j;
+    diag = p[side ? 3 * rs : 0];
+    off = p[side ? 2 * rs : rs];
+    const double f = p[4 * rs];
+    rhs[0] = side ? f : -f;
   }
   __device__ __forceinline__ static void block(
     const double* res, double& LL, double& LR, double& RL, double& RR,
@@ -277,6 +325,7 @@ struct MomentumUvwP
 {
   /* x, u, dudx, visc, rho, mask */
   static constexpr int NC = 2 * ND + ND * ND + 3;
+  static constexpr int kMinBlocks = 2; /* 128 registers x 256 threads x 2 */
   static constexpr int NRES = 4 + ND;
   static constexpr int NR = ND;
   static constexpr bool kNeedsMdot = true;
@@ -333,13 +382,17 @@ struct MomentumUvwP
       res[4 + d] = m.flux[d];
   }
   __device__ __forceinline__ static void contrib(
-    uint32_t side, const double* res, double& diag, double& off, double* rhs)
+    uint32_t side, const double* s_res, int rs, int j, double& diag,
+    double& off, double* rhs)
   {
-    diag = side ? res[3] : res[0];
-    off = side ? res[2] : res[1];
+    const double* p = s_res + j;
+    diag = p[side ? 3 * rs : 0];
+    off = p[side ? 2 * rs : rs];
 #pragma unroll
-    for (int d = 0; d < ND; ++d)
-      rhs[d] = side ? res[4 + d] : -res[4 + d];
+    for (int d = 0; d < ND; ++d) {
+      const double f = p[(4 + d) * rs];
+      rhs[d] = side ? f : -f;
+    }
   }
   __device__ __forceinline__ static void block(
     const double* res, double& LL, double& LR, double& RL, double& RR,
@@ -379,8 +432,40 @@ struct GmemLd
 /*  linear-system tile kernel                                          */
 /* ------------------------------------------------------------------ */
 
+/* shared-memory carve-up of ls_tile_kernel, shared by the kernel and the
+ * host-side size computation (all region sizes are multiples of 16 bytes) */
+template <class P>
+struct LsSmem
+{
+  int nodeRegion; /* doubles: node stage, reused as row staging after phase 1 */
+  int resStride;  /* doubles per result component */
+  int valsLen;    /* doubles: staged matrix values */
+  int entStride;  /* doubles per rhs column */
+  int ellLen;     /* uint32 records */
+  int entLen;     /* EntInfo / rhs-row records */
+  int runsLen;    /* Run records */
+  __host__ __device__ LsSmem(const MeshPlanDev& mp, const LsPlanDev& lp)
+  {
+    resStride = (mp.maxTileEdges + 1) & ~1;
+    valsLen = (lp.maxTileNnz + 1) & ~1;
+    entStride = (lp.maxTileEnts + 1) & ~1;
+    const int rowRegion = valsLen + P::NR * entStride;
+    const int stage = P::NC * mp.maxStaged;
+    nodeRegion = stage > rowRegion ? stage : rowRegion;
+    ellLen = lp.maxTileEll;
+    entLen = (lp.maxTileEnts + 3) & ~3;
+    runsLen = lp.maxTileRuns;
+  }
+  __host__ __device__ size_t bytes() const
+  {
+    return sizeof(double) * ((size_t)nodeRegion + (size_t)P::NRES * resStride) +
+           4u * (size_t)ellLen + 8u * (size_t)entLen +
+           sizeof(Run) * (size_t)runsLen;
+  }
+};
+
 template <class P, int ND>
-__global__ void __launch_bounds__(kTileThreads, 2) ls_tile_kernel(
+__global__ void __launch_bounds__(kTileThreads, P::kMinBlocks) ls_tile_kernel(
   const MeshPlanDev mp,
   const LsPlanDev lp,
   const NodeComps nc,
@@ -388,24 +473,49 @@ __global__ void __launch_bounds__(kTileThreads, 2) ls_tile_kernel(
   const typename P::Opts o)
 {
   extern __shared__ __align__(16) double smem[];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar[2];
 
   const TileHdr h = mp.tiles[blockIdx.x];
   const LsTileHdr lh = lp.tiles[blockIdx.x];
+  const LsSmem<P> L(mp, lp);
   const int stride = even_up_i(h.nOwnPad + h.nHalo);
-  const int resStride = even_up_i(mp.maxTileEdges);
-  const int entStride = even_up_i(lp.maxTileEnts);
 
-  /* [ node stage | edge results ]; the row staging of phases 2-3 reuses the
-   * node stage, which is dead once phase 1 is over */
-  const int nodeRegion = max(
-    P::NC * mp.maxStaged, even_up_i(lp.maxTileNnz) + P::NR * entStride);
   double* s_node = smem;
-  double* s_res = s_node + nodeRegion;
-  double* s_vals = s_node;
-  double* s_rhs = s_vals + even_up_i(lp.maxTileNnz);
+  double* s_res = s_node + L.nodeRegion;
+  double* s_vals = s_node; /* row staging: the node stage is dead by then */
+  double* s_rhs = s_vals + L.valsLen;
+  uint32_t* s_ell = reinterpret_cast<uint32_t*>(s_res + P::NRES * L.resStride);
+  EntInfo* s_ent = reinterpret_cast<EntInfo*>(s_ell + L.ellLen);
+  int32_t* s_row = reinterpret_cast<int32_t*>(s_ent + L.entLen);
+  Run* s_runs = reinterpret_cast<Run*>(s_row + L.entLen);
 
-  stage_nodes<P::NC>(s_node, stride, nc, h, mp.haloNodes, &bar);
+  /* ---- stage: every contiguous per-tile stream is a TMA bulk copy ---- */
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+  }
+  __syncthreads();
+  stage_nodes_issue<P::NC>(s_node, stride, nc, h, &bar[0]);
+  if (threadIdx.x == 0) {
+    /* the reduction plan of phases 2-3: half-edge records, row layout, rhs
+     * rows, copy-out runs; needed only after phase 1, so its latency hides
+     * behind the physics */
+    const uint32_t bEll = (uint32_t)lh.ellLen * 4u;
+    const uint32_t bEnt = round16((uint32_t)lh.nEnts * 4u);
+    const uint32_t bRun = (uint32_t)lh.nRuns * (uint32_t)sizeof(Run);
+    mbar_expect_tx(&bar[1], bEll + 2u * bEnt + bRun);
+    if (bEll)
+      tma_load_1d(s_ell, lp.heEll + lh.ellPtr, bEll, &bar[1]);
+    if (bEnt) {
+      tma_load_1d(s_ent, lp.entInfo + lh.entPtr, bEnt, &bar[1]);
+      tma_load_1d(s_row, lp.entRhsRow + lh.entPtr, bEnt, &bar[1]);
+    }
+    if (bRun)
+      tma_load_1d(s_runs, lp.runs + lh.runPtr, bRun, &bar[1]);
+  }
+  stage_halo_gather<P::NC>(s_node, stride, nc, h, mp.haloNodes);
+  mbar_wait(&bar[0], 0);
+  __syncthreads();
 
   /* ---- phase 1: per-edge physics ---- */
   {
@@ -427,65 +537,47 @@ __global__ void __launch_bounds__(kTileThreads, 2) ls_tile_kernel(
       P::compute(ld, l, r, av, mdot, pecfac, o, res);
 #pragma unroll
       for (int k = 0; k < P::NRES; ++k)
-        s_res[k * resStride + j] = res[k];
+        s_res[k * L.resStride + j] = res[k];
     }
   }
+  mbar_wait(&bar[1], 0);
   __syncthreads();
 
-  /* zero the row staging (diagonal and rhs are accumulated by segment tails) */
-  for (int i = threadIdx.x; i < lh.nnz; i += blockDim.x)
-    s_vals[i] = 0.0;
-  for (int i = threadIdx.x; i < P::NR * entStride; i += blockDim.x)
-    s_rhs[i] = 0.0;
-  __syncthreads();
-
-  /* ---- phase 2: row-sorted segmented reduction ---- */
+  /* ---- phase 2: one thread per row, sequential over the row's half-edges ---- */
   {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int32_t* split = lp.warpSplit + lh.warpPtr;
-    const int ws = __ldg(split + warp), we = __ldg(split + warp + 1);
-    const uint32_t* he = lp.he + lh.hePtr;
-    const EntInfo* ents = lp.entInfo + lh.entPtr;
-    for (int base = ws; base < we; base += 32) {
-      const int idx = base + lane;
-      const bool valid = idx < we;
-      const uint32_t hv = valid ? __ldg(he + idx) : 0u;
-      const uint32_t ent = he_ent(hv);
-      const uint32_t key = valid ? ent : 0xffffffffu;
-      double acc[1 + P::NR];
-      double off = 0.0;
-      EntInfo ei;
-      ei.base = 0;
-      ei.diagK = 0;
-      ei.nnz = 0;
-      if (valid) {
-        const int j = (int)he_edge(hv);
-        double res[P::NRES];
+    const int32_t* sliceOff = lp.sliceOff + lh.slicePtr;
+    for (int row = threadIdx.x; row < lh.nEnts; row += blockDim.x) {
+      const int sl = row >> 5;
+      const int o0 = __ldg(sliceOff + sl), o1 = __ldg(sliceOff + sl + 1);
+      const uint32_t* hp = s_ell + o0 + (row & 31);
+      const int W = (o1 - o0) >> 5;
+      const EntInfo ei = s_ent[row];
+      double* vrow = s_vals + ei.base;
+      double diag = 0.0;
+      double rhs[P::NR];
 #pragma unroll
-        for (int k = 0; k < P::NRES; ++k)
-          res[k] = s_res[k * resStride + j];
-        P::contrib(he_side(hv), res, acc[0], off, &acc[1]);
-        ei = ents[ent];
-      } else {
-#pragma unroll
-        for (int k = 0; k < 1 + P::NR; ++k)
-          acc[k] = 0.0;
-      }
-      seg_scan<1 + P::NR>(acc, key, lane);
-      const bool tail = seg_tail(key, lane);
-      if (valid) {
-        if (hv & kHeDup)
-          atomicAdd(&s_vals[ei.base + he_k(hv)], off);
-        else
-          s_vals[ei.base + he_k(hv)] = off;
-        if (tail) {
-          s_vals[ei.base + ei.diagK] += acc[0];
+      for (int d = 0; d < P::NR; ++d)
+        rhs[d] = 0.0;
+      for (int w = 0; w < W; ++w) {
+        const uint32_t hv = hp[w * 32];
+        if (hv & kHeValid) {
+          double dg, off, rr[P::NR];
+          P::contrib(
+            he_side(hv), s_res, L.resStride, (int)he_edge(hv), dg, off, rr);
+          diag += dg;
 #pragma unroll
           for (int d = 0; d < P::NR; ++d)
-            s_rhs[d * entStride + ent] += acc[1 + d];
+            rhs[d] += rr[d];
+          double* dst = vrow + he_k(hv);
+          if (hv & kHeDup)
+            off += *dst;
+          *dst = off;
         }
       }
-      __syncwarp();
+      vrow[ei.diagK] = diag;
+#pragma unroll
+      for (int d = 0; d < P::NR; ++d)
+        s_rhs[d * L.entStride + row] = rhs[d];
     }
   }
   __syncthreads();
@@ -493,19 +585,17 @@ __global__ void __launch_bounds__(kTileThreads, 2) ls_tile_kernel(
   /* ---- phase 3: copy-out, every value written exactly once ---- */
   {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const Run* runs = lp.runs + lh.runPtr;
     for (int q = warp; q < lh.nRuns; q += kTileThreads / 32) {
-      const Run rn = runs[q];
+      const Run rn = s_runs[q];
       double* dst = lp.values + rn.go;
       for (int k = lane; k < rn.len; k += 32)
         dst[k] = s_vals[rn.so + k];
     }
-    const int32_t* rows = lp.entRhsRow + lh.entPtr;
     for (int i = threadIdx.x; i < lh.nEnts; i += blockDim.x) {
-      const int64_t row = __ldg(rows + i);
+      const int64_t row = s_row[i];
 #pragma unroll
       for (int d = 0; d < P::NR; ++d)
-        lp.rhs[(int64_t)d * lp.rhsStride + row] = s_rhs[d * entStride + i];
+        lp.rhs[(int64_t)d * lp.rhsStride + row] = s_rhs[d * L.entStride + i];
     }
   }
 }
@@ -768,8 +858,9 @@ struct GradOut
 };
 
 /* NodalGradEdgeAlg (src/ngp_algorithms/NodalGradEdgeAlg.C:85-109) with the
- * zero-fill of NodalGradAlgDriver::pre_work fused: every owned node's
- * gradient is written once. */
+ * zero-fill of NodalGradAlgDriver::pre_work fused: one thread per owned node
+ * walks the node's half-edges (sliced-ELL list, TMA-staged), sums in
+ * registers in list order and writes the node's gradient once, coalesced. */
 template <int D1, int ND>
 __global__ void __launch_bounds__(kTileThreads) grad_tile_kernel(
   const MeshPlanDev mp,
@@ -780,66 +871,68 @@ __global__ void __launch_bounds__(kTileThreads) grad_tile_kernel(
 {
   constexpr int NV = D1 * ND;
   extern __shared__ __align__(16) double smem[];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar[2];
   const TileHdr h = mp.tiles[blockIdx.x];
   const int stride = even_up_i(h.nOwnPad + h.nHalo);
-  const int outStride = even_up_i(mp.maxTileNodes);
   double* s_phi = smem;
-  double* s_out = smem + (size_t)D1 * mp.maxStaged;
-  stage_nodes<D1>(s_phi, stride, phi, h, mp.haloNodes, &bar);
-  for (int i = threadIdx.x; i < NV * outStride; i += blockDim.x)
-    s_out[i] = 0.0;
+  uint32_t* s_ell = reinterpret_cast<uint32_t*>(smem + (size_t)D1 * mp.maxStaged);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+  }
+  __syncthreads();
+  stage_nodes_issue<D1>(s_phi, stride, phi, h, &bar[0]);
+  if (threadIdx.x == 0) {
+    const uint32_t bEll = (uint32_t)h.ellLenNode * 4u;
+    mbar_expect_tx(&bar[1], bEll);
+    if (bEll)
+      tma_load_1d(s_ell, mp.heNodeEll + h.ellPtrNode, bEll, &bar[1]);
+  }
+  stage_halo_gather<D1>(s_phi, stride, phi, h, mp.haloNodes);
+  mbar_wait(&bar[0], 0);
+  mbar_wait(&bar[1], 0);
   __syncthreads();
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int32_t* split = mp.warpSplitNode + h.warpPtrNode;
-  const int ws = __ldg(split + warp), we = __ldg(split + warp + 1);
-  const uint32_t* he = mp.heNode + h.hePtrNode;
-  for (int base = ws; base < we; base += 32) {
-    const int idx = base + lane;
-    const bool valid = idx < we;
-    const uint32_t hv = valid ? __ldg(he + idx) : 0u;
-    const uint32_t ent = he_ent(hv);
-    const uint32_t key = valid ? ent : 0xffffffffu;
+  const int32_t* sliceOff = mp.sliceOffNode + h.slicePtrNode;
+  const uint32_t* lr = mp.lr + h.edge0;
+  for (int i = threadIdx.x; i < h.nOwn; i += blockDim.x) {
+    const int sl = i >> 5;
+    const int o0 = __ldg(sliceOff + sl), o1 = __ldg(sliceOff + sl + 1);
+    const uint32_t* hp = s_ell + o0 + (i & 31);
+    const int W = (o1 - o0) >> 5;
     double acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k)
       acc[k] = 0.0;
-    if (valid) {
-      const int j = (int)he_edge(hv);
-      const uint32_t v = __ldg(mp.lr + h.edge0 + j);
-      const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
-      const double invVol = 1.0 / __ldg(dualVol + h.node0 + ent);
-      const double sgn = he_side(hv) ? -1.0 : 1.0;
-      double av[ND];
+    for (int w = 0; w < W; ++w) {
+      const uint32_t hv = hp[w * 32];
+      if (hv & kHeValid) {
+        const int j = (int)he_edge(hv);
+        const uint32_t v = __ldg(lr + j);
+        const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
+        /* L node: += a_j phiIp ; R node: -= a_j phiIp (NodalGradEdgeAlg.C:100-106) */
+        const double sgn = he_side(hv) ? -1.0 : 1.0;
+        double av[ND];
 #pragma unroll
-      for (int d = 0; d < ND; ++d)
-        av[d] = __ldg(ec.area[d] + h.edge0 + j);
+        for (int d = 0; d < ND; ++d)
+          av[d] = sgn * __ldg(ec.area[d] + h.edge0 + j);
 #pragma unroll
-      for (int i = 0; i < D1; ++i) {
-        const double phiIp = 0.5 * (s_phi[i * stride + l] + s_phi[i * stride + r]);
+        for (int c = 0; c < D1; ++c) {
+          const double phiIp =
+            0.5 * (s_phi[c * stride + l] + s_phi[c * stride + r]);
 #pragma unroll
-        for (int d = 0; d < ND; ++d) {
-          const double ajPhiIp = av[d] * phiIp;
-          acc[i * ND + d] = sgn * (ajPhiIp * invVol);
+          for (int d = 0; d < ND; ++d)
+            acc[c * ND + d] += av[d] * phiIp;
         }
       }
     }
-    seg_scan<NV>(acc, key, lane);
-    /* the shuffle inside seg_tail needs every lane: never short-circuit it */
-    const bool tail = seg_tail(key, lane);
-    if (valid && tail) {
-#pragma unroll
-      for (int k = 0; k < NV; ++k)
-        s_out[k * outStride + ent] += acc[k];
-    }
-    __syncwarp();
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < h.nOwn; i += blockDim.x) {
+    /* the reference divides every edge term by the dual volume before summing;
+     * scaling the node's sum once differs by rounding only (a few ulp) and
+     * saves a divide per half-edge */
+    const double invVol = nw_rcp(__ldg(dualVol + h.node0 + i));
 #pragma unroll
     for (int k = 0; k < NV; ++k)
-      out.c[k][h.node0 + i] = s_out[k * outStride + i];
+      out.c[k][h.node0 + i] = acc[k] * invVol;
   }
 }
 
@@ -1148,21 +1241,11 @@ set_smem(K kernel, size_t bytes)
   return cudaSuccess;
 }
 
-inline int
-even_up_h(int v)
-{
-  return (v + 1) & ~1;
-}
-
 template <class P>
 size_t
 ls_tile_smem(const MeshPlanDev& mp, const LsPlanDev& lp)
 {
-  const size_t nodeRegion = std::max<size_t>(
-    (size_t)P::NC * mp.maxStaged,
-    (size_t)even_up_h(lp.maxTileNnz) + (size_t)P::NR * even_up_h(lp.maxTileEnts));
-  return sizeof(double) *
-         (nodeRegion + (size_t)P::NRES * even_up_h(mp.maxTileEdges));
+  return LsSmem<P>(mp, lp).bytes();
 }
 
 template <class P, int ND>
@@ -1280,8 +1363,7 @@ launch_grad_tile_t(
   for (int k = 0; k < D1 * ND; ++k)
     go.c[k] = gradOut[k];
   const size_t bytes =
-    sizeof(double) * ((size_t)D1 * mp.maxStaged +
-                      (size_t)D1 * ND * even_up_h(mp.maxTileNodes));
+    sizeof(double) * (size_t)D1 * mp.maxStaged + 4u * (size_t)mp.maxTileEllNode;
   cudaError_t e = set_smem(grad_tile_kernel<D1, ND>, bytes);
   if (e != cudaSuccess)
     return e;

@@ -18,14 +18,15 @@ struct MeshPlanDev
   const TileHdr* tiles = nullptr;
   const int32_t* haloNodes = nullptr;
   const uint32_t* lr = nullptr;
-  const uint32_t* heNode = nullptr;
-  const int32_t* warpSplitNode = nullptr;
+  const uint32_t* heNodeEll = nullptr;   /* sliced-ELL node-keyed half-edges */
+  const int32_t* sliceOffNode = nullptr;
   const uint8_t* primary = nullptr;
   int nTiles = 0;
   int ndim = 3;
   int maxStaged = 0;   /* max over tiles of even(nOwnPad + nHalo) */
   int maxTileEdges = 0;
   int maxTileNodes = 0;
+  int maxTileEllNode = 0;
 };
 
 struct LsPlanDev
@@ -33,11 +34,13 @@ struct LsPlanDev
   const LsTileHdr* tiles = nullptr;
   const EntInfo* entInfo = nullptr;
   const int32_t* entRhsRow = nullptr;
-  const uint32_t* he = nullptr;
-  const int32_t* warpSplit = nullptr;
+  const uint32_t* heEll = nullptr;   /* sliced-ELL row-keyed half-edges */
+  const int32_t* sliceOff = nullptr;
   const Run* runs = nullptr;
   int maxTileNnz = 0;
   int maxTileEnts = 0;
+  int maxTileEll = 0;
+  int maxTileRuns = 0;
   double* values = nullptr;
   double* rhs = nullptr;
   int64_t rhsStride = 0; /* rows_owned + rows_shared */

@@ -24,8 +24,17 @@ constexpr int kTileThreads = 256;
  *   [12]    side: 0 = this entity is the edge's L node, 1 = R node
  *   [13,20) k: position of the off-diagonal entry inside the entity's row
  *   [20,30) entity-local index (row or node within the tile)
- *   [30]    dup: another half-edge of this tile hits the same (row, k) slot
- *   [31]    valid */
+ *   [30]    dup: an earlier half-edge of this row hits the same (row, k) slot
+ *           (periodic aliases); the first one of a group is not marked, so
+ *           "dup ? accumulate : store" writes every staged slot without a
+ *           zero fill
+ *   [31]    valid
+ * The lists are kept in two forms: the flat row-sorted list (host side: plan
+ * checks, CPU walk-through) and a sliced-ELL transposition for the device --
+ * slices of 32 entities, slice s stored as W_s x 32 records so that lane i of
+ * a warp reads the w-th half-edge of entity 32 s + i with one coalesced
+ * load; sliceOff[s] is the record offset of slice s inside the tile's block
+ * (sliceOff[s+1] - sliceOff[s] = 32 W_s). */
 constexpr uint32_t kHeValid = 0x80000000u;
 constexpr uint32_t kHeDup = 0x40000000u;
 inline uint32_t
@@ -55,9 +64,12 @@ struct TileHdr
   int32_t edge0;      /* first tile-edge slot (even) */
   int32_t nEdges;     /* tile-edges (internal + cut) */
   int32_t nHalfNode;  /* node-keyed half-edges (gradient) */
-  int32_t hePtrNode;  /* offset into heNode[] */
+  int32_t hePtrNode;  /* offset into heNode[] (flat list, host side) */
   int32_t warpPtrNode;/* offset into warp split table (kMaxWarps+1 entries) */
-  int32_t pad[6];
+  int32_t ellPtrNode; /* offset into heNodeEll[] (multiple of 32) */
+  int32_t ellLenNode; /* records incl. padding (multiple of 32) */
+  int32_t slicePtrNode; /* offset into sliceOffNode[]: nSlices+1 entries */
+  int32_t pad[3];
 };
 
 /* Tile header: linear-system part. 64 bytes. */
@@ -71,7 +83,10 @@ struct LsTileHdr
   int32_t warpPtr;    /* offset into warp split table */
   int32_t runPtr;     /* offset into runs[] */
   int32_t nRuns;
-  int32_t pad[8];
+  int32_t ellPtr;     /* offset into heEll[] (multiple of 32) */
+  int32_t ellLen;     /* records incl. padding (multiple of 32) */
+  int32_t slicePtr;   /* offset into sliceOff[]: nSlices+1 entries */
+  int32_t pad[5];
 };
 
 /* per tile row: where its values sit in the staging buffer */

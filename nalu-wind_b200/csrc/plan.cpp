@@ -106,6 +106,37 @@ split_half_edges(const uint32_t* he, int n, int nWarps, int32_t* split)
   split[nWarps] = n;
 }
 
+int64_t
+append_sliced_ell(
+  const uint32_t* he,
+  int n,
+  int nEnts,
+  std::vector<uint32_t>& ell,
+  std::vector<int32_t>& sliceOff)
+{
+  const int nSlices = (nEnts + 31) / 32;
+  std::vector<int32_t> first(nEnts + 1, 0);
+  for (int q = 0; q < n; ++q)
+    first[he_ent(he[q]) + 1]++;
+  for (int i = 0; i < nEnts; ++i)
+    first[i + 1] += first[i];
+  const size_t base = ell.size();
+  int64_t off = 0;
+  for (int s = 0; s < nSlices; ++s) {
+    sliceOff.push_back((int32_t)off);
+    int w = 0;
+    for (int i = 32 * s; i < std::min(nEnts, 32 * s + 32); ++i)
+      w = std::max(w, first[i + 1] - first[i]);
+    ell.resize(base + off + size_t(w) * 32, 0u);
+    for (int i = 32 * s; i < std::min(nEnts, 32 * s + 32); ++i)
+      for (int k = 0; k < first[i + 1] - first[i]; ++k)
+        ell[base + off + size_t(k) * 32 + (i - 32 * s)] = he[first[i] + k];
+    off += int64_t(w) * 32;
+  }
+  sliceOff.push_back((int32_t)off);
+  return off;
+}
+
 void
 build_mesh_plan(const MeshInput& in, MeshPlan& mp)
 {
@@ -237,14 +268,15 @@ build_mesh_plan(const MeshInput& in, MeshPlan& mp)
     if (cnt[t] > kMaxTileEdges)
       fail("nw_mesh_create: tile exceeds the per-tile edge limit; lower "
            "tile_nodes");
-    edge0[t + 1] = even_up(edge0[t] + cnt[t]);
+    /* tile starts on a multiple of 4: 16-byte aligned runs of 4-byte records */
+    edge0[t + 1] = (edge0[t] + cnt[t] + 3) & ~int64_t(3);
     mp.tiles[t].edge0 = (int32_t)edge0[t];
     mp.tiles[t].nEdges = (int32_t)cnt[t];
     mp.maxTileEdges = std::max(mp.maxTileEdges, cnt[t]);
   }
   if (edge0[nTiles] + 2 >= (int64_t(1) << 31))
     fail("nw_mesh_create: too many tile-edges for 32-bit indices");
-  mp.nTileEdgeSlots = edge0[nTiles] + 2;
+  mp.nTileEdgeSlots = edge0[nTiles] + 4;
   mp.tileEdgeSrc.assign(mp.nTileEdgeSlots, -1);
   mp.lr.assign(mp.nTileEdgeSlots, 0u);
   mp.tileEdgePrimary.assign(mp.nTileEdgeSlots, 0);
@@ -370,6 +402,19 @@ build_mesh_plan(const MeshInput& in, MeshPlan& mp)
       mp.heNode.data() + h.hePtrNode, h.nHalfNode, kMaxWarps,
       mp.warpSplitNode.data() + h.warpPtrNode);
   }
+  for (int64_t t = 0; t < nTiles; ++t) {
+    TileHdr& h = mp.tiles[t];
+    h.ellPtrNode = (int32_t)mp.heNodeEll.size();
+    h.slicePtrNode = (int32_t)mp.sliceOffNode.size();
+    if (mp.heNodeEll.size() >= (size_t(1) << 31) - 65536)
+      fail("nw_mesh_create: plan arrays exceed 32-bit offsets");
+    h.ellLenNode = (int32_t)append_sliced_ell(
+      mp.heNode.data() + h.hePtrNode, h.nHalfNode, h.nOwn, mp.heNodeEll,
+      mp.sliceOffNode);
+    mp.maxTileEllNode = std::max<int64_t>(mp.maxTileEllNode, h.ellLenNode);
+  }
+  mp.heNodeEll.resize(mp.heNodeEll.size() + 32, 0u);
+  mp.sliceOffNode.push_back(0);
 }
 
 /* ------------------------------------------------------------------ */
@@ -730,10 +775,9 @@ build_ls_plan(const MeshPlan& mp, const Graph& g, LsPlan& lp)
     std::vector<uint32_t>& he = hePer[t];
     he.resize(hes.size());
     for (size_t i = 0; i < hes.size(); ++i) {
+      /* only the later members of a (row, k) group are marked */
       const bool dup =
-        (i > 0 && hes[i - 1].ent == hes[i].ent && hes[i - 1].k == hes[i].k) ||
-        (i + 1 < hes.size() && hes[i + 1].ent == hes[i].ent &&
-         hes[i + 1].k == hes[i].k);
+        i > 0 && hes[i - 1].ent == hes[i].ent && hes[i - 1].k == hes[i].k;
       he[i] = he_pack(hes[i].j, hes[i].side, hes[i].k, hes[i].ent, dup);
     }
     lh.nHalf = (int32_t)he.size();
@@ -752,9 +796,11 @@ build_ls_plan(const MeshPlan& mp, const Graph& g, LsPlan& lp)
     lh.hePtr = (int32_t)hp;
     lh.runPtr = (int32_t)rp;
     lh.warpPtr = (int32_t)(t * (kMaxWarps + 1));
-    ep += lh.nEnts;
+    /* 4-aligned: the per-tile runs of 4-byte records are bulk-copied */
+    ep = (ep + lh.nEnts + 3) & ~int64_t(3);
     hp = (hp + lh.nHalf + 3) & ~int64_t(3);
     rp += lh.nRuns;
+    lp.maxTileRuns = std::max<int64_t>(lp.maxTileRuns, lh.nRuns);
     lp.maxTileNnz = std::max<int64_t>(lp.maxTileNnz, lh.nnz);
     lp.maxTileEnts = std::max<int64_t>(lp.maxTileEnts, lh.nEnts);
     lp.maxTileHalf = std::max<int64_t>(lp.maxTileHalf, lh.nHalf);
@@ -764,8 +810,8 @@ build_ls_plan(const MeshPlan& mp, const Graph& g, LsPlan& lp)
     lp.whyNot = "half-edge list exceeds 32-bit offsets";
     return;
   }
-  lp.entInfo.resize(ep + 1);
-  lp.entRhsRow.resize(ep + 1);
+  lp.entInfo.resize(ep + 4);
+  lp.entRhsRow.assign(ep + 4, -1);
   lp.he.assign(hp + 4, 0u);
   lp.runs.resize(rp + 1);
   for (int64_t t = 0; t < nTiles; ++t) {
@@ -779,9 +825,25 @@ build_ls_plan(const MeshPlan& mp, const Graph& g, LsPlan& lp)
       lp.he.data() + lh.hePtr, lh.nHalf, kMaxWarps,
       lp.warpSplit.data() + lh.warpPtr);
   }
+  for (int64_t t = 0; t < nTiles; ++t) {
+    LsTileHdr& lh = lp.tiles[t];
+    lh.ellPtr = (int32_t)lp.heEll.size();
+    lh.slicePtr = (int32_t)lp.sliceOff.size();
+    if (lp.heEll.size() >= (size_t(1) << 31) - 65536) {
+      lp.usable = false;
+      lp.whyNot = "half-edge list exceeds 32-bit offsets";
+      return;
+    }
+    lh.ellLen = (int32_t)append_sliced_ell(
+      lp.he.data() + lh.hePtr, lh.nHalf, lh.nEnts, lp.heEll, lp.sliceOff);
+    lp.maxTileEll = std::max<int64_t>(lp.maxTileEll, lh.ellLen);
+  }
+  lp.heEll.resize(lp.heEll.size() + 32, 0u);
+  lp.sliceOff.push_back(0);
   std::vector<uint8_t> covered(g.numRowsLocal(), 0);
   for (int64_t i = 0; i < ep; ++i)
-    covered[lp.entRhsRow[i]] = 1;
+    if (lp.entRhsRow[i] >= 0)
+      covered[lp.entRhsRow[i]] = 1;
   for (int64_t r = 0; r < g.numRowsLocal(); ++r)
     if (!covered[r])
       lp.uncoveredRows.push_back((int32_t)r);

@@ -67,9 +67,12 @@ struct MeshPlan
   std::vector<int32_t> primarySlotOfEdge; /* [nEdges] */
   std::vector<int32_t> secondSlotOfEdge;  /* [nEdges] copy in tile(R) or -1 */
 
-  /* node-keyed half-edges */
+  /* node-keyed half-edges: flat sorted list + sliced-ELL form (nw_types.h) */
   std::vector<uint32_t> heNode;
   std::vector<int32_t> warpSplitNode; /* per tile kMaxWarps+1 */
+  std::vector<uint32_t> heNodeEll;
+  std::vector<int32_t> sliceOffNode;
+  int64_t maxTileEllNode = 0;
 
   int64_t maxTileNodes = 0, maxTileStaged = 0, maxTileEdges = 0,
           maxTileHalf = 0;
@@ -128,19 +131,30 @@ struct LsPlan
   std::vector<LsTileHdr> tiles;
   std::vector<EntInfo> entInfo;
   std::vector<int32_t> entRhsRow; /* local row (index into rhs) per tile ent */
-  std::vector<uint32_t> he;
+  std::vector<uint32_t> he;       /* flat, sorted by (row, k, edge) */
   std::vector<int32_t> warpSplit;
+  std::vector<uint32_t> heEll;    /* sliced-ELL form read by the kernels */
+  std::vector<int32_t> sliceOff;
   std::vector<Run> runs;
   /* local rows no tile writes (Dirichlet / periodic-slave / untouched rows):
    * zeroed (periodic: diag 1) by the row-init kernel */
   std::vector<int32_t> uncoveredRows;
-  int64_t maxTileNnz = 0, maxTileEnts = 0, maxTileHalf = 0;
+  int64_t maxTileNnz = 0, maxTileEnts = 0, maxTileHalf = 0, maxTileEll = 0,
+          maxTileRuns = 0;
   bool usable = true;       /* false: tile path impossible, use atomics */
   std::string whyNot;
 };
 
 /* 1-dof graphs only (scalar / continuity / UVW momentum) */
 void build_ls_plan(const MeshPlan& mp, const Graph& g, LsPlan& lp);
+
+/* sliced-ELL transposition of one tile's sorted half-edge list (nEnts
+ * entities): appends the records to ell (padding records are 0) and the
+ * nSlices+1 slice offsets (relative to the tile's block) to sliceOff; returns
+ * the number of records appended (a multiple of 32) */
+int64_t append_sliced_ell(
+  const uint32_t* he, int n, int nEnts, std::vector<uint32_t>& ell,
+  std::vector<int32_t>& sliceOff);
 
 /* balanced split of a sorted half-edge list among warps at entity boundaries */
 void split_half_edges(

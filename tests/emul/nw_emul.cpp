@@ -22,6 +22,37 @@ using namespace nw;
 
 namespace {
 
+/* visit the half-edges of one tile in the device's order: entity by entity,
+ * each entity's records from its sliced-ELL column (w ascending) */
+template <class F>
+bool
+walk_ell(
+  const uint32_t* ell, const int32_t* sliceOff, int nEnts, int ellLen, F&& f)
+{
+  const int nSlices = (nEnts + 31) / 32;
+  if (sliceOff[0] != 0 || sliceOff[nSlices] != ellLen)
+    return false;
+  for (int row = 0; row < nEnts; ++row) {
+    const int sl = row >> 5;
+    const int o0 = sliceOff[sl], o1 = sliceOff[sl + 1];
+    if (o1 < o0 || ((o1 - o0) & 31))
+      return false;
+    const int W = (o1 - o0) >> 5;
+    bool ended = false;
+    for (int w = 0; w < W; ++w) {
+      const uint32_t hv = ell[o0 + w * 32 + (row & 31)];
+      if (!(hv & kHeValid)) {
+        ended = true;
+        continue;
+      }
+      if (ended || (int)he_ent(hv) != row)
+        return false;
+      f(row, hv);
+    }
+  }
+  return true;
+}
+
 struct Emu
 {
   MeshPlan mp;
@@ -210,6 +241,20 @@ emu_check_plan(void* h)
           he_ent(he[sp[w]]) == he_ent(he[sp[w] - 1]))
         return bad("warp split inside an entity");
     }
+    /* the sliced-ELL form must replay the flat list exactly */
+    if ((hd.ellPtrNode & 31) || (hd.ellLenNode & 31) || (hd.edge0 & 3))
+      return bad("node ELL block / tile-edge run not aligned");
+    int q = 0;
+    bool same = true;
+    if (!walk_ell(
+          mp.heNodeEll.data() + hd.ellPtrNode,
+          mp.sliceOffNode.data() + hd.slicePtrNode, hd.nOwn, hd.ellLenNode,
+          [&](int, uint32_t hv) {
+            same = same && q < hd.nHalfNode && he[q] == hv;
+            ++q;
+          }) ||
+        !same || q != hd.nHalfNode)
+      return bad("node ELL list differs from the flat list");
   }
   for (int64_t n = 0; n < mp.nNodes; ++n)
     if (seen[n] != 1)
@@ -258,6 +303,19 @@ emu_check_plan(void* h)
         if (sp[w] > 0 && sp[w] < lh.nHalf &&
             he_ent(he[sp[w]]) == he_ent(he[sp[w] - 1]))
           return bad("ls warp split inside a row");
+      if ((lh.ellPtr & 31) || (lh.ellLen & 31) || (lh.entPtr & 3))
+        return bad("row ELL block / ent run not aligned");
+      int q = 0;
+      bool same = true;
+      if (!walk_ell(
+            lp.heEll.data() + lh.ellPtr, lp.sliceOff.data() + lh.slicePtr,
+            lh.nEnts, lh.ellLen,
+            [&](int, uint32_t hv) {
+              same = same && q < lh.nHalf && he[q] == hv;
+              ++q;
+            }) ||
+          !same || q != lh.nHalf)
+        return bad("row ELL list differs from the flat list");
     }
     for (int32_t r : lp.uncoveredRows)
       cov[r]++;
@@ -413,43 +471,51 @@ emu_assemble(
       for (int k = 0; k < NRES; ++k)
         res[size_t(k) * hd.nEdges + j] = out[k];
     }
-    /* phase 2: half-edges in plan order, warp by warp, chunk by chunk (the
-     * sum order differs from the GPU's shuffle tree only by rounding) */
-    std::vector<double> sVals(lh.nnz, 0.0), sRhs(size_t(NR) * lh.nEnts, 0.0);
-    const uint32_t* he = lp.he.data() + lh.hePtr;
-    for (int q = 0; q < lh.nHalf; ++q) {
-      const uint32_t hv = he[q];
-      if (!(hv & kHeValid)) {
-        e->err = "invalid half-edge inside the list";
-        return 1;
-      }
-      const int j = he_edge(hv), side = he_side(hv), ent = he_ent(hv);
-      const EntInfo& ei = lp.entInfo[lh.entPtr + ent];
-      double r_[8];
-      for (int k = 0; k < NRES; ++k)
-        r_[k] = res[size_t(k) * hd.nEdges + j];
-      double diag, off, rr[3];
-      if (kind == 0) {
-        diag = -r_[0];
-        off = r_[0];
-        rr[0] = side ? r_[1] : -r_[1];
-      } else {
-        diag = side ? r_[3] : r_[0];
-        off = side ? r_[2] : r_[1];
+    /* phase 2: one row at a time through the sliced-ELL list, exactly the
+     * device's order; the staging is poisoned so an unwritten slot shows */
+    std::vector<double> sVals(lh.nnz, NAN), sRhs(size_t(NR) * lh.nEnts, NAN);
+    std::vector<double> diagAcc(lh.nEnts, 0.0), rhsAcc(size_t(NR) * lh.nEnts, 0.0);
+    bool slotBad = false;
+    const bool okWalk = walk_ell(
+      lp.heEll.data() + lh.ellPtr, lp.sliceOff.data() + lh.slicePtr, lh.nEnts,
+      lh.ellLen, [&](int ent, uint32_t hv) {
+        const int j = he_edge(hv), side = he_side(hv);
+        const EntInfo& ei = lp.entInfo[lh.entPtr + ent];
+        double r_[8];
+        for (int k = 0; k < NRES; ++k)
+          r_[k] = res[size_t(k) * hd.nEdges + j];
+        double diag, off, rr[3];
+        if (kind == 0) {
+          diag = -r_[0];
+          off = r_[0];
+          rr[0] = side ? r_[1] : -r_[1];
+        } else {
+          diag = side ? r_[3] : r_[0];
+          off = side ? r_[2] : r_[1];
+          for (int d = 0; d < NR; ++d)
+            rr[d] = side ? r_[4 + d] : -r_[4 + d];
+        }
+        if (he_k(hv) >= ei.nnz || he_k(hv) == ei.diagK) {
+          slotBad = true;
+          return;
+        }
+        double& dst = sVals[ei.base + he_k(hv)];
+        if (hv & kHeDup)
+          off += dst;
+        dst = off;
+        diagAcc[ent] += diag;
         for (int d = 0; d < NR; ++d)
-          rr[d] = side ? r_[4 + d] : -r_[4 + d];
-      }
-      if (he_k(hv) >= ei.nnz || he_k(hv) == ei.diagK) {
-        e->err = "half-edge slot out of row";
-        return 1;
-      }
-      if (hv & kHeDup)
-        sVals[ei.base + he_k(hv)] += off;
-      else
-        sVals[ei.base + he_k(hv)] = off;
-      sVals[ei.base + ei.diagK] += diag;
+          rhsAcc[size_t(d) * lh.nEnts + ent] += rr[d];
+      });
+    if (!okWalk || slotBad) {
+      e->err = "row ELL list malformed or half-edge slot out of row";
+      return 1;
+    }
+    for (int i = 0; i < lh.nEnts; ++i) {
+      const EntInfo& ei = lp.entInfo[lh.entPtr + i];
+      sVals[ei.base + ei.diagK] = diagAcc[i];
       for (int d = 0; d < NR; ++d)
-        sRhs[size_t(d) * lh.nEnts + ent] += rr[d];
+        sRhs[size_t(d) * lh.nEnts + i] = rhsAcc[size_t(d) * lh.nEnts + i];
     }
     /* phase 3 */
     for (int q = 0; q < lh.nRuns; ++q) {
@@ -499,21 +565,28 @@ emu_nodal_grad(
       comps.push_back(sPhi.data() + size_t(c) * mp.nSlots);
     Staged st = stage(mp, hd, comps);
     std::vector<double> out(size_t(NV) * hd.nOwn, 0.0);
-    const uint32_t* he = mp.heNode.data() + hd.hePtrNode;
-    for (int q = 0; q < hd.nHalfNode; ++q) {
-      const uint32_t hv = he[q];
-      const int j = he_edge(hv), ent = he_ent(hv);
-      const uint32_t v = mp.lr[hd.edge0 + j];
-      const int l = v & 0xffff, r = v >> 16;
-      const double invVol = 1.0 / sVol[hd.node0 + ent];
-      const double sgn = he_side(hv) ? -1.0 : 1.0;
-      for (int i = 0; i < dim1; ++i) {
-        const double phiIp = 0.5 * (st(i, l) + st(i, r));
-        for (int d = 0; d < ND; ++d) {
-          const double ajPhiIp = sArea[size_t(d) * S + hd.edge0 + j] * phiIp;
-          out[size_t(i * ND + d) * hd.nOwn + ent] += sgn * (ajPhiIp * invVol);
-        }
-      }
+    if (!walk_ell(
+          mp.heNodeEll.data() + hd.ellPtrNode,
+          mp.sliceOffNode.data() + hd.slicePtrNode, hd.nOwn, hd.ellLenNode,
+          [&](int ent, uint32_t hv) {
+            const int j = he_edge(hv);
+            const uint32_t v = mp.lr[hd.edge0 + j];
+            const int l = v & 0xffff, r = v >> 16;
+            const double sgn = he_side(hv) ? -1.0 : 1.0;
+            for (int i = 0; i < dim1; ++i) {
+              const double phiIp = 0.5 * (st(i, l) + st(i, r));
+              for (int d = 0; d < ND; ++d)
+                out[size_t(i * ND + d) * hd.nOwn + ent] +=
+                  (sgn * sArea[size_t(d) * S + hd.edge0 + j]) * phiIp;
+            }
+          })) {
+      e->err = "node ELL list malformed";
+      return 1;
+    }
+    for (int i = 0; i < hd.nOwn; ++i) {
+      const double invVol = 1.0 / sVol[hd.node0 + i];
+      for (int k = 0; k < NV; ++k)
+        out[size_t(k) * hd.nOwn + i] *= invVol;
     }
     for (int i = 0; i < hd.nOwn; ++i) {
       const int32_t n = mp.nodeOfSlot[hd.node0 + i];
