@@ -108,11 +108,12 @@ stage_nodes_issue(
   int stride,
   const NodeComps& nc,
   const TileHdr& h,
-  uint64_t* bar)
+  uint64_t* bar,
+  uint32_t extraTx = 0)
 {
   if (threadIdx.x == 0) {
     const uint32_t bytes = (uint32_t)h.nOwnPad * 8u;
-    mbar_expect_tx(bar, bytes * NC);
+    mbar_expect_tx(bar, bytes * NC + extraTx);
     if (bytes) {
 #pragma unroll
       for (int c = 0; c < NC; ++c)
@@ -162,6 +163,37 @@ __device__ __forceinline__ uint32_t
 round16(uint32_t bytes)
 {
   return (bytes + 15u) & ~15u;
+}
+
+/* bytes the edge-stream bulk copies of one tile deliver: the packed (L,R)
+ * records plus `ncomp` double components (tile-edge runs start on a multiple
+ * of 4 records and the arrays are padded, so the rounded sizes stay in bounds) */
+__device__ __forceinline__ uint32_t
+edge_stream_bytes(const TileHdr& h, int ncomp)
+{
+  return round16((uint32_t)h.nEdges * 4u) +
+         (uint32_t)ncomp * round16((uint32_t)h.nEdges * 8u);
+}
+
+/* thread 0: TMA bulk copies of the tile's edge streams (expect_tx is the
+ * caller's); component c lands at s_edge[c * estride + j] */
+__device__ __forceinline__ void
+stage_edges_issue(
+  uint32_t* s_lr,
+  double* s_edge,
+  int estride,
+  const MeshPlanDev& mp,
+  const TileHdr& h,
+  const double* const* comps,
+  int ncomp,
+  uint64_t* bar)
+{
+  if (h.nEdges == 0)
+    return;
+  tma_load_1d(s_lr, mp.lr + h.edge0, round16((uint32_t)h.nEdges * 4u), bar);
+  const uint32_t b = round16((uint32_t)h.nEdges * 8u);
+  for (int c = 0; c < ncomp; ++c)
+    tma_load_1d(s_edge + c * estride, comps[c] + h.edge0, b, bar);
 }
 
 template <int NV>
@@ -444,9 +476,16 @@ struct LsSmem
   int ellLen;     /* uint32 records */
   int entLen;     /* EntInfo / rhs-row records */
   int runsLen;    /* Run records */
+  int lrLen;      /* packed (L,R) records */
+  /* the edge inputs (area, mdot, pecfac) are bulk-copied into the result
+   * region: a thread has read edge j's inputs before it writes edge j's
+   * results, so the two share storage */
+  static constexpr int NIN_MAX = 5;
+  static constexpr int NEDGE = P::NRES > NIN_MAX ? P::NRES : NIN_MAX;
   __host__ __device__ LsSmem(const MeshPlanDev& mp, const LsPlanDev& lp)
   {
     resStride = (mp.maxTileEdges + 1) & ~1;
+    lrLen = (mp.maxTileEdges + 3) & ~3;
     valsLen = (lp.maxTileNnz + 1) & ~1;
     entStride = (lp.maxTileEnts + 1) & ~1;
     const int rowRegion = valsLen + P::NR * entStride;
@@ -458,9 +497,9 @@ struct LsSmem
   }
   __host__ __device__ size_t bytes() const
   {
-    return sizeof(double) * ((size_t)nodeRegion + (size_t)P::NRES * resStride) +
+    return sizeof(double) * ((size_t)nodeRegion + (size_t)NEDGE * resStride) +
            4u * (size_t)ellLen + 8u * (size_t)entLen +
-           sizeof(Run) * (size_t)runsLen;
+           sizeof(Run) * (size_t)runsLen + 4u * (size_t)lrLen;
   }
 };
 
@@ -484,10 +523,26 @@ __global__ void __launch_bounds__(kTileThreads, P::kMinBlocks) ls_tile_kernel(
   double* s_res = s_node + L.nodeRegion;
   double* s_vals = s_node; /* row staging: the node stage is dead by then */
   double* s_rhs = s_vals + L.valsLen;
-  uint32_t* s_ell = reinterpret_cast<uint32_t*>(s_res + P::NRES * L.resStride);
+  uint32_t* s_ell =
+    reinterpret_cast<uint32_t*>(s_res + LsSmem<P>::NEDGE * L.resStride);
   EntInfo* s_ent = reinterpret_cast<EntInfo*>(s_ell + L.ellLen);
   int32_t* s_row = reinterpret_cast<int32_t*>(s_ent + L.entLen);
   Run* s_runs = reinterpret_cast<Run*>(s_row + L.entLen);
+  uint32_t* s_lr = reinterpret_cast<uint32_t*>(s_runs + L.runsLen);
+
+  /* edge input streams of this policy: area, [mdot], [pecfac] */
+  const double* ecomp[LsSmem<P>::NIN_MAX];
+  int nin = 0;
+#pragma unroll
+  for (int d = 0; d < ND; ++d)
+    ecomp[nin++] = ec.area[d];
+  const int kMdot = nin;
+  if (P::kNeedsMdot)
+    ecomp[nin++] = ec.mdot;
+  const int kPec = nin;
+  const bool hasPec = P::kNeedsPec && ec.pecfac != nullptr;
+  if (hasPec)
+    ecomp[nin++] = ec.pecfac;
 
   /* ---- stage: every contiguous per-tile stream is a TMA bulk copy ---- */
   if (threadIdx.x == 0) {
@@ -495,8 +550,10 @@ __global__ void __launch_bounds__(kTileThreads, P::kMinBlocks) ls_tile_kernel(
     mbar_init(&bar[1], 1);
   }
   __syncthreads();
-  stage_nodes_issue<P::NC>(s_node, stride, nc, h, &bar[0]);
+  stage_nodes_issue<P::NC>(
+    s_node, stride, nc, h, &bar[0], edge_stream_bytes(h, nin));
   if (threadIdx.x == 0) {
+    stage_edges_issue(s_lr, s_res, L.resStride, mp, h, ecomp, nin, &bar[0]);
     /* the reduction plan of phases 2-3: half-edge records, row layout, rhs
      * rows, copy-out runs; needed only after phase 1, so its latency hides
      * behind the physics */
@@ -517,24 +574,24 @@ __global__ void __launch_bounds__(kTileThreads, P::kMinBlocks) ls_tile_kernel(
   mbar_wait(&bar[0], 0);
   __syncthreads();
 
-  /* ---- phase 1: per-edge physics ---- */
+  /* ---- phase 1: per-edge physics, entirely out of shared memory ---- */
   {
     const SmemLd ld{s_node, stride};
-    const uint32_t* lr = mp.lr + h.edge0;
     for (int j = threadIdx.x; j < h.nEdges; j += blockDim.x) {
-      const uint32_t v = __ldg(lr + j);
+      const uint32_t v = s_lr[j];
       const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
       double av[ND];
 #pragma unroll
       for (int d = 0; d < ND; ++d)
-        av[d] = __ldg(ec.area[d] + h.edge0 + j);
+        av[d] = s_res[d * L.resStride + j];
       double mdot = 0.0, pecfac = 0.0;
       if (P::kNeedsMdot)
-        mdot = __ldg(ec.mdot + h.edge0 + j);
-      if (P::kNeedsPec && ec.pecfac)
-        pecfac = __ldg(ec.pecfac + h.edge0 + j);
+        mdot = s_res[kMdot * L.resStride + j];
+      if (hasPec)
+        pecfac = s_res[kPec * L.resStride + j];
       double res[P::NRES];
       P::compute(ld, l, r, av, mdot, pecfac, o, res);
+      /* results overwrite this edge's own inputs (all read above) */
 #pragma unroll
       for (int k = 0; k < P::NRES; ++k)
         s_res[k * L.resStride + j] = res[k];
@@ -795,16 +852,26 @@ __global__ void __launch_bounds__(kTileThreads) mdot_tile_kernel(
   __shared__ __align__(8) uint64_t bar;
   const TileHdr h = mp.tiles[blockIdx.x];
   const int stride = even_up_i(h.nOwnPad + h.nHalo);
-  stage_nodes<P::NC>(smem, stride, nc, h, mp.haloNodes, &bar);
+  const int estride = even_up_i(mp.maxTileEdges);
+  double* s_area = smem + (size_t)P::NC * mp.maxStaged;
+  uint32_t* s_lr = reinterpret_cast<uint32_t*>(s_area + ND * estride);
+  if (threadIdx.x == 0)
+    mbar_init(&bar, 1);
+  __syncthreads();
+  stage_nodes_issue<P::NC>(smem, stride, nc, h, &bar, edge_stream_bytes(h, ND));
+  if (threadIdx.x == 0)
+    stage_edges_issue(s_lr, s_area, estride, mp, h, ec.area, ND, &bar);
+  stage_halo_gather<P::NC>(smem, stride, nc, h, mp.haloNodes);
+  mbar_wait(&bar, 0);
+  __syncthreads();
   const SmemLd ld{smem, stride};
-  const uint32_t* lr = mp.lr + h.edge0;
   for (int j = threadIdx.x; j < h.nEdges; j += blockDim.x) {
-    const uint32_t v = __ldg(lr + j);
+    const uint32_t v = s_lr[j];
     const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
     double av[ND];
 #pragma unroll
     for (int d = 0; d < ND; ++d)
-      av[d] = __ldg(ec.area[d] + h.edge0 + j);
+      av[d] = s_area[d * estride + j];
     ContNode<ND> L, R;
     P::load(ld, l, L);
     P::load(ld, r, R);
@@ -826,11 +893,19 @@ __global__ void __launch_bounds__(kTileThreads) peclet_tile_kernel(
   __shared__ __align__(8) uint64_t bar;
   const TileHdr h = mp.tiles[blockIdx.x];
   const int stride = even_up_i(h.nOwnPad + h.nHalo);
-  stage_nodes<NC>(smem, stride, nc, h, mp.haloNodes, &bar);
+  uint32_t* s_lr = reinterpret_cast<uint32_t*>(smem + (size_t)NC * mp.maxStaged);
+  if (threadIdx.x == 0)
+    mbar_init(&bar, 1);
+  __syncthreads();
+  stage_nodes_issue<NC>(smem, stride, nc, h, &bar, edge_stream_bytes(h, 0));
+  if (threadIdx.x == 0)
+    stage_edges_issue(s_lr, nullptr, 0, mp, h, nullptr, 0, &bar);
+  stage_halo_gather<NC>(smem, stride, nc, h, mp.haloNodes);
+  mbar_wait(&bar, 0);
+  __syncthreads();
   const SmemLd ld{smem, stride};
-  const uint32_t* lr = mp.lr + h.edge0;
   for (int j = threadIdx.x; j < h.nEdges; j += blockDim.x) {
-    const uint32_t v = __ldg(lr + j);
+    const uint32_t v = s_lr[j];
     const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
     PecNode<ND> L, R;
 #pragma unroll
@@ -874,15 +949,19 @@ __global__ void __launch_bounds__(kTileThreads) grad_tile_kernel(
   __shared__ __align__(8) uint64_t bar[2];
   const TileHdr h = mp.tiles[blockIdx.x];
   const int stride = even_up_i(h.nOwnPad + h.nHalo);
+  const int estride = even_up_i(mp.maxTileEdges);
   double* s_phi = smem;
-  uint32_t* s_ell = reinterpret_cast<uint32_t*>(smem + (size_t)D1 * mp.maxStaged);
+  double* s_area = smem + (size_t)D1 * mp.maxStaged;
+  uint32_t* s_ell = reinterpret_cast<uint32_t*>(s_area + ND * estride);
+  uint32_t* s_lr = s_ell + mp.maxTileEllNode;
   if (threadIdx.x == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
   }
   __syncthreads();
-  stage_nodes_issue<D1>(s_phi, stride, phi, h, &bar[0]);
+  stage_nodes_issue<D1>(s_phi, stride, phi, h, &bar[0], edge_stream_bytes(h, ND));
   if (threadIdx.x == 0) {
+    stage_edges_issue(s_lr, s_area, estride, mp, h, ec.area, ND, &bar[0]);
     const uint32_t bEll = (uint32_t)h.ellLenNode * 4u;
     mbar_expect_tx(&bar[1], bEll);
     if (bEll)
@@ -894,7 +973,6 @@ __global__ void __launch_bounds__(kTileThreads) grad_tile_kernel(
   __syncthreads();
 
   const int32_t* sliceOff = mp.sliceOffNode + h.slicePtrNode;
-  const uint32_t* lr = mp.lr + h.edge0;
   for (int i = threadIdx.x; i < h.nOwn; i += blockDim.x) {
     const int sl = i >> 5;
     const int o0 = __ldg(sliceOff + sl), o1 = __ldg(sliceOff + sl + 1);
@@ -908,14 +986,14 @@ __global__ void __launch_bounds__(kTileThreads) grad_tile_kernel(
       const uint32_t hv = hp[w * 32];
       if (hv & kHeValid) {
         const int j = (int)he_edge(hv);
-        const uint32_t v = __ldg(lr + j);
+        const uint32_t v = s_lr[j];
         const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
         /* L node: += a_j phiIp ; R node: -= a_j phiIp (NodalGradEdgeAlg.C:100-106) */
         const double sgn = he_side(hv) ? -1.0 : 1.0;
         double av[ND];
 #pragma unroll
         for (int d = 0; d < ND; ++d)
-          av[d] = sgn * __ldg(ec.area[d] + h.edge0 + j);
+          av[d] = sgn * s_area[d * estride + j];
 #pragma unroll
         for (int c = 0; c < D1; ++c) {
           const double phiIp =
@@ -1241,6 +1319,15 @@ set_smem(K kernel, size_t bytes)
   return cudaSuccess;
 }
 
+/* node stage (nodeComps) + edge components + packed (L,R) records */
+inline size_t
+edge_kernel_smem(const MeshPlanDev& mp, int nodeComps, int edgeComps)
+{
+  const size_t estride = (size_t)((mp.maxTileEdges + 1) & ~1);
+  return sizeof(double) * ((size_t)nodeComps * mp.maxStaged + edgeComps * estride) +
+         4u * (size_t)((mp.maxTileEdges + 3) & ~3);
+}
+
 template <class P>
 size_t
 ls_tile_smem(const MeshPlanDev& mp, const LsPlanDev& lp)
@@ -1308,13 +1395,13 @@ launch_mdot_tile(
 {
   cudaError_t e;
   if (mp.ndim == 3) {
-    const size_t bytes = sizeof(double) * ContinuityP<3>::NC * mp.maxStaged;
+    const size_t bytes = edge_kernel_smem(mp, ContinuityP<3>::NC, 3);
     if ((e = set_smem(mdot_tile_kernel<3>, bytes)) != cudaSuccess)
       return e;
     mdot_tile_kernel<3>
       <<<mp.nTiles, kTileThreads, bytes, s>>>(mp, nc, ec, mdotOut, o);
   } else {
-    const size_t bytes = sizeof(double) * ContinuityP<2>::NC * mp.maxStaged;
+    const size_t bytes = edge_kernel_smem(mp, ContinuityP<2>::NC, 2);
     if ((e = set_smem(mdot_tile_kernel<2>, bytes)) != cudaSuccess)
       return e;
     mdot_tile_kernel<2>
@@ -1333,13 +1420,13 @@ launch_peclet_tile(
 {
   cudaError_t e;
   if (mp.ndim == 3) {
-    const size_t bytes = sizeof(double) * 8 * mp.maxStaged;
+    const size_t bytes = edge_kernel_smem(mp, 8, 0);
     if ((e = set_smem(peclet_tile_kernel<3>, bytes)) != cudaSuccess)
       return e;
     peclet_tile_kernel<3>
       <<<mp.nTiles, kTileThreads, bytes, s>>>(mp, nc, pecfacOut, o);
   } else {
-    const size_t bytes = sizeof(double) * 6 * mp.maxStaged;
+    const size_t bytes = edge_kernel_smem(mp, 6, 0);
     if ((e = set_smem(peclet_tile_kernel<2>, bytes)) != cudaSuccess)
       return e;
     peclet_tile_kernel<2>
@@ -1362,8 +1449,7 @@ launch_grad_tile_t(
   GradOut go;
   for (int k = 0; k < D1 * ND; ++k)
     go.c[k] = gradOut[k];
-  const size_t bytes =
-    sizeof(double) * (size_t)D1 * mp.maxStaged + 4u * (size_t)mp.maxTileEllNode;
+  const size_t bytes = edge_kernel_smem(mp, D1, ND) + 4u * (size_t)mp.maxTileEllNode;
   cudaError_t e = set_smem(grad_tile_kernel<D1, ND>, bytes);
   if (e != cudaSuccess)
     return e;

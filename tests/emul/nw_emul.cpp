@@ -654,4 +654,33 @@ emu_mdot(
   return 0;
 }
 
+/* plan statistics for design work: 32-byte sectors a warp-wide halo gather of
+ * one field component touches, summed over tiles (out[0]), halo entries
+ * (out[1]), tile-edge records (out[2]), ELL records row/node (out[3], out[4]) */
+int
+emu_plan_stats(void* h, int64_t* out)
+{
+  Emu* e = static_cast<Emu*>(h);
+  const MeshPlan& mp = e->mp;
+  int64_t sectors = 0, halo = 0, te = 0;
+  for (int64_t t = 0; t < mp.nTiles; ++t) {
+    const TileHdr& hd = mp.tiles[t];
+    halo += hd.nHalo;
+    te += hd.nEdges;
+    for (int k0 = 0; k0 < hd.nHalo; k0 += 32) {
+      std::vector<int64_t> sec;
+      for (int k = k0; k < std::min(hd.nHalo, k0 + 32); ++k)
+        sec.push_back(mp.haloNodes[hd.haloPtr + k] / 4);
+      std::sort(sec.begin(), sec.end());
+      sectors += std::unique(sec.begin(), sec.end()) - sec.begin();
+    }
+  }
+  out[0] = sectors;
+  out[1] = halo;
+  out[2] = te;
+  out[3] = e->hasLs ? (int64_t)e->lp.heEll.size() : 0;
+  out[4] = (int64_t)mp.heNodeEll.size();
+  return 0;
+}
+
 } // extern "C"
