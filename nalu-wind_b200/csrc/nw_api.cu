@@ -681,18 +681,17 @@ linsys_upload(nw_linsys* ls)
         (rc = upload(ls->dEntRhsRow, ls->lp.entRhsRow, s, nullptr)) ||
         (rc = upload(ls->dHe, ls->lp.heEll, s, nullptr)) ||
         (rc = upload(ls->dWarp, ls->lp.sliceOff, s, nullptr)) ||
-        (rc = upload(ls->dRuns, ls->lp.runs, s, nullptr)))
+        (rc = upload(ls->dRuns, ls->lp.entGo, s, nullptr)))
       return rc;
     ls->dev.tiles = ls->dLsTiles.as<LsTileHdr>();
     ls->dev.entInfo = ls->dEntInfo.as<EntInfo>();
     ls->dev.entRhsRow = ls->dEntRhsRow.as<int32_t>();
     ls->dev.heEll = ls->dHe.as<uint32_t>();
     ls->dev.sliceOff = ls->dWarp.as<int32_t>();
-    ls->dev.runs = ls->dRuns.as<Run>();
+    ls->dev.entGo = ls->dRuns.as<int32_t>();
     ls->dev.maxTileNnz = (int)ls->lp.maxTileNnz;
     ls->dev.maxTileEnts = (int)ls->lp.maxTileEnts;
     ls->dev.maxTileEll = (int)ls->lp.maxTileEll;
-    ls->dev.maxTileRuns = (int)ls->lp.maxTileRuns;
     /* rows the tiles do not write */
     std::vector<uint8_t> isPer(ls->lp.uncoveredRows.size(), 0);
     for (size_t i = 0; i < isPer.size(); ++i) {

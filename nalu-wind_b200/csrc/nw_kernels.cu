@@ -17,7 +17,9 @@
  *           profile: the segmented warp-shuffle scan this replaces was 45 % of
  *           all issued instructions, profiles/r01a_*; it survives only as the
  *           warp aggregation of the atomic comparison variant);
- *   phase3: the staged rows are copied out in contiguous runs -- each matrix
+ *   phase3: each warp copies the staging range of the 32 rows it has just
+ *           reduced to the CSR value array, element-wise (coalesced wherever
+ *           the rows are consecutive) -- each matrix
  *           value and rhs entry is written exactly once, no atomics, no
  *           zero-fill pass (replaces resetCoeffApplierData's deep_copy(0) and
  *           the column walk + atomic_add of sum_into,
@@ -471,11 +473,9 @@ struct LsSmem
 {
   int nodeRegion; /* doubles: node stage, reused as row staging after phase 1 */
   int resStride;  /* doubles per result component */
-  int valsLen;    /* doubles: staged matrix values */
-  int entStride;  /* doubles per rhs column */
+  int valsLen;    /* staged matrix values (doubles) + their int32 deltas */
   int ellLen;     /* uint32 records */
-  int entLen;     /* EntInfo / rhs-row records */
-  int runsLen;    /* Run records */
+  int entLen;     /* EntInfo / rhs-row / value-offset records */
   int lrLen;      /* packed (L,R) records */
   /* the edge inputs (area, mdot, pecfac) are bulk-copied into the result
    * region: a thread has read edge j's inputs before it writes edge j's
@@ -486,20 +486,18 @@ struct LsSmem
   {
     resStride = (mp.maxTileEdges + 1) & ~1;
     lrLen = (mp.maxTileEdges + 3) & ~3;
-    valsLen = (lp.maxTileNnz + 1) & ~1;
-    entStride = (lp.maxTileEnts + 1) & ~1;
-    const int rowRegion = valsLen + P::NR * entStride;
+    valsLen = (lp.maxTileNnz + 3) & ~3;
+    /* row staging: values (8 B) + value-offset deltas (4 B) */
+    const int rowRegion = valsLen + valsLen / 2;
     const int stage = P::NC * mp.maxStaged;
     nodeRegion = stage > rowRegion ? stage : rowRegion;
     ellLen = lp.maxTileEll;
     entLen = (lp.maxTileEnts + 3) & ~3;
-    runsLen = lp.maxTileRuns;
   }
   __host__ __device__ size_t bytes() const
   {
     return sizeof(double) * ((size_t)nodeRegion + (size_t)NEDGE * resStride) +
-           4u * (size_t)ellLen + 8u * (size_t)entLen +
-           sizeof(Run) * (size_t)runsLen + 4u * (size_t)lrLen;
+           4u * (size_t)ellLen + 12u * (size_t)entLen + 4u * (size_t)lrLen;
   }
 };
 
@@ -522,13 +520,13 @@ __global__ void __launch_bounds__(kTileThreads, P::kMinBlocks) ls_tile_kernel(
   double* s_node = smem;
   double* s_res = s_node + L.nodeRegion;
   double* s_vals = s_node; /* row staging: the node stage is dead by then */
-  double* s_rhs = s_vals + L.valsLen;
+  int32_t* s_delta = reinterpret_cast<int32_t*>(s_vals + L.valsLen);
   uint32_t* s_ell =
     reinterpret_cast<uint32_t*>(s_res + LsSmem<P>::NEDGE * L.resStride);
   EntInfo* s_ent = reinterpret_cast<EntInfo*>(s_ell + L.ellLen);
   int32_t* s_row = reinterpret_cast<int32_t*>(s_ent + L.entLen);
-  Run* s_runs = reinterpret_cast<Run*>(s_row + L.entLen);
-  uint32_t* s_lr = reinterpret_cast<uint32_t*>(s_runs + L.runsLen);
+  int32_t* s_go = s_row + L.entLen;
+  uint32_t* s_lr = reinterpret_cast<uint32_t*>(s_go + L.entLen);
 
   /* edge input streams of this policy: area, [mdot], [pecfac] */
   const double* ecomp[LsSmem<P>::NIN_MAX];
@@ -555,20 +553,18 @@ __global__ void __launch_bounds__(kTileThreads, P::kMinBlocks) ls_tile_kernel(
   if (threadIdx.x == 0) {
     stage_edges_issue(s_lr, s_res, L.resStride, mp, h, ecomp, nin, &bar[0]);
     /* the reduction plan of phases 2-3: half-edge records, row layout, rhs
-     * rows, copy-out runs; needed only after phase 1, so its latency hides
+     * rows, value offsets; needed only after phase 1, so its latency hides
      * behind the physics */
     const uint32_t bEll = (uint32_t)lh.ellLen * 4u;
     const uint32_t bEnt = round16((uint32_t)lh.nEnts * 4u);
-    const uint32_t bRun = (uint32_t)lh.nRuns * (uint32_t)sizeof(Run);
-    mbar_expect_tx(&bar[1], bEll + 2u * bEnt + bRun);
+    mbar_expect_tx(&bar[1], bEll + 3u * bEnt);
     if (bEll)
       tma_load_1d(s_ell, lp.heEll + lh.ellPtr, bEll, &bar[1]);
     if (bEnt) {
       tma_load_1d(s_ent, lp.entInfo + lh.entPtr, bEnt, &bar[1]);
       tma_load_1d(s_row, lp.entRhsRow + lh.entPtr, bEnt, &bar[1]);
+      tma_load_1d(s_go, lp.entGo + lh.entPtr, bEnt, &bar[1]);
     }
-    if (bRun)
-      tma_load_1d(s_runs, lp.runs + lh.runPtr, bRun, &bar[1]);
   }
   stage_halo_gather<P::NC>(s_node, stride, nc, h, mp.haloNodes);
   mbar_wait(&bar[0], 0);
@@ -600,59 +596,62 @@ __global__ void __launch_bounds__(kTileThreads, P::kMinBlocks) ls_tile_kernel(
   mbar_wait(&bar[1], 0);
   __syncthreads();
 
-  /* ---- phase 2: one thread per row, sequential over the row's half-edges ---- */
+  /* ---- phases 2+3, warp by warp: one thread per row reduces the row's
+   * half-edges in list order, then the warp copies the staging range of its
+   * 32 rows to the CSR arrays (only a warp-level sync in between) ---- */
   {
     const int32_t* sliceOff = lp.sliceOff + lh.slicePtr;
-    for (int row = threadIdx.x; row < lh.nEnts; row += blockDim.x) {
-      const int sl = row >> 5;
-      const int o0 = __ldg(sliceOff + sl), o1 = __ldg(sliceOff + sl + 1);
-      const uint32_t* hp = s_ell + o0 + (row & 31);
-      const int W = (o1 - o0) >> 5;
-      const EntInfo ei = s_ent[row];
-      double* vrow = s_vals + ei.base;
-      double diag = 0.0;
-      double rhs[P::NR];
+    const int lane = threadIdx.x & 31;
+    for (int row0 = (int)threadIdx.x - lane; row0 < lh.nEnts;
+         row0 += blockDim.x) {
+      const int row = row0 + lane;
+      if (row < lh.nEnts) {
+        const int sl = row0 >> 5;
+        const int o0 = __ldg(sliceOff + sl), o1 = __ldg(sliceOff + sl + 1);
+        const uint32_t* hp = s_ell + o0 + lane;
+        const int W = (o1 - o0) >> 5;
+        const EntInfo ei = s_ent[row];
+        double* vrow = s_vals + ei.base;
+        double diag = 0.0;
+        double rhs[P::NR];
 #pragma unroll
-      for (int d = 0; d < P::NR; ++d)
-        rhs[d] = 0.0;
-      for (int w = 0; w < W; ++w) {
-        const uint32_t hv = hp[w * 32];
-        if (hv & kHeValid) {
-          double dg, off, rr[P::NR];
-          P::contrib(
-            he_side(hv), s_res, L.resStride, (int)he_edge(hv), dg, off, rr);
-          diag += dg;
+        for (int d = 0; d < P::NR; ++d)
+          rhs[d] = 0.0;
+        for (int w = 0; w < W; ++w) {
+          const uint32_t hv = hp[w * 32];
+          if (hv & kHeValid) {
+            double dg, off, rr[P::NR];
+            P::contrib(
+              he_side(hv), s_res, L.resStride, (int)he_edge(hv), dg, off, rr);
+            diag += dg;
 #pragma unroll
-          for (int d = 0; d < P::NR; ++d)
-            rhs[d] += rr[d];
-          double* dst = vrow + he_k(hv);
-          if (hv & kHeDup)
-            off += *dst;
-          *dst = off;
+            for (int d = 0; d < P::NR; ++d)
+              rhs[d] += rr[d];
+            double* dst = vrow + he_k(hv);
+            if (hv & kHeDup)
+              off += *dst;
+            *dst = off;
+          }
         }
+        vrow[ei.diagK] = diag;
+        /* value offset of every staged element of this row */
+        const int32_t delta = s_go[row] - (int32_t)ei.base;
+        for (int k = 0; k < (int)ei.nnz; ++k)
+          s_delta[ei.base + k] = delta;
+        const int64_t grow = s_row[row];
+#pragma unroll
+        for (int d = 0; d < P::NR; ++d)
+          lp.rhs[(int64_t)d * lp.rhsStride + grow] = rhs[d];
       }
-      vrow[ei.diagK] = diag;
-#pragma unroll
-      for (int d = 0; d < P::NR; ++d)
-        s_rhs[d * L.entStride + row] = rhs[d];
-    }
-  }
-  __syncthreads();
-
-  /* ---- phase 3: copy-out, every value written exactly once ---- */
-  {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int q = warp; q < lh.nRuns; q += kTileThreads / 32) {
-      const Run rn = s_runs[q];
-      double* dst = lp.values + rn.go;
-      for (int k = lane; k < rn.len; k += 32)
-        dst[k] = s_vals[rn.so + k];
-    }
-    for (int i = threadIdx.x; i < lh.nEnts; i += blockDim.x) {
-      const int64_t row = s_row[i];
-#pragma unroll
-      for (int d = 0; d < P::NR; ++d)
-        lp.rhs[(int64_t)d * lp.rhsStride + row] = s_rhs[d * L.entStride + i];
+      __syncwarp();
+      /* copy-out of this warp's rows: every value written exactly once */
+      {
+        const int last = min(row0 + 31, lh.nEnts - 1);
+        const EntInfo e0 = s_ent[row0], e1 = s_ent[last];
+        const int end = (int)e1.base + (int)e1.nnz;
+        for (int e = (int)e0.base + lane; e < end; e += 32)
+          lp.values[e + s_delta[e]] = s_vals[e];
+      }
     }
   }
 }

@@ -36,11 +36,10 @@ struct LsPlanDev
   const int32_t* entRhsRow = nullptr;
   const uint32_t* heEll = nullptr;   /* sliced-ELL row-keyed half-edges */
   const int32_t* sliceOff = nullptr;
-  const Run* runs = nullptr;
+  const int32_t* entGo = nullptr; /* value offset of each tile row */
   int maxTileNnz = 0;
   int maxTileEnts = 0;
   int maxTileEll = 0;
-  int maxTileRuns = 0;
   double* values = nullptr;
   double* rhs = nullptr;
   int64_t rhsStride = 0; /* rows_owned + rows_shared */

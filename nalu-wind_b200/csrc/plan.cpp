@@ -812,6 +812,7 @@ build_ls_plan(const MeshPlan& mp, const Graph& g, LsPlan& lp)
   }
   lp.entInfo.resize(ep + 4);
   lp.entRhsRow.assign(ep + 4, -1);
+  lp.entGo.assign(ep + 4, 0);
   lp.he.assign(hp + 4, 0u);
   lp.runs.resize(rp + 1);
   for (int64_t t = 0; t < nTiles; ++t) {
@@ -819,6 +820,8 @@ build_ls_plan(const MeshPlan& mp, const Graph& g, LsPlan& lp)
     std::copy(entPer[t].begin(), entPer[t].end(), lp.entInfo.begin() + lh.entPtr);
     std::copy(rowPer[t].begin(), rowPer[t].end(),
               lp.entRhsRow.begin() + lh.entPtr);
+    for (size_t i = 0; i < rowPer[t].size(); ++i)
+      lp.entGo[lh.entPtr + i] = (int32_t)g.rowPtr(rowPer[t][i]);
     std::copy(hePer[t].begin(), hePer[t].end(), lp.he.begin() + lh.hePtr);
     std::copy(runPer[t].begin(), runPer[t].end(), lp.runs.begin() + lh.runPtr);
     split_half_edges(

@@ -131,6 +131,7 @@ struct LsPlan
   std::vector<LsTileHdr> tiles;
   std::vector<EntInfo> entInfo;
   std::vector<int32_t> entRhsRow; /* local row (index into rhs) per tile ent */
+  std::vector<int32_t> entGo;     /* offset of the row's first value in values[] */
   std::vector<uint32_t> he;       /* flat, sorted by (row, k, edge) */
   std::vector<int32_t> warpSplit;
   std::vector<uint32_t> heEll;    /* sliced-ELL form read by the kernels */

@@ -517,16 +517,20 @@ emu_assemble(
       for (int d = 0; d < NR; ++d)
         sRhs[size_t(d) * lh.nEnts + i] = rhsAcc[size_t(d) * lh.nEnts + i];
     }
-    /* phase 3 */
-    for (int q = 0; q < lh.nRuns; ++q) {
-      const Run& rn = lp.runs[lh.runPtr + q];
-      for (int k = 0; k < rn.len; ++k)
-        values[rn.go + k] = sVals[rn.so + k];
-    }
-    for (int i = 0; i < lh.nEnts; ++i)
+    /* phase 3: element-wise copy-out through the per-row value offsets */
+    for (int i = 0; i < lh.nEnts; ++i) {
+      const EntInfo& ei = lp.entInfo[lh.entPtr + i];
+      const int64_t go = lp.entGo[lh.entPtr + i];
+      if (go != g.rowPtr(lp.entRhsRow[lh.entPtr + i])) {
+        e->err = "entGo does not match the row's value offset";
+        return 1;
+      }
+      for (int k = 0; k < ei.nnz; ++k)
+        values[go + k] = sVals[ei.base + k];
       for (int d = 0; d < NR; ++d)
         rhs[size_t(d) * rows + lp.entRhsRow[lh.entPtr + i]] =
           sRhs[size_t(d) * lh.nEnts + i];
+    }
   }
   /* row init of the rows no tile writes */
   for (int32_t r : lp.uncoveredRows) {
