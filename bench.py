@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--sst", action="store_true",
                     help="add the k and omega scalar assemblies + gradients")
     ap.add_argument("--mode", default="segmented", choices=["segmented", "atomic"])
+    ap.add_argument("--fuse-peclet", action="store_true",
+                    help="fold MomentumEdgePecletAlg into the momentum kernel "
+                         "(SURVEY 8f-1) instead of launching it separately")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--detail", action="store_true",
                     help="also print per-kernel timings (stderr)")
@@ -252,6 +255,7 @@ def workload_config(args, n_gpus):
                         " + k/omega scalar assemblies + gradients" if args.sst else "",
                         n_gpus),
         "scatter": args.mode,
+        "peclet": "fused into momentum" if args.fuse_peclet else "separate kernel",
         "l2": "inputs larger than L2 (sweep working set ~%.1f GB per GPU vs "
               "126 MB L2), no explicit flush" % (
                   ((n + 1) ** 3 * 8 * 60) / 1e9),
@@ -331,12 +335,17 @@ def main():
 
     def sweep(record=False, detail=False):
         rec = record or detail
-        timed("peclet", lambda: mesh.peclet_edge("viscosity", pf), detail)
+        if not args.fuse_peclet:
+            timed("peclet", lambda: mesh.peclet_edge("viscosity", pf), detail)
         m = systems["momentum"]
 
         def mom():
             m.zeroSystem()
-            m.assemble_momentum_edge("viscosity", **MOM_OPTS)
+            if args.fuse_peclet:
+                m.assemble_momentum_edge("viscosity", fuse_peclet=True, pf=pf,
+                                         **MOM_OPTS)
+            else:
+                m.assemble_momentum_edge("viscosity", **MOM_OPTS)
         timed("momentum_uvw", mom, rec)
         m.loadComplete()
         c = systems["continuity"]
@@ -403,7 +412,9 @@ def main():
     peak, peak_src = measured_peak()
     ach = ALG_BYTES["momentum_uvw"] * edges_local / (mom_ms * 1e-3) / 1e9
     sweep_bytes = sum(ALG_BYTES[k] for k in (
-        "peclet", "momentum_uvw", "continuity", "mdot", "grad_scalar", "grad_vector"))
+        "momentum_uvw", "continuity", "mdot", "grad_scalar", "grad_vector"))
+    if not args.fuse_peclet:
+        sweep_bytes += ALG_BYTES["peclet"]
     if args.sst:
         sweep_bytes += 2 * (ALG_BYTES["scalar"] + ALG_BYTES["grad_scalar"])
     traffic = None
@@ -462,7 +473,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = edges_total * args.steps / (float(t.item()) * 1e-3) / 1e6
 
-    launches_per_step = 6 + 2  # 6 edge kernels + 2 row-init (when rows exist)
+    # edge kernels (+ row-init launches only when a system has rows no tile
+    # owns: none on this mesh)
+    launches_per_step = 5 if args.fuse_peclet else 6
     if args.sst:
         launches_per_step += 2 * 3
     line = {

@@ -243,6 +243,7 @@ even_up_i(int v)
 template <int ND>
 struct ContinuityP
 {
+  static constexpr int kND = ND;
   static constexpr int NC = 3 * ND + 3; /* x, u, dpdx, rho, p, udiag */
   static constexpr int kMinBlocks = 3;  /* <= 85 registers: 3 CTAs per SM */
   static constexpr int NRES = 2;
@@ -300,6 +301,7 @@ struct ContinuityP
 template <int ND>
 struct ScalarP
 {
+  static constexpr int kND = ND;
   static constexpr int NC = 3 * ND + 3; /* x, vrtm, dqdx, q, rho, dflux */
   static constexpr int kMinBlocks = 2;
   static constexpr int NRES = 5;
@@ -358,6 +360,7 @@ template <int ND>
 struct MomentumUvwP
 {
   /* x, u, dudx, visc, rho, mask */
+  static constexpr int kND = ND;
   static constexpr int NC = 2 * ND + ND * ND + 3;
   static constexpr int kMinBlocks = 2; /* 128 registers x 256 threads x 2 */
   static constexpr int NRES = 4 + ND;
@@ -480,7 +483,8 @@ struct LsSmem
   /* the edge inputs (area, mdot, pecfac) are bulk-copied into the result
    * region: a thread has read edge j's inputs before it writes edge j's
    * results, so the two share storage */
-  static constexpr int NIN_MAX = 5;
+  static constexpr int NIN_MAX =
+    P::kND + (P::kNeedsMdot ? 1 : 0) + (P::kNeedsPec ? 1 : 0);
   static constexpr int NEDGE = P::NRES > NIN_MAX ? P::NRES : NIN_MAX;
   __host__ __device__ LsSmem(const MeshPlanDev& mp, const LsPlanDev& lp)
   {

@@ -170,7 +170,10 @@ build_mesh_plan(const MeshInput& in, MeshPlan& mp)
     if (mp.edgeNodes[e] < 0 || mp.edgeNodes[e] >= N)
       fail("nw_mesh_create: edge node index out of range");
 
-  int T = in.tileNodes > 0 ? in.tileNodes : 256;
+  /* default 192: momentum then fits two CTAs per SM (<= 113 KB of shared
+   * memory each) and the ~700 tile-edges fill three rounds of 256 threads;
+   * measured best of 128..256 on a 128^3 hex box (profiles/r01b_*) */
+  int T = in.tileNodes > 0 ? in.tileNodes : 192;
   if (T > kMaxTileEnts)
     T = kMaxTileEnts;
   if (T < 8)
