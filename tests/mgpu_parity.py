@@ -1,0 +1,176 @@
+"""Multi-GPU parity check, run under torchrun (one rank per GPU):
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
+      --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_parity.py
+
+Every rank assembles its partition on its GPU through the C ABI (continuity,
+momentum-UVW, nodal gradients), the library exchanges the shared rows / shared
+nodes over NCCL (nw_linsys_load_complete, nw_nodal_grad_edge), and the owned
+rows of every rank are compared entry by entry (rel. 1e-12, cancellation-aware
+scale) with the CPU oracle's serial assembly of the whole mesh.  Test
+infrastructure: the oracle is only the checker.  tests/test_gpu_parity.py
+launches this when two GPUs are visible."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.dirname(HERE), os.path.join(os.path.dirname(HERE), "oracle"), HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import oracle_py as orc  # noqa: E402
+import parity_util as pu  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    dims = tuple(int(x) for x in os.environ.get("NW_MGPU_DIMS", "14,12,20").split(","))
+    periodic = os.environ.get("NW_MGPU_PERIODIC", "0") == "1"
+    lengths = (50.0, 40.0, 30.0)
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    P = pu.pkg()
+    ctx = P.Context(local)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.tensor(list(P.Context.comm_unique_id()), dtype=torch.uint8,
+                           device="cuda")
+    dist.broadcast(uid, 0)
+    ctx.comm_init(bytes(uid.cpu().tolist()), world, rank)
+
+    kw = dict(dims=dims, lengths=lengths, periodic=(periodic, periodic))
+    case = pu.Case(nranks=world, rank=rank, **kw)
+    full = pu.Case(**kw)
+    b = case.box
+    mesh = b.make_mesh(ctx, tile_nodes=48)
+    pu.upload_state(P, mesh, case)
+
+    # hid -> gid of every rank (columns refer to nodes other ranks own)
+    mine_map = np.array([[int(b.own_hid[l]), int(b.gid[l])]
+                         for l in range(b.n_nodes)], dtype=np.int64)
+    allmaps = [None] * world
+    dist.all_gather_object(allmaps, mine_map)
+    hid2gid = {}
+    for m in allmaps:
+        for h, g in m:
+            hid2gid[int(h)] = int(g)
+    gid2ser = {int(full.box.gid[l]): int(full.box.own_hid[l])
+               for l in range(full.box.n_nodes)}
+    ser = lambda h: gid2ser[hid2gid[int(h)]]
+
+    gfull = full.oracle_graph()
+    fmdot = full.oracle_mdot()
+    fpec = full.oracle_pecfac(orc.peclet("classic", 1.0))
+    res = {}
+
+    def check_system(name, ls, oref, nrhs):
+        vals, rhs = ls.values()
+        gr = ls.graph()
+        s = ls.sizes
+        erows, ecols = ls.extra()
+        fv, fr = oref.get()
+        fa, fra = oref.get_abs()
+        fdict, adict = {}, {}
+        for r in range(gfull.num_rows_owned):
+            for k in range(gfull.row_start_owned[r], gfull.row_start_owned[r + 1]):
+                fdict[(r, int(gfull.cols[k]))] = fv[k]
+                adict[(r, int(gfull.cols[k]))] = fa[k]
+        rows_arr = np.concatenate([gr["rows"][:s.num_nonzeros_owned], erows])
+        cols_arr = np.concatenate([gr["cols"][:s.num_nonzeros_owned], ecols])
+        vv = np.concatenate([vals[:s.num_nonzeros_owned],
+                             vals[s.num_nonzeros_owned + s.num_nonzeros_shared:]])
+        periodic_rows = set(gr["periodic_rows"].tolist())
+        worst, n = 0.0, 0
+        seen = set()
+        for r_, c_, v_ in zip(rows_arr, cols_arr, vv):
+            if int(r_) in periodic_rows:
+                continue
+            key = (ser(r_), ser(c_))
+            assert key in fdict and key not in seen, key
+            seen.add(key)
+            worst = max(worst, abs(v_ - fdict[key]) /
+                        (pu.TOL * max(adict[key], abs(fdict[key]), 1e-300)))
+            n += 1
+        mine_ser = {ser(s.i_lower + i) for i in range(s.num_rows_owned)
+                    if s.i_lower + i not in periodic_rows}
+        expected = sum(1 for (r, c) in fdict if r in mine_ser)
+        assert n == expected, (name, n, expected)
+        rhs = rhs.reshape(nrhs, -1)
+        for i in range(s.num_rows_owned):
+            if s.i_lower + i in periodic_rows:
+                continue
+            sr = ser(s.i_lower + i)
+            for d in range(nrhs):
+                worst = max(worst, abs(rhs[d, i] - fr[d, sr]) /
+                            (pu.TOL * max(fra[d, sr], abs(fr[d, sr]), 1e-300)))
+        res[name] = worst
+
+    # mdot on this rank's edges must equal the serial value of the same edge
+    mesh.mdot_edge(1.0, 1.0)
+    mdot = mesh.download("mass_flow_rate")
+    key_full = {(int(full.box.gid[a]), int(full.box.gid[c_])): i
+                for i, (a, c_) in enumerate(full.edges.reshape(-1, 2))}
+    idx = np.array([key_full[(int(b.gid[a]), int(b.gid[c_]))]
+                    for a, c_ in case.edges.reshape(-1, 2)])
+    res["mdot"] = pu.scaled_err(mdot, fmdot[idx],
+                                np.abs(fmdot[idx]) + 1e-3 * np.max(np.abs(fmdot)))
+    mesh.upload("mass_flow_rate", fmdot[idx])
+    mesh.upload("peclet_factor", fpec[idx])
+
+    ls = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE, 1)
+    ls.buildEdgeToNodeGraph()
+    ls.finalizeLinearSystem()
+    ls.zeroSystem()
+    ls.assemble_continuity_edge(**pu.CONT_OPTS)
+    ls.loadComplete()
+    check_system("continuity", ls, pu.oracle_continuity(full, gfull), 1)
+    ls.close()
+
+    ls = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE_UVW, 3)
+    ls.buildEdgeToNodeGraph()
+    ls.finalizeLinearSystem()
+    ls.zeroSystem()
+    ls.assemble_momentum_edge("viscosity", **pu.MOM_OPTS)
+    ls.loadComplete()
+    check_system("momentum_uvw", ls,
+                 pu.oracle_momentum(full, gfull, fmdot, fpec, uvw=True), 3)
+    ls.close()
+
+    # nodal gradients incl. the shared-node sum over NCCL
+    gid2loc_full = {int(g): l for l, g in enumerate(full.box.gid)}
+    for phi, d1 in (("pressure", 1), ("velocity", 3)):
+        mesh.register("g_" + phi, P.NW_NODE, d1 * 3)
+        mesh.nodal_grad_edge(phi, "g_" + phi)
+        got = mesh.download("g_" + phi).reshape(b.n_nodes, d1 * 3)
+        ref = orc.nodal_grad_edge(d1, 3, full.edges, full.fields[phi], full.area,
+                                  full.fields["dual_nodal_volume"], full.n_nodes)
+        ref = ref.reshape(full.n_nodes, d1 * 3)
+        scale = 1e-12 * (np.max(np.abs(ref)) + 1e-300)
+        worst = 0.0
+        for l in range(b.n_nodes):  # owned AND shared copies carry the total
+            if periodic and b.own_hid[l] != b.hid[l]:
+                continue
+            worst = max(worst, float(np.max(np.abs(
+                got[l] - ref[gid2loc_full[int(b.gid[l])]])) / scale))
+        res["grad_" + phi] = worst
+
+    allres = [None] * world
+    dist.all_gather_object(allres, res)
+    if rank == 0:
+        worst = max(max(r.values()) for r in allres)
+        print(json.dumps({"world": world, "dims": dims, "periodic": periodic,
+                          "worst_scaled_error": worst, "per_rank": allres}))
+        assert worst < 1.0, allres
+    mesh.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

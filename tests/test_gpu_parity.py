@@ -347,3 +347,24 @@ def test_full_size_conservation(P, ctx, big):
     interior = np.all((ijk > 0) & (ijk < n), axis=1)
     assert np.max(np.abs(gl[interior] - np.array([3.0, -2.0, 0.5]))) < 1e-10
     ls.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("periodic", ["0", "1"])
+def test_two_gpu_partitioned_assembly_matches_serial_oracle(periodic):
+    """NCCL path: 2 ranks, shared-row halo sum (loadComplete) and shared-node
+    gradient sum, owned rows vs the serial oracle (tests/mgpu_parity.py)."""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    env = dict(os.environ, NW_MGPU_PERIODIC=periodic)
+    port = 29600 + (os.getpid() % 300) + int(periodic)
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+         "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+         "--master-port", str(port),
+         os.path.join(os.path.dirname(os.path.abspath(__file__)), "mgpu_parity.py")],
+        env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert '"worst_scaled_error"' in out.stdout
