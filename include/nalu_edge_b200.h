@@ -51,6 +51,10 @@ typedef struct nw_linsys nw_linsys; /* LinearSystem: graph + values */
 const char* nw_last_error(void);
 /* library / ABI version: major*1000 + minor */
 int nw_version(void);
+/* Diagnostics (no reference counterpart; the reference relies on Kokkos
+ * tools): per-phase cycle counters of the tile kernels, out[8][12], filled
+ * only by the NW_PHASE_TIMING build of the library (zeros otherwise). */
+int nw_debug_phase_times(unsigned long long* out, int n, int reset);
 
 /* ------------------------------------------------------------------ */
 /* context                                                             */

@@ -17,7 +17,9 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnalu_edge_b200.so")
+# NW_LIB_PATH: load another build of the same ABI (the phase-timing build)
+LIB_PATH = os.environ.get("NW_LIB_PATH") or os.path.join(
+    _HERE, "libnalu_edge_b200.so")
 MESHGEN_PATH = os.path.join(_HERE, "libnw_meshgen.so")
 
 NW_NODE, NW_EDGE = 0, 1
@@ -94,7 +96,7 @@ class LinsysSizes(C.Structure):
 
 # every symbol include/nalu_edge_b200.h declares (checked by the CPU tests)
 ABI_SYMBOLS = [
-    "nw_last_error", "nw_version", "nw_ctx_create", "nw_ctx_destroy",
+    "nw_last_error", "nw_version", "nw_debug_phase_times", "nw_ctx_create", "nw_ctx_destroy",
     "nw_ctx_sync", "nw_ctx_stream", "nw_comm_unique_id", "nw_ctx_comm_init",
     "nw_mesh_create", "nw_mesh_destroy", "nw_mesh_get_stats",
     "nw_field_register", "nw_field_find", "nw_field_upload",

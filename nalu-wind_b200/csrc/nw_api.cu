@@ -89,6 +89,16 @@ nw_version(void)
   return 1000;
 }
 
+extern "C" int
+nw_debug_phase_times(unsigned long long* out, int n, int reset)
+{
+  if (!out || n < kPhaseKernels * kPhaseSlots)
+    return fail(NW_ERR_ARG, "nw_debug_phase_times: buffer too small");
+  if (phase_times_read(out, reset != 0) != cudaSuccess)
+    return fail(NW_ERR_CUDA, "nw_debug_phase_times: device read failed");
+  return NW_OK;
+}
+
 /* ------------------------------------------------------------------ */
 /*  context                                                            */
 /* ------------------------------------------------------------------ */

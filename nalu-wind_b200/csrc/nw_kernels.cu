@@ -42,6 +42,53 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 
 /* ------------------------------------------------------------------ */
+/*  optional per-phase cycle accounting (diagnostic build only:        */
+/*  make prof -> libnalu_edge_b200_prof.so, tools/phase_times.py)      */
+/* ------------------------------------------------------------------ */
+#ifdef NW_PHASE_TIMING
+__device__ unsigned long long g_phase[kPhaseKernels][kPhaseSlots];
+__device__ __forceinline__ long long
+phase_clock()
+{
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+  return t;
+}
+struct PhaseTimer
+{
+  int kid;
+  int slot = 0;
+  long long last;
+  __device__ __forceinline__ explicit PhaseTimer(int k) : kid(k)
+  {
+    last = phase_clock();
+  }
+  /* thread 0: add the cycles since the previous mark to the next slot */
+  __device__ __forceinline__ void mark()
+  {
+    if (threadIdx.x == 0) {
+      const long long t = phase_clock();
+      atomicAdd(&g_phase[kid][slot], (unsigned long long)(t - last));
+      last = t;
+    }
+    ++slot;
+  }
+  __device__ __forceinline__ void done()
+  {
+    if (threadIdx.x == 0)
+      atomicAdd(&g_phase[kid][kPhaseSlots - 1], 1ull);
+  }
+};
+#define NW_PT_BEGIN(k) PhaseTimer pt_(k)
+#define NW_PT_MARK() pt_.mark()
+#define NW_PT_END() pt_.done()
+#else
+#define NW_PT_BEGIN(k) (void)(k)
+#define NW_PT_MARK()
+#define NW_PT_END()
+#endif
+
+/* ------------------------------------------------------------------ */
 /*  TMA bulk copy + mbarrier (PTX)                                     */
 /* ------------------------------------------------------------------ */
 
@@ -245,6 +292,7 @@ struct ContinuityP
 {
   static constexpr int kND = ND;
   static constexpr int NC = 3 * ND + 3; /* x, u, dpdx, rho, p, udiag */
+  static constexpr int kPhaseId = 0;
   static constexpr int kMinBlocks = 3;  /* <= 85 registers: 3 CTAs per SM */
   static constexpr int NRES = 2;
   static constexpr int NR = 1;
@@ -303,6 +351,7 @@ struct ScalarP
 {
   static constexpr int kND = ND;
   static constexpr int NC = 3 * ND + 3; /* x, vrtm, dqdx, q, rho, dflux */
+  static constexpr int kPhaseId = 1;
   static constexpr int kMinBlocks = 2;
   static constexpr int NRES = 5;
   static constexpr int NR = 1;
@@ -362,6 +411,7 @@ struct MomentumUvwP
   /* x, u, dudx, visc, rho, mask */
   static constexpr int kND = ND;
   static constexpr int NC = 2 * ND + ND * ND + 3;
+  static constexpr int kPhaseId = 2;
   static constexpr int kMinBlocks = 2; /* 128 registers x 256 threads x 2 */
   static constexpr int NRES = 4 + ND;
   static constexpr int NR = ND;
@@ -515,6 +565,7 @@ __global__ void __launch_bounds__(kTileThreads, P::kMinBlocks) ls_tile_kernel(
 {
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t bar[2];
+  NW_PT_BEGIN(P::kPhaseId);
 
   const TileHdr h = mp.tiles[blockIdx.x];
   const LsTileHdr lh = lp.tiles[blockIdx.x];
@@ -552,6 +603,7 @@ __global__ void __launch_bounds__(kTileThreads, P::kMinBlocks) ls_tile_kernel(
     mbar_init(&bar[1], 1);
   }
   __syncthreads();
+  NW_PT_MARK(); /* 0: headers + barrier init */
   stage_nodes_issue<P::NC>(
     s_node, stride, nc, h, &bar[0], edge_stream_bytes(h, nin));
   if (threadIdx.x == 0) {
@@ -570,9 +622,12 @@ __global__ void __launch_bounds__(kTileThreads, P::kMinBlocks) ls_tile_kernel(
       tma_load_1d(s_go, lp.entGo + lh.entPtr, bEnt, &bar[1]);
     }
   }
+  NW_PT_MARK(); /* 1: TMA issue */
   stage_halo_gather<P::NC>(s_node, stride, nc, h, mp.haloNodes);
+  NW_PT_MARK(); /* 2: halo gather */
   mbar_wait(&bar[0], 0);
   __syncthreads();
+  NW_PT_MARK(); /* 3: stage wait */
 
   /* ---- phase 1: per-edge physics, entirely out of shared memory ---- */
   {
@@ -597,8 +652,10 @@ __global__ void __launch_bounds__(kTileThreads, P::kMinBlocks) ls_tile_kernel(
         s_res[k * L.resStride + j] = res[k];
     }
   }
+  NW_PT_MARK(); /* 4: phase 1 */
   mbar_wait(&bar[1], 0);
   __syncthreads();
+  NW_PT_MARK(); /* 5: phase-1 barrier */
 
   /* ---- phases 2+3, warp by warp: one thread per row reduces the row's
    * half-edges in list order, then the warp copies the staging range of its
@@ -658,6 +715,8 @@ __global__ void __launch_bounds__(kTileThreads, P::kMinBlocks) ls_tile_kernel(
       }
     }
   }
+  NW_PT_MARK(); /* 6: phases 2+3 */
+  NW_PT_END();
 }
 
 /* ------------------------------------------------------------------ */
@@ -853,6 +912,7 @@ __global__ void __launch_bounds__(kTileThreads) mdot_tile_kernel(
   using P = ContinuityP<ND>;
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t bar;
+  NW_PT_BEGIN(3);
   const TileHdr h = mp.tiles[blockIdx.x];
   const int stride = even_up_i(h.nOwnPad + h.nHalo);
   const int estride = even_up_i(mp.maxTileEdges);
@@ -861,12 +921,16 @@ __global__ void __launch_bounds__(kTileThreads) mdot_tile_kernel(
   if (threadIdx.x == 0)
     mbar_init(&bar, 1);
   __syncthreads();
+  NW_PT_MARK();
   stage_nodes_issue<P::NC>(smem, stride, nc, h, &bar, edge_stream_bytes(h, ND));
   if (threadIdx.x == 0)
     stage_edges_issue(s_lr, s_area, estride, mp, h, ec.area, ND, &bar);
+  NW_PT_MARK();
   stage_halo_gather<P::NC>(smem, stride, nc, h, mp.haloNodes);
+  NW_PT_MARK();
   mbar_wait(&bar, 0);
   __syncthreads();
+  NW_PT_MARK();
   const SmemLd ld{smem, stride};
   for (int j = threadIdx.x; j < h.nEdges; j += blockDim.x) {
     const uint32_t v = s_lr[j];
@@ -882,6 +946,8 @@ __global__ void __launch_bounds__(kTileThreads) mdot_tile_kernel(
       mdot_core<ND>(L, R, av, o.noc_fac, o.interp_together);
     mdotOut[h.edge0 + j] = c.tmdot;
   }
+  NW_PT_MARK();
+  NW_PT_END();
 }
 
 template <int ND>
@@ -894,18 +960,23 @@ __global__ void __launch_bounds__(kTileThreads) peclet_tile_kernel(
   constexpr int NC = 2 * ND + 2;
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t bar;
+  NW_PT_BEGIN(4);
   const TileHdr h = mp.tiles[blockIdx.x];
   const int stride = even_up_i(h.nOwnPad + h.nHalo);
   uint32_t* s_lr = reinterpret_cast<uint32_t*>(smem + (size_t)NC * mp.maxStaged);
   if (threadIdx.x == 0)
     mbar_init(&bar, 1);
   __syncthreads();
+  NW_PT_MARK();
   stage_nodes_issue<NC>(smem, stride, nc, h, &bar, edge_stream_bytes(h, 0));
   if (threadIdx.x == 0)
     stage_edges_issue(s_lr, nullptr, 0, mp, h, nullptr, 0, &bar);
+  NW_PT_MARK();
   stage_halo_gather<NC>(smem, stride, nc, h, mp.haloNodes);
+  NW_PT_MARK();
   mbar_wait(&bar, 0);
   __syncthreads();
+  NW_PT_MARK();
   const SmemLd ld{smem, stride};
   for (int j = threadIdx.x; j < h.nEdges; j += blockDim.x) {
     const uint32_t v = s_lr[j];
@@ -924,6 +995,8 @@ __global__ void __launch_bounds__(kTileThreads) peclet_tile_kernel(
     R.mu = ld(2 * ND + 1, r);
     pecfacOut[h.edge0 + j] = peclet_eval(o.pf, peclet_number<ND>(L, R, o.eps));
   }
+  NW_PT_MARK();
+  NW_PT_END();
 }
 
 /* ------------------------------------------------------------------ */
@@ -950,6 +1023,7 @@ __global__ void __launch_bounds__(kTileThreads) grad_tile_kernel(
   constexpr int NV = D1 * ND;
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t bar[2];
+  NW_PT_BEGIN(D1 == 1 ? 5 : 6);
   const TileHdr h = mp.tiles[blockIdx.x];
   const int stride = even_up_i(h.nOwnPad + h.nHalo);
   const int estride = even_up_i(mp.maxTileEdges);
@@ -962,6 +1036,7 @@ __global__ void __launch_bounds__(kTileThreads) grad_tile_kernel(
     mbar_init(&bar[1], 1);
   }
   __syncthreads();
+  NW_PT_MARK();
   stage_nodes_issue<D1>(s_phi, stride, phi, h, &bar[0], edge_stream_bytes(h, ND));
   if (threadIdx.x == 0) {
     stage_edges_issue(s_lr, s_area, estride, mp, h, ec.area, ND, &bar[0]);
@@ -970,10 +1045,13 @@ __global__ void __launch_bounds__(kTileThreads) grad_tile_kernel(
     if (bEll)
       tma_load_1d(s_ell, mp.heNodeEll + h.ellPtrNode, bEll, &bar[1]);
   }
+  NW_PT_MARK();
   stage_halo_gather<D1>(s_phi, stride, phi, h, mp.haloNodes);
+  NW_PT_MARK();
   mbar_wait(&bar[0], 0);
   mbar_wait(&bar[1], 0);
   __syncthreads();
+  NW_PT_MARK();
 
   const int32_t* sliceOff = mp.sliceOffNode + h.slicePtrNode;
   for (int i = threadIdx.x; i < h.nOwn; i += blockDim.x) {
@@ -1015,6 +1093,8 @@ __global__ void __launch_bounds__(kTileThreads) grad_tile_kernel(
     for (int k = 0; k < NV; ++k)
       out.c[k][h.node0 + i] = acc[k] * invVol;
   }
+  NW_PT_MARK();
+  NW_PT_END();
 }
 
 /* atomic comparison variant: grad must be zeroed beforehand */
@@ -1386,6 +1466,23 @@ blocks_for(int64_t n, int bs)
 /* ------------------------------------------------------------------ */
 /*  launchers                                                          */
 /* ------------------------------------------------------------------ */
+
+cudaError_t
+phase_times_read(unsigned long long* out, bool reset)
+{
+#ifdef NW_PHASE_TIMING
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_phase, sizeof(g_phase));
+  if (e != cudaSuccess || !reset)
+    return e;
+  static const unsigned long long zero[kPhaseKernels][kPhaseSlots] = {};
+  return cudaMemcpyToSymbol(g_phase, zero, sizeof(zero));
+#else
+  (void)reset;
+  for (int i = 0; i < kPhaseKernels * kPhaseSlots; ++i)
+    out[i] = 0;
+  return cudaSuccess;
+#endif
+}
 
 cudaError_t
 launch_mdot_tile(
