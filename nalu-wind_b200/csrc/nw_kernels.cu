@@ -30,6 +30,7 @@
 #include "nw_kernels.cuh"
 
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -58,33 +59,46 @@ struct PhaseTimer
 {
   int kid;
   int slot = 0;
+  bool me;
   long long last;
-  __device__ __forceinline__ explicit PhaseTimer(int k) : kid(k)
+  __device__ __forceinline__ explicit PhaseTimer(int k, int who = 0)
+    : kid(k), me((int)threadIdx.x == who)
   {
     last = phase_clock();
   }
-  /* thread 0: add the cycles since the previous mark to the next slot */
+  /* the observing thread: add the cycles since the previous mark to the next slot */
   __device__ __forceinline__ void mark()
   {
-    if (threadIdx.x == 0) {
+    if (me) {
       const long long t = phase_clock();
       atomicAdd(&g_phase[kid][slot], (unsigned long long)(t - last));
       last = t;
     }
     ++slot;
   }
+  /* persistent kernels: restart the slot sequence for the next tile */
+  __device__ __forceinline__ void lap()
+  {
+    slot = 0;
+    if (me)
+      atomicAdd(&g_phase[kid][kPhaseSlots - 1], 1ull);
+  }
   __device__ __forceinline__ void done()
   {
-    if (threadIdx.x == 0)
+    if (me)
       atomicAdd(&g_phase[kid][kPhaseSlots - 1], 1ull);
   }
 };
 #define NW_PT_BEGIN(k) PhaseTimer pt_(k)
+#define NW_PT_BEGIN_AT(k, who) PhaseTimer pt_(k, who)
 #define NW_PT_MARK() pt_.mark()
+#define NW_PT_LAP() pt_.lap()
 #define NW_PT_END() pt_.done()
 #else
 #define NW_PT_BEGIN(k) (void)(k)
+#define NW_PT_BEGIN_AT(k, who) (void)(k)
 #define NW_PT_MARK()
+#define NW_PT_LAP()
 #define NW_PT_END()
 #endif
 
@@ -180,8 +194,13 @@ stage_halo_gather(
   const TileHdr& h,
   const int32_t* __restrict__ haloNodes)
 {
+  /* warp 0 is busy issuing the bulk copies (~100 cycles of issue latency
+   * each, profiles/r01c_phase_cycles_tile192.txt): the other warps gather,
+   * so the two overlap instead of thread 0 doing one after the other */
+  if (threadIdx.x < 32)
+    return;
   const int32_t* halo = haloNodes + h.haloPtr;
-  for (int k = threadIdx.x; k < h.nHalo; k += blockDim.x) {
+  for (int k = threadIdx.x - 32; k < h.nHalo; k += blockDim.x - 32) {
     const int32_t g = __ldg(halo + k);
 #pragma unroll
     for (int c = 0; c < NC; ++c)
@@ -293,7 +312,8 @@ struct ContinuityP
   static constexpr int kND = ND;
   static constexpr int NC = 3 * ND + 3; /* x, u, dpdx, rho, p, udiag */
   static constexpr int kPhaseId = 0;
-  static constexpr int kMinBlocks = 3;  /* <= 85 registers: 3 CTAs per SM */
+  static constexpr int kMinBlocks = 3; /* <= 85 registers: 3 CTAs per SM */
+  static constexpr int kStreamCtas = 3;
   static constexpr int NRES = 2;
   static constexpr int NR = 1;
   static constexpr bool kNeedsMdot = false;
@@ -353,6 +373,7 @@ struct ScalarP
   static constexpr int NC = 3 * ND + 3; /* x, vrtm, dqdx, q, rho, dflux */
   static constexpr int kPhaseId = 1;
   static constexpr int kMinBlocks = 2;
+  static constexpr int kStreamCtas = 2;
   static constexpr int NRES = 5;
   static constexpr int NR = 1;
   static constexpr bool kNeedsMdot = true;
@@ -413,6 +434,7 @@ struct MomentumUvwP
   static constexpr int NC = 2 * ND + ND * ND + 3;
   static constexpr int kPhaseId = 2;
   static constexpr int kMinBlocks = 2; /* 128 registers x 256 threads x 2 */
+  static constexpr int kStreamCtas = 2;
   static constexpr int NRES = 4 + ND;
   static constexpr int NR = ND;
   static constexpr bool kNeedsMdot = true;
@@ -555,8 +577,8 @@ struct LsSmem
   }
 };
 
-template <class P, int ND>
-__global__ void __launch_bounds__(kTileThreads, P::kMinBlocks) ls_tile_kernel(
+template <class P, int ND, int MINB = P::kMinBlocks>
+__global__ void __launch_bounds__(kTileThreads, MINB) ls_tile_kernel(
   const MeshPlanDev mp,
   const LsPlanDev lp,
   const NodeComps nc,
@@ -1130,6 +1152,432 @@ __global__ void __launch_bounds__(kTileThreads) grad_atomic_kernel(
 }
 
 /* ------------------------------------------------------------------ */
+/*  stream kernels: persistent CTAs, software-pipelined tile staging   */
+/* ------------------------------------------------------------------ */
+
+/* Round-1c per-phase cycle accounting (profiles/r01c_phase_cycles_tile192.txt)
+ * showed the one-CTA-per-tile kernels spend 40-55 % of a CTA's life in the
+ * stage: header read -> ~100 cycles of issue latency per TMA bulk copy (28 of
+ * them for momentum, serialised in the SM's TMA unit whichever warp issues
+ * them, profiles/r01d_*) -> dependent halo gather (three DRAM round trips).
+ * The stream kernels keep 256-thread CTAs resident for the whole launch (two
+ * or three per SM, so that one CTA's barriers and row reduction overlap the
+ * other's physics) and run a software pipeline over the tiles
+ * t_k = blockIdx.x + k * gridDim.x :
+ *
+ *   after the phase-1 barrier of tile k (node stage dead) the CTA issues
+ *     - the node data of t_{k+1}: own range as 16-byte cp.async.cg (LDGSTS,
+ *       8 cycles of issue per warp-op, spread over all warps), halo nodes as
+ *       8-byte cp.async through the staged halo list;
+ *     - the reduction plan of t_{k+1} into the other plan buffer;
+ *     - the halo slot list of t_{k+2} and the 64-byte headers of t_{k+3}
+ *       into small rings,
+ *   and after the phase-2 barrier (edge results dead) the edge streams of
+ *   t_{k+1}.  Every dependent address (header -> list -> halo data) is in
+ *   shared memory a full tile time before it is needed.
+ *
+ * Same plan data, same physics, same write-once row ownership as the tile
+ * kernels; the row reduction uses four lanes per row (partial sums combined by
+ * a fixed xor-shuffle tree, so the result is still deterministic). */
+
+constexpr int kStreamThreads = 256;
+constexpr int kStreamWarps = kStreamThreads / 32;
+constexpr int kHdrRing = 4;
+constexpr int kListRing = 2;
+
+__device__ __forceinline__ void
+cp_async4(void* dstSmem, const void* src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dstSmem)),
+               "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void
+cp_async8(void* dstSmem, const void* src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dstSmem)),
+               "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void
+cp_async16(void* dstSmem, const void* src)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dstSmem)),
+               "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void
+cp_async_commit()
+{
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void
+cp_async_wait_all()
+{
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+/* one warp copies `bytes` (multiple of 16, both ends 16-byte aligned) */
+__device__ __forceinline__ void
+warp_copy16(void* dstSmem, const void* src, uint32_t bytes, int lane)
+{
+  char* d = static_cast<char*>(dstSmem);
+  const char* s = static_cast<const char*>(src);
+  for (uint32_t q = (uint32_t)lane * 16u; q < bytes; q += 32u * 16u)
+    cp_async16(d + q, s + q);
+}
+
+/* static shared state of a stream kernel */
+struct StreamShared
+{
+  TileHdr hdr[kHdrRing];
+  LsTileHdr lhdr[kHdrRing];
+};
+
+/* headers of this CTA's k-th tile -> ring slot k % kHdrRing (threads 0..7) */
+template <bool LS>
+__device__ __forceinline__ void
+stream_issue_hdr(
+  StreamShared& ss, const TileHdr* tiles, const LsTileHdr* ltiles, int k, int tile)
+{
+  const int t = threadIdx.x;
+  if (t < 4)
+    cp_async16(
+      reinterpret_cast<char*>(&ss.hdr[k % kHdrRing]) + 16 * t,
+      reinterpret_cast<const char*>(tiles + tile) + 16 * t);
+  else if (LS && t < 8)
+    cp_async16(
+      reinterpret_cast<char*>(&ss.lhdr[k % kHdrRing]) + 16 * (t - 4),
+      reinterpret_cast<const char*>(ltiles + tile) + 16 * (t - 4));
+}
+
+/* halo slot list of a tile -> ring slot */
+__device__ __forceinline__ void
+stream_issue_list(
+  int32_t* s_list, const TileHdr& h, const int32_t* __restrict__ haloNodes)
+{
+  for (int i = threadIdx.x; i < h.nHalo; i += kStreamThreads)
+    cp_async4(s_list + i, haloNodes + h.haloPtr + i);
+}
+
+/* node data of a tile: comp c of the own range by warp c % nWarps (16-byte
+ * copies), halo nodes by per-thread 8-byte async copies through the staged
+ * halo list */
+template <int NC>
+__device__ __forceinline__ void
+stream_issue_nodes(
+  double* s_node, int stride, const NodeComps& nc, const TileHdr& h,
+  const int32_t* s_list, int warp, int lane)
+{
+  const uint32_t bNode = (uint32_t)h.nOwnPad * 8u;
+  for (int c = warp; c < NC; c += kStreamWarps)
+    warp_copy16(s_node + c * stride, nc.c[c] + h.node0, bNode, lane);
+  for (int i = threadIdx.x; i < h.nHalo; i += kStreamThreads) {
+    const int32_t g = s_list[i];
+    double* dst = s_node + h.nOwnPad + i;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      cp_async8(dst + c * stride, nc.c[c] + g);
+  }
+}
+
+/* shared-memory carve-up of ls_stream_kernel (sizes in bytes, 16-aligned) */
+template <class P>
+struct LsStreamSmem
+{
+  static constexpr int NEDGE = LsSmem<P>::NEDGE;
+  int stride, resStride, lrLen, valsLen, ellLen, entLen, listLen, sliceLen;
+  size_t nodeBytes, resBytes, planBytes, valsBytes, listBytes;
+  __host__ __device__ LsStreamSmem(const MeshPlanDev& mp, const LsPlanDev& lp)
+  {
+    stride = mp.maxStaged;
+    resStride = (mp.maxTileEdges + 1) & ~1;
+    lrLen = (mp.maxTileEdges + 3) & ~3;
+    valsLen = (lp.maxTileNnz + 3) & ~3;
+    ellLen = (lp.maxTileEll + 3) & ~3;
+    entLen = (lp.maxTileEnts + 3) & ~3;
+    listLen = (mp.maxStaged + 3) & ~3;
+    sliceLen = ((lp.maxTileEnts + 31) / 32 + 1 + 3) & ~3;
+    nodeBytes = sizeof(double) * (size_t)P::NC * stride;
+    resBytes = sizeof(double) * (size_t)NEDGE * resStride + 4u * (size_t)lrLen;
+    planBytes = 4u * (size_t)ellLen + 12u * (size_t)entLen + 4u * (size_t)sliceLen;
+    valsBytes = 12u * (size_t)valsLen;
+    listBytes = 4u * (size_t)listLen;
+  }
+  __host__ __device__ size_t bytes() const
+  {
+    return nodeBytes + resBytes + 2 * planBytes + valsBytes + kListRing * listBytes;
+  }
+};
+
+template <class P, int ND, int MINB>
+__global__ void __launch_bounds__(kStreamThreads, MINB) ls_stream_kernel(
+  const MeshPlanDev mp,
+  const LsPlanDev lp,
+  const NodeComps nc,
+  const EdgeComps ec,
+  const typename P::Opts o)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(16) StreamShared ss;
+  using SM = LsStreamSmem<P>;
+  const SM L(mp, lp);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x;
+  const int nMine = (mp.nTiles - (int)blockIdx.x + G - 1) / G;
+  NW_PT_BEGIN_AT(8 + P::kPhaseId, 32 * 5);
+
+  /* every region is an offset from the dynamic shared base, so that all
+   * accesses stay shared-space LDS/STS */
+  double* s_node = reinterpret_cast<double*>(smem_raw);
+  double* s_res = reinterpret_cast<double*>(smem_raw + L.nodeBytes);
+  uint32_t* s_lr = reinterpret_cast<uint32_t*>(s_res + SM::NEDGE * L.resStride);
+  unsigned char* s_planBase = smem_raw + L.nodeBytes + L.resBytes;
+  double* s_vals = reinterpret_cast<double*>(s_planBase + 2 * L.planBytes);
+  int32_t* s_delta = reinterpret_cast<int32_t*>(s_vals + L.valsLen);
+  int32_t* s_listRing =
+    reinterpret_cast<int32_t*>(s_planBase + 2 * L.planBytes + L.valsBytes);
+  const int stride = L.stride;
+  auto s_ell_of = [&](int b) {
+    return reinterpret_cast<uint32_t*>(s_planBase + (size_t)b * L.planBytes);
+  };
+
+  /* edge input streams of this policy: area, [mdot], [pecfac] */
+  constexpr int kMdot = ND;
+  constexpr int kPec = ND + (P::kNeedsMdot ? 1 : 0);
+  const bool hasPec = P::kNeedsPec && ec.pecfac != nullptr;
+  const int nin = kPec + (hasPec ? 1 : 0);
+
+  auto tile_of = [&](int k) { return (int)blockIdx.x + k * G; };
+
+  /* node data + reduction plan of the k-th tile (headers and halo list of
+   * that tile are already visible in their rings) */
+  auto issue_nodes_plan = [&](int k) {
+    const TileHdr& h = ss.hdr[k % kHdrRing];
+    const LsTileHdr& lh = ss.lhdr[k % kHdrRing];
+    stream_issue_nodes<P::NC>(
+      s_node, stride, nc, h, s_listRing + (k % kListRing) * L.listLen, warp,
+      lane);
+    uint32_t* s_ell = s_ell_of(k & 1);
+    EntInfo* s_ent = reinterpret_cast<EntInfo*>(s_ell + L.ellLen);
+    int32_t* s_row = reinterpret_cast<int32_t*>(s_ent + L.entLen);
+    int32_t* s_go = s_row + L.entLen;
+    int32_t* s_slice = s_go + L.entLen;
+    const uint32_t bEnt = round16((uint32_t)lh.nEnts * 4u);
+    /* the node copies went to warps 0 .. NC-1 (mod nWarps): start the plan
+     * copies where they stopped */
+    const int w0 = P::NC % kStreamWarps;
+    if (warp == (w0 + 0) % kStreamWarps)
+      warp_copy16(s_ell, lp.heEll + lh.ellPtr, (uint32_t)lh.ellLen * 4u, lane);
+    if (warp == (w0 + 1) % kStreamWarps)
+      warp_copy16(s_ent, lp.entInfo + lh.entPtr, bEnt, lane);
+    if (warp == (w0 + 2) % kStreamWarps)
+      warp_copy16(s_row, lp.entRhsRow + lh.entPtr, bEnt, lane);
+    if (warp == (w0 + 3) % kStreamWarps) {
+      warp_copy16(s_go, lp.entGo + lh.entPtr, bEnt, lane);
+      const int nSl = (lh.nEnts + 31) / 32 + 1;
+      for (int i = lane; i < nSl; i += 32)
+        cp_async4(s_slice + i, lp.sliceOff + lh.slicePtr + i);
+    }
+  };
+  /* edge streams of the k-th tile: packed (L,R) records + input components */
+  auto issue_edges = [&](int k) {
+    const TileHdr& h = ss.hdr[k % kHdrRing];
+    const uint32_t bEdge = round16((uint32_t)h.nEdges * 8u);
+    for (int i = warp; i < nin + 1; i += kStreamWarps) {
+      if (i == nin) {
+        warp_copy16(s_lr, mp.lr + h.edge0, round16((uint32_t)h.nEdges * 4u), lane);
+      } else {
+        const double* src =
+          i < ND ? ec.area[i < ND ? i : 0]
+                 : (P::kNeedsMdot && i == kMdot ? ec.mdot : ec.pecfac);
+        warp_copy16(s_res + i * L.resStride, src + h.edge0, bEdge, lane);
+      }
+    }
+  };
+  auto issue_list = [&](int k) {
+    stream_issue_list(
+      s_listRing + (k % kListRing) * L.listLen, ss.hdr[k % kHdrRing],
+      mp.haloNodes);
+  };
+
+  /* ---- prologue: fill the rings ---- */
+  for (int k = 0; k < 3 && k < nMine; ++k)
+    stream_issue_hdr<true>(ss, mp.tiles, lp.tiles, k, tile_of(k));
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+  for (int k = 0; k < 2 && k < nMine; ++k)
+    issue_list(k);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+  if (nMine > 0) {
+    issue_nodes_plan(0);
+    issue_edges(0);
+  }
+  cp_async_commit();
+
+  for (int k = 0; k < nMine; ++k) {
+    NW_PT_MARK(); /* 0: loop overhead (first lap: prologue) */
+    /* everything issued for tile k (and the ring entries issued during the
+     * previous iteration) has landed */
+    cp_async_wait_all();
+    NW_PT_MARK(); /* 1: own cp.async landed */
+    __syncthreads();
+    NW_PT_MARK(); /* 2: top barrier */
+
+    const TileHdr& h = ss.hdr[k % kHdrRing];
+    const LsTileHdr& lh = ss.lhdr[k % kHdrRing];
+    const uint32_t* s_ell = s_ell_of(k & 1);
+    const EntInfo* s_ent = reinterpret_cast<const EntInfo*>(s_ell + L.ellLen);
+    const int32_t* s_row = reinterpret_cast<const int32_t*>(s_ent + L.entLen);
+    const int32_t* s_go = s_row + L.entLen;
+    const int32_t* s_slice = s_go + L.entLen;
+
+    /* row staging starts from zero: a slot no local half-edge touches (a
+     * column that only other algorithms fill) is written as 0 */
+    for (int e = tid; e < lh.nnz; e += kStreamThreads)
+      s_vals[e] = 0.0;
+
+    /* ---- phase 1: per-edge physics out of shared memory ---- */
+    {
+      const SmemLd ld{s_node, stride};
+      for (int j = tid; j < h.nEdges; j += kStreamThreads) {
+        const uint32_t v = s_lr[j];
+        const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
+        double av[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+          av[d] = s_res[d * L.resStride + j];
+        double mdot = 0.0, pecfac = 0.0;
+        if (P::kNeedsMdot)
+          mdot = s_res[kMdot * L.resStride + j];
+        if (hasPec)
+          pecfac = s_res[kPec * L.resStride + j];
+        double res[P::NRES];
+        P::compute(ld, l, r, av, mdot, pecfac, o, res);
+#pragma unroll
+        for (int q = 0; q < P::NRES; ++q)
+          s_res[q * L.resStride + j] = res[q];
+      }
+    }
+    NW_PT_MARK(); /* 3: zero + phase 1 */
+    __syncthreads();
+    NW_PT_MARK(); /* 4: phase-1 barrier */
+
+    /* the node stage is dead: start pulling the next tile in */
+    if (k + 3 < nMine)
+      stream_issue_hdr<true>(ss, mp.tiles, lp.tiles, k + 3, tile_of(k + 3));
+    if (k + 2 < nMine)
+      issue_list(k + 2);
+    if (k + 1 < nMine)
+      issue_nodes_plan(k + 1);
+    cp_async_commit();
+    NW_PT_MARK(); /* 5: issue nodes + plan of the next tile */
+
+    /* ---- phase 2: four lanes per row ---- */
+    {
+      const int sub = lane & 3;
+      for (int rbase = warp * 8; rbase < lh.nEnts; rbase += kStreamWarps * 8) {
+        const int row = rbase + (lane >> 2);
+        const bool active = row < lh.nEnts;
+        double diag = 0.0;
+        double rhs[P::NR];
+#pragma unroll
+        for (int d = 0; d < P::NR; ++d)
+          rhs[d] = 0.0;
+        EntInfo ei{0, 0, 0};
+        const uint32_t* hp = s_ell;
+        int W = 0;
+        bool sawDup = false;
+        if (active) {
+          const int sl = row >> 5;
+          const int o0 = s_slice[sl], o1 = s_slice[sl + 1];
+          hp = s_ell + o0 + (row & 31);
+          W = (o1 - o0) >> 5;
+          ei = s_ent[row];
+          double* vrow = s_vals + ei.base;
+          for (int w = sub; w < W; w += 4) {
+            const uint32_t hv = hp[w * 32];
+            if (hv & kHeValid) {
+              double dg, off, rr[P::NR];
+              P::contrib(
+                he_side(hv), s_res, L.resStride, (int)he_edge(hv), dg, off, rr);
+              diag += dg;
+#pragma unroll
+              for (int d = 0; d < P::NR; ++d)
+                rhs[d] += rr[d];
+              if (hv & kHeDup)
+                sawDup = true;
+              else
+                vrow[he_k(hv)] = off;
+            }
+          }
+        }
+        /* fixed combination tree over the four lanes of the row */
+        diag += __shfl_xor_sync(kFull, diag, 1);
+        diag += __shfl_xor_sync(kFull, diag, 2);
+#pragma unroll
+        for (int d = 0; d < P::NR; ++d) {
+          rhs[d] += __shfl_xor_sync(kFull, rhs[d], 1);
+          rhs[d] += __shfl_xor_sync(kFull, rhs[d], 2);
+        }
+        const bool anyDup = __any_sync(kFull, sawDup);
+        if (anyDup) {
+          /* periodic aliases: later members of a (row, column) group are added
+           * in list order by one lane, after the group's first store */
+          __syncwarp();
+          if (active && sub == 0) {
+            double* vrow = s_vals + ei.base;
+            for (int w = 0; w < W; ++w) {
+              const uint32_t hv = hp[w * 32];
+              if ((hv & kHeValid) && (hv & kHeDup)) {
+                double dg, off, rr[P::NR];
+                P::contrib(
+                  he_side(hv), s_res, L.resStride, (int)he_edge(hv), dg, off, rr);
+                vrow[he_k(hv)] += off;
+              }
+            }
+          }
+        }
+        if (active) {
+          if (sub == 0)
+            s_vals[ei.base + ei.diagK] = diag;
+          const int32_t delta = s_go[row] - (int32_t)ei.base;
+          for (int q = sub; q < (int)ei.nnz; q += 4)
+            s_delta[ei.base + q] = delta;
+          if (sub < P::NR) {
+            double mine = rhs[0];
+#pragma unroll
+            for (int d = 1; d < P::NR; ++d)
+              if (sub == d)
+                mine = rhs[d];
+            lp.rhs[(int64_t)sub * lp.rhsStride + s_row[row]] = mine;
+          }
+        }
+      }
+    }
+    NW_PT_MARK(); /* 6: phase 2 */
+    __syncthreads();
+    NW_PT_MARK(); /* 7: phase-2 barrier */
+
+    /* the edge results are dead: pull the next tile's edge streams */
+    if (k + 1 < nMine)
+      issue_edges(k + 1);
+    cp_async_commit();
+    NW_PT_MARK(); /* 8: issue edge streams of the next tile */
+
+    /* ---- phase 3: coalesced copy-out, every value written exactly once ---- */
+    for (int e = tid; e < lh.nnz; e += kStreamThreads)
+      lp.values[e + s_delta[e]] = s_vals[e];
+    NW_PT_MARK(); /* 9: phase 3 */
+    NW_PT_LAP();
+  }
+}
+
+
+/* ------------------------------------------------------------------ */
 /*  utility kernels                                                    */
 /* ------------------------------------------------------------------ */
 
@@ -1396,7 +1844,8 @@ template <class K>
 cudaError_t
 set_smem(K kernel, size_t bytes)
 {
-  if (bytes > 48 * 1024)
+  /* static shared memory counts against the 48 KB default too */
+  if (bytes > 40 * 1024)
     return cudaFuncSetAttribute(
       kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   return cudaSuccess;
@@ -1418,6 +1867,43 @@ ls_tile_smem(const MeshPlanDev& mp, const LsPlanDev& lp)
   return LsSmem<P>(mp, lp).bytes();
 }
 
+/* SM count of the current device (persistent grids) */
+inline int
+sm_count()
+{
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+/* tuning switches (diagnostic; the defaults are the product path):
+ *   NW_STREAM=1        use the persistent stream kernels (comparison variant)
+ *   NW_STREAM_CTAS=n   resident stream CTAs per SM (1 or 2) */
+inline int
+env_int(const char* name, int dflt)
+{
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+inline bool
+stream_enabled()
+{
+  static const int on = env_int("NW_STREAM", 0);
+  return on != 0;
+}
+
+template <class P, int ND>
+cudaError_t launch_ls_stream(
+  const MeshPlanDev& mp, const LsPlanDev& lp, const NodeComps& nc,
+  const EdgeComps& ec, const typename P::Opts& o, cudaStream_t s,
+  bool* launched);
+
 template <class P, int ND>
 cudaError_t
 launch_ls_tile(
@@ -1428,13 +1914,72 @@ launch_ls_tile(
   const typename P::Opts& o,
   cudaStream_t s)
 {
+  bool launched = false;
+  cudaError_t e = launch_ls_stream<P, ND>(mp, lp, nc, ec, o, s, &launched);
+  if (e != cudaSuccess || launched)
+    return e;
   const size_t bytes = ls_tile_smem<P>(mp, lp);
   if (bytes > 227 * 1024)
     return cudaErrorInvalidConfiguration;
-  cudaError_t e = set_smem(ls_tile_kernel<P, ND>, bytes);
+  /* diagnostic: NW_TILE_CTAS=3 forces the 3-CTA (<= 85 register) build when
+   * three copies of the tile's shared memory fit */
+  static const int ctasEnv = env_int("NW_TILE_CTAS", 0);
+  if (ctasEnv == 3 && 3 * (bytes + 1024) <= 228 * 1024) {
+    e = set_smem(ls_tile_kernel<P, ND, 3>, bytes);
+    if (e != cudaSuccess)
+      return e;
+    ls_tile_kernel<P, ND, 3>
+      <<<mp.nTiles, kTileThreads, bytes, s>>>(mp, lp, nc, ec, o);
+    return cudaGetLastError();
+  }
+  e = set_smem(ls_tile_kernel<P, ND>, bytes);
   if (e != cudaSuccess)
     return e;
   ls_tile_kernel<P, ND><<<mp.nTiles, kTileThreads, bytes, s>>>(mp, lp, nc, ec, o);
+  return cudaGetLastError();
+}
+
+template <class P, int ND>
+cudaError_t
+launch_ls_stream(
+  const MeshPlanDev& mp,
+  const LsPlanDev& lp,
+  const NodeComps& nc,
+  const EdgeComps& ec,
+  const typename P::Opts& o,
+  cudaStream_t s,
+  bool* launched)
+{
+  *launched = false;
+  if (!stream_enabled() || mp.nTiles == 0)
+    return cudaSuccess;
+  const size_t bytes = LsStreamSmem<P>(mp, lp).bytes();
+  static const int ctasEnv = env_int("NW_STREAM_CTAS", 0);
+  int ctas = ctasEnv > 0 ? ctasEnv : P::kStreamCtas;
+  /* resident CTAs the shared memory allows (1 KB reserved per CTA) */
+  while (ctas > 1 && (size_t)ctas * (bytes + 1024 + sizeof(StreamShared)) > 228 * 1024)
+    --ctas;
+  if (bytes + 1024 + sizeof(StreamShared) > 227 * 1024)
+    return cudaSuccess; /* tile too large for the stream layout: tile kernel */
+  const int grid = std::min(mp.nTiles, sm_count() * ctas);
+  cudaError_t e;
+  if (ctas >= 3) {
+    if ((e = set_smem(ls_stream_kernel<P, ND, 3>, bytes)) != cudaSuccess)
+      return e;
+    ls_stream_kernel<P, ND, 3>
+      <<<grid, kStreamThreads, bytes, s>>>(mp, lp, nc, ec, o);
+  } else if (ctas == 2) {
+    if ((e = set_smem(ls_stream_kernel<P, ND, 2>, bytes)) != cudaSuccess)
+      return e;
+    ls_stream_kernel<P, ND, 2>
+      <<<grid, kStreamThreads, bytes, s>>>(mp, lp, nc, ec, o);
+  } else {
+    if ((e = set_smem(ls_stream_kernel<P, ND, 1>, bytes)) != cudaSuccess)
+      return e;
+    ls_stream_kernel<P, ND, 1>
+      <<<grid, kStreamThreads, bytes, s>>>(mp, lp, nc, ec, o);
+  }
+  *launched = true;
   return cudaGetLastError();
 }
 

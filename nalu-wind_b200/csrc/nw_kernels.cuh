@@ -16,7 +16,7 @@ constexpr int kMaxNodeComps = 20;
 /* diagnostic per-phase cycle counters (filled only by the NW_PHASE_TIMING
  * build): [kernel][slot], last slot = CTA count.  Kernels: 0 continuity,
  * 1 scalar, 2 momentum, 3 mdot, 4 peclet, 5 grad scalar, 6 grad vector. */
-constexpr int kPhaseKernels = 8;
+constexpr int kPhaseKernels = 16; /* 8.. : stream kernels */
 constexpr int kPhaseSlots = 12;
 cudaError_t phase_times_read(unsigned long long* out, bool reset);
 

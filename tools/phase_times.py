@@ -20,7 +20,11 @@ import bench  # noqa: E402
 import __graft_entry__ as graft  # noqa: E402
 
 KERNELS = ["continuity", "scalar", "momentum", "mdot", "peclet", "grad_scalar",
-           "grad_vector", "-"]
+           "grad_vector", "-",
+           "continuity/stream", "scalar/stream", "momentum/stream", "mdot/stream",
+           "peclet/stream", "grad_scalar/stream", "grad_vector/stream", "-"]
+STREAM = ["loop", "cp.async wait", "tma wait", "top barrier", "issue next",
+          "zero+phase 1", "p1 barrier", "phase 2", "p2 barrier", "phase 3"]
 LS = ["hdr+init", "tma issue", "halo gather", "stage wait", "phase 1",
       "p1 barrier", "phase 2+3"]
 EDGE = ["hdr+init", "tma issue", "halo gather", "stage wait", "compute"]
@@ -63,24 +67,24 @@ def main():
         mesh.nodal_grad_edge("velocity", "dudx_new")
 
     L = P.lib()
-    buf = (C.c_ulonglong * (8 * 12))()
+    buf = (C.c_ulonglong * (16 * 12))()
     for _ in range(3):
         sweep()
     ctx.sync()
-    L.nw_debug_phase_times(buf, 96, 1)
+    L.nw_debug_phase_times(buf, 192, 1)
     for _ in range(a.reps):
         sweep()
     ctx.sync()
-    L.nw_debug_phase_times(buf, 96, 1)
+    L.nw_debug_phase_times(buf, 192, 1)
     print("stats", mesh.stats())
-    for k in range(7):
+    for k in range(15):
         row = [buf[k * 12 + s] for s in range(12)]
         n = row[11]
         if not n:
             continue
-        names = LS if k < 3 else EDGE
+        names = STREAM if k >= 8 else (LS if k < 3 else EDGE)
         tot = sum(row[:len(names)])
-        print("%-12s CTAs/launch %d, total %.0f cycles per CTA (thread 0)" %
+        print("%-18s tiles/launch %d, total %.0f cycles per tile (one observer thread)" %
               (KERNELS[k], n // a.reps, tot / n))
         for nm, v in zip(names, row):
             print("    %-12s %9.0f cycles  %5.1f%%" % (nm, v / n, 100.0 * v / tot))
