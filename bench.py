@@ -39,7 +39,10 @@ CONT_OPTS = dict(dt=DT, gamma1=GAMMA1, noc_fac=1.0, interp_together=1.0,
                  solve_incompressible=0.0)
 
 # ALGORITHMIC bytes per edge on a hex mesh (r = 1/3, z = 7)
-ALG_BYTES = {"peclet": 69.3333, "momentum_uvw": 122.6667, "continuity": 85.3333,
+# momentum_uvw_fused: the Peclet factor is computed in the kernel, so its 8 B /
+# edge read (and the whole K9 pass) drop out of the algorithmic traffic
+ALG_BYTES = {"peclet": 69.3333, "momentum_uvw": 122.6667,
+             "momentum_uvw_fused": 114.6667, "continuity": 85.3333,
              "mdot": 72.0, "grad_scalar": 45.3333, "grad_vector": 66.6667,
              "scalar": 93.3333}
 STATE_FIELDS = [("velocity", 3), ("pressure", 1), ("density", 1),
@@ -59,9 +62,15 @@ def parse():
     ap.add_argument("--sst", action="store_true",
                     help="add the k and omega scalar assemblies + gradients")
     ap.add_argument("--mode", default="segmented", choices=["segmented", "atomic"])
-    ap.add_argument("--fuse-peclet", action="store_true",
+    ap.add_argument("--fuse-peclet", dest="fuse_peclet", action="store_true",
+                    default=True,
                     help="fold MomentumEdgePecletAlg into the momentum kernel "
-                         "(SURVEY 8f-1) instead of launching it separately")
+                         "(SURVEY 8f-1; default: r01d measured +6%% sweep throughput)")
+    ap.add_argument("--no-fuse-peclet", dest="fuse_peclet", action="store_false",
+                    help="launch MomentumEdgePecletAlg as its own kernel")
+    ap.add_argument("--serial-upload", action="store_true",
+                    help="e2e leg: nw_field_upload on the compute stream instead "
+                         "of the pipelined nw_field_stage / nw_field_commit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--detail", action="store_true",
                     help="also print per-kernel timings (stderr)")
@@ -410,26 +419,33 @@ def main():
     # dominant kernel: momentum UVW assembly, timed live inside the region
     mom_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events["momentum_uvw"]]))
     peak, peak_src = measured_peak()
-    ach = ALG_BYTES["momentum_uvw"] * edges_local / (mom_ms * 1e-3) / 1e9
-    sweep_bytes = sum(ALG_BYTES[k] for k in (
+    mom_key = "momentum_uvw_fused" if args.fuse_peclet else "momentum_uvw"
+    ALG_BYTES_RUN = dict(ALG_BYTES, momentum_uvw=ALG_BYTES[mom_key])
+    ach = ALG_BYTES_RUN["momentum_uvw"] * edges_local / (mom_ms * 1e-3) / 1e9
+    sweep_bytes = sum(ALG_BYTES_RUN[k] for k in (
         "momentum_uvw", "continuity", "mdot", "grad_scalar", "grad_vector"))
     if not args.fuse_peclet:
         sweep_bytes += ALG_BYTES["peclet"]
     if args.sst:
         sweep_bytes += 2 * (ALG_BYTES["scalar"] + ALG_BYTES["grad_scalar"])
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel
+    # from the committed `ncu --set full` capture (same mesh: 128^3 per GPU,
+    # default tile); null for any other configuration
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic_momentum_uvw.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and args.n == 128 and not args.tile:
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get(mom_key, {}).get(
+                "dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "ls_tile_kernel<MomentumUvwP<3>> "
-                "(momentum UVW edge assembly incl. row init)",
+                "(momentum UVW edge assembly incl. row init%s)" % (
+                    ", Peclet factor fused" if args.fuse_peclet else ""),
                 "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src,
-                "algorithmic_bytes_per_edge": ALG_BYTES["momentum_uvw"],
+                "algorithmic_bytes_per_edge": ALG_BYTES_RUN["momentum_uvw"],
                 "kernel_ms": mom_ms,
                 "sweep_achieved_gbs": sweep_bytes * edges_local /
                 (ms_max * 1e-3 / args.steps) / 1e9,
@@ -440,7 +456,7 @@ def main():
         for k, v in kernel_events.items():
             tms = float(np.mean([a.elapsed_time(b) for a, b in v]))
             calls = len(v) / args.steps
-            gbs = ALG_BYTES[k] * edges_local / (tms * 1e-3) / 1e9
+            gbs = ALG_BYTES_RUN[k] * edges_local / (tms * 1e-3) / 1e9
             print("  %-14s %8.3f ms x%.0f  %8.1f GB/s algorithmic  %5.1f%% of peak"
                   % (k, tms, calls, gbs, 100 * gbs / peak), file=sys.stderr)
 
@@ -452,13 +468,27 @@ def main():
     h2d = sum(tns.numel() * 8 for _, tns in pinned.values())
     d2h = 8 * (3 + 1)
 
-    def e2e_step():
+    def stage_all():
         for fid, tns in pinned.values():
-            mesh.upload_ptr(fid, tns.data_ptr())
+            mesh.stage_ptr(fid, tns.data_ptr())
+
+    def e2e_step():
+        """every step copies its nodal state host -> device and reads its
+        residual norms back.  Pipelined form (default): the state of step i+1
+        is staged on the copy stream while step i computes."""
+        if args.serial_upload:
+            for fid, tns in pinned.values():
+                mesh.upload_ptr(fid, tns.data_ptr())
+        else:
+            for fid, _ in pinned.values():
+                mesh.commit(fid)
+            stage_all()
         sweep()
         n_m = systems["momentum"].rhs_norm2()
         n_c = systems["continuity"].rhs_norm2()
         return n_m, n_c
+    if not args.serial_upload:
+        stage_all()
     for _ in range(3):
         e2e_step()
     barrier()
@@ -467,6 +497,9 @@ def main():
     for _ in range(args.steps):
         norms = e2e_step()
     e1.record(stream)
+    if not args.serial_upload:
+        for fid, _ in pinned.values():  # drain the look-ahead copy
+            mesh.commit(fid)
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -490,8 +523,12 @@ def main():
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "what": "per step: H2D of the nodal state (velocity, pressure, "
                         "density, viscosity, momentum_diag) from pinned host "
-                        "memory through nw_field_upload, the sweep, D2H of the "
-                        "rhs norms of both systems (nw_linsys_rhs_norm2)"},
+                        "memory (%s), the sweep, D2H of the rhs norms of both "
+                        "systems (nw_linsys_rhs_norm2)" % (
+                            "nw_field_upload on the compute stream"
+                            if args.serial_upload else
+                            "nw_field_stage on the copy stream one step ahead + "
+                            "nw_field_commit")},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
         "mesh_stats": mesh.stats() if rank == 0 else None,

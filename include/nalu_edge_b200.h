@@ -138,6 +138,19 @@ int nw_field_find(const nw_mesh* mesh, const char* name, int* field_id);
 int nw_field_upload(nw_mesh* mesh, int field_id, const double* host);
 /* device -> host, reference layout; synchronises the stream */
 int nw_field_download(nw_mesh* mesh, int field_id, double* host);
+/* Pipelined form of nw_field_upload for a caller that feeds new nodal state
+ * every step from pinned host memory (the ngp_field sync_to_device of the
+ * reference, include/ngp_utils/NgpFieldManager.h, stk::mesh::NgpField::
+ * sync_to_device): nw_field_stage enqueues the host -> device copy on the
+ * context's copy stream into a staging buffer owned by the field and returns
+ * at once, so the copy overlaps whatever the compute stream is doing;
+ * nw_field_commit makes the compute stream wait for that copy and permutes the
+ * staged data into the field (internal SoA layout).  A second nw_field_stage
+ * on the same field waits (on the copy stream) until the previous commit has
+ * consumed the staging buffer.  `host` must stay valid until the matching
+ * commit has been issued and must be pinned for the copy to be asynchronous. */
+int nw_field_stage(nw_mesh* mesh, int field_id, const double* host);
+int nw_field_commit(nw_mesh* mesh, int field_id);
 /* fill every component with a constant (stk::mesh::field_fill) */
 int nw_field_fill(nw_mesh* mesh, int field_id, double value);
 /* Device view of the internal storage: component c of internal entity i is at

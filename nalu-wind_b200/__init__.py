@@ -100,7 +100,7 @@ ABI_SYMBOLS = [
     "nw_ctx_sync", "nw_ctx_stream", "nw_comm_unique_id", "nw_ctx_comm_init",
     "nw_mesh_create", "nw_mesh_destroy", "nw_mesh_get_stats",
     "nw_field_register", "nw_field_find", "nw_field_upload",
-    "nw_field_download", "nw_field_fill", "nw_field_device_view",
+    "nw_field_stage", "nw_field_commit", "nw_field_download", "nw_field_fill", "nw_field_device_view",
     "nw_mesh_get_node_permutation", "nw_mdot_edge", "nw_peclet_edge",
     "nw_nodal_grad_edge", "nw_linsys_create", "nw_linsys_destroy",
     "nw_linsys_set_skipped_rows", "nw_linsys_build_edge_to_node_graph",
@@ -153,6 +153,8 @@ def lib():
     L.nw_field_find.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int)]
     L.nw_field_upload.argtypes = [vp, C.c_int, vp]
     L.nw_field_download.argtypes = [vp, C.c_int, vp]
+    L.nw_field_stage.argtypes = [vp, C.c_int, vp]
+    L.nw_field_commit.argtypes = [vp, C.c_int]
     L.nw_field_fill.argtypes = [vp, C.c_int, C.c_double]
     L.nw_field_device_view.argtypes = [vp, C.c_int, C.POINTER(vp),
                                        C.POINTER(C.c_int64)]
@@ -310,6 +312,15 @@ class Mesh:
     def upload_ptr(self, fid, ptr):
         """raw pointer variant (pinned host memory, asynchronous)"""
         _chk(lib().nw_field_upload(self.h, fid, C.c_void_p(ptr)))
+
+    def stage_ptr(self, fid, ptr):
+        """H2D on the copy stream into the field's staging buffer (pinned
+        host memory); overlaps the compute stream until commit()"""
+        _chk(lib().nw_field_stage(self.h, fid, C.c_void_p(ptr)))
+
+    def commit(self, fid):
+        """compute stream waits for the staged copy and permutes it in"""
+        _chk(lib().nw_field_commit(self.h, fid))
 
     def put(self, name, rank, host):
         """register (shape from the array) + upload"""

@@ -142,6 +142,8 @@ nw_ctx_destroy(nw_ctx* ctx)
   comm_destroy(ctx->comm);
   if (ctx->stream)
     cudaStreamDestroy(ctx->stream);
+  if (ctx->copyStream)
+    cudaStreamDestroy(ctx->copyStream);
   delete ctx;
   return NW_OK;
 }
@@ -408,6 +410,61 @@ nw_field_upload(nw_mesh* mesh, int field_id, const double* host)
     NW_CUDA(launch_edge_gather(
       mesh->scratch.as<double>(), f->ncomp, mesh->dTileEdgeSrc.as<int32_t>(),
       f->stride, f->buf.as<double>(), s));
+  return NW_OK;
+}
+
+extern "C" int
+nw_field_stage(nw_mesh* mesh, int field_id, const double* host)
+{
+  nw_field_t* f = get_field(mesh, field_id);
+  if (!f || !host)
+    return fail(NW_ERR_ARG, "nw_field_stage: bad field id or NULL buffer");
+  if (int rc = need_device(mesh->ctx, "nw_field_stage"))
+    return rc;
+  nw_ctx* ctx = mesh->ctx;
+  if (!ctx->copyStream)
+    NW_CUDA(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+  const int64_t nEnt = f->rank == NW_NODE ? mesh->plan.nNodes : mesh->plan.nEdges;
+  const size_t bytes = sizeof(double) * nEnt * f->ncomp;
+  if (f->staging.bytes < bytes) {
+    if (f->stagePending)
+      return fail(NW_ERR_STATE, "nw_field_stage: previous stage not committed");
+    NW_CUDA(f->staging.alloc(bytes));
+  }
+  if (!f->staged) {
+    NW_CUDA(cudaEventCreateWithFlags(&f->staged, cudaEventDisableTiming));
+    NW_CUDA(cudaEventCreateWithFlags(&f->consumed, cudaEventDisableTiming));
+  } else {
+    /* the previous commit's permute kernel must have read the buffer */
+    NW_CUDA(cudaStreamWaitEvent(ctx->copyStream, f->consumed, 0));
+  }
+  NW_CUDA(cudaMemcpyAsync(
+    f->staging.p, host, bytes, cudaMemcpyHostToDevice, ctx->copyStream));
+  NW_CUDA(cudaEventRecord(f->staged, ctx->copyStream));
+  f->stagePending = true;
+  return NW_OK;
+}
+
+extern "C" int
+nw_field_commit(nw_mesh* mesh, int field_id)
+{
+  nw_field_t* f = get_field(mesh, field_id);
+  if (!f)
+    return fail(NW_ERR_ARG, "nw_field_commit: bad field id");
+  if (!f->stagePending)
+    return fail(NW_ERR_STATE, "nw_field_commit: nothing staged for this field");
+  cudaStream_t s = mesh->ctx->stream;
+  NW_CUDA(cudaStreamWaitEvent(s, f->staged, 0));
+  if (f->rank == NW_NODE)
+    NW_CUDA(launch_node_gather(
+      f->staging.as<double>(), f->ncomp, mesh->dNodeOfSlot.as<int32_t>(),
+      f->stride, f->buf.as<double>(), s));
+  else
+    NW_CUDA(launch_edge_gather(
+      f->staging.as<double>(), f->ncomp, mesh->dTileEdgeSrc.as<int32_t>(),
+      f->stride, f->buf.as<double>(), s));
+  NW_CUDA(cudaEventRecord(f->consumed, s));
+  f->stagePending = false;
   return NW_OK;
 }
 

@@ -81,6 +81,7 @@ struct nw_ctx
 {
   int device = -1; /* < 0: host-only context (plan building, no compute) */
   cudaStream_t stream = nullptr;
+  cudaStream_t copyStream = nullptr; /* nw_field_stage: H2D beside the compute */
   nw::Comm comm;
 };
 
@@ -91,6 +92,18 @@ struct nw_field_t
   int ncomp = 1;
   int64_t stride = 0; /* entities incl. padding */
   nw::DevBuf buf;
+  /* nw_field_stage / nw_field_commit */
+  nw::DevBuf staging;
+  cudaEvent_t staged = nullptr;   /* copy stream: staging holds the new data */
+  cudaEvent_t consumed = nullptr; /* compute stream: staging may be reused */
+  bool stagePending = false;
+  ~nw_field_t()
+  {
+    if (staged)
+      cudaEventDestroy(staged);
+    if (consumed)
+      cudaEventDestroy(consumed);
+  }
 };
 
 /* neighbour exchange lists of one mesh (nodal fields) */

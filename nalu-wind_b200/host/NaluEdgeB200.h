@@ -113,6 +113,15 @@ public:
   {
     nw_check(nw_field_upload(mesh_, field_ordinal(name), host));
   }
+  /* pipelined upload: copy on the copy stream now, permute in at commit */
+  void stage(const std::string& name, const double* pinnedHost)
+  {
+    nw_check(nw_field_stage(mesh_, field_ordinal(name), pinnedHost));
+  }
+  void commit(const std::string& name)
+  {
+    nw_check(nw_field_commit(mesh_, field_ordinal(name)));
+  }
   void download(const std::string& name, double* host)
   {
     nw_check(nw_field_download(mesh_, field_ordinal(name), host));

@@ -41,17 +41,56 @@ def scaled_err(got, ref, scale):
     return float(np.max(np.abs(got - ref) / (TOL * s)))
 
 
+def add_tet_split_edges(b, seed=20261017):
+    """Turn the hex box's edge graph into that of its 6-tet (Kuhn) split: every
+    cell gains its three face diagonals towards (+,+,0), (+,0,+), (0,+,+) and
+    the body diagonal (+,+,+) -- the connectivity of the reference's tet /
+    mixed-element meshes (BASELINE configs[4]; up to 14 neighbours per node,
+    ragged rows, edges that are not grid-aligned).  Single rank, non-periodic.
+    The new edges get synthetic area vectors (mostly along the edge, plus a
+    seeded transverse part), which is all the edge kernels see of geometry."""
+    assert b.nranks == 1 and not any(b.periodic)
+    nx, ny, nz = b.dims
+    # lattice index of every node from its global id (1 + i + (nx+1) j + ...)
+    g0 = b.gid - 1
+    i, j, k = g0 % (nx + 1), (g0 // (nx + 1)) % (ny + 1), g0 // ((nx + 1) * (ny + 1))
+    node_at = -np.ones((nx + 1, ny + 1, nz + 1), dtype=np.int64)
+    node_at[i, j, k] = np.arange(b.n_nodes)
+    assert node_at.min() >= 0
+    extra = []
+    for di, dj, dk in ((1, 1, 0), (1, 0, 1), (0, 1, 1), (1, 1, 1)):
+        a = node_at[:nx + 1 - di, :ny + 1 - dj, :nz + 1 - dk].ravel()
+        c = node_at[di:, dj:, dk:].ravel()
+        extra.append(np.stack([a, c], axis=1))
+    extra = np.concatenate(extra)
+    # reference orientation: L = lower global id (STK edge creation)
+    swap = b.gid[extra[:, 0]] > b.gid[extra[:, 1]]
+    extra[swap] = extra[swap][:, ::-1]
+    rng = np.random.default_rng(seed)
+    dx = b.coords[extra[:, 1]] - b.coords[extra[:, 0]]
+    ln = np.linalg.norm(dx, axis=1, keepdims=True)
+    area = 0.35 * dx / ln * ln + 0.05 * ln * rng.standard_normal(dx.shape)
+    order = rng.permutation(len(extra))  # irregular edge ordering
+    b.edges = np.ascontiguousarray(
+        np.concatenate([b.edges, extra[order].astype(np.int32)]))
+    b.area = np.ascontiguousarray(np.concatenate([b.area, area[order]]))
+    b.n_edges = len(b.edges)
+
+
 class Case:
     """generated hex box + synthetic state (one rank)"""
 
     def __init__(self, dims=(12, 10, 8), lengths=None, periodic=(False, False),
-                 warp=0.0, zstretch=1.0, nranks=1, rank=0, shuffle_bucket=0):
+                 warp=0.0, zstretch=1.0, nranks=1, rank=0, shuffle_bucket=0,
+                 tet_split=False):
         P = pkg()
         synth = __import__("nalu_wind_b200.synth", fromlist=["state"])
         self.box = P.BoxMesh(*dims, lengths=lengths, periodic=periodic,
                              warp=warp, zstretch=zstretch, nranks=nranks,
                              rank=rank, shuffle_bucket=shuffle_bucket)
         b = self.box
+        if tet_split:
+            add_tet_split_edges(b)
         L = lengths if lengths else tuple(float(d) for d in dims)
         self.lengths = L
         pg = None

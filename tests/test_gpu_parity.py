@@ -199,6 +199,9 @@ SWEEP_CASES = [
     dict(dims=(14, 11, 40), tile_nodes=256, zstretch=1.15),
     dict(dims=(1, 1, 1), tile_nodes=8),
     dict(dims=(2, 1, 1), tile_nodes=1024),
+    # tet-split connectivity (mixed-element style: ragged rows, 14 neighbours)
+    dict(dims=(9, 8, 7), tile_nodes=96, tet_split=True),
+    dict(dims=(9, 8, 7), tile_nodes=96, tet_split=True, mode=1),
 ]
 
 
@@ -265,6 +268,25 @@ def test_skipped_rows_and_accumulation(P, ctx):
         assert pu.scaled_err(vals2, 2 * ov, 2 * av) < 1
         assert pu.scaled_err(rhs2, 2 * orhs, 2 * arhs) < 1
         ls.close()
+
+
+def test_staged_upload_matches_upload(P, ctx):
+    """nw_field_stage (copy stream) + nw_field_commit leaves the same bits in
+    the field as nw_field_upload, also when re-staged back to back"""
+    import torch
+    case = pu.Case(dims=(7, 6, 5))
+    mesh = case.box.make_mesh(ctx, tile_nodes=48)
+    fid = mesh.register("velocity", P.NW_NODE, 3)
+    with pytest.raises(P.NwError):
+        mesh.commit(fid)  # nothing staged
+    for rep in range(3):
+        a = np.ascontiguousarray(case.fields["velocity"] * (1.0 + rep))
+        pinned = torch.from_numpy(a).pin_memory()
+        mesh.stage_ptr(fid, pinned.data_ptr())
+        mesh.commit(fid)
+        got = mesh.download("velocity")
+        assert np.array_equal(got.reshape(a.shape), a)
+    mesh.close()
 
 
 def test_no_silent_fallback(P, ctx):

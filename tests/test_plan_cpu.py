@@ -13,6 +13,7 @@ CASES = [
     dict(dims=(7, 6, 9), nranks=2, rank=0),
     dict(dims=(7, 6, 9), nranks=2, rank=1),
     dict(dims=(5, 4, 9), nranks=3, rank=1, periodic=(True, False)),
+    dict(dims=(6, 5, 4), tet_split=True),
 ]
 
 
