@@ -106,6 +106,14 @@ struct nw_field_t
   }
 };
 
+/* owner-side accumulation plan: distinct destinations, each with the buffer
+ * positions that add into it, in ascending (peer, entry) order */
+struct nw_accum_plan
+{
+  int64_t nDst = 0;
+  nw::DevBuf dDst, dPtr, dPos; /* int64 */
+};
+
 /* neighbour exchange lists of one mesh (nodal fields) */
 struct nw_node_halo
 {
@@ -117,6 +125,10 @@ struct nw_node_halo
   /* as the owner: my owned nodes other ranks hold copies of */
   std::vector<std::vector<int32_t>> ownedSlots; /* per peer */
   std::vector<nw::DevBuf> dGhostIdx, dOwnedIdx; /* int64 slot lists */
+  /* all peers concatenated (ascending peer): one launch per exchange phase */
+  nw::DevBuf dGhostAll, dOwnedAll;
+  std::vector<int64_t> ghostOff, ownedOff; /* per peer offsets, +1 total */
+  nw_accum_plan ownedAccum;
   nw::DevBuf sendBuf, recvBuf;
 };
 
@@ -179,6 +191,9 @@ struct nw_linsys
   std::vector<Peer> peers;
   bool haloBuilt = false;
   nw::DevBuf haloRecv;
+  /* receive layout: [all peers' values | rhs column 0 rows | column 1 ...] */
+  int64_t recvValTotal = 0, recvRowTotal = 0;
+  nw_accum_plan valAccum, rhsAccum;
   /* columns received for owned rows that the local graph does not have:
    * (row, col) pairs appended after the reference-layout arrays */
   int64_t nExtra = 0;

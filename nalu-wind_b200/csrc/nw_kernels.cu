@@ -1840,6 +1840,60 @@ scatter_assign_kernel(
     dst[idx[i]] = src[i];
 }
 
+/* halo exchange, all peers and all components in one launch.
+ * buffer element of concatenated entry g, component c:
+ *   buf[g * entStride + c * compStride] */
+__global__ void
+pack_multi_kernel(
+  const double* __restrict__ src, int64_t srcCompStride, int nc,
+  const int64_t* __restrict__ idx, int64_t n, double* __restrict__ buf,
+  int64_t entStride, int64_t compStride)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * nc)
+    return;
+  const int64_t g = t / nc;
+  const int c = (int)(t - g * nc);
+  buf[g * entStride + c * compStride] = src[(int64_t)c * srcCompStride + idx[g]];
+}
+
+__global__ void
+scatter_multi_kernel(
+  const double* __restrict__ buf, int64_t entStride, int64_t compStride, int nc,
+  const int64_t* __restrict__ idx, int64_t n, double* __restrict__ dst,
+  int64_t dstCompStride)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * nc)
+    return;
+  const int64_t g = t / nc;
+  const int c = (int)(t - g * nc);
+  if (idx[g] >= 0)
+    dst[(int64_t)c * dstCompStride + idx[g]] = buf[g * entStride + c * compStride];
+}
+
+/* owner-side sum: destination u receives the buffer entries pos[ptr[u] ..
+ * ptr[u+1]) in that (ascending peer) order -- race-free when several peers
+ * share one destination, and a fixed summation order */
+__global__ void
+accumulate_multi_kernel(
+  const double* __restrict__ buf, int64_t entStride, int64_t compStride, int nc,
+  const int64_t* __restrict__ dstIdx, const int64_t* __restrict__ ptr,
+  const int64_t* __restrict__ pos, int64_t nDst, double* dst,
+  int64_t dstCompStride)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nDst * nc)
+    return;
+  const int64_t u = t / nc;
+  const int c = (int)(t - u * nc);
+  double* d = dst + (int64_t)c * dstCompStride + dstIdx[u];
+  double v = *d;
+  for (int64_t q = ptr[u]; q < ptr[u + 1]; ++q)
+    v += buf[pos[q] * entStride + c * compStride];
+  *d = v;
+}
+
 template <class K>
 cudaError_t
 set_smem(K kernel, size_t bytes)
@@ -2428,6 +2482,44 @@ launch_scatter_assign(
   if (n == 0)
     return cudaSuccess;
   scatter_assign_kernel<<<blocks_for(n, 256), 256, 0, s>>>(src, idx, n, dst);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_pack_multi(
+  const double* src, int64_t srcCompStride, int nc, const int64_t* idx,
+  int64_t n, double* buf, int64_t entStride, int64_t compStride, cudaStream_t s)
+{
+  if (n == 0)
+    return cudaSuccess;
+  pack_multi_kernel<<<blocks_for(n * nc, 256), 256, 0, s>>>(
+    src, srcCompStride, nc, idx, n, buf, entStride, compStride);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_scatter_multi(
+  const double* buf, int64_t entStride, int64_t compStride, int nc,
+  const int64_t* idx, int64_t n, double* dst, int64_t dstCompStride,
+  cudaStream_t s)
+{
+  if (n == 0)
+    return cudaSuccess;
+  scatter_multi_kernel<<<blocks_for(n * nc, 256), 256, 0, s>>>(
+    buf, entStride, compStride, nc, idx, n, dst, dstCompStride);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_accumulate_multi(
+  const double* buf, int64_t entStride, int64_t compStride, int nc,
+  const int64_t* dstIdx, const int64_t* ptr, const int64_t* pos, int64_t nDst,
+  double* dst, int64_t dstCompStride, cudaStream_t s)
+{
+  if (nDst == 0)
+    return cudaSuccess;
+  accumulate_multi_kernel<<<blocks_for(nDst * nc, 256), 256, 0, s>>>(
+    buf, entStride, compStride, nc, dstIdx, ptr, pos, nDst, dst, dstCompStride);
   return cudaGetLastError();
 }
 

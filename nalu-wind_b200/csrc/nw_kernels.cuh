@@ -154,6 +154,21 @@ cudaError_t launch_pack(
 cudaError_t launch_scatter_assign(
   const double* src, const int64_t* idx, int64_t n, double* dst,
   cudaStream_t s);
+/* all peers + all components in one launch; buffer element of concatenated
+ * entry g, component c at buf[g * entStride + c * compStride] */
+cudaError_t launch_pack_multi(
+  const double* src, int64_t srcCompStride, int nc, const int64_t* idx,
+  int64_t n, double* buf, int64_t entStride, int64_t compStride,
+  cudaStream_t s);
+cudaError_t launch_scatter_multi(
+  const double* buf, int64_t entStride, int64_t compStride, int nc,
+  const int64_t* idx, int64_t n, double* dst, int64_t dstCompStride,
+  cudaStream_t s);
+/* dst[dstIdx[u]] += sum of buf entries pos[ptr[u] .. ptr[u+1]) in that order */
+cudaError_t launch_accumulate_multi(
+  const double* buf, int64_t entStride, int64_t compStride, int nc,
+  const int64_t* dstIdx, const int64_t* ptr, const int64_t* pos, int64_t nDst,
+  double* dst, int64_t dstCompStride, cudaStream_t s);
 cudaError_t launch_unpack_add(
   const double* src, const int64_t* idx, int64_t n, double* dst,
   cudaStream_t s);
