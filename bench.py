@@ -531,6 +531,8 @@ def main():
                             "nw_field_commit")},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
+        "halo_transport": {"nodal_sum": mesh.halo_transport(),
+                           "load_complete": systems["momentum"].halo_transport()},
         "mesh_stats": mesh.stats() if rank == 0 else None,
         "residual_norms": {"momentum": [float(x) for x in norms[0]],
                            "continuity": [float(x) for x in norms[1]]},

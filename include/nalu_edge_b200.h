@@ -76,6 +76,19 @@ void* nw_ctx_stream(nw_ctx* ctx);
 #define NW_UNIQUE_ID_BYTES 128
 int nw_comm_unique_id(void* unique_id_out);
 int nw_ctx_comm_init(nw_ctx* ctx, const void* unique_id, int nranks, int rank);
+/* Transport of the two halo exchanges (shared-row add of loadComplete,
+ * shared-node sum of the nodal gradient).  nw_ctx_comm_init also tries to set
+ * up a peer-memory mailbox over NVLink (CUDA IPC windows; NW_P2P=0 disables
+ * it): an exchange is then a push kernel (pack + remote stores + release flag)
+ * and a pull kernel (acquire wait + ordered add) instead of pack / ncclSend /
+ * ncclRecv / unpack.  All ranks use the same transport (agreed collectively);
+ * results are bit-identical between the two. */
+typedef enum {
+  NW_TRANSPORT_NONE = 0,       /* single rank / structure not built yet */
+  NW_TRANSPORT_NCCL = 1,
+  NW_TRANSPORT_PEER_MEMORY = 2
+} nw_halo_transport;
+int nw_ctx_peer_memory(const nw_ctx* ctx); /* 1 if the mailbox is up */
 
 /* ------------------------------------------------------------------ */
 /* mesh partition                                                      */
@@ -179,6 +192,8 @@ int nw_mesh_halo_commit(nw_mesh* mesh);
  * with the sum over all ranks' copies (owner adds in ascending rank order,
  * then owner -> sharers).  Single rank: no-op. */
 int nw_field_parallel_sum(nw_mesh* mesh, int field_id);
+/* transport the nodal halo sum of this mesh uses (nw_halo_transport) */
+int nw_mesh_halo_transport(const nw_mesh* mesh);
 
 /* ------------------------------------------------------------------ */
 /* edge algorithms without a linear system                             */
@@ -368,6 +383,8 @@ int nw_linsys_get_extra(
 /* LinearSystem::loadComplete (src/HypreLinearSystem.C:1848-1889): the
  * shared-row halo sum.  Single rank: no-op. */
 int nw_linsys_load_complete(nw_linsys* ls);
+/* transport nw_linsys_load_complete uses (nw_halo_transport) */
+int nw_linsys_halo_transport(const nw_linsys* ls);
 
 /* Device pointers in exactly the layout the reference hands to
  * HYPRE_IJMatrixSetValues2 / AddToValues2 and HYPRE_IJVectorSetValues

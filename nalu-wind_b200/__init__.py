@@ -98,6 +98,7 @@ class LinsysSizes(C.Structure):
 ABI_SYMBOLS = [
     "nw_last_error", "nw_version", "nw_debug_phase_times", "nw_ctx_create", "nw_ctx_destroy",
     "nw_ctx_sync", "nw_ctx_stream", "nw_comm_unique_id", "nw_ctx_comm_init",
+    "nw_ctx_peer_memory", "nw_mesh_halo_transport", "nw_linsys_halo_transport",
     "nw_mesh_create", "nw_mesh_destroy", "nw_mesh_get_stats",
     "nw_field_register", "nw_field_find", "nw_field_upload",
     "nw_field_stage", "nw_field_commit", "nw_field_download", "nw_field_fill", "nw_field_device_view",
@@ -145,6 +146,9 @@ def lib():
     L.nw_ctx_stream.argtypes = [vp]
     L.nw_comm_unique_id.argtypes = [vp]
     L.nw_ctx_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.nw_ctx_peer_memory.argtypes = [vp]
+    L.nw_mesh_halo_transport.argtypes = [vp]
+    L.nw_linsys_halo_transport.argtypes = [vp]
     L.nw_mesh_create.argtypes = [vp, C.POINTER(MeshDesc), C.POINTER(vp)]
     L.nw_mesh_destroy.argtypes = [vp]
     L.nw_mesh_get_stats.argtypes = [vp, C.POINTER(MeshStats)]
@@ -231,6 +235,10 @@ class Context:
     def comm_init(self, unique_id_bytes, nranks, rank):
         buf = C.create_string_buffer(bytes(unique_id_bytes), 128)
         _chk(lib().nw_ctx_comm_init(self.h, buf, nranks, rank))
+
+    def peer_memory(self):
+        """True if the NVLink peer-memory mailbox is up (else NCCL send/recv)"""
+        return bool(lib().nw_ctx_peer_memory(self.h))
 
     @staticmethod
     def comm_unique_id():
@@ -376,6 +384,9 @@ class Mesh:
     def parallel_sum(self, name):
         _chk(lib().nw_field_parallel_sum(self.h, self.field_id(name)))
 
+    def halo_transport(self):
+        return ["none", "nccl", "peer_memory"][lib().nw_mesh_halo_transport(self.h)]
+
     def close(self):
         if self.h:
             lib().nw_mesh_destroy(self.h)
@@ -469,6 +480,9 @@ class LinearSystem:
 
     def loadComplete(self):
         _chk(lib().nw_linsys_load_complete(self.h))
+
+    def halo_transport(self):
+        return ["none", "nccl", "peer_memory"][lib().nw_linsys_halo_transport(self.h)]
 
     # --- shared-row exchange structure (caller-side transport) ---
     def halo_send(self, peer):

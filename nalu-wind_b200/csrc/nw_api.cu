@@ -134,11 +134,15 @@ nw_ctx_create(int cuda_device, nw_ctx** out)
   return NW_OK;
 }
 
+static int p2p_init(nw_ctx* ctx);
+static void p2p_close(nw_ctx* ctx);
+
 extern "C" int
 nw_ctx_destroy(nw_ctx* ctx)
 {
   if (!ctx)
     return NW_OK;
+  p2p_close(ctx);
   comm_destroy(ctx->comm);
   if (ctx->stream)
     cudaStreamDestroy(ctx->stream);
@@ -154,6 +158,15 @@ nw_ctx_sync(nw_ctx* ctx)
   if (int rc = need_device(ctx, "nw_ctx_sync"))
     return rc;
   NW_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->p2p.ok) {
+    /* a pull kernel that gave up waiting for a peer leaves a mark */
+    unsigned w[2] = {0, 0};
+    NW_CUDA(cudaMemcpy(w, ctx->p2p.sync.p, sizeof(w), cudaMemcpyDeviceToHost));
+    if (w[1] != 0)
+      return fail(
+        NW_ERR_COMM, "nw_ctx_sync: a peer-memory halo exchange timed out "
+                     "waiting for a neighbour rank (results are incomplete)");
+  }
   return NW_OK;
 }
 
@@ -181,7 +194,8 @@ nw_ctx_comm_init(nw_ctx* ctx, const void* unique_id, int nranks, int rank)
   std::string err;
   if (!comm_init(ctx->comm, unique_id, nranks, rank, err))
     return fail(NW_ERR_COMM, "nw_ctx_comm_init: " + err);
-  return NW_OK;
+  /* peer-memory mailbox for the halo exchanges (falls back to NCCL) */
+  return p2p_init(ctx);
 }
 
 /* ------------------------------------------------------------------ */

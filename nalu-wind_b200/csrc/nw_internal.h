@@ -77,12 +77,33 @@ struct Comm
 
 } // namespace nw
 
+/* Peer-memory mailbox over NVLink (one process per GPU, CUDA IPC): every rank
+ * owns a double-buffered receive window and one flag word per peer; a halo
+ * exchange is then two kernels -- push (pack + remote stores into the peers'
+ * windows + release-store of the epoch into their flag words) and pull
+ * (acquire-wait on the own flag words + ordered accumulate) -- instead of
+ * pack / ncclSend+ncclRecv / unpack.  Set up once at nw_ctx_comm_init; any
+ * failure (IPC not permitted, window too small) leaves the NCCL path in use on
+ * ALL ranks (the decision is agreed with an all-reduce). */
+struct nw_p2p
+{
+  bool ok = false;
+  int64_t winDoubles = 0; /* doubles per parity half of the window */
+  nw::DevBuf window;      /* [2][winDoubles] */
+  nw::DevBuf flags;       /* unsigned long long [nranks]: epoch written by rank r */
+  nw::DevBuf sync;        /* [0] block counter, [1] timeout/error word */
+  std::vector<void*> mappedWindow, mappedFlags; /* per rank, opened IPC handles */
+  nw::DevBuf dPeerWindow, dPeerFlags; /* device arrays of those pointers */
+  unsigned long long epoch = 0;
+};
+
 struct nw_ctx
 {
   int device = -1; /* < 0: host-only context (plan building, no compute) */
   cudaStream_t stream = nullptr;
   cudaStream_t copyStream = nullptr; /* nw_field_stage: H2D beside the compute */
   nw::Comm comm;
+  nw_p2p p2p;
 };
 
 struct nw_field_t
@@ -130,6 +151,12 @@ struct nw_node_halo
   std::vector<int64_t> ghostOff, ownedOff; /* per peer offsets, +1 total */
   nw_accum_plan ownedAccum;
   nw::DevBuf sendBuf, recvBuf;
+  /* peer-memory path (every shared node has exactly two sharers): per peer
+   * send [ghosts owned by it | my owned nodes it ghosts], receive the mirror */
+  bool p2p = false;
+  int64_t nSendP2p = 0, nRecvP2p = 0;
+  nw::DevBuf dSendIdx, dSendDst, dRecvIdx; /* int64 */
+  nw::DevBuf dSendPeer, dPeerList;         /* int32 */
 };
 
 struct nw_mesh
@@ -194,6 +221,13 @@ struct nw_linsys
   /* receive layout: [all peers' values | rhs column 0 rows | column 1 ...] */
   int64_t recvValTotal = 0, recvRowTotal = 0;
   nw_accum_plan valAccum, rhsAccum;
+  /* peer-memory path: my tail segments -> the owners' windows */
+  bool p2p = false;
+  std::vector<int64_t> p2pPeerInfo; /* per peer: voff, roff, valTotal, rowTotal */
+  const double* p2pBuiltFor = nullptr; /* dev.values the segment table was built for */
+  int p2pNSeg = 0;
+  int64_t p2pTotal = 0;
+  nw::DevBuf dSegSrc, dSegStart, dSegDst, dSegPeer, dPeerList;
   /* columns received for owned rows that the local graph does not have:
    * (row, col) pairs appended after the reference-layout arrays */
   int64_t nExtra = 0;

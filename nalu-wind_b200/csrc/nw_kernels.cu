@@ -1894,6 +1894,136 @@ accumulate_multi_kernel(
   *d = v;
 }
 
+/* ---- peer-memory halo exchange (NVLink, CUDA IPC windows) ---- */
+
+__device__ __forceinline__ void
+st_release_sys(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long
+ld_acquire_sys(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+/* end of a push kernel: when the last block has made its remote stores
+ * visible, publish `epoch` in every peer's flag word for this rank */
+__device__ __forceinline__ void
+p2p_signal(const P2pDev& pp)
+{
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(pp.sync, 1u) + 1u;
+    if (done == gridDim.x) {
+      pp.sync[0] = 0u; /* next launch on this stream starts from zero */
+      __threadfence_system();
+      for (int i = 0; i < pp.nPeers; ++i)
+        st_release_sys(pp.peerFlags[pp.peers[i]] + pp.myRank, pp.epoch);
+    }
+  }
+}
+
+/* start of a pull kernel: every peer's push of this epoch has landed in the
+ * own window.  Bounded spin: a peer that never arrives sets the error word
+ * instead of hanging the GPU. */
+__device__ __forceinline__ void
+p2p_wait(const P2pDev& pp)
+{
+  if ((int)threadIdx.x < pp.nPeers) {
+    const unsigned long long* f = pp.myFlags + pp.peers[threadIdx.x];
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < pp.epoch) {
+      if (clock64() - t0 > 6000000000ll) { /* ~3 s */
+        atomicExch(pp.sync + 1, 1u);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+}
+
+/* nodal push: entry g of the concatenated send list, component c ->
+ * window of rank sendPeer[g] at entry sendDst[g] */
+__global__ void __launch_bounds__(256) p2p_push_nodal_kernel(
+  const double* __restrict__ base, int64_t stride, int nc,
+  const int64_t* __restrict__ sendIdx, const int32_t* __restrict__ sendPeer,
+  const int64_t* __restrict__ sendDst, int64_t n, const P2pDev pp)
+{
+  const int64_t total = n * nc;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = t / nc;
+    const int c = (int)(t - g * nc);
+    pp.peerWindow[sendPeer[g]][pp.winOff + sendDst[g] * nc + c] =
+      base[(int64_t)c * stride + sendIdx[g]];
+  }
+  p2p_signal(pp);
+}
+
+/* nodal pull: own partial + the other sharer's partial (two sharers per node:
+ * a + b on one side, b + a on the other -- the same bits) */
+__global__ void __launch_bounds__(256) p2p_pull_nodal_kernel(
+  double* base, int64_t stride, int nc, const int64_t* __restrict__ recvIdx,
+  int64_t n, const P2pDev pp)
+{
+  p2p_wait(pp);
+  const double* win = pp.myWindow + pp.winOff;
+  const int64_t total = n * nc;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = t / nc;
+    const int c = (int)(t - g * nc);
+    double* d = base + (int64_t)c * stride + recvIdx[g];
+    *d += __ldcg(win + t);
+  }
+}
+
+/* linear-system push: contiguous tail segments -> the owners' windows */
+__global__ void __launch_bounds__(256) p2p_push_segments_kernel(
+  const double* const* __restrict__ segSrc, const int64_t* __restrict__ segStart,
+  const int64_t* __restrict__ segDst, const int32_t* __restrict__ segPeer,
+  int nSeg, const P2pDev pp)
+{
+  const int64_t total = segStart[nSeg];
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int sg = 0;
+    while (sg + 1 < nSeg && segStart[sg + 1] <= t)
+      ++sg;
+    const int64_t k = t - segStart[sg];
+    pp.peerWindow[segPeer[sg]][pp.winOff + segDst[sg] + k] = segSrc[sg][k];
+  }
+  p2p_signal(pp);
+}
+
+/* linear-system pull: accumulate_multi out of the own window, after the wait */
+__global__ void __launch_bounds__(256) p2p_pull_accumulate_kernel(
+  int64_t bufOff, int64_t entStride, int64_t compStride, int nc,
+  const int64_t* __restrict__ dstIdx, const int64_t* __restrict__ ptr,
+  const int64_t* __restrict__ pos, int64_t nDst, double* dst,
+  int64_t dstCompStride, const P2pDev pp, int wait)
+{
+  if (wait)
+    p2p_wait(pp);
+  const double* buf = pp.myWindow + pp.winOff + bufOff;
+  const int64_t total = nDst * nc;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t u = t / nc;
+    const int c = (int)(t - u * nc);
+    double* d = dst + (int64_t)c * dstCompStride + dstIdx[u];
+    double v = *d;
+    for (int64_t q = ptr[u]; q < ptr[u + 1]; ++q)
+      v += __ldcg(buf + pos[q] * entStride + c * compStride);
+    *d = v;
+  }
+}
+
 template <class K>
 cudaError_t
 set_smem(K kernel, size_t bytes)
@@ -2520,6 +2650,61 @@ launch_accumulate_multi(
     return cudaSuccess;
   accumulate_multi_kernel<<<blocks_for(nDst * nc, 256), 256, 0, s>>>(
     buf, entStride, compStride, nc, dstIdx, ptr, pos, nDst, dst, dstCompStride);
+  return cudaGetLastError();
+}
+
+namespace {
+inline int
+p2p_grid(int64_t elems)
+{
+  const int64_t b = (elems + 255) / 256;
+  const int64_t cap = 2 * (int64_t)sm_count();
+  return (int)std::max<int64_t>(1, std::min(b, cap));
+}
+} // namespace
+
+cudaError_t
+launch_p2p_push_nodal(
+  const double* base, int64_t stride, int nc, const int64_t* sendIdx,
+  const int32_t* sendPeer, const int64_t* sendDst, int64_t n, const P2pDev& pp,
+  cudaStream_t s)
+{
+  p2p_push_nodal_kernel<<<p2p_grid(n * nc), 256, 0, s>>>(
+    base, stride, nc, sendIdx, sendPeer, sendDst, n, pp);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_p2p_pull_nodal(
+  double* base, int64_t stride, int nc, const int64_t* recvIdx, int64_t n,
+  const P2pDev& pp, cudaStream_t s)
+{
+  p2p_pull_nodal_kernel<<<p2p_grid(n * nc), 256, 0, s>>>(
+    base, stride, nc, recvIdx, n, pp);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_p2p_push_segments(
+  const double* const* segSrc, const int64_t* segStart, const int64_t* segDst,
+  const int32_t* segPeer, int nSeg, int64_t total, const P2pDev& pp,
+  cudaStream_t s)
+{
+  p2p_push_segments_kernel<<<p2p_grid(total), 256, 0, s>>>(
+    segSrc, segStart, segDst, segPeer, nSeg, pp);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_p2p_pull_accumulate(
+  int64_t bufOff, int64_t entStride, int64_t compStride, int nc,
+  const int64_t* dstIdx, const int64_t* ptr, const int64_t* pos, int64_t nDst,
+  double* dst, int64_t dstCompStride, const P2pDev& pp, bool wait,
+  cudaStream_t s)
+{
+  p2p_pull_accumulate_kernel<<<p2p_grid(nDst * nc), 256, 0, s>>>(
+    bufOff, entStride, compStride, nc, dstIdx, ptr, pos, nDst, dst,
+    dstCompStride, pp, wait ? 1 : 0);
   return cudaGetLastError();
 }
 

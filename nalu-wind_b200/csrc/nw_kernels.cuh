@@ -154,6 +154,37 @@ cudaError_t launch_pack(
 cudaError_t launch_scatter_assign(
   const double* src, const int64_t* idx, int64_t n, double* dst,
   cudaStream_t s);
+/* peer-memory mailbox as the kernels see it (nw_p2p in nw_internal.h) */
+struct P2pDev
+{
+  double* const* peerWindow = nullptr;            /* [nranks] window base of rank r */
+  unsigned long long* const* peerFlags = nullptr; /* [nranks] flag array of rank r */
+  double* myWindow = nullptr;
+  const unsigned long long* myFlags = nullptr;
+  unsigned* sync = nullptr; /* [0] block counter, [1] error word */
+  const int32_t* peers = nullptr; /* ranks taking part in this exchange */
+  int nPeers = 0;
+  int myRank = 0;
+  int64_t winOff = 0; /* parity * winDoubles */
+  unsigned long long epoch = 0;
+};
+cudaError_t launch_p2p_push_nodal(
+  const double* base, int64_t stride, int nc, const int64_t* sendIdx,
+  const int32_t* sendPeer, const int64_t* sendDst, int64_t n, const P2pDev& pp,
+  cudaStream_t s);
+cudaError_t launch_p2p_pull_nodal(
+  double* base, int64_t stride, int nc, const int64_t* recvIdx, int64_t n,
+  const P2pDev& pp, cudaStream_t s);
+cudaError_t launch_p2p_push_segments(
+  const double* const* segSrc, const int64_t* segStart, const int64_t* segDst,
+  const int32_t* segPeer, int nSeg, int64_t total, const P2pDev& pp,
+  cudaStream_t s);
+cudaError_t launch_p2p_pull_accumulate(
+  int64_t bufOff, int64_t entStride, int64_t compStride, int nc,
+  const int64_t* dstIdx, const int64_t* ptr, const int64_t* pos, int64_t nDst,
+  double* dst, int64_t dstCompStride, const P2pDev& pp, bool wait,
+  cudaStream_t s);
+
 /* all peers + all components in one launch; buffer element of concatenated
  * entry g, component c at buf[g * entStride + c * compStride] */
 cudaError_t launch_pack_multi(

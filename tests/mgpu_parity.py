@@ -166,6 +166,8 @@ def main():
     if rank == 0:
         worst = max(max(r.values()) for r in allres)
         print(json.dumps({"world": world, "dims": dims, "periodic": periodic,
+                          "peer_memory": ctx.peer_memory(),
+                          "nodal_transport": mesh.halo_transport(),
                           "worst_scaled_error": worst, "per_rank": allres}))
         assert worst < 1.0, allres
     mesh.close()
