@@ -577,8 +577,8 @@ struct LsSmem
   }
 };
 
-template <class P, int ND, int MINB = P::kMinBlocks>
-__global__ void __launch_bounds__(kTileThreads, MINB) ls_tile_kernel(
+template <class P, int ND, int MINB = P::kMinBlocks, int THREADS = kTileThreads>
+__global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
   const MeshPlanDev mp,
   const LsPlanDev lp,
   const NodeComps nc,
@@ -2114,6 +2114,16 @@ launch_ls_tile(
       return e;
     ls_tile_kernel<P, ND, 3>
       <<<mp.nTiles, kTileThreads, bytes, s>>>(mp, lp, nc, ec, o);
+    return cudaGetLastError();
+  }
+  /* diagnostic: NW_TILE_THREADS=384 runs 12-warp CTAs (2 per SM, <= 85
+   * registers) instead of 8-warp ones */
+  static const int thrEnv = env_int("NW_TILE_THREADS", 0);
+  if (thrEnv == 384 && 2 * (bytes + 1024) <= 228 * 1024) {
+    e = set_smem(ls_tile_kernel<P, ND, 2, 384>, bytes);
+    if (e != cudaSuccess)
+      return e;
+    ls_tile_kernel<P, ND, 2, 384><<<mp.nTiles, 384, bytes, s>>>(mp, lp, nc, ec, o);
     return cudaGetLastError();
   }
   e = set_smem(ls_tile_kernel<P, ND>, bytes);

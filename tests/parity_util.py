@@ -390,3 +390,151 @@ def run_lowmach_case(P, ctx, dims=(12, 10, 8), tile_nodes=64, mode=None,
     ls.close()
     mesh.close()
     return res
+
+
+# ---------------------------------------------------------------------------
+# 2-D quad O-grid (airfoilRANSEdge-style: the reference's airfoil mesh is a 2-D
+# QUAD4 mesh, ndim = 2; all kernels loop d < ndim)
+# ---------------------------------------------------------------------------
+
+class OGrid2D:
+    """curvilinear O-grid of ntheta x nr quads around an ellipse, wall-normal
+    stretching 1.15, edges shuffled within buckets (irregular ordering)"""
+
+    def __init__(self, ntheta=48, nr=20, stretch=1.15, bucket=64, seed=20261017):
+        pkg()
+        synth = __import__("nalu_wind_b200.synth", fromlist=["state"])
+        rng = np.random.default_rng(seed)
+        i, j = np.meshgrid(np.arange(ntheta), np.arange(nr), indexing="xy")
+        i, j = i.ravel(), j.ravel()
+        th = 2.0 * np.pi * i / ntheta
+        dr0 = 0.01
+        r = 0.5 + dr0 * (stretch ** j - 1.0) / (stretch - 1.0)
+        self.coords = np.stack([1.3 * r * np.cos(th) + 0.02 * np.sin(3 * th),
+                                0.8 * r * np.sin(th)], axis=1)
+        n = ntheta * nr
+        self.n_nodes = n
+        self.gid = np.arange(1, n + 1, dtype=np.int64)
+        self.hid = np.arange(n, dtype=np.int64)
+        node = lambda a, b: (a % ntheta) + ntheta * b
+        ring = np.stack([node(i, j), node(i + 1, j)], axis=1)
+        m = j < nr - 1
+        rad = np.stack([node(i[m], j[m]), node(i[m], j[m] + 1)], axis=1)
+        edges = np.concatenate([ring, rad])
+        swap = edges[:, 0] > edges[:, 1]  # L = lower global id
+        edges[swap] = edges[swap][:, ::-1]
+        # shuffle within buckets
+        order = np.arange(len(edges))
+        for a in range(0, len(edges), bucket):
+            rng.shuffle(order[a:a + bucket])
+        edges = edges[order]
+        self.edges = np.ascontiguousarray(edges.astype(np.int32))
+        self.n_edges = len(edges)
+        dx = self.coords[edges[:, 1]] - self.coords[edges[:, 0]]
+        ln = np.linalg.norm(dx, axis=1, keepdims=True)
+        rr = np.linalg.norm(0.5 * (self.coords[edges[:, 1]] + self.coords[edges[:, 0]]),
+                            axis=1, keepdims=True)
+        width = np.where(ln > 0.5 * 2 * np.pi * rr / ntheta, dr0 * 4, 2 * np.pi * rr / ntheta)
+        t = np.stack([-dx[:, 1], dx[:, 0]], axis=1) / ln
+        self.area = np.ascontiguousarray(dx / ln * width + 0.1 * width * t *
+                                         rng.standard_normal((len(edges), 1)))
+        self.vol = (r * (2 * np.pi / ntheta) * dr0 * stretch ** j).astype(np.float64)
+        c3 = np.concatenate([self.coords, np.zeros((n, 1))], axis=1)
+        f3 = synth.state(c3 + 2.0, self.gid, (4.0, 4.0, 1.0), DT, GAMMA1)
+        f = {}
+        for k, v in f3.items():
+            if v.ndim == 2 and v.shape[1] == 3:
+                f[k] = np.ascontiguousarray(v[:, :2])
+            elif v.ndim == 2 and v.shape[1] == 9:
+                f[k] = np.ascontiguousarray(v[:, [0, 1, 3, 4]])
+            else:
+                f[k] = v
+        f["dual_nodal_volume"] = self.vol
+        self.fields = f
+
+
+def run_quad2d_case(P, ctx, tile_nodes=64, mode=None, **kw):
+    """the edge sweep on the 2-D quad O-grid, product vs oracle (ndim = 2)"""
+    c = OGrid2D(**kw)
+    f = c.fields
+    mesh = P.Mesh(ctx, 2, c.edges, c.hid, c.coords, tile_nodes=tile_nodes)
+    for name, arr in f.items():
+        mesh.put(name, P.NW_NODE, arr)
+    mesh.put("edge_area_vector", P.NW_EDGE, c.area)
+    mesh.register("mass_flow_rate", P.NW_EDGE, 1)
+    mesh.register("peclet_factor", P.NW_EDGE, 1)
+    res = {}
+    pf, opf = P.peclet_fn("classic", 1.0), orc.peclet("classic", 1.0)
+    mesh.mdot_edge(1.0, 1.0)
+    mdot = mesh.download("mass_flow_rate")
+    omdot = orc.mdot_edge(2, c.edges, c.coords, f["velocity"], f["dpdx"],
+                          f["density"], f["pressure"], f["momentum_diag"],
+                          c.area, 1.0, 1.0)
+    res["mdot"] = scaled_err(mdot, omdot, np.abs(omdot) + 1e-3 * np.max(np.abs(omdot)))
+    mesh.peclet_edge("viscosity", pf)
+    pec = mesh.download("peclet_factor")
+    opec = orc.peclet_edge(2, c.edges, c.coords, f["velocity"], f["density"],
+                           f["viscosity"], opf)[1]
+    res["peclet"] = scaled_err(pec, opec, np.ones_like(opec))
+    mesh.upload("mass_flow_rate", omdot)
+    mesh.upload("peclet_factor", opec)
+    for phi, grad, d1 in (("pressure", "dpdx_out", 1), ("velocity", "dudx_out", 2)):
+        mesh.register(grad, P.NW_NODE, d1 * 2)
+        mesh.nodal_grad_edge(phi, grad)
+        got = mesh.download(grad)
+        ref = orc.nodal_grad_edge(d1, 2, c.edges, f[phi], c.area, c.vol, c.n_nodes)
+        mag = np.abs(orc.nodal_grad_edge(d1, 2, c.edges, np.abs(f[phi]),
+                                         np.abs(c.area), c.vol, c.n_nodes))
+        mag = mag + np.max(np.abs(ref)) * 1e-3
+        res["grad_" + phi] = scaled_err(got.reshape(ref.shape), ref, mag)
+    g = orc.Graph(1, 0, c.n_nodes - 1)
+    g.add_edges(c.edges, c.hid)
+    g.finalize()
+
+    def system(kind, nd):
+        ls = P.LinearSystem(mesh, kind, nd)
+        if mode is not None:
+            ls.set_scatter_mode(mode)
+        ls.buildEdgeToNodeGraph()
+        ls.finalizeLinearSystem()
+        ls.zeroSystem()
+        return ls
+
+    def compare(name, ls, sink):
+        vals, rhs = ls.values()
+        ov, orhs = sink.get()
+        av, arhs = sink.get_abs()
+        res[name + "_lhs"] = scaled_err(vals, ov, av)
+        res[name + "_rhs"] = scaled_err(rhs, orhs, arhs)
+
+    ls = system(P.NW_LINSYS_HYPRE, 1)
+    ls.assemble_continuity_edge(**CONT_OPTS)
+    s = orc.HypreSink(g, c.hid)
+    orc.continuity_edge(2, c.edges, c.coords, f["velocity"], f["dpdx"],
+                        f["density"], f["pressure"], f["momentum_diag"], c.area,
+                        s, **CONT_OPTS)
+    compare("continuity", ls, s)
+    ls.close()
+    ls = system(P.NW_LINSYS_HYPRE, 1)
+    ls.assemble_scalar_edge("turbulent_ke", "dkdx", "effective_viscosity_tke",
+                            pf=P.peclet_fn("tanh", 2.0, 1.0), **SCAL_OPTS)
+    s = orc.HypreSink(g, c.hid)
+    orc.scalar_edge(2, c.edges, c.coords, f["velocity"], f["turbulent_ke"],
+                    f["dkdx"], f["density"], f["effective_viscosity_tke"], c.area,
+                    omdot, s, pf=orc.peclet("tanh", 2.0, 1.0), **SCAL_OPTS)
+    compare("scalar", ls, s)
+    ls.close()
+    ls = system(P.NW_LINSYS_HYPRE_UVW, 2)
+    ls.assemble_momentum_edge("viscosity", **MOM_OPTS)
+    s = orc.HypreSink(g, c.hid, uvw_ndim=2)
+    orc.momentum_edge(2, c.edges, c.coords, f["velocity"], f["dudx"],
+                      f["viscosity"], f["density"],
+                      f["abl_wall_no_slip_wall_func_node_mask"], c.area, omdot,
+                      opec, s, **MOM_OPTS)
+    compare("momentum_uvw", ls, s)
+    ls.zeroSystem()
+    ls.assemble_momentum_edge("viscosity", fuse_peclet=True, pf=pf, **MOM_OPTS)
+    compare("momentum_fused", ls, s)
+    ls.close()
+    mesh.close()
+    return res

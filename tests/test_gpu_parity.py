@@ -213,6 +213,16 @@ def test_lowmach_sweep_vs_oracle(P, ctx, kw):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("mode", [None, 1])
+@pytest.mark.parametrize("tile", [64, 192])
+def test_quad2d_ogrid_sweep_vs_oracle(P, ctx, tile, mode):
+    """ndim = 2 instantiations on a curvilinear quad O-grid (the reference's
+    airfoilRANSEdge mesh is 2-D QUAD4; BASELINE configs[3])"""
+    res = pu.run_quad2d_case(P, ctx, tile_nodes=tile, mode=mode)
+    bad = {k: v for k, v in res.items() if not v < 1.0}
+    assert not bad, bad
+
+
 def test_monolithic_momentum_vs_oracle(P, ctx):
     case = pu.Case(dims=(10, 9, 7))
     mesh = case.box.make_mesh(ctx, tile_nodes=64)
