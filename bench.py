@@ -401,6 +401,7 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         sweep(record=True, detail=args.detail)
+    ctx.join_comm()  # the last step's halo adds (communication stream) count
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -496,6 +497,7 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         norms = e2e_step()
+    ctx.join_comm()
     e1.record(stream)
     if not args.serial_upload:
         for fid, _ in pinned.values():  # drain the look-ahead copy

@@ -89,6 +89,15 @@ typedef enum {
   NW_TRANSPORT_PEER_MEMORY = 2
 } nw_halo_transport;
 int nw_ctx_peer_memory(const nw_ctx* ctx); /* 1 if the mailbox is up */
+/* With NW_P2P_ASYNC=1 the receiving half of a peer-memory exchange (wait for
+ * the neighbour + add) runs on a separate high-priority communication stream,
+ * so that it overlaps whatever the caller enqueues next; every nw_* call that
+ * touches the exchanged field / linear system again is ordered after it
+ * automatically.  nw_ctx_join_comm orders the context's compute stream after
+ * all exchanges issued so far (no host synchronisation) -- for callers that
+ * hand raw device pointers (nw_field_device_view, nw_linsys_device_arrays) to
+ * their own kernels on nw_ctx_stream.  A no-op in the default one-stream mode. */
+int nw_ctx_join_comm(nw_ctx* ctx);
 
 /* ------------------------------------------------------------------ */
 /* mesh partition                                                      */

@@ -98,7 +98,8 @@ class LinsysSizes(C.Structure):
 ABI_SYMBOLS = [
     "nw_last_error", "nw_version", "nw_debug_phase_times", "nw_ctx_create", "nw_ctx_destroy",
     "nw_ctx_sync", "nw_ctx_stream", "nw_comm_unique_id", "nw_ctx_comm_init",
-    "nw_ctx_peer_memory", "nw_mesh_halo_transport", "nw_linsys_halo_transport",
+    "nw_ctx_peer_memory", "nw_ctx_join_comm", "nw_mesh_halo_transport",
+    "nw_linsys_halo_transport",
     "nw_mesh_create", "nw_mesh_destroy", "nw_mesh_get_stats",
     "nw_field_register", "nw_field_find", "nw_field_upload",
     "nw_field_stage", "nw_field_commit", "nw_field_download", "nw_field_fill", "nw_field_device_view",
@@ -147,6 +148,7 @@ def lib():
     L.nw_comm_unique_id.argtypes = [vp]
     L.nw_ctx_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     L.nw_ctx_peer_memory.argtypes = [vp]
+    L.nw_ctx_join_comm.argtypes = [vp]
     L.nw_mesh_halo_transport.argtypes = [vp]
     L.nw_linsys_halo_transport.argtypes = [vp]
     L.nw_mesh_create.argtypes = [vp, C.POINTER(MeshDesc), C.POINTER(vp)]
@@ -235,6 +237,10 @@ class Context:
     def comm_init(self, unique_id_bytes, nranks, rank):
         buf = C.create_string_buffer(bytes(unique_id_bytes), 128)
         _chk(lib().nw_ctx_comm_init(self.h, buf, nranks, rank))
+
+    def join_comm(self):
+        """order the compute stream after all halo exchanges issued so far"""
+        _chk(lib().nw_ctx_join_comm(self.h))
 
     def peer_memory(self):
         """True if the NVLink peer-memory mailbox is up (else NCCL send/recv)"""

@@ -158,6 +158,8 @@ nw_ctx_sync(nw_ctx* ctx)
   if (int rc = need_device(ctx, "nw_ctx_sync"))
     return rc;
   NW_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->p2p.commStream)
+    NW_CUDA(cudaStreamSynchronize(ctx->p2p.commStream));
   if (ctx->p2p.ok) {
     /* a pull kernel that gave up waiting for a peer leaves a mark */
     unsigned w[2] = {0, 0};
@@ -291,6 +293,13 @@ nw_mesh_create(nw_ctx* ctx, const nw_mesh_desc* desc, nw_mesh** out)
 extern "C" int
 nw_mesh_destroy(nw_mesh* mesh)
 {
+  if (mesh)
+    for (auto& f : mesh->fields)
+      if (f->pullDone) {
+        cudaEventSynchronize(f->pullDone);
+        if (mesh->ctx->p2p.lastPull == f->pullDone)
+          mesh->ctx->p2p.lastPull = nullptr;
+      }
   delete mesh;
   return NW_OK;
 }
@@ -383,12 +392,25 @@ nw_field_find(const nw_mesh* mesh, const char* name, int* field_id)
   return NW_OK;
 }
 
+/* a halo sum of this field may still be running on the communication stream:
+ * order the compute stream (and with it every later use) after it */
+static void
+field_wait_pull(nw_mesh* mesh, nw_field_t* f)
+{
+  if (f->pullPending) {
+    cudaStreamWaitEvent(mesh->ctx->stream, f->pullDone, 0);
+    f->pullPending = false;
+  }
+}
+
 static nw_field_t*
 get_field(nw_mesh* mesh, int id)
 {
   if (!mesh || id < 0 || id >= (int)mesh->fields.size())
     return nullptr;
-  return mesh->fields[id].get();
+  nw_field_t* f = mesh->fields[id].get();
+  field_wait_pull(mesh, f);
+  return f;
 }
 
 static int
@@ -547,6 +569,7 @@ bind(
       NW_ERR_STATE, std::string("required field '") + name +
                       "' is not registered (get_field_ordinal would throw)");
   nw_field_t& f = *mesh->fields[it->second];
+  field_wait_pull(mesh, &f);
   if (f.rank != rank || f.ncomp != ncomp)
     return fail(
       NW_ERR_STATE, std::string("field '") + name + "' has the wrong shape");
@@ -717,6 +740,13 @@ nw_linsys_create(nw_mesh* mesh, int kind, int num_dof, nw_linsys** out)
 extern "C" int
 nw_linsys_destroy(nw_linsys* ls)
 {
+  if (ls && ls->pullDone) {
+    cudaEventSynchronize(ls->pullDone);
+    if (ls->mesh->ctx->p2p.lastPull == ls->pullDone)
+      ls->mesh->ctx->p2p.lastPull = nullptr;
+    cudaEventDestroy(ls->pullDone);
+    ls->pullDone = nullptr;
+  }
   delete ls;
   return NW_OK;
 }
@@ -909,6 +939,12 @@ ls_ready(nw_linsys* ls, const char* what)
     return fail(
       NW_ERR_STATE,
       std::string(what) + ": finalizeLinearSystem has not been called");
+  if (ls->pullPending) {
+    /* the shared-row add of the last loadComplete may still be running on the
+     * communication stream: every later use of the system comes after it */
+    cudaStreamWaitEvent(ls->mesh->ctx->stream, ls->pullDone, 0);
+    ls->pullPending = false;
+  }
   return NW_OK;
 }
 

@@ -95,6 +95,15 @@ struct nw_p2p
   std::vector<void*> mappedWindow, mappedFlags; /* per rank, opened IPC handles */
   nw::DevBuf dPeerWindow, dPeerFlags; /* device arrays of those pointers */
   unsigned long long epoch = 0;
+  /* asynchronous completion (NW_P2P_ASYNC=1): pushes run on the compute stream, pulls on
+   * `commStream` beside whatever the compute stream does next.  An object with
+   * a pull in flight carries its completion event; every later use of the
+   * object (and every later push: the window protocol needs pull(e) before
+   * push(e+1)) first makes the compute stream wait for it. */
+  bool async = false;
+  cudaStream_t commStream = nullptr;
+  cudaEvent_t pushDone = nullptr; /* compute stream: producer + push issued */
+  cudaEvent_t lastPull = nullptr; /* completion event of the latest pull (not owned) */
 };
 
 struct nw_ctx
@@ -118,8 +127,13 @@ struct nw_field_t
   cudaEvent_t staged = nullptr;   /* copy stream: staging holds the new data */
   cudaEvent_t consumed = nullptr; /* compute stream: staging may be reused */
   bool stagePending = false;
+  /* peer-memory halo sum in flight on the communication stream */
+  cudaEvent_t pullDone = nullptr;
+  bool pullPending = false;
   ~nw_field_t()
   {
+    if (pullDone)
+      cudaEventDestroy(pullDone);
     if (staged)
       cudaEventDestroy(staged);
     if (consumed)
@@ -223,6 +237,8 @@ struct nw_linsys
   nw_accum_plan valAccum, rhsAccum;
   /* peer-memory path: my tail segments -> the owners' windows */
   bool p2p = false;
+  cudaEvent_t pullDone = nullptr; /* shared-row add in flight (communication stream) */
+  bool pullPending = false;
   std::vector<int64_t> p2pPeerInfo; /* per peer: voff, roff, valTotal, rowTotal */
   const double* p2pBuiltFor = nullptr; /* dev.values the segment table was built for */
   int p2pNSeg = 0;

@@ -2671,6 +2671,17 @@ p2p_grid(int64_t elems)
   const int64_t cap = 2 * (int64_t)sm_count();
   return (int)std::max<int64_t>(1, std::min(b, cap));
 }
+/* pull kernels run on the communication stream beside the compute kernels of
+ * the main stream and spin until the neighbour's push has landed: keep them
+ * small so that they hold few SM resources while they wait */
+inline int
+p2p_pull_grid(int64_t elems, bool beside)
+{
+  if (!beside)
+    return p2p_grid(elems);
+  const int64_t b = (elems + 255) / 256;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(b, 32));
+}
 } // namespace
 
 cudaError_t
@@ -2687,9 +2698,9 @@ launch_p2p_push_nodal(
 cudaError_t
 launch_p2p_pull_nodal(
   double* base, int64_t stride, int nc, const int64_t* recvIdx, int64_t n,
-  const P2pDev& pp, cudaStream_t s)
+  const P2pDev& pp, bool beside, cudaStream_t s)
 {
-  p2p_pull_nodal_kernel<<<p2p_grid(n * nc), 256, 0, s>>>(
+  p2p_pull_nodal_kernel<<<p2p_pull_grid(n * nc, beside), 256, 0, s>>>(
     base, stride, nc, recvIdx, n, pp);
   return cudaGetLastError();
 }
@@ -2709,10 +2720,10 @@ cudaError_t
 launch_p2p_pull_accumulate(
   int64_t bufOff, int64_t entStride, int64_t compStride, int nc,
   const int64_t* dstIdx, const int64_t* ptr, const int64_t* pos, int64_t nDst,
-  double* dst, int64_t dstCompStride, const P2pDev& pp, bool wait,
+  double* dst, int64_t dstCompStride, const P2pDev& pp, bool wait, bool beside,
   cudaStream_t s)
 {
-  p2p_pull_accumulate_kernel<<<p2p_grid(nDst * nc), 256, 0, s>>>(
+  p2p_pull_accumulate_kernel<<<p2p_pull_grid(nDst * nc, beside), 256, 0, s>>>(
     bufOff, entStride, compStride, nc, dstIdx, ptr, pos, nDst, dst,
     dstCompStride, pp, wait ? 1 : 0);
   return cudaGetLastError();

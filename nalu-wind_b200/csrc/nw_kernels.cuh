@@ -172,9 +172,11 @@ cudaError_t launch_p2p_push_nodal(
   const double* base, int64_t stride, int nc, const int64_t* sendIdx,
   const int32_t* sendPeer, const int64_t* sendDst, int64_t n, const P2pDev& pp,
   cudaStream_t s);
+/* beside: the launch shares the GPU with compute kernels of another stream
+ * (asynchronous completion) -- small grid */
 cudaError_t launch_p2p_pull_nodal(
   double* base, int64_t stride, int nc, const int64_t* recvIdx, int64_t n,
-  const P2pDev& pp, cudaStream_t s);
+  const P2pDev& pp, bool beside, cudaStream_t s);
 cudaError_t launch_p2p_push_segments(
   const double* const* segSrc, const int64_t* segStart, const int64_t* segDst,
   const int32_t* segPeer, int nSeg, int64_t total, const P2pDev& pp,
@@ -182,7 +184,7 @@ cudaError_t launch_p2p_push_segments(
 cudaError_t launch_p2p_pull_accumulate(
   int64_t bufOff, int64_t entStride, int64_t compStride, int nc,
   const int64_t* dstIdx, const int64_t* ptr, const int64_t* pos, int64_t nDst,
-  double* dst, int64_t dstCompStride, const P2pDev& pp, bool wait,
+  double* dst, int64_t dstCompStride, const P2pDev& pp, bool wait, bool beside,
   cudaStream_t s);
 
 /* all peers + all components in one launch; buffer element of concatenated
