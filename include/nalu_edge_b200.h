@@ -362,6 +362,30 @@ int nw_linsys_sum_into(
   const double* d_lhs,
   const double* d_rhs);
 
+/* CoeffApplier::resetRows (include/LinearSystem.h:53-60;
+ * HypreLinSysCoeffApplier::reset_rows src/HypreLinearSystem.C:2262-2330,
+ * HypreUVWLinSysCoeffApplier::reset_rows src/HypreUVWLinearSystem.C:787-851):
+ * zero the matrix rows of the given local nodes (all dofs; owned rows and rows
+ * in the shared tail), set their diagonal to diag_value and their rhs (every
+ * column) to rhs_residual.  FixPressureAtNodeAlgorithm::execute
+ * (src/FixPressureAtNodeAlgorithm.C:57-121) is this call with (0, 0) followed
+ * by nw_linsys_sum_into of the 1x1 block lhs = 1, rhs = refPressure - p.
+ * `nodes` is a host array. */
+int nw_linsys_reset_rows(
+  nw_linsys* ls, int64_t n_nodes, const int32_t* nodes, double diag_value,
+  double rhs_residual);
+
+/* HypreLinearSystem::applyDirichletBCs (src/HypreLinearSystem.C:2407-2457) /
+ * HypreUVWLinearSystem::applyDirichletBCs (src/HypreUVWLinearSystem.C:377-427):
+ * for every locally-owned node of the list and every dof d, the first entry of
+ * the row (the diagonal: Dirichlet rows are the skipped, diagonal-only rows of
+ * nw_linsys_set_skipped_rows) becomes 1 and rhs = bc_values(node, d) -
+ * solution(node, d).  Fields are nodal with one component per dof.  `nodes` is
+ * a host array of local node indices. */
+int nw_linsys_apply_dirichlet_bcs(
+  nw_linsys* ls, int solution_field, int bc_values_field, int64_t n_nodes,
+  const int32_t* nodes);
+
 
 /* ---- shared-row exchange structure (multi-rank) ----
  * The rows of the shared tail destined to one owner form one contiguous

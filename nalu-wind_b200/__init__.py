@@ -110,7 +110,8 @@ ABI_SYMBOLS = [
     "nw_linsys_get_edge_slots", "nw_linsys_zero",
     "nw_linsys_set_scatter_mode", "nw_assemble_continuity_edge",
     "nw_assemble_scalar_edge", "nw_assemble_momentum_edge",
-    "nw_linsys_sum_into", "nw_linsys_load_complete",
+    "nw_linsys_sum_into", "nw_linsys_reset_rows",
+    "nw_linsys_apply_dirichlet_bcs", "nw_linsys_load_complete",
     "nw_linsys_device_arrays", "nw_linsys_get_values", "nw_linsys_rhs_norm2",
     "nw_mesh_halo_send_count", "nw_mesh_halo_get_send", "nw_mesh_halo_set_recv",
     "nw_mesh_halo_commit", "nw_field_parallel_sum", "nw_linsys_halo_send_info",
@@ -184,6 +185,8 @@ def lib():
     L.nw_assemble_momentum_edge.argtypes = [vp, C.c_int,
                                             C.POINTER(MomentumOpts)]
     L.nw_linsys_sum_into.argtypes = [vp, C.c_int64, C.c_int, vp, vp, vp]
+    L.nw_linsys_reset_rows.argtypes = [vp, C.c_int64, vp, C.c_double, C.c_double]
+    L.nw_linsys_apply_dirichlet_bcs.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp]
     L.nw_linsys_load_complete.argtypes = [vp]
     L.nw_linsys_device_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(vp),
                                           C.POINTER(C.c_int64)]
@@ -483,6 +486,32 @@ class LinearSystem:
                          m.field_id(diag_field) if diag_field else -1)
         _chk(lib().nw_assemble_momentum_edge(
             self.h, m.field_id(viscosity), C.byref(o)))
+
+    def sumInto(self, entity_nodes, lhs, rhs):
+        """generic CoeffApplier::operator(): entity_nodes [nEnt][npe] local node
+        indices, lhs [nEnt][n][n], rhs [nEnt][n] (host arrays; copied to the
+        device for the call)"""
+        import torch
+        en = np.ascontiguousarray(entity_nodes, dtype=np.int32)
+        d_en = torch.from_numpy(en).cuda()
+        d_l = torch.from_numpy(np.ascontiguousarray(lhs, dtype=np.float64)).cuda()
+        d_r = torch.from_numpy(np.ascontiguousarray(rhs, dtype=np.float64)).cuda()
+        torch.cuda.synchronize()
+        _chk(lib().nw_linsys_sum_into(
+            self.h, en.shape[0], en.shape[1], C.c_void_p(d_en.data_ptr()),
+            C.c_void_p(d_l.data_ptr()), C.c_void_p(d_r.data_ptr())))
+        self.mesh.ctx.sync()
+
+    def resetRows(self, nodes, diag_value=0.0, rhs_residual=0.0):
+        nd = np.ascontiguousarray(nodes, dtype=np.int32)
+        _chk(lib().nw_linsys_reset_rows(self.h, nd.size, _ptr(nd), diag_value,
+                                        rhs_residual))
+
+    def applyDirichletBCs(self, solution, bc_values, nodes):
+        nd = np.ascontiguousarray(nodes, dtype=np.int32)
+        _chk(lib().nw_linsys_apply_dirichlet_bcs(
+            self.h, self.mesh.field_id(solution), self.mesh.field_id(bc_values),
+            nd.size, _ptr(nd)))
 
     def loadComplete(self):
         _chk(lib().nw_linsys_load_complete(self.h))

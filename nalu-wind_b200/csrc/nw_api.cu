@@ -1193,6 +1193,126 @@ nw_assemble_momentum_edge(
   return NW_OK;
 }
 
+/* local row (owned, then shared tail) of a global row id, -1 if this rank
+ * holds no such row (non-owned rows absent from map_shared_ are skipped,
+ * src/HypreLinearSystem.C:2301-2302) */
+static int64_t
+local_row_of(const Graph& g, int64_t hid)
+{
+  if (hid >= g.iLower && hid <= g.iUpper)
+    return hid - g.iLower;
+  auto it = std::lower_bound(
+    g.rowIndicesShared.begin(), g.rowIndicesShared.end(), hid);
+  if (it == g.rowIndicesShared.end() || *it != hid)
+    return -1;
+  return g.numRowsOwned + (it - g.rowIndicesShared.begin());
+}
+
+extern "C" int
+nw_linsys_reset_rows(
+  nw_linsys* ls, int64_t n_nodes, const int32_t* nodes, double diag_value,
+  double rhs_residual)
+{
+  if (int rc = ls_ready(ls, "nw_linsys_reset_rows"))
+    return rc;
+  if (n_nodes < 0 || (n_nodes > 0 && !nodes))
+    return fail(NW_ERR_ARG, "nw_linsys_reset_rows: bad node list");
+  const MeshPlan& mp = ls->mesh->plan;
+  const Graph& g = ls->g;
+  /* UVW: one matrix row per node, all rhs columns; else numDof rows per node */
+  const int nd = ls->kind == NW_LINSYS_HYPRE_UVW ? 1 : ls->numDof;
+  std::vector<int64_t> rows;
+  for (int64_t i = 0; i < n_nodes; ++i) {
+    if (nodes[i] < 0 || nodes[i] >= mp.nNodes)
+      return fail(NW_ERR_ARG, "nw_linsys_reset_rows: node index out of range");
+    for (int d = 0; d < nd; ++d) {
+      const int64_t hid = mp.nodeHid[nodes[i]] * nd + d;
+      const int64_t lr = local_row_of(g, hid);
+      if (lr < 0)
+        continue;
+      const int64_t a = g.rowPtr(lr), len = g.rowLen(lr);
+      const int64_t* rc = g.cols.data() + a;
+      const int64_t* p = std::lower_bound(rc, rc + len, hid);
+      rows.push_back(a);
+      rows.push_back(len);
+      rows.push_back((p != rc + len && *p == hid) ? (p - rc) : -1);
+      rows.push_back(lr);
+    }
+  }
+  if (ls->state != NW_LS_ACCUM)
+    if (int rc = materialize_zero(ls))
+      return rc;
+  if (rows.empty())
+    return NW_OK;
+  cudaStream_t s = ls->mesh->ctx->stream;
+  DevBuf d;
+  if (int rc = upload(d, rows, s, nullptr))
+    return rc;
+  NW_CUDA(launch_reset_rows(
+    d.as<int64_t>(), (int64_t)rows.size() / 4, diag_value, rhs_residual,
+    ls->dev.values, ls->dev.rhs, ls->dev.rhsStride, ls->nRhs, s));
+  NW_CUDA(cudaStreamSynchronize(s)); /* the row table is freed on return */
+  return NW_OK;
+}
+
+extern "C" int
+nw_linsys_apply_dirichlet_bcs(
+  nw_linsys* ls, int solution_field, int bc_values_field, int64_t n_nodes,
+  const int32_t* nodes)
+{
+  if (int rc = ls_ready(ls, "nw_linsys_apply_dirichlet_bcs"))
+    return rc;
+  if (n_nodes < 0 || (n_nodes > 0 && !nodes))
+    return fail(NW_ERR_ARG, "nw_linsys_apply_dirichlet_bcs: bad node list");
+  nw_mesh* mesh = ls->mesh;
+  const MeshPlan& mp = mesh->plan;
+  const Graph& g = ls->g;
+  const bool uvw = ls->kind == NW_LINSYS_HYPRE_UVW;
+  const int ncomp = uvw ? ls->nRhs : ls->numDof;
+  nw_field_t* sol = get_field(mesh, solution_field);
+  nw_field_t* bc = get_field(mesh, bc_values_field);
+  if (!sol || !bc || sol->rank != NW_NODE || bc->rank != NW_NODE ||
+      sol->ncomp != ncomp || bc->ncomp != ncomp)
+    return fail(
+      NW_ERR_ARG, "nw_linsys_apply_dirichlet_bcs: solution / bc fields must be "
+                  "nodal with one component per dof");
+  std::vector<int64_t> rows;
+  for (int64_t i = 0; i < n_nodes; ++i) {
+    if (nodes[i] < 0 || nodes[i] >= mp.nNodes)
+      return fail(
+        NW_ERR_ARG, "nw_linsys_apply_dirichlet_bcs: node index out of range");
+    const int64_t hid = mp.nodeHid[nodes[i]];
+    const int64_t slot = mp.slotOfNode[nodes[i]];
+    for (int d = 0; d < ncomp; ++d) {
+      /* locally-owned rows only (the reference's selector) */
+      const int64_t row = uvw ? hid : hid * ls->numDof + d;
+      if (row < g.iLower || row > g.iUpper)
+        continue;
+      const int64_t lr = row - g.iLower;
+      rows.push_back(g.rowStartOwned[lr]);
+      rows.push_back(lr);
+      rows.push_back(uvw ? d : 0);
+      rows.push_back(slot);
+      rows.push_back(d);
+    }
+  }
+  if (ls->state != NW_LS_ACCUM)
+    if (int rc = materialize_zero(ls))
+      return rc;
+  if (rows.empty())
+    return NW_OK;
+  cudaStream_t s = mesh->ctx->stream;
+  DevBuf d;
+  if (int rc = upload(d, rows, s, nullptr))
+    return rc;
+  NW_CUDA(launch_dirichlet_rows(
+    d.as<int64_t>(), (int64_t)rows.size() / 5, sol->buf.as<double>(),
+    bc->buf.as<double>(), sol->stride, ls->dev.values, ls->dev.rhs,
+    ls->dev.rhsStride, s));
+  NW_CUDA(cudaStreamSynchronize(s));
+  return NW_OK;
+}
+
 static int
 build_dev_graph(nw_linsys* ls)
 {

@@ -1664,6 +1664,44 @@ row_init_kernel(
     rhs[(int64_t)d * rhsStride + r] = 0.0;
 }
 
+/* CoeffApplier::resetRows: rows[t] = (value offset, length, diagonal position
+ * or -1, rhs row): zero the row, diagonal = diagValue, every rhs column =
+ * rhsResidual (src/HypreLinearSystem.C:2262-2315) */
+__global__ void
+reset_rows_kernel(
+  const int64_t* __restrict__ rows, int64_t nRows, double diagValue,
+  double rhsResidual, double* values, double* rhs, int64_t rhsStride, int nRhs)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nRows)
+    return;
+  const int64_t a = rows[4 * t], len = rows[4 * t + 1], dk = rows[4 * t + 2],
+                rr = rows[4 * t + 3];
+  for (int64_t k = 0; k < len; ++k)
+    values[a + k] = (k == dk) ? diagValue : 0.0;
+  for (int d = 0; d < nRhs; ++d)
+    rhs[(int64_t)d * rhsStride + rr] = rhsResidual;
+}
+
+/* applyDirichletBCs (src/HypreLinearSystem.C:2446-2456): rows[t] = (value
+ * offset of the row's first entry, rhs row, rhs column, field slot, field
+ * component): first entry = 1, rhs = bc - solution */
+__global__ void
+dirichlet_rows_kernel(
+  const int64_t* __restrict__ rows, int64_t nRows,
+  const double* __restrict__ solution, const double* __restrict__ bc,
+  int64_t fieldStride, double* values, double* rhs, int64_t rhsStride)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nRows)
+    return;
+  const int64_t a = rows[5 * t], rr = rows[5 * t + 1], col = rows[5 * t + 2],
+                slot = rows[5 * t + 3], comp = rows[5 * t + 4];
+  values[a] = 1.0;
+  rhs[col * rhsStride + rr] =
+    bc[comp * fieldStride + slot] - solution[comp * fieldStride + slot];
+}
+
 /* fixed-shape two-level reduction: deterministic for a given (n, nPartial) */
 __global__ void __launch_bounds__(256) norm2_partial_kernel(
   const double* __restrict__ rhs, int64_t n, int64_t stride, double* partial)
@@ -2547,6 +2585,31 @@ launch_row_init(
     return cudaSuccess;
   row_init_kernel<<<blocks_for(nRows, 128), 128, 0, s>>>(
     rows, nRows, rowPtr, isPeriodic, values, rhs, rhsStride, nRhs);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_reset_rows(
+  const int64_t* rows, int64_t nRows, double diagValue, double rhsResidual,
+  double* values, double* rhs, int64_t rhsStride, int nRhs, cudaStream_t s)
+{
+  if (nRows == 0)
+    return cudaSuccess;
+  reset_rows_kernel<<<blocks_for(nRows, 128), 128, 0, s>>>(
+    rows, nRows, diagValue, rhsResidual, values, rhs, rhsStride, nRhs);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_dirichlet_rows(
+  const int64_t* rows, int64_t nRows, const double* solution, const double* bc,
+  int64_t fieldStride, double* values, double* rhs, int64_t rhsStride,
+  cudaStream_t s)
+{
+  if (nRows == 0)
+    return cudaSuccess;
+  dirichlet_rows_kernel<<<blocks_for(nRows, 128), 128, 0, s>>>(
+    rows, nRows, solution, bc, fieldStride, values, rhs, rhsStride);
   return cudaGetLastError();
 }
 

@@ -134,6 +134,17 @@ cudaError_t launch_row_init(
   const int32_t* rows, int nRows, const int64_t* rowPtr /* [R+1] */,
   const uint8_t* isPeriodic, double* values, double* rhs, int64_t rhsStride,
   int nRhs, cudaStream_t s);
+/* CoeffApplier::resetRows; rows: int64[nRows][4] = value offset, length,
+ * diagonal position (-1: none), rhs row */
+cudaError_t launch_reset_rows(
+  const int64_t* rows, int64_t nRows, double diagValue, double rhsResidual,
+  double* values, double* rhs, int64_t rhsStride, int nRhs, cudaStream_t s);
+/* applyDirichletBCs; rows: int64[nRows][5] = value offset of the row's first
+ * entry, rhs row, rhs column, field slot, field component */
+cudaError_t launch_dirichlet_rows(
+  const int64_t* rows, int64_t nRows, const double* solution, const double* bc,
+  int64_t fieldStride, double* values, double* rhs, int64_t rhsStride,
+  cudaStream_t s);
 /* deterministic sum of squares of rhs[d*stride + (0..n)] for each d */
 cudaError_t launch_norm2(
   const double* rhs, int64_t n, int64_t stride, int nRhs, double* partial,

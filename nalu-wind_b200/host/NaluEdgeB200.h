@@ -239,6 +239,34 @@ public:
   {
     nw_check(nw_linsys_set_skipped_rows(ls_, rows.data(), (int64_t)rows.size()));
   }
+  /* LinearSystem::applyDirichletBCs (include/LinearSystem.h:163-168): the
+   * part vector becomes the list of local nodes of those parts */
+  virtual void applyDirichletBCs(
+    const std::string& solutionField, const std::string& bcValuesField,
+    const std::vector<int32_t>& nodes)
+  {
+    nw_check(nw_linsys_apply_dirichlet_bcs(
+      ls_, realm_.field_ordinal(solutionField), realm_.field_ordinal(bcValuesField),
+      (int64_t)nodes.size(), nodes.data()));
+  }
+  /* CoeffApplier::resetRows (include/LinearSystem.h:53-60) */
+  virtual void resetRows(
+    const std::vector<int32_t>& nodeList, const unsigned /*beginPos*/,
+    const unsigned /*endPos*/, const double diag_value = 0.0,
+    const double rhs_residual = 0.0)
+  {
+    nw_check(nw_linsys_reset_rows(
+      ls_, (int64_t)nodeList.size(), nodeList.data(), diag_value, rhs_residual));
+  }
+  /* CoeffApplier::operator() (include/LinearSystem.h:62-70) for blocks the
+   * caller computed on the device */
+  void sumInto(
+    int64_t numEntities, int nodesPerEntity, const int32_t* d_entityNodes,
+    const double* d_lhs, const double* d_rhs)
+  {
+    nw_check(nw_linsys_sum_into(
+      ls_, numEntities, nodesPerEntity, d_entityNodes, d_lhs, d_rhs));
+  }
   unsigned numDof() const { return numDof_; }
   nw_linsys* handle() { return ls_; }
   nw_linsys_sizes sizes() const

@@ -716,6 +716,108 @@ orc_applier_hypre_create(
   return new HypreApplier(g, node_hid, n_nodes, uvw_ndim);
 }
 
+/* CoeffApplier::operator() (include/LinearSystem.h:62-70) for a batch of
+ * entities: lhs [nEnt][n][n] row-major, rhs [nEnt][n] */
+extern "C" void
+orc_applier_apply(
+  orc_applier* a, int64_t n_entities, int nodes_per_entity,
+  const int32_t* entity_nodes, const double* lhs, const double* rhs, int n)
+{
+  for (int64_t e = 0; e < n_entities; ++e)
+    a->apply(
+      nodes_per_entity, entity_nodes + e * nodes_per_entity, rhs + e * n,
+      lhs + e * n * n, n);
+}
+
+/* HypreLinSysCoeffApplier::reset_rows (src/HypreLinearSystem.C:2262-2315) /
+ * HypreUVWLinSysCoeffApplier::reset_rows (src/HypreUVWLinearSystem.C:787-835):
+ * zero the rows of the given nodes, diagonal = diag_value, rhs = rhs_residual */
+extern "C" void
+orc_applier_hypre_reset_rows(
+  orc_applier* a, int64_t n_nodes, const int32_t* nodes, double diag_value,
+  double rhs_residual)
+{
+  auto* h = static_cast<HypreApplier*>(a);
+  const orc_graph* g = h->g;
+  const int numDof = h->uvwDim > 0 ? 1 : g->numDof;
+  const int64_t memShift = g->nnzOwned;
+  for (int64_t i = 0; i < n_nodes; ++i) {
+    const int64_t lid = h->nodeHid[nodes[i]];
+    for (int d = 0; d < numDof; ++d) {
+      const int64_t hid = lid * numDof + d;
+      int64_t lower, upper, rhsIndex;
+      if (hid >= g->iLower && hid <= g->iUpper) {
+        const int64_t index = hid - g->iLower;
+        lower = g->rowStartOwned[index];
+        upper = g->rowStartOwned[index + 1];
+        rhsIndex = index;
+      } else {
+        auto it = g->mapShared.find(hid);
+        if (it == g->mapShared.end())
+          continue;
+        const int64_t index = it->second;
+        lower = g->rowStartShared[index] + memShift;
+        upper = g->rowStartShared[index + 1] + memShift;
+        rhsIndex = index + (g->iUpper - g->iLower + 1);
+      }
+      for (int64_t k = lower; k < upper; ++k) {
+        h->values[k] = 0.0;
+        h->absValues[k] = 0.0;
+        if (g->cols[k] == hid) {
+          h->values[k] = diag_value;
+          h->absValues[k] = std::fabs(diag_value);
+        }
+      }
+      for (int q = 0; q < h->nRhs; ++q) {
+        h->rhs[size_t(q) * h->totalRows + rhsIndex] = rhs_residual;
+        h->absRhs[size_t(q) * h->totalRows + rhsIndex] = std::fabs(rhs_residual);
+      }
+    }
+  }
+}
+
+/* HypreLinearSystem::applyDirichletBCs (src/HypreLinearSystem.C:2407-2457) /
+ * HypreUVWLinearSystem::applyDirichletBCs (src/HypreUVWLinearSystem.C:377-427),
+ * locally-owned nodes only: first entry of the row = 1, rhs = bc - solution.
+ * solution / bc: [n_local_nodes][ncomp] in the reference layout. */
+extern "C" void
+orc_applier_hypre_dirichlet(
+  orc_applier* a, int64_t n_nodes, const int32_t* nodes, const double* solution,
+  const double* bc_values, int ncomp)
+{
+  auto* h = static_cast<HypreApplier*>(a);
+  const orc_graph* g = h->g;
+  for (int64_t i = 0; i < n_nodes; ++i) {
+    const int64_t hid = h->nodeHid[nodes[i]];
+    if (h->uvwDim > 0) {
+      if (hid < g->iLower || hid > g->iUpper)
+        continue;
+      const int64_t matIndex = g->rowStartOwned[hid - g->iLower];
+      h->values[matIndex] = 1.0;
+      h->absValues[matIndex] = 1.0;
+      for (int d = 0; d < h->uvwDim; ++d) {
+        const double v = bc_values[size_t(nodes[i]) * ncomp + d] -
+                         solution[size_t(nodes[i]) * ncomp + d];
+        h->rhs[size_t(d) * h->totalRows + (hid - g->iLower)] = v;
+        h->absRhs[size_t(d) * h->totalRows + (hid - g->iLower)] = std::fabs(v);
+      }
+    } else {
+      for (int d = 0; d < g->numDof; ++d) {
+        const int64_t lid = hid * g->numDof + d;
+        if (lid < g->iLower || lid > g->iUpper)
+          continue;
+        const int64_t matIndex = g->rowStartOwned[lid - g->iLower];
+        h->values[matIndex] = 1.0;
+        h->absValues[matIndex] = 1.0;
+        const double v = bc_values[size_t(nodes[i]) * ncomp + d] -
+                         solution[size_t(nodes[i]) * ncomp + d];
+        h->rhs[lid - g->iLower] = v;
+        h->absRhs[lid - g->iLower] = std::fabs(v);
+      }
+    }
+  }
+}
+
 extern "C" void
 orc_applier_hypre_reset(orc_applier* a)
 {

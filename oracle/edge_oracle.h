@@ -112,6 +112,22 @@ void orc_applier_hypre_get_log(
  * cancellation scale for the 1e-12 tolerance. */
 void orc_applier_hypre_get_abs(const orc_applier*, double* values, double* rhs);
 
+/* CoeffApplier::operator() (include/LinearSystem.h:62-70) over a batch:
+ * lhs [n_entities][n][n] row-major, rhs [n_entities][n] */
+void orc_applier_apply(
+  orc_applier*, int64_t n_entities, int nodes_per_entity,
+  const int32_t* entity_nodes, const double* lhs, const double* rhs, int n);
+/* CoeffApplier::resetRows (src/HypreLinearSystem.C:2262-2330,
+ * src/HypreUVWLinearSystem.C:787-851) */
+void orc_applier_hypre_reset_rows(
+  orc_applier*, int64_t n_nodes, const int32_t* nodes, double diag_value,
+  double rhs_residual);
+/* applyDirichletBCs (src/HypreLinearSystem.C:2407-2457,
+ * src/HypreUVWLinearSystem.C:377-427) */
+void orc_applier_hypre_dirichlet(
+  orc_applier*, int64_t n_nodes, const int32_t* nodes, const double* solution,
+  const double* bc_values, int ncomp);
+
 void orc_applier_destroy(orc_applier*);
 
 /* ---- edge algorithms ---- */

@@ -234,6 +234,35 @@ class HypreSink:
     def get(self):
         return self._get(lib().orc_applier_hypre_get)
 
+    def apply(self, entity_nodes, lhs, rhs):
+        """CoeffApplier::operator() over a batch: entity_nodes [nEnt][npe],
+        lhs [nEnt][n][n], rhs [nEnt][n]"""
+        en = np.ascontiguousarray(entity_nodes, dtype=np.int32)
+        L = np.ascontiguousarray(lhs, dtype=np.float64)
+        R = np.ascontiguousarray(rhs, dtype=np.float64)
+        n_ent, npe = en.shape
+        n = R.shape[1]
+        f = lib().orc_applier_apply
+        f.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                      C.c_void_p, C.c_int]
+        f(self.h, n_ent, npe, en.ctypes.data, L.ctypes.data, R.ctypes.data, n)
+
+    def reset_rows(self, nodes, diag_value=0.0, rhs_residual=0.0):
+        nd = np.ascontiguousarray(nodes, dtype=np.int32)
+        f = lib().orc_applier_hypre_reset_rows
+        f.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_double]
+        f(self.h, nd.size, nd.ctypes.data, diag_value, rhs_residual)
+
+    def apply_dirichlet(self, nodes, solution, bc_values):
+        nd = np.ascontiguousarray(nodes, dtype=np.int32)
+        sol = np.ascontiguousarray(solution, dtype=np.float64)
+        bc = np.ascontiguousarray(bc_values, dtype=np.float64)
+        ncomp = 1 if sol.ndim == 1 else sol.shape[1]
+        f = lib().orc_applier_hypre_dirichlet
+        f.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                      C.c_int]
+        f(self.h, nd.size, nd.ctypes.data, sol.ctypes.data, bc.ctypes.data, ncomp)
+
     def get_abs(self):
         return self._get(lib().orc_applier_hypre_get_abs)
 

@@ -94,6 +94,13 @@ def main():
             "rhs": flat(f, "rhs_" + tag),
         }
     out["scalar_adv_diff"] = sc
+    # FixPressureAtNode / applyDirichletBCs variants of the same case
+    # (UnitTestScalarAdvDiffEdge.C:39-76, 108-125, 236-380)
+    for kind in ("fixed", "dirichlet"):
+        sc[kind + "_serial"] = {
+            "vals": flat(f, kind + "_vals_serial"),
+            "rhs": flat(f, kind + "_rhs_serial"),
+        }
 
     f = strip_comments(open(os.path.join(
         REF, "unit_tests/ngp_algorithms/UnitTestNodalGradAlg.C")).read())

@@ -280,6 +280,102 @@ def test_skipped_rows_and_accumulation(P, ctx):
         ls.close()
 
 
+def test_gold_fix_pressure_and_dirichlet(P, ctx):
+    """the reference's fixed_* / dirichlet_* golds through the product:
+    nw_linsys_reset_rows + nw_linsys_sum_into (FixPressureAtNodeAlgorithm) and
+    nw_linsys_apply_dirichlet_bcs (UnitTestScalarAdvDiffEdge.C:236-380)"""
+    m, c, e = _cube_mesh(P, ctx)
+    n = len(c)
+    av = uc.edge_area(c, e)
+    z, rho, visc = uc.mixture_fraction_fields(c)
+    vel = uc.velocity(c)
+    m.put("velocity", P.NW_NODE, vel)
+    m.put("density", P.NW_NODE, rho)
+    m.put("mixture_fraction", P.NW_NODE, z)
+    m.put("dzdx", P.NW_NODE, np.zeros((n, 3)))
+    m.put("viscosity", P.NW_NODE, visc)
+    m.put("edge_area_vector", P.NW_EDGE, av)
+    m.put("mass_flow_rate", P.NW_EDGE, uc.fixture_mdot(e, vel, rho, av))
+    kw = dict(alpha=0.0, alpha_upw=0.0, ho_upwind=0.0, relax_fac=1.0,
+              pf=P.peclet_fn("classic", 0.0))
+    for mode in (0, 1):
+        ls = P.LinearSystem(m)
+        ls.set_scatter_mode(mode)
+        ls.buildEdgeToNodeGraph()
+        ls.finalizeLinearSystem()
+        ls.zeroSystem()
+        ls.assemble_scalar_edge("mixture_fraction", "dzdx", "viscosity", **kw)
+        ls.resetRows([0])
+        ls.sumInto([[0]], [[[1.0]]], [[1.0 - rho[0]]])
+        vals, rhs = ls.values()
+        gold = G["scalar_adv_diff"]["fixed_serial"]
+        assert np.max(np.abs(vals - np.array(gold["vals"]))) <= 1e-12
+        assert np.max(np.abs(rhs[0] - np.array(gold["rhs"]))) <= 1e-12
+        ls.close()
+    # Dirichlet on every node: skipped (diagonal-only) rows, then (1, bc - sol)
+    m.put("solution", P.NW_NODE, np.full(n, 2.0))
+    bc = np.zeros(n)
+    bc[0] = 1.0
+    m.put("bc_values", P.NW_NODE, bc)
+    ls = P.LinearSystem(m)
+    ls.set_skipped_rows(np.arange(n, dtype=np.int64))
+    ls.buildEdgeToNodeGraph()
+    ls.finalizeLinearSystem()
+    ls.zeroSystem()
+    ls.assemble_scalar_edge("mixture_fraction", "dzdx", "viscosity", **kw)
+    ls.applyDirichletBCs("solution", "bc_values", np.arange(n))
+    vals, rhs = ls.values()
+    g = ls.graph()
+    assert g["cols"].tolist() == list(range(n))
+    assert np.array_equal(vals, np.ones(n))
+    gold = G["scalar_adv_diff"]["dirichlet_serial"]
+    assert np.max(np.abs(rhs[0] - np.array(gold["rhs"]))) <= 1e-12
+    ls.close()
+
+
+@pytest.mark.parametrize("kind", ["hypre", "uvw"])
+def test_sum_into_reset_rows_dirichlet_vs_oracle(P, ctx, kind):
+    """generic CoeffApplier entry (include/LinearSystem.h:62-70) + resetRows +
+    applyDirichletBCs on a synthetic case with Dirichlet rows, vs the oracle"""
+    case = pu.Case(dims=(7, 6, 5))
+    mesh = case.box.make_mesh(ctx, tile_nodes=48)
+    pu.upload_state(P, mesh, case)
+    rng = np.random.default_rng(7)
+    uvw = kind == "uvw"
+    ncomp = 3 if uvw else 1
+    skipped = np.sort(rng.choice(case.n_nodes, 9, replace=False)).astype(np.int64)
+    g = case.oracle_graph(skipped=skipped)
+    sink = orc.HypreSink(g, case.box.hid, uvw_ndim=3 if uvw else 0)
+    ls = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE_UVW if uvw else P.NW_LINSYS_HYPRE,
+                        3 if uvw else 1)
+    ls.set_skipped_rows(skipped)
+    ls.buildEdgeToNodeGraph()
+    ls.finalizeLinearSystem()
+    ls.zeroSystem()
+    # one block per edge: n = 2 nodes x (3 for UVW, 1 otherwise) dofs
+    nb = 2 * ncomp
+    lhs = rng.standard_normal((case.n_edges, nb, nb))
+    rhs = rng.standard_normal((case.n_edges, nb))
+    ls.sumInto(case.edges, lhs, rhs)
+    sink.apply(case.edges, lhs, rhs)
+    reset = np.array([3, 11, int(skipped[0]), case.n_nodes - 1], dtype=np.int32)
+    ls.resetRows(reset, 2.5, -0.75)
+    sink.reset_rows(reset, 2.5, -0.75)
+    sol = rng.standard_normal((case.n_nodes, ncomp))
+    bc = rng.standard_normal((case.n_nodes, ncomp))
+    mesh.put("sol_f", P.NW_NODE, sol)
+    mesh.put("bc_f", P.NW_NODE, bc)
+    ls.applyDirichletBCs("sol_f", "bc_f", skipped.astype(np.int32))
+    sink.apply_dirichlet(skipped.astype(np.int32), sol, bc)
+    vals, r = ls.values()
+    ov, orhs = sink.get()
+    av_, arhs = sink.get_abs()
+    assert pu.scaled_err(vals, ov, av_) < 1
+    assert pu.scaled_err(r, orhs, arhs) < 1
+    ls.close()
+    mesh.close()
+
+
 def test_staged_upload_matches_upload(P, ctx):
     """nw_field_stage (copy stream) + nw_field_commit leaves the same bits in
     the field as nw_field_upload, also when re-staged back to back"""

@@ -184,3 +184,62 @@ def test_scalar_two_rank_csr_gold():
             for k in gd:
                 assert abs(rowd[k] - gd[k]) <= 1e-12, (r, lr, k)
         assert np.max(np.abs(rhs - np.array(gold["rhs"]))) <= 1e-12
+
+
+def test_scalar_fix_pressure_gold():
+    """UnitTestScalarAdvDiffEdge.C:236-300 (NGP_adv_diff_edge_tpetra_fix_pressure_at_node):
+    after the edge assembly FixPressureAtNodeAlgorithm::execute resets the row of
+    STK node 1 (CoeffApplier::resetRows) and sums the 1x1 block lhs = 1,
+    rhs = refPressure - p into it (src/FixPressureAtNodeAlgorithm.C:103-116; the
+    test passes the density field as 'pressure', refPressure = 1)."""
+    c, e, av, z, rho, visc, vel = _scalar_case(1)
+    n = len(c)
+    hid = np.arange(n, dtype=np.int64)
+    g = orc.Graph(1, 0, n - 1)
+    g.add_edges(e, hid)
+    g.finalize()
+    sink = orc.HypreSink(g, hid)
+    _run_scalar(c, e, av, z, rho, visc, vel, uc.fixture_mdot(e, vel, rho, av),
+                sink)
+    sink.reset_rows([0])
+    sink.apply([[0]], [[[1.0]]], [[1.0 - rho[0]]])
+    vals, rhs = sink.get()
+    gold = G["scalar_adv_diff"]["fixed_serial"]
+    assert np.max(np.abs(vals - np.array(gold["vals"]))) <= 1e-12
+    assert np.max(np.abs(rhs[0] - np.array(gold["rhs"]))) <= 1e-12
+
+
+def test_scalar_dirichlet_gold():
+    """UnitTestScalarAdvDiffEdge.C:302-380 (NGP_adv_diff_edge_tpetra_dirichlet):
+    every node of the part is a Dirichlet node, solution = 2, bc = 1 at STK node
+    1 and 0 elsewhere.  The gold is the Tpetra system (full rows, zeroed); the
+    hypre system of this path keeps Dirichlet rows as skipped diagonal-only rows
+    (src/HypreLinearSystem.C:1032-1034) that no kernel assembles into and
+    applyDirichletBCs sets to (1, bc - solution) (:2446-2456): the same matrix,
+    compared densely."""
+    c, e, av, z, rho, visc, vel = _scalar_case(1)
+    n = len(c)
+    hid = np.arange(n, dtype=np.int64)
+    g = orc.Graph(1, 0, n - 1)
+    g.set_skipped(hid)
+    g.add_edges(e, hid)
+    g.finalize()
+    assert g.nnz_owned == n  # diagonal-only rows
+    sink = orc.HypreSink(g, hid)
+    _run_scalar(c, e, av, z, rho, visc, vel, uc.fixture_mdot(e, vel, rho, av),
+                sink)
+    sol = np.full(n, 2.0)
+    bc = np.zeros(n)
+    bc[0] = 1.0
+    sink.apply_dirichlet(np.arange(n), sol, bc)
+    vals, rhs = sink.get()
+    gold = G["scalar_adv_diff"]["dirichlet_serial"]
+    ref = G["scalar_adv_diff"]["serial"]
+    dense_gold = np.zeros((n, n))
+    for r in range(n):
+        for k in range(ref["rowOffsets"][r], ref["rowOffsets"][r + 1]):
+            dense_gold[r, ref["cols"][k]] = gold["vals"][k]
+    dense = np.zeros((n, n))
+    dense[np.arange(n), g.cols[:n]] = vals
+    assert np.array_equal(dense, dense_gold)
+    assert np.max(np.abs(rhs[0] - np.array(gold["rhs"]))) <= 1e-12
