@@ -362,6 +362,33 @@ int nw_linsys_sum_into(
   const double* d_lhs,
   const double* d_rhs);
 
+/* Time-derivative node kernels through AssembleNGPNodeSolverAlgorithm
+ * (src/AssembleNGPNodeSolverAlgorithm.C:85-146: every locally-owned node that
+ * is not a periodic slave; 1-node block zeroed, kernel, CoeffApplier):
+ *   NW_MASS_SCALAR     ScalarMassBDFNodeKernel::execute
+ *                      (src/node_kernels/ScalarMassBDFNodeKernel.C:72-96)
+ *   NW_MASS_MOMENTUM   MomentumMassBDFNodeKernel::execute
+ *                      (src/node_kernels/MomentumMassBDFNodeKernel.C:80-107)
+ *   NW_MASS_CONTINUITY ContinuityMassBDFNodeKernel::execute
+ *                      (src/node_kernels/ContinuityMassBDFNodeKernel.C:63-84)
+ * Accumulates into the system (call after the edge assembly, before
+ * loadComplete).  Field ids name the three time states of each field; a
+ * two-state field passes its N id for NM1 as the reference does. */
+typedef enum {
+  NW_MASS_SCALAR = 0,
+  NW_MASS_MOMENTUM = 1,
+  NW_MASS_CONTINUITY = 2
+} nw_mass_kind;
+typedef struct {
+  double dt, gamma1, gamma2, gamma3;
+  int32_t q_nm1, q_n, q_np1;       /* scalar (1 comp) / velocity (ndim); unused for continuity */
+  int32_t rho_nm1, rho_n, rho_np1; /* density */
+  int32_t dnv_nm1, dnv_n, dnv_np1; /* dual_nodal_volume */
+  int32_t dpdx;                    /* momentum only */
+} nw_mass_bdf_opts;
+int nw_assemble_mass_bdf_node(
+  nw_linsys* ls, int kind, const nw_mass_bdf_opts* opts);
+
 /* CoeffApplier::resetRows (include/LinearSystem.h:53-60;
  * HypreLinSysCoeffApplier::reset_rows src/HypreLinearSystem.C:2262-2330,
  * HypreUVWLinSysCoeffApplier::reset_rows src/HypreUVWLinearSystem.C:787-851):

@@ -85,6 +85,17 @@ class MomentumOpts(C.Structure):
                 ("diag_field", C.c_int32)]
 
 
+class MassBdfOpts(C.Structure):
+    _fields_ = [("dt", C.c_double), ("gamma1", C.c_double),
+                ("gamma2", C.c_double), ("gamma3", C.c_double)] + [
+        (n, C.c_int32) for n in (
+            "q_nm1", "q_n", "q_np1", "rho_nm1", "rho_n", "rho_np1",
+            "dnv_nm1", "dnv_n", "dnv_np1", "dpdx")]
+
+
+NW_MASS_SCALAR, NW_MASS_MOMENTUM, NW_MASS_CONTINUITY = 0, 1, 2
+
+
 class LinsysSizes(C.Structure):
     _fields_ = [("i_lower", C.c_int64), ("i_upper", C.c_int64),
                 ("num_rows_owned", C.c_int64), ("num_nonzeros_owned", C.c_int64),
@@ -110,7 +121,7 @@ ABI_SYMBOLS = [
     "nw_linsys_get_edge_slots", "nw_linsys_zero",
     "nw_linsys_set_scatter_mode", "nw_assemble_continuity_edge",
     "nw_assemble_scalar_edge", "nw_assemble_momentum_edge",
-    "nw_linsys_sum_into", "nw_linsys_reset_rows",
+    "nw_assemble_mass_bdf_node", "nw_linsys_sum_into", "nw_linsys_reset_rows",
     "nw_linsys_apply_dirichlet_bcs", "nw_linsys_load_complete",
     "nw_linsys_device_arrays", "nw_linsys_get_values", "nw_linsys_rhs_norm2",
     "nw_mesh_halo_send_count", "nw_mesh_halo_get_send", "nw_mesh_halo_set_recv",
@@ -186,6 +197,7 @@ def lib():
                                             C.POINTER(MomentumOpts)]
     L.nw_linsys_sum_into.argtypes = [vp, C.c_int64, C.c_int, vp, vp, vp]
     L.nw_linsys_reset_rows.argtypes = [vp, C.c_int64, vp, C.c_double, C.c_double]
+    L.nw_assemble_mass_bdf_node.argtypes = [vp, C.c_int, C.POINTER(MassBdfOpts)]
     L.nw_linsys_apply_dirichlet_bcs.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp]
     L.nw_linsys_load_complete.argtypes = [vp]
     L.nw_linsys_device_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(vp),
@@ -486,6 +498,19 @@ class LinearSystem:
                          m.field_id(diag_field) if diag_field else -1)
         _chk(lib().nw_assemble_momentum_edge(
             self.h, m.field_id(viscosity), C.byref(o)))
+
+    def assemble_mass_bdf_node(self, kind, dt, gammas, q=None, rho=None,
+                               dnv=None, dpdx=None):
+        """time-derivative node kernel; q / rho / dnv = (NM1, N, NP1) field names"""
+        fid = self.mesh.field_id
+        o = MassBdfOpts()
+        o.dt, (o.gamma1, o.gamma2, o.gamma3) = dt, gammas
+        if q is not None:
+            o.q_nm1, o.q_n, o.q_np1 = (fid(x) for x in q)
+        o.rho_nm1, o.rho_n, o.rho_np1 = (fid(x) for x in rho)
+        o.dnv_nm1, o.dnv_n, o.dnv_np1 = (fid(x) for x in dnv)
+        o.dpdx = fid(dpdx) if dpdx is not None else -1
+        _chk(lib().nw_assemble_mass_bdf_node(self.h, kind, C.byref(o)))
 
     def sumInto(self, entity_nodes, lhs, rhs):
         """generic CoeffApplier::operator(): entity_nodes [nEnt][npe] local node

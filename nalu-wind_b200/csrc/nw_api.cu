@@ -267,6 +267,18 @@ nw_mesh_create(nw_ctx* ctx, const nw_mesh_desc* desc, nw_mesh** out)
     if (int rc = mesh_upload_plan(m.get()))
       return rc;
   }
+  {
+    /* node-kernel selector (src/AssembleNGPNodeSolverAlgorithm.C:108-111):
+     * locally owned & !periodic-slave.  A slave carries its master's row id
+     * in node_hypre_id and its own in node_own_hypre_id. */
+    const int64_t* own =
+      desc->node_own_hypre_id ? desc->node_own_hypre_id : desc->node_hypre_id;
+    m->nodeKernelActive.assign(desc->n_nodes, 0);
+    for (int64_t n = 0; n < desc->n_nodes; ++n)
+      m->nodeKernelActive[n] =
+        own[n] >= m->plan.iLowerNode && own[n] <= m->plan.iUpperNode &&
+        own[n] == desc->node_hypre_id[n];
+  }
   if (desc->nranks > 1) {
     const int64_t* own =
       desc->node_own_hypre_id ? desc->node_own_hypre_id : desc->node_hypre_id;
@@ -1206,6 +1218,89 @@ local_row_of(const Graph& g, int64_t hid)
   if (it == g.rowIndicesShared.end() || *it != hid)
     return -1;
   return g.numRowsOwned + (it - g.rowIndicesShared.begin());
+}
+
+extern "C" int
+nw_assemble_mass_bdf_node(nw_linsys* ls, int kind, const nw_mass_bdf_opts* opts)
+{
+  if (int rc = ls_ready(ls, "nw_assemble_mass_bdf_node"))
+    return rc;
+  if (!opts || kind < NW_MASS_SCALAR || kind > NW_MASS_CONTINUITY)
+    return fail(NW_ERR_ARG, "nw_assemble_mass_bdf_node: bad argument");
+  nw_mesh* mesh = ls->mesh;
+  const MeshPlan& mp = mesh->plan;
+  const Graph& g = ls->g;
+  const bool uvw = ls->kind == NW_LINSYS_HYPRE_UVW;
+  const int nd = mp.ndim;
+  if (kind == NW_MASS_MOMENTUM ? !(uvw || ls->numDof == nd)
+                               : (uvw || ls->numDof != 1))
+    return fail(
+      NW_ERR_ARG, "nw_assemble_mass_bdf_node: kernel / system dof mismatch");
+  MassBdfFields F{};
+  F.fieldStride = mp.nSlots;
+  auto nodal = [&](int id, int ncomp, const double** out) -> int {
+    nw_field_t* f = get_field(mesh, id);
+    if (!f || f->rank != NW_NODE || f->ncomp != ncomp)
+      return fail(
+        NW_ERR_ARG, "nw_assemble_mass_bdf_node: bad field id or shape");
+    *out = f->buf.as<double>();
+    F.fieldStride = f->stride; /* the same for every nodal field of a mesh */
+    return NW_OK;
+  };
+  int rc;
+  const int rid[3] = {opts->rho_nm1, opts->rho_n, opts->rho_np1};
+  const int vid[3] = {opts->dnv_nm1, opts->dnv_n, opts->dnv_np1};
+  const int qid[3] = {opts->q_nm1, opts->q_n, opts->q_np1};
+  for (int k = 0; k < 3; ++k) {
+    if ((rc = nodal(rid[k], 1, &F.rho[k])) || (rc = nodal(vid[k], 1, &F.dnv[k])))
+      return rc;
+    if (kind != NW_MASS_CONTINUITY)
+      if ((rc = nodal(qid[k], kind == NW_MASS_MOMENTUM ? nd : 1, &F.q[k])))
+        return rc;
+  }
+  if (kind == NW_MASS_MOMENTUM)
+    if ((rc = nodal(opts->dpdx, nd, &F.dpdx)))
+      return rc;
+  cudaStream_t s = mesh->ctx->stream;
+  if (!ls->nodeRowsBuilt) {
+    std::vector<int64_t> rows;
+    const int ndof = uvw ? 1 : ls->numDof;
+    for (int64_t n = 0; n < mp.nNodes; ++n) {
+      if (!mesh->nodeKernelActive[n])
+        continue;
+      /* the applier tests the skipped-row map with the first dof's row id
+       * (src/HypreLinearSystem.C:2095-2099) */
+      if (std::binary_search(
+            g.skippedRows.begin(), g.skippedRows.end(), mp.nodeHid[n] * ndof))
+        continue;
+      for (int d = 0; d < ndof; ++d) {
+        const int64_t hid = mp.nodeHid[n] * ndof + d;
+        const int64_t lr = hid - g.iLower; /* owned by the selector */
+        const int64_t a = g.rowStartOwned[lr], len = g.rowStartOwned[lr + 1] - a;
+        const int64_t* rc2 = g.cols.data() + a;
+        const int64_t* p = std::lower_bound(rc2, rc2 + len, hid);
+        if (p == rc2 + len || *p != hid)
+          return fail(NW_ERR_STATE, "nw_assemble_mass_bdf_node: row without diagonal");
+        rows.push_back(mp.slotOfNode[n]);
+        rows.push_back(a + (p - rc2));
+        rows.push_back(lr);
+        rows.push_back(uvw ? -1 : (ls->numDof > 1 ? d : 0));
+      }
+    }
+    ls->nNodeRows = (int64_t)rows.size() / 4;
+    if ((rc = upload(ls->dNodeRows, rows, s, nullptr)))
+      return rc;
+    NW_CUDA(cudaStreamSynchronize(s));
+    ls->nodeRowsBuilt = true;
+  }
+  if (ls->state != NW_LS_ACCUM)
+    if ((rc = materialize_zero(ls)))
+      return rc;
+  NW_CUDA(launch_mass_bdf_node(
+    kind, nd, ls->dNodeRows.as<int64_t>(), ls->nNodeRows, F, opts->dt,
+    opts->gamma1, opts->gamma2, opts->gamma3, ls->dev.values, ls->dev.rhs,
+    ls->dev.rhsStride, s));
+  return NW_OK;
 }
 
 extern "C" int

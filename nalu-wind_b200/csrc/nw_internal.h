@@ -185,6 +185,8 @@ struct nw_mesh
   std::map<std::string, int> fieldByName;
   nw_node_halo halo;
   std::map<int64_t, int32_t> ownedNodeOfHid; /* own row id -> local node */
+  /* node-kernel selector: locally owned and not a periodic slave */
+  std::vector<uint8_t> nodeKernelActive;
   int64_t planBytes = 0;
 };
 
@@ -216,6 +218,11 @@ struct nw_linsys
   nw::DevBuf dRowStartOwned, dRowStartShared, dRowIndicesShared, dCols,
     dSkipped, dNodeHid;
   nw::DevBuf dNormPartial, dNormOut;
+  /* node-kernel scatter table (lazy): int64[n][4] = slot, diagonal value
+   * offset, rhs row, dof (-1: UVW, all rhs columns) */
+  bool nodeRowsBuilt = false;
+  int64_t nNodeRows = 0;
+  nw::DevBuf dNodeRows;
 
   /* shared-row halo (multi-rank) */
   struct Peer

@@ -1664,6 +1664,54 @@ row_init_kernel(
     rhs[(int64_t)d * rhsStride + r] = 0.0;
 }
 
+/* time-derivative node kernels (src/node_kernels/{Scalar,Momentum,Continuity}
+ * MassBDFNodeKernel.C): one thread per (node, row), plain read-modify-write --
+ * every selected node owns its rows */
+template <int KIND>
+__global__ void
+mass_bdf_node_kernel(
+  int ndim, const int64_t* __restrict__ rows, int64_t nRows,
+  const MassBdfFields f, double dt, double gamma1, double gamma2,
+  double gamma3, double* values, double* rhs, int64_t rhsStride)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nRows)
+    return;
+  const int64_t slot = rows[4 * t], diagOff = rows[4 * t + 1],
+                rr = rows[4 * t + 2], dof = rows[4 * t + 3];
+  const double rhoNm1 = f.rho[0][slot], rhoN = f.rho[1][slot],
+               rhoNp1 = f.rho[2][slot];
+  const double dnvNm1 = f.dnv[0][slot], dnvN = f.dnv[1][slot],
+               dnvNp1 = f.dnv[2][slot];
+  if (KIND == NW_MASS_SCALAR) {
+    const double qNm1 = f.q[0][slot], qN = f.q[1][slot], qNp1 = f.q[2][slot];
+    const double lhsTime = gamma1 * rhoNp1 * dnvNp1 / dt;
+    rhs[rr] -= (gamma1 * rhoNp1 * qNp1 * dnvNp1 + gamma2 * qN * rhoN * dnvN +
+                gamma3 * qNm1 * rhoNm1 * dnvNm1) /
+               dt;
+    values[diagOff] += lhsTime;
+  } else if (KIND == NW_MASS_MOMENTUM) {
+    const double lhsfac = gamma1 * rhoNp1 * dnvNp1 / dt;
+    const int i0 = dof < 0 ? 0 : (int)dof, i1 = dof < 0 ? ndim : (int)dof + 1;
+    for (int i = i0; i < i1; ++i) {
+      const int64_t o = (int64_t)i * f.fieldStride + slot;
+      const double uNm1 = f.q[0][o], uN = f.q[1][o], uNp1 = f.q[2][o];
+      const double dpdx = f.dpdx[o];
+      const int64_t ri = dof < 0 ? (int64_t)i * rhsStride + rr : rr;
+      rhs[ri] += -(gamma1 * rhoNp1 * uNp1 * dnvNp1 + gamma2 * rhoN * uN * dnvN +
+                   gamma3 * rhoNm1 * uNm1 * dnvNm1) /
+                   dt -
+                 dpdx * dnvNp1;
+    }
+    /* lhs(i,i) += lhsfac; the UVW system keeps the x-x entry only */
+    values[diagOff] += lhsfac;
+  } else {
+    rhs[rr] -= (gamma1 * rhoNp1 * dnvNp1 + gamma2 * rhoN * dnvN +
+                gamma3 * rhoNm1 * dnvNm1) /
+               dt * (gamma1 / dt);
+  }
+}
+
 /* CoeffApplier::resetRows: rows[t] = (value offset, length, diagonal position
  * or -1, rhs row): zero the row, diagonal = diagValue, every rhs column =
  * rhsResidual (src/HypreLinearSystem.C:2262-2315) */
@@ -2585,6 +2633,27 @@ launch_row_init(
     return cudaSuccess;
   row_init_kernel<<<blocks_for(nRows, 128), 128, 0, s>>>(
     rows, nRows, rowPtr, isPeriodic, values, rhs, rhsStride, nRhs);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_mass_bdf_node(
+  int kind, int ndim, const int64_t* rows, int64_t nRows,
+  const MassBdfFields& f, double dt, double gamma1, double gamma2,
+  double gamma3, double* values, double* rhs, int64_t rhsStride, cudaStream_t s)
+{
+  if (nRows == 0)
+    return cudaSuccess;
+  const int nb = blocks_for(nRows, 256);
+  if (kind == NW_MASS_SCALAR)
+    mass_bdf_node_kernel<NW_MASS_SCALAR><<<nb, 256, 0, s>>>(
+      ndim, rows, nRows, f, dt, gamma1, gamma2, gamma3, values, rhs, rhsStride);
+  else if (kind == NW_MASS_MOMENTUM)
+    mass_bdf_node_kernel<NW_MASS_MOMENTUM><<<nb, 256, 0, s>>>(
+      ndim, rows, nRows, f, dt, gamma1, gamma2, gamma3, values, rhs, rhsStride);
+  else
+    mass_bdf_node_kernel<NW_MASS_CONTINUITY><<<nb, 256, 0, s>>>(
+      ndim, rows, nRows, f, dt, gamma1, gamma2, gamma3, values, rhs, rhsStride);
   return cudaGetLastError();
 }
 

@@ -134,6 +134,22 @@ cudaError_t launch_row_init(
   const int32_t* rows, int nRows, const int64_t* rowPtr /* [R+1] */,
   const uint8_t* isPeriodic, double* values, double* rhs, int64_t rhsStride,
   int nRhs, cudaStream_t s);
+/* mass-BDF node kernels; rows: int64[n][4] = slot, diagonal value offset, rhs
+ * row, dof (-1: UVW system, all rhs columns).  q / rho / dnv: the NM1, N, NP1
+ * states (SoA, stride fieldStride). */
+struct MassBdfFields
+{
+  const double* q[3];
+  const double* rho[3];
+  const double* dnv[3];
+  const double* dpdx;
+  int64_t fieldStride;
+};
+cudaError_t launch_mass_bdf_node(
+  int kind, int ndim, const int64_t* rows, int64_t nRows,
+  const MassBdfFields& f, double dt, double gamma1, double gamma2,
+  double gamma3, double* values, double* rhs, int64_t rhsStride,
+  cudaStream_t s);
 /* CoeffApplier::resetRows; rows: int64[nRows][4] = value offset, length,
  * diagonal position (-1: none), rhs row */
 cudaError_t launch_reset_rows(

@@ -729,6 +729,75 @@ orc_applier_apply(
       lhs + e * n * n, n);
 }
 
+/* ---- node kernels (AssembleNGPNodeSolverAlgorithm::execute,
+ * src/AssembleNGPNodeSolverAlgorithm.C:85-146: per selected node zero the
+ * 1-node block, run the kernel, hand it to the CoeffApplier) ---- */
+
+/* ScalarMassBDFNodeKernel::execute, src/node_kernels/ScalarMassBDFNodeKernel.C:72-96 */
+extern "C" void
+orc_scalar_mass_bdf_node(
+  int64_t n_sel, const int32_t* nodes, const double* qNm1, const double* qN,
+  const double* qNp1, const double* rhoNm1, const double* rhoN,
+  const double* rhoNp1, const double* dnvNm1, const double* dnvN,
+  const double* dnvNp1, double dt, double gamma1, double gamma2, double gamma3,
+  orc_applier* a)
+{
+  for (int64_t i = 0; i < n_sel; ++i) {
+    const int32_t n = nodes[i];
+    double lhs = 0.0, rhs = 0.0;
+    const double lhsTime = gamma1 * rhoNp1[n] * dnvNp1[n] / dt;
+    rhs -= (gamma1 * rhoNp1[n] * qNp1[n] * dnvNp1[n] +
+            gamma2 * qN[n] * rhoN[n] * dnvN[n] +
+            gamma3 * qNm1[n] * rhoNm1[n] * dnvNm1[n]) /
+           dt;
+    lhs += lhsTime;
+    a->apply(1, &n, &rhs, &lhs, 1);
+  }
+}
+
+/* MomentumMassBDFNodeKernel::execute, src/node_kernels/MomentumMassBDFNodeKernel.C:80-107 */
+extern "C" void
+orc_momentum_mass_bdf_node(
+  int ndim, int64_t n_sel, const int32_t* nodes, const double* uNm1,
+  const double* uN, const double* uNp1, const double* rhoNm1,
+  const double* rhoN, const double* rhoNp1, const double* dnvNm1,
+  const double* dnvN, const double* dnvNp1, const double* dpdx, double dt,
+  double gamma1, double gamma2, double gamma3, orc_applier* a)
+{
+  for (int64_t q = 0; q < n_sel; ++q) {
+    const int32_t n = nodes[q];
+    double lhs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, rhs[3] = {0, 0, 0};
+    const double lhsfac = gamma1 * rhoNp1[n] * dnvNp1[n] / dt;
+    for (int i = 0; i < ndim; ++i) {
+      rhs[i] += -(gamma1 * rhoNp1[n] * uNp1[n * ndim + i] * dnvNp1[n] +
+                  gamma2 * rhoN[n] * uN[n * ndim + i] * dnvN[n] +
+                  gamma3 * rhoNm1[n] * uNm1[n * ndim + i] * dnvNm1[n]) /
+                  dt -
+                dpdx[n * ndim + i] * dnvNp1[n];
+      lhs[i * ndim + i] += lhsfac;
+    }
+    a->apply(1, &n, rhs, lhs, ndim);
+  }
+}
+
+/* ContinuityMassBDFNodeKernel::execute, src/node_kernels/ContinuityMassBDFNodeKernel.C:63-84 */
+extern "C" void
+orc_continuity_mass_bdf_node(
+  int64_t n_sel, const int32_t* nodes, const double* rhoNm1, const double* rhoN,
+  const double* rhoNp1, const double* dnvNm1, const double* dnvN,
+  const double* dnvNp1, double dt, double gamma1, double gamma2, double gamma3,
+  orc_applier* a)
+{
+  for (int64_t i = 0; i < n_sel; ++i) {
+    const int32_t n = nodes[i];
+    double lhs = 0.0, rhs = 0.0;
+    rhs -= (gamma1 * rhoNp1[n] * dnvNp1[n] + gamma2 * rhoN[n] * dnvN[n] +
+            gamma3 * rhoNm1[n] * dnvNm1[n]) /
+           dt * (gamma1 / dt);
+    a->apply(1, &n, &rhs, &lhs, 1);
+  }
+}
+
 /* HypreLinSysCoeffApplier::reset_rows (src/HypreLinearSystem.C:2262-2315) /
  * HypreUVWLinSysCoeffApplier::reset_rows (src/HypreUVWLinearSystem.C:787-835):
  * zero the rows of the given nodes, diagonal = diag_value, rhs = rhs_residual */

@@ -128,6 +128,27 @@ void orc_applier_hypre_dirichlet(
   orc_applier*, int64_t n_nodes, const int32_t* nodes, const double* solution,
   const double* bc_values, int ncomp);
 
+/* node kernels through AssembleNGPNodeSolverAlgorithm
+ * (src/AssembleNGPNodeSolverAlgorithm.C:85-146); nodes = selected local nodes
+ * (locally owned, not periodic slaves); fields in the reference layout */
+void orc_scalar_mass_bdf_node(
+  int64_t n_sel, const int32_t* nodes, const double* qNm1, const double* qN,
+  const double* qNp1, const double* rhoNm1, const double* rhoN,
+  const double* rhoNp1, const double* dnvNm1, const double* dnvN,
+  const double* dnvNp1, double dt, double gamma1, double gamma2, double gamma3,
+  orc_applier*);
+void orc_momentum_mass_bdf_node(
+  int ndim, int64_t n_sel, const int32_t* nodes, const double* uNm1,
+  const double* uN, const double* uNp1, const double* rhoNm1,
+  const double* rhoN, const double* rhoNp1, const double* dnvNm1,
+  const double* dnvN, const double* dnvNp1, const double* dpdx, double dt,
+  double gamma1, double gamma2, double gamma3, orc_applier*);
+void orc_continuity_mass_bdf_node(
+  int64_t n_sel, const int32_t* nodes, const double* rhoNm1, const double* rhoN,
+  const double* rhoNp1, const double* dnvNm1, const double* dnvN,
+  const double* dnvNp1, double dt, double gamma1, double gamma2, double gamma3,
+  orc_applier*);
+
 void orc_applier_destroy(orc_applier*);
 
 /* ---- edge algorithms ---- */

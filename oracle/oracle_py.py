@@ -343,3 +343,34 @@ def momentum_edge(ndim, edge_nodes, coords, vel, dudx, visc, rho, mask, area,
         ud = udiag_accum.ctypes.data_as(c_f64p)
     lib().orc_momentum_edge(ndim, en.size // 2, pe, *[a[1] for a in arrs],
                             C.byref(o), sink.h, ud)
+
+
+def _f64s(*arrs):
+    keep = [np.ascontiguousarray(a, dtype=np.float64) for a in arrs]
+    return keep, [C.c_void_p(a.ctypes.data) for a in keep]
+
+
+def scalar_mass_bdf_node(nodes, q3, rho3, dnv3, dt, g1, g2, g3, sink):
+    """ScalarMassBDFNodeKernel over `nodes`; q3/rho3/dnv3 = (Nm1, N, Np1)"""
+    nd = np.ascontiguousarray(nodes, dtype=np.int32)
+    keep, ptrs = _f64s(*q3, *rho3, *dnv3)
+    f = lib().orc_scalar_mass_bdf_node
+    f.argtypes = [C.c_int64, C.c_void_p] + [C.c_void_p] * 9 + [C.c_double] * 4 + [C.c_void_p]
+    f(nd.size, nd.ctypes.data, *ptrs, dt, g1, g2, g3, sink.h)
+
+
+def momentum_mass_bdf_node(ndim, nodes, u3, rho3, dnv3, dpdx, dt, g1, g2, g3, sink):
+    nd = np.ascontiguousarray(nodes, dtype=np.int32)
+    keep, ptrs = _f64s(*u3, *rho3, *dnv3, dpdx)
+    f = lib().orc_momentum_mass_bdf_node
+    f.argtypes = ([C.c_int, C.c_int64, C.c_void_p] + [C.c_void_p] * 10 +
+                  [C.c_double] * 4 + [C.c_void_p])
+    f(ndim, nd.size, nd.ctypes.data, *ptrs, dt, g1, g2, g3, sink.h)
+
+
+def continuity_mass_bdf_node(nodes, rho3, dnv3, dt, g1, g2, g3, sink):
+    nd = np.ascontiguousarray(nodes, dtype=np.int32)
+    keep, ptrs = _f64s(*rho3, *dnv3)
+    f = lib().orc_continuity_mass_bdf_node
+    f.argtypes = [C.c_int64, C.c_void_p] + [C.c_void_p] * 6 + [C.c_double] * 4 + [C.c_void_p]
+    f(nd.size, nd.ctypes.data, *ptrs, dt, g1, g2, g3, sink.h)

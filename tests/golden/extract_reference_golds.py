@@ -102,6 +102,17 @@ def main():
             "rhs": flat(f, kind + "_rhs_serial"),
         }
 
+    # node kernels through the same CoeffApplier boundary
+    f = strip_comments(open(os.path.join(
+        REF, "unit_tests/node_kernels/UnitTestScalarMassBDFNodeKernel.C")).read())
+    out["scalar_mass_bdf_node"] = {
+        "rhs": flat(f, "rhs[8]"), "lhs": matrix(f, "lhs[8][8]", 8)}
+    f = strip_comments(open(os.path.join(
+        REF, "unit_tests/node_kernels/UnitTestMomentumMassBDFNodeKernel.C")).read())
+    out["momentum_mass_bdf_node"] = {"rhs": flat(f, "rhs[24]"), "lhs_diag": 1.25}
+    # UnitTestContinuityMassBDFNodeKernel.C:45: expect_all_near(rhs, -12.5)
+    out["continuity_mass_bdf_node"] = {"rhs_all": -12.5}
+
     f = strip_comments(open(os.path.join(
         REF, "unit_tests/ngp_algorithms/UnitTestNodalGradAlg.C")).read())
     i0 = f.index("NGP_nodal_grad_edge)")

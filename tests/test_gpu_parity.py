@@ -333,6 +333,151 @@ def test_gold_fix_pressure_and_dirichlet(P, ctx):
     ls.close()
 
 
+def test_gold_mass_bdf_node_kernels(P, ctx):
+    """the reference's node-kernel golds (UnitTestScalarMassBDFNodeKernel.C,
+    UnitTestMomentumMassBDFNodeKernel.C, UnitTestContinuityMassBDFNodeKernel.C;
+    dt = 0.1, gamma = (1, -1, 0), only StateNP1 initialised) through
+    nw_assemble_mass_bdf_node"""
+    m, c, e = _cube_mesh(P, ctx)
+    n = len(c)
+    z, rho, visc = uc.mixture_fraction_fields(c)
+    zero = np.zeros(n)
+    m.put("zero", P.NW_NODE, zero)
+    m.put("zero3", P.NW_NODE, np.zeros((n, 3)))
+    m.put("dnv", P.NW_NODE, np.full(n, 0.125))
+    m.put("z", P.NW_NODE, z)
+    m.put("rho_mix", P.NW_NODE, rho)
+    m.put("one", P.NW_NODE, np.ones(n))
+    m.put("velocity", P.NW_NODE, uc.velocity(c))
+    m.put("dpdx", P.NW_NODE, uc.dpdx(c))
+    dnv3 = ("dnv", "dnv", "dnv")
+    gam = (1.0, -1.0, 0.0)
+
+    def system(kind=P.NW_LINSYS_HYPRE, nd=1):
+        ls = P.LinearSystem(m, kind, nd)
+        ls.buildEdgeToNodeGraph()
+        ls.finalizeLinearSystem()
+        ls.zeroSystem()
+        return ls
+
+    def dense(ls, vals):
+        g = ls.graph()
+        d = np.zeros((n, n))
+        d[g["rows"], g["cols"]] = vals
+        return d
+
+    ls = system()
+    ls.assemble_mass_bdf_node(P.NW_MASS_SCALAR, 0.1, gam, q=("zero", "zero", "z"),
+                              rho=("zero", "zero", "rho_mix"), dnv=dnv3)
+    vals, rhs = ls.values()
+    gold = G["scalar_mass_bdf_node"]
+    assert np.max(np.abs(dense(ls, vals) - np.array(gold["lhs"]))) <= 1e-12
+    assert np.max(np.abs(rhs[0] - np.array(gold["rhs"]))) <= 1e-12
+    ls.close()
+
+    ls = system(P.NW_LINSYS_HYPRE_UVW, 3)
+    ls.assemble_mass_bdf_node(P.NW_MASS_MOMENTUM, 0.1, gam,
+                              q=("zero3", "zero3", "velocity"),
+                              rho=("zero", "zero", "one"), dnv=dnv3, dpdx="dpdx")
+    vals, rhs = ls.values()
+    gold = G["momentum_mass_bdf_node"]
+    assert np.max(np.abs(dense(ls, vals) - gold["lhs_diag"] * np.eye(n))) <= 1e-12
+    assert np.max(np.abs(rhs.T.ravel() - np.array(gold["rhs"]))) <= 1e-12
+    ls.close()
+
+    ls = system()
+    ls.assemble_mass_bdf_node(P.NW_MASS_CONTINUITY, 0.1, gam,
+                              rho=("zero", "zero", "one"), dnv=dnv3)
+    vals, rhs = ls.values()
+    assert np.max(np.abs(vals)) == 0.0
+    assert np.max(np.abs(rhs[0] - G["continuity_mass_bdf_node"]["rhs_all"])) <= 1e-12
+    ls.close()
+
+
+@pytest.mark.parametrize("kind", ["scalar", "momentum_uvw", "momentum_mono",
+                                  "continuity"])
+def test_mass_bdf_node_after_edge_assembly_vs_oracle(P, ctx, kind):
+    """node kernels accumulate on top of the edge assembly, skip Dirichlet rows
+    and periodic slaves (AssembleNGPNodeSolverAlgorithm.C:108-111), vs oracle"""
+    case = pu.Case(dims=(7, 6, 5), periodic=(True, False),
+                   lengths=(7.0, 6.0, 5.0))
+    mesh = case.box.make_mesh(ctx, tile_nodes=48)
+    pu.upload_state(P, mesh, case)
+    f, b = case.fields, case.box
+    rng = np.random.default_rng(11)
+    nn = case.n_nodes
+    extra = {"rho_n": f["density"] * 0.98, "rho_nm1": f["density"] * 0.97,
+             "u_n": f["velocity"] * 0.9, "u_nm1": f["velocity"] * 0.8,
+             "k_n": f["turbulent_ke"] * 0.9, "k_nm1": f["turbulent_ke"] * 0.85,
+             "dnv_n": f["dual_nodal_volume"] * 1.01,
+             "dnv_nm1": f["dual_nodal_volume"] * 1.02}
+    for k, v in extra.items():
+        mesh.put(k, P.NW_NODE, v)
+    dt, gam = 0.5, (1.5, -2.0, 0.5)
+    rho3 = ("rho_nm1", "rho_n", "density")
+    dnv3 = ("dnv_nm1", "dnv_n", "dual_nodal_volume")
+    orho = (extra["rho_nm1"], extra["rho_n"], f["density"])
+    odnv = (extra["dnv_nm1"], extra["dnv_n"], f["dual_nodal_volume"])
+    active = np.flatnonzero((b.own_hid == b.hid)).astype(np.int32)
+    ndof = 3 if kind == "momentum_mono" else 1
+    own_rows = np.unique(b.hid)
+    skipped_nodes = np.sort(rng.choice(own_rows, 6, replace=False))
+    skipped = (skipped_nodes[:, None] * ndof + np.arange(ndof)).ravel().astype(np.int64)
+    g = case.oracle_graph(num_dof=ndof, skipped=skipped)
+    uvw = kind == "momentum_uvw"
+    sink = orc.HypreSink(g, b.hid, uvw_ndim=3 if uvw else 0)
+    ls = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE_UVW if uvw else P.NW_LINSYS_HYPRE,
+                        3 if kind.startswith("momentum") else 1)
+    ls.set_skipped_rows(skipped)
+    ls.buildEdgeToNodeGraph()
+    ls.finalizeLinearSystem()
+    ls.zeroSystem()
+    if kind == "continuity":
+        ls.assemble_continuity_edge(**pu.CONT_OPTS)
+        orc.continuity_edge(3, case.edges, b.coords, f["velocity"], f["dpdx"],
+                            f["density"], f["pressure"], f["momentum_diag"],
+                            case.area, sink, **pu.CONT_OPTS)
+        ls.assemble_mass_bdf_node(P.NW_MASS_CONTINUITY, dt, gam, rho=rho3, dnv=dnv3)
+        orc.continuity_mass_bdf_node(active, orho, odnv, dt, *gam, sink)
+    elif kind == "scalar":
+        mesh.upload("mass_flow_rate", case.oracle_mdot())
+        ls.assemble_scalar_edge("turbulent_ke", "dkdx", "effective_viscosity_tke",
+                                pf=P.peclet_fn("tanh", 2.0, 1.0), **pu.SCAL_OPTS)
+        orc.scalar_edge(3, case.edges, b.coords, f["velocity"], f["turbulent_ke"],
+                        f["dkdx"], f["density"], f["effective_viscosity_tke"],
+                        case.area, case.oracle_mdot(), sink,
+                        pf=orc.peclet("tanh", 2.0, 1.0), **pu.SCAL_OPTS)
+        ls.assemble_mass_bdf_node(P.NW_MASS_SCALAR, dt, gam,
+                                  q=("k_nm1", "k_n", "turbulent_ke"), rho=rho3,
+                                  dnv=dnv3)
+        orc.scalar_mass_bdf_node(active, (extra["k_nm1"], extra["k_n"],
+                                          f["turbulent_ke"]), orho, odnv, dt,
+                                 *gam, sink)
+    else:
+        omdot = case.oracle_mdot()
+        opec = case.oracle_pecfac(orc.peclet("classic", 1.0))
+        mesh.upload("mass_flow_rate", omdot)
+        mesh.upload("peclet_factor", opec)
+        ls.assemble_momentum_edge("viscosity", **pu.MOM_OPTS)
+        orc.momentum_edge(3, case.edges, b.coords, f["velocity"], f["dudx"],
+                          f["viscosity"], f["density"],
+                          f["abl_wall_no_slip_wall_func_node_mask"], case.area,
+                          omdot, opec, sink, **pu.MOM_OPTS)
+        ls.assemble_mass_bdf_node(P.NW_MASS_MOMENTUM, dt, gam,
+                                  q=("u_nm1", "u_n", "velocity"), rho=rho3,
+                                  dnv=dnv3, dpdx="dpdx")
+        orc.momentum_mass_bdf_node(3, active, (extra["u_nm1"], extra["u_n"],
+                                               f["velocity"]), orho, odnv,
+                                   f["dpdx"], dt, *gam, sink)
+    vals, r = ls.values()
+    ov, orhs = sink.get()
+    av_, arhs = sink.get_abs()
+    assert pu.scaled_err(vals, ov, av_) < 1
+    assert pu.scaled_err(r, orhs, arhs) < 1
+    ls.close()
+    mesh.close()
+
+
 @pytest.mark.parametrize("kind", ["hypre", "uvw"])
 def test_sum_into_reset_rows_dirichlet_vs_oracle(P, ctx, kind):
     """generic CoeffApplier entry (include/LinearSystem.h:62-70) + resetRows +

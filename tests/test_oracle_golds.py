@@ -243,3 +243,52 @@ def test_scalar_dirichlet_gold():
     dense[np.arange(n), g.cols[:n]] = vals
     assert np.array_equal(dense, dense_gold)
     assert np.max(np.abs(rhs[0] - np.array(gold["rhs"]))) <= 1e-12
+
+
+def _bdf_states(x):
+    """the unit-test fixtures only initialise StateNP1; N / NM1 stay zero"""
+    z = np.zeros_like(x)
+    return (z, z, x)
+
+
+def test_scalar_mass_bdf_node_gold():
+    """UnitTestScalarMassBDFNodeKernel.C:106-150 (dt = 0.1, gamma = 1, -1, 0)"""
+    c, e, av, z, rho, visc, vel = _scalar_case(1)
+    n = len(c)
+    dnv = np.full(n, 0.125)
+    sink = orc.DenseSink(n, 1)
+    orc.scalar_mass_bdf_node(np.arange(n), _bdf_states(z), _bdf_states(rho),
+                             (dnv, dnv, dnv), 0.1, 1.0, -1.0, 0.0, sink)
+    lhs, rhs = sink.get()
+    gold = G["scalar_mass_bdf_node"]
+    assert np.max(np.abs(lhs - np.array(gold["lhs"]))) <= 1e-12
+    assert np.max(np.abs(rhs - np.array(gold["rhs"]))) <= 1e-12
+
+
+def test_momentum_mass_bdf_node_gold():
+    """UnitTestMomentumMassBDFNodeKernel.C:51-100: lhs = 1.25 I, rhs gold"""
+    c, e = uc.mesh(1)
+    n = len(c)
+    vel, dp = uc.velocity(c), uc.dpdx(c)
+    rho, dnv = np.ones(n), np.full(n, 0.125)
+    sink = orc.DenseSink(n, 3)
+    orc.momentum_mass_bdf_node(3, np.arange(n), _bdf_states(vel),
+                               _bdf_states(rho), (dnv, dnv, dnv), dp, 0.1, 1.0,
+                               -1.0, 0.0, sink)
+    lhs, rhs = sink.get()
+    gold = G["momentum_mass_bdf_node"]
+    assert np.max(np.abs(lhs - gold["lhs_diag"] * np.eye(3 * n))) <= 1e-12
+    assert np.max(np.abs(rhs - np.array(gold["rhs"]))) <= 1e-12
+
+
+def test_continuity_mass_bdf_node_gold():
+    """UnitTestContinuityMassBDFNodeKernel.C:17-46: rhs = -12.5 everywhere"""
+    c, e = uc.mesh(1)
+    n = len(c)
+    rho, dnv = np.ones(n), np.full(n, 0.125)
+    sink = orc.DenseSink(n, 1)
+    orc.continuity_mass_bdf_node(np.arange(n), _bdf_states(rho), (dnv, dnv, dnv),
+                                 0.1, 1.0, -1.0, 0.0, sink)
+    lhs, rhs = sink.get()
+    assert np.max(np.abs(lhs)) == 0.0
+    assert np.max(np.abs(rhs - G["continuity_mass_bdf_node"]["rhs_all"])) <= 1e-12
