@@ -362,6 +362,15 @@ int nw_linsys_sum_into(
   const double* d_lhs,
   const double* d_rhs);
 
+/* Poisson system of the SST minimum wall distance:
+ * WallDistEdgeSolverAlg::execute (src/edge_kernels/WallDistEdgeSolverAlg.C:28-66,
+ * lhs = asq/axdx [[+1,-1],[-1,+1]], no rhs; same tile / atomic kernels as the
+ * other edge systems) and WallDistNodeKernel::execute
+ * (src/node_kernels/WallDistNodeKernel.C:34-43, rhs += dual_nodal_volume on
+ * owned non-slave nodes). */
+int nw_assemble_wall_dist_edge(nw_linsys* ls);
+int nw_assemble_wall_dist_node(nw_linsys* ls, int dual_nodal_volume_field);
+
 /* Time-derivative node kernels through AssembleNGPNodeSolverAlgorithm
  * (src/AssembleNGPNodeSolverAlgorithm.C:85-146: every locally-owned node that
  * is not a periodic slave; 1-node block zeroed, kernel, CoeffApplier):

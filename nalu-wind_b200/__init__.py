@@ -121,7 +121,8 @@ ABI_SYMBOLS = [
     "nw_linsys_get_edge_slots", "nw_linsys_zero",
     "nw_linsys_set_scatter_mode", "nw_assemble_continuity_edge",
     "nw_assemble_scalar_edge", "nw_assemble_momentum_edge",
-    "nw_assemble_mass_bdf_node", "nw_linsys_sum_into", "nw_linsys_reset_rows",
+    "nw_assemble_mass_bdf_node", "nw_assemble_wall_dist_edge",
+    "nw_assemble_wall_dist_node", "nw_linsys_sum_into", "nw_linsys_reset_rows",
     "nw_linsys_apply_dirichlet_bcs", "nw_linsys_load_complete",
     "nw_linsys_device_arrays", "nw_linsys_get_values", "nw_linsys_rhs_norm2",
     "nw_mesh_halo_send_count", "nw_mesh_halo_get_send", "nw_mesh_halo_set_recv",
@@ -198,6 +199,8 @@ def lib():
     L.nw_linsys_sum_into.argtypes = [vp, C.c_int64, C.c_int, vp, vp, vp]
     L.nw_linsys_reset_rows.argtypes = [vp, C.c_int64, vp, C.c_double, C.c_double]
     L.nw_assemble_mass_bdf_node.argtypes = [vp, C.c_int, C.POINTER(MassBdfOpts)]
+    L.nw_assemble_wall_dist_edge.argtypes = [vp]
+    L.nw_assemble_wall_dist_node.argtypes = [vp, C.c_int]
     L.nw_linsys_apply_dirichlet_bcs.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp]
     L.nw_linsys_load_complete.argtypes = [vp]
     L.nw_linsys_device_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(vp),
@@ -511,6 +514,12 @@ class LinearSystem:
         o.dnv_nm1, o.dnv_n, o.dnv_np1 = (fid(x) for x in dnv)
         o.dpdx = fid(dpdx) if dpdx is not None else -1
         _chk(lib().nw_assemble_mass_bdf_node(self.h, kind, C.byref(o)))
+
+    def assemble_wall_dist_edge(self):
+        _chk(lib().nw_assemble_wall_dist_edge(self.h))
+
+    def assemble_wall_dist_node(self, dnv="dual_nodal_volume"):
+        _chk(lib().nw_assemble_wall_dist_node(self.h, self.mesh.field_id(dnv)))
 
     def sumInto(self, entity_nodes, lhs, rhs):
         """generic CoeffApplier::operator(): entity_nodes [nEnt][npe] local node

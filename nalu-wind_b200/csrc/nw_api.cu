@@ -1220,6 +1220,50 @@ local_row_of(const Graph& g, int64_t hid)
   return g.numRowsOwned + (it - g.rowIndicesShared.begin());
 }
 
+/* scatter table of the node algorithms (AssembleNGPNodeSolverAlgorithm's
+ * selector + the applier's skipped-row test), built once per system */
+static int
+build_node_rows(nw_linsys* ls)
+{
+  if (ls->nodeRowsBuilt)
+    return NW_OK;
+  nw_mesh* mesh = ls->mesh;
+  const MeshPlan& mp = mesh->plan;
+  const Graph& g = ls->g;
+  const bool uvw = ls->kind == NW_LINSYS_HYPRE_UVW;
+  cudaStream_t s = mesh->ctx->stream;
+  std::vector<int64_t> rows;
+  const int ndof = uvw ? 1 : ls->numDof;
+  for (int64_t n = 0; n < mp.nNodes; ++n) {
+    if (!mesh->nodeKernelActive[n])
+      continue;
+    /* the applier tests the skipped-row map with the first dof's row id
+     * (src/HypreLinearSystem.C:2095-2099) */
+    if (std::binary_search(
+          g.skippedRows.begin(), g.skippedRows.end(), mp.nodeHid[n] * ndof))
+      continue;
+    for (int d = 0; d < ndof; ++d) {
+      const int64_t hid = mp.nodeHid[n] * ndof + d;
+      const int64_t lr = hid - g.iLower; /* owned by the selector */
+      const int64_t a = g.rowStartOwned[lr], len = g.rowStartOwned[lr + 1] - a;
+      const int64_t* rc2 = g.cols.data() + a;
+      const int64_t* p = std::lower_bound(rc2, rc2 + len, hid);
+      if (p == rc2 + len || *p != hid)
+        return fail(NW_ERR_STATE, "node algorithm: row without a diagonal entry");
+      rows.push_back(mp.slotOfNode[n]);
+      rows.push_back(a + (p - rc2));
+      rows.push_back(lr);
+      rows.push_back(uvw ? -1 : (ls->numDof > 1 ? d : 0));
+    }
+  }
+  ls->nNodeRows = (int64_t)rows.size() / 4;
+  if (int rc = upload(ls->dNodeRows, rows, s, nullptr))
+    return rc;
+  NW_CUDA(cudaStreamSynchronize(s));
+  ls->nodeRowsBuilt = true;
+  return NW_OK;
+}
+
 extern "C" int
 nw_assemble_mass_bdf_node(nw_linsys* ls, int kind, const nw_mass_bdf_opts* opts)
 {
@@ -1262,37 +1306,8 @@ nw_assemble_mass_bdf_node(nw_linsys* ls, int kind, const nw_mass_bdf_opts* opts)
     if ((rc = nodal(opts->dpdx, nd, &F.dpdx)))
       return rc;
   cudaStream_t s = mesh->ctx->stream;
-  if (!ls->nodeRowsBuilt) {
-    std::vector<int64_t> rows;
-    const int ndof = uvw ? 1 : ls->numDof;
-    for (int64_t n = 0; n < mp.nNodes; ++n) {
-      if (!mesh->nodeKernelActive[n])
-        continue;
-      /* the applier tests the skipped-row map with the first dof's row id
-       * (src/HypreLinearSystem.C:2095-2099) */
-      if (std::binary_search(
-            g.skippedRows.begin(), g.skippedRows.end(), mp.nodeHid[n] * ndof))
-        continue;
-      for (int d = 0; d < ndof; ++d) {
-        const int64_t hid = mp.nodeHid[n] * ndof + d;
-        const int64_t lr = hid - g.iLower; /* owned by the selector */
-        const int64_t a = g.rowStartOwned[lr], len = g.rowStartOwned[lr + 1] - a;
-        const int64_t* rc2 = g.cols.data() + a;
-        const int64_t* p = std::lower_bound(rc2, rc2 + len, hid);
-        if (p == rc2 + len || *p != hid)
-          return fail(NW_ERR_STATE, "nw_assemble_mass_bdf_node: row without diagonal");
-        rows.push_back(mp.slotOfNode[n]);
-        rows.push_back(a + (p - rc2));
-        rows.push_back(lr);
-        rows.push_back(uvw ? -1 : (ls->numDof > 1 ? d : 0));
-      }
-    }
-    ls->nNodeRows = (int64_t)rows.size() / 4;
-    if ((rc = upload(ls->dNodeRows, rows, s, nullptr)))
-      return rc;
-    NW_CUDA(cudaStreamSynchronize(s));
-    ls->nodeRowsBuilt = true;
-  }
+  if ((rc = build_node_rows(ls)))
+    return rc;
   if (ls->state != NW_LS_ACCUM)
     if ((rc = materialize_zero(ls)))
       return rc;
@@ -1300,6 +1315,56 @@ nw_assemble_mass_bdf_node(nw_linsys* ls, int kind, const nw_mass_bdf_opts* opts)
     kind, nd, ls->dNodeRows.as<int64_t>(), ls->nNodeRows, F, opts->dt,
     opts->gamma1, opts->gamma2, opts->gamma3, ls->dev.values, ls->dev.rhs,
     ls->dev.rhsStride, s));
+  return NW_OK;
+}
+
+extern "C" int
+nw_assemble_wall_dist_edge(nw_linsys* ls)
+{
+  if (int rc = ls_ready(ls, "nw_assemble_wall_dist_edge"))
+    return rc;
+  if (ls->numDof != 1 || ls->kind != NW_LINSYS_HYPRE)
+    return fail(
+      NW_ERR_ARG, "nw_assemble_wall_dist_edge: needs a 1-dof hypre system");
+  nw_mesh* mesh = ls->mesh;
+  NodeComps nc;
+  EdgeComps ec;
+  int rc;
+  if ((rc = bind(mesh, "coordinates", NW_NODE, mesh->plan.ndim, &nc.c[0])) ||
+      (rc = bind_edge_common(mesh, ec, false, false)))
+    return rc;
+  cudaStream_t s = mesh->ctx->stream;
+  if (use_tile_path(ls, false, &rc)) {
+    NW_CUDA(launch_wall_dist_tile(mesh->dev, ls->dev, nc, ec, s));
+    return finish_tile_assembly(ls);
+  }
+  if (rc)
+    return rc;
+  AtomicMapDev am{ls->dASlots.as<int32_t>(), ls->dARhsRows.as<int32_t>()};
+  NW_CUDA(launch_wall_dist_atomic(mesh->dev, ls->dev, am, nc, ec, s));
+  return NW_OK;
+}
+
+extern "C" int
+nw_assemble_wall_dist_node(nw_linsys* ls, int dual_nodal_volume_field)
+{
+  if (int rc = ls_ready(ls, "nw_assemble_wall_dist_node"))
+    return rc;
+  if (ls->numDof != 1 || ls->kind != NW_LINSYS_HYPRE)
+    return fail(
+      NW_ERR_ARG, "nw_assemble_wall_dist_node: needs a 1-dof hypre system");
+  nw_field_t* f = get_field(ls->mesh, dual_nodal_volume_field);
+  if (!f || f->rank != NW_NODE || f->ncomp != 1)
+    return fail(NW_ERR_ARG, "nw_assemble_wall_dist_node: bad field");
+  int rc;
+  if ((rc = build_node_rows(ls)))
+    return rc;
+  if (ls->state != NW_LS_ACCUM)
+    if ((rc = materialize_zero(ls)))
+      return rc;
+  NW_CUDA(launch_wall_dist_node(
+    ls->dNodeRows.as<int64_t>(), ls->nNodeRows, f->buf.as<double>(),
+    ls->dev.rhs, ls->mesh->ctx->stream));
   return NW_OK;
 }
 

@@ -366,6 +366,63 @@ struct ContinuityP
   }
 };
 
+/* WallDistEdgeSolverAlg (src/edge_kernels/WallDistEdgeSolverAlg.C:28-66):
+ * lhsfac = asq / axdx, lhs = [[+f, -f], [-f, +f]], no rhs.  Stages the
+ * coordinates only. */
+struct nw_wall_dist_opts_
+{
+  int unused;
+};
+template <int ND>
+struct WallDistP
+{
+  static constexpr int kND = ND;
+  static constexpr bool kPairLanes = false;
+  static constexpr int NC = ND; /* x */
+  static constexpr int kPhaseId = 7;
+  static constexpr int kMinBlocks = 3;
+  static constexpr int kStreamCtas = 3;
+  static constexpr int NRES = 1;
+  static constexpr int NR = 1;
+  static constexpr bool kNeedsMdot = false;
+  static constexpr bool kNeedsPec = false;
+  using Opts = nw_wall_dist_opts_;
+  template <class LD>
+  __device__ __forceinline__ static void compute(
+    const LD& ld, int l, int r, const double* av, double, double, const Opts&,
+    double* res)
+  {
+    double asq = 0.0, axdx = 0.0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      const double dxj = ld(d, r) - ld(d, l);
+      asq += av[d] * av[d];
+      axdx += av[d] * dxj;
+    }
+    /* an exact divide: this kernel is nowhere near any arithmetic limit */
+    res[0] = asq / axdx;
+  }
+  __device__ __forceinline__ static void contrib(
+    uint32_t, const double* s_res, int, int j, double& diag, double& off,
+    double* rhs)
+  {
+    const double f = s_res[j];
+    diag = f;
+    off = -f;
+    rhs[0] = 0.0;
+  }
+  __device__ __forceinline__ static void block(
+    const double* res, double& LL, double& LR, double& RL, double& RR,
+    double* flux)
+  {
+    LL = res[0];
+    LR = -res[0];
+    RL = -res[0];
+    RR = res[0];
+    flux[0] = 0.0;
+  }
+};
+
 template <int ND>
 struct ScalarP
 {
@@ -1712,6 +1769,17 @@ mass_bdf_node_kernel(
   }
 }
 
+/* WallDistNodeKernel (src/node_kernels/WallDistNodeKernel.C:34-43): rhs += V */
+__global__ void
+wall_dist_node_kernel(
+  const int64_t* __restrict__ rows, int64_t nRows,
+  const double* __restrict__ dualVol, double* rhs)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nRows)
+    rhs[rows[4 * t + 2]] += dualVol[rows[4 * t]];
+}
+
 /* CoeffApplier::resetRows: rows[t] = (value offset, length, diagonal position
  * or -1, rhs row): zero the row, diagonal = diagValue, every rhs column =
  * rhsResidual (src/HypreLinearSystem.C:2262-2315) */
@@ -2453,6 +2521,27 @@ launch_continuity_tile(
 }
 
 cudaError_t
+launch_wall_dist_tile(
+  const MeshPlanDev& mp, const LsPlanDev& lp, const NodeComps& nc,
+  const EdgeComps& ec, cudaStream_t s)
+{
+  const nw_wall_dist_opts_ o{0};
+  return mp.ndim == 3 ? launch_ls_tile<WallDistP<3>, 3>(mp, lp, nc, ec, o, s)
+                      : launch_ls_tile<WallDistP<2>, 2>(mp, lp, nc, ec, o, s);
+}
+
+cudaError_t
+launch_wall_dist_atomic(
+  const MeshPlanDev& mp, const LsPlanDev& lp, const AtomicMapDev& am,
+  const NodeComps& nc, const EdgeComps& ec, cudaStream_t s)
+{
+  const nw_wall_dist_opts_ o{0};
+  return mp.ndim == 3
+           ? launch_ls_atomic<WallDistP<3>, 3>(mp, lp, am, nc, ec, o, nullptr, s)
+           : launch_ls_atomic<WallDistP<2>, 2>(mp, lp, am, nc, ec, o, nullptr, s);
+}
+
+cudaError_t
 launch_scalar_tile(
   const MeshPlanDev& mp,
   const LsPlanDev& lp,
@@ -2654,6 +2743,18 @@ launch_mass_bdf_node(
   else
     mass_bdf_node_kernel<NW_MASS_CONTINUITY><<<nb, 256, 0, s>>>(
       ndim, rows, nRows, f, dt, gamma1, gamma2, gamma3, values, rhs, rhsStride);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_wall_dist_node(
+  const int64_t* rows, int64_t nRows, const double* dualVol, double* rhs,
+  cudaStream_t s)
+{
+  if (nRows == 0)
+    return cudaSuccess;
+  wall_dist_node_kernel<<<blocks_for(nRows, 256), 256, 0, s>>>(
+    rows, nRows, dualVol, rhs);
   return cudaGetLastError();
 }
 

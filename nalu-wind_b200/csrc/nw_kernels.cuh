@@ -86,6 +86,16 @@ cudaError_t launch_grad_tile(
 cudaError_t launch_continuity_tile(
   const MeshPlanDev& mp, const LsPlanDev& lp, const NodeComps& nc,
   const EdgeComps& ec, nw_continuity_opts o, cudaStream_t s);
+/* WallDistEdgeSolverAlg: coordinates in nc.c[0..ndim), area in ec */
+cudaError_t launch_wall_dist_tile(
+  const MeshPlanDev& mp, const LsPlanDev& lp, const NodeComps& nc,
+  const EdgeComps& ec, cudaStream_t s);
+cudaError_t launch_wall_dist_atomic(
+  const MeshPlanDev& mp, const LsPlanDev& lp, const AtomicMapDev& am,
+  const NodeComps& nc, const EdgeComps& ec, cudaStream_t s);
+cudaError_t launch_wall_dist_node(
+  const int64_t* rows, int64_t nRows, const double* dualVol, double* rhs,
+  cudaStream_t s);
 cudaError_t launch_scalar_tile(
   const MeshPlanDev& mp, const LsPlanDev& lp, const NodeComps& nc,
   const EdgeComps& ec, nw_scalar_opts o, cudaStream_t s);

@@ -1095,6 +1095,45 @@ orc_nodal_grad_edge(
 /*  ContinuityEdgeSolverAlg                                            */
 /* ------------------------------------------------------------------ */
 
+/* WallDistEdgeSolverAlg::execute, src/edge_kernels/WallDistEdgeSolverAlg.C:28-66 */
+extern "C" void
+orc_wall_dist_edge(
+  int ndim, int64_t n_edges, const int32_t* edge_nodes, const double* coords,
+  const double* edge_area, orc_applier* sink)
+{
+  ORC_EDGE_LOOP
+  for (int64_t e = 0; e < n_edges; ++e) {
+    const int32_t nodes[2] = {edge_nodes[2 * e], edge_nodes[2 * e + 1]};
+    const int64_t nL = nodes[0], nR = nodes[1];
+    double asq = 0.0, axdx = 0.0;
+    for (int d = 0; d < ndim; d++) {
+      const double axj = edge_area[e * ndim + d];
+      const double dxj = coords[nR * ndim + d] - coords[nL * ndim + d];
+      asq += axj * axj;
+      axdx += axj * dxj;
+    }
+    const double pfac = 1.0;
+    const double lhsfac = pfac * asq / axdx;
+    const double lhs[4] = {+lhsfac, -lhsfac, -lhsfac, +lhsfac};
+    const double rhs[2] = {0.0, 0.0};
+    sink->apply(2, nodes, rhs, lhs, 2);
+  }
+}
+
+/* WallDistNodeKernel::execute, src/node_kernels/WallDistNodeKernel.C:34-43 */
+extern "C" void
+orc_wall_dist_node(
+  int64_t n_sel, const int32_t* nodes, const double* dual_nodal_volume,
+  orc_applier* a)
+{
+  for (int64_t i = 0; i < n_sel; ++i) {
+    const int32_t n = nodes[i];
+    double lhs = 0.0, rhs = 0.0;
+    rhs += dual_nodal_volume[n];
+    a->apply(1, &n, &rhs, &lhs, 1);
+  }
+}
+
 extern "C" void
 orc_continuity_edge(
   int ndim,

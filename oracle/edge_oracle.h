@@ -149,6 +149,16 @@ void orc_continuity_mass_bdf_node(
   const double* dnvNp1, double dt, double gamma1, double gamma2, double gamma3,
   orc_applier*);
 
+/* src/edge_kernels/WallDistEdgeSolverAlg.C:28-66 and
+ * src/node_kernels/WallDistNodeKernel.C:34-43 (Poisson system of the SST
+ * minimum wall distance) */
+void orc_wall_dist_edge(
+  int ndim, int64_t n_edges, const int32_t* edge_nodes, const double* coords,
+  const double* edge_area, orc_applier* sink);
+void orc_wall_dist_node(
+  int64_t n_sel, const int32_t* nodes, const double* dual_nodal_volume,
+  orc_applier*);
+
 void orc_applier_destroy(orc_applier*);
 
 /* ---- edge algorithms ---- */

@@ -374,3 +374,19 @@ def continuity_mass_bdf_node(nodes, rho3, dnv3, dt, g1, g2, g3, sink):
     f = lib().orc_continuity_mass_bdf_node
     f.argtypes = [C.c_int64, C.c_void_p] + [C.c_void_p] * 6 + [C.c_double] * 4 + [C.c_void_p]
     f(nd.size, nd.ctypes.data, *ptrs, dt, g1, g2, g3, sink.h)
+
+
+def wall_dist_edge(ndim, edge_nodes, coords, area, sink):
+    en = np.ascontiguousarray(edge_nodes, dtype=np.int32)
+    keep, ptrs = _f64s(coords, area)
+    f = lib().orc_wall_dist_edge
+    f.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    f(ndim, en.size // 2, en.ctypes.data, *ptrs, sink.h)
+
+
+def wall_dist_node(nodes, dnv, sink):
+    nd = np.ascontiguousarray(nodes, dtype=np.int32)
+    keep, ptrs = _f64s(dnv)
+    f = lib().orc_wall_dist_node
+    f.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    f(nd.size, nd.ctypes.data, *ptrs, sink.h)

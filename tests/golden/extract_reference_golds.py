@@ -102,6 +102,11 @@ def main():
             "rhs": flat(f, kind + "_rhs_serial"),
         }
 
+    # WallDistEdgeSolverAlg: pure 2x2 Laplacian, no rhs
+    f = strip_comments(open(os.path.join(
+        REF, "unit_tests/edge_kernels/UnitTestWallDistEdgeSolver.C")).read())
+    out["wall_dist_edge"] = {"lhs": matrix(f, "lhs[8][8]", 8)}
+
     # node kernels through the same CoeffApplier boundary
     f = strip_comments(open(os.path.join(
         REF, "unit_tests/node_kernels/UnitTestScalarMassBDFNodeKernel.C")).read())

@@ -478,6 +478,50 @@ def test_mass_bdf_node_after_edge_assembly_vs_oracle(P, ctx, kind):
     mesh.close()
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_wall_dist_system(P, ctx, mode):
+    """WallDistEdgeSolverAlg + WallDistNodeKernel: the reference's 8x8 gold on
+    the unit cube, and a synthetic warped case vs the oracle"""
+    m, c, e = _cube_mesh(P, ctx)
+    n = len(c)
+    m.put("edge_area_vector", P.NW_EDGE, uc.edge_area(c, e))
+    ls = P.LinearSystem(m)
+    ls.set_scatter_mode(mode)
+    ls.buildEdgeToNodeGraph()
+    ls.finalizeLinearSystem()
+    ls.zeroSystem()
+    ls.assemble_wall_dist_edge()
+    vals, rhs = ls.values()
+    g = ls.graph()
+    dense = np.zeros((n, n))
+    dense[g["rows"], g["cols"]] = vals
+    assert np.max(np.abs(dense - np.array(G["wall_dist_edge"]["lhs"]))) <= 1e-12
+    assert np.max(np.abs(rhs)) == 0.0
+    ls.close()
+    m.close()
+    case = pu.Case(dims=(9, 8, 7), warp=0.15, shuffle_bucket=128)
+    mesh = case.box.make_mesh(ctx, tile_nodes=64)
+    pu.upload_state(P, mesh, case)
+    gg = case.oracle_graph()
+    sink = orc.HypreSink(gg, case.box.hid)
+    orc.wall_dist_edge(3, case.edges, case.box.coords, case.area, sink)
+    orc.wall_dist_node(np.arange(case.n_nodes), case.fields["dual_nodal_volume"], sink)
+    ls = P.LinearSystem(mesh)
+    ls.set_scatter_mode(mode)
+    ls.buildEdgeToNodeGraph()
+    ls.finalizeLinearSystem()
+    ls.zeroSystem()
+    ls.assemble_wall_dist_edge()
+    ls.assemble_wall_dist_node()
+    vals, rhs = ls.values()
+    ov, orhs = sink.get()
+    av_, arhs = sink.get_abs()
+    assert pu.scaled_err(vals, ov, av_) < 1
+    assert pu.scaled_err(rhs, orhs, arhs) < 1
+    ls.close()
+    mesh.close()
+
+
 @pytest.mark.parametrize("kind", ["hypre", "uvw"])
 def test_sum_into_reset_rows_dirichlet_vs_oracle(P, ctx, kind):
     """generic CoeffApplier entry (include/LinearSystem.h:62-70) + resetRows +

@@ -292,3 +292,14 @@ def test_continuity_mass_bdf_node_gold():
     lhs, rhs = sink.get()
     assert np.max(np.abs(lhs)) == 0.0
     assert np.max(np.abs(rhs - G["continuity_mass_bdf_node"]["rhs_all"])) <= 1e-12
+
+
+def test_wall_dist_edge_gold():
+    """UnitTestWallDistEdgeSolver.C:103-125: 2x2 Laplacian blocks, no rhs"""
+    c, e = uc.mesh(1)
+    n = len(c)
+    sink = orc.DenseSink(n, 1)
+    orc.wall_dist_edge(3, e, c, uc.edge_area(c, e), sink)
+    lhs, rhs = sink.get()
+    assert np.max(np.abs(lhs - np.array(G["wall_dist_edge"]["lhs"]))) <= 1e-12
+    assert np.max(np.abs(rhs)) == 0.0
