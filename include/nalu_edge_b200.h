@@ -451,6 +451,24 @@ int nw_linsys_get_extra(
 
 /* LinearSystem::loadComplete (src/HypreLinearSystem.C:1848-1889): the
  * shared-row halo sum.  Single rank: no-op. */
+/* The reference's pre-assembly dump (solver option
+ * write_preassembly_matrix_files; HypreLinearSystem::hypreIJMatrixSetAddToValues
+ * src/HypreLinearSystem.C:1517-1568, hypreIJVectorSetAddToValues :1625-1661,
+ * HypreUVWLinearSystem.C:135-166), byte for byte, so that a site with a real
+ * nalu-wind build can diff this library's assembly against its own:
+ *   <eq>.IJM.<n>.mat.<rank%05d>.preassem.{i,j,v,meta}
+ *   <eq>[d].IJV.<n>.rhs.<rank%05d>.preassem.{i,v,meta}   ([d] for UVW systems)
+ * i/j: HypreIntType row / column ids of the owned entries followed by the
+ * shared tail; v: doubles; mat meta = {globalNumRows, iLower, iUpper,
+ * nnzOwned, nnzShared, nnzOwned+nnzShared}; rhs meta = {rowsOwned, rowsShared,
+ * rowsOwned+rowsShared}.  Like the reference, call it before
+ * nw_linsys_load_complete (the state hypre would receive).  hypre_int_bytes =
+ * sizeof(HYPRE_Int) of the build to compare with (4, or 8 for bigint).
+ * `directory` may be NULL (current directory).  Synchronises the stream. */
+int nw_linsys_write_preassembly_files(
+  nw_linsys* ls, const char* directory, const char* eq_sys_name,
+  int write_counter, int hypre_int_bytes);
+
 int nw_linsys_load_complete(nw_linsys* ls);
 /* transport nw_linsys_load_complete uses (nw_halo_transport) */
 int nw_linsys_halo_transport(const nw_linsys* ls);

@@ -122,7 +122,7 @@ ABI_SYMBOLS = [
     "nw_linsys_set_scatter_mode", "nw_assemble_continuity_edge",
     "nw_assemble_scalar_edge", "nw_assemble_momentum_edge",
     "nw_assemble_mass_bdf_node", "nw_assemble_wall_dist_edge",
-    "nw_assemble_wall_dist_node", "nw_linsys_sum_into", "nw_linsys_reset_rows",
+    "nw_assemble_wall_dist_node", "nw_linsys_write_preassembly_files", "nw_linsys_sum_into", "nw_linsys_reset_rows",
     "nw_linsys_apply_dirichlet_bcs", "nw_linsys_load_complete",
     "nw_linsys_device_arrays", "nw_linsys_get_values", "nw_linsys_rhs_norm2",
     "nw_mesh_halo_send_count", "nw_mesh_halo_get_send", "nw_mesh_halo_set_recv",
@@ -200,6 +200,8 @@ def lib():
     L.nw_linsys_reset_rows.argtypes = [vp, C.c_int64, vp, C.c_double, C.c_double]
     L.nw_assemble_mass_bdf_node.argtypes = [vp, C.c_int, C.POINTER(MassBdfOpts)]
     L.nw_assemble_wall_dist_edge.argtypes = [vp]
+    L.nw_linsys_write_preassembly_files.argtypes = [vp, C.c_char_p, C.c_char_p,
+                                                    C.c_int, C.c_int]
     L.nw_assemble_wall_dist_node.argtypes = [vp, C.c_int]
     L.nw_linsys_apply_dirichlet_bcs.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp]
     L.nw_linsys_load_complete.argtypes = [vp]
@@ -546,6 +548,12 @@ class LinearSystem:
         _chk(lib().nw_linsys_apply_dirichlet_bcs(
             self.h, self.mesh.field_id(solution), self.mesh.field_id(bc_values),
             nd.size, _ptr(nd)))
+
+    def write_preassembly_files(self, directory, eq_sys_name, write_counter=1,
+                                hypre_int_bytes=4):
+        _chk(lib().nw_linsys_write_preassembly_files(
+            self.h, str(directory).encode(), eq_sys_name.encode(),
+            write_counter, hypre_int_bytes))
 
     def loadComplete(self):
         _chk(lib().nw_linsys_load_complete(self.h))

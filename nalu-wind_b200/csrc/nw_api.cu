@@ -1526,6 +1526,95 @@ nw_linsys_sum_into(
   return NW_OK;
 }
 
+static bool
+write_ints(const std::string& path, const std::vector<int64_t>& v, int bytes)
+{
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f)
+    return false;
+  bool ok = true;
+  if (bytes == 8) {
+    ok = v.empty() || fwrite(v.data(), 8, v.size(), f) == v.size();
+  } else {
+    std::vector<int32_t> w(v.begin(), v.end());
+    ok = w.empty() || fwrite(w.data(), 4, w.size(), f) == w.size();
+  }
+  return fclose(f) == 0 && ok;
+}
+
+static bool
+write_doubles(const std::string& path, const double* v, size_t n)
+{
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f)
+    return false;
+  const bool ok = n == 0 || fwrite(v, 8, n, f) == n;
+  return fclose(f) == 0 && ok;
+}
+
+extern "C" int
+nw_linsys_write_preassembly_files(
+  nw_linsys* ls, const char* directory, const char* eq_sys_name,
+  int write_counter, int hypre_int_bytes)
+{
+  if (int rc = ls_ready(ls, "nw_linsys_write_preassembly_files"))
+    return rc;
+  if (!eq_sys_name || (hypre_int_bytes != 4 && hypre_int_bytes != 8))
+    return fail(NW_ERR_ARG, "nw_linsys_write_preassembly_files: bad argument");
+  if (ls->state == NW_LS_LAZY_ZERO)
+    if (int rc = materialize_zero(ls))
+      return rc;
+  const Graph& g = ls->g;
+  const MeshPlan& mp = ls->mesh->plan;
+  cudaStream_t s = ls->mesh->ctx->stream;
+  const int64_t nnz = g.nnzOwned + g.nnzShared;
+  const int64_t nrows = g.numRowsOwned + g.numRowsShared;
+  std::vector<double> vals(nnz), rhs((size_t)nrows * ls->nRhs);
+  if (nnz)
+    NW_CUDA(cudaMemcpyAsync(
+      vals.data(), ls->dev.values, sizeof(double) * nnz, cudaMemcpyDeviceToHost, s));
+  for (int d = 0; d < ls->nRhs; ++d)
+    if (nrows)
+      NW_CUDA(cudaMemcpyAsync(
+        rhs.data() + (size_t)d * nrows, ls->dev.rhs + (int64_t)d * ls->dev.rhsStride,
+        sizeof(double) * nrows, cudaMemcpyDeviceToHost, s));
+  NW_CUDA(cudaStreamSynchronize(s));
+  char rank_str[16];
+  snprintf(rank_str, sizeof(rank_str), "%05d", mp.rank);
+  const std::string dir =
+    (directory && *directory) ? std::string(directory) + "/" : std::string();
+  const std::string cnt = std::to_string(write_counter);
+  const std::string mat =
+    dir + eq_sys_name + ".IJM." + cnt + ".mat." + rank_str + ".preassem.";
+  const int ib = hypre_int_bytes;
+  const std::vector<int64_t> meta = {
+    mp.hypreOffsets.back() * g.numDof, g.iLower, g.iUpper, g.nnzOwned,
+    g.nnzShared, nnz};
+  bool ok = write_ints(mat + "i", g.rows, ib) && write_ints(mat + "j", g.cols, ib) &&
+            write_doubles(mat + "v", vals.data(), (size_t)nnz) &&
+            write_ints(mat + "meta", meta, ib);
+  /* rhs rows: owned rows ascending, then the shared tail (:963-984) */
+  std::vector<int64_t> rrows(nrows);
+  for (int64_t i = 0; i < g.numRowsOwned; ++i)
+    rrows[i] = g.iLower + i;
+  for (int64_t i = 0; i < g.numRowsShared; ++i)
+    rrows[g.numRowsOwned + i] = g.rowIndicesShared[i];
+  const std::vector<int64_t> rmeta = {g.numRowsOwned, g.numRowsShared, nrows};
+  const bool uvw = ls->kind == NW_LINSYS_HYPRE_UVW;
+  for (int d = 0; d < ls->nRhs && ok; ++d) {
+    const std::string vec = dir + eq_sys_name + (uvw ? std::to_string(d) : "") +
+                            ".IJV." + cnt + ".rhs." + rank_str + ".preassem.";
+    ok = write_ints(vec + "i", rrows, ib) &&
+         write_doubles(vec + "v", rhs.data() + (size_t)d * nrows, (size_t)nrows) &&
+         write_ints(vec + "meta", rmeta, ib);
+  }
+  if (!ok)
+    return fail(
+      NW_ERR_ARG, "nw_linsys_write_preassembly_files: cannot write under '" +
+                    dir + "'");
+  return NW_OK;
+}
+
 extern "C" int
 nw_linsys_device_arrays(
   nw_linsys* ls, double** values, double** rhs, int64_t* rhs_stride)

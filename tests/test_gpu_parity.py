@@ -565,6 +565,53 @@ def test_sum_into_reset_rows_dirichlet_vs_oracle(P, ctx, kind):
     mesh.close()
 
 
+@pytest.mark.parametrize("int_bytes", [4, 8])
+def test_preassembly_files_round_trip(P, ctx, tmp_path, int_bytes):
+    """the reference's write_preassembly_matrix_files dump
+    (src/HypreLinearSystem.C:1517-1568, 1625-1661; HypreUVWLinearSystem.C:135-166):
+    file names, integer width, entry order and meta words"""
+    case = pu.Case(dims=(5, 4, 3))
+    mesh = case.box.make_mesh(ctx, tile_nodes=32)
+    pu.upload_state(P, mesh, case)
+    mesh.upload("mass_flow_rate", case.oracle_mdot())
+    mesh.upload("peclet_factor",
+                case.oracle_pecfac(orc.peclet("classic", 1.0)))
+    it = np.int32 if int_bytes == 4 else np.int64
+    for kind, nd, name in ((P.NW_LINSYS_HYPRE, 1, "ContinuityEQS"),
+                           (P.NW_LINSYS_HYPRE_UVW, 3, "MomentumEQS")):
+        ls = P.LinearSystem(mesh, kind, nd)
+        ls.buildEdgeToNodeGraph()
+        ls.finalizeLinearSystem()
+        ls.zeroSystem()
+        if nd == 1:
+            ls.assemble_continuity_edge(**pu.CONT_OPTS)
+        else:
+            ls.assemble_momentum_edge("viscosity", **pu.MOM_OPTS)
+        ls.write_preassembly_files(tmp_path, name, 7, int_bytes)
+        vals, rhs = ls.values()
+        g = ls.graph()
+        s = ls.sizes
+        base = tmp_path / ("%s.IJM.7.mat.00000.preassem." % name)
+        nnz = s.num_nonzeros_owned + s.num_nonzeros_shared
+        assert np.array_equal(np.fromfile(str(base) + "i", dtype=it), g["rows"])
+        assert np.array_equal(np.fromfile(str(base) + "j", dtype=it), g["cols"])
+        assert np.array_equal(np.fromfile(str(base) + "v"), vals[:nnz])
+        meta = np.fromfile(str(base) + "meta", dtype=it)
+        assert meta.tolist() == [case.n_nodes, s.i_lower, s.i_upper,
+                                 s.num_nonzeros_owned, s.num_nonzeros_shared, nnz]
+        nrows = s.num_rows_owned + s.num_rows_shared
+        for d in range(3 if nd == 3 else 1):
+            tag = name + (str(d) if nd == 3 else "")
+            vb = tmp_path / ("%s.IJV.7.rhs.00000.preassem." % tag)
+            assert np.array_equal(np.fromfile(str(vb) + "i", dtype=it),
+                                  np.arange(s.i_lower, s.i_upper + 1))
+            assert np.array_equal(np.fromfile(str(vb) + "v"), rhs[d][:nrows])
+            assert np.fromfile(str(vb) + "meta", dtype=it).tolist() == [
+                s.num_rows_owned, s.num_rows_shared, nrows]
+        ls.close()
+    mesh.close()
+
+
 def test_staged_upload_matches_upload(P, ctx):
     """nw_field_stage (copy stream) + nw_field_commit leaves the same bits in
     the field as nw_field_upload, also when re-staged back to back"""
