@@ -362,6 +362,23 @@ int nw_linsys_sum_into(
   const double* d_lhs,
   const double* d_rhs);
 
+/* GeometryInteriorAlg<AlgTraitsHex8> (src/ngp_algorithms/GeometryInteriorAlg.C:
+ * 72-112 dual nodal volume, 165-225 edge area vectors; HexSCV / HexSCS
+ * determinants src/master_element/Hex8CVFEM.C:365-390, 567-592) on the device,
+ * so that a moving-mesh run refreshes the geometric inputs of the edge
+ * kernels without the host.  elem_nodes: host array [n_elems][8] of local node
+ * indices in the Hex8 node order.  Volumes are accumulated from the elements
+ * flagged in elem_owned (NULL: all; the reference's locally_owned selector --
+ * follow with nw_field_parallel_sum), area vectors from every element given,
+ * into the mesh's (locally owned) edges with the reference's sign rule (left
+ * sub-control-volume node == first edge node).  Accumulates with fp64 atomics:
+ * zero the fields first (GeometryAlgDriver::pre_work) with nw_field_fill.
+ * Either field id may be -1.  coordinates_field: the (current) coordinates. */
+int nw_geometry_interior_hex8(
+  nw_mesh* mesh, int64_t n_elems, const int32_t* elem_nodes,
+  const unsigned char* elem_owned, int coordinates_field,
+  int dual_nodal_volume_field, int edge_area_vector_field);
+
 /* Poisson system of the SST minimum wall distance:
  * WallDistEdgeSolverAlg::execute (src/edge_kernels/WallDistEdgeSolverAlg.C:28-66,
  * lhs = asq/axdx [[+1,-1],[-1,+1]], no rhs; same tile / atomic kernels as the

@@ -114,7 +114,7 @@ ABI_SYMBOLS = [
     "nw_mesh_create", "nw_mesh_destroy", "nw_mesh_get_stats",
     "nw_field_register", "nw_field_find", "nw_field_upload",
     "nw_field_stage", "nw_field_commit", "nw_field_download", "nw_field_fill", "nw_field_device_view",
-    "nw_mesh_get_node_permutation", "nw_mdot_edge", "nw_peclet_edge",
+    "nw_mesh_get_node_permutation", "nw_geometry_interior_hex8", "nw_mdot_edge", "nw_peclet_edge",
     "nw_nodal_grad_edge", "nw_linsys_create", "nw_linsys_destroy",
     "nw_linsys_set_skipped_rows", "nw_linsys_build_edge_to_node_graph",
     "nw_linsys_finalize", "nw_linsys_get_sizes", "nw_linsys_get_graph",
@@ -179,6 +179,8 @@ def lib():
                                        C.POINTER(C.c_int64)]
     L.nw_mesh_get_node_permutation.argtypes = [vp, C.POINTER(C.c_int64), c_i32p]
     L.nw_mdot_edge.argtypes = [vp, C.POINTER(MdotOpts)]
+    L.nw_geometry_interior_hex8.argtypes = [vp, C.c_int64, vp, vp, C.c_int,
+                                            C.c_int, C.c_int]
     L.nw_peclet_edge.argtypes = [vp, C.c_int, C.POINTER(PecletOpts)]
     L.nw_nodal_grad_edge.argtypes = [vp, C.c_int, C.c_int]
     L.nw_linsys_create.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
@@ -385,6 +387,18 @@ class Mesh:
     def peclet_edge(self, viscosity="viscosity", pf=None, eps=1e-16):
         o = PecletOpts(pf or peclet_fn(), eps)
         _chk(lib().nw_peclet_edge(self.h, self.field_id(viscosity), C.byref(o)))
+
+    def geometry_interior_hex8(self, elem_nodes, dnv=None, area=None,
+                               coords="coordinates", elem_owned=None):
+        """GeometryInteriorAlg<Hex8>: accumulate dual nodal volumes / edge area
+        vectors (zero the fields first)"""
+        el = np.ascontiguousarray(elem_nodes, dtype=np.int32)
+        ow = None if elem_owned is None else np.ascontiguousarray(
+            elem_owned, dtype=np.uint8)
+        _chk(lib().nw_geometry_interior_hex8(
+            self.h, len(el), _ptr(el), None if ow is None else _ptr(ow),
+            self.field_id(coords), -1 if dnv is None else self.field_id(dnv),
+            -1 if area is None else self.field_id(area)))
 
     def nodal_grad_edge(self, phi, grad):
         _chk(lib().nw_nodal_grad_edge(self.h, self.field_id(phi),

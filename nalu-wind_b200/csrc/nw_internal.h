@@ -179,12 +179,21 @@ struct nw_mesh
   nw::MeshPlan plan;
   nw::MeshPlanDev dev;
   nw::DevBuf dTiles, dHalo, dLr, dHeNode, dWarpNode, dPrimary, dNodeOfSlot,
-    dTileEdgeSrc, dPrimarySlot;
+    dTileEdgeSrc, dPrimarySlot, dSecondSlot;
   nw::DevBuf scratch; /* staging for field upload / download */
   std::vector<std::unique_ptr<nw_field_t>> fields;
   std::map<std::string, int> fieldByName;
   nw_node_halo halo;
   std::map<int64_t, int32_t> ownedNodeOfHid; /* own row id -> local node */
+  /* GeometryInteriorAlg tables of the last element block (cached: a moving
+   * mesh calls every step with the same connectivity) */
+  struct GeoCache
+  {
+    int64_t nElems = -1;
+    uint64_t hash = 0;
+    nw::DevBuf dElemSlots, dElemEdges, dOwned;
+    bool hasOwned = false;
+  } geo;
   /* node-kernel selector: locally owned and not a periodic slave */
   std::vector<uint8_t> nodeKernelActive;
   int64_t planBytes = 0;

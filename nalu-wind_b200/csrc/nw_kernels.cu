@@ -1721,6 +1721,151 @@ row_init_kernel(
     rhs[(int64_t)d * rhsStride + r] = 0.0;
 }
 
+/* ---- GeometryInteriorAlg<Hex8>: dual nodal volumes and edge area vectors ----
+ * (src/ngp_algorithms/GeometryInteriorAlg.C:72-112, 165-225).  One thread per
+ * element.  The 27 points of the 8-hex subdivision (corners, edge / face /
+ * body mid points, Hex8GeometryFunctions.h:258-325) are averages of corner
+ * subsets, kept as bit masks; sub-control-volume volumes use Grandy's 24
+ * triangle formula (:83-158), sub-control-surface areas the 4-triangle fan
+ * about the facet mid point (:33-81), both in the reference's summation order.
+ */
+__constant__ unsigned char kHexSubMask[27] = {
+  0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40, 0x80, /* corners 0..7 */
+  0x03, 0x06, 0x0c, 0x09, 0x0f,                   /* face 0: edges + centre */
+  0x30, 0x60, 0xc0, 0x90, 0xf0,                   /* face 1 */
+  0x22, 0x11, 0x33,                               /* face 2 */
+  0x88, 0x44, 0xcc,                               /* face 3 */
+  0x66, 0x99,                                     /* faces 4, 5 */
+  0xff};                                          /* centroid */
+__constant__ unsigned char kHexScvTable[8][8] = {
+  {0, 8, 12, 11, 19, 20, 26, 25},  {8, 1, 9, 12, 20, 18, 24, 26},
+  {12, 9, 2, 10, 26, 24, 22, 23},  {11, 12, 10, 3, 25, 26, 23, 21},
+  {19, 20, 26, 25, 4, 13, 17, 16}, {20, 18, 24, 26, 13, 5, 14, 17},
+  {26, 24, 22, 23, 17, 14, 6, 15}, {25, 26, 23, 21, 16, 17, 15, 7}};
+__constant__ unsigned char kHexScsTable[12][4] = {
+  {20, 8, 12, 26},  {24, 9, 12, 26},  {10, 12, 26, 23}, {11, 25, 26, 12},
+  {13, 20, 26, 17}, {17, 14, 24, 26}, {17, 15, 23, 26}, {16, 17, 26, 25},
+  {19, 20, 26, 25}, {20, 18, 24, 26}, {22, 23, 26, 24}, {21, 25, 26, 23}};
+__constant__ unsigned char kGrandyFace[6][4] = {
+  {0, 3, 2, 1}, {4, 5, 6, 7}, {0, 1, 5, 4}, {2, 3, 7, 6}, {1, 2, 6, 5}, {0, 4, 3, 7}};
+__constant__ unsigned char kGrandyTri[24][3] = {
+  {0, 8, 1},  {8, 2, 1},  {3, 2, 8},  {3, 8, 0},  {6, 9, 5},  {7, 9, 6},
+  {4, 9, 7},  {4, 5, 9},  {10, 0, 1}, {5, 10, 1}, {4, 10, 5}, {4, 0, 10},
+  {7, 6, 11}, {6, 2, 11}, {2, 3, 11}, {3, 7, 11}, {6, 12, 2}, {5, 12, 6},
+  {5, 1, 12}, {1, 2, 12}, {0, 4, 13}, {4, 7, 13}, {7, 3, 13}, {3, 0, 13}};
+
+__global__ void __launch_bounds__(128) geometry_hex8_kernel(
+  int64_t nElems, const int32_t* __restrict__ elemSlots /* [n][8] */,
+  const int32_t* __restrict__ elemEdges /* [n][12]: 2*slot + negate, -1 none */,
+  const unsigned char* __restrict__ owned, const double* __restrict__ x,
+  int64_t xStride, double* dualVol, double* area, int64_t areaStride)
+{
+  const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (el >= nElems)
+    return;
+  double v[27][3];
+  {
+    double c[8][3];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const int64_t sl = elemSlots[8 * el + n];
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        c[n][d] = x[(int64_t)d * xStride + sl];
+    }
+    for (int p = 0; p < 27; ++p) {
+      const unsigned m = kHexSubMask[p];
+      const int cnt = __popc(m);
+      /* the reference sums the subset in ascending corner order and scales by
+       * 1, 0.5, 0.25 or 0.125 (exact powers of two) */
+      const double w = cnt == 1 ? 1.0 : (cnt == 2 ? 0.5 : (cnt == 4 ? 0.25 : 0.125));
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        double acc = 0.0;
+        bool first = true;
+        for (int n = 0; n < 8; ++n)
+          if (m & (1u << n)) {
+            acc = first ? c[n][d] : acc + c[n][d];
+            first = false;
+          }
+        v[p][d] = cnt == 1 ? acc : w * acc;
+      }
+    }
+    /* edge mid point 11 is (c3 + c0) and 16 is (c7 + c4) in the reference:
+     * addition is commutative, the bits are the same */
+  }
+  if (dualVol && (!owned || owned[el])) {
+    for (int ip = 0; ip < 8; ++ip) {
+      double cv[14][3];
+      for (int n = 0; n < 8; ++n)
+        for (int d = 0; d < 3; ++d)
+          cv[n][d] = v[kHexScvTable[ip][n]][d];
+      for (int k = 0; k < 6; ++k)
+        for (int d = 0; d < 3; ++d)
+          cv[8 + k][d] =
+            0.25 * (cv[kGrandyFace[k][0]][d] + cv[kGrandyFace[k][1]][d] +
+                    cv[kGrandyFace[k][2]][d] + cv[kGrandyFace[k][3]][d]);
+      double vol = 0.0;
+      for (int k = 0; k < 24; ++k) {
+        const int p = kGrandyTri[k][0], q = kGrandyTri[k][1], r = kGrandyTri[k][2];
+        const double m0 = cv[p][0] + cv[q][0] + cv[r][0];
+        const double m1 = cv[p][1] + cv[q][1] + cv[r][1];
+        const double m2 = cv[p][2] + cv[q][2] + cv[r][2];
+        const double d0 = (cv[q][1] - cv[p][1]) * (cv[r][2] - cv[p][2]) -
+                          (cv[r][1] - cv[p][1]) * (cv[q][2] - cv[p][2]);
+        const double d1 = (cv[r][0] - cv[p][0]) * (cv[q][2] - cv[p][2]) -
+                          (cv[q][0] - cv[p][0]) * (cv[r][2] - cv[p][2]);
+        const double d2 = (cv[q][0] - cv[p][0]) * (cv[r][1] - cv[p][1]) -
+                          (cv[r][0] - cv[p][0]) * (cv[q][1] - cv[p][1]);
+        vol += m0 * d0 + m1 * d1 + m2 * d2;
+      }
+      vol /= 18.0;
+      atomicAdd(dualVol + elemSlots[8 * el + ip], vol);
+    }
+  }
+  if (!area)
+    return;
+  for (int ip = 0; ip < 12; ++ip) {
+    const int32_t code = elemEdges[12 * el + ip];
+    if (code < 0)
+      continue;
+    const double* q0 = v[kHexScsTable[ip][0]];
+    double xm[3], r1[3], a[3] = {0.0, 0.0, 0.0};
+    for (int d = 0; d < 3; ++d) {
+      xm[d] = 0.25 * (v[kHexScsTable[ip][0]][d] + v[kHexScsTable[ip][1]][d] +
+                      v[kHexScsTable[ip][2]][d] + v[kHexScsTable[ip][3]][d]);
+      r1[d] = q0[d] - xm[d];
+    }
+    for (int it = 0; it < 4; ++it) {
+      const double* qt = v[kHexScsTable[ip][(it + 1) & 3]];
+      const double r2[3] = {qt[0] - xm[0], qt[1] - xm[1], qt[2] - xm[2]};
+      a[0] += r1[1] * r2[2] - r2[1] * r1[2];
+      a[1] += r1[2] * r2[0] - r2[2] * r1[0];
+      a[2] += r1[0] * r2[1] - r2[0] * r1[1];
+      r1[0] = r2[0];
+      r1[1] = r2[1];
+      r1[2] = r2[2];
+    }
+    const double sg = (code & 1) ? -0.5 : 0.5;
+    const int64_t slot = code >> 1;
+    for (int d = 0; d < 3; ++d)
+      atomicAdd(area + (int64_t)d * areaStride + slot, a[d] * sg);
+  }
+}
+
+/* a cut edge has a second tile-edge slot: keep it equal to the primary one */
+__global__ void
+edge_mirror_kernel(
+  const int32_t* __restrict__ primarySlot, const int32_t* __restrict__ secondSlot,
+  int64_t nEdges, int ncomp, int64_t stride, double* f)
+{
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nEdges || secondSlot[e] < 0)
+    return;
+  for (int c = 0; c < ncomp; ++c)
+    f[(int64_t)c * stride + secondSlot[e]] = f[(int64_t)c * stride + primarySlot[e]];
+}
+
 /* time-derivative node kernels (src/node_kernels/{Scalar,Momentum,Continuity}
  * MassBDFNodeKernel.C): one thread per (node, row), plain read-modify-write --
  * every selected node owns its rows */
@@ -2722,6 +2867,31 @@ launch_row_init(
     return cudaSuccess;
   row_init_kernel<<<blocks_for(nRows, 128), 128, 0, s>>>(
     rows, nRows, rowPtr, isPeriodic, values, rhs, rhsStride, nRhs);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_geometry_hex8(
+  int64_t nElems, const int32_t* elemSlots, const int32_t* elemEdges,
+  const unsigned char* owned, const double* x, int64_t xStride, double* dualVol,
+  double* area, int64_t areaStride, cudaStream_t s)
+{
+  if (nElems == 0)
+    return cudaSuccess;
+  geometry_hex8_kernel<<<blocks_for(nElems, 128), 128, 0, s>>>(
+    nElems, elemSlots, elemEdges, owned, x, xStride, dualVol, area, areaStride);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_edge_mirror(
+  const int32_t* primarySlot, const int32_t* secondSlot, int64_t nEdges,
+  int ncomp, int64_t stride, double* f, cudaStream_t s)
+{
+  if (nEdges == 0)
+    return cudaSuccess;
+  edge_mirror_kernel<<<blocks_for(nEdges, 256), 256, 0, s>>>(
+    primarySlot, secondSlot, nEdges, ncomp, stride, f);
   return cudaGetLastError();
 }
 

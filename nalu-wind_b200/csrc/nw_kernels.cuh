@@ -144,6 +144,16 @@ cudaError_t launch_row_init(
   const int32_t* rows, int nRows, const int64_t* rowPtr /* [R+1] */,
   const uint8_t* isPeriodic, double* values, double* rhs, int64_t rhsStride,
   int nRhs, cudaStream_t s);
+/* GeometryInteriorAlg<Hex8>: elemSlots [n][8] node slots, elemEdges [n][12] =
+ * 2 * primary tile-edge slot + (1: negate), -1: edge not local; accumulates
+ * with fp64 atomics (as the reference does) */
+cudaError_t launch_geometry_hex8(
+  int64_t nElems, const int32_t* elemSlots, const int32_t* elemEdges,
+  const unsigned char* owned, const double* x, int64_t xStride, double* dualVol,
+  double* area, int64_t areaStride, cudaStream_t s);
+cudaError_t launch_edge_mirror(
+  const int32_t* primarySlot, const int32_t* secondSlot, int64_t nEdges,
+  int ncomp, int64_t stride, double* f, cudaStream_t s);
 /* mass-BDF node kernels; rows: int64[n][4] = slot, diagonal value offset, rhs
  * row, dof (-1: UVW system, all rhs columns).  q / rho / dnv: the NM1, N, NP1
  * states (SoA, stride fieldStride). */

@@ -1095,6 +1095,185 @@ orc_nodal_grad_edge(
 /*  ContinuityEdgeSolverAlg                                            */
 /* ------------------------------------------------------------------ */
 
+/* ------------------------------------------------------------------ */
+/*  GeometryInteriorAlg<Hex8>                                          */
+/* ------------------------------------------------------------------ */
+namespace {
+
+/* subdivide_hex_8, include/master_element/Hex8GeometryFunctions.h:258-325 */
+void
+geo_subdivide_hex8(const double c[8][3], double v[27][3])
+{
+  for (int n = 0; n < 8; ++n)
+    for (int d = 0; d < 3; ++d)
+      v[n][d] = c[n][d];
+  for (int d = 0; d < 3; ++d) {
+    v[8][d] = 0.5 * (c[0][d] + c[1][d]);
+    v[9][d] = 0.5 * (c[1][d] + c[2][d]);
+    v[10][d] = 0.5 * (c[2][d] + c[3][d]);
+    v[11][d] = 0.5 * (c[3][d] + c[0][d]);
+    v[12][d] = 0.25 * (c[0][d] + c[1][d] + c[2][d] + c[3][d]);
+    v[13][d] = 0.5 * (c[4][d] + c[5][d]);
+    v[14][d] = 0.5 * (c[5][d] + c[6][d]);
+    v[15][d] = 0.5 * (c[6][d] + c[7][d]);
+    v[16][d] = 0.5 * (c[7][d] + c[4][d]);
+    v[17][d] = 0.25 * (c[4][d] + c[5][d] + c[6][d] + c[7][d]);
+    v[18][d] = 0.5 * (c[1][d] + c[5][d]);
+    v[19][d] = 0.5 * (c[0][d] + c[4][d]);
+    v[20][d] = 0.25 * (c[0][d] + c[1][d] + c[4][d] + c[5][d]);
+    v[21][d] = 0.5 * (c[3][d] + c[7][d]);
+    v[22][d] = 0.5 * (c[2][d] + c[6][d]);
+    v[23][d] = 0.25 * (c[2][d] + c[3][d] + c[6][d] + c[7][d]);
+    v[24][d] = 0.25 * (c[1][d] + c[2][d] + c[5][d] + c[6][d]);
+    v[25][d] = 0.25 * (c[0][d] + c[3][d] + c[4][d] + c[7][d]);
+    v[26][d] = 0.;
+    for (int n = 0; n < 8; ++n)
+      v[26][d] += c[n][d];
+    v[26][d] *= 0.125;
+  }
+}
+
+/* hex_volume_grandy, Hex8GeometryFunctions.h:83-158 */
+double
+geo_hex_volume_grandy(const double sc[8][3])
+{
+  double cv[14][3];
+  for (int n = 0; n < 8; ++n)
+    for (int d = 0; d < 3; ++d)
+      cv[n][d] = sc[n][d];
+  static const int face_nodes[6][4] = {{0, 3, 2, 1}, {4, 5, 6, 7}, {0, 1, 5, 4},
+                                       {2, 3, 7, 6}, {1, 2, 6, 5}, {0, 4, 3, 7}};
+  for (int k = 0; k < 6; ++k)
+    for (int d = 0; d < 3; ++d)
+      cv[k + 8][d] =
+        0.25 * (cv[face_nodes[k][0]][d] + cv[face_nodes[k][1]][d] +
+                cv[face_nodes[k][2]][d] + cv[face_nodes[k][3]][d]);
+  static const int tf[24][3] = {
+    {0, 8, 1},  {8, 2, 1},  {3, 2, 8},  {3, 8, 0},  {6, 9, 5},  {7, 9, 6},
+    {4, 9, 7},  {4, 5, 9},  {10, 0, 1}, {5, 10, 1}, {4, 10, 5}, {4, 0, 10},
+    {7, 6, 11}, {6, 2, 11}, {2, 3, 11}, {3, 7, 11}, {6, 12, 2}, {5, 12, 6},
+    {5, 1, 12}, {1, 2, 12}, {0, 4, 13}, {4, 7, 13}, {7, 3, 13}, {3, 0, 13}};
+  double volume = 0.0;
+  for (int k = 0; k < 24; ++k) {
+    const int p = tf[k][0], q = tf[k][1], r = tf[k][2];
+    const double mid[3] = {cv[p][0] + cv[q][0] + cv[r][0],
+                           cv[p][1] + cv[q][1] + cv[r][1],
+                           cv[p][2] + cv[q][2] + cv[r][2]};
+    double dxv[3];
+    dxv[0] = (cv[q][1] - cv[p][1]) * (cv[r][2] - cv[p][2]) -
+             (cv[r][1] - cv[p][1]) * (cv[q][2] - cv[p][2]);
+    dxv[1] = (cv[r][0] - cv[p][0]) * (cv[q][2] - cv[p][2]) -
+             (cv[q][0] - cv[p][0]) * (cv[r][2] - cv[p][2]);
+    dxv[2] = (cv[q][0] - cv[p][0]) * (cv[r][1] - cv[p][1]) -
+             (cv[r][0] - cv[p][0]) * (cv[q][1] - cv[p][1]);
+    volume += mid[0] * dxv[0] + mid[1] * dxv[1] + mid[2] * dxv[2];
+  }
+  volume /= 18.0;
+  return volume;
+}
+
+/* quad_area_by_triangulation, Hex8GeometryFunctions.h:33-81 */
+void
+geo_quad_area(const double ac[4][3], double* area)
+{
+  area[0] = area[1] = area[2] = 0.0;
+  const double xmid[3] = {0.25 * (ac[0][0] + ac[1][0] + ac[2][0] + ac[3][0]),
+                          0.25 * (ac[0][1] + ac[1][1] + ac[2][1] + ac[3][1]),
+                          0.25 * (ac[0][2] + ac[1][2] + ac[2][2] + ac[3][2])};
+  double r1[3] = {ac[0][0] - xmid[0], ac[0][1] - xmid[1], ac[0][2] - xmid[2]};
+  for (int it = 0; it < 4; ++it) {
+    const int t = (it + 1) % 4;
+    const double r2[3] = {ac[t][0] - xmid[0], ac[t][1] - xmid[1],
+                          ac[t][2] - xmid[2]};
+    area[0] += r1[1] * r2[2] - r2[1] * r1[2];
+    area[1] += r1[2] * r2[0] - r2[2] * r1[0];
+    area[2] += r1[0] * r2[1] - r2[0] * r1[1];
+    r1[0] = r2[0];
+    r1[1] = r2[1];
+    r1[2] = r2[2];
+  }
+  area[0] *= 0.5;
+  area[1] *= 0.5;
+  area[2] *= 0.5;
+}
+
+} // namespace
+
+/* GeometryInteriorAlg<AlgTraitsHex8>: impl_compute_dual_nodal_volume
+ * (src/ngp_algorithms/GeometryInteriorAlg.C:72-112) and
+ * impl_compute_edge_area_vector (:165-225), with HexSCV::determinant_scv
+ * (src/master_element/Hex8CVFEM.C:365-390) and HexSCS::determinant_scs
+ * (:567-592).  elem_nodes: [n_elems][8] local nodes in the topology's node
+ * order; elem_owned (may be NULL): volumes are accumulated from locally-owned
+ * elements only (the reference's selector; the shared-node sum follows), edge
+ * area vectors from every element given, into the edges of `edge_nodes` (an
+ * element edge that is not in the list is skipped).  Accumulates (the driver's
+ * pre_work zero-fill is the caller's). */
+extern "C" void
+orc_geometry_interior_hex8(
+  int64_t n_elems, const int32_t* elem_nodes, const unsigned char* elem_owned,
+  const double* coords, int64_t n_edges, const int32_t* edge_nodes,
+  double* dual_nodal_volume, double* elem_volume, double* edge_area)
+{
+  static const int subDivisionTable[8][8] = {
+    {0, 8, 12, 11, 19, 20, 26, 25},  {8, 1, 9, 12, 20, 18, 24, 26},
+    {12, 9, 2, 10, 26, 24, 22, 23},  {11, 12, 10, 3, 25, 26, 23, 21},
+    {19, 20, 26, 25, 4, 13, 17, 16}, {20, 18, 24, 26, 13, 5, 14, 17},
+    {26, 24, 22, 23, 17, 14, 6, 15}, {25, 26, 23, 21, 16, 17, 15, 7}};
+  static const int hex_edge_facet_table[12][4] = {
+    {20, 8, 12, 26},  {24, 9, 12, 26},  {10, 12, 26, 23}, {11, 25, 26, 12},
+    {13, 20, 26, 17}, {17, 14, 24, 26}, {17, 15, 23, 26}, {16, 17, 26, 25},
+    {19, 20, 26, 25}, {20, 18, 24, 26}, {22, 23, 26, 24}, {21, 25, 26, 23}};
+  static const int lrscv[24] = {0, 1, 1, 2, 2, 3, 0, 3, 4, 5, 5, 6,
+                                6, 7, 4, 7, 0, 4, 1, 5, 2, 6, 3, 7};
+  static const int ipNodeMap[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+  std::map<std::pair<int32_t, int32_t>, int64_t> edgeOf;
+  for (int64_t e = 0; e < n_edges; ++e) {
+    const int32_t a = edge_nodes[2 * e], b = edge_nodes[2 * e + 1];
+    edgeOf[{std::min(a, b), std::max(a, b)}] = e;
+  }
+  for (int64_t el = 0; el < n_elems; ++el) {
+    const int32_t* en = elem_nodes + 8 * el;
+    double c[8][3], v[27][3];
+    for (int n = 0; n < 8; ++n)
+      for (int d = 0; d < 3; ++d)
+        c[n][d] = coords[size_t(en[n]) * 3 + d];
+    geo_subdivide_hex8(c, v);
+    if (!elem_owned || elem_owned[el]) {
+      double ev = 0.0;
+      for (int ip = 0; ip < 8; ++ip) {
+        double sc[8][3];
+        for (int n = 0; n < 8; ++n)
+          for (int d = 0; d < 3; ++d)
+            sc[n][d] = v[subDivisionTable[ip][n]][d];
+        const double vol = geo_hex_volume_grandy(sc);
+        dual_nodal_volume[en[ipNodeMap[ip]]] += vol;
+        ev += vol;
+      }
+      if (elem_volume)
+        elem_volume[el] = ev;
+    }
+    if (!edge_area)
+      continue;
+    for (int ip = 0; ip < 12; ++ip) {
+      double sc[4][3], av[3];
+      for (int n = 0; n < 4; ++n)
+        for (int d = 0; d < 3; ++d)
+          sc[n][d] = v[hex_edge_facet_table[ip][n]][d];
+      geo_quad_area(sc, av);
+      /* scsIpEdgeOrd is the identity for Hex8: edge `ip` joins lrscv pair ip */
+      const int32_t nl = en[lrscv[2 * ip]], nr = en[lrscv[2 * ip + 1]];
+      auto it = edgeOf.find({std::min(nl, nr), std::max(nl, nr)});
+      if (it == edgeOf.end())
+        continue;
+      const int64_t e = it->second;
+      const double sign = (nl == edge_nodes[2 * e]) ? 1.0 : -1.0;
+      for (int d = 0; d < 3; ++d)
+        edge_area[e * 3 + d] += av[d] * sign;
+    }
+  }
+}
+
 /* WallDistEdgeSolverAlg::execute, src/edge_kernels/WallDistEdgeSolverAlg.C:28-66 */
 extern "C" void
 orc_wall_dist_edge(

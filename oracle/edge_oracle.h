@@ -159,6 +159,15 @@ void orc_wall_dist_node(
   int64_t n_sel, const int32_t* nodes, const double* dual_nodal_volume,
   orc_applier*);
 
+/* GeometryInteriorAlg<AlgTraitsHex8> (src/ngp_algorithms/GeometryInteriorAlg.C:72-112,
+ * 165-225; Hex8CVFEM.C:365-390, 567-592; Hex8GeometryFunctions.h:33-325):
+ * accumulates dual_nodal_volume [n_nodes], edge_area [n_edges][3] (may be NULL),
+ * writes elem_volume [n_elems] (may be NULL) */
+void orc_geometry_interior_hex8(
+  int64_t n_elems, const int32_t* elem_nodes, const unsigned char* elem_owned,
+  const double* coords, int64_t n_edges, const int32_t* edge_nodes,
+  double* dual_nodal_volume, double* elem_volume, double* edge_area);
+
 void orc_applier_destroy(orc_applier*);
 
 /* ---- edge algorithms ---- */

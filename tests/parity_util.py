@@ -77,6 +77,23 @@ def add_tet_split_edges(b, seed=20261017):
     b.n_edges = len(b.edges)
 
 
+def box_hex_elements(b):
+    """hex8 connectivity [n_elems][8] (local nodes, Exodus / STK node order) of a
+    single-rank, non-periodic BoxMesh, from the generator's global ids"""
+    assert b.nranks == 1 and not any(b.periodic)
+    nx, ny, nz = b.dims
+    g0 = b.gid - 1
+    i, j, k = g0 % (nx + 1), (g0 // (nx + 1)) % (ny + 1), g0 // ((nx + 1) * (ny + 1))
+    at = -np.ones((nx + 1, ny + 1, nz + 1), dtype=np.int64)
+    at[i, j, k] = np.arange(b.n_nodes)
+    I, J, K = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    I, J, K = I.ravel(), J.ravel(), K.ravel()
+    corners = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0),
+               (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]
+    return np.stack([at[I + a, J + bb, K + c] for a, bb, c in corners],
+                    axis=1).astype(np.int32)
+
+
 class Case:
     """generated hex box + synthetic state (one rank)"""
 

@@ -7,6 +7,7 @@ import os
 import numpy as np
 
 import oracle_py as orc
+import parity_util as pu
 import unit_cube as uc
 
 G = json.load(open(os.path.join(os.path.dirname(__file__), "golden",
@@ -303,3 +304,29 @@ def test_wall_dist_edge_gold():
     lhs, rhs = sink.get()
     assert np.max(np.abs(lhs - np.array(G["wall_dist_edge"]["lhs"]))) <= 1e-12
     assert np.max(np.abs(rhs)) == 0.0
+
+
+def test_geometry_interior_hex8_gold():
+    """UnitTestGeometryAlg.C:25-101 (NGP_geometry_interior, generated:1x1x1):
+    dual volume 0.125 on 8 nodes, element volume 1, |edge area|^2 = 0.25^2 on
+    12 edges, tol 1e-16; directions follow the L->R (ascending id) rule that
+    the fixture's edge_area_vector uses"""
+    c, e = uc.mesh(1)
+    elem = np.array([uc.HEX_LOCAL_TO_ID], dtype=np.int32)
+    dnv, ev, area = orc.geometry_interior_hex8(elem, c, e, len(c))
+    assert np.max(np.abs(dnv - 0.125)) <= 1e-16
+    assert abs(ev[0] - 1.0) <= 1e-16
+    assert np.max(np.abs(np.sum(area * area, axis=1) - 0.0625)) <= 1e-16
+    assert np.max(np.abs(area - uc.edge_area(c, e))) <= 1e-16
+
+
+def test_geometry_interior_hex8_vs_generator():
+    """on a warped, stretched box the restated Grandy volumes / triangulated
+    SCS areas agree with the mesh generator's independent evaluation of the
+    same dual mesh"""
+    case = pu.Case(dims=(6, 5, 4), warp=0.15, zstretch=1.1)
+    b = case.box
+    elems = pu.box_hex_elements(b)
+    dnv, ev, area = orc.geometry_interior_hex8(elems, b.coords, b.edges, b.n_nodes)
+    assert np.max(np.abs(dnv - b.vol)) <= 1e-12 * np.max(b.vol)
+    assert np.max(np.abs(area - b.area)) <= 1e-12 * np.max(np.abs(b.area))
