@@ -201,6 +201,11 @@ int nw_mesh_halo_commit(nw_mesh* mesh);
  * with the sum over all ranks' copies (owner adds in ascending rank order,
  * then owner -> sharers).  Single rank: no-op. */
 int nw_field_parallel_sum(nw_mesh* mesh, int field_id);
+/* stk::mesh::copy_owned_to_shared(bulk, {field}) for a nodal field (what the
+ * reference does to a solution field after every solve, src/LinearSystem.C:
+ * 161-169, so that the next sweep reads current values on shared nodes): every
+ * non-owned copy takes its owner's value.  Single rank: no-op. */
+int nw_field_copy_owned_to_shared(nw_mesh* mesh, int field_id);
 /* transport the nodal halo sum of this mesh uses (nw_halo_transport) */
 int nw_mesh_halo_transport(const nw_mesh* mesh);
 

@@ -171,6 +171,7 @@ struct nw_node_halo
   int64_t nSendP2p = 0, nRecvP2p = 0;
   nw::DevBuf dSendIdx, dSendDst, dRecvIdx; /* int64 */
   nw::DevBuf dSendPeer, dPeerList;         /* int32 */
+  nw::DevBuf dRecvIsGhost;                 /* uint8: receive entry is a ghost of mine */
 };
 
 struct nw_mesh

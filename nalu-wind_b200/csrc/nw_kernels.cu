@@ -2282,6 +2282,25 @@ __global__ void __launch_bounds__(256) p2p_pull_nodal_kernel(
   }
 }
 
+/* copy_owned_to_shared: same push; the receiver overwrites its ghost copies
+ * (entries flagged in recvIsGhost) with the owner's values */
+__global__ void __launch_bounds__(256) p2p_pull_assign_nodal_kernel(
+  double* base, int64_t stride, int nc, const int64_t* __restrict__ recvIdx,
+  const unsigned char* __restrict__ recvIsGhost, int64_t n, const P2pDev pp)
+{
+  p2p_wait(pp);
+  const double* win = pp.myWindow + pp.winOff;
+  const int64_t total = n * nc;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = t / nc;
+    if (!recvIsGhost[g])
+      continue;
+    const int c = (int)(t - g * nc);
+    base[(int64_t)c * stride + recvIdx[g]] = __ldcg(win + t);
+  }
+}
+
 /* linear-system push: contiguous tail segments -> the owners' windows */
 __global__ void __launch_bounds__(256) p2p_push_segments_kernel(
   const double* const* __restrict__ segSrc, const int64_t* __restrict__ segStart,
@@ -3105,6 +3124,17 @@ launch_p2p_pull_nodal(
 {
   p2p_pull_nodal_kernel<<<p2p_pull_grid(n * nc, beside), 256, 0, s>>>(
     base, stride, nc, recvIdx, n, pp);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_p2p_pull_assign_nodal(
+  double* base, int64_t stride, int nc, const int64_t* recvIdx,
+  const unsigned char* recvIsGhost, int64_t n, const P2pDev& pp, bool beside,
+  cudaStream_t s)
+{
+  p2p_pull_assign_nodal_kernel<<<p2p_pull_grid(n * nc, beside), 256, 0, s>>>(
+    base, stride, nc, recvIdx, recvIsGhost, n, pp);
   return cudaGetLastError();
 }
 

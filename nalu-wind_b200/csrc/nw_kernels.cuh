@@ -224,6 +224,10 @@ cudaError_t launch_p2p_push_nodal(
 cudaError_t launch_p2p_pull_nodal(
   double* base, int64_t stride, int nc, const int64_t* recvIdx, int64_t n,
   const P2pDev& pp, bool beside, cudaStream_t s);
+cudaError_t launch_p2p_pull_assign_nodal(
+  double* base, int64_t stride, int nc, const int64_t* recvIdx,
+  const unsigned char* recvIsGhost, int64_t n, const P2pDev& pp, bool beside,
+  cudaStream_t s);
 cudaError_t launch_p2p_push_segments(
   const double* const* segSrc, const int64_t* segStart, const int64_t* segDst,
   const int32_t* segPeer, int nSeg, int64_t total, const P2pDev& pp,

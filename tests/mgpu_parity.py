@@ -161,6 +161,20 @@ def main():
                 got[l] - ref[gid2loc_full[int(b.gid[l])]])) / scale))
         res["grad_" + phi] = worst
 
+    # copy_owned_to_shared: poison the non-owned copies, every copy must come
+    # back equal to the serial field (bit-exact: a pure copy)
+    lo, hi = int(b.offsets[rank]), int(b.offsets[rank + 1]) - 1
+    mine = (b.own_hid >= lo) & (b.own_hid <= hi)
+    for name, nc in (("pressure", 1), ("velocity", 3)):
+        ref = full.fields[name].reshape(full.n_nodes, nc)
+        loc = np.array([ref[gid2loc_full[int(g)]] for g in b.gid])
+        poisoned = loc.copy()
+        poisoned[~mine] = -777.0
+        mesh.upload(name, poisoned.reshape(case.fields[name].shape))
+        mesh.copy_owned_to_shared(name)
+        got = mesh.download(name).reshape(b.n_nodes, nc)
+        res["copy_" + name] = 0.0 if np.array_equal(got, loc) else float("inf")
+
     allres = [None] * world
     dist.all_gather_object(allres, res)
     if rank == 0:

@@ -1,5 +1,5 @@
 #!/bin/bash
-# quick 2-rank A/B of the asynchronous pull (bench only)
+# quick multi-rank parity (peer-memory and NCCL transports) -- no bench
 set -u
 N=${1:-2}
 mkdir -p gpurun_out
@@ -7,9 +7,10 @@ cd "$(dirname "$0")/.."
 export PYTHONUNBUFFERED=1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 port=29600
-for m in 11 10; do
-p2p=${m:0:1}; as=${m:1:1}
+for m in 1 0; do
+for per in 0 1; do
 port=$((port+1))
-echo "=== bench N=$N p2p=$p2p async=$as"
-NW_P2P=$p2p NW_P2P_ASYNC=$as timeout 300 $TR --master-port $port bench.py --gpus $N --steps 10 --warmup 3 --detail > gpurun_out/bench_n${N}_m$m.json 2> gpurun_out/bench_n${N}_m$m.err; grep "ms x" gpurun_out/bench_n${N}_m$m.err; cut -c1-230 gpurun_out/bench_n${N}_m$m.json
+echo "=== mgpu parity periodic=$per p2p=$m"
+NW_P2P=$m NW_MGPU_PERIODIC=$per timeout 300 $TR --master-port $port tests/mgpu_parity.py > gpurun_out/mgpu_parity_p${per}_p2p$m.log 2>&1; tail -1 gpurun_out/mgpu_parity_p${per}_p2p$m.log | cut -c1-900
+done
 done
