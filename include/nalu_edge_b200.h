@@ -383,6 +383,13 @@ int nw_geometry_interior_hex8(
   nw_mesh* mesh, int64_t n_elems, const int32_t* elem_nodes,
   const unsigned char* elem_owned, int coordinates_field,
   int dual_nodal_volume_field, int edge_area_vector_field);
+/* The same for 2-D Quad4 blocks (AlgTraitsQuad4_2D; Quad42DSCV / Quad42DSCS
+ * determinants, src/master_element/Quad42DCVFEM.C:139-200, 384-445);
+ * elem_nodes is [n_elems][4]. */
+int nw_geometry_interior_quad4(
+  nw_mesh* mesh, int64_t n_elems, const int32_t* elem_nodes,
+  const unsigned char* elem_owned, int coordinates_field,
+  int dual_nodal_volume_field, int edge_area_vector_field);
 
 /* Poisson system of the SST minimum wall distance:
  * WallDistEdgeSolverAlg::execute (src/edge_kernels/WallDistEdgeSolverAlg.C:28-66,

@@ -114,7 +114,7 @@ ABI_SYMBOLS = [
     "nw_mesh_create", "nw_mesh_destroy", "nw_mesh_get_stats",
     "nw_field_register", "nw_field_find", "nw_field_upload",
     "nw_field_stage", "nw_field_commit", "nw_field_download", "nw_field_fill", "nw_field_device_view",
-    "nw_mesh_get_node_permutation", "nw_geometry_interior_hex8", "nw_mdot_edge", "nw_peclet_edge",
+    "nw_mesh_get_node_permutation", "nw_geometry_interior_hex8", "nw_geometry_interior_quad4", "nw_mdot_edge", "nw_peclet_edge",
     "nw_nodal_grad_edge", "nw_linsys_create", "nw_linsys_destroy",
     "nw_linsys_set_skipped_rows", "nw_linsys_build_edge_to_node_graph",
     "nw_linsys_finalize", "nw_linsys_get_sizes", "nw_linsys_get_graph",
@@ -181,6 +181,7 @@ def lib():
     L.nw_mdot_edge.argtypes = [vp, C.POINTER(MdotOpts)]
     L.nw_geometry_interior_hex8.argtypes = [vp, C.c_int64, vp, vp, C.c_int,
                                             C.c_int, C.c_int]
+    L.nw_geometry_interior_quad4.argtypes = L.nw_geometry_interior_hex8.argtypes
     L.nw_peclet_edge.argtypes = [vp, C.c_int, C.POINTER(PecletOpts)]
     L.nw_nodal_grad_edge.argtypes = [vp, C.c_int, C.c_int]
     L.nw_linsys_create.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
@@ -391,15 +392,20 @@ class Mesh:
 
     def geometry_interior_hex8(self, elem_nodes, dnv=None, area=None,
                                coords="coordinates", elem_owned=None):
-        """GeometryInteriorAlg<Hex8>: accumulate dual nodal volumes / edge area
-        vectors (zero the fields first)"""
+        """GeometryInteriorAlg<Hex8> ([n][8]) or <Quad4_2D> ([n][4]):
+        accumulate dual nodal volumes / edge area vectors (zero the fields
+        first)"""
         el = np.ascontiguousarray(elem_nodes, dtype=np.int32)
         ow = None if elem_owned is None else np.ascontiguousarray(
             elem_owned, dtype=np.uint8)
-        _chk(lib().nw_geometry_interior_hex8(
+        fn = (lib().nw_geometry_interior_hex8 if el.shape[1] == 8
+              else lib().nw_geometry_interior_quad4)
+        _chk(fn(
             self.h, len(el), _ptr(el), None if ow is None else _ptr(ow),
             self.field_id(coords), -1 if dnv is None else self.field_id(dnv),
             -1 if area is None else self.field_id(area)))
+
+    geometry_interior = geometry_interior_hex8
 
     def nodal_grad_edge(self, phi, grad):
         _chk(lib().nw_nodal_grad_edge(self.h, self.field_id(phi),

@@ -644,67 +644,70 @@ bind_cont_nodes(nw_mesh* mesh, NodeComps& nc)
 /*  geometry producers                                                 */
 /* ------------------------------------------------------------------ */
 
-extern "C" int
-nw_geometry_interior_hex8(
-  nw_mesh* mesh, int64_t n_elems, const int32_t* elem_nodes,
-  const unsigned char* elem_owned, int coordinates_field,
-  int dual_nodal_volume_field, int edge_area_vector_field)
+/* GeometryInteriorAlg for one element block of `npe`-node elements whose
+ * sub-control surfaces pair local nodes lr[2 ip], lr[2 ip + 1] (scsIpEdgeOrd
+ * is the identity for Hex8 and Quad4) */
+static int
+geometry_interior(
+  nw_mesh* mesh, const char* what, int ndim, int npe, int nScs, const int* lr,
+  int64_t n_elems, const int32_t* elem_nodes, const unsigned char* elem_owned,
+  int coordinates_field, int dual_nodal_volume_field, int edge_area_vector_field)
 {
   if (!mesh || n_elems < 0 || (n_elems > 0 && !elem_nodes))
-    return fail(NW_ERR_ARG, "nw_geometry_interior_hex8: bad argument");
-  if (int rc = need_device(mesh->ctx, "nw_geometry_interior_hex8"))
+    return fail(NW_ERR_ARG, std::string(what) + ": bad argument");
+  if (int rc = need_device(mesh->ctx, what))
     return rc;
   const MeshPlan& mp = mesh->plan;
-  if (mp.ndim != 3)
-    return fail(NW_ERR_ARG, "nw_geometry_interior_hex8: 3-D meshes only");
+  if (mp.ndim != ndim)
+    return fail(NW_ERR_ARG, std::string(what) + ": wrong spatial dimension");
   nw_field_t* xf = get_field(mesh, coordinates_field);
   nw_field_t* vf =
     dual_nodal_volume_field >= 0 ? get_field(mesh, dual_nodal_volume_field) : nullptr;
   nw_field_t* af =
     edge_area_vector_field >= 0 ? get_field(mesh, edge_area_vector_field) : nullptr;
-  if (!xf || xf->rank != NW_NODE || xf->ncomp != 3 ||
+  if (!xf || xf->rank != NW_NODE || xf->ncomp != ndim ||
       (dual_nodal_volume_field >= 0 &&
        (!vf || vf->rank != NW_NODE || vf->ncomp != 1)) ||
       (edge_area_vector_field >= 0 &&
-       (!af || af->rank != NW_EDGE || af->ncomp != 3)))
-    return fail(NW_ERR_ARG, "nw_geometry_interior_hex8: bad field id or shape");
+       (!af || af->rank != NW_EDGE || af->ncomp != ndim)))
+    return fail(NW_ERR_ARG, std::string(what) + ": bad field id or shape");
   cudaStream_t s = mesh->ctx->stream;
   /* FNV-1a over the connectivity (+ ownership flags): rebuild on change */
-  uint64_t h = 1469598103934665603ull;
+  uint64_t h = 1469598103934665603ull ^ (uint64_t)npe;
   auto mix = [&](const unsigned char* p, size_t n) {
     for (size_t i = 0; i < n; ++i) {
       h ^= p[i];
       h *= 1099511628211ull;
     }
   };
-  mix(reinterpret_cast<const unsigned char*>(elem_nodes), sizeof(int32_t) * 8 * n_elems);
+  mix(reinterpret_cast<const unsigned char*>(elem_nodes),
+      sizeof(int32_t) * (size_t)npe * n_elems);
   if (elem_owned)
     mix(elem_owned, (size_t)n_elems);
   nw_mesh::GeoCache& gc = mesh->geo;
   if (gc.nElems != n_elems || gc.hash != h) {
-    static const int lr[24] = {0, 1, 1, 2, 2, 3, 0, 3, 4, 5, 5, 6,
-                               6, 7, 4, 7, 0, 4, 1, 5, 2, 6, 3, 7};
     std::map<std::pair<int32_t, int32_t>, int64_t> edgeOf;
     for (int64_t e = 0; e < mp.nEdges; ++e) {
       const int32_t a = mp.edgeNodes[2 * e], b = mp.edgeNodes[2 * e + 1];
       edgeOf[{std::min(a, b), std::max(a, b)}] = e;
     }
-    std::vector<int32_t> slots((size_t)n_elems * 8), edges((size_t)n_elems * 12, -1);
+    std::vector<int32_t> slots((size_t)n_elems * npe),
+      edges((size_t)n_elems * nScs, -1);
     for (int64_t el = 0; el < n_elems; ++el) {
-      const int32_t* en = elem_nodes + 8 * el;
-      for (int n = 0; n < 8; ++n) {
+      const int32_t* en = elem_nodes + (size_t)npe * el;
+      for (int n = 0; n < npe; ++n) {
         if (en[n] < 0 || en[n] >= mp.nNodes)
-          return fail(NW_ERR_ARG, "nw_geometry_interior_hex8: node index out of range");
-        slots[8 * el + n] = mp.slotOfNode[en[n]];
+          return fail(NW_ERR_ARG, std::string(what) + ": node index out of range");
+        slots[(size_t)npe * el + n] = mp.slotOfNode[en[n]];
       }
-      for (int ip = 0; ip < 12; ++ip) {
+      for (int ip = 0; ip < nScs; ++ip) {
         const int32_t nl = en[lr[2 * ip]], nr = en[lr[2 * ip + 1]];
         auto it = edgeOf.find({std::min(nl, nr), std::max(nl, nr)});
         if (it == edgeOf.end())
           continue; /* edge owned by another rank */
         const int64_t e = it->second;
         const int negate = nl == mp.edgeNodes[2 * e] ? 0 : 1;
-        edges[12 * el + ip] = 2 * mp.primarySlotOfEdge[e] + negate;
+        edges[(size_t)nScs * el + ip] = 2 * mp.primarySlotOfEdge[e] + negate;
       }
     }
     int rc;
@@ -721,16 +724,51 @@ nw_geometry_interior_hex8(
     gc.nElems = n_elems;
     gc.hash = h;
   }
-  NW_CUDA(launch_geometry_hex8(
-    n_elems, gc.dElemSlots.as<int32_t>(), gc.dElemEdges.as<int32_t>(),
-    gc.hasOwned ? gc.dOwned.as<unsigned char>() : nullptr, xf->buf.as<double>(),
-    xf->stride, vf ? vf->buf.as<double>() : nullptr,
-    af ? af->buf.as<double>() : nullptr, af ? af->stride : 0, s));
+  const unsigned char* ow = gc.hasOwned ? gc.dOwned.as<unsigned char>() : nullptr;
+  double* vol = vf ? vf->buf.as<double>() : nullptr;
+  double* area = af ? af->buf.as<double>() : nullptr;
+  if (npe == 8)
+    NW_CUDA(launch_geometry_hex8(
+      n_elems, gc.dElemSlots.as<int32_t>(), gc.dElemEdges.as<int32_t>(), ow,
+      xf->buf.as<double>(), xf->stride, vol, area, af ? af->stride : 0, s));
+  else
+    NW_CUDA(launch_geometry_quad4(
+      n_elems, gc.dElemSlots.as<int32_t>(), gc.dElemEdges.as<int32_t>(), ow,
+      xf->buf.as<double>(), xf->stride, vol, area, af ? af->stride : 0, s));
   if (af)
     NW_CUDA(launch_edge_mirror(
       mesh->dPrimarySlot.as<int32_t>(), mesh->dSecondSlot.as<int32_t>(),
-      mp.nEdges, 3, af->stride, af->buf.as<double>(), s));
+      mp.nEdges, ndim, af->stride, af->buf.as<double>(), s));
   return NW_OK;
+}
+
+extern "C" int
+nw_geometry_interior_hex8(
+  nw_mesh* mesh, int64_t n_elems, const int32_t* elem_nodes,
+  const unsigned char* elem_owned, int coordinates_field,
+  int dual_nodal_volume_field, int edge_area_vector_field)
+{
+  /* HexSCS::lrscv_, include/master_element/Hex8CVFEM.h:292-293 */
+  static const int lr[24] = {0, 1, 1, 2, 2, 3, 0, 3, 4, 5, 5, 6,
+                             6, 7, 4, 7, 0, 4, 1, 5, 2, 6, 3, 7};
+  return geometry_interior(
+    mesh, "nw_geometry_interior_hex8", 3, 8, 12, lr, n_elems, elem_nodes,
+    elem_owned, coordinates_field, dual_nodal_volume_field,
+    edge_area_vector_field);
+}
+
+extern "C" int
+nw_geometry_interior_quad4(
+  nw_mesh* mesh, int64_t n_elems, const int32_t* elem_nodes,
+  const unsigned char* elem_owned, int coordinates_field,
+  int dual_nodal_volume_field, int edge_area_vector_field)
+{
+  /* Quad42DSCS::lrscv_, include/master_element/Quad42DCVFEM.h:250 */
+  static const int lr[8] = {0, 1, 1, 2, 2, 3, 0, 3};
+  return geometry_interior(
+    mesh, "nw_geometry_interior_quad4", 2, 4, 4, lr, n_elems, elem_nodes,
+    elem_owned, coordinates_field, dual_nodal_volume_field,
+    edge_area_vector_field);
 }
 
 /* ------------------------------------------------------------------ */

@@ -1853,6 +1853,70 @@ __global__ void __launch_bounds__(128) geometry_hex8_kernel(
   }
 }
 
+/* GeometryInteriorAlg<Quad4_2D> (src/master_element/Quad42DCVFEM.C:139-200,
+ * 384-445): four 2x2-Gauss sub-control-volume areas, four sub-control-surface
+ * normals from the element centre to the face mid points */
+__global__ void __launch_bounds__(128) geometry_quad4_kernel(
+  int64_t nElems, const int32_t* __restrict__ elemSlots /* [n][4] */,
+  const int32_t* __restrict__ elemEdges /* [n][4] */,
+  const unsigned char* __restrict__ owned, const double* __restrict__ x,
+  int64_t xStride, double* dualVol, double* area, int64_t areaStride)
+{
+  const int64_t el = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (el >= nElems)
+    return;
+  double cx[4], cy[4];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    const int64_t sl = elemSlots[4 * el + n];
+    cx[n] = x[sl];
+    cy[n] = x[xStride + sl];
+  }
+  if (dualVol && (!owned || owned[el])) {
+    const double gp[2] = {-0.144337567, 0.144337567};
+    const double cv[2] = {-0.25, 0.25};
+    /* corner k of the parent square: xi sign pattern (-,+,+,-), eta (-,-,+,+) */
+    const int sx[4] = {0, 1, 1, 0}, sy[4] = {0, 0, 1, 1};
+    for (int ki = 0; ki < 4; ++ki) {
+      double vol = 0.0;
+      for (int kq = 0; kq < 4; ++kq) {
+        const double xi = cv[sx[ki]] + gp[sx[kq]];
+        const double eta = cv[sy[ki]] + gp[sy[kq]];
+        const double d0[4] = {-(0.5 - eta), (0.5 - eta), (0.5 + eta), -(0.5 + eta)};
+        const double d1[4] = {-(0.5 - xi), -(0.5 + xi), (0.5 + xi), (0.5 - xi)};
+        double xs1 = 0.0, xs2 = 0.0, ys1 = 0.0, ys2 = 0.0;
+#pragma unroll
+        for (int kn = 0; kn < 4; ++kn) {
+          xs1 += d0[kn] * cx[kn];
+          xs2 += d1[kn] * cx[kn];
+          ys1 += d0[kn] * cy[kn];
+          ys2 += d1[kn] * cy[kn];
+        }
+        vol += (xs1 * ys2 - ys1 * xs2) * 0.0625;
+      }
+      atomicAdd(dualVol + elemSlots[4 * el + ki], vol);
+    }
+  }
+  if (!area)
+    return;
+  const double x1 = (cx[0] + cx[1] + cx[2] + cx[3]) * 0.25;
+  const double y1 = (cy[0] + cy[1] + cy[2] + cy[3]) * 0.25;
+  for (int f = 0; f < 4; ++f) {
+    const int32_t code = elemEdges[4 * el + f];
+    if (code < 0)
+      continue;
+    const int a = f, b = (f + 1) & 3;
+    const double x2 = (cx[a] + cx[b]) * 0.5, y2 = (cy[a] + cy[b]) * 0.5;
+    /* surfaces 0-2: (-(dy), dx); surface 3 points from node 0 to node 3 */
+    const double ax = f < 3 ? -(y2 - y1) : (y2 - y1);
+    const double ay = f < 3 ? (x2 - x1) : -(x2 - x1);
+    const double sg = (code & 1) ? -1.0 : 1.0;
+    const int64_t slot = code >> 1;
+    atomicAdd(area + slot, ax * sg);
+    atomicAdd(area + areaStride + slot, ay * sg);
+  }
+}
+
 /* a cut edge has a second tile-edge slot: keep it equal to the primary one */
 __global__ void
 edge_mirror_kernel(
@@ -2898,6 +2962,19 @@ launch_geometry_hex8(
   if (nElems == 0)
     return cudaSuccess;
   geometry_hex8_kernel<<<blocks_for(nElems, 128), 128, 0, s>>>(
+    nElems, elemSlots, elemEdges, owned, x, xStride, dualVol, area, areaStride);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_geometry_quad4(
+  int64_t nElems, const int32_t* elemSlots, const int32_t* elemEdges,
+  const unsigned char* owned, const double* x, int64_t xStride, double* dualVol,
+  double* area, int64_t areaStride, cudaStream_t s)
+{
+  if (nElems == 0)
+    return cudaSuccess;
+  geometry_quad4_kernel<<<blocks_for(nElems, 128), 128, 0, s>>>(
     nElems, elemSlots, elemEdges, owned, x, xStride, dualVol, area, areaStride);
   return cudaGetLastError();
 }

@@ -151,6 +151,11 @@ cudaError_t launch_geometry_hex8(
   int64_t nElems, const int32_t* elemSlots, const int32_t* elemEdges,
   const unsigned char* owned, const double* x, int64_t xStride, double* dualVol,
   double* area, int64_t areaStride, cudaStream_t s);
+/* GeometryInteriorAlg<Quad4_2D>: elemSlots [n][4], elemEdges [n][4] */
+cudaError_t launch_geometry_quad4(
+  int64_t nElems, const int32_t* elemSlots, const int32_t* elemEdges,
+  const unsigned char* owned, const double* x, int64_t xStride, double* dualVol,
+  double* area, int64_t areaStride, cudaStream_t s);
 cudaError_t launch_edge_mirror(
   const int32_t* primarySlot, const int32_t* secondSlot, int64_t nEdges,
   int ncomp, int64_t stride, double* f, cudaStream_t s);

@@ -1274,6 +1274,97 @@ orc_geometry_interior_hex8(
   }
 }
 
+/* GeometryInteriorAlg<AlgTraitsQuad4_2D>: Quad42DSCV::determinant_scv
+ * (src/master_element/Quad42DCVFEM.C:139-200) and Quad42DSCS::determinant_scs
+ * (:384-445), lrscv / scsIpEdgeOrd include/master_element/Quad42DCVFEM.h:250-253.
+ * Same conventions as orc_geometry_interior_hex8; coords / edge_area have 2
+ * components. */
+extern "C" void
+orc_geometry_interior_quad4(
+  int64_t n_elems, const int32_t* elem_nodes, const unsigned char* elem_owned,
+  const double* coords, int64_t n_edges, const int32_t* edge_nodes,
+  double* dual_nodal_volume, double* elem_volume, double* edge_area)
+{
+  static const int lrscv[8] = {0, 1, 1, 2, 2, 3, 0, 3};
+  std::map<std::pair<int32_t, int32_t>, int64_t> edgeOf;
+  for (int64_t e = 0; e < n_edges; ++e) {
+    const int32_t a = edge_nodes[2 * e], b = edge_nodes[2 * e + 1];
+    edgeOf[{std::min(a, b), std::max(a, b)}] = e;
+  }
+  for (int64_t el = 0; el < n_elems; ++el) {
+    const int32_t* en = elem_nodes + 4 * el;
+    double c[4][2];
+    for (int n = 0; n < 4; ++n)
+      for (int d = 0; d < 2; ++d)
+        c[n][d] = coords[size_t(en[n]) * 2 + d];
+    if (!elem_owned || elem_owned[el]) {
+      const double gpp = 0.144337567, gpm = -0.144337567;
+      const double cvm = -0.25, cvp = 0.25;
+      const double half = 0.5, zero = 0.0, one16th = 0.0625;
+      const double xi[2][4] = {{cvm, cvp, cvp, cvm}, {cvm, cvm, cvp, cvp}};
+      const double xigp[2][4] = {{gpm, gpp, gpp, gpm}, {gpm, gpm, gpp, gpp}};
+      double ev = 0.0;
+      for (int ki = 0; ki < 4; ++ki) {
+        double vol = zero;
+        for (int kq = 0; kq < 4; ++kq) {
+          double dx_ds1 = zero, dx_ds2 = zero, dy_ds1 = zero, dy_ds2 = zero;
+          const double ximod = xi[0][ki] + xigp[0][kq];
+          const double etamod = xi[1][ki] + xigp[1][kq];
+          double deriv[2][4];
+          deriv[0][0] = -(half - etamod);
+          deriv[0][1] = (half - etamod);
+          deriv[0][2] = (half + etamod);
+          deriv[0][3] = -(half + etamod);
+          deriv[1][0] = -(half - ximod);
+          deriv[1][1] = -(half + ximod);
+          deriv[1][2] = (half + ximod);
+          deriv[1][3] = (half - ximod);
+          for (int kn = 0; kn < 4; ++kn) {
+            dx_ds1 += deriv[0][kn] * c[kn][0];
+            dx_ds2 += deriv[1][kn] * c[kn][0];
+            dy_ds1 += deriv[0][kn] * c[kn][1];
+            dy_ds2 += deriv[1][kn] * c[kn][1];
+          }
+          const double det_j = (dx_ds1 * dy_ds2 - dy_ds1 * dx_ds2);
+          vol += det_j * one16th;
+        }
+        dual_nodal_volume[en[ki]] += vol; /* ipNodeMap is the identity */
+        ev += vol;
+      }
+      if (elem_volume)
+        elem_volume[el] = ev;
+    }
+    if (!edge_area)
+      continue;
+    const double x1 = (c[0][0] + c[1][0] + c[2][0] + c[3][0]) * 0.25;
+    const double y1 = (c[0][1] + c[1][1] + c[2][1] + c[3][1]) * 0.25;
+    double areav[4][2];
+    for (int f = 0; f < 4; ++f) {
+      const int a = f, b = (f + 1) % 4;
+      /* mid-face f joins nodes (f, f+1); face 3 is written (3, 0) */
+      const double x2 = (c[a][0] + c[b][0]) * 0.5, y2 = (c[a][1] + c[b][1]) * 0.5;
+      const double rr = 1.0;
+      if (f < 3) {
+        areav[f][0] = -(y2 - y1) * rr;
+        areav[f][1] = (x2 - x1) * rr;
+      } else {
+        areav[f][0] = (y2 - y1) * rr;
+        areav[f][1] = -(x2 - x1) * rr;
+      }
+    }
+    for (int ip = 0; ip < 4; ++ip) {
+      const int32_t nl = en[lrscv[2 * ip]], nr = en[lrscv[2 * ip + 1]];
+      auto it = edgeOf.find({std::min(nl, nr), std::max(nl, nr)});
+      if (it == edgeOf.end())
+        continue;
+      const int64_t e = it->second;
+      const double sign = (nl == edge_nodes[2 * e]) ? 1.0 : -1.0;
+      for (int d = 0; d < 2; ++d)
+        edge_area[e * 2 + d] += areav[ip][d] * sign;
+    }
+  }
+}
+
 /* WallDistEdgeSolverAlg::execute, src/edge_kernels/WallDistEdgeSolverAlg.C:28-66 */
 extern "C" void
 orc_wall_dist_edge(

@@ -168,6 +168,13 @@ void orc_geometry_interior_hex8(
   const double* coords, int64_t n_edges, const int32_t* edge_nodes,
   double* dual_nodal_volume, double* elem_volume, double* edge_area);
 
+/* GeometryInteriorAlg<AlgTraitsQuad4_2D> (src/master_element/Quad42DCVFEM.C:
+ * 139-200, 384-445); 2-component coords / edge_area */
+void orc_geometry_interior_quad4(
+  int64_t n_elems, const int32_t* elem_nodes, const unsigned char* elem_owned,
+  const double* coords, int64_t n_edges, const int32_t* edge_nodes,
+  double* dual_nodal_volume, double* elem_volume, double* edge_area);
+
 void orc_applier_destroy(orc_applier*);
 
 /* ---- edge algorithms ---- */

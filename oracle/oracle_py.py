@@ -408,3 +408,21 @@ def geometry_interior_hex8(elem_nodes, coords, edge_nodes, n_nodes, elem_owned=N
       xyz.ctypes.data, en.size // 2, en.ctypes.data, dnv.ctypes.data,
       ev.ctypes.data, area.ctypes.data)
     return dnv, ev, area
+
+
+def geometry_interior_quad4(elem_nodes, coords, edge_nodes, n_nodes, elem_owned=None):
+    """GeometryInteriorAlg<Quad4_2D>: (dual_nodal_volume, elem_volume, edge_area[n][2])"""
+    el = np.ascontiguousarray(elem_nodes, dtype=np.int32)
+    en = np.ascontiguousarray(edge_nodes, dtype=np.int32)
+    xy = np.ascontiguousarray(coords, dtype=np.float64)
+    own = None if elem_owned is None else np.ascontiguousarray(elem_owned, dtype=np.uint8)
+    dnv = np.zeros(n_nodes)
+    ev = np.zeros(len(el))
+    area = np.zeros((en.size // 2, 2))
+    f = lib().orc_geometry_interior_quad4
+    f.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    f(len(el), el.ctypes.data, None if own is None else own.ctypes.data,
+      xy.ctypes.data, en.size // 2, en.ctypes.data, dnv.ctypes.data,
+      ev.ctypes.data, area.ctypes.data)
+    return dnv, ev, area

@@ -447,6 +447,13 @@ class OGrid2D:
         edges = edges[order]
         self.edges = np.ascontiguousarray(edges.astype(np.int32))
         self.n_edges = len(edges)
+        # quad4 connectivity (counter-clockwise in the (theta, r) chart flipped
+        # to a positive Jacobian in (x, y))
+        ei, ej = np.meshgrid(np.arange(ntheta), np.arange(nr - 1), indexing="xy")
+        ei, ej = ei.ravel(), ej.ravel()
+        self.elems = np.stack([node(ei, ej), node(ei, ej + 1),
+                               node(ei + 1, ej + 1), node(ei + 1, ej)],
+                              axis=1).astype(np.int32)
         dx = self.coords[edges[:, 1]] - self.coords[edges[:, 0]]
         ln = np.linalg.norm(dx, axis=1, keepdims=True)
         rr = np.linalg.norm(0.5 * (self.coords[edges[:, 1]] + self.coords[edges[:, 0]]),

@@ -522,6 +522,30 @@ def test_geometry_interior_hex8(P, ctx):
     mesh.close()
 
 
+def test_geometry_interior_quad4(P, ctx):
+    """GeometryInteriorAlg<Quad4_2D> on the curvilinear O-grid vs the oracle
+    (Quad42DCVFEM.C:139-200, 384-445), plus closure of the dual cells"""
+    g = pu.OGrid2D()
+    odnv, oev, oarea = orc.geometry_interior_quad4(g.elems, g.coords, g.edges,
+                                                   g.n_nodes)
+    mesh = P.Mesh(ctx, 2, g.edges, g.hid, g.coords, tile_nodes=64)
+    mesh.register("dual_nodal_volume", P.NW_NODE, 1)
+    mesh.register("edge_area_vector", P.NW_EDGE, 2)
+    mesh.geometry_interior(g.elems, dnv="dual_nodal_volume",
+                           area="edge_area_vector")
+    dnv = mesh.download("dual_nodal_volume")
+    area = mesh.download("edge_area_vector").reshape(-1, 2)
+    assert np.max(np.abs(dnv - odnv)) <= 1e-12 * np.max(odnv)
+    assert np.max(np.abs(area - oarea)) <= 1e-12 * np.max(np.abs(oarea))
+    acc = np.zeros((g.n_nodes, 2))
+    np.add.at(acc, g.edges[:, 0], area)
+    np.add.at(acc, g.edges[:, 1], -area)
+    j = np.arange(g.n_nodes) // 48
+    inner = (j > 0) & (j < 19)
+    assert np.max(np.abs(acc[inner])) <= 1e-14
+    mesh.close()
+
+
 @pytest.mark.parametrize("mode", [0, 1])
 def test_wall_dist_system(P, ctx, mode):
     """WallDistEdgeSolverAlg + WallDistNodeKernel: the reference's 8x8 gold on

@@ -330,3 +330,22 @@ def test_geometry_interior_hex8_vs_generator():
     dnv, ev, area = orc.geometry_interior_hex8(elems, b.coords, b.edges, b.n_nodes)
     assert np.max(np.abs(dnv - b.vol)) <= 1e-12 * np.max(b.vol)
     assert np.max(np.abs(area - b.area)) <= 1e-12 * np.max(np.abs(b.area))
+
+
+def test_geometry_interior_quad4_properties():
+    """Quad42DSCV / Quad42DSCS restatement: the unit square gives 0.25 per
+    node and 0.5 L->R normals; on the curvilinear O-grid the sub-volumes tile
+    the elements and every interior dual cell closes"""
+    c = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], dtype=float)
+    e = np.array([[0, 1], [1, 2], [2, 3], [0, 3]], dtype=np.int32)
+    dnv, ev, area = orc.geometry_interior_quad4([[0, 1, 2, 3]], c, e, 4)
+    assert np.max(np.abs(dnv - 0.25)) <= 1e-9  # 9-digit Gauss points (:146-147)
+    assert np.array_equal(area, [[0.5, 0], [0, 0.5], [-0.5, 0], [0, 0.5]])
+    g = pu.OGrid2D()
+    dnv, ev, area = orc.geometry_interior_quad4(g.elems, g.coords, g.edges, g.n_nodes)
+    assert ev.min() > 0 and abs(dnv.sum() - ev.sum()) <= 1e-12 * ev.sum()
+    acc = np.zeros((g.n_nodes, 2))
+    np.add.at(acc, g.edges[:, 0], area)
+    np.add.at(acc, g.edges[:, 1], -area)
+    j = np.arange(g.n_nodes) // 48
+    assert np.max(np.abs(acc[(j > 0) & (j < 19)])) <= 1e-14
