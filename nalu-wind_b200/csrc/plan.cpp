@@ -667,10 +667,18 @@ build_ls_plan(const MeshPlan& mp, const Graph& g, LsPlan& lp)
   auto isSkipped = [&](int64_t row) {
     return std::binary_search(g.skippedRows.begin(), g.skippedRows.end(), row);
   };
+  /* a row nothing assembles into (no columns: a periodic slave's own row, or a
+   * node no edge touches) is one of the reference's periodic_bc_rows_owned_
+   * (src/HypreLinearSystem.C:1036-1039): diagonal 1, rhs 0 after every reset
+   * (:1420-1428).  No tile may own it -- it stays with row_init. */
+  auto isDiagOnlyRow = [&](int64_t row) {
+    return std::binary_search(
+      g.periodicRowsOwned.begin(), g.periodicRowsOwned.end(), row);
+  };
 #pragma omp parallel for schedule(static)
   for (int64_t n = 0; n < N; ++n) {
     const int64_t h = mp.nodeHid[n];
-    nodeRow[n] = isSkipped(h) ? -1 : g.localRow(h);
+    nodeRow[n] = (isSkipped(h) || isDiagOnlyRow(h)) ? -1 : g.localRow(h);
   }
 
   lp.tiles.assign(nTiles, LsTileHdr());

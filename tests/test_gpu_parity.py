@@ -223,6 +223,66 @@ def test_quad2d_ogrid_sweep_vs_oracle(P, ctx, tile, mode):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("n_edges", [0, 1, 3])
+def test_ragged_inputs_isolated_nodes_and_no_edges(P, ctx, n_edges):
+    """edge cases of the inputs: a mesh with no edges at all, and meshes whose
+    edges touch only some nodes (rows of untouched nodes are the reference's
+    diagonal-only rows, src/HypreLinearSystem.C:1036-1039, diag 1 / rhs 0 after
+    every reset, :1420-1428)"""
+    rng = np.random.default_rng(3)
+    n = 7
+    c = rng.random((n, 3)) * 3.0
+    e = np.array([[1, 3], [3, 6], [0, 6]], dtype=np.int32)[:n_edges].reshape(-1, 2)
+    hid = np.arange(n, dtype=np.int64)
+    mesh = P.Mesh(ctx, 3, e, hid, c, tile_nodes=4)
+    f = {"velocity": rng.standard_normal((n, 3)), "dpdx": rng.standard_normal((n, 3)),
+         "density": 1.0 + rng.random(n), "pressure": rng.standard_normal(n),
+         "momentum_diag": 2.0 + rng.random(n), "dual_nodal_volume": 0.5 + rng.random(n)}
+    for k, v in f.items():
+        mesh.put(k, P.NW_NODE, v)
+    area = rng.standard_normal((len(e), 3)) + 2.0 * (c[e[:, 1]] - c[e[:, 0]])
+    mesh.register("edge_area_vector", P.NW_EDGE, 3)
+    if len(e):
+        mesh.upload("edge_area_vector", area)
+    mesh.register("mass_flow_rate", P.NW_EDGE, 1)
+    mesh.mdot_edge(1.0, 1.0)
+    got = mesh.download("mass_flow_rate")
+    ref = orc.mdot_edge(3, e, c, f["velocity"], f["dpdx"], f["density"],
+                        f["pressure"], f["momentum_diag"], area, 1.0, 1.0)
+    assert got.shape == ref.shape
+    if len(e):
+        assert pu.scaled_err(got, ref, np.abs(ref) + 1e-3 * np.max(np.abs(ref))) < 1
+    mesh.register("g", P.NW_NODE, 3)
+    mesh.nodal_grad_edge("pressure", "g")
+    gg = mesh.download("g").reshape(n, 3)
+    gref = orc.nodal_grad_edge(1, 3, e, f["pressure"], area,
+                               f["dual_nodal_volume"], n).reshape(n, 3)
+    assert np.max(np.abs(gg - gref)) <= 1e-12 * (np.max(np.abs(gref)) + 1.0)
+    g = orc.Graph(1, 0, n - 1)
+    g.add_edges(e, hid)
+    g.finalize()
+    sink = orc.HypreSink(g, hid)
+    orc.continuity_edge(3, e, c, f["velocity"], f["dpdx"], f["density"],
+                        f["pressure"], f["momentum_diag"], area, sink,
+                        **pu.CONT_OPTS)
+    ov, orhs = sink.get()
+    av_, arhs = sink.get_abs()
+    for mode in (0, 1):
+        ls = P.LinearSystem(mesh)
+        ls.set_scatter_mode(mode)
+        ls.buildEdgeToNodeGraph()
+        ls.finalizeLinearSystem()
+        assert ls.graph()["cols"].tolist() == g.cols.tolist()
+        ls.zeroSystem()
+        ls.assemble_continuity_edge(**pu.CONT_OPTS)
+        ls.loadComplete()
+        vals, rhs = ls.values()
+        assert pu.scaled_err(vals, ov, av_) < 1
+        assert pu.scaled_err(rhs, orhs, arhs) < 1
+        ls.close()
+    mesh.close()
+
+
 def test_monolithic_momentum_vs_oracle(P, ctx):
     case = pu.Case(dims=(10, 9, 7))
     mesh = case.box.make_mesh(ctx, tile_nodes=64)
