@@ -319,6 +319,31 @@ typedef struct {
  * (src/edge_kernels/ContinuityEdgeSolverAlg.C:37-195). */
 int nw_assemble_continuity_edge(nw_linsys* ls, const nw_continuity_opts* opts);
 
+/* The optional terms of MdotEdgeAlg / ContinuityEdgeSolverAlg
+ * (src/ngp_algorithms/MdotEdgeAlg.C:153-163, 175-180;
+ * src/edge_kernels/ContinuityEdgeSolverAlg.C:147-158, 172-177), off in the
+ * ABL / airfoil decks: balanced buoyancy forcing
+ * (solutionOptions_->use_balanced_buoyancy_force_: gravity vector, nodal fields
+ * buoyancy_source [ndim] and buoyancy_source_mask [1]) and the GCL term of
+ * deforming meshes (realm_.has_mesh_deformation(): edge field
+ * edge_face_velocity_mag [1]).  The *_ext entry points take them in `extra`;
+ * they use direct-gather kernels (the continuity one scatters with fp64
+ * atomics through the edge->slot map and accumulates like the atomic mode),
+ * the default entry points above stay on the tile kernels. */
+typedef struct {
+  int32_t add_balanced_forcing;
+  double gravity[3];
+  int32_t source_field;            /* buoyancy_source */
+  int32_t source_mask_field;       /* buoyancy_source_mask */
+  int32_t needs_gcl;
+  int32_t edge_face_vel_mag_field; /* edge_face_velocity_mag */
+} nw_mdot_extra_opts;
+int nw_mdot_edge_ext(
+  nw_mesh* mesh, const nw_mdot_opts* opts, const nw_mdot_extra_opts* extra);
+int nw_assemble_continuity_edge_ext(
+  nw_linsys* ls, const nw_continuity_opts* opts,
+  const nw_mdot_extra_opts* extra);
+
 typedef struct {
   double alpha, alpha_upw, ho_upwind, relax_fac;
   int32_t use_limiter;

@@ -85,6 +85,12 @@ class MomentumOpts(C.Structure):
                 ("diag_field", C.c_int32)]
 
 
+class MdotExtraOpts(C.Structure):
+    _fields_ = [("add_balanced_forcing", C.c_int32), ("gravity", C.c_double * 3),
+                ("source_field", C.c_int32), ("source_mask_field", C.c_int32),
+                ("needs_gcl", C.c_int32), ("edge_face_vel_mag_field", C.c_int32)]
+
+
 class MassBdfOpts(C.Structure):
     _fields_ = [("dt", C.c_double), ("gamma1", C.c_double),
                 ("gamma2", C.c_double), ("gamma3", C.c_double)] + [
@@ -114,7 +120,8 @@ ABI_SYMBOLS = [
     "nw_mesh_create", "nw_mesh_destroy", "nw_mesh_get_stats",
     "nw_field_register", "nw_field_find", "nw_field_upload",
     "nw_field_stage", "nw_field_commit", "nw_field_download", "nw_field_fill", "nw_field_device_view",
-    "nw_mesh_get_node_permutation", "nw_geometry_interior_hex8", "nw_geometry_interior_quad4", "nw_mdot_edge", "nw_peclet_edge",
+    "nw_mesh_get_node_permutation", "nw_geometry_interior_hex8", "nw_geometry_interior_quad4", "nw_mdot_edge",
+    "nw_mdot_edge_ext", "nw_assemble_continuity_edge_ext", "nw_peclet_edge",
     "nw_nodal_grad_edge", "nw_linsys_create", "nw_linsys_destroy",
     "nw_linsys_set_skipped_rows", "nw_linsys_build_edge_to_node_graph",
     "nw_linsys_finalize", "nw_linsys_get_sizes", "nw_linsys_get_graph",
@@ -182,6 +189,9 @@ def lib():
     L.nw_geometry_interior_hex8.argtypes = [vp, C.c_int64, vp, vp, C.c_int,
                                             C.c_int, C.c_int]
     L.nw_geometry_interior_quad4.argtypes = L.nw_geometry_interior_hex8.argtypes
+    L.nw_mdot_edge_ext.argtypes = [vp, C.POINTER(MdotOpts), C.POINTER(MdotExtraOpts)]
+    L.nw_assemble_continuity_edge_ext.argtypes = [
+        vp, C.POINTER(ContinuityOpts), C.POINTER(MdotExtraOpts)]
     L.nw_peclet_edge.argtypes = [vp, C.c_int, C.POINTER(PecletOpts)]
     L.nw_nodal_grad_edge.argtypes = [vp, C.c_int, C.c_int]
     L.nw_linsys_create.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
@@ -407,6 +417,25 @@ class Mesh:
 
     geometry_interior = geometry_interior_hex8
 
+    def extra_opts(self, gravity=None, source=None, source_mask=None,
+                   edge_face_vel_mag=None):
+        """nw_mdot_extra_opts: balanced forcing if gravity is given, GCL if the
+        edge_face_velocity_mag field name is given"""
+        x = MdotExtraOpts()
+        x.add_balanced_forcing = int(gravity is not None)
+        for d, gv in enumerate(gravity or ()):
+            x.gravity[d] = float(gv)
+        x.source_field = self.field_id(source) if source else -1
+        x.source_mask_field = self.field_id(source_mask) if source_mask else -1
+        x.needs_gcl = int(edge_face_vel_mag is not None)
+        x.edge_face_vel_mag_field = (self.field_id(edge_face_vel_mag)
+                                     if edge_face_vel_mag else -1)
+        return x
+
+    def mdot_edge_ext(self, extra, noc_fac=1.0, interp_together=1.0):
+        o = MdotOpts(noc_fac, interp_together)
+        _chk(lib().nw_mdot_edge_ext(self.h, C.byref(o), C.byref(extra)))
+
     def nodal_grad_edge(self, phi, grad):
         _chk(lib().nw_nodal_grad_edge(self.h, self.field_id(phi),
                                       self.field_id(grad)))
@@ -504,6 +533,14 @@ class LinearSystem:
         o = ContinuityOpts(dt, gamma1, noc_fac, interp_together,
                            solve_incompressible)
         _chk(lib().nw_assemble_continuity_edge(self.h, C.byref(o)))
+
+    def assemble_continuity_edge_ext(self, extra, dt=1.0, gamma1=1.0,
+                                     noc_fac=1.0, interp_together=1.0,
+                                     solve_incompressible=0.0):
+        o = ContinuityOpts(dt, gamma1, noc_fac, interp_together,
+                           solve_incompressible)
+        _chk(lib().nw_assemble_continuity_edge_ext(self.h, C.byref(o),
+                                                   C.byref(extra)))
 
     def assemble_scalar_edge(self, q, dqdx, dflux, alpha=0.0, alpha_upw=1.0,
                              ho_upwind=1.0, relax_fac=1.0, use_limiter=False,

@@ -177,6 +177,72 @@ mdot_core(
   return r;
 }
 
+/* mdot_core plus the optional terms of MdotEdgeAlg / ContinuityEdgeSolverAlg
+ * (src/ngp_algorithms/MdotEdgeAlg.C:153-163, 175-180;
+ * src/edge_kernels/ContinuityEdgeSolverAlg.C:147-158, 172-177): balanced
+ * buoyancy forcing (gravity, source, source mask) and the GCL term
+ * (edge_face_velocity_mag).  Used by the *_ext kernels only. */
+template <int ND>
+struct ContExtra
+{
+  bool balanced, gcl;
+  double gravity[ND];
+  double smaskL, smaskR;
+  double srcL[ND], srcR[ND];
+  double faceVelMag;
+};
+
+template <int ND>
+NW_HD MdotCore<ND>
+mdot_core_ext(
+  const ContNode<ND>& L,
+  const ContNode<ND>& R,
+  const ContExtra<ND>& x,
+  const double* av,
+  double nocFac,
+  double interpTogether)
+{
+  const double om_interpTogether = 1.0 - interpTogether;
+  MdotCore<ND> r;
+  const double invUdL = nw_rcp(L.ud), invUdR = nw_rcp(R.ud);
+  r.projTimeScale = 0.5 * (invUdL + invUdR);
+  r.rhoIp = 0.5 * (L.rho + R.rho);
+  double axdx = 0.0, asq = 0.0;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const double dxj = R.x[d] - L.x[d];
+    asq += av[d] * av[d];
+    axdx += av[d] * dxj;
+  }
+  const double inv_axdx = nw_rcp(axdx);
+  double tmdot = -r.projTimeScale * (R.p - L.p) * asq * inv_axdx;
+  if (x.balanced) {
+    const double masked_weights = 0.5 * (x.smaskL + x.smaskR);
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+      tmdot += r.projTimeScale * av[d] * x.gravity[d] * r.rhoIp * masked_weights;
+  }
+  if (x.gcl)
+    tmdot -= r.rhoIp * x.faceVelMag;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const double dxj = R.x[d] - L.x[d];
+    const double kxj = av[d] - asq * inv_axdx * dxj;
+    const double rhoUjIp = 0.5 * (R.rho * R.u[d] + L.rho * L.u[d]);
+    const double ujIp = 0.5 * (R.u[d] + L.u[d]);
+    double GjIp = 0.5 * (R.g[d] * invUdR + L.g[d] * invUdL);
+    if (x.balanced)
+      GjIp -= 0.5 * ((x.smaskR * x.srcR[d]) * invUdR + (x.smaskL * x.srcL[d]) * invUdL);
+    tmdot += (interpTogether * rhoUjIp + om_interpTogether * r.rhoIp * ujIp +
+              GjIp) *
+               av[d] -
+             kxj * GjIp * nocFac;
+  }
+  r.tmdot = tmdot;
+  r.asq_inv_axdx = asq * inv_axdx;
+  return r;
+}
+
 /* result: res[0] = lhsfac, res[1] = tmdot (scaled).
  * lhs = [[-f, +f], [+f, -f]], rhs = [-m, +m]. */
 template <int ND>

@@ -796,6 +796,53 @@ nw_mdot_edge(nw_mesh* mesh, const nw_mdot_opts* opts)
   return NW_OK;
 }
 
+/* device view of the optional mdot / continuity terms */
+static int
+bind_cont_extra(nw_mesh* mesh, const nw_mdot_extra_opts* x, ContExtraDev& ex)
+{
+  ex = ContExtraDev();
+  if (!x)
+    return fail(NW_ERR_ARG, "extra options: NULL");
+  const int nd = mesh->plan.ndim;
+  ex.balanced = x->add_balanced_forcing != 0;
+  ex.gcl = x->needs_gcl != 0;
+  for (int d = 0; d < nd; ++d)
+    ex.gravity[d] = x->gravity[d];
+  int rc;
+  if (ex.balanced)
+    if ((rc = bind_id(mesh, x->source_mask_field, NW_NODE, 1, &ex.smask)) ||
+        (rc = bind_id(mesh, x->source_field, NW_NODE, nd, ex.src)))
+      return rc;
+  if (ex.gcl)
+    if ((rc = bind_id(mesh, x->edge_face_vel_mag_field, NW_EDGE, 1, &ex.faceVelMag)))
+      return rc;
+  return NW_OK;
+}
+
+extern "C" int
+nw_mdot_edge_ext(
+  nw_mesh* mesh, const nw_mdot_opts* opts, const nw_mdot_extra_opts* extra)
+{
+  if (!mesh || !opts)
+    return fail(NW_ERR_ARG, "nw_mdot_edge_ext: NULL argument");
+  if (int rc = need_device(mesh->ctx, "nw_mdot_edge_ext"))
+    return rc;
+  NodeComps nc;
+  EdgeComps ec;
+  ContExtraDev ex;
+  int rc;
+  if ((rc = bind_cont_nodes(mesh, nc)) ||
+      (rc = bind_edge_common(mesh, ec, false, false)) ||
+      (rc = bind_cont_extra(mesh, extra, ex)))
+    return rc;
+  const double* out = nullptr;
+  if ((rc = bind(mesh, "mass_flow_rate", NW_EDGE, 1, &out)))
+    return rc;
+  NW_CUDA(launch_mdot_ext(
+    mesh->dev, nc, ec, ex, const_cast<double*>(out), *opts, mesh->ctx->stream));
+  return NW_OK;
+}
+
 extern "C" int
 nw_peclet_edge(nw_mesh* mesh, int viscosity_field, const nw_peclet_opts* opts)
 {
@@ -1231,6 +1278,37 @@ nw_assemble_continuity_edge(nw_linsys* ls, const nw_continuity_opts* opts)
     return rc;
   AtomicMapDev am{ls->dASlots.as<int32_t>(), ls->dARhsRows.as<int32_t>()};
   NW_CUDA(launch_continuity_atomic(mesh->dev, ls->dev, am, nc, ec, *opts, s));
+  return NW_OK;
+}
+
+extern "C" int
+nw_assemble_continuity_edge_ext(
+  nw_linsys* ls, const nw_continuity_opts* opts, const nw_mdot_extra_opts* extra)
+{
+  if (int rc = ls_ready(ls, "nw_assemble_continuity_edge_ext"))
+    return rc;
+  if (!opts)
+    return fail(NW_ERR_ARG, "nw_assemble_continuity_edge_ext: NULL options");
+  if (ls->numDof != 1 || ls->kind != NW_LINSYS_HYPRE)
+    return fail(
+      NW_ERR_ARG, "nw_assemble_continuity_edge_ext: needs a 1-dof hypre system");
+  nw_mesh* mesh = ls->mesh;
+  NodeComps nc;
+  EdgeComps ec;
+  ContExtraDev ex;
+  int rc;
+  if ((rc = bind_cont_nodes(mesh, nc)) ||
+      (rc = bind_edge_common(mesh, ec, false, false)) ||
+      (rc = bind_cont_extra(mesh, extra, ex)))
+    return rc;
+  if (ls->state != NW_LS_ACCUM)
+    if ((rc = materialize_zero(ls)))
+      return rc;
+  if ((rc = build_atomic_map(ls)))
+    return rc;
+  AtomicMapDev am{ls->dASlots.as<int32_t>(), ls->dARhsRows.as<int32_t>()};
+  NW_CUDA(launch_continuity_ext_atomic(
+    mesh->dev, ls->dev, am, nc, ec, ex, *opts, mesh->ctx->stream));
   return NW_OK;
 }
 

@@ -1079,6 +1079,118 @@ __global__ void __launch_bounds__(kTileThreads) peclet_tile_kernel(
 }
 
 /* ------------------------------------------------------------------ */
+/*  mdot / continuity with the optional terms (balanced forcing, GCL)  */
+/* ------------------------------------------------------------------ */
+
+template <int ND>
+__device__ __forceinline__ ContExtra<ND>
+load_cont_extra(const ContExtraDev& ex, int gl, int gr, int64_t es)
+{
+  ContExtra<ND> x;
+  x.balanced = ex.balanced != 0;
+  x.gcl = ex.gcl != 0;
+  x.smaskL = x.smaskR = 0.0;
+  x.faceVelMag = 0.0;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    x.gravity[d] = ex.gravity[d];
+    x.srcL[d] = x.srcR[d] = 0.0;
+  }
+  if (x.balanced) {
+    x.smaskL = __ldg(ex.smask + gl);
+    x.smaskR = __ldg(ex.smask + gr);
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      x.srcL[d] = __ldg(ex.src[d] + gl);
+      x.srcR[d] = __ldg(ex.src[d] + gr);
+    }
+  }
+  if (x.gcl)
+    x.faceVelMag = __ldg(ex.faceVelMag + es);
+  return x;
+}
+
+/* MdotEdgeAlg with the optional terms: every tile-edge slot (both copies of a
+ * cut edge) is written, like mdot_tile_kernel */
+template <int ND>
+__global__ void __launch_bounds__(kTileThreads) mdot_ext_kernel(
+  const MeshPlanDev mp, const NodeComps nc, const EdgeComps ec,
+  const ContExtraDev ex, double* __restrict__ mdotOut, const nw_mdot_opts o)
+{
+  using P = ContinuityP<ND>;
+  const TileHdr h = mp.tiles[blockIdx.x];
+  const GmemLd ld{&nc};
+  for (int j = threadIdx.x; j < h.nEdges; j += blockDim.x) {
+    const int64_t es = (int64_t)h.edge0 + j;
+    const uint32_t v = __ldg(mp.lr + es);
+    const int gl = global_slot(h, mp.haloNodes, (int)(v & 0xffffu));
+    const int gr = global_slot(h, mp.haloNodes, (int)(v >> 16));
+    double av[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+      av[d] = __ldg(ec.area[d] + es);
+    ContNode<ND> L, R;
+    P::load(ld, gl, L);
+    P::load(ld, gr, R);
+    const ContExtra<ND> x = load_cont_extra<ND>(ex, gl, gr, es);
+    mdotOut[es] = mdot_core_ext<ND>(L, R, x, av, o.noc_fac, o.interp_together).tmdot;
+  }
+}
+
+/* ContinuityEdgeSolverAlg with the optional terms, atomic scatter through the
+ * slot map (primary copies only) */
+template <int ND>
+__global__ void __launch_bounds__(kTileThreads) continuity_ext_atomic_kernel(
+  const MeshPlanDev mp, const LsPlanDev lp, const AtomicMapDev am,
+  const NodeComps nc, const EdgeComps ec, const ContExtraDev ex,
+  const nw_continuity_opts o)
+{
+  using P = ContinuityP<ND>;
+  const TileHdr h = mp.tiles[blockIdx.x];
+  const GmemLd ld{&nc};
+  for (int j = threadIdx.x; j < h.nEdges; j += blockDim.x) {
+    const int64_t es = (int64_t)h.edge0 + j;
+    if (!mp.primary[es])
+      continue;
+    const uint32_t v = __ldg(mp.lr + es);
+    const int gl = global_slot(h, mp.haloNodes, (int)(v & 0xffffu));
+    const int gr = global_slot(h, mp.haloNodes, (int)(v >> 16));
+    double av[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+      av[d] = __ldg(ec.area[d] + es);
+    ContNode<ND> L, R;
+    P::load(ld, gl, L);
+    P::load(ld, gr, R);
+    const ContExtra<ND> x = load_cont_extra<ND>(ex, gl, gr, es);
+    const MdotCore<ND> c =
+      mdot_core_ext<ND>(L, R, x, av, o.noc_fac, o.interp_together);
+    /* scaling as continuity_edge */
+    const double solveInc = o.solve_incompressible;
+    const double denScale = nw_rcp(c.rhoIp) * solveInc + (1.0 - solveInc);
+    const double invTauScale = o.gamma1 * nw_rcp(o.dt);
+    double tmdot = c.tmdot;
+    tmdot *= invTauScale;
+    tmdot *= denScale;
+    const double lhsfac = -c.asq_inv_axdx * c.projTimeScale * denScale * invTauScale;
+    const int4 s4 = __ldg(reinterpret_cast<const int4*>(am.slots) + es);
+    const int2 r2 = __ldg(reinterpret_cast<const int2*>(am.rhsRows) + es);
+    if (s4.x >= 0) {
+      atomicAdd(lp.values + s4.x, -lhsfac);
+      atomicAdd(lp.rhs + r2.x, -tmdot);
+    }
+    if (s4.y >= 0)
+      atomicAdd(lp.values + s4.y, lhsfac);
+    if (s4.z >= 0)
+      atomicAdd(lp.values + s4.z, lhsfac);
+    if (s4.w >= 0) {
+      atomicAdd(lp.values + s4.w, -lhsfac);
+      atomicAdd(lp.rhs + r2.y, tmdot);
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ */
 /*  nodal gradient                                                     */
 /* ------------------------------------------------------------------ */
 
@@ -2628,6 +2740,33 @@ launch_mdot_tile(
     mdot_tile_kernel<2>
       <<<mp.nTiles, kTileThreads, bytes, s>>>(mp, nc, ec, mdotOut, o);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_mdot_ext(
+  const MeshPlanDev& mp, const NodeComps& nc, const EdgeComps& ec,
+  const ContExtraDev& ex, double* mdotOut, nw_mdot_opts o, cudaStream_t s)
+{
+  if (mp.ndim == 3)
+    mdot_ext_kernel<3><<<mp.nTiles, kTileThreads, 0, s>>>(mp, nc, ec, ex, mdotOut, o);
+  else
+    mdot_ext_kernel<2><<<mp.nTiles, kTileThreads, 0, s>>>(mp, nc, ec, ex, mdotOut, o);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_continuity_ext_atomic(
+  const MeshPlanDev& mp, const LsPlanDev& lp, const AtomicMapDev& am,
+  const NodeComps& nc, const EdgeComps& ec, const ContExtraDev& ex,
+  nw_continuity_opts o, cudaStream_t s)
+{
+  if (mp.ndim == 3)
+    continuity_ext_atomic_kernel<3>
+      <<<mp.nTiles, kTileThreads, 0, s>>>(mp, lp, am, nc, ec, ex, o);
+  else
+    continuity_ext_atomic_kernel<2>
+      <<<mp.nTiles, kTileThreads, 0, s>>>(mp, lp, am, nc, ec, ex, o);
   return cudaGetLastError();
 }
 

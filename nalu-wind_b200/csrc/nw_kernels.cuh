@@ -71,6 +71,27 @@ struct EdgeComps
   const double* pecfac;
 };
 
+/* optional mdot / continuity terms (balanced buoyancy forcing, GCL): device
+ * view of nw_mdot_extra_opts */
+struct ContExtraDev
+{
+  int balanced = 0, gcl = 0;
+  double gravity[3] = {0.0, 0.0, 0.0};
+  const double* smask = nullptr;  /* nodal, 1 comp */
+  const double* src[3] = {nullptr, nullptr, nullptr}; /* nodal, ndim comps */
+  const double* faceVelMag = nullptr; /* edge (tile-edge slots), 1 comp */
+};
+/* extended variants: direct gathers, one thread per tile-edge; continuity
+ * scatters through the atomic slot map (values / rhs must be zeroed or hold
+ * what is to be accumulated onto) */
+cudaError_t launch_mdot_ext(
+  const MeshPlanDev& mp, const NodeComps& nc, const EdgeComps& ec,
+  const ContExtraDev& ex, double* mdotOut, nw_mdot_opts o, cudaStream_t s);
+cudaError_t launch_continuity_ext_atomic(
+  const MeshPlanDev& mp, const LsPlanDev& lp, const AtomicMapDev& am,
+  const NodeComps& nc, const EdgeComps& ec, const ContExtraDev& ex,
+  nw_continuity_opts o, cudaStream_t s);
+
 /* every launcher returns the cudaError_t of the launch */
 cudaError_t launch_mdot_tile(
   const MeshPlanDev& mp, const NodeComps& nc, const EdgeComps& ec,

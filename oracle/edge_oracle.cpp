@@ -1365,6 +1365,83 @@ orc_geometry_interior_quad4(
   }
 }
 
+/* MdotEdgeAlg / ContinuityEdgeSolverAlg with the optional terms:
+ * balanced buoyancy forcing (use_balanced_buoyancy_force; gravity, fields
+ * buoyancy_source / buoyancy_source_mask) and the GCL term of deforming meshes
+ * (edge_face_velocity_mag).  src/ngp_algorithms/MdotEdgeAlg.C:117-190 (terms
+ * :153-163, :175-180); src/edge_kernels/ContinuityEdgeSolverAlg.C:109-194
+ * (terms :147-158, :172-177).  sink == NULL: MdotEdgeAlg (writes mdot);
+ * else ContinuityEdgeSolverAlg (scaled tmdot, 2x2 block into the sink). */
+extern "C" void
+orc_mdot_continuity_edge_ext(
+  int ndim, int64_t n_edges, const int32_t* edge_nodes, const double* coords,
+  const double* velocity, const double* gpdx, const double* density,
+  const double* pressure, const double* udiag, const double* edge_area,
+  double noc_fac, double interp_together, int add_balanced_forcing,
+  const double* gravity, const double* source, const double* source_mask,
+  int needs_gcl, const double* edge_face_vel_mag,
+  /* continuity only: */ double dt, double gamma1, double solve_incompressible,
+  double* mdot, orc_applier* sink)
+{
+  const double om_interp = 1.0 - interp_together;
+  const double tauScale = dt / gamma1;
+  const double om_solveInc = 1.0 - solve_incompressible;
+  for (int64_t e = 0; e < n_edges; ++e) {
+    double av[kMaxDim];
+    for (int d = 0; d < ndim; ++d)
+      av[d] = edge_area[e * ndim + d];
+    const int32_t nodes[2] = {edge_nodes[2 * e], edge_nodes[2 * e + 1]};
+    const int64_t nL = nodes[0], nR = nodes[1];
+    const double pressureL = pressure[nL], pressureR = pressure[nR];
+    const double densityL = density[nL], densityR = density[nR];
+    const double udiagL = udiag[nL], udiagR = udiag[nR];
+    const double projTimeScale = 0.5 * (1.0 / udiagL + 1.0 / udiagR);
+    const double rhoIp = 0.5 * (densityL + densityR);
+    const double denScale = (1.0 / rhoIp) * solve_incompressible + om_solveInc;
+    double axdx = 0.0, asq = 0.0;
+    for (int d = 0; d < ndim; ++d) {
+      const double dxj = coords[nR * ndim + d] - coords[nL * ndim + d];
+      asq += av[d] * av[d];
+      axdx += av[d] * dxj;
+    }
+    const double inv_axdx = 1.0 / axdx;
+    double tmdot = -projTimeScale * (pressureR - pressureL) * asq * inv_axdx;
+    if (add_balanced_forcing) {
+      const double masked_weights = 0.5 * (source_mask[nL] + source_mask[nR]);
+      for (int d = 0; d < ndim; ++d)
+        tmdot += projTimeScale * av[d] * gravity[d] * rhoIp * masked_weights;
+    }
+    if (needs_gcl)
+      tmdot -= rhoIp * edge_face_vel_mag[e];
+    for (int d = 0; d < ndim; ++d) {
+      const double dxj = coords[nR * ndim + d] - coords[nL * ndim + d];
+      const double kxj = av[d] - asq * inv_axdx * dxj;
+      const double rhoUjIp = 0.5 * (densityR * velocity[nR * ndim + d] +
+                                    densityL * velocity[nL * ndim + d]);
+      const double ujIp =
+        0.5 * (velocity[nR * ndim + d] + velocity[nL * ndim + d]);
+      double GjIp =
+        0.5 * (gpdx[nR * ndim + d] / udiagR + gpdx[nL * ndim + d] / udiagL);
+      if (add_balanced_forcing)
+        GjIp -= 0.5 * ((source_mask[nR] * source[nR * ndim + d]) / (udiagR) +
+                       (source_mask[nL] * source[nL * ndim + d]) / (udiagL));
+      tmdot +=
+        (interp_together * rhoUjIp + om_interp * rhoIp * ujIp + GjIp) * av[d] -
+        kxj * GjIp * noc_fac;
+    }
+    if (!sink) {
+      mdot[e] = tmdot;
+      continue;
+    }
+    tmdot /= tauScale;
+    tmdot *= denScale;
+    const double lhsfac = -asq * inv_axdx * projTimeScale * denScale / tauScale;
+    const double lhs[4] = {-lhsfac, +lhsfac, +lhsfac, -lhsfac};
+    const double rhs[2] = {-tmdot, tmdot};
+    sink->apply(2, nodes, rhs, lhs, 2);
+  }
+}
+
 /* WallDistEdgeSolverAlg::execute, src/edge_kernels/WallDistEdgeSolverAlg.C:28-66 */
 extern "C" void
 orc_wall_dist_edge(

@@ -175,6 +175,18 @@ void orc_geometry_interior_quad4(
   const double* coords, int64_t n_edges, const int32_t* edge_nodes,
   double* dual_nodal_volume, double* elem_volume, double* edge_area);
 
+/* MdotEdgeAlg (sink == NULL) / ContinuityEdgeSolverAlg (sink != NULL) with the
+ * optional balanced-buoyancy and GCL terms (MdotEdgeAlg.C:153-163, 175-180;
+ * ContinuityEdgeSolverAlg.C:147-158, 172-177) */
+void orc_mdot_continuity_edge_ext(
+  int ndim, int64_t n_edges, const int32_t* edge_nodes, const double* coords,
+  const double* velocity, const double* gpdx, const double* density,
+  const double* pressure, const double* udiag, const double* edge_area,
+  double noc_fac, double interp_together, int add_balanced_forcing,
+  const double* gravity, const double* source, const double* source_mask,
+  int needs_gcl, const double* edge_face_vel_mag, double dt, double gamma1,
+  double solve_incompressible, double* mdot, orc_applier* sink);
+
 void orc_applier_destroy(orc_applier*);
 
 /* ---- edge algorithms ---- */

@@ -426,3 +426,31 @@ def geometry_interior_quad4(elem_nodes, coords, edge_nodes, n_nodes, elem_owned=
       xy.ctypes.data, en.size // 2, en.ctypes.data, dnv.ctypes.data,
       ev.ctypes.data, area.ctypes.data)
     return dnv, ev, area
+
+
+def mdot_continuity_edge_ext(ndim, edge_nodes, coords, vel, gpdx, rho, p, udiag,
+                             area, noc_fac=1.0, interp_together=1.0,
+                             gravity=None, source=None, source_mask=None,
+                             edge_face_vel_mag=None, dt=1.0, gamma1=1.0,
+                             solve_incompressible=0.0, sink=None):
+    """MdotEdgeAlg (sink None: returns mdot) / ContinuityEdgeSolverAlg with the
+    optional balanced-forcing (gravity + source + source_mask) and GCL
+    (edge_face_vel_mag) terms"""
+    en = np.ascontiguousarray(edge_nodes, dtype=np.int32)
+    ne = en.size // 2
+    bal = gravity is not None
+    gcl = edge_face_vel_mag is not None
+    z1 = np.zeros(1)
+    keep, ptrs = _f64s(coords, vel, gpdx, rho, p, udiag, area)
+    k2, p2 = _f64s(gravity if bal else np.zeros(3), source if bal else z1,
+                   source_mask if bal else z1, edge_face_vel_mag if gcl else z1)
+    out = np.zeros(ne)
+    f = lib().orc_mdot_continuity_edge_ext
+    f.argtypes = ([C.c_int, C.c_int64, C.c_void_p] + [C.c_void_p] * 7 +
+                  [C.c_double, C.c_double, C.c_int] + [C.c_void_p] * 3 +
+                  [C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double,
+                   C.c_void_p, C.c_void_p])
+    f(ndim, ne, en.ctypes.data, *ptrs, noc_fac, interp_together, int(bal),
+      p2[0], p2[1], p2[2], int(gcl), p2[3], dt, gamma1, solve_incompressible,
+      out.ctypes.data, None if sink is None else sink.h)
+    return out

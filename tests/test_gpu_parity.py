@@ -538,6 +538,58 @@ def test_mass_bdf_node_after_edge_assembly_vs_oracle(P, ctx, kind):
     mesh.close()
 
 
+@pytest.mark.parametrize("which", ["none", "balanced", "gcl", "both"])
+def test_mdot_continuity_optional_terms_vs_oracle(P, ctx, which):
+    """balanced buoyancy forcing and GCL terms (MdotEdgeAlg.C:153-163, 175-180;
+    ContinuityEdgeSolverAlg.C:147-158, 172-177) through the *_ext entries"""
+    case = pu.Case(dims=(8, 7, 6), warp=0.12, shuffle_bucket=64)
+    mesh = case.box.make_mesh(ctx, tile_nodes=48)
+    pu.upload_state(P, mesh, case)
+    f, b = case.fields, case.box
+    rng = np.random.default_rng(5)
+    src = rng.standard_normal((case.n_nodes, 3))
+    smask = (rng.random(case.n_nodes) > 0.3).astype(np.float64)
+    fvm = 0.1 * rng.standard_normal(case.n_edges)
+    mesh.put("buoyancy_source", P.NW_NODE, src)
+    mesh.put("buoyancy_source_mask", P.NW_NODE, smask)
+    mesh.put("edge_face_velocity_mag", P.NW_EDGE, fvm)
+    bal = which in ("balanced", "both")
+    gcl = which in ("gcl", "both")
+    grav = (0.0, 0.3, -9.81)
+    x = mesh.extra_opts(gravity=grav if bal else None,
+                        source="buoyancy_source" if bal else None,
+                        source_mask="buoyancy_source_mask" if bal else None,
+                        edge_face_vel_mag="edge_face_velocity_mag" if gcl else None)
+    okw = dict(gravity=np.array(grav) if bal else None, source=src if bal else None,
+               source_mask=smask if bal else None,
+               edge_face_vel_mag=fvm if gcl else None)
+    args = (3, case.edges, b.coords, f["velocity"], f["dpdx"], f["density"],
+            f["pressure"], f["momentum_diag"], case.area)
+    mesh.mdot_edge_ext(x, 1.0, 1.0)
+    got = mesh.download("mass_flow_rate")
+    ref = orc.mdot_continuity_edge_ext(*args, **okw)
+    assert pu.scaled_err(got, ref, np.abs(ref) + 1e-3 * np.max(np.abs(ref))) < 1
+    if which == "none":  # the default entry gives the same field
+        mesh.mdot_edge(1.0, 1.0)
+        assert pu.scaled_err(mesh.download("mass_flow_rate"), ref,
+                             np.abs(ref) + 1e-3 * np.max(np.abs(ref))) < 1
+    g = case.oracle_graph()
+    sink = orc.HypreSink(g, b.hid)
+    orc.mdot_continuity_edge_ext(*args, dt=pu.DT, gamma1=pu.GAMMA1, sink=sink, **okw)
+    ls = P.LinearSystem(mesh)
+    ls.buildEdgeToNodeGraph()
+    ls.finalizeLinearSystem()
+    ls.zeroSystem()
+    ls.assemble_continuity_edge_ext(x, **pu.CONT_OPTS)
+    vals, rhs = ls.values()
+    ov, orhs = sink.get()
+    av_, arhs = sink.get_abs()
+    assert pu.scaled_err(vals, ov, av_) < 1
+    assert pu.scaled_err(rhs, orhs, arhs) < 1
+    ls.close()
+    mesh.close()
+
+
 def test_geometry_interior_hex8(P, ctx):
     """GeometryInteriorAlg<Hex8> on the device: the reference's unit-cube gold
     (UnitTestGeometryAlg.C:25-101, tol 1e-16) and a warped, stretched box vs the
