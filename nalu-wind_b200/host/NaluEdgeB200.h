@@ -33,6 +33,7 @@
 
 #include <map>
 #include <stdexcept>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -131,10 +132,36 @@ public:
   /* time integrator scalars */
   double get_time_step() const { return dt_; }
   double get_gamma1() const { return gamma1_; }
+  double get_gamma2() const { return gamma2_; }
+  double get_gamma3() const { return gamma3_; }
   void set_time_step(double dt, double gamma1)
   {
     dt_ = dt;
     gamma1_ = gamma1;
+  }
+  /* TimeIntegrator BDF coefficients (BDF1: 1, -1, 0; BDF2: 1.5, -2, 0.5) */
+  void set_bdf(double dt, double gamma1, double gamma2, double gamma3)
+  {
+    dt_ = dt;
+    gamma1_ = gamma1;
+    gamma2_ = gamma2;
+    gamma3_ = gamma3;
+  }
+  /* field_of_state: states of field F are registered as F (NP1), F_n, F_nm1;
+   * a two-state field has no F_nm1 and uses F_n (number_of_states() == 2,
+   * src/node_kernels/ScalarMassBDFNodeKernel.C:36-40) */
+  bool has_field(const std::string& name) const
+  {
+    int id;
+    return nw_field_find(mesh_, name.c_str(), &id) == NW_OK;
+  }
+  int state_ordinal(const std::string& name, int state /* 0 NP1, 1 N, 2 NM1 */) const
+  {
+    if (state == 0)
+      return field_ordinal(name);
+    if (state == 2 && has_field(name + "_nm1"))
+      return field_ordinal(name + "_nm1");
+    return field_ordinal(name + "_n");
   }
 
   /* option getters, same names and defaults as the reference */
@@ -215,7 +242,7 @@ private:
   nw_ctx* ctx_ = nullptr;
   nw_mesh* mesh_ = nullptr;
   int ndim_ = 3;
-  double dt_ = 1.0, gamma1_ = 1.0;
+  double dt_ = 1.0, gamma1_ = 1.0, gamma2_ = -1.0, gamma3_ = 0.0;
 };
 
 /* include/LinearSystem.h:88-256 (assembly part) */
@@ -515,6 +542,203 @@ public:
 private:
   std::string phi_, gradPhi_;
 };
+/* src/edge_kernels/WallDistEdgeSolverAlg.C */
+class WallDistEdgeSolverAlg : public AssembleEdgeSolverAlgorithm
+{
+public:
+  using AssembleEdgeSolverAlgorithm::AssembleEdgeSolverAlgorithm;
+  void execute() override
+  {
+    nw_check(nw_assemble_wall_dist_edge(eqSystem_->linsys_->handle()));
+  }
+};
+
+/* Node kernels (src/node_kernels/) as the reference registers them:
+ *   nodeAlg.add_kernel<ScalarMassBDFNodeKernel>("turbulent_ke");
+ * Time states of a field follow Realm::state_ordinal. */
+struct NodeKernel
+{
+  virtual ~NodeKernel() = default;
+  virtual void execute(Realm& realm, LinearSystem& linsys) = 0;
+};
+
+namespace detail {
+inline nw_mass_bdf_opts
+mass_opts(Realm& realm, const std::string& q, bool hasQ, bool momentum)
+{
+  nw_mass_bdf_opts o{};
+  o.dt = realm.get_time_step();
+  o.gamma1 = realm.get_gamma1();
+  o.gamma2 = realm.get_gamma2();
+  o.gamma3 = realm.get_gamma3();
+  o.q_nm1 = o.q_n = o.q_np1 = -1;
+  if (hasQ) {
+    o.q_np1 = realm.state_ordinal(q, 0);
+    o.q_n = realm.state_ordinal(q, 1);
+    o.q_nm1 = realm.state_ordinal(q, 2);
+  }
+  o.rho_np1 = realm.state_ordinal("density", 0);
+  o.rho_n = realm.state_ordinal("density", 1);
+  o.rho_nm1 = realm.state_ordinal("density", 2);
+  /* populate_dnv_states: a static mesh has one dual_nodal_volume state */
+  const bool moving = realm.has_field("dual_nodal_volume_n");
+  o.dnv_np1 = realm.state_ordinal("dual_nodal_volume", 0);
+  o.dnv_n = moving ? realm.state_ordinal("dual_nodal_volume", 1) : o.dnv_np1;
+  o.dnv_nm1 = moving ? realm.state_ordinal("dual_nodal_volume", 2) : o.dnv_np1;
+  o.dpdx = momentum ? realm.field_ordinal("dpdx") : -1;
+  return o;
+}
+} // namespace detail
+
+/* src/node_kernels/ScalarMassBDFNodeKernel.C */
+class ScalarMassBDFNodeKernel : public NodeKernel
+{
+public:
+  explicit ScalarMassBDFNodeKernel(const std::string& scalarQ) : q_(scalarQ) {}
+  void execute(Realm& realm, LinearSystem& linsys) override
+  {
+    const nw_mass_bdf_opts o = detail::mass_opts(realm, q_, true, false);
+    nw_check(nw_assemble_mass_bdf_node(linsys.handle(), NW_MASS_SCALAR, &o));
+  }
+
+private:
+  std::string q_;
+};
+
+/* src/node_kernels/MomentumMassBDFNodeKernel.C */
+class MomentumMassBDFNodeKernel : public NodeKernel
+{
+public:
+  void execute(Realm& realm, LinearSystem& linsys) override
+  {
+    const nw_mass_bdf_opts o = detail::mass_opts(realm, "velocity", true, true);
+    nw_check(nw_assemble_mass_bdf_node(linsys.handle(), NW_MASS_MOMENTUM, &o));
+  }
+};
+
+/* src/node_kernels/ContinuityMassBDFNodeKernel.C */
+class ContinuityMassBDFNodeKernel : public NodeKernel
+{
+public:
+  void execute(Realm& realm, LinearSystem& linsys) override
+  {
+    const nw_mass_bdf_opts o = detail::mass_opts(realm, "", false, false);
+    nw_check(nw_assemble_mass_bdf_node(linsys.handle(), NW_MASS_CONTINUITY, &o));
+  }
+};
+
+/* src/node_kernels/WallDistNodeKernel.C */
+class WallDistNodeKernel : public NodeKernel
+{
+public:
+  void execute(Realm& realm, LinearSystem& linsys) override
+  {
+    nw_check(nw_assemble_wall_dist_node(
+      linsys.handle(), realm.field_ordinal("dual_nodal_volume")));
+  }
+};
+
+/* src/AssembleNGPNodeSolverAlgorithm.C */
+class AssembleNGPNodeSolverAlgorithm : public SolverAlgorithm
+{
+public:
+  using SolverAlgorithm::SolverAlgorithm;
+  /* the reference's node graph (one (row,row) entry per node) is contained in
+   * the edge graph of this path */
+  void initialize_connectivity() override {}
+  template <typename T, class... Args>
+  void add_kernel(Args&&... args)
+  {
+    nodeKernels_.emplace_back(new T(std::forward<Args>(args)...));
+  }
+  void execute() override
+  {
+    for (auto& k : nodeKernels_)
+      k->execute(realm_, *eqSystem_->linsys_);
+  }
+
+private:
+  std::vector<std::unique_ptr<NodeKernel>> nodeKernels_;
+};
+
+/* src/FixPressureAtNodeAlgorithm.C:57-121: reset the row of the reference
+ * node, then sum lhs = 1, rhs = refPressure - p into it */
+class FixPressureAtNodeAlgorithm : public Algorithm
+{
+public:
+  FixPressureAtNodeAlgorithm(
+    Realm& realm, EquationSystem* eqSystem, int32_t targetNode,
+    double refPressure, double pressureAtNode)
+    : Algorithm(realm),
+      eqSystem_(eqSystem),
+      targetNode_(targetNode),
+      refPressure_(refPressure),
+      pressureN_(pressureAtNode)
+  {
+  }
+  /* d_scratch: device memory for one node index + two doubles (the caller's
+   * device allocator; this header stays free of CUDA runtime calls) */
+  void execute(int32_t* d_node, double* d_lhs, double* d_rhs)
+  {
+    eqSystem_->linsys_->resetRows({targetNode_}, 0, 1);
+    eqSystem_->linsys_->sumInto(1, 1, d_node, d_lhs, d_rhs);
+  }
+  void execute() override
+  {
+    throw std::runtime_error(
+      "FixPressureAtNodeAlgorithm: pass device scratch holding {node}, {1.0}, "
+      "{refPressure - p} to execute(d_node, d_lhs, d_rhs)");
+  }
+  double rhs_value() const { return refPressure_ - pressureN_; }
+
+private:
+  EquationSystem* eqSystem_;
+  int32_t targetNode_;
+  double refPressure_, pressureN_;
+};
+
+/* src/ngp_algorithms/GeometryAlgDriver.C + GeometryInteriorAlg.C: pre_work
+ * zero-fill, interior element blocks, shared-node sum of the volumes */
+class GeometryAlgDriver : public Algorithm
+{
+public:
+  using Algorithm::Algorithm;
+  /* one call per element block; npe = 8 (Hex8) or 4 (2-D Quad4) */
+  void register_elem_block(
+    int npe, std::vector<int32_t> elemNodes, std::vector<unsigned char> owned = {})
+  {
+    blocks_.push_back({npe, std::move(elemNodes), std::move(owned)});
+  }
+  void execute() override
+  {
+    const int x = realm_.field_ordinal("coordinates");
+    const int v = realm_.field_ordinal("dual_nodal_volume");
+    const int a = realm_.field_ordinal("edge_area_vector");
+    nw_check(nw_field_fill(realm_.mesh(), v, 0.0));
+    nw_check(nw_field_fill(realm_.mesh(), a, 0.0));
+    for (auto& b : blocks_) {
+      const int64_t n = (int64_t)b.nodes.size() / b.npe;
+      const unsigned char* ow = b.owned.empty() ? nullptr : b.owned.data();
+      if (b.npe == 8)
+        nw_check(nw_geometry_interior_hex8(
+          realm_.mesh(), n, b.nodes.data(), ow, x, v, a));
+      else
+        nw_check(nw_geometry_interior_quad4(
+          realm_.mesh(), n, b.nodes.data(), ow, x, v, a));
+    }
+    nw_check(nw_field_parallel_sum(realm_.mesh(), v));
+  }
+
+private:
+  struct Block
+  {
+    int npe;
+    std::vector<int32_t> nodes;
+    std::vector<unsigned char> owned;
+  };
+  std::vector<Block> blocks_;
+};
+
 using ScalarNodalGradEdgeAlg = NodalGradEdgeAlg<ScalarFieldType, VectorFieldType>;
 using VectorNodalGradEdgeAlg = NodalGradEdgeAlg<VectorFieldType, TensorFieldType>;
 using TensorNodalGradEdgeAlg = VectorNodalGradEdgeAlg;
