@@ -283,6 +283,68 @@ def test_ragged_inputs_isolated_nodes_and_no_edges(P, ctx, n_edges):
     mesh.close()
 
 
+@pytest.mark.parametrize("seed", [0, 2, 5, 7, 11, 13, 17, 19])
+def test_fuzz_random_graphs_on_device(P, ctx, seed):
+    """the seeded random unstructured meshes of tests/test_plan_fuzz_cpu.py
+    (periodic aliases -> several edges per (row, column) slot, isolated nodes,
+    ragged rows, tile sizes 1..256) through the CUDA kernels"""
+    import test_plan_fuzz_cpu as fz
+    case = fz.FuzzCase(seed)
+    rng = np.random.default_rng(2000 + seed)
+    tile = int(rng.choice([1, 2, 3, 5, 8, 16, 33, 64, 256]))
+    mesh = case.box.make_mesh(ctx, tile_nodes=tile)
+    pu.upload_state(P, mesh, case)
+    f, b = case.fields, case.box
+    g = case.oracle_graph()
+    omdot = case.oracle_mdot()
+    opec = case.oracle_pecfac(orc.peclet("classic", 1.0))
+    mesh.mdot_edge(1.0, 1.0)
+    if case.n_edges:
+        got = mesh.download("mass_flow_rate")
+        assert pu.scaled_err(got, omdot,
+                             np.abs(omdot) + 1e-3 * np.max(np.abs(omdot))) < 1
+        mesh.upload("mass_flow_rate", omdot)
+        mesh.upload("peclet_factor", opec)
+    mesh.register("g_u", P.NW_NODE, 9)
+    mesh.nodal_grad_edge("velocity", "g_u")
+    got = mesh.download("g_u")
+    ref = orc.nodal_grad_edge(3, 3, case.edges, f["velocity"], case.area,
+                              f["dual_nodal_volume"], case.n_nodes)
+    mag = np.abs(orc.nodal_grad_edge(
+        3, 3, case.edges, np.abs(f["velocity"]), np.abs(case.area),
+        f["dual_nodal_volume"], case.n_nodes)) + 1e-3 * (np.max(np.abs(ref)) + 1e-300)
+    assert pu.scaled_err(got.reshape(ref.shape), ref, mag) < 1
+    oc = pu.oracle_continuity(case, g)
+    om = pu.oracle_momentum(case, g, omdot, opec, uvw=True)
+    for mode in (0, 1):
+        ls = P.LinearSystem(mesh)
+        ls.set_scatter_mode(mode)
+        ls.buildEdgeToNodeGraph()
+        ls.finalizeLinearSystem()
+        ls.zeroSystem()
+        ls.assemble_continuity_edge(**pu.CONT_OPTS)
+        vals, rhs = ls.values()
+        ov, orhs = oc.get()
+        av_, arhs = oc.get_abs()
+        assert pu.scaled_err(vals, ov, av_) < 1
+        assert pu.scaled_err(rhs, orhs, arhs) < 1
+        ls.close()
+        ls = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE_UVW, 3)
+        ls.set_scatter_mode(mode)
+        ls.buildEdgeToNodeGraph()
+        ls.finalizeLinearSystem()
+        ls.zeroSystem()
+        ls.assemble_momentum_edge("viscosity", fuse_peclet=(mode == 0),
+                                  pf=P.peclet_fn("classic", 1.0), **pu.MOM_OPTS)
+        vals, rhs = ls.values()
+        ov, orhs = om.get()
+        av_, arhs = om.get_abs()
+        assert pu.scaled_err(vals, ov, av_) < 1
+        assert pu.scaled_err(rhs, orhs, arhs) < 1
+        ls.close()
+    mesh.close()
+
+
 def test_monolithic_momentum_vs_oracle(P, ctx):
     case = pu.Case(dims=(10, 9, 7))
     mesh = case.box.make_mesh(ctx, tile_nodes=64)
