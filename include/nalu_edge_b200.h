@@ -82,7 +82,9 @@ int nw_ctx_comm_init(nw_ctx* ctx, const void* unique_id, int nranks, int rank);
  * it): an exchange is then a push kernel (pack + remote stores + release flag)
  * and a pull kernel (acquire wait + ordered add) instead of pack / ncclSend /
  * ncclRecv / unpack.  All ranks use the same transport (agreed collectively);
- * results are bit-identical between the two. */
+ * results are bit-identical between the two.  The mailbox's window reuse
+ * assumes that all exchanges of a context involve the same neighbour ranks
+ * (slab-type decompositions); otherwise run with NW_P2P=0. */
 typedef enum {
   NW_TRANSPORT_NONE = 0,       /* single rank / structure not built yet */
   NW_TRANSPORT_NCCL = 1,
