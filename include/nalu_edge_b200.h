@@ -541,6 +541,9 @@ int nw_linsys_get_values(nw_linsys* ls, double* values, double* rhs);
  * deterministic); feeds the nonlinear residual norm
  * (src/HypreLinearSystem.C:2534, 2611-2638).  out[num_rhs]. */
 int nw_linsys_rhs_norm2(nw_linsys* ls, double* out);
+/* the same summed over all ranks (one ncclAllReduce of num_rhs doubles): the
+ * squared nonlinear residual norm of the whole system.  Collective. */
+int nw_linsys_rhs_norm2_global(nw_linsys* ls, double* out);
 
 #ifdef __cplusplus
 }

@@ -131,7 +131,7 @@ ABI_SYMBOLS = [
     "nw_assemble_mass_bdf_node", "nw_assemble_wall_dist_edge",
     "nw_assemble_wall_dist_node", "nw_linsys_write_preassembly_files", "nw_linsys_sum_into", "nw_linsys_reset_rows",
     "nw_linsys_apply_dirichlet_bcs", "nw_linsys_load_complete",
-    "nw_linsys_device_arrays", "nw_linsys_get_values", "nw_linsys_rhs_norm2",
+    "nw_linsys_device_arrays", "nw_linsys_get_values", "nw_linsys_rhs_norm2", "nw_linsys_rhs_norm2_global",
     "nw_mesh_halo_send_count", "nw_mesh_halo_get_send", "nw_mesh_halo_set_recv",
     "nw_mesh_halo_commit", "nw_field_parallel_sum", "nw_field_copy_owned_to_shared", "nw_linsys_halo_send_info",
     "nw_linsys_halo_get_send", "nw_linsys_halo_set_recv",
@@ -222,6 +222,7 @@ def lib():
                                           C.POINTER(C.c_int64)]
     L.nw_linsys_get_values.argtypes = [vp, vp, vp]
     L.nw_linsys_rhs_norm2.argtypes = [vp, c_f64p]
+    L.nw_linsys_rhs_norm2_global.argtypes = [vp, c_f64p]
     L.nw_mesh_halo_send_count.argtypes = [vp, C.c_int, c_i64p]
     L.nw_mesh_halo_get_send.argtypes = [vp, C.c_int, c_i64p]
     L.nw_mesh_halo_set_recv.argtypes = [vp, C.c_int, C.c_int64, c_i64p]
@@ -676,6 +677,12 @@ class LinearSystem:
         rhs = np.zeros((s.num_rhs, rows))
         _chk(lib().nw_linsys_get_values(self.h, _ptr(vals), _ptr(rhs)))
         return vals, rhs
+
+    def rhs_norm2_global(self):
+        """summed over all ranks (collective)"""
+        out = np.zeros(self.sizes.num_rhs)
+        _chk(lib().nw_linsys_rhs_norm2_global(self.h, out.ctypes.data_as(c_f64p)))
+        return out
 
     def rhs_norm2(self):
         out = np.zeros(self.sizes.num_rhs)

@@ -1886,6 +1886,38 @@ nw_linsys_rhs_norm2(nw_linsys* ls, double* out)
   return NW_OK;
 }
 
+/* the same summed over all ranks (the nonlinear residual norm the reference
+ * prints and reg_test check_norms compares): local deterministic reduction,
+ * then one ncclAllReduce of num_rhs doubles */
+extern "C" int
+nw_linsys_rhs_norm2_global(nw_linsys* ls, double* out)
+{
+  if (int rc = ls_ready(ls, "nw_linsys_rhs_norm2_global"))
+    return rc;
+  if (!out)
+    return fail(NW_ERR_ARG, "nw_linsys_rhs_norm2_global: NULL output");
+  if (ls->state == NW_LS_LAZY_ZERO)
+    if (int rc = materialize_zero(ls))
+      return rc;
+  nw_ctx* ctx = ls->mesh->ctx;
+  cudaStream_t s = ctx->stream;
+  NW_CUDA(launch_norm2(
+    ls->dev.rhs, ls->g.numRowsOwned, ls->dev.rhsStride, ls->nRhs,
+    ls->dNormPartial.as<double>(), 296, ls->dNormOut.as<double>(), s));
+  if (ls->mesh->plan.nranks > 1) {
+    if (!ctx->comm.comm)
+      return fail(NW_ERR_COMM, "nw_linsys_rhs_norm2_global: no communicator");
+    std::string err;
+    if (!comm_allreduce_sum_f64(
+          ctx->comm, ls->dNormOut.as<double>(), ls->nRhs, s, err))
+      return fail(NW_ERR_COMM, "nw_linsys_rhs_norm2_global: " + err);
+  }
+  NW_CUDA(cudaMemcpyAsync(
+    out, ls->dNormOut.p, sizeof(double) * ls->nRhs, cudaMemcpyDeviceToHost, s));
+  NW_CUDA(cudaStreamSynchronize(s));
+  return NW_OK;
+}
+
 /* ------------------------------------------------------------------ */
 /*  multi-rank halo (see nw_halo.cu)                                   */
 /* ------------------------------------------------------------------ */

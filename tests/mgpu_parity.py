@@ -130,7 +130,15 @@ def main():
     ls.zeroSystem()
     ls.assemble_continuity_edge(**pu.CONT_OPTS)
     ls.loadComplete()
-    check_system("continuity", ls, pu.oracle_continuity(full, gfull), 1)
+    ocont = pu.oracle_continuity(full, gfull)
+    check_system("continuity", ls, ocont, 1)
+    # residual norm over all ranks (ncclAllReduce) == serial norm
+    n2 = ls.rhs_norm2_global()
+    fr, fra = ocont.get()[1], ocont.get_abs()[1]
+    pr = set(gfull.periodic_rows.tolist())
+    keep = np.array([r not in pr for r in range(gfull.num_rows_owned)])
+    ref2 = float(np.sum(fr[0, :gfull.num_rows_owned][keep] ** 2))
+    res["norm2_global"] = abs(n2[0] - ref2) / (1e-10 * ref2)
     ls.close()
 
     ls = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE_UVW, 3)

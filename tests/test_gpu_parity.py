@@ -942,6 +942,7 @@ def test_full_size_conservation(P, ctx, big):
     assert np.all(diag > 0)
     n2 = ls.rhs_norm2()
     assert abs(n2[0] - np.sum(rhs[0] ** 2)) <= 1e-12 * n2[0]
+    assert np.array_equal(ls.rhs_norm2_global(), n2)  # single rank: the same
     # gradient of a linear field is exact at interior nodes
     f = 3.0 * case.box.coords[:, 0] - 2.0 * case.box.coords[:, 1] + 0.5 * case.box.coords[:, 2]
     mesh.put("lin", P.NW_NODE, f)

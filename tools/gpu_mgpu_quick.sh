@@ -7,7 +7,7 @@ cd "$(dirname "$0")/.."
 export PYTHONUNBUFFERED=1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 port=29600
-for m in 1 0; do
+for m in ${MODES:-1 0}; do
 for per in 0 1; do
 port=$((port+1))
 echo "=== mgpu parity periodic=$per p2p=$m"
