@@ -256,6 +256,24 @@ nw_mesh_create(nw_ctx* ctx, const nw_mesh_desc* desc, nw_mesh** out)
   in.coords = desc->coords;
   in.tileNodes = desc->tile_nodes;
   NW_TRY(build_mesh_plan(in, m->plan);)
+  if (desc->tile_nodes <= 0) {
+    /* default tile size: meshes with many edges per node (tets: ~7 against a
+     * hex mesh's 3) stage more per tile; halve the tile until the largest
+     * shared-memory layout (momentum: 18 node components, 7 doubles per edge,
+     * row staging, reduction plan) fits one CTA with room to spare */
+    int T = 192;
+    auto need = [&]() {
+      const MeshPlan& q = m->plan;
+      const size_t staged = (size_t)q.maxTileStaged + 2, te = (size_t)q.maxTileEdges + 4;
+      return 8 * (18 * staged + 7 * te) + 4 * te + 6 * (size_t)q.maxTileHalf +
+             (size_t)16 * 192 * 8;
+    };
+    while (need() > 200 * 1024 && T > 24) {
+      T /= 2;
+      in.tileNodes = T;
+      NW_TRY(build_mesh_plan(in, m->plan);)
+    }
+  }
   MeshPlanDev& d = m->dev;
   d.nTiles = (int)m->plan.nTiles;
   d.ndim = m->plan.ndim;

@@ -345,6 +345,37 @@ def test_fuzz_random_graphs_on_device(P, ctx, seed):
     mesh.close()
 
 
+@pytest.mark.parametrize("name,tile", [("multiElemTypeCylinder", 0),
+                                       ("hybrid_g_8_0", 0),
+                                       ("multiElemTypeCylinder", 64)])
+def test_reference_mixed_element_meshes(P, ctx, name, tile):
+    """BASELINE configs[4]: the reference's own tet / wedge / pyramid / hex
+    regression meshes (tests/golden/mesh_*.npz), full sweep vs the oracle"""
+    res = pu.run_lowmach_case(P, ctx, tile_nodes=tile, case=pu.RealMeshCase(name))
+    bad = {k: v for k, v in res.items() if not v < 1.0}
+    assert not bad, bad
+
+
+def test_reference_airfoil_mesh_2d(P, ctx):
+    """BASELINE configs[3]: the reference's airfoilRANSEdge mesh (2-D QUAD4,
+    49 536 nodes): device geometry (GeometryInteriorAlg<Quad4_2D>) vs the
+    oracle, then the edge sweep on that true CVFEM geometry"""
+    g2 = pu.RealMesh2D()
+    mesh = P.Mesh(ctx, 2, g2.edges, g2.hid, g2.coords)
+    mesh.register("dual_nodal_volume", P.NW_NODE, 1)
+    mesh.register("edge_area_vector", P.NW_EDGE, 2)
+    mesh.geometry_interior(g2.elems, dnv="dual_nodal_volume",
+                           area="edge_area_vector")
+    dnv = mesh.download("dual_nodal_volume")
+    area = mesh.download("edge_area_vector").reshape(-1, 2)
+    assert np.max(np.abs(dnv - g2.vol)) <= 1e-12 * np.max(g2.vol)
+    assert np.max(np.abs(area - g2.area)) <= 1e-12 * np.max(np.abs(g2.area))
+    mesh.close()
+    res = pu.run_quad2d_case(P, ctx, tile_nodes=0, grid=g2)
+    bad = {k: v for k, v in res.items() if not v < 1.0}
+    assert not bad, bad
+
+
 def test_monolithic_momentum_vs_oracle(P, ctx):
     case = pu.Case(dims=(10, 9, 7))
     mesh = case.box.make_mesh(ctx, tile_nodes=64)
