@@ -418,6 +418,27 @@ int nw_geometry_interior_quad4(
   const unsigned char* elem_owned, int coordinates_field,
   int dual_nodal_volume_field, int edge_area_vector_field);
 
+/* The same for Tet4, Wed6 and Pyr5 blocks of a 3-D mesh (AlgTraitsTet4 / Wed6 /
+ * Pyr5; TetSCV / TetSCS src/master_element/Tet4CVFEM.C:243-343, 522-619,
+ * WedSCV / WedSCS Wed6CVFEM.C:267-369, 541-647, PyrSCV / PyrSCS
+ * Pyr5CVFEM.C:348-572, 772-900 -- the pyramid has two sub-control surfaces on
+ * each apex edge, scsIpEdgeOrd include/master_element/Pyr5CVFEM.h:304-305).
+ * elem_nodes is [n_elems][4 | 6 | 5] in the stk / Exodus node order of the
+ * topology.  A mixed mesh calls once per block into the same two fields, as
+ * GeometryAlgDriver runs one GeometryInteriorAlg per topology. */
+int nw_geometry_interior_tet4(
+  nw_mesh* mesh, int64_t n_elems, const int32_t* elem_nodes,
+  const unsigned char* elem_owned, int coordinates_field,
+  int dual_nodal_volume_field, int edge_area_vector_field);
+int nw_geometry_interior_wed6(
+  nw_mesh* mesh, int64_t n_elems, const int32_t* elem_nodes,
+  const unsigned char* elem_owned, int coordinates_field,
+  int dual_nodal_volume_field, int edge_area_vector_field);
+int nw_geometry_interior_pyr5(
+  nw_mesh* mesh, int64_t n_elems, const int32_t* elem_nodes,
+  const unsigned char* elem_owned, int coordinates_field,
+  int dual_nodal_volume_field, int edge_area_vector_field);
+
 /* Poisson system of the SST minimum wall distance:
  * WallDistEdgeSolverAlg::execute (src/edge_kernels/WallDistEdgeSolverAlg.C:28-66,
  * lhs = asq/axdx [[+1,-1],[-1,+1]], no rhs; same tile / atomic kernels as the

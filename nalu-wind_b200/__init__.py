@@ -120,7 +120,8 @@ ABI_SYMBOLS = [
     "nw_mesh_create", "nw_mesh_destroy", "nw_mesh_get_stats",
     "nw_field_register", "nw_field_find", "nw_field_upload",
     "nw_field_stage", "nw_field_commit", "nw_field_download", "nw_field_fill", "nw_field_device_view",
-    "nw_mesh_get_node_permutation", "nw_geometry_interior_hex8", "nw_geometry_interior_quad4", "nw_mdot_edge",
+    "nw_mesh_get_node_permutation", "nw_geometry_interior_hex8", "nw_geometry_interior_quad4",
+    "nw_geometry_interior_tet4", "nw_geometry_interior_wed6", "nw_geometry_interior_pyr5", "nw_mdot_edge",
     "nw_mdot_edge_ext", "nw_assemble_continuity_edge_ext", "nw_peclet_edge",
     "nw_nodal_grad_edge", "nw_linsys_create", "nw_linsys_destroy",
     "nw_linsys_set_skipped_rows", "nw_linsys_build_edge_to_node_graph",
@@ -189,6 +190,9 @@ def lib():
     L.nw_geometry_interior_hex8.argtypes = [vp, C.c_int64, vp, vp, C.c_int,
                                             C.c_int, C.c_int]
     L.nw_geometry_interior_quad4.argtypes = L.nw_geometry_interior_hex8.argtypes
+    for _t in ("tet4", "wed6", "pyr5"):
+        getattr(L, "nw_geometry_interior_" + _t).argtypes = \
+            L.nw_geometry_interior_hex8.argtypes
     L.nw_mdot_edge_ext.argtypes = [vp, C.POINTER(MdotOpts), C.POINTER(MdotExtraOpts)]
     L.nw_assemble_continuity_edge_ext.argtypes = [
         vp, C.POINTER(ContinuityOpts), C.POINTER(MdotExtraOpts)]
@@ -403,14 +407,16 @@ class Mesh:
 
     def geometry_interior_hex8(self, elem_nodes, dnv=None, area=None,
                                coords="coordinates", elem_owned=None):
-        """GeometryInteriorAlg<Hex8> ([n][8]) or <Quad4_2D> ([n][4]):
-        accumulate dual nodal volumes / edge area vectors (zero the fields
+        """GeometryInteriorAlg for one element block: Hex8 ([n][8]), Tet4
+        ([n][4]), Wed6 ([n][6]), Pyr5 ([n][5]); on a 2-D mesh Quad4 ([n][4]).
+        Accumulates dual nodal volumes / edge area vectors (zero the fields
         first)"""
         el = np.ascontiguousarray(elem_nodes, dtype=np.int32)
         ow = None if elem_owned is None else np.ascontiguousarray(
             elem_owned, dtype=np.uint8)
-        fn = (lib().nw_geometry_interior_hex8 if el.shape[1] == 8
-              else lib().nw_geometry_interior_quad4)
+        name = "quad4" if self.ndim == 2 else {
+            8: "hex8", 4: "tet4", 6: "wed6", 5: "pyr5"}[el.shape[1]]
+        fn = getattr(lib(), "nw_geometry_interior_" + name)
         _chk(fn(
             self.h, len(el), _ptr(el), None if ow is None else _ptr(ow),
             self.field_id(coords), -1 if dnv is None else self.field_id(dnv),

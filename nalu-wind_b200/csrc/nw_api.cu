@@ -8,6 +8,7 @@
 #include <cstring>
 #include <stdexcept>
 
+#include "geometry_cvfem.h"
 #include "nw_comm.h"
 #include "nw_internal.h"
 
@@ -665,9 +666,11 @@ bind_cont_nodes(nw_mesh* mesh, NodeComps& nc)
 /* GeometryInteriorAlg for one element block of `npe`-node elements whose
  * sub-control surfaces pair local nodes lr[2 ip], lr[2 ip + 1] (scsIpEdgeOrd
  * is the identity for Hex8 and Quad4) */
+enum { NW_GEO_HEX8 = 0, NW_GEO_QUAD4 = 1, NW_GEO_TET4 = 2, NW_GEO_WED6 = 3, NW_GEO_PYR5 = 4 };
+
 static int
 geometry_interior(
-  nw_mesh* mesh, const char* what, int ndim, int npe, int nScs, const int* lr,
+  nw_mesh* mesh, const char* what, int topo, int ndim, int npe, int nScs, const int* lr,
   int64_t n_elems, const int32_t* elem_nodes, const unsigned char* elem_owned,
   int coordinates_field, int dual_nodal_volume_field, int edge_area_vector_field)
 {
@@ -702,7 +705,7 @@ geometry_interior(
       sizeof(int32_t) * (size_t)npe * n_elems);
   if (elem_owned)
     mix(elem_owned, (size_t)n_elems);
-  nw_mesh::GeoCache& gc = mesh->geo;
+  nw_mesh::GeoCache& gc = mesh->geo[topo];
   if (gc.nElems != n_elems || gc.hash != h) {
     std::map<std::pair<int32_t, int32_t>, int64_t> edgeOf;
     for (int64_t e = 0; e < mp.nEdges; ++e) {
@@ -745,12 +748,17 @@ geometry_interior(
   const unsigned char* ow = gc.hasOwned ? gc.dOwned.as<unsigned char>() : nullptr;
   double* vol = vf ? vf->buf.as<double>() : nullptr;
   double* area = af ? af->buf.as<double>() : nullptr;
-  if (npe == 8)
+  if (topo == NW_GEO_HEX8)
     NW_CUDA(launch_geometry_hex8(
       n_elems, gc.dElemSlots.as<int32_t>(), gc.dElemEdges.as<int32_t>(), ow,
       xf->buf.as<double>(), xf->stride, vol, area, af ? af->stride : 0, s));
-  else
+  else if (topo == NW_GEO_QUAD4)
     NW_CUDA(launch_geometry_quad4(
+      n_elems, gc.dElemSlots.as<int32_t>(), gc.dElemEdges.as<int32_t>(), ow,
+      xf->buf.as<double>(), xf->stride, vol, area, af ? af->stride : 0, s));
+  else
+    NW_CUDA(launch_geometry_cvfem(
+      topo == NW_GEO_TET4 ? geo::TET4 : (topo == NW_GEO_WED6 ? geo::WED6 : geo::PYR5),
       n_elems, gc.dElemSlots.as<int32_t>(), gc.dElemEdges.as<int32_t>(), ow,
       xf->buf.as<double>(), xf->stride, vol, area, af ? af->stride : 0, s));
   if (af)
@@ -770,7 +778,7 @@ nw_geometry_interior_hex8(
   static const int lr[24] = {0, 1, 1, 2, 2, 3, 0, 3, 4, 5, 5, 6,
                              6, 7, 4, 7, 0, 4, 1, 5, 2, 6, 3, 7};
   return geometry_interior(
-    mesh, "nw_geometry_interior_hex8", 3, 8, 12, lr, n_elems, elem_nodes,
+    mesh, "nw_geometry_interior_hex8", NW_GEO_HEX8, 3, 8, 12, lr, n_elems, elem_nodes,
     elem_owned, coordinates_field, dual_nodal_volume_field,
     edge_area_vector_field);
 }
@@ -784,7 +792,62 @@ nw_geometry_interior_quad4(
   /* Quad42DSCS::lrscv_, include/master_element/Quad42DCVFEM.h:250 */
   static const int lr[8] = {0, 1, 1, 2, 2, 3, 0, 3};
   return geometry_interior(
-    mesh, "nw_geometry_interior_quad4", 2, 4, 4, lr, n_elems, elem_nodes,
+    mesh, "nw_geometry_interior_quad4", NW_GEO_QUAD4, 2, 4, 4, lr, n_elems, elem_nodes,
+    elem_owned, coordinates_field, dual_nodal_volume_field,
+    edge_area_vector_field);
+}
+
+/* Tet4 / Wed6 / Pyr5 blocks: the (left, right) node pair of every sub-control
+ * surface comes from the same tables the kernel uses (geometry_cvfem.h) */
+template <int T>
+static int
+geometry_interior_cvfem(
+  nw_mesh* mesh, const char* what, int topo, int64_t n_elems,
+  const int32_t* elem_nodes, const unsigned char* elem_owned,
+  int coordinates_field, int dual_nodal_volume_field, int edge_area_vector_field)
+{
+  constexpr int nScs = geo::Traits<T>::nScs;
+  int lr[2 * nScs];
+  for (int ip = 0; ip < nScs; ++ip)
+    geo::scs_nodes<T>(ip, &lr[2 * ip], &lr[2 * ip + 1]);
+  return geometry_interior(
+    mesh, what, topo, 3, geo::Traits<T>::npe, nScs, lr, n_elems, elem_nodes,
+    elem_owned, coordinates_field, dual_nodal_volume_field,
+    edge_area_vector_field);
+}
+
+extern "C" int
+nw_geometry_interior_tet4(
+  nw_mesh* mesh, int64_t n_elems, const int32_t* elem_nodes,
+  const unsigned char* elem_owned, int coordinates_field,
+  int dual_nodal_volume_field, int edge_area_vector_field)
+{
+  return geometry_interior_cvfem<geo::TET4>(
+    mesh, "nw_geometry_interior_tet4", NW_GEO_TET4, n_elems, elem_nodes,
+    elem_owned, coordinates_field, dual_nodal_volume_field,
+    edge_area_vector_field);
+}
+
+extern "C" int
+nw_geometry_interior_wed6(
+  nw_mesh* mesh, int64_t n_elems, const int32_t* elem_nodes,
+  const unsigned char* elem_owned, int coordinates_field,
+  int dual_nodal_volume_field, int edge_area_vector_field)
+{
+  return geometry_interior_cvfem<geo::WED6>(
+    mesh, "nw_geometry_interior_wed6", NW_GEO_WED6, n_elems, elem_nodes,
+    elem_owned, coordinates_field, dual_nodal_volume_field,
+    edge_area_vector_field);
+}
+
+extern "C" int
+nw_geometry_interior_pyr5(
+  nw_mesh* mesh, int64_t n_elems, const int32_t* elem_nodes,
+  const unsigned char* elem_owned, int coordinates_field,
+  int dual_nodal_volume_field, int edge_area_vector_field)
+{
+  return geometry_interior_cvfem<geo::PYR5>(
+    mesh, "nw_geometry_interior_pyr5", NW_GEO_PYR5, n_elems, elem_nodes,
     elem_owned, coordinates_field, dual_nodal_volume_field,
     edge_area_vector_field);
 }

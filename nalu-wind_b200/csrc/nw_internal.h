@@ -186,15 +186,16 @@ struct nw_mesh
   std::map<std::string, int> fieldByName;
   nw_node_halo halo;
   std::map<int64_t, int32_t> ownedNodeOfHid; /* own row id -> local node */
-  /* GeometryInteriorAlg tables of the last element block (cached: a moving
-   * mesh calls every step with the same connectivity) */
+  /* GeometryInteriorAlg tables of the last element block of each topology
+   * (hex8, quad4, tet4, wed6, pyr5; cached: a moving mesh calls every step
+   * with the same connectivity) */
   struct GeoCache
   {
     int64_t nElems = -1;
     uint64_t hash = 0;
     nw::DevBuf dElemSlots, dElemEdges, dOwned;
     bool hasOwned = false;
-  } geo;
+  } geo[5];
   /* node-kernel selector: locally owned and not a periodic slave */
   std::vector<uint8_t> nodeKernelActive;
   int64_t planBytes = 0;

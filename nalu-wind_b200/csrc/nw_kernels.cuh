@@ -177,6 +177,12 @@ cudaError_t launch_geometry_quad4(
   int64_t nElems, const int32_t* elemSlots, const int32_t* elemEdges,
   const unsigned char* owned, const double* x, int64_t xStride, double* dualVol,
   double* area, int64_t areaStride, cudaStream_t s);
+/* GeometryInteriorAlg<Tet4 / Wed6 / Pyr5> (nw_geometry.cu; topology = the
+ * nw::geo::Topology of geometry_cvfem.h): elemSlots [n][npe], elemEdges [n][nScs] */
+cudaError_t launch_geometry_cvfem(
+  int topology, int64_t nElems, const int32_t* elemSlots, const int32_t* elemEdges,
+  const unsigned char* owned, const double* x, int64_t xStride, double* dualVol,
+  double* area, int64_t areaStride, cudaStream_t s);
 cudaError_t launch_edge_mirror(
   const int32_t* primarySlot, const int32_t* secondSlot, int64_t nEdges,
   int ncomp, int64_t stride, double* f, cudaStream_t s);

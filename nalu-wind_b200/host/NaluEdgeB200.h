@@ -703,7 +703,8 @@ class GeometryAlgDriver : public Algorithm
 {
 public:
   using Algorithm::Algorithm;
-  /* one call per element block; npe = 8 (Hex8) or 4 (2-D Quad4) */
+  /* one call per element block; npe = 8 (Hex8), 4 (Tet4; 2-D mesh: Quad4),
+   * 6 (Wed6) or 5 (Pyr5) */
   void register_elem_block(
     int npe, std::vector<int32_t> elemNodes, std::vector<unsigned char> owned = {})
   {
@@ -719,12 +720,20 @@ public:
     for (auto& b : blocks_) {
       const int64_t n = (int64_t)b.nodes.size() / b.npe;
       const unsigned char* ow = b.owned.empty() ? nullptr : b.owned.data();
-      if (b.npe == 8)
-        nw_check(nw_geometry_interior_hex8(
-          realm_.mesh(), n, b.nodes.data(), ow, x, v, a));
-      else
-        nw_check(nw_geometry_interior_quad4(
-          realm_.mesh(), n, b.nodes.data(), ow, x, v, a));
+      /* one GeometryInteriorAlg<AlgTraits> per block topology
+       * (GeometryAlgDriver::register_elem_algorithm) */
+      auto fn = nw_geometry_interior_hex8;
+      if (realm_.spatial_dimension() == 2)
+        fn = nw_geometry_interior_quad4;
+      else if (b.npe == 4)
+        fn = nw_geometry_interior_tet4;
+      else if (b.npe == 6)
+        fn = nw_geometry_interior_wed6;
+      else if (b.npe == 5)
+        fn = nw_geometry_interior_pyr5;
+      else if (b.npe != 8)
+        throw std::runtime_error("GeometryAlgDriver: unsupported element topology");
+      nw_check(fn(realm_.mesh(), n, b.nodes.data(), ow, x, v, a));
     }
     nw_check(nw_field_parallel_sum(realm_.mesh(), v));
   }

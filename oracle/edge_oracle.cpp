@@ -1365,6 +1365,317 @@ orc_geometry_interior_quad4(
   }
 }
 
+/* ------------------------------------------------------------------ */
+/*  GeometryInteriorAlg<Tet4 / Wed6 / Pyr5>                            */
+/* ------------------------------------------------------------------ */
+namespace {
+
+/* bhex_volume_grandy, Hex8GeometryFunctions.h:161-252: Grandy's formula with
+ * the top face (nodes 4..7) split along its 5-7 diagonal */
+double
+geo_bhex_volume_grandy(const double sc[8][3])
+{
+  double cv[14][3];
+  for (int n = 0; n < 8; ++n)
+    for (int d = 0; d < 3; ++d)
+      cv[n][d] = sc[n][d];
+  for (int d = 0; d < 3; ++d) {
+    cv[8][d] = 0.25 * (sc[0][d] + sc[1][d] + sc[2][d] + sc[3][d]);
+    cv[9][d] = 0.5 * (sc[5][d] + sc[7][d]);
+    cv[10][d] = 0.25 * (sc[0][d] + sc[1][d] + sc[5][d] + sc[4][d]);
+    cv[11][d] = 0.25 * (sc[3][d] + sc[2][d] + sc[6][d] + sc[7][d]);
+    cv[12][d] = 0.25 * (sc[1][d] + sc[2][d] + sc[6][d] + sc[5][d]);
+    cv[13][d] = 0.25 * (sc[0][d] + sc[3][d] + sc[7][d] + sc[4][d]);
+  }
+  static const int tf[24][3] = {
+    {0, 8, 1},  {8, 2, 1},  {3, 2, 8},  {3, 8, 0},  {6, 9, 5},  {7, 9, 6},
+    {4, 9, 7},  {4, 5, 9},  {10, 0, 1}, {5, 10, 1}, {4, 10, 5}, {4, 0, 10},
+    {7, 6, 11}, {6, 2, 11}, {2, 3, 11}, {3, 7, 11}, {6, 12, 2}, {5, 12, 6},
+    {5, 1, 12}, {1, 2, 12}, {0, 4, 13}, {4, 7, 13}, {7, 3, 13}, {3, 0, 13}};
+  double volume = 0.0;
+  for (int k = 0; k < 24; ++k) {
+    const int p = tf[k][0], q = tf[k][1], r = tf[k][2];
+    const double mid[3] = {cv[p][0] + cv[q][0] + cv[r][0],
+                           cv[p][1] + cv[q][1] + cv[r][1],
+                           cv[p][2] + cv[q][2] + cv[r][2]};
+    double dxv[3];
+    dxv[0] = (cv[q][1] - cv[p][1]) * (cv[r][2] - cv[p][2]) -
+             (cv[r][1] - cv[p][1]) * (cv[q][2] - cv[p][2]);
+    dxv[1] = (cv[r][0] - cv[p][0]) * (cv[q][2] - cv[p][2]) -
+             (cv[q][0] - cv[p][0]) * (cv[r][2] - cv[p][2]);
+    dxv[2] = (cv[q][0] - cv[p][0]) * (cv[r][1] - cv[p][1]) -
+             (cv[r][0] - cv[p][0]) * (cv[q][1] - cv[p][1]);
+    volume += mid[0] * dxv[0] + mid[1] * dxv[1] + mid[2] * dxv[2];
+  }
+  volume /= 18.0;
+  return volume;
+}
+
+/* octohedron_volume_by_triangle_facets + polyhedral_volume_by_faces,
+ * src/master_element/Pyr5CVFEM.C:348-432 (the apex control volume) */
+double
+geo_octohedron_volume(const double vc[10][3])
+{
+  double c[14][3];
+  for (int j = 0; j < 10; ++j)
+    for (int k = 0; k < 3; ++k)
+      c[j][k] = vc[j][k];
+  for (int k = 0; k < 3; ++k) {
+    c[10][k] = 0.50 * (vc[3][k] + vc[9][k]);
+    c[11][k] = 0.50 * (vc[3][k] + vc[5][k]);
+    c[12][k] = 0.50 * (vc[5][k] + vc[7][k]);
+    c[13][k] = 0.50 * (vc[7][k] + vc[9][k]);
+  }
+  static const int tf[24][3] = {
+    {1, 3, 10}, {2, 10, 3}, {2, 9, 10}, {10, 9, 1}, {4, 3, 11}, {3, 1, 11},
+    {11, 1, 5}, {4, 11, 5}, {1, 12, 5}, {1, 7, 12}, {12, 7, 6}, {5, 12, 6},
+    {9, 8, 13}, {13, 8, 7}, {13, 7, 1}, {9, 13, 1}, {4, 5, 0},  {5, 6, 0},
+    {6, 7, 0},  {7, 8, 0},  {0, 8, 9},  {0, 9, 2},  {0, 2, 3},  {0, 3, 4}};
+  double volume = 0.0;
+  for (int t = 0; t < 24; ++t) {
+    const int ip = tf[t][0], iq = tf[t][1], ir = tf[t][2];
+    double xf[3];
+    for (int k = 0; k < 3; ++k)
+      xf[k] = c[ip][k] + c[iq][k] + c[ir][k];
+    volume = volume +
+             xf[0] * ((c[iq][1] - c[ip][1]) * (c[ir][2] - c[ip][2]) -
+                      (c[ir][1] - c[ip][1]) * (c[iq][2] - c[ip][2])) -
+             xf[1] * ((c[iq][0] - c[ip][0]) * (c[ir][2] - c[ip][2]) -
+                      (c[ir][0] - c[ip][0]) * (c[iq][2] - c[ip][2])) +
+             xf[2] * ((c[iq][0] - c[ip][0]) * (c[ir][1] - c[ip][1]) -
+                      (c[ir][0] - c[ip][0]) * (c[iq][1] - c[ip][1]));
+  }
+  volume = volume / 18.0;
+  return volume;
+}
+
+/* the 15 points of TetSCV/TetSCS::determinant_*,
+ * src/master_element/Tet4CVFEM.C:255-322, 536-603 */
+void
+geo_subdivide_tet4(const double c[][3], double v[][3])
+{
+  const double half = 0.5, one3rd = 1.0 / 3.0;
+  for (int j = 0; j < 4; ++j)
+    for (int k = 0; k < 3; ++k)
+      v[j][k] = c[j][k];
+  for (int k = 0; k < 3; ++k) {
+    v[4][k] = half * (c[0][k] + c[1][k]);
+    v[5][k] = half * (c[1][k] + c[2][k]);
+    v[6][k] = half * (c[2][k] + c[0][k]);
+    v[7][k] = one3rd * (c[0][k] + c[1][k] + c[2][k]);
+    v[8][k] = half * (c[2][k] + c[3][k]);
+    v[9][k] = half * (c[3][k] + c[1][k]);
+    v[10][k] = one3rd * (c[1][k] + c[2][k] + c[3][k]);
+    v[11][k] = half * (c[0][k] + c[3][k]);
+    v[12][k] = one3rd * (c[0][k] + c[2][k] + c[3][k]);
+    v[13][k] = one3rd * (c[0][k] + c[1][k] + c[3][k]);
+    v[14][k] = 0.0;
+    for (int j = 0; j < 4; ++j)
+      v[14][k] = v[14][k] + 0.25 * c[j][k];
+  }
+}
+
+/* the 21 points of WedSCV/WedSCS::determinant_*,
+ * src/master_element/Wed6CVFEM.C:286-358, 565-636 */
+void
+geo_subdivide_wed6(const double c[][3], double v[][3])
+{
+  const double half = 0.5, one3rd = 1.0 / 3.0, one6th = 1.0 / 6.0;
+  for (int j = 0; j < 6; ++j)
+    for (int k = 0; k < 3; ++k)
+      v[j][k] = c[j][k];
+  for (int k = 0; k < 3; ++k) {
+    v[6][k] = half * (c[0][k] + c[1][k]);
+    v[7][k] = half * (c[1][k] + c[2][k]);
+    v[8][k] = half * (c[2][k] + c[0][k]);
+    v[9][k] = one3rd * (c[0][k] + c[1][k] + c[2][k]);
+    v[10][k] = half * (c[3][k] + c[4][k]);
+    v[11][k] = half * (c[4][k] + c[5][k]);
+    v[12][k] = half * (c[5][k] + c[3][k]);
+    v[13][k] = one3rd * (c[3][k] + c[4][k] + c[5][k]);
+    v[14][k] = half * (c[1][k] + c[4][k]);
+    v[15][k] = half * (c[0][k] + c[3][k]);
+    v[16][k] = 0.25 * (c[0][k] + c[1][k] + c[4][k] + c[3][k]);
+    v[17][k] = half * (c[2][k] + c[5][k]);
+    v[18][k] = 0.25 * (c[1][k] + c[4][k] + c[5][k] + c[2][k]);
+    v[19][k] = 0.25 * (c[5][k] + c[3][k] + c[0][k] + c[2][k]);
+    v[20][k] = 0.0;
+    for (int j = 0; j < 6; ++j)
+      v[20][k] += one6th * c[j][k];
+  }
+}
+
+/* the 19 points of PyrSCV/PyrSCS::determinant_*,
+ * src/master_element/Pyr5CVFEM.C:459-543, 798-883 */
+void
+geo_subdivide_pyr5(const double c[][3], double v[][3])
+{
+  const double one3rd = 1.0 / 3.0;
+  for (int j = 0; j < 5; ++j)
+    for (int k = 0; k < 3; ++k)
+      v[j][k] = c[j][k];
+  for (int k = 0; k < 3; ++k) {
+    v[5][k] = 0.5 * (c[0][k] + c[1][k]);
+    v[6][k] = 0.5 * (c[1][k] + c[2][k]);
+    v[7][k] = 0.5 * (c[2][k] + c[3][k]);
+    v[8][k] = 0.5 * (c[3][k] + c[0][k]);
+    v[9][k] = 0.25 * (c[0][k] + c[1][k] + c[2][k] + c[3][k]);
+    v[10][k] = 0.5 * (c[1][k] + c[4][k]);
+    v[11][k] = 0.5 * (c[4][k] + c[0][k]);
+    v[12][k] = one3rd * (c[0][k] + c[1][k] + c[4][k]);
+    v[13][k] = 0.5 * (c[2][k] + c[4][k]);
+    v[14][k] = one3rd * (c[1][k] + c[2][k] + c[4][k]);
+    v[15][k] = 0.5 * (c[3][k] + c[4][k]);
+    v[16][k] = one3rd * (c[3][k] + c[4][k] + c[2][k]);
+    v[17][k] = one3rd * (c[0][k] + c[4][k] + c[3][k]);
+    v[18][k] = 0.0;
+    for (int j = 0; j < 5; ++j)
+      v[18][k] += 0.2 * c[j][k];
+  }
+}
+
+struct GeoTopo3
+{
+  int npe, nScv, nScs;
+  void (*subdivide)(const double c[][3], double v[][3]);
+  int scvHex[6][10]; /* sub-control volume -> sub-points (8, apex of Pyr5: 10) */
+  int scsQuad[12][4];
+  int lrscv[24];
+};
+
+/* tables: Tet4CVFEM.C:247-251, 526-528 + Tet4CVFEM.h:266;
+ * Wed6CVFEM.C:271-275, 545-555 + Wed6CVFEM.h:268;
+ * Pyr5CVFEM.C:448-453, 776-789 + Pyr5CVFEM.h:300-301 */
+const GeoTopo3 kGeoTet4 = {
+  4, 4, 6, geo_subdivide_tet4,
+  {{0, 4, 7, 6, 11, 13, 14, 12}, {1, 5, 7, 4, 9, 10, 14, 13},
+   {2, 6, 7, 5, 8, 12, 14, 10}, {3, 9, 13, 11, 8, 10, 14, 12}},
+  {{4, 7, 14, 13}, {7, 14, 10, 5}, {6, 12, 14, 7}, {11, 13, 14, 12},
+   {13, 9, 10, 14}, {10, 8, 12, 14}},
+  {0, 1, 1, 2, 0, 2, 0, 3, 1, 3, 2, 3}};
+const GeoTopo3 kGeoWed6 = {
+  6, 6, 9, geo_subdivide_wed6,
+  {{0, 15, 16, 6, 8, 19, 20, 9}, {9, 6, 1, 7, 20, 16, 14, 18},
+   {8, 9, 7, 2, 19, 20, 18, 17}, {19, 15, 16, 20, 12, 3, 10, 13},
+   {20, 16, 14, 18, 13, 10, 4, 11}, {19, 20, 18, 17, 12, 13, 11, 5}},
+  {{6, 9, 20, 16}, {7, 9, 20, 18}, {9, 8, 19, 20}, {10, 16, 20, 13},
+   {13, 11, 18, 20}, {12, 13, 20, 19}, {15, 16, 20, 19}, {16, 14, 18, 20},
+   {19, 20, 18, 17}},
+  {0, 1, 1, 2, 0, 2, 3, 4, 4, 5, 3, 5, 0, 3, 1, 4, 2, 5}};
+const GeoTopo3 kGeoPyr5 = {
+  5, 5, 12, geo_subdivide_pyr5,
+  {{0, 5, 9, 8, 11, 12, 18, 17, -1, -1}, {1, 6, 9, 5, 10, 14, 18, 12, -1, -1},
+   {2, 7, 9, 6, 13, 16, 18, 14, -1, -1}, {3, 8, 9, 7, 15, 17, 18, 16, -1, -1},
+   {4, 18, 15, 17, 11, 12, 10, 14, 13, 16}},
+  {{5, 9, 18, 12}, {6, 9, 18, 14}, {7, 9, 18, 16}, {8, 17, 18, 9},
+   {12, 12, 18, 17}, {11, 12, 12, 17}, {14, 14, 18, 12}, {10, 14, 14, 12},
+   {16, 16, 18, 14}, {13, 16, 16, 14}, {17, 17, 18, 16}, {15, 17, 17, 16}},
+  {0, 1, 1, 2, 2, 3, 0, 3, 0, 4, 0, 4, 1, 4, 1, 4, 2, 4, 2, 4, 3, 4, 3, 4}};
+
+void
+geo_interior_3d(
+  const GeoTopo3& T, int64_t n_elems, const int32_t* elem_nodes,
+  const unsigned char* elem_owned, const double* coords, int64_t n_edges,
+  const int32_t* edge_nodes, double* dual_nodal_volume, double* elem_volume,
+  double* edge_area)
+{
+  std::map<std::pair<int32_t, int32_t>, int64_t> edgeOf;
+  for (int64_t e = 0; e < n_edges; ++e) {
+    const int32_t a = edge_nodes[2 * e], b = edge_nodes[2 * e + 1];
+    edgeOf[{std::min(a, b), std::max(a, b)}] = e;
+  }
+  for (int64_t el = 0; el < n_elems; ++el) {
+    const int32_t* en = elem_nodes + T.npe * el;
+    double c[6][3], v[21][3];
+    for (int n = 0; n < T.npe; ++n)
+      for (int d = 0; d < 3; ++d)
+        c[n][d] = coords[size_t(en[n]) * 3 + d];
+    T.subdivide(c, v);
+    if (!elem_owned || elem_owned[el]) {
+      double ev = 0.0;
+      for (int ip = 0; ip < T.nScv; ++ip) {
+        double vol;
+        if (T.npe == 5 && ip == 4) {
+          double oc[10][3];
+          for (int n = 0; n < 10; ++n)
+            for (int d = 0; d < 3; ++d)
+              oc[n][d] = v[T.scvHex[ip][n]][d];
+          vol = geo_octohedron_volume(oc);
+        } else {
+          double sc[8][3];
+          for (int n = 0; n < 8; ++n)
+            for (int d = 0; d < 3; ++d)
+              sc[n][d] = v[T.scvHex[ip][n]][d];
+          /* the pyramid's base volumes have a bent top face */
+          vol = T.npe == 5 ? geo_bhex_volume_grandy(sc) : geo_hex_volume_grandy(sc);
+        }
+        dual_nodal_volume[en[ip]] += vol; /* ipNodeMap is the identity */
+        ev += vol;
+      }
+      if (elem_volume)
+        elem_volume[el] = ev;
+    }
+    if (!edge_area)
+      continue;
+    for (int ip = 0; ip < T.nScs; ++ip) {
+      double sc[4][3], av[3];
+      for (int n = 0; n < 4; ++n)
+        for (int d = 0; d < 3; ++d)
+          sc[n][d] = v[T.scsQuad[ip][n]][d];
+      geo_quad_area(sc, av);
+      /* scsIpEdgeOrd (Pyr5: {0,1,2,3,4,4,5,5,6,6,7,7}) names the element edge
+       * that joins the ip's lrscv pair: look it up by its two nodes */
+      const int32_t nl = en[T.lrscv[2 * ip]], nr = en[T.lrscv[2 * ip + 1]];
+      auto it = edgeOf.find({std::min(nl, nr), std::max(nl, nr)});
+      if (it == edgeOf.end())
+        continue;
+      const int64_t e = it->second;
+      const double sign = (nl == edge_nodes[2 * e]) ? 1.0 : -1.0;
+      for (int d = 0; d < 3; ++d)
+        edge_area[e * 3 + d] += av[d] * sign;
+    }
+  }
+}
+
+} // namespace
+
+/* GeometryInteriorAlg<AlgTraitsTet4 / Wed6 / Pyr5>
+ * (src/ngp_algorithms/GeometryInteriorAlg.C:72-112, 165-225) with
+ * TetSCV/TetSCS (src/master_element/Tet4CVFEM.C:243-343, 522-619),
+ * WedSCV/WedSCS (Wed6CVFEM.C:267-369, 541-647) and PyrSCV/PyrSCS
+ * (Pyr5CVFEM.C:438-572, 772-900).  Conventions of orc_geometry_interior_hex8.
+ * No in-tree known-answer test holds values for these three topologies: the
+ * restatement is pinned by properties (tests/test_geometry_topologies_cpu.py). */
+extern "C" void
+orc_geometry_interior_tet4(
+  int64_t n_elems, const int32_t* elem_nodes, const unsigned char* elem_owned,
+  const double* coords, int64_t n_edges, const int32_t* edge_nodes,
+  double* dual_nodal_volume, double* elem_volume, double* edge_area)
+{
+  geo_interior_3d(kGeoTet4, n_elems, elem_nodes, elem_owned, coords, n_edges,
+                  edge_nodes, dual_nodal_volume, elem_volume, edge_area);
+}
+
+extern "C" void
+orc_geometry_interior_wed6(
+  int64_t n_elems, const int32_t* elem_nodes, const unsigned char* elem_owned,
+  const double* coords, int64_t n_edges, const int32_t* edge_nodes,
+  double* dual_nodal_volume, double* elem_volume, double* edge_area)
+{
+  geo_interior_3d(kGeoWed6, n_elems, elem_nodes, elem_owned, coords, n_edges,
+                  edge_nodes, dual_nodal_volume, elem_volume, edge_area);
+}
+
+extern "C" void
+orc_geometry_interior_pyr5(
+  int64_t n_elems, const int32_t* elem_nodes, const unsigned char* elem_owned,
+  const double* coords, int64_t n_edges, const int32_t* edge_nodes,
+  double* dual_nodal_volume, double* elem_volume, double* edge_area)
+{
+  geo_interior_3d(kGeoPyr5, n_elems, elem_nodes, elem_owned, coords, n_edges,
+                  edge_nodes, dual_nodal_volume, elem_volume, edge_area);
+}
+
 /* MdotEdgeAlg / ContinuityEdgeSolverAlg with the optional terms:
  * balanced buoyancy forcing (use_balanced_buoyancy_force; gravity, fields
  * buoyancy_source / buoyancy_source_mask) and the GCL term of deforming meshes

@@ -175,6 +175,22 @@ void orc_geometry_interior_quad4(
   const double* coords, int64_t n_edges, const int32_t* edge_nodes,
   double* dual_nodal_volume, double* elem_volume, double* edge_area);
 
+/* GeometryInteriorAlg<AlgTraitsTet4 / Wed6 / Pyr5> (Tet4CVFEM.C:243-343, 522-619;
+ * Wed6CVFEM.C:267-369, 541-647; Pyr5CVFEM.C:348-572, 772-900); conventions of
+ * orc_geometry_interior_hex8 */
+void orc_geometry_interior_tet4(
+  int64_t n_elems, const int32_t* elem_nodes, const unsigned char* elem_owned,
+  const double* coords, int64_t n_edges, const int32_t* edge_nodes,
+  double* dual_nodal_volume, double* elem_volume, double* edge_area);
+void orc_geometry_interior_wed6(
+  int64_t n_elems, const int32_t* elem_nodes, const unsigned char* elem_owned,
+  const double* coords, int64_t n_edges, const int32_t* edge_nodes,
+  double* dual_nodal_volume, double* elem_volume, double* edge_area);
+void orc_geometry_interior_pyr5(
+  int64_t n_elems, const int32_t* elem_nodes, const unsigned char* elem_owned,
+  const double* coords, int64_t n_edges, const int32_t* edge_nodes,
+  double* dual_nodal_volume, double* elem_volume, double* edge_area);
+
 /* MdotEdgeAlg (sink == NULL) / ContinuityEdgeSolverAlg (sink != NULL) with the
  * optional balanced-buoyancy and GCL terms (MdotEdgeAlg.C:153-163, 175-180;
  * ContinuityEdgeSolverAlg.C:147-158, 172-177) */

@@ -428,6 +428,30 @@ def geometry_interior_quad4(elem_nodes, coords, edge_nodes, n_nodes, elem_owned=
     return dnv, ev, area
 
 
+def geometry_interior_3d(topo, elem_nodes, coords, edge_nodes, n_nodes,
+                         elem_owned=None, accumulate=None):
+    """GeometryInteriorAlg for one 3-D element block; topo in 'hex' 'tet' 'wed'
+    'pyr'.  Returns (dual_nodal_volume, elem_volume, edge_area); `accumulate` =
+    (dual_nodal_volume, edge_area) of earlier blocks of the same mesh to add to."""
+    name = {"hex": "hex8", "tet": "tet4", "wed": "wed6", "pyr": "pyr5"}[topo]
+    el = np.ascontiguousarray(elem_nodes, dtype=np.int32)
+    en = np.ascontiguousarray(edge_nodes, dtype=np.int32)
+    xyz = np.ascontiguousarray(coords, dtype=np.float64)
+    own = None if elem_owned is None else np.ascontiguousarray(elem_owned, dtype=np.uint8)
+    if accumulate is None:
+        dnv, area = np.zeros(n_nodes), np.zeros((en.size // 2, 3))
+    else:
+        dnv, area = accumulate
+    ev = np.zeros(len(el))
+    f = getattr(lib(), "orc_geometry_interior_" + name)
+    f.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    f(len(el), el.ctypes.data, None if own is None else own.ctypes.data,
+      xyz.ctypes.data, en.size // 2, en.ctypes.data, dnv.ctypes.data,
+      ev.ctypes.data, area.ctypes.data)
+    return dnv, ev, area
+
+
 def mdot_continuity_edge_ext(ndim, edge_nodes, coords, vel, gpdx, rho, p, udiag,
                              area, noc_fac=1.0, interp_together=1.0,
                              gravity=None, source=None, source_mask=None,

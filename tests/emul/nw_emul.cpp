@@ -15,7 +15,10 @@
 #include <string>
 #include <vector>
 
+#include <map>
+
 #include "edge_physics.h"
+#include "geometry_cvfem.h"
 #include "plan.h"
 
 using namespace nw;
@@ -116,6 +119,50 @@ stage(const MeshPlan& mp, const TileHdr& h, const std::vector<const double*>& co
 }
 
 } // namespace
+
+/* GeometryInteriorAlg<Tet4 / Wed6 / Pyr5> with the product's per-element
+ * arithmetic (csrc/geometry_cvfem.h) replayed element by element: the host
+ * side of nw_geometry_interior_* (edge look-up by the surface's node pair,
+ * sign from the edge's first node) + the body of geometry_cvfem_kernel.
+ * topo: 0 tet4, 1 wed6, 2 pyr5; accumulates into dnv [n_nodes], area [n_edges][3] */
+template <int T>
+static void
+emu_geo_block(
+  int64_t nElems, const int32_t* elemNodes, const double* coords, int64_t nEdges,
+  const int32_t* edgeNodes, double* dnv, double* area)
+{
+  constexpr int npe = geo::Traits<T>::npe;
+  std::map<std::pair<int32_t, int32_t>, int64_t> edgeOf;
+  for (int64_t e = 0; e < nEdges; ++e) {
+    const int32_t a = edgeNodes[2 * e], b = edgeNodes[2 * e + 1];
+    edgeOf[{std::min(a, b), std::max(a, b)}] = e;
+  }
+  for (int64_t el = 0; el < nElems; ++el) {
+    const int32_t* en = elemNodes + (int64_t)npe * el;
+    double c[npe][3], v[geo::Traits<T>::nSub][3];
+    for (int n = 0; n < npe; ++n)
+      for (int d = 0; d < 3; ++d)
+        c[n][d] = coords[(int64_t)en[n] * 3 + d];
+    geo::sub_points<T>(c, v);
+    if (dnv)
+      for (int ip = 0; ip < geo::Traits<T>::nScv; ++ip)
+        dnv[en[ip]] += geo::scv_volume<T>(ip, v);
+    if (!area)
+      continue;
+    for (int ip = 0; ip < geo::Traits<T>::nScs; ++ip) {
+      int l, r;
+      geo::scs_nodes<T>(ip, &l, &r);
+      auto it = edgeOf.find({std::min(en[l], en[r]), std::max(en[l], en[r])});
+      if (it == edgeOf.end())
+        continue;
+      double a[3];
+      geo::scs_area<T>(ip, v, a);
+      const double sg = en[l] == edgeNodes[2 * it->second] ? 1.0 : -1.0;
+      for (int d = 0; d < 3; ++d)
+        area[it->second * 3 + d] += a[d] * sg;
+    }
+  }
+}
 
 extern "C" {
 
@@ -685,6 +732,25 @@ emu_plan_stats(void* h, int64_t* out)
   out[3] = e->hasLs ? (int64_t)e->lp.heEll.size() : 0;
   out[4] = (int64_t)mp.heNodeEll.size();
   return 0;
+}
+
+int
+emu_geometry_cvfem(
+  int topo, int64_t nElems, const int32_t* elemNodes, const double* coords,
+  int64_t nEdges, const int32_t* edgeNodes, double* dnv, double* area)
+{
+  switch (topo) {
+  case geo::TET4:
+    emu_geo_block<geo::TET4>(nElems, elemNodes, coords, nEdges, edgeNodes, dnv, area);
+    return 0;
+  case geo::WED6:
+    emu_geo_block<geo::WED6>(nElems, elemNodes, coords, nEdges, edgeNodes, dnv, area);
+    return 0;
+  case geo::PYR5:
+    emu_geo_block<geo::PYR5>(nElems, elemNodes, coords, nEdges, edgeNodes, dnv, area);
+    return 0;
+  }
+  return 1;
 }
 
 } // extern "C"

@@ -3,8 +3,8 @@
 (reg_tests/mesh, NetCDF-3 Exodus files readable with scipy) and write them to
 tests/golden/mesh_*.npz: node coordinates, global node ids, the edge list
 stk::mesh::create_edges would make (unique element edges, each ordered by
-ascending global id, first-visit order) and -- for the 2-D quad mesh -- the
-element connectivity.  Run in the build container only (the GPU box has no
+ascending global id, first-visit order) and the element connectivity per
+topology (elems_tet / elems_pyr / elems_wed / elems_hex / elems_qua).  Run in the build container only (the GPU box has no
 /root/reference):  python tests/golden/extract_reference_meshes.py
 
   multiElemTypeCylinder.g   TETRA4 / HEX8 / WEDGE6 / PYRAMID5   (BASELINE configs[4])
@@ -64,8 +64,8 @@ def convert(fname, out, keep_elems=False):
 
 
 def main():
-    convert("multiElemTypeCylinder.g", "mesh_multiElemTypeCylinder.npz")
-    convert("hybrid.g.8.0", "mesh_hybrid_g_8_0.npz")
+    convert("multiElemTypeCylinder.g", "mesh_multiElemTypeCylinder.npz", keep_elems=True)
+    convert("hybrid.g.8.0", "mesh_hybrid_g_8_0.npz", keep_elems=True)
     convert("airfoilRANSEdgeTrilinos.rst", "mesh_airfoilRANSEdge.npz", keep_elems=True)
 
 

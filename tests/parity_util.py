@@ -597,6 +597,74 @@ def load_reference_mesh(name):
     return np.load(os.path.join(HERE, "golden", "mesh_%s.npz" % name))
 
 
+# element faces, outward (stk / Exodus node order), for boundary detection and an
+# independent element volume
+ELEM_FACES = {
+    "tet": [(0, 1, 3), (1, 2, 3), (0, 3, 2), (0, 2, 1)],
+    "pyr": [(0, 1, 4), (1, 2, 4), (2, 3, 4), (0, 4, 3), (0, 3, 2, 1)],
+    "wed": [(0, 1, 4, 3), (1, 2, 5, 4), (0, 3, 5, 2), (0, 2, 1), (3, 4, 5)],
+    "hex": [(0, 1, 5, 4), (1, 2, 6, 5), (2, 3, 7, 6), (0, 4, 7, 3),
+            (0, 3, 2, 1), (4, 5, 6, 7)],
+}
+TOPOLOGIES = ("hex", "tet", "wed", "pyr")
+
+
+def mesh_blocks(m):
+    """{topology: [n][npe] connectivity} of a mesh fixture"""
+    return {t: np.ascontiguousarray(m["elems_" + t]) for t in TOPOLOGIES
+            if "elems_" + t in m.files}
+
+
+def boundary_nodes(blocks, n_nodes):
+    """mask of the nodes on faces that belong to one element only"""
+    keys, nodes = [], []
+    for t, conn in blocks.items():
+        for f in ELEM_FACES[t]:
+            fn = conn[:, list(f)].astype(np.int64)
+            if fn.shape[1] == 3:
+                fn = np.concatenate([fn, -np.ones((len(fn), 1), np.int64)], axis=1)
+            nodes.append(fn)
+            k = np.sort(fn, axis=1)
+            keys.append(((k[:, 0] * (n_nodes + 1) + k[:, 1] + 1) * (n_nodes + 1)
+                         + k[:, 2] + 1) * (n_nodes + 1) + k[:, 3] + 1)
+    keys, nodes = np.concatenate(keys), np.concatenate(nodes)
+    _, inv, cnt = np.unique(keys, return_inverse=True, return_counts=True)
+    once = nodes[cnt[inv] == 1].ravel()
+    mask = np.zeros(n_nodes, dtype=bool)
+    mask[once[once >= 0]] = True
+    return mask
+
+
+def element_volumes_by_faces(topo, conn, coords):
+    """divergence-theorem volume of every element, quadrilateral faces fanned
+    about their centroid (independent of the sub-control-volume construction)"""
+    vol = np.zeros(len(conn))
+    x = coords[conn]  # [n][npe][3]
+    x = x - x[:, :1]  # element-local origin: no cancellation against |x|^3
+    for f in ELEM_FACES[topo]:
+        p = x[:, list(f)]
+        if len(f) == 3:
+            tris = [(p[:, 0], p[:, 1], p[:, 2])]
+        else:
+            c = p.mean(axis=1)
+            tris = [(p[:, k], p[:, (k + 1) % 4], c) for k in range(4)]
+        for a, b, c in tris:
+            vol += np.einsum("ij,ij->i", a, np.cross(b, c)) / 6.0
+    return vol
+
+
+def oracle_mesh_geometry(blocks, coords, edges):
+    """GeometryInteriorAlg over every block (oracle): dual volumes, edge area
+    vectors, {topology: element volumes}"""
+    n = len(coords)
+    acc = (np.zeros(n), np.zeros((len(edges), 3)))
+    ev = {}
+    for t, conn in blocks.items():
+        _, ev[t], _ = orc.geometry_interior_3d(t, conn, coords, edges, n,
+                                               accumulate=acc)
+    return acc[0], acc[1], ev
+
+
 class _Obj:
     pass
 
