@@ -672,9 +672,12 @@ class _Obj:
 class RealMeshCase:
     """a 3-D reference mesh as one rank, with the attributes of Case: synthetic
     smooth + noise state, synthetic (edge-aligned + seeded transverse) area
-    vectors and positive dual volumes -- all the edge kernels see of geometry"""
+    vectors and positive dual volumes -- all the edge kernels see of geometry --
+    or the mesh's true CVFEM dual geometry"""
 
-    def __init__(self, name, seed=20261017):
+    def __init__(self, name, seed=20261017, geometry="synthetic"):
+        """geometry="cvfem": the true dual mesh (GeometryInteriorAlg over the
+        tet / pyramid / wedge / hex blocks, from the oracle) instead"""
         P = pkg()
         synth = __import__("nalu_wind_b200.synth", fromlist=["state"])
         m = load_reference_mesh(name)
@@ -696,6 +699,9 @@ class RealMeshCase:
         b.area = np.ascontiguousarray(
             0.3 * ln * dx + 0.05 * ln * ln * rng.standard_normal(dx.shape))
         b.vol = (0.5 + rng.random(n)) * float(np.mean(ln)) ** 3
+        if geometry == "cvfem":
+            self.blocks = mesh_blocks(m)
+            b.vol, b.area, _ = oracle_mesh_geometry(self.blocks, coords, edges)
         b.make_mesh = lambda ctx, tile_nodes=0: P.Mesh(
             ctx, 3, b.edges, b.hid, b.coords, tile_nodes=tile_nodes)
         self.box = b

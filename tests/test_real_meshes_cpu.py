@@ -29,10 +29,11 @@ def test_fixture_edge_counts():
     assert 49536 + 49152 == 98688
 
 
-@pytest.mark.parametrize("name", MESHES_3D)
-def test_real_mesh_graph_slot_map_and_walkthrough(name):
+@pytest.mark.parametrize("name,geometry", [(n, g) for n in MESHES_3D
+                                           for g in ("synthetic", "cvfem")])
+def test_real_mesh_graph_slot_map_and_walkthrough(name, geometry):
     P = pu.pkg()
-    case = pu.RealMeshCase(name)
+    case = pu.RealMeshCase(name, geometry=geometry)
     ctx = P.Context(-1)
     mesh = case.box.make_mesh(ctx)
     st = mesh.stats()
