@@ -734,6 +734,39 @@ emu_plan_stats(void* h, int64_t* out)
   return 0;
 }
 
+/* the same sector count for a field stored node-major with k components
+ * (per-field AoS, 8k bytes per node): distinct 32-byte sectors touched by each
+ * tile's halo list (whole tile, not per warp: an upper bound on reuse) and per
+ * group of `group` consecutive halo entries (out[0], out[1]) */
+int
+emu_halo_sectors_aos(void* h, int k, int group, int64_t* out)
+{
+  Emu* e = static_cast<Emu*>(h);
+  const MeshPlan& mp = e->mp;
+  int64_t perTile = 0, perGroup = 0;
+  for (int64_t t = 0; t < mp.nTiles; ++t) {
+    const TileHdr& hd = mp.tiles[t];
+    std::vector<int64_t> all;
+    for (int k0 = 0; k0 < hd.nHalo; k0 += group) {
+      std::vector<int64_t> sec;
+      for (int q = k0; q < std::min(hd.nHalo, k0 + group); ++q) {
+        const int64_t n = mp.haloNodes[hd.haloPtr + q];
+        for (int64_t b = n * 8 * k / 32; b <= ((n + 1) * 8 * k - 1) / 32; ++b)
+          sec.push_back(b);
+      }
+      std::sort(sec.begin(), sec.end());
+      sec.erase(std::unique(sec.begin(), sec.end()), sec.end());
+      perGroup += (int64_t)sec.size();
+      all.insert(all.end(), sec.begin(), sec.end());
+    }
+    std::sort(all.begin(), all.end());
+    perTile += std::unique(all.begin(), all.end()) - all.begin();
+  }
+  out[0] = perTile;
+  out[1] = perGroup;
+  return 0;
+}
+
 int
 emu_geometry_cvfem(
   int topo, int64_t nElems, const int32_t* elemNodes, const double* coords,
