@@ -159,11 +159,13 @@ def cpu_sweep(orc, box, fields, g, sst):
                           f["density"], f["pressure"], f["momentum_diag"],
                           box.area, 1.0, 1.0)
     s = orc.HypreSink(g, box.hid, uvw_ndim=3)
+    s.track_abs(False)  # test-only bookkeeping the reference does not have
     orc.momentum_edge(3, box.edges, box.coords, f["velocity"], f["dudx"],
                       f["viscosity"], f["density"],
                       f["abl_wall_no_slip_wall_func_node_mask"], box.area, mdot0,
                       pec, s, **MOM_OPTS)
     s2 = orc.HypreSink(g, box.hid)
+    s2.track_abs(False)
     orc.continuity_edge(3, box.edges, box.coords, f["velocity"], f["dpdx"],
                         f["density"], f["pressure"], f["momentum_diag"],
                         box.area, s2, **CONT_OPTS)
@@ -176,6 +178,7 @@ def cpu_sweep(orc, box, fields, g, sst):
                           ("specific_dissipation_rate", "dwdx",
                            "effective_viscosity_sdr")):
             s3 = orc.HypreSink(g, box.hid)
+            s3.track_abs(False)
             orc.scalar_edge(3, box.edges, box.coords, f["velocity"], f[q], f[dq],
                             f["density"], f[mu], box.area, mdot0, s3,
                             pf=orc.peclet("tanh", 2.0, 1.0), **SCAL_OPTS)
@@ -206,8 +209,10 @@ def run_cpu_baseline(P, n, sst, threads):
         tot += cpu_sweep(orc, box, fields, g, sst)
         reps += 1
     orc.set_num_threads(1)
+    t1 = cpu_sweep(orc, box, fields, g, sst)  # also single-thread
     return {"value": box.n_edges * reps / tot / 1e6, "unit": "Medges/s",
             "cores": threads, "kind": "port",
+            "single_thread_value": box.n_edges / t1 / 1e6,
             "sample": "%d^3-element box (%d edges), %d full sweeps, %.1f s; "
                       "oracle/edge_oracle.cpp (reference cannot be compiled: no "
                       "Kokkos/STK/hypre)" % (ns, box.n_edges, reps, tot)}
@@ -235,6 +240,8 @@ def main_reference(args):
     for _ in range(args.steps):
         t += cpu_sweep(orc, box, fields, g, args.sst)
     val = box.n_edges * args.steps / t / 1e6
+    orc.set_num_threads(1)
+    t1 = cpu_sweep(orc, box, fields, g, args.sst)  # also single-thread
     sample = ("each step = one full sweep over a %d^3-element box (%d edges), "
               "same fields/options as the GPU arm" % (ns, box.n_edges))
     line = {
@@ -246,7 +253,8 @@ def main_reference(args):
         "data": "synthetic",
         "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": val, "unit": "Medges/s", "cores": threads,
-                         "kind": "port", "sample": sample},
+                         "kind": "port", "single_thread_value": box.n_edges / t1 / 1e6,
+                         "sample": sample},
         "e2e": {"value": val, "unit": "Medges/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }

@@ -99,6 +99,8 @@ orc_applier* orc_applier_hypre_create(
   const orc_graph*, const int64_t* node_hid, int64_t n_nodes, int uvw_ndim);
 /* resetCoeffApplierData (:1386-1430): zero + periodic rows diag 1 / rhs 0 */
 void orc_applier_hypre_reset(orc_applier*);
+/* |contribution| sums (the tests' tolerance scale) on / off; off for timing runs */
+void orc_applier_hypre_track_abs(orc_applier*, int on);
 /* values: [nnzOwned+nnzShared]; rhs: column-major [numRows][nrhs] where
  * numRows = owned+shared, nrhs = 1 or uvw_ndim (rhs_dev_(index,d)). */
 void orc_applier_hypre_get(const orc_applier*, double* values, double* rhs);

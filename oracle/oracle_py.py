@@ -77,6 +77,7 @@ def lib():
     L.orc_applier_hypre_create.restype = vp
     L.orc_applier_hypre_create.argtypes = [vp, c_i64p, C.c_int64, C.c_int]
     L.orc_applier_hypre_reset.argtypes = [vp]
+    L.orc_applier_hypre_track_abs.argtypes = [vp, C.c_int]
     L.orc_applier_hypre_get.argtypes = [vp, c_f64p, c_f64p]
     L.orc_applier_hypre_get_abs.argtypes = [vp, c_f64p, c_f64p]
     L.orc_applier_hypre_enable_log.argtypes = [vp, C.c_int64]
@@ -212,6 +213,10 @@ class HypreSink:
 
     def reset(self):
         lib().orc_applier_hypre_reset(self.h)
+
+    def track_abs(self, on):
+        """|contribution| sums (tolerance scale of the tests); off for timing"""
+        lib().orc_applier_hypre_track_abs(self.h, int(bool(on)))
 
     def enable_log(self, n_calls):
         self._log_calls = n_calls
