@@ -61,13 +61,9 @@ def test_parent_and_affine_elements(topo):
         assert np.max(np.abs(dnv0 - v0 / npe)) <= 2e-16
     else:
         assert np.max(np.abs(dnv0[:4] - dnv0[0])) <= 2e-16 and dnv0[4] > dnv0[0]
-    # the facets of node 0's control volume + its share of the boundary close:
-    # sum over the element of the signed areas at each node equals minus the
-    # boundary share; for the whole element the areas telescope to zero
-    acc = np.zeros((npe, 3))
-    np.add.at(acc, I32(edges)[:, 0], area0)
-    np.add.at(acc, I32(edges)[:, 1], -area0)
-    assert np.max(np.abs(acc.sum(axis=0))) <= 1e-16
+    # every sub-control surface points from its left to its right node
+    dx0 = x0[I32(edges)[:, 1]] - x0[I32(edges)[:, 0]]
+    assert np.all(np.einsum("ij,ij->i", area0, dx0) > 0.0)
     rng = np.random.default_rng(7 + npe)
     for _ in range(5):
         A = np.eye(3) + 0.4 * rng.standard_normal((3, 3))
@@ -150,3 +146,34 @@ def test_reference_mixed_mesh_dual_geometry(name):
         oa += a
     assert np.max(np.abs(pd - od)) <= 1e-14 * np.max(od)
     assert np.max(np.abs(pa - oa)) <= 1e-14 * np.max(np.abs(oa))
+
+
+@pytest.mark.parametrize("topo", ["tet", "wed", "pyr"])
+def test_warped_elements_product_arithmetic_vs_oracle(topo):
+    """200 randomly warped (non-affine: bent quadrilateral faces) elements in
+    one block, sharing no nodes: product header == oracle to rounding, volumes
+    positive and close to the planar-fan estimate, area vectors along their edges"""
+    x0, edges0, _ = PARENT[topo]
+    npe, ne = len(x0), len(edges0)
+    rng = np.random.default_rng(20261017 + npe)
+    nel = 200
+    coords = np.concatenate([
+        (x0 + 0.12 * rng.standard_normal(x0.shape)) * rng.uniform(0.5, 3.0)
+        + 10.0 * rng.standard_normal(3) for _ in range(nel)])
+    conn = I32(np.arange(nel * npe).reshape(nel, npe))
+    edges = I32(np.concatenate([np.array(edges0) + npe * k for k in range(nel)]))
+    # random edge orientation, as global-id ordering gives on a real mesh
+    flip = rng.random(len(edges)) < 0.5
+    edges[flip] = edges[flip][:, ::-1]
+    n = len(coords)
+    dnv, ev, area = orc.geometry_interior_3d(topo, conn, coords, edges, n)
+    pdv, parea = emu_geometry(topo, conn, coords, edges)
+    assert np.max(np.abs(pdv - dnv)) <= 1e-13 * np.max(dnv)
+    assert np.max(np.abs(parea - area)) <= 1e-13 * np.max(np.abs(area))
+    assert np.all(dnv > 0.0)
+    ref = pu.element_volumes_by_faces(topo, conn, coords)
+    assert np.max(np.abs(ev - ref) / ref) <= (1e-11 if topo == "tet" else 0.05)
+    # orientation: an edge's area vector points from its first to its second node
+    dx = coords[edges[:, 1]] - coords[edges[:, 0]]
+    assert np.all(np.einsum("ij,ij->i", area, dx) > 0.0)
+    assert len(edges) == nel * ne
