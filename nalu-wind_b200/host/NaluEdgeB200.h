@@ -18,7 +18,7 @@
  *   SolverAlgorithm::initialize_connectivity                 SolverAlgorithm
  *   AssembleEdgeSolverAlgorithm                              same name
  *   MomentumEdgeSolverAlg / ContinuityEdgeSolverAlg /
- *   ScalarEdgeSolverAlg (src/edge_kernels/*.C)               same names
+ *   ScalarEdgeSolverAlg (src/edge_kernels/ *.C)               same names
  *   MdotEdgeAlg, NodalGradEdgeAlg<Phi,Grad> + aliases,
  *   MomentumEdgePecletAlg                                    same names
  *
