@@ -136,6 +136,9 @@ nw_ctx_create(int cuda_device, nw_ctx** out)
 }
 
 static int p2p_init(nw_ctx* ctx);
+static int p2p_check_error(nw_ctx* ctx);
+static void p2p_queue_error_read(nw_ctx* ctx, cudaStream_t s);
+static int p2p_error_after_sync(nw_ctx* ctx);
 static void p2p_close(nw_ctx* ctx);
 
 extern "C" int
@@ -161,16 +164,8 @@ nw_ctx_sync(nw_ctx* ctx)
   NW_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ctx->p2p.commStream)
     NW_CUDA(cudaStreamSynchronize(ctx->p2p.commStream));
-  if (ctx->p2p.ok) {
-    /* a pull kernel that gave up waiting for a peer leaves a mark */
-    unsigned w[2] = {0, 0};
-    NW_CUDA(cudaMemcpy(w, ctx->p2p.sync.p, sizeof(w), cudaMemcpyDeviceToHost));
-    if (w[1] != 0)
-      return fail(
-        NW_ERR_COMM, "nw_ctx_sync: a peer-memory halo exchange timed out "
-                     "waiting for a neighbour rank (results are incomplete)");
-  }
-  return NW_OK;
+  /* a pull kernel that gave up waiting for a peer leaves a mark */
+  return p2p_check_error(ctx);
 }
 
 extern "C" void*
@@ -302,9 +297,12 @@ nw_mesh_create(nw_ctx* ctx, const nw_mesh_desc* desc, nw_mesh** out)
   if (desc->nranks > 1) {
     const int64_t* own =
       desc->node_own_hypre_id ? desc->node_own_hypre_id : desc->node_hypre_id;
+    m->ownedNodeOfHid.assign(
+      (size_t)std::max<int64_t>(0, m->plan.iUpperNode - m->plan.iLowerNode + 1),
+      -1);
     for (int64_t n = 0; n < desc->n_nodes; ++n)
       if (own[n] >= m->plan.iLowerNode && own[n] <= m->plan.iUpperNode)
-        m->ownedNodeOfHid[own[n]] = (int32_t)n;
+        m->ownedNodeOfHid[own[n] - m->plan.iLowerNode] = (int32_t)n;
     if (int rc = mesh_halo_prepare(m.get(), own))
       return rc;
   }
@@ -558,8 +556,9 @@ nw_field_download(nw_mesh* mesh, int field_id, double* host)
       f->buf.as<double>(), f->ncomp, mesh->dPrimarySlot.as<int32_t>(),
       mesh->plan.nEdges, f->stride, mesh->scratch.as<double>(), s));
   NW_CUDA(cudaMemcpyAsync(host, mesh->scratch.p, bytes, cudaMemcpyDeviceToHost, s));
+  p2p_queue_error_read(mesh->ctx, s);
   NW_CUDA(cudaStreamSynchronize(s));
-  return NW_OK;
+  return p2p_error_after_sync(mesh->ctx);
 }
 
 extern "C" int
@@ -1001,6 +1000,7 @@ nw_linsys_create(nw_mesh* mesh, int kind, int num_dof, nw_linsys** out)
   if (kind == NW_LINSYS_HYPRE && !(num_dof == 1 || num_dof == mesh->plan.ndim))
     return fail(NW_ERR_ARG, "nw_linsys_create: num_dof must be 1 or ndim");
   auto* ls = new nw_linsys;
+  ls->sh = std::make_shared<nw_ls_shared>();
   ls->mesh = mesh;
   ls->kind = kind;
   ls->numDof = kind == NW_LINSYS_HYPRE_UVW ? 1 : num_dof;
@@ -1049,7 +1049,8 @@ linsys_upload(nw_linsys* ls)
   nw_mesh* m = ls->mesh;
   cudaStream_t s = m->ctx->stream;
   NW_CUDA(cudaSetDevice(m->ctx->device));
-  const Graph& g = ls->g;
+  nw_ls_shared& sh = *ls->sh;
+  const Graph& g = sh.g;
   const int64_t nnz = g.nnzOwned + g.nnzShared + ls->nExtra;
   const int64_t rows = g.numRowsLocal();
   NW_CUDA(ls->dValues.alloc(sizeof(double) * (nnz + 2)));
@@ -1058,47 +1059,52 @@ linsys_upload(nw_linsys* ls)
   ls->dev.rhs = ls->dRhs.as<double>();
   ls->dev.rhsStride = rows;
   int rc;
-  if (ls->lp.usable) {
-    if ((rc = upload(ls->dLsTiles, ls->lp.tiles, s, nullptr)) ||
-        (rc = upload(ls->dEntInfo, ls->lp.entInfo, s, nullptr)) ||
-        (rc = upload(ls->dEntRhsRow, ls->lp.entRhsRow, s, nullptr)) ||
-        (rc = upload(ls->dHe, ls->lp.heEll, s, nullptr)) ||
-        (rc = upload(ls->dWarp, ls->lp.sliceOff, s, nullptr)) ||
-        (rc = upload(ls->dRuns, ls->lp.entGo, s, nullptr)))
-      return rc;
-    ls->dev.tiles = ls->dLsTiles.as<LsTileHdr>();
-    ls->dev.entInfo = ls->dEntInfo.as<EntInfo>();
-    ls->dev.entRhsRow = ls->dEntRhsRow.as<int32_t>();
-    ls->dev.heEll = ls->dHe.as<uint32_t>();
-    ls->dev.sliceOff = ls->dWarp.as<int32_t>();
-    ls->dev.entGo = ls->dRuns.as<int32_t>();
-    ls->dev.maxTileNnz = (int)ls->lp.maxTileNnz;
-    ls->dev.maxTileEnts = (int)ls->lp.maxTileEnts;
-    ls->dev.maxTileEll = (int)ls->lp.maxTileEll;
-    /* rows the tiles do not write */
-    std::vector<uint8_t> isPer(ls->lp.uncoveredRows.size(), 0);
-    for (size_t i = 0; i < isPer.size(); ++i) {
-      const int64_t r = ls->lp.uncoveredRows[i];
-      if (r < g.numRowsOwned)
-        isPer[i] = std::binary_search(
-          g.periodicRowsOwned.begin(), g.periodicRowsOwned.end(), g.iLower + r);
+  /* the integer plan is uploaded once per shared graph */
+  if (!sh.uploaded) {
+    if (sh.lp.usable) {
+      if ((rc = upload(sh.dLsTiles, sh.lp.tiles, s, nullptr)) ||
+          (rc = upload(sh.dEntInfo, sh.lp.entInfo, s, nullptr)) ||
+          (rc = upload(sh.dEntRhsRow, sh.lp.entRhsRow, s, nullptr)) ||
+          (rc = upload(sh.dHe, sh.lp.heEll, s, nullptr)) ||
+          (rc = upload(sh.dWarp, sh.lp.sliceOff, s, nullptr)) ||
+          (rc = upload(sh.dRuns, sh.lp.entGo, s, nullptr)))
+        return rc;
+      /* rows the tiles do not write */
+      std::vector<uint8_t> isPer(sh.lp.uncoveredRows.size(), 0);
+      for (size_t i = 0; i < isPer.size(); ++i) {
+        const int64_t r = sh.lp.uncoveredRows[i];
+        if (r < g.numRowsOwned)
+          isPer[i] = std::binary_search(
+            g.periodicRowsOwned.begin(), g.periodicRowsOwned.end(),
+            g.iLower + r);
+      }
+      if ((rc = upload(sh.dUncovered, sh.lp.uncoveredRows, s, nullptr)) ||
+          (rc = upload(sh.dUncoveredPeriodic, isPer, s, nullptr)))
+        return rc;
     }
-    if ((rc = upload(ls->dUncovered, ls->lp.uncoveredRows, s, nullptr)) ||
-        (rc = upload(ls->dUncoveredPeriodic, isPer, s, nullptr)))
-      return rc;
-  }
-  {
     std::vector<int64_t> rowPtr(rows + 1);
     for (int64_t r = 0; r < rows; ++r)
       rowPtr[r] = g.rowPtr(r);
     rowPtr[rows] = g.nnzOwned + g.nnzShared;
-    if ((rc = upload(ls->dRowPtr, rowPtr, s, nullptr)))
+    if ((rc = upload(sh.dRowPtr, rowPtr, s, nullptr)))
       return rc;
     std::vector<int64_t> per(g.periodicRowsOwned.size());
     for (size_t i = 0; i < per.size(); ++i)
       per[i] = g.rowStartOwned[g.periodicRowsOwned[i] - g.iLower];
-    if ((rc = upload(ls->dPeriodicRows, per, s, nullptr)))
+    if ((rc = upload(sh.dPeriodicRows, per, s, nullptr)))
       return rc;
+    sh.uploaded = true;
+  }
+  if (sh.lp.usable) {
+    ls->dev.tiles = sh.dLsTiles.as<LsTileHdr>();
+    ls->dev.entInfo = sh.dEntInfo.as<EntInfo>();
+    ls->dev.entRhsRow = sh.dEntRhsRow.as<int32_t>();
+    ls->dev.heEll = sh.dHe.as<uint32_t>();
+    ls->dev.sliceOff = sh.dWarp.as<int32_t>();
+    ls->dev.entGo = sh.dRuns.as<int32_t>();
+    ls->dev.maxTileNnz = (int)sh.lp.maxTileNnz;
+    ls->dev.maxTileEnts = (int)sh.lp.maxTileEnts;
+    ls->dev.maxTileEll = (int)sh.lp.maxTileEll;
   }
   const int nPartial = 296;
   NW_CUDA(ls->dNormPartial.alloc(sizeof(double) * nPartial * ls->nRhs));
@@ -1119,9 +1125,28 @@ nw_linsys_finalize(nw_linsys* ls)
       NW_ERR_STATE, "nw_linsys_finalize: buildEdgeToNodeGraph not called");
   if (ls->finalized)
     return NW_OK;
-  NW_TRY(build_graph(ls->mesh->plan, ls->kind, ls->numDof, ls->skipped, ls->g);
-         build_ls_plan(ls->mesh->plan, ls->g, ls->lp);)
-  if (ls->g.nnzOwned + ls->g.nnzShared >= (int64_t(1) << 31) - 8)
+  {
+    /* same dofs per node + same skipped rows => same graph, slot map and
+     * reduction plan: reuse the instance another system of this mesh built */
+    std::vector<int64_t> key = ls->skipped;
+    std::sort(key.begin(), key.end());
+    key.erase(std::unique(key.begin(), key.end()), key.end());
+    std::shared_ptr<nw_ls_shared> hit;
+    for (auto& c : ls->mesh->lsCache)
+      if (c->numDof == ls->numDof && c->skipped == key)
+        hit = c;
+    if (hit) {
+      ls->sh = hit;
+    } else {
+      NW_TRY(build_graph(
+               ls->mesh->plan, ls->kind, ls->numDof, ls->skipped, ls->sh->g);
+             build_ls_plan(ls->mesh->plan, ls->sh->g, ls->sh->lp);)
+      ls->sh->numDof = ls->numDof;
+      ls->sh->skipped = key;
+      ls->mesh->lsCache.push_back(ls->sh);
+    }
+  }
+  if (ls->sh->g.nnzOwned + ls->sh->g.nnzShared >= (int64_t(1) << 31) - 8)
     return fail(
       NW_ERR_LIMIT, "nw_linsys_finalize: more than 2^31 nonzeros per rank");
   if (ls->mesh->plan.nranks > 1)
@@ -1142,7 +1167,7 @@ nw_linsys_get_sizes(const nw_linsys* ls, nw_linsys_sizes* out)
     return fail(NW_ERR_ARG, "nw_linsys_get_sizes: NULL argument");
   if (!ls->finalized)
     return fail(NW_ERR_STATE, "nw_linsys_get_sizes: not finalized");
-  const Graph& g = ls->g;
+  const Graph& g = ls->sh->g;
   out->i_lower = g.iLower;
   out->i_upper = g.iUpper;
   out->num_rows_owned = g.numRowsOwned;
@@ -1177,7 +1202,7 @@ nw_linsys_get_graph(
     return fail(NW_ERR_ARG, "nw_linsys_get_graph: NULL");
   if (!ls->finalized)
     return fail(NW_ERR_STATE, "nw_linsys_get_graph: not finalized");
-  const Graph& g = ls->g;
+  const Graph& g = ls->sh->g;
   copy_out(mat_row_start_owned, g.rowStartOwned);
   copy_out(mat_row_start_shared, g.rowStartShared);
   copy_out(cols, g.cols);
@@ -1195,8 +1220,8 @@ nw_linsys_get_edge_slots(
     return fail(NW_ERR_ARG, "nw_linsys_get_edge_slots: NULL");
   if (!ls->finalized)
     return fail(NW_ERR_STATE, "nw_linsys_get_edge_slots: not finalized");
-  copy_out(slots, ls->g.edgeSlots);
-  copy_out(rhs_rows, ls->g.edgeRhsRows);
+  copy_out(slots, ls->sh->g.edgeSlots);
+  copy_out(rhs_rows, ls->sh->g.edgeRhsRows);
   return NW_OK;
 }
 
@@ -1225,7 +1250,7 @@ static int
 materialize_zero(nw_linsys* ls)
 {
   cudaStream_t s = ls->mesh->ctx->stream;
-  const Graph& g = ls->g;
+  const Graph& g = ls->sh->g;
   const int64_t nnz = g.nnzOwned + g.nnzShared + ls->nExtra;
   NW_CUDA(cudaMemsetAsync(ls->dValues.p, 0, sizeof(double) * nnz, s));
   NW_CUDA(cudaMemsetAsync(
@@ -1243,7 +1268,7 @@ materialize_zero(nw_linsys* ls)
     NW_CUDA(cudaStreamSynchronize(s));
     /* scatter: dst[idx[i]] += src[i] on zeroed memory */
     NW_CUDA(launch_unpack_add(
-      ls->mesh->scratch.as<double>(), ls->dPeriodicRows.as<int64_t>(), np,
+      ls->mesh->scratch.as<double>(), ls->sh->dPeriodicRows.as<int64_t>(), np,
       ls->dValues.as<double>(), s));
   }
   ls->state = NW_LS_ACCUM;
@@ -1276,7 +1301,7 @@ build_atomic_map(nw_linsys* ls)
   if (ls->atomicBuilt)
     return NW_OK;
   const MeshPlan& mp = ls->mesh->plan;
-  const Graph& g = ls->g;
+  const Graph& g = ls->sh->g;
   const int nb = g.block;
   const int64_t S = mp.nTileEdgeSlots;
   std::vector<int32_t> slots(size_t(S) * nb * nb, -1);
@@ -1306,12 +1331,12 @@ finish_tile_assembly(nw_linsys* ls)
 {
   cudaStream_t s = ls->mesh->ctx->stream;
   NW_CUDA(launch_row_init(
-    ls->dUncovered.as<int32_t>(), (int)ls->lp.uncoveredRows.size(),
-    ls->dRowPtr.as<int64_t>(), ls->dUncoveredPeriodic.as<uint8_t>(),
+    ls->sh->dUncovered.as<int32_t>(), (int)ls->sh->lp.uncoveredRows.size(),
+    ls->sh->dRowPtr.as<int64_t>(), ls->sh->dUncoveredPeriodic.as<uint8_t>(),
     ls->dev.values, ls->dev.rhs, ls->dev.rhsStride, ls->nRhs, s));
   if (ls->nExtra > 0)
     NW_CUDA(cudaMemsetAsync(
-      ls->dev.values + ls->g.nnzOwned + ls->g.nnzShared, 0,
+      ls->dev.values + ls->sh->g.nnzOwned + ls->sh->g.nnzShared, 0,
       sizeof(double) * ls->nExtra, s));
   ls->state = NW_LS_ACCUM;
   return NW_OK;
@@ -1322,7 +1347,7 @@ static int
 use_tile_path(nw_linsys* ls, bool needsDiagExtract, int* rcOut)
 {
   *rcOut = NW_OK;
-  const bool tile = ls->mode == NW_SCATTER_SEGMENTED && ls->lp.usable &&
+  const bool tile = ls->mode == NW_SCATTER_SEGMENTED && ls->sh->lp.usable &&
                     ls->state == NW_LS_LAZY_ZERO && !needsDiagExtract;
   if (tile)
     return 1;
@@ -1520,7 +1545,7 @@ build_node_rows(nw_linsys* ls)
     return NW_OK;
   nw_mesh* mesh = ls->mesh;
   const MeshPlan& mp = mesh->plan;
-  const Graph& g = ls->g;
+  const Graph& g = ls->sh->g;
   const bool uvw = ls->kind == NW_LINSYS_HYPRE_UVW;
   cudaStream_t s = mesh->ctx->stream;
   std::vector<int64_t> rows;
@@ -1564,7 +1589,7 @@ nw_assemble_mass_bdf_node(nw_linsys* ls, int kind, const nw_mass_bdf_opts* opts)
     return fail(NW_ERR_ARG, "nw_assemble_mass_bdf_node: bad argument");
   nw_mesh* mesh = ls->mesh;
   const MeshPlan& mp = mesh->plan;
-  const Graph& g = ls->g;
+  const Graph& g = ls->sh->g;
   const bool uvw = ls->kind == NW_LINSYS_HYPRE_UVW;
   const int nd = mp.ndim;
   if (kind == NW_MASS_MOMENTUM ? !(uvw || ls->numDof == nd)
@@ -1669,7 +1694,7 @@ nw_linsys_reset_rows(
   if (n_nodes < 0 || (n_nodes > 0 && !nodes))
     return fail(NW_ERR_ARG, "nw_linsys_reset_rows: bad node list");
   const MeshPlan& mp = ls->mesh->plan;
-  const Graph& g = ls->g;
+  const Graph& g = ls->sh->g;
   /* UVW: one matrix row per node, all rhs columns; else numDof rows per node */
   const int nd = ls->kind == NW_LINSYS_HYPRE_UVW ? 1 : ls->numDof;
   std::vector<int64_t> rows;
@@ -1717,7 +1742,7 @@ nw_linsys_apply_dirichlet_bcs(
     return fail(NW_ERR_ARG, "nw_linsys_apply_dirichlet_bcs: bad node list");
   nw_mesh* mesh = ls->mesh;
   const MeshPlan& mp = mesh->plan;
-  const Graph& g = ls->g;
+  const Graph& g = ls->sh->g;
   const bool uvw = ls->kind == NW_LINSYS_HYPRE_UVW;
   const int ncomp = uvw ? ls->nRhs : ls->numDof;
   nw_field_t* sol = get_field(mesh, solution_field);
@@ -1770,7 +1795,7 @@ build_dev_graph(nw_linsys* ls)
   if (ls->devGraphBuilt)
     return NW_OK;
   cudaStream_t s = ls->mesh->ctx->stream;
-  const Graph& g = ls->g;
+  const Graph& g = ls->sh->g;
   int rc;
   if ((rc = upload(ls->dRowStartOwned, g.rowStartOwned, s, nullptr)) ||
       (rc = upload(ls->dRowStartShared, g.rowStartShared, s, nullptr)) ||
@@ -1804,7 +1829,7 @@ nw_linsys_sum_into(
       return rc;
   if ((rc = build_dev_graph(ls)))
     return rc;
-  const Graph& g = ls->g;
+  const Graph& g = ls->sh->g;
   NW_CUDA(launch_sum_into(
     n_entities, nodes_per_entity, ls->numDof, d_entity_nodes,
     ls->dNodeHid.as<int64_t>(), d_lhs, d_rhs, g.iLower, g.iUpper,
@@ -1855,7 +1880,7 @@ nw_linsys_write_preassembly_files(
   if (ls->state == NW_LS_LAZY_ZERO)
     if (int rc = materialize_zero(ls))
       return rc;
-  const Graph& g = ls->g;
+  const Graph& g = ls->sh->g;
   const MeshPlan& mp = ls->mesh->plan;
   cudaStream_t s = ls->mesh->ctx->stream;
   const int64_t nnz = g.nnzOwned + g.nnzShared;
@@ -1933,7 +1958,7 @@ nw_linsys_get_values(nw_linsys* ls, double* values, double* rhs)
     if (int rc = materialize_zero(ls))
       return rc;
   cudaStream_t s = ls->mesh->ctx->stream;
-  const Graph& g = ls->g;
+  const Graph& g = ls->sh->g;
   if (values)
     NW_CUDA(cudaMemcpyAsync(
       values, ls->dev.values,
@@ -1943,8 +1968,9 @@ nw_linsys_get_values(nw_linsys* ls, double* values, double* rhs)
     NW_CUDA(cudaMemcpyAsync(
       rhs, ls->dev.rhs, sizeof(double) * g.numRowsLocal() * ls->nRhs,
       cudaMemcpyDeviceToHost, s));
+  p2p_queue_error_read(ls->mesh->ctx, s);
   NW_CUDA(cudaStreamSynchronize(s));
-  return NW_OK;
+  return p2p_error_after_sync(ls->mesh->ctx);
 }
 
 extern "C" int
@@ -1959,12 +1985,13 @@ nw_linsys_rhs_norm2(nw_linsys* ls, double* out)
       return rc;
   cudaStream_t s = ls->mesh->ctx->stream;
   NW_CUDA(launch_norm2(
-    ls->dev.rhs, ls->g.numRowsOwned, ls->dev.rhsStride, ls->nRhs,
+    ls->dev.rhs, ls->sh->g.numRowsOwned, ls->dev.rhsStride, ls->nRhs,
     ls->dNormPartial.as<double>(), 296, ls->dNormOut.as<double>(), s));
   NW_CUDA(cudaMemcpyAsync(
     out, ls->dNormOut.p, sizeof(double) * ls->nRhs, cudaMemcpyDeviceToHost, s));
+  p2p_queue_error_read(ls->mesh->ctx, s);
   NW_CUDA(cudaStreamSynchronize(s));
-  return NW_OK;
+  return p2p_error_after_sync(ls->mesh->ctx);
 }
 
 /* the same summed over all ranks (the nonlinear residual norm the reference
@@ -1983,7 +2010,7 @@ nw_linsys_rhs_norm2_global(nw_linsys* ls, double* out)
   nw_ctx* ctx = ls->mesh->ctx;
   cudaStream_t s = ctx->stream;
   NW_CUDA(launch_norm2(
-    ls->dev.rhs, ls->g.numRowsOwned, ls->dev.rhsStride, ls->nRhs,
+    ls->dev.rhs, ls->sh->g.numRowsOwned, ls->dev.rhsStride, ls->nRhs,
     ls->dNormPartial.as<double>(), 296, ls->dNormOut.as<double>(), s));
   if (ls->mesh->plan.nranks > 1) {
     if (!ctx->comm.comm)
@@ -1995,8 +2022,9 @@ nw_linsys_rhs_norm2_global(nw_linsys* ls, double* out)
   }
   NW_CUDA(cudaMemcpyAsync(
     out, ls->dNormOut.p, sizeof(double) * ls->nRhs, cudaMemcpyDeviceToHost, s));
+  p2p_queue_error_read(ls->mesh->ctx, s);
   NW_CUDA(cudaStreamSynchronize(s));
-  return NW_OK;
+  return p2p_error_after_sync(ls->mesh->ctx);
 }
 
 /* ------------------------------------------------------------------ */

@@ -109,21 +109,24 @@ exchange(
   }
   if (!check(a.GroupStart(), "ncclGroupStart", err))
     return false;
-  for (int i = 0; i < nPeers; ++i) {
+  /* a failed send / receive must not leave the group open (the communicator
+   * would be unusable afterwards): always close it, report the first error */
+  bool ok = true;
+  for (int i = 0; i < nPeers && ok; ++i) {
     if (sendCount[i] > 0)
-      if (!check(
-            a.Send(sendPtr[i], (size_t)sendCount[i], dtype, peers[i],
-                   c.comm, s),
-            "ncclSend", err))
-        return false;
-    if (recvCount[i] > 0)
-      if (!check(
-            a.Recv(recvPtr[i], (size_t)recvCount[i], dtype, peers[i],
-                   c.comm, s),
-            "ncclRecv", err))
-        return false;
+      ok = check(
+        a.Send(sendPtr[i], (size_t)sendCount[i], dtype, peers[i], c.comm, s),
+        "ncclSend", err);
+    if (ok && recvCount[i] > 0)
+      ok = check(
+        a.Recv(recvPtr[i], (size_t)recvCount[i], dtype, peers[i], c.comm, s),
+        "ncclRecv", err);
   }
-  return check(a.GroupEnd(), "ncclGroupEnd", err);
+  std::string endErr;
+  const bool ended = check(a.GroupEnd(), "ncclGroupEnd", endErr);
+  if (ok && !ended)
+    err = endErr;
+  return ok && ended;
 }
 
 } // namespace

@@ -95,6 +95,15 @@ struct nw_p2p
   std::vector<void*> mappedWindow, mappedFlags; /* per rank, opened IPC handles */
   nw::DevBuf dPeerWindow, dPeerFlags; /* device arrays of those pointers */
   unsigned long long epoch = 0;
+  /* Flags are exchanged with the UNION of the neighbours of every exchange
+   * object registered on this context (p2p_register_peers): an exchange
+   * signals and waits for all of them whether or not it carries data for
+   * them, so the epoch / window-parity protocol holds for objects with
+   * different neighbour sets (general RCB / graph partitions). */
+  std::vector<int32_t> unionPeers; /* ascending */
+  nw::DevBuf dUnionPeers;          /* int32 [nranks] */
+  long long timeoutCycles = 40000000000ll; /* NW_P2P_TIMEOUT_S, default 20 s */
+  unsigned* hErr = nullptr; /* pinned host copy of sync[1] (p2p_queue_error_read) */
   /* asynchronous completion (NW_P2P_ASYNC=1): pushes run on the compute stream, pulls on
    * `commStream` beside whatever the compute stream does next.  An object with
    * a pull in flight carries its completion event; every later use of the
@@ -165,15 +174,24 @@ struct nw_node_halo
   std::vector<int64_t> ghostOff, ownedOff; /* per peer offsets, +1 total */
   nw_accum_plan ownedAccum;
   nw::DevBuf sendBuf, recvBuf;
-  /* peer-memory path (every shared node has exactly two sharers): per peer
-   * send [ghosts owned by it | my owned nodes it ghosts], receive the mirror */
+  /* peer-memory path.  p2pMode 1 (every shared node has exactly two sharers):
+   * per peer send [ghosts owned by it | my owned nodes it ghosts], receive the
+   * mirror, both sides add (one epoch).  p2pMode 2 (any number of sharers):
+   * ghosts -> owner with the ordered accumulate, then owner -> ghosts (two
+   * epochs), same summation order as the NCCL path. */
   bool p2p = false;
+  int p2pMode = 0;
+  int64_t nSendA = 0, nSendB = 0, nRecvB = 0;
+  nw::DevBuf dSendIdxA, dSendDstA, dSendIdxB, dSendDstB, dRecvIdxB; /* int64 */
+  nw::DevBuf dSendPeerA, dSendPeerB;                                /* int32 */
+  nw::DevBuf dRecvAllGhost;                                         /* uint8, all 1 */
   int64_t nSendP2p = 0, nRecvP2p = 0;
   nw::DevBuf dSendIdx, dSendDst, dRecvIdx; /* int64 */
   nw::DevBuf dSendPeer, dPeerList;         /* int32 */
   nw::DevBuf dRecvIsGhost;                 /* uint8: receive entry is a ghost of mine */
 };
 
+struct nw_ls_shared;
 struct nw_mesh
 {
   nw_ctx* ctx = nullptr;
@@ -185,7 +203,8 @@ struct nw_mesh
   std::vector<std::unique_ptr<nw_field_t>> fields;
   std::map<std::string, int> fieldByName;
   nw_node_halo halo;
-  std::map<int64_t, int32_t> ownedNodeOfHid; /* own row id -> local node */
+  /* own row id - iLowerNode -> local node, -1 = none (multi-rank meshes only) */
+  std::vector<int32_t> ownedNodeOfHid;
   /* GeometryInteriorAlg tables of the last element block of each topology
    * (hex8, quad4, tet4, wed6, pyr5; cached: a moving mesh calls every step
    * with the same connectivity) */
@@ -199,28 +218,43 @@ struct nw_mesh
   /* node-kernel selector: locally owned and not a periodic slave */
   std::vector<uint8_t> nodeKernelActive;
   int64_t planBytes = 0;
+  /* finalized graphs / plans of this mesh's linear systems (see nw_ls_shared) */
+  std::vector<std::shared_ptr<nw_ls_shared>> lsCache;
 };
 
 enum nw_ls_state { NW_LS_UNSET = 0, NW_LS_LAZY_ZERO = 1, NW_LS_ACCUM = 2 };
 
+/* graph + reduction plan of a linear system.  Systems of one mesh with the same
+ * dofs per node and the same skipped rows (continuity, TKE, SDR, the UVW
+ * momentum system: all node-row graphs of the same edge list) share one
+ * instance, host and device side -- HypreLinearSystem builds the same graph
+ * once per equation system (src/HypreLinearSystem.C:412-478). */
+struct nw_ls_shared
+{
+  int numDof = 1;
+  std::vector<int64_t> skipped; /* sorted, unique: the cache key */
+  nw::Graph g;
+  nw::LsPlan lp;
+  bool uploaded = false;
+  nw::DevBuf dLsTiles, dEntInfo, dEntRhsRow, dHe, dWarp, dRuns;
+  nw::DevBuf dUncovered, dUncoveredPeriodic, dRowPtr;
+  nw::DevBuf dPeriodicRows;
+};
+
 struct nw_linsys
 {
   nw_mesh* mesh = nullptr;
+  std::shared_ptr<nw_ls_shared> sh;
   int kind = NW_LINSYS_HYPRE;
   int numDof = 1;
   int nRhs = 1;
   bool graphBuilt = false, finalized = false;
   std::vector<int64_t> skipped;
-  nw::Graph g;
-  nw::LsPlan lp;
   nw::LsPlanDev dev;
   int mode = NW_SCATTER_SEGMENTED;
   int state = NW_LS_UNSET;
 
-  nw::DevBuf dLsTiles, dEntInfo, dEntRhsRow, dHe, dWarp, dRuns;
   nw::DevBuf dValues, dRhs;
-  nw::DevBuf dUncovered, dUncoveredPeriodic, dRowPtr;
-  nw::DevBuf dPeriodicRows;
   /* atomic variant maps (lazy) */
   bool atomicBuilt = false;
   nw::DevBuf dASlots, dARhsRows;

@@ -2403,23 +2403,30 @@ p2p_signal(const P2pDev& pp)
 }
 
 /* start of a pull kernel: every peer's push of this epoch has landed in the
- * own window.  Bounded spin: a peer that never arrives sets the error word
- * instead of hanging the GPU. */
-__device__ __forceinline__ void
+ * own window.  Bounded spin (pp.timeoutCycles): a peer that never arrives sets
+ * the error word and the WHOLE kernel returns without touching the window --
+ * nothing stale is ever accumulated; the host reports NW_ERR_COMM at its next
+ * synchronisation point (p2p_check_error).  Returns false on timeout (or when
+ * an earlier exchange of this context already failed). */
+__device__ __forceinline__ bool
 p2p_wait(const P2pDev& pp)
 {
+  int bad = 0;
   if ((int)threadIdx.x < pp.nPeers) {
     const unsigned long long* f = pp.myFlags + pp.peers[threadIdx.x];
     const long long t0 = clock64();
     while (ld_acquire_sys(f) < pp.epoch) {
-      if (clock64() - t0 > 6000000000ll) { /* ~3 s */
+      if (clock64() - t0 > pp.timeoutCycles) {
         atomicExch(pp.sync + 1, 1u);
+        bad = 1;
         break;
       }
       __nanosleep(64);
     }
   }
-  __syncthreads();
+  if (threadIdx.x == 0 && *(volatile unsigned*)(pp.sync + 1) != 0u)
+    bad = 1; /* the data of a failed exchange is never consumed later either */
+  return __syncthreads_or(bad) == 0;
 }
 
 /* nodal push: entry g of the concatenated send list, component c ->
@@ -2446,7 +2453,8 @@ __global__ void __launch_bounds__(256) p2p_pull_nodal_kernel(
   double* base, int64_t stride, int nc, const int64_t* __restrict__ recvIdx,
   int64_t n, const P2pDev pp)
 {
-  p2p_wait(pp);
+  if (!p2p_wait(pp))
+    return;
   const double* win = pp.myWindow + pp.winOff;
   const int64_t total = n * nc;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -2464,7 +2472,8 @@ __global__ void __launch_bounds__(256) p2p_pull_assign_nodal_kernel(
   double* base, int64_t stride, int nc, const int64_t* __restrict__ recvIdx,
   const unsigned char* __restrict__ recvIsGhost, int64_t n, const P2pDev pp)
 {
-  p2p_wait(pp);
+  if (!p2p_wait(pp))
+    return;
   const double* win = pp.myWindow + pp.winOff;
   const int64_t total = n * nc;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -2502,8 +2511,12 @@ __global__ void __launch_bounds__(256) p2p_pull_accumulate_kernel(
   const int64_t* __restrict__ pos, int64_t nDst, double* dst,
   int64_t dstCompStride, const P2pDev pp, int wait)
 {
-  if (wait)
-    p2p_wait(pp);
+  if (wait) {
+    if (!p2p_wait(pp))
+      return;
+  } else if (*(volatile unsigned*)(pp.sync + 1) != 0u) {
+    return; /* the launch that waited for this epoch timed out */
+  }
   const double* buf = pp.myWindow + pp.winOff + bufOff;
   const int64_t total = nDst * nc;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;

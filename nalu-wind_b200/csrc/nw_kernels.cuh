@@ -241,11 +241,14 @@ struct P2pDev
   double* myWindow = nullptr;
   const unsigned long long* myFlags = nullptr;
   unsigned* sync = nullptr; /* [0] block counter, [1] error word */
-  const int32_t* peers = nullptr; /* ranks taking part in this exchange */
+  /* ranks signalled / waited for: the union of the neighbours of every
+   * exchange object of the context (see p2p_register_peers) */
+  const int32_t* peers = nullptr;
   int nPeers = 0;
   int myRank = 0;
   int64_t winOff = 0; /* parity * winDoubles */
   unsigned long long epoch = 0;
+  long long timeoutCycles = 40000000000ll; /* bounded spin of the pull kernels */
 };
 cudaError_t launch_p2p_push_nodal(
   const double* base, int64_t stride, int nc, const int64_t* sendIdx,

@@ -8,6 +8,9 @@
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace nw {
 
@@ -19,6 +22,23 @@ fail(const std::string& m)
   throw std::runtime_error(m);
 }
 
+/* NW_PLAN_TIMING=1: wall-clock of the plan-builder stages on stderr */
+struct StageTimer
+{
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  StageTimer() : on(std::getenv("NW_PLAN_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* what)
+  {
+    if (!on)
+      return;
+    const auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[nw plan] %-28s %8.3f s\n", what,
+                 std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 inline int64_t
 even_up(int64_t v)
 {
@@ -27,15 +47,94 @@ even_up(int64_t v)
 
 /* ---- recursive coordinate bisection over row groups ---- */
 
-struct RcbTask
-{
-  int64_t begin, end;
-  int64_t leaves;
-};
-
 /* items: group ids; pts: representative coordinates [G][3].  Emits leaves in
  * depth-first (left first) order, which keeps spatially adjacent tiles close
  * in launch order (L2 reuse of halo nodes). */
+/* one bisection step of items[begin, end) into `leaves` leaves; returns the
+ * split position (the same arithmetic rule rcb_leaf_bounds uses) */
+int64_t
+rcb_split(
+  std::vector<int32_t>& items,
+  const std::vector<double>& pts,
+  int64_t begin,
+  int64_t end,
+  int64_t leaves)
+{
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int64_t i = begin; i < end; ++i) {
+    const double* p = &pts[size_t(items[i]) * 3];
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = std::min(lo[d], p[d]);
+      hi[d] = std::max(hi[d], p[d]);
+    }
+  }
+  int dim = 0;
+  for (int d = 1; d < 3; ++d)
+    if (hi[d] - lo[d] > hi[dim] - lo[dim])
+      dim = d;
+  const int d1 = (dim + 1) % 3, d2 = (dim + 2) % 3;
+  const int64_t l1 = leaves / 2;
+  const int64_t mid = begin + (end - begin) * l1 / leaves;
+  auto cmp = [&](int32_t a, int32_t b) {
+    const double* pa = &pts[size_t(a) * 3];
+    const double* pb = &pts[size_t(b) * 3];
+    if (pa[dim] != pb[dim])
+      return pa[dim] < pb[dim];
+    if (pa[d1] != pb[d1])
+      return pa[d1] < pb[d1];
+    if (pa[d2] != pb[d2])
+      return pa[d2] < pb[d2];
+    return a < b;
+  };
+  std::nth_element(
+    items.begin() + begin, items.begin() + mid, items.begin() + end, cmp);
+  return mid;
+}
+
+void
+rcb_part(
+  std::vector<int32_t>& items,
+  const std::vector<double>& pts,
+  int64_t begin,
+  int64_t end,
+  int64_t leaves)
+{
+  if (leaves <= 1 || end - begin <= 1)
+    return;
+  const int64_t mid = rcb_split(items, pts, begin, end, leaves);
+  const int64_t l1 = leaves / 2;
+  /* the two halves are independent: sub-trees above a size threshold become
+   * OpenMP tasks (the result does not depend on the execution order) */
+  if (end - begin > 200000) {
+#pragma omp task shared(items, pts)
+    rcb_part(items, pts, begin, mid, l1);
+#pragma omp task shared(items, pts)
+    rcb_part(items, pts, mid, end, leaves - l1);
+#pragma omp taskwait
+  } else {
+    rcb_part(items, pts, begin, mid, l1);
+    rcb_part(items, pts, mid, end, leaves - l1);
+  }
+}
+
+/* the leaf boundaries follow from the split rule alone (no coordinates) */
+void
+rcb_leaf_bounds(
+  int64_t begin, int64_t end, int64_t leaves, std::vector<int64_t>& leafBegin)
+{
+  if (leaves <= 1 || end - begin <= 1) {
+    leafBegin.push_back(begin);
+    return;
+  }
+  const int64_t l1 = leaves / 2;
+  const int64_t mid = begin + (end - begin) * l1 / leaves;
+  rcb_leaf_bounds(begin, mid, l1, leafBegin);
+  rcb_leaf_bounds(mid, end, leaves - l1, leafBegin);
+}
+
+/* items: group ids; pts: representative coordinates [G][3].  Leaves come out
+ * in depth-first (left first) order, which keeps spatially adjacent tiles
+ * close in launch order (L2 reuse of halo nodes). */
 void
 rcb(
   std::vector<int32_t>& items,
@@ -44,47 +143,10 @@ rcb(
   std::vector<int64_t>& leafBegin)
 {
   leafBegin.clear();
-  std::vector<RcbTask> stack;
-  stack.push_back({0, (int64_t)items.size(), nLeaves});
-  while (!stack.empty()) {
-    RcbTask t = stack.back();
-    stack.pop_back();
-    if (t.leaves <= 1 || t.end - t.begin <= 1) {
-      leafBegin.push_back(t.begin);
-      continue;
-    }
-    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-    for (int64_t i = t.begin; i < t.end; ++i) {
-      const double* p = &pts[size_t(items[i]) * 3];
-      for (int d = 0; d < 3; ++d) {
-        lo[d] = std::min(lo[d], p[d]);
-        hi[d] = std::max(hi[d], p[d]);
-      }
-    }
-    int dim = 0;
-    for (int d = 1; d < 3; ++d)
-      if (hi[d] - lo[d] > hi[dim] - lo[dim])
-        dim = d;
-    const int d1 = (dim + 1) % 3, d2 = (dim + 2) % 3;
-    const int64_t l1 = t.leaves / 2;
-    const int64_t mid = t.begin + (t.end - t.begin) * l1 / t.leaves;
-    auto cmp = [&](int32_t a, int32_t b) {
-      const double* pa = &pts[size_t(a) * 3];
-      const double* pb = &pts[size_t(b) * 3];
-      if (pa[dim] != pb[dim])
-        return pa[dim] < pb[dim];
-      if (pa[d1] != pb[d1])
-        return pa[d1] < pb[d1];
-      if (pa[d2] != pb[d2])
-        return pa[d2] < pb[d2];
-      return a < b;
-    };
-    std::nth_element(
-      items.begin() + t.begin, items.begin() + mid, items.begin() + t.end, cmp);
-    /* right pushed first so the left half is processed (emitted) first */
-    stack.push_back({mid, t.end, t.leaves - l1});
-    stack.push_back({t.begin, mid, l1});
-  }
+#pragma omp parallel
+#pragma omp single
+  rcb_part(items, pts, 0, (int64_t)items.size(), nLeaves);
+  rcb_leaf_bounds(0, (int64_t)items.size(), nLeaves, leafBegin);
   leafBegin.push_back((int64_t)items.size());
 }
 
@@ -155,6 +217,7 @@ build_mesh_plan(const MeshInput& in, MeshPlan& mp)
 
   const int64_t N = in.nNodes, E = in.nEdges;
   const int nd = in.ndim;
+  StageTimer tm;
   mp = MeshPlan();
   mp.ndim = nd;
   mp.rank = in.rank;
@@ -212,12 +275,14 @@ build_mesh_plan(const MeshInput& in, MeshPlan& mp)
       pts[size_t(g) * 3 + d] = in.coords[size_t(rep) * nd + d];
   }
 
+  tm.mark("mesh: copy + row groups");
   /* ---- tiles ---- */
   std::vector<int32_t> items(G);
   std::iota(items.begin(), items.end(), 0);
   const int64_t nLeaves = std::max<int64_t>(1, (N + T - 1) / T);
   std::vector<int64_t> leafBegin;
   rcb(items, pts, nLeaves, leafBegin);
+  tm.mark("mesh: rcb");
   const int64_t nTiles = (int64_t)leafBegin.size() - 1;
   mp.nTiles = nTiles;
   mp.tiles.assign(nTiles, TileHdr());
@@ -257,6 +322,7 @@ build_mesh_plan(const MeshInput& in, MeshPlan& mp)
   for (int64_t n = 0; n < N; ++n)
     mp.nodeOfSlot[mp.slotOfNode[n]] = (int32_t)n;
 
+  tm.mark("mesh: tile numbering");
   /* ---- tile-edges ---- */
   std::vector<int64_t> cnt(nTiles + 1, 0);
   for (int64_t e = 0; e < E; ++e) {
@@ -296,6 +362,7 @@ build_mesh_plan(const MeshInput& in, MeshPlan& mp)
     }
   }
 
+  tm.mark("mesh: tile-edge bins");
   std::vector<std::vector<int32_t>> haloPer(nTiles);
   std::vector<std::vector<uint32_t>> hePer(nTiles);
   std::string err;
@@ -375,6 +442,7 @@ build_mesh_plan(const MeshInput& in, MeshPlan& mp)
   if (!err.empty())
     fail(err);
 
+  tm.mark("mesh: per-tile lists");
   /* flatten halo + half-edge lists */
   mp.warpSplitNode.assign(size_t(nTiles) * (kMaxWarps + 1), 0);
   int64_t hp = 0, qp = 0;
@@ -418,6 +486,7 @@ build_mesh_plan(const MeshInput& in, MeshPlan& mp)
   }
   mp.heNodeEll.resize(mp.heNodeEll.size() + 32, 0u);
   mp.sliceOffNode.push_back(0);
+  tm.mark("mesh: flatten + sliced ELL");
 }
 
 /* ------------------------------------------------------------------ */
@@ -444,6 +513,7 @@ build_graph(
   const std::vector<int64_t>& skippedIn,
   Graph& g)
 {
+  StageTimer tm;
   g = Graph();
   if (kind == NW_LINSYS_HYPRE_UVW)
     numDof = 1; /* HypreUVWLinearSystem builds its base with numDof = 1
@@ -521,6 +591,7 @@ build_graph(
     ucount[u] = std::unique(b, e) - b;
   }
 
+  tm.mark("graph: adjacency");
   /* ---- owned rows: src/HypreLinearSystem.C:999-1066 ---- */
   g.numRowsOwned = nOwnedNodes * numDof;
   g.rowStartOwned.assign(g.numRowsOwned + 1, 0);
@@ -594,6 +665,7 @@ build_graph(
       g.rowStartShared[i + 1] - g.rowStartShared[i], g.rowIndicesShared[i],
       nOwnedNodes + sharedNodeOfRow[i]);
 
+  tm.mark("graph: rows + cols");
   /* ---- edge -> slot map ---- */
   const int nb = (kind == NW_LINSYS_HYPRE_UVW) ? 2 : g.block;
   g.block = nb;
@@ -646,6 +718,7 @@ build_graph(
   }
   if (!err.empty())
     fail("nw_linsys_finalize: " + err);
+  tm.mark("graph: edge slots");
 }
 
 /* ------------------------------------------------------------------ */
@@ -655,6 +728,7 @@ build_graph(
 void
 build_ls_plan(const MeshPlan& mp, const Graph& g, LsPlan& lp)
 {
+  StageTimer tm;
   lp = LsPlan();
   if (g.numDof != 1) {
     lp.usable = false;
@@ -799,6 +873,7 @@ build_ls_plan(const MeshPlan& mp, const Graph& g, LsPlan& lp)
     return;
   }
 
+  tm.mark("lsplan: per-tile lists");
   lp.warpSplit.assign(size_t(nTiles) * (kMaxWarps + 1), 0);
   int64_t ep = 0, hp = 0, rp = 0;
   for (int64_t t = 0; t < nTiles; ++t) {
@@ -861,6 +936,7 @@ build_ls_plan(const MeshPlan& mp, const Graph& g, LsPlan& lp)
   for (int64_t r = 0; r < g.numRowsLocal(); ++r)
     if (!covered[r])
       lp.uncoveredRows.push_back((int32_t)r);
+  tm.mark("lsplan: flatten + sliced ELL");
 }
 
 } // namespace nw

@@ -78,6 +78,29 @@ def state(coords, gid, lengths, dt=0.5, gamma1=1.5, periodic_gid=None):
     return f
 
 
+def state_chunked(coords, gid, lengths, dt=0.5, gamma1=1.5, periodic_gid=None,
+                  threads=None, chunk=1 << 20):
+    """state() evaluated on node chunks in a thread pool (numpy releases the
+    GIL inside its loops): every field is a pure function of the node, so the
+    result is identical to state(); used by bench.py for the 10^7..10^8-node
+    partitions of the 512^3 configuration."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    n = len(coords)
+    if n <= chunk:
+        return state(coords, gid, lengths, dt, gamma1, periodic_gid)
+    threads = threads or min(16, os.cpu_count() or 1)
+    cuts = list(range(0, n, chunk)) + [n]
+
+    def part(i):
+        a, b = cuts[i], cuts[i + 1]
+        return state(coords[a:b], gid[a:b], lengths, dt, gamma1,
+                     None if periodic_gid is None else periodic_gid[a:b])
+    with ThreadPoolExecutor(threads) as ex:
+        parts = list(ex.map(part, range(len(cuts) - 1)))
+    return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+
+
 NODE_FIELDS = {
     "velocity": 3, "pressure": 1, "density": 1, "viscosity": 1,
     "momentum_diag": 1, "dpdx": 3, "dudx": 9, "turbulent_ke": 1, "dkdx": 3,

@@ -9,6 +9,8 @@ topology (elems_tet / elems_pyr / elems_wed / elems_hex / elems_qua).  Run in th
 
   multiElemTypeCylinder.g   TETRA4 / HEX8 / WEDGE6 / PYRAMID5   (BASELINE configs[4])
   hybrid.g.8.0              tetra / pyramid / hex, rank 0 of 8   (BASELINE configs[4])
+  hybrid.g.8.0 .. .7        all eight parts of the reference's own decomposition,
+                            with node / edge ownership (multi-rank parity)
   airfoilRANSEdgeTrilinos.rst  2-D QUAD4, 49 536 nodes            (BASELINE configs[3])
 """
 import os
@@ -63,7 +65,66 @@ def convert(fname, out, keep_elems=False):
           "%.0f kB" % (os.path.getsize(os.path.join(HERE, out)) / 1e3))
 
 
+def read_part(fname):
+    """(coords, gid, local unique edges in first-visit order with L = lower
+    global id) of one Exodus part file"""
+    f = netcdf_file(os.path.join(REF, "reg_tests", "mesh", fname), "r", mmap=False)
+    ndim = int(f.dimensions["num_dim"])
+    coords = np.stack([np.array(f.variables["coord" + "xyz"[d]][:], dtype=np.float64)
+                       for d in range(ndim)], axis=1)
+    gid = np.array(f.variables["node_num_map"][:], dtype=np.int64)
+    pairs = []
+    for b in range(1, int(f.dimensions["num_el_blk"]) + 1):
+        if "connect%d" % b not in f.variables:
+            continue  # this part holds no element of the block
+        v = f.variables["connect%d" % b]
+        conn = np.array(v[:], dtype=np.int64) - 1
+        kind = v.elem_type.decode().lower()[:3]
+        for a, c in EDGES[kind]:
+            pairs.append(np.stack([conn[:, a], conn[:, c]], axis=1))
+    p = np.concatenate(pairs)
+    lo, hi = np.minimum(p[:, 0], p[:, 1]), np.maximum(p[:, 0], p[:, 1])
+    _, first = np.unique(lo * len(coords) + hi, return_index=True)
+    first.sort()
+    e = np.stack([lo[first], hi[first]], axis=1)
+    swap = gid[e[:, 0]] > gid[e[:, 1]]
+    e[swap] = e[swap][:, ::-1]
+    return coords, gid, e.astype(np.int32)
+
+
+def convert_decomposition(stem, nparts, out):
+    """All parts of a pre-split Exodus mesh (the decomposition the reference's
+    regression test runs on, reg_tests/mesh/<stem>.<nparts>.<rank>): per part
+    the node coordinates, global ids, local edges, and -- recorded explicitly
+    -- the STK ownership of shared nodes and edges: the lowest rank that holds
+    the entity (every element lives in exactly one part; a node / edge on a
+    partition interface appears in several)."""
+    parts = [read_part("%s.%d.%d" % (stem, nparts, r)) for r in range(nparts)]
+    node_owner, edge_owner = {}, {}
+    for r, (coords, gid, e) in enumerate(parts):
+        for g in gid.tolist():
+            node_owner.setdefault(g, r)
+        for a, c in zip(gid[e[:, 0]].tolist(), gid[e[:, 1]].tolist()):
+            edge_owner.setdefault((a, c), r)
+    data = {"nparts": np.int64(nparts)}
+    for r, (coords, gid, e) in enumerate(parts):
+        data["coords_%d" % r] = coords
+        data["gid_%d" % r] = gid
+        data["edges_%d" % r] = e
+        data["node_owner_%d" % r] = np.array(
+            [node_owner[g] for g in gid.tolist()], dtype=np.int32)
+        data["edge_owner_%d" % r] = np.array(
+            [edge_owner[(a, c)] for a, c in zip(gid[e[:, 0]].tolist(),
+                                                gid[e[:, 1]].tolist())], dtype=np.int32)
+    np.savez_compressed(os.path.join(HERE, out), **data)
+    nn = len(node_owner)
+    print(out, "parts", nparts, "global nodes", nn, "global edges", len(edge_owner),
+          "shared node copies", sum(len(p[1]) for p in parts) - nn,
+          "%.0f kB" % (os.path.getsize(os.path.join(HERE, out)) / 1e3))
+
+
 def main():
+    convert_decomposition("hybrid.g", 8, "mesh_hybrid_g_8_parts.npz")
     convert("multiElemTypeCylinder.g", "mesh_multiElemTypeCylinder.npz", keep_elems=True)
     convert("hybrid.g.8.0", "mesh_hybrid_g_8_0.npz", keep_elems=True)
     convert("airfoilRANSEdgeTrilinos.rst", "mesh_airfoilRANSEdge.npz", keep_elems=True)

@@ -9,7 +9,15 @@ nodes over NCCL (nw_linsys_load_complete, nw_nodal_grad_edge), and the owned
 rows of every rank are compared entry by entry (rel. 1e-12, cancellation-aware
 scale) with the CPU oracle's serial assembly of the whole mesh.  Test
 infrastructure: the oracle is only the checker.  tests/test_gpu_parity.py
-launches this when two GPUs are visible."""
+launches this when two GPUs are visible.
+
+  NW_MGPU_MESH=hybrid8  (world size 8): the reference's own decomposition
+      reg_tests/mesh/hybrid.g.8.0-7 (tet / pyramid / hex, shared nodes with up
+      to 4 sharers, neighbour sets that differ per exchange object) against the
+      serial oracle on the union mesh.
+  NW_MGPU_DELAY=1: afterwards, rank 1 arrives late (longer than
+      NW_P2P_TIMEOUT_S) at one nodal sum; the waiting ranks must report
+      NW_ERR_COMM and leave the field untouched instead of adding stale data."""
 import json
 import os
 import sys
@@ -25,6 +33,40 @@ for p in (os.path.dirname(HERE), os.path.join(os.path.dirname(HERE), "oracle"), 
 
 import oracle_py as orc  # noqa: E402
 import parity_util as pu  # noqa: E402
+
+
+def delay_test(P, ctx, mesh, rank, b):
+    """a neighbour that is late by more than the timeout must
+    produce NW_ERR_COMM, never a silent add of stale window contents.  Rank 1
+    sleeps before its push; every rank that waits for it must (a) get the error
+    at its next synchronisation and (b) find the field it exchanged equal to
+    its own partial sums (nothing accumulated)."""
+    import time
+    mesh.register("delay_probe", P.NW_NODE, 1)
+    mine = np.full(b.n_nodes, float(rank + 1))
+    mesh.upload("delay_probe", mine)
+    ctx.sync()
+    dist.barrier()
+    if rank == 1:
+        time.sleep(float(os.environ.get("NW_P2P_TIMEOUT_S", "2")) + 2.0)
+    err = None
+    try:
+        mesh.parallel_sum("delay_probe")
+        ctx.sync()
+    except P.NwError as e:
+        err = str(e)
+    got = None
+    try:
+        got = mesh.download("delay_probe")
+    except P.NwError as e:
+        err = err or str(e)
+    if rank == 1 or err is None:
+        # the late rank finds its peers' pushes waiting; a rank whose flag set
+        # does not contain rank 1 is not affected
+        ok = True
+    else:
+        ok = "did not arrive" in err and (got is None or np.array_equal(got, mine))
+    return {"rank": rank, "error": err, "ok": bool(ok)}
 
 
 def main():
@@ -45,9 +87,16 @@ def main():
     dist.broadcast(uid, 0)
     ctx.comm_init(bytes(uid.cpu().tolist()), world, rank)
 
-    kw = dict(dims=dims, lengths=lengths, periodic=(periodic, periodic))
-    case = pu.Case(nranks=world, rank=rank, **kw)
-    full = pu.Case(**kw)
+    which = os.environ.get("NW_MGPU_MESH", "box")
+    if which == "hybrid8":
+        assert world == 8, "the hybrid.g.8 decomposition needs 8 ranks"
+        case = pu.DecomposedRealMesh(rank)
+        full = pu.DecomposedRealMesh(None)
+        dims, periodic = "hybrid.g.8", False
+    else:
+        kw = dict(dims=dims, lengths=lengths, periodic=(periodic, periodic))
+        case = pu.Case(nranks=world, rank=rank, **kw)
+        full = pu.Case(**kw)
     b = case.box
     mesh = b.make_mesh(ctx, tile_nodes=48)
     pu.upload_state(P, mesh, case)
@@ -69,6 +118,7 @@ def main():
     fmdot = full.oracle_mdot()
     fpec = full.oracle_pecfac(orc.peclet("classic", 1.0))
     res = {}
+    plain = {}  # worst |got - ref| / |ref| (no cancellation-aware scale)
 
     def check_system(name, ls, oref, nrhs):
         vals, rhs = ls.values()
@@ -87,7 +137,7 @@ def main():
         vv = np.concatenate([vals[:s.num_nonzeros_owned],
                              vals[s.num_nonzeros_owned + s.num_nonzeros_shared:]])
         periodic_rows = set(gr["periodic_rows"].tolist())
-        worst, n = 0.0, 0
+        worst, n, wplain = 0.0, 0, 0.0
         seen = set()
         for r_, c_, v_ in zip(rows_arr, cols_arr, vv):
             if int(r_) in periodic_rows:
@@ -97,6 +147,8 @@ def main():
             seen.add(key)
             worst = max(worst, abs(v_ - fdict[key]) /
                         (pu.TOL * max(adict[key], abs(fdict[key]), 1e-300)))
+            if fdict[key] != 0.0:
+                wplain = max(wplain, abs(v_ - fdict[key]) / abs(fdict[key]))
             n += 1
         mine_ser = {ser(s.i_lower + i) for i in range(s.num_rows_owned)
                     if s.i_lower + i not in periodic_rows}
@@ -110,7 +162,10 @@ def main():
             for d in range(nrhs):
                 worst = max(worst, abs(rhs[d, i] - fr[d, sr]) /
                             (pu.TOL * max(fra[d, sr], abs(fr[d, sr]), 1e-300)))
+                if fr[d, sr] != 0.0:
+                    wplain = max(wplain, abs(rhs[d, i] - fr[d, sr]) / abs(fr[d, sr]))
         res[name] = worst
+        plain[name] = wplain
 
     # mdot on this rank's edges must equal the serial value of the same edge
     mesh.mdot_edge(1.0, 1.0)
@@ -149,6 +204,7 @@ def main():
     ls.loadComplete()
     check_system("momentum_uvw", ls,
                  pu.oracle_momentum(full, gfull, fmdot, fpec, uvw=True), 3)
+    linsys_transport = ls.halo_transport()
     ls.close()
 
     # nodal gradients incl. the shared-node sum over NCCL
@@ -183,15 +239,39 @@ def main():
         got = mesh.download(name).reshape(b.n_nodes, nc)
         res["copy_" + name] = 0.0 if np.array_equal(got, loc) else float("inf")
 
+    peer_memory = ctx.peer_memory()
+    nodal_transport = mesh.halo_transport()
+    delay = None
+    if os.environ.get("NW_MGPU_DELAY") == "1" and ctx.peer_memory():
+        delay = delay_test(P, ctx, mesh, rank, b)
+        ctx = None  # the context is unusable after a communication error
+
     allres = [None] * world
     dist.all_gather_object(allres, res)
+    allplain = [None] * world
+    dist.all_gather_object(allplain, plain)
+    alldelay = [None] * world
+    dist.all_gather_object(alldelay, delay)
     if rank == 0:
         worst = max(max(r.values()) for r in allres)
-        print(json.dumps({"world": world, "dims": dims, "periodic": periodic,
-                          "peer_memory": ctx.peer_memory(),
-                          "nodal_transport": mesh.halo_transport(),
-                          "worst_scaled_error": worst, "per_rank": allres}))
+        out = {"world": world, "mesh": which, "dims": dims, "periodic": periodic,
+               "peer_memory": peer_memory, "nodal_transport": nodal_transport,
+               "linsys_transport": linsys_transport,
+               "tolerance": "scaled: |got-ref| <= 1e-12 max(|ref|, sum |contributions|)",
+               "worst_scaled_error": worst,
+               "worst_plain_relative_error": {
+                   k: max(p_[k] for p_ in allplain) for k in allplain[0]},
+               "per_rank": allres}
+        if delay is not None:
+            out["delayed_rank_test"] = alldelay
+        print(json.dumps(out))
         assert worst < 1.0, allres
+        if delay is not None:
+            assert all(d["ok"] for d in alldelay), alldelay
+            assert any(d["error"] for d in alldelay if d["rank"] != 1), alldelay
+    if ctx is None:
+        dist.destroy_process_group()
+        os._exit(0)  # handles of a failed context are not torn down in order
     mesh.close()
     dist.destroy_process_group()
 

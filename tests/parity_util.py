@@ -716,6 +716,101 @@ class RealMeshCase:
     oracle_pecfac = Case.oracle_pecfac
 
 
+class DecomposedRealMesh:
+    """The reference's own 8-way decomposition of hybrid.g
+    (reg_tests/mesh/hybrid.g.8.0 .. .7, fixture mesh_hybrid_g_8_parts.npz):
+    rank=None is the serial mesh (union of the parts, nodes in ascending global
+    id, every edge once); rank=r is part r as STK would hold it -- all nodes of
+    the part's elements, the edges the rank OWNS (lowest holding rank), node
+    ownership = lowest sharing rank, hypre row ids by Realm::set_hypre_global_id
+    (src/Realm.C:3587-3679: a rank's owned nodes, sorted by global id, numbered
+    from the rank's offset; shared copies carry the owner's id).  Geometry and
+    state are pure functions of the global ids, so every rank sees what the
+    serial mesh sees.  Attributes as Case."""
+
+    def __init__(self, rank=None, name="hybrid_g_8_parts", seed=20261017):
+        P = pkg()
+        synth = __import__("nalu_wind_b200.synth", fromlist=["state"])
+        m = load_reference_mesh(name)
+        np_ = int(m["nparts"])
+        self.nparts = np_
+        # serial union: nodes by ascending global id
+        gids = np.unique(np.concatenate([m["gid_%d" % r] for r in range(np_)]))
+        xyz = np.zeros((len(gids), 3))
+        owner = np.zeros(len(gids), dtype=np.int32)
+        for r in range(np_ - 1, -1, -1):  # the lowest rank writes last (same values)
+            at = np.searchsorted(gids, m["gid_%d" % r])
+            xyz[at] = m["coords_%d" % r]
+            owner[at] = m["node_owner_%d" % r]
+        # hypre ids: per owner, owned nodes in ascending global id
+        counts = np.bincount(owner, minlength=np_)
+        offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        hyp = np.zeros(len(gids), dtype=np.int64)
+        for r in range(np_):
+            mine = np.nonzero(owner == r)[0]  # ascending gid already
+            hyp[mine] = offsets[r] + np.arange(len(mine))
+        # serial edge list: the owned edges of every rank, rank by rank
+        eg = []
+        for r in range(np_):
+            e = m["edges_%d" % r][m["edge_owner_%d" % r] == r]
+            g = m["gid_%d" % r]
+            eg.append(np.stack([g[e[:, 0]], g[e[:, 1]]], axis=1))
+        eg_all = np.concatenate(eg)
+        key_all = eg_all[:, 0] * (gids[-1] + 1) + eg_all[:, 1]
+        assert len(np.unique(key_all)) == len(key_all)
+        ser_edges = np.stack([np.searchsorted(gids, eg_all[:, 0]),
+                              np.searchsorted(gids, eg_all[:, 1])], axis=1)
+        rng = np.random.default_rng(seed)
+        dx = xyz[ser_edges[:, 1]] - xyz[ser_edges[:, 0]]
+        ln = np.linalg.norm(dx, axis=1, keepdims=True)
+        ser_area = np.ascontiguousarray(
+            0.3 * ln * dx + 0.05 * ln * ln * rng.standard_normal(dx.shape))
+        ser_vol = (0.5 + rng.random(len(gids))) * float(np.mean(ln)) ** 3
+        lo, hi = xyz.min(0), xyz.max(0)
+        b = _Obj()
+        b.periodic = (False, False)
+        if rank is None:
+            sel_n = np.arange(len(gids))
+            b.edges = np.ascontiguousarray(ser_edges.astype(np.int32))
+            b.area = ser_area
+            b.rank, b.nranks = 0, 1
+            b.hid = np.arange(len(gids), dtype=np.int64)  # serial numbering
+            b.offsets = np.array([0, len(gids)], dtype=np.int64)
+        else:
+            g = m["gid_%d" % rank]
+            sel_n = np.searchsorted(gids, g)
+            own = m["edge_owner_%d" % rank] == rank
+            e = m["edges_%d" % rank][own]
+            b.edges = np.ascontiguousarray(e.astype(np.int32))
+            k = g[e[:, 0]] * (gids[-1] + 1) + g[e[:, 1]]
+            order = np.argsort(key_all)
+            at = order[np.searchsorted(key_all[order], k)]
+            assert np.array_equal(key_all[at], k)
+            b.area = np.ascontiguousarray(ser_area[at])
+            b.rank, b.nranks = rank, np_
+            b.hid = hyp[sel_n]
+            b.offsets = offsets
+        b.n_nodes, b.n_edges = len(sel_n), len(b.edges)
+        b.coords = np.ascontiguousarray(xyz[sel_n])
+        b.gid = gids[sel_n]
+        b.own_hid = b.hid
+        b.owner = owner[sel_n]
+        b.vol = ser_vol[sel_n]
+        b.hypre_of_serial = hyp  # serial node index -> decomposed hypre id
+        b.make_mesh = lambda ctx, tile_nodes=0: P.Mesh(
+            ctx, 3, b.edges, b.hid, b.coords, hypre_offsets=b.offsets,
+            rank=b.rank, nranks=b.nranks, tile_nodes=tile_nodes)
+        self.box = b
+        self.fields = synth.state(b.coords - lo, b.gid, tuple(hi - lo), DT, GAMMA1)
+        self.fields["dual_nodal_volume"] = b.vol
+        self.edges, self.area = b.edges, b.area
+        self.n_nodes, self.n_edges = b.n_nodes, b.n_edges
+
+    oracle_graph = Case.oracle_graph
+    oracle_mdot = Case.oracle_mdot
+    oracle_pecfac = Case.oracle_pecfac
+
+
 class RealMesh2D:
     """the airfoilRANSEdge mesh (2-D QUAD4) with OGrid2D's attributes; geometry
     (edge area vectors, dual volumes) is the true CVFEM dual mesh from the

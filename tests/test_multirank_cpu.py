@@ -1,4 +1,4 @@
-"""world_size-2/3 gloo tests (CPU) of the multi-rank host logic: the shared-row
+"""world_size-2/3/8 gloo tests (CPU) of the multi-rank host logic: the shared-row
 and shared-node exchange lists the library builds, driven with a caller-side
 transport (torch.distributed gloo) exactly as include/nalu_edge_b200.h describes
 for callers without NCCL.  The per-rank numbers come from the CPU oracle; what is
@@ -71,8 +71,12 @@ def _worker(rank, world, port, dims, periodic, q):
         import oracle_py as orc
         import parity_util as pu
         P = pu.pkg()
-        case = pu.Case(dims=dims, nranks=world, rank=rank, periodic=periodic,
-                       lengths=(50.0, 40.0, 30.0))
+        if dims == "hybrid8":
+            # the reference's own 8-way decomposition (reg_tests/mesh/hybrid.g.8.*)
+            case = pu.DecomposedRealMesh(rank)
+        else:
+            case = pu.Case(dims=dims, nranks=world, rank=rank, periodic=periodic,
+                           lengths=(50.0, 40.0, 30.0))
         b = case.box
         ctx = P.Context(-1)
         mesh = b.make_mesh(ctx, tile_nodes=40)
@@ -127,7 +131,10 @@ def _worker(rank, world, port, dims, periodic, q):
             np.add.at(rhs, rr, rgot[peer])
 
         # ---- compare the owned rows with the serial assembly ----
-        full = pu.Case(dims=dims, periodic=periodic, lengths=(50.0, 40.0, 30.0))
+        if dims == "hybrid8":
+            full = pu.DecomposedRealMesh(None)
+        else:
+            full = pu.Case(dims=dims, periodic=periodic, lengths=(50.0, 40.0, 30.0))
         # serial row ids == global ids - 1 resolved; map through gid
         gfull = full.oracle_graph()
         of = pu.oracle_continuity(full, gfull)
@@ -225,6 +232,7 @@ def _worker(rank, world, port, dims, periodic, q):
     (2, (5, 4, 6), (False, False)),
     (3, (4, 5, 9), (False, False)),
     (2, (5, 4, 6), (True, True)),
+    (8, "hybrid8", (False, False)),
 ])
 def test_halo_lists_route_partitioned_assembly(world, dims, periodic):
     ctx = mp.get_context("spawn")
