@@ -55,6 +55,13 @@ int nw_version(void);
  * tools): per-phase cycle counters of the tile kernels, out[8][12], filled
  * only by the NW_PHASE_TIMING build of the library (zeros otherwise). */
 int nw_debug_phase_times(unsigned long long* out, int n, int reset);
+/* Measurement aid (no reference counterpart): while on, nw_linsys_load_complete,
+ * nw_nodal_grad_edge's shared-node sum and nw_field_parallel_sum /
+ * nw_field_copy_owned_to_shared return without exchanging anything, so that a
+ * bench can time the same sweep with and without its halo exchanges
+ * (bench.py north_star.exchange_share).  Results of a multi-rank assembly are
+ * INCOMPLETE while it is on; never set it in a solver. */
+int nw_debug_skip_exchange(nw_ctx* ctx, int on);
 
 /* ------------------------------------------------------------------ */
 /* context                                                             */

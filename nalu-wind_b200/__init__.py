@@ -113,7 +113,7 @@ class LinsysSizes(C.Structure):
 
 # every symbol include/nalu_edge_b200.h declares (checked by the CPU tests)
 ABI_SYMBOLS = [
-    "nw_last_error", "nw_version", "nw_debug_phase_times", "nw_ctx_create", "nw_ctx_destroy",
+    "nw_last_error", "nw_version", "nw_debug_phase_times", "nw_debug_skip_exchange", "nw_ctx_create", "nw_ctx_destroy",
     "nw_ctx_sync", "nw_ctx_stream", "nw_comm_unique_id", "nw_ctx_comm_init",
     "nw_ctx_peer_memory", "nw_ctx_join_comm", "nw_mesh_halo_transport",
     "nw_linsys_halo_transport",
@@ -164,6 +164,7 @@ def lib():
     L.nw_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.nw_ctx_destroy.argtypes = [vp]
     L.nw_ctx_sync.argtypes = [vp]
+    L.nw_debug_skip_exchange.argtypes = [vp, C.c_int]
     L.nw_ctx_stream.restype = vp
     L.nw_ctx_stream.argtypes = [vp]
     L.nw_comm_unique_id.argtypes = [vp]
@@ -276,6 +277,10 @@ class Context:
     def comm_init(self, unique_id_bytes, nranks, rank):
         buf = C.create_string_buffer(bytes(unique_id_bytes), 128)
         _chk(lib().nw_ctx_comm_init(self.h, buf, nranks, rank))
+
+    def debug_skip_exchange(self, on):
+        """measurement aid: halo exchanges become no-ops while on"""
+        _chk(lib().nw_debug_skip_exchange(self.h, 1 if on else 0))
 
     def join_comm(self):
         """order the compute stream after all halo exchanges issued so far"""

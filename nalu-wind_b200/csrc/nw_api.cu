@@ -168,6 +168,15 @@ nw_ctx_sync(nw_ctx* ctx)
   return p2p_check_error(ctx);
 }
 
+extern "C" int
+nw_debug_skip_exchange(nw_ctx* ctx, int on)
+{
+  if (!ctx)
+    return fail(NW_ERR_ARG, "nw_debug_skip_exchange: NULL context");
+  ctx->skipExchange = on != 0;
+  return NW_OK;
+}
+
 extern "C" void*
 nw_ctx_stream(nw_ctx* ctx)
 {

@@ -122,6 +122,7 @@ struct nw_ctx
   cudaStream_t copyStream = nullptr; /* nw_field_stage: H2D beside the compute */
   nw::Comm comm;
   nw_p2p p2p;
+  bool skipExchange = false; /* nw_debug_skip_exchange (measurement aid) */
 };
 
 struct nw_field_t
