@@ -544,8 +544,13 @@ def main():
     # ------------- parity gate of a multi-rank run (before any timing) ------
     gate = None
     if world > 1:
-        gate = parity_gate(P, ctx, args, world, rank, torch, dist)
-        if not gate["ok"]:
+        try:
+            gate = parity_gate(P, ctx, args, world, rank, torch, dist)
+        except P.NwError:
+            raise  # the product refused: that is a failure, not a gate problem
+        except Exception as e:  # a bug in the checker must not pose as a mismatch
+            gate = {"ok": None, "checker_error": str(e)[:300]}
+        if gate["ok"] is False:
             if rank == 0:
                 log("PARITY GATE FAILED, no bench line:", json.dumps(gate))
             dist.destroy_process_group()
