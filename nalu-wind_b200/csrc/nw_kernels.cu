@@ -644,6 +644,9 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
 {
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t bar[2];
+  /* slice offsets of the tile's sliced-ELL list (fetched during the stage: a
+   * global load at the top of phase 2 would sit on the critical path) */
+  __shared__ int32_t s_slice[kMaxTileEnts / 32 + 2];
   NW_PT_BEGIN(P::kPhaseId);
 
   const TileHdr h = mp.tiles[blockIdx.x];
@@ -702,6 +705,12 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
     }
   }
   NW_PT_MARK(); /* 1: TMA issue */
+  {
+    const int nSl = (lh.nEnts + 31) >> 5;
+    const int t = (int)threadIdx.x - 32;
+    if (t >= 0 && t <= nSl)
+      s_slice[t] = __ldg(lp.sliceOff + lh.slicePtr + t);
+  }
   stage_halo_gather<P::NC>(s_node, stride, nc, h, mp.haloNodes);
   NW_PT_MARK(); /* 2: halo gather */
   mbar_wait(&bar[0], 0);
@@ -738,16 +747,19 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
 
   /* ---- phases 2+3, warp by warp: one thread per row reduces the row's
    * half-edges in list order, then the warp copies the staging range of its
-   * 32 rows to the CSR arrays (only a warp-level sync in between) ---- */
+   * 32 rows to the CSR arrays (only a warp-level sync in between).  The walk
+   * is blocked by four list steps: the records, then the edge results they
+   * point to, are loaded before anything of the block is stored, so that the
+   * shared-memory latencies of a block overlap (round-1 phase cycles: this
+   * phase was a chain of dependent 30-cycle loads, 20 % of a CTA's life). ---- */
   {
-    const int32_t* sliceOff = lp.sliceOff + lh.slicePtr;
     const int lane = threadIdx.x & 31;
     for (int row0 = (int)threadIdx.x - lane; row0 < lh.nEnts;
          row0 += blockDim.x) {
       const int row = row0 + lane;
       if (row < lh.nEnts) {
         const int sl = row0 >> 5;
-        const int o0 = __ldg(sliceOff + sl), o1 = __ldg(sliceOff + sl + 1);
+        const int o0 = s_slice[sl], o1 = s_slice[sl + 1];
         const uint32_t* hp = s_ell + o0 + lane;
         const int W = (o1 - o0) >> 5;
         const EntInfo ei = s_ent[row];
@@ -757,21 +769,31 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
 #pragma unroll
         for (int d = 0; d < P::NR; ++d)
           rhs[d] = 0.0;
-        for (int w = 0; w < W; ++w) {
-          const uint32_t hv = hp[w * 32];
-          if (hv & kHeValid) {
-            double dg, off, rr[P::NR];
-            P::contrib(
-              he_side(hv), s_res, L.resStride, (int)he_edge(hv), dg, off, rr);
-            diag += dg;
+        constexpr int kBlk = 4;
+        for (int w0 = 0; w0 < W; w0 += kBlk) {
+          uint32_t hv[kBlk];
 #pragma unroll
-            for (int d = 0; d < P::NR; ++d)
-              rhs[d] += rr[d];
-            double* dst = vrow + he_k(hv);
-            if (hv & kHeDup)
-              off += *dst;
-            *dst = off;
-          }
+          for (int u = 0; u < kBlk; ++u)
+            hv[u] = (w0 + u < W) ? hp[(w0 + u) * 32] : 0u;
+          double dg[kBlk], off[kBlk], rr[kBlk][P::NR];
+#pragma unroll
+          for (int u = 0; u < kBlk; ++u)
+            if (hv[u] & kHeValid)
+              P::contrib(
+                he_side(hv[u]), s_res, L.resStride, (int)he_edge(hv[u]), dg[u],
+                off[u], rr[u]);
+#pragma unroll
+          for (int u = 0; u < kBlk; ++u)
+            if (hv[u] & kHeValid) {
+              diag += dg[u];
+#pragma unroll
+              for (int d = 0; d < P::NR; ++d)
+                rhs[d] += rr[u][d];
+              double* dst = vrow + he_k(hv[u]);
+              if (hv[u] & kHeDup)
+                off[u] += *dst;
+              *dst = off[u];
+            }
         }
         vrow[ei.diagK] = diag;
         /* value offset of every staged element of this row */
@@ -789,6 +811,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
         const int last = min(row0 + 31, lh.nEnts - 1);
         const EntInfo e0 = s_ent[row0], e1 = s_ent[last];
         const int end = (int)e1.base + (int)e1.nnz;
+#pragma unroll 4
         for (int e = (int)e0.base + lane; e < end; e += 32)
           lp.values[e + s_delta[e]] = s_vals[e];
       }
@@ -1204,7 +1227,7 @@ struct GradOut
  * walks the node's half-edges (sliced-ELL list, TMA-staged), sums in
  * registers in list order and writes the node's gradient once, coalesced. */
 template <int D1, int ND>
-__global__ void __launch_bounds__(kTileThreads) grad_tile_kernel(
+__global__ void __launch_bounds__(kTileThreads, 4) grad_tile_kernel(
   const MeshPlanDev mp,
   const NodeComps phi,
   const double* __restrict__ dualVol,
@@ -1214,6 +1237,7 @@ __global__ void __launch_bounds__(kTileThreads) grad_tile_kernel(
   constexpr int NV = D1 * ND;
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t bar[2];
+  __shared__ int32_t s_slice[kMaxTileEnts / 32 + 2];
   NW_PT_BEGIN(D1 == 1 ? 5 : 6);
   const TileHdr h = mp.tiles[blockIdx.x];
   const int stride = even_up_i(h.nOwnPad + h.nHalo);
@@ -1237,6 +1261,12 @@ __global__ void __launch_bounds__(kTileThreads) grad_tile_kernel(
       tma_load_1d(s_ell, mp.heNodeEll + h.ellPtrNode, bEll, &bar[1]);
   }
   NW_PT_MARK();
+  {
+    const int nSl = (h.nOwn + 31) >> 5;
+    const int t = (int)threadIdx.x - 32;
+    if (t >= 0 && t <= nSl)
+      s_slice[t] = __ldg(mp.sliceOffNode + h.slicePtrNode + t);
+  }
   stage_halo_gather<D1>(s_phi, stride, phi, h, mp.haloNodes);
   NW_PT_MARK();
   mbar_wait(&bar[0], 0);
@@ -1244,42 +1274,59 @@ __global__ void __launch_bounds__(kTileThreads) grad_tile_kernel(
   __syncthreads();
   NW_PT_MARK();
 
-  const int32_t* sliceOff = mp.sliceOffNode + h.slicePtrNode;
   for (int i = threadIdx.x; i < h.nOwn; i += blockDim.x) {
     const int sl = i >> 5;
-    const int o0 = __ldg(sliceOff + sl), o1 = __ldg(sliceOff + sl + 1);
+    const int o0 = s_slice[sl], o1 = s_slice[sl + 1];
     const uint32_t* hp = s_ell + o0 + (i & 31);
     const int W = (o1 - o0) >> 5;
+    /* issued now, needed after the walk */
+    const double vol = __ldg(dualVol + h.node0 + i);
     double acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k)
       acc[k] = 0.0;
-    for (int w = 0; w < W; ++w) {
-      const uint32_t hv = hp[w * 32];
-      if (hv & kHeValid) {
-        const int j = (int)he_edge(hv);
-        const uint32_t v = s_lr[j];
-        const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
-        /* L node: += a_j phiIp ; R node: -= a_j phiIp (NodalGradEdgeAlg.C:100-106) */
-        const double sgn = he_side(hv) ? -1.0 : 1.0;
-        double av[ND];
+    /* blocked by four list steps: records, then (L,R) pairs, then areas and
+     * phi are loaded for the whole block before the sums (same order of
+     * additions as the plain walk); the block is sized so that four CTAs stay
+     * resident per SM */
+    constexpr int kBlk = D1 == 1 ? 4 : 2;
+    for (int w0 = 0; w0 < W; w0 += kBlk) {
+      uint32_t hv[kBlk], lrv[kBlk];
 #pragma unroll
-        for (int d = 0; d < ND; ++d)
-          av[d] = sgn * s_area[d * estride + j];
+      for (int u = 0; u < kBlk; ++u)
+        hv[u] = (w0 + u < W) ? hp[(w0 + u) * 32] : 0u;
 #pragma unroll
-        for (int c = 0; c < D1; ++c) {
-          const double phiIp =
-            0.5 * (s_phi[c * stride + l] + s_phi[c * stride + r]);
+      for (int u = 0; u < kBlk; ++u)
+        lrv[u] = (hv[u] & kHeValid) ? s_lr[he_edge(hv[u])] : 0u;
+      double av[kBlk][ND], ph[kBlk][D1];
+#pragma unroll
+      for (int u = 0; u < kBlk; ++u)
+        if (hv[u] & kHeValid) {
+          const int j = (int)he_edge(hv[u]);
+          const int l = (int)(lrv[u] & 0xffffu), r = (int)(lrv[u] >> 16);
+          /* L node: += a_j phiIp ; R node: -= a_j phiIp (NodalGradEdgeAlg.C:100-106) */
+          const double sgn = he_side(hv[u]) ? -1.0 : 1.0;
 #pragma unroll
           for (int d = 0; d < ND; ++d)
-            acc[c * ND + d] += av[d] * phiIp;
+            av[u][d] = sgn * s_area[d * estride + j];
+#pragma unroll
+          for (int c = 0; c < D1; ++c)
+            ph[u][c] = 0.5 * (s_phi[c * stride + l] + s_phi[c * stride + r]);
         }
-      }
+#pragma unroll
+      for (int u = 0; u < kBlk; ++u)
+        if (hv[u] & kHeValid) {
+#pragma unroll
+          for (int c = 0; c < D1; ++c)
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+              acc[c * ND + d] += av[u][d] * ph[u][c];
+        }
     }
     /* the reference divides every edge term by the dual volume before summing;
      * scaling the node's sum once differs by rounding only (a few ulp) and
      * saves a divide per half-edge */
-    const double invVol = nw_rcp(__ldg(dualVol + h.node0 + i));
+    const double invVol = nw_rcp(vol);
 #pragma unroll
     for (int k = 0; k < NV; ++k)
       out.c[k][h.node0 + i] = acc[k] * invVol;

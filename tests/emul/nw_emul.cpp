@@ -786,4 +786,95 @@ emu_geometry_cvfem(
   return 1;
 }
 
+/* The default-option paths of momentum_edge / scalar_edge (edge_physics.h,
+ * template DEF) against the general paths on n seeded random edges with
+ * alpha = 0, alpha_upw = 1, hoUpwind = 1: returns the number of result doubles
+ * whose bits differ (exact zeros of either sign count as equal). */
+int64_t
+emu_default_path_mismatches(int64_t n, uint64_t seed)
+{
+  uint64_t st = seed * 0x9E3779B97F4A7C15ull + 1;
+  auto rnd = [&]() { /* splitmix64 -> (-1, 1) */
+    st += 0x9E3779B97F4A7C15ull;
+    uint64_t z = st;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return 2.0 * (double(z >> 11) / 9007199254740992.0) - 1.0;
+  };
+  auto same = [](double a, double b) {
+    if (a == 0.0 && b == 0.0)
+      return true;
+    return std::memcmp(&a, &b, sizeof(double)) == 0;
+  };
+  int64_t bad = 0;
+  for (int64_t q = 0; q < n; ++q) {
+    MomNode<3> L, R;
+    ScalNode<3> sl, sr;
+    double av[3];
+    for (int d = 0; d < 3; ++d) {
+      L.x[d] = rnd();
+      R.x[d] = L.x[d] + 0.2 * rnd() + (d == int(q % 3) ? 0.5 : 0.0);
+      L.u[d] = 5.0 * rnd();
+      R.u[d] = L.u[d] + rnd();
+      av[d] = (R.x[d] - L.x[d]) * (0.5 + 0.4 * rnd());
+      sl.x[d] = L.x[d];
+      sr.x[d] = R.x[d];
+      sl.v[d] = L.u[d];
+      sr.v[d] = R.u[d];
+      sl.dq[d] = rnd();
+      sr.dq[d] = rnd();
+    }
+    for (int d = 0; d < 9; ++d) {
+      L.g[d] = rnd();
+      R.g[d] = rnd();
+    }
+    L.mu = 1e-5 * (2.0 + rnd());
+    R.mu = 1e-5 * (2.0 + rnd());
+    L.rho = 1.2 + 0.1 * rnd();
+    R.rho = 1.2 + 0.1 * rnd();
+    L.mask = R.mask = 1.0;
+    sl.q = 2.0 + rnd();
+    sr.q = q % 7 == 0 ? sl.q : 2.0 + rnd(); /* flat field: limiter corner */
+    sl.rho = L.rho;
+    sr.rho = R.rho;
+    sl.mu = 3.0 * L.mu;
+    sr.mu = 3.0 * R.mu;
+    const double mdot = q % 5 == 0 ? 0.0 : rnd();
+    const double pecfac = q % 3 == 0 ? 1.0 - 1e-11 * (1.0 + rnd()) : 0.5 * (1.0 + rnd());
+    nw_momentum_opts mo{};
+    mo.include_divu = 0.0;
+    mo.alpha = 0.0;
+    mo.alpha_upw = 1.0;
+    mo.ho_upwind = 1.0;
+    mo.relax_fac = 0.7;
+    mo.use_limiter = 1;
+    mo.eps = 1e-16;
+    MomResult<3> a, b;
+    momentum_edge_t<3, true>(L, R, av, mdot, pecfac, mo, a);
+    momentum_edge_t<3, false>(L, R, av, mdot, pecfac, mo, b);
+    bad += !same(a.sLL, b.sLL) + !same(a.sLR, b.sLR) + !same(a.sRL, b.sRL) +
+           !same(a.sRR, b.sRR);
+    for (int d = 0; d < 3; ++d)
+      bad += !same(a.flux[d], b.flux[d]);
+    nw_scalar_opts so{};
+    so.alpha = 0.0;
+    so.alpha_upw = 1.0;
+    so.ho_upwind = 1.0;
+    so.relax_fac = 0.9;
+    so.use_limiter = 1;
+    so.eps = 1e-16;
+    so.pf.form = NW_PECLET_TANH;
+    so.pf.a = 2.0;
+    so.pf.b = 1.0;
+    double ca[4], cb[4], fa, fb;
+    scalar_edge_t<3, true>(sl, sr, av, mdot, so, ca, fa);
+    scalar_edge_t<3, false>(sl, sr, av, mdot, so, cb, fb);
+    for (int k = 0; k < 4; ++k)
+      bad += !same(ca[k], cb[k]);
+    bad += !same(fa, fb);
+  }
+  return bad;
+}
+
 } // extern "C"

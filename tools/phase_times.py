@@ -38,7 +38,7 @@ def main():
     a = ap.parse_args()
     P = graft.load_package()
     ctx = P.Context(0)
-    box, fields = bench.build_case(P, a.n, 1, 0)
+    box, fields = bench.build_case(P, (a.n, a.n, a.n), 1, 0)
     mesh = box.make_mesh(ctx, tile_nodes=a.tile)
     for name, arr in fields.items():
         mesh.put(name, P.NW_NODE, arr)
@@ -57,7 +57,8 @@ def main():
     def sweep():
         mesh.peclet_edge("viscosity", pf)
         mom.zeroSystem()
-        mom.assemble_momentum_edge("viscosity", **bench.MOM_OPTS)
+        mom.assemble_momentum_edge("viscosity", fuse_peclet=True, pf=pf,
+                                   **bench.MOM_OPTS)  # the bench default
         mom.loadComplete()
         con.zeroSystem()
         con.assemble_continuity_edge(**bench.CONT_OPTS)
