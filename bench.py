@@ -197,7 +197,8 @@ def build_case(P, dims, nranks, rank):
     nx, ny, nz = dims
     box = P.BoxMesh(nx, ny, nz, nranks=nranks, rank=rank)
     fields = synth.state_chunked(box.coords, box.gid,
-                                 (float(nx), float(ny), float(nz)), DT, GAMMA1)
+                                 (float(nx), float(ny), float(nz)), DT, GAMMA1,
+                                 threads=int(os.environ.get("NW_HOST_THREADS", "0")) or None)
     fields["dual_nodal_volume"] = box.vol
     return box, fields
 
@@ -499,6 +500,11 @@ def main():
                          "fallback (use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local)
     numa = bind_to_gpu_numa_node(local)
+    # host-side set-up (mesh generation, plan builder): share the cores among
+    # the ranks of this node (torchrun exports OMP_NUM_THREADS=1)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    os.environ.setdefault("NW_HOST_THREADS", str(max(
+        1, len(os.sched_getaffinity(0)) // max(1, local_world))))
     P = graft.load_package()
     ctx = P.Context(local)
     if world > 1:

@@ -8,6 +8,9 @@
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
+#if defined(_OPENMP)
+#include <omp.h>
+#endif
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -38,6 +41,21 @@ struct StageTimer
     t0 = t1;
   }
 };
+
+/* NW_HOST_THREADS=n: OpenMP threads of the plan builder.  Launchers such as
+ * torchrun export OMP_NUM_THREADS=1 to every rank; a caller that knows how many
+ * cores one rank may use (bench.py: cores / ranks) says so here. */
+void
+apply_host_threads()
+{
+#if defined(_OPENMP)
+  if (const char* e = std::getenv("NW_HOST_THREADS")) {
+    const int n = std::atoi(e);
+    if (n > 0)
+      omp_set_num_threads(n);
+  }
+#endif
+}
 
 inline int64_t
 even_up(int64_t v)
@@ -217,6 +235,7 @@ build_mesh_plan(const MeshInput& in, MeshPlan& mp)
 
   const int64_t N = in.nNodes, E = in.nEdges;
   const int nd = in.ndim;
+  apply_host_threads();
   StageTimer tm;
   mp = MeshPlan();
   mp.ndim = nd;
@@ -513,6 +532,7 @@ build_graph(
   const std::vector<int64_t>& skippedIn,
   Graph& g)
 {
+  apply_host_threads();
   StageTimer tm;
   g = Graph();
   if (kind == NW_LINSYS_HYPRE_UVW)
@@ -728,6 +748,7 @@ build_graph(
 void
 build_ls_plan(const MeshPlan& mp, const Graph& g, LsPlan& lp)
 {
+  apply_host_threads();
   StageTimer tm;
   lp = LsPlan();
   if (g.numDof != 1) {

@@ -20,6 +20,10 @@
  * Ownership follows STK's convention: a node / edge shared by several ranks is
  * owned by the lowest rank.
  */
+#if defined(_OPENMP)
+#include <omp.h>
+#endif
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -406,6 +410,11 @@ mg_generate(const mg_params* p)
   g->rank = p->rank;
   g->shuffleBucket = p->shuffle_bucket;
   g->seed = p->seed;
+#if defined(_OPENMP)
+  if (const char* e = std::getenv("NW_HOST_THREADS")) /* see plan.cpp */
+    if (std::atoi(e) > 0)
+      omp_set_num_threads(std::atoi(e));
+#endif
   generate(*g);
   return g;
 }
