@@ -210,6 +210,15 @@ int nw_mesh_halo_commit(nw_mesh* mesh);
  * with the sum over all ranks' copies (owner adds in ascending rank order,
  * then owner -> sharers).  Single rank: no-op. */
 int nw_field_parallel_sum(nw_mesh* mesh, int field_id);
+/* Realm::periodic_field_update(field, size) (src/Realm.C:3090-3100 ->
+ * PeriodicManager::apply_constraints with addSlaves and setSlaves,
+ * src/PeriodicManager.C:1007-1058, 1139-1190) for a nodal field: the nodes that
+ * resolve to one row (node_hypre_id equal: a periodic master and its slaves)
+ * end with master + sum of the slaves -- added in ascending own-id order --
+ * on every copy.  No-op on a mesh without periodic aliases.  A master that
+ * lives on another rank than its slaves is NW_ERR_LIMIT (the slab / block
+ * decompositions of the periodic decks keep them together). */
+int nw_field_periodic_update(nw_mesh* mesh, int field_id);
 /* stk::mesh::copy_owned_to_shared(bulk, {field}) for a nodal field (what the
  * reference does to a solution field after every solve, src/LinearSystem.C:
  * 161-169, so that the next sweep reads current values on shared nodes): every
@@ -250,9 +259,13 @@ int nw_peclet_edge(
 
 /* NodalGradAlgDriver::execute for the interior edge algorithm
  * (src/ngp_algorithms/NodalGradAlgDriver.C:30-72 +
- *  NodalGradEdgeAlg.C:58-111): grad = 0; grad += edge contributions; then the
- * shared-node sum over ranks (stk::mesh::parallel_sum) when a communicator is
- * attached.  phi has dim1 components (1 or ndim), grad dim1*ndim. */
+ *  NodalGradEdgeAlg.C:58-111): pre_work grad = 0 (fused); execute grad += edge
+ * contributions; post_work the shared-node sum over ranks
+ * (stk::mesh::parallel_sum; a multi-rank mesh needs a communicator or
+ * caller-committed halo lists, else NW_ERR_STATE) and, on a mesh with periodic
+ * aliases, realm_.periodic_field_update(gradPhi) (:63-65) as
+ * nw_field_periodic_update does.  phi has dim1 components (1 or ndim), grad
+ * dim1*ndim. */
 int nw_nodal_grad_edge(nw_mesh* mesh, int phi_field, int grad_field);
 
 /* ------------------------------------------------------------------ */

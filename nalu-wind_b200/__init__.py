@@ -134,7 +134,7 @@ ABI_SYMBOLS = [
     "nw_linsys_apply_dirichlet_bcs", "nw_linsys_load_complete",
     "nw_linsys_device_arrays", "nw_linsys_get_values", "nw_linsys_rhs_norm2", "nw_linsys_rhs_norm2_global",
     "nw_mesh_halo_send_count", "nw_mesh_halo_get_send", "nw_mesh_halo_set_recv",
-    "nw_mesh_halo_commit", "nw_field_parallel_sum", "nw_field_copy_owned_to_shared", "nw_linsys_halo_send_info",
+    "nw_mesh_halo_commit", "nw_field_parallel_sum", "nw_field_periodic_update", "nw_field_copy_owned_to_shared", "nw_linsys_halo_send_info",
     "nw_linsys_halo_get_send", "nw_linsys_halo_set_recv",
     "nw_linsys_halo_commit", "nw_linsys_halo_get_recv_slots",
     "nw_linsys_get_extra",
@@ -233,6 +233,7 @@ def lib():
     L.nw_mesh_halo_set_recv.argtypes = [vp, C.c_int, C.c_int64, c_i64p]
     L.nw_mesh_halo_commit.argtypes = [vp]
     L.nw_field_parallel_sum.argtypes = [vp, C.c_int]
+    L.nw_field_periodic_update.argtypes = [vp, C.c_int]
     L.nw_field_copy_owned_to_shared.argtypes = [vp, C.c_int]
     L.nw_linsys_halo_send_info.argtypes = [vp, C.c_int, c_i64p, c_i64p]
     L.nw_linsys_halo_get_send.argtypes = [vp, C.c_int, c_i64p, c_i64p, c_i64p]
@@ -471,6 +472,10 @@ class Mesh:
 
     def parallel_sum(self, name):
         _chk(lib().nw_field_parallel_sum(self.h, self.field_id(name)))
+
+    def periodic_update(self, name):
+        """Realm::periodic_field_update: master + slaves summed, on every copy"""
+        _chk(lib().nw_field_periodic_update(self.h, self.field_id(name)))
 
     def copy_owned_to_shared(self, name):
         _chk(lib().nw_field_copy_owned_to_shared(self.h, self.field_id(name)))

@@ -303,6 +303,44 @@ nw_mesh_create(nw_ctx* ctx, const nw_mesh_desc* desc, nw_mesh** out)
         own[n] >= m->plan.iLowerNode && own[n] <= m->plan.iUpperNode &&
         own[n] == desc->node_hypre_id[n];
   }
+  if (desc->node_own_hypre_id) {
+    /* periodic row groups: nodes whose resolved row id coincides */
+    const int64_t* hid = desc->node_hypre_id;
+    const int64_t* own = desc->node_own_hypre_id;
+    std::vector<int32_t> alias; /* nodes of groups with a slave */
+    std::vector<int64_t> slaveRows;
+    for (int64_t n = 0; n < desc->n_nodes; ++n)
+      if (own[n] != hid[n])
+        slaveRows.push_back(hid[n]);
+    if (!slaveRows.empty()) {
+      std::sort(slaveRows.begin(), slaveRows.end());
+      slaveRows.erase(
+        std::unique(slaveRows.begin(), slaveRows.end()), slaveRows.end());
+      for (int64_t n = 0; n < desc->n_nodes; ++n)
+        if (std::binary_search(slaveRows.begin(), slaveRows.end(), hid[n]))
+          alias.push_back((int32_t)n);
+      std::sort(alias.begin(), alias.end(), [&](int32_t x, int32_t y) {
+        if (hid[x] != hid[y])
+          return hid[x] < hid[y];
+        const bool mx = own[x] == hid[x], my = own[y] == hid[y];
+        if (mx != my)
+          return mx; /* the master leads its group */
+        if (own[x] != own[y])
+          return own[x] < own[y];
+        return x < y;
+      });
+      for (size_t q = 0; q < alias.size(); ++q) {
+        const int32_t n = alias[q];
+        if (q == 0 || hid[n] != hid[alias[q - 1]]) {
+          m->perPtr.push_back((int32_t)m->perSlots.size());
+          if (own[n] != hid[n])
+            m->perMasterMissing = true;
+        }
+        m->perSlots.push_back(m->plan.slotOfNode[n]);
+      }
+      m->perPtr.push_back((int32_t)m->perSlots.size());
+    }
+  }
   if (desc->nranks > 1) {
     const int64_t* own =
       desc->node_own_hypre_id ? desc->node_own_hypre_id : desc->node_hypre_id;
@@ -957,6 +995,42 @@ nw_peclet_edge(nw_mesh* mesh, int viscosity_field, const nw_peclet_opts* opts)
 
 static int node_halo_sum(nw_mesh* mesh, nw_field_t* f);
 
+/* Realm::periodic_field_update on one nodal field (compute stream) */
+static int
+periodic_update(nw_mesh* mesh, nw_field_t* f)
+{
+  if (mesh->perPtr.size() < 2)
+    return NW_OK;
+  if (mesh->perMasterMissing)
+    return fail(
+      NW_ERR_LIMIT, "periodic_field_update: a periodic master lives on another "
+                    "rank than its slaves (not supported)");
+  cudaStream_t s = mesh->ctx->stream;
+  if (!mesh->perUploaded) {
+    int rc;
+    if ((rc = upload(mesh->dPerPtr, mesh->perPtr, s, &mesh->planBytes)) ||
+        (rc = upload(mesh->dPerSlots, mesh->perSlots, s, &mesh->planBytes)))
+      return rc;
+    mesh->perUploaded = true;
+  }
+  field_wait_pull(mesh, f); /* after the shared-node sum, as the reference */
+  NW_CUDA(launch_periodic_update(
+    f->buf.as<double>(), f->stride, f->ncomp, mesh->dPerPtr.as<int32_t>(),
+    mesh->dPerSlots.as<int32_t>(), (int)mesh->perPtr.size() - 1, s));
+  return NW_OK;
+}
+
+extern "C" int
+nw_field_periodic_update(nw_mesh* mesh, int field_id)
+{
+  nw_field_t* f = get_field(mesh, field_id);
+  if (!f || f->rank != NW_NODE)
+    return fail(NW_ERR_ARG, "nw_field_periodic_update: bad nodal field id");
+  if (int rc = need_device(mesh->ctx, "nw_field_periodic_update"))
+    return rc;
+  return periodic_update(mesh, f);
+}
+
 extern "C" int
 nw_nodal_grad_edge(nw_mesh* mesh, int phi_field, int grad_field)
 {
@@ -990,9 +1064,11 @@ nw_nodal_grad_edge(nw_mesh* mesh, int phi_field, int grad_field)
     out[c] = grad->buf.as<double>() + (int64_t)c * grad->stride;
   NW_CUDA(launch_grad_tile(
     mesh->dev, phi->ncomp, nc, vol, ec, out, mesh->ctx->stream));
+  /* NodalGradAlgDriver::post_work (NodalGradAlgDriver.C:41-71) */
   if (mesh->plan.nranks > 1)
-    return node_halo_sum(mesh, grad);
-  return NW_OK;
+    if (int rc2 = node_halo_sum(mesh, grad))
+      return rc2;
+  return periodic_update(mesh, grad);
 }
 
 /* ------------------------------------------------------------------ */

@@ -216,6 +216,13 @@ struct nw_mesh
     nw::DevBuf dElemSlots, dElemEdges, dOwned;
     bool hasOwned = false;
   } geo[5];
+  /* periodic row groups (nodes sharing one node_hypre_id, more than one
+   * member): CSR over internal slots, master first, slaves in ascending own id;
+   * perMasterMissing: a group without its master on this rank exists */
+  std::vector<int32_t> perPtr, perSlots;
+  bool perMasterMissing = false;
+  bool perUploaded = false;
+  nw::DevBuf dPerPtr, dPerSlots;
   /* node-kernel selector: locally owned and not a periodic slave */
   std::vector<uint8_t> nodeKernelActive;
   int64_t planBytes = 0;

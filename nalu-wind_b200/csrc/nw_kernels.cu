@@ -161,30 +161,83 @@ tma_load_1d(void* dstSmem, const void* srcGmem, uint32_t bytes, uint64_t* bar)
     : "memory");
 }
 
-/* Stage NC node components of one tile: own range by TMA, halo by gather.
- * s_node[c*stride + i]; i < nOwnPad own, nOwnPad + k halo k.  The caller has
- * initialised `bar` (count 1) and synchronised the CTA. */
-template <int NC>
 __device__ __forceinline__ void
-stage_nodes_issue(
-  double* s_node,
-  int stride,
-  const NodeComps& nc,
-  const TileHdr& h,
-  uint64_t* bar,
-  uint32_t extraTx = 0)
+cp_async4(void* dstSmem, const void* src)
 {
-  if (threadIdx.x == 0) {
-    const uint32_t bytes = (uint32_t)h.nOwnPad * 8u;
-    mbar_expect_tx(bar, bytes * NC + extraTx);
-    if (bytes) {
-#pragma unroll
-      for (int c = 0; c < NC; ++c)
-        tma_load_1d(s_node + c * stride, nc.c[c] + h.node0, bytes, bar);
-    }
-  }
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dstSmem)),
+               "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void
+cp_async8(void* dstSmem, const void* src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dstSmem)),
+               "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void
+cp_async16(void* dstSmem, const void* src)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dstSmem)),
+               "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void
+cp_async_commit()
+{
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void
+cp_async_wait_all()
+{
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+__device__ __forceinline__ uint32_t
+round16(uint32_t bytes)
+{
+  return (bytes + 15u) & ~15u;
+}
+
+/* Issue of a tile's bulk copies: copy q is issued by lane 0 of warp
+ * q mod nWarps.  A bulk copy costs its issuing WARP ~100 cycles (UBLKCP is a
+ * uniform-datapath instruction: lanes of one warp take turns, profiles/
+ * r02c_phase_cycles_tile192.txt: 28 copies from one warp = 2.4-3 k cycles per
+ * tile, whichever lanes issue them), while the TMA unit accepts copies from
+ * different warps back to back (r02b_microbench_stage_layouts.txt, V4). */
+template <class F>
+__device__ __forceinline__ void
+issue_spread(int nCopies, F&& copy)
+{
+  if ((threadIdx.x & 31) == 0)
+    for (int q = threadIdx.x >> 5; q < nCopies; q += blockDim.x >> 5)
+      copy(q);
+}
+
+/* Stage NC node components of one tile: own range by TMA, halo by gather.
+ * s_node[c*stride + i]; i < nOwnPad own, nOwnPad + k halo k.  The caller has
+ * initialised `bar` (count 1), posted the expected bytes and synchronised the
+ * CTA.  Copy q < NC of the tile's copy table. */
+template <int NC>
+__device__ __forceinline__ void
+node_copy(
+  int q, double* s_node, int stride, const NodeComps& nc, const TileHdr& h,
+  uint64_t* bar, bool skip = false)
+{
+  const uint32_t bytes = skip ? 0u : (uint32_t)h.nOwnPad * 8u;
+  if (bytes)
+    tma_load_1d(s_node + q * stride, nc.c[q] + h.node0, bytes, bar);
+}
+__device__ __forceinline__ uint32_t
+node_copy_bytes(int ncomp, const TileHdr& h, bool skip = false)
+{
+  return skip ? 0u : (uint32_t)h.nOwnPad * 8u * (uint32_t)ncomp;
+}
+
+/* halo nodes: asynchronous 8-byte copies global -> shared (LDGSTS: one
+ * load/store-unit operation per value instead of a load and a store, no
+ * register round trip); the issuing thread waits for its own copies with
+ * stage_halo_wait() before the CTA barrier */
 template <int NC>
 __device__ __forceinline__ void
 stage_halo_gather(
@@ -194,18 +247,19 @@ stage_halo_gather(
   const TileHdr& h,
   const int32_t* __restrict__ haloNodes)
 {
-  /* warp 0 is busy issuing the bulk copies (~100 cycles of issue latency
-   * each, profiles/r01c_phase_cycles_tile192.txt): the other warps gather,
-   * so the two overlap instead of thread 0 doing one after the other */
-  if (threadIdx.x < 32)
-    return;
   const int32_t* halo = haloNodes + h.haloPtr;
-  for (int k = threadIdx.x - 32; k < h.nHalo; k += blockDim.x - 32) {
+  for (int k = threadIdx.x; k < h.nHalo; k += blockDim.x) {
     const int32_t g = __ldg(halo + k);
 #pragma unroll
     for (int c = 0; c < NC; ++c)
-      s_node[c * stride + h.nOwnPad + k] = __ldg(nc.c[c] + g);
+      cp_async8(s_node + c * stride + h.nOwnPad + k, nc.c[c] + g);
   }
+  cp_async_commit();
+}
+__device__ __forceinline__ void
+stage_halo_wait()
+{
+  cp_async_wait_all();
 }
 
 template <int NC>
@@ -218,19 +272,16 @@ stage_nodes(
   const int32_t* __restrict__ haloNodes,
   uint64_t* bar)
 {
-  if (threadIdx.x == 0)
+  if (threadIdx.x == 0) {
     mbar_init(bar, 1);
+    mbar_expect_tx(bar, node_copy_bytes(NC, h));
+  }
   __syncthreads();
-  stage_nodes_issue<NC>(s_node, stride, nc, h, bar);
+  issue_spread(NC, [&](int q) { node_copy<NC>(q, s_node, stride, nc, h, bar); });
   stage_halo_gather<NC>(s_node, stride, nc, h, haloNodes);
+  stage_halo_wait();
   mbar_wait(bar, 0);
   __syncthreads();
-}
-
-__device__ __forceinline__ uint32_t
-round16(uint32_t bytes)
-{
-  return (bytes + 15u) & ~15u;
 }
 
 /* bytes the edge-stream bulk copies of one tile deliver: the packed (L,R)
@@ -243,25 +294,39 @@ edge_stream_bytes(const TileHdr& h, int ncomp)
          (uint32_t)ncomp * round16((uint32_t)h.nEdges * 8u);
 }
 
-/* thread 0: TMA bulk copies of the tile's edge streams (expect_tx is the
- * caller's); component c lands at s_edge[c * estride + j] */
+/* edge input component c of a kernel: area[0..ND), then mdot, then pecfac
+ * (constant indices only: a dynamic index into the by-value kernel parameter
+ * would copy the struct to local memory) */
+template <int ND>
+struct EdgeCompSel
+{
+  const EdgeComps& ec;
+  __device__ __forceinline__ const double* operator()(int c) const
+  {
+    return c == 0 ? ec.area[0]
+           : c == 1 ? ec.area[1]
+           : (ND == 3 && c == 2) ? ec.area[2]
+           : c == ND ? ec.mdot
+                     : ec.pecfac;
+  }
+};
+
+/* edge-stream copy q of a tile: q == 0 the packed (L,R) records, q - 1 = c the
+ * edge component c, which lands at s_edge[c * estride + j] */
+template <class F>
 __device__ __forceinline__ void
-stage_edges_issue(
-  uint32_t* s_lr,
-  double* s_edge,
-  int estride,
-  const MeshPlanDev& mp,
-  const TileHdr& h,
-  const double* const* comps,
-  int ncomp,
-  uint64_t* bar)
+edge_copy(
+  int q, uint32_t* s_lr, double* s_edge, int estride, const MeshPlanDev& mp,
+  const TileHdr& h, const F& comps, uint64_t* bar)
 {
   if (h.nEdges == 0)
     return;
-  tma_load_1d(s_lr, mp.lr + h.edge0, round16((uint32_t)h.nEdges * 4u), bar);
-  const uint32_t b = round16((uint32_t)h.nEdges * 8u);
-  for (int c = 0; c < ncomp; ++c)
-    tma_load_1d(s_edge + c * estride, comps[c] + h.edge0, b, bar);
+  if (q == 0)
+    tma_load_1d(s_lr, mp.lr + h.edge0, round16((uint32_t)h.nEdges * 4u), bar);
+  else
+    tma_load_1d(
+      s_edge + (q - 1) * estride, comps(q - 1) + h.edge0,
+      round16((uint32_t)h.nEdges * 8u), bar);
 }
 
 template <int NV>
@@ -666,53 +731,56 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
   uint32_t* s_lr = reinterpret_cast<uint32_t*>(s_go + L.entLen);
 
   /* edge input streams of this policy: area, [mdot], [pecfac] */
-  const double* ecomp[LsSmem<P>::NIN_MAX];
-  int nin = 0;
-#pragma unroll
-  for (int d = 0; d < ND; ++d)
-    ecomp[nin++] = ec.area[d];
-  const int kMdot = nin;
-  if (P::kNeedsMdot)
-    ecomp[nin++] = ec.mdot;
-  const int kPec = nin;
+  constexpr int kMdot = ND;
+  constexpr int kPec = ND + 1;
   const bool hasPec = P::kNeedsPec && ec.pecfac != nullptr;
-  if (hasPec)
-    ecomp[nin++] = ec.pecfac;
+  const int nin = ND + (P::kNeedsMdot ? 1 : 0) + (hasPec ? 1 : 0);
+  const EdgeCompSel<ND> ecomp{ec};
 
   /* ---- stage: every contiguous per-tile stream is a TMA bulk copy ---- */
+  const uint32_t bEll = (uint32_t)lh.ellLen * 4u;
+  const uint32_t bEnt = round16((uint32_t)lh.nEnts * 4u);
+  const bool skipOwn = (mp.dbgSkip & 8) != 0;
   if (threadIdx.x == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
+    mbar_expect_tx(
+      &bar[0], node_copy_bytes(P::NC, h, skipOwn) + edge_stream_bytes(h, nin));
+    mbar_expect_tx(&bar[1], bEll + 3u * bEnt);
   }
   __syncthreads();
   NW_PT_MARK(); /* 0: headers + barrier init */
-  stage_nodes_issue<P::NC>(
-    s_node, stride, nc, h, &bar[0], edge_stream_bytes(h, nin));
-  if (threadIdx.x == 0) {
-    stage_edges_issue(s_lr, s_res, L.resStride, mp, h, ecomp, nin, &bar[0]);
-    /* the reduction plan of phases 2-3: half-edge records, row layout, rhs
-     * rows, value offsets; needed only after phase 1, so its latency hides
-     * behind the physics */
-    const uint32_t bEll = (uint32_t)lh.ellLen * 4u;
-    const uint32_t bEnt = round16((uint32_t)lh.nEnts * 4u);
-    mbar_expect_tx(&bar[1], bEll + 3u * bEnt);
-    if (bEll)
-      tma_load_1d(s_ell, lp.heEll + lh.ellPtr, bEll, &bar[1]);
-    if (bEnt) {
-      tma_load_1d(s_ent, lp.entInfo + lh.entPtr, bEnt, &bar[1]);
-      tma_load_1d(s_row, lp.entRhsRow + lh.entPtr, bEnt, &bar[1]);
-      tma_load_1d(s_go, lp.entGo + lh.entPtr, bEnt, &bar[1]);
+  /* copy table: node components, (L,R) records + edge components, then the
+   * reduction plan of phases 2-3 (half-edge records, row layout, rhs rows,
+   * value offsets; second barrier: needed only after phase 1, so its latency
+   * hides behind the physics) */
+  issue_spread(P::NC + 1 + nin + 4, [&](int q) {
+    if (q < P::NC)
+      node_copy<P::NC>(q, s_node, stride, nc, h, &bar[0], skipOwn);
+    else if (q <= P::NC + nin)
+      edge_copy(q - P::NC, s_lr, s_res, L.resStride, mp, h, ecomp, &bar[0]);
+    else {
+      const int r = q - (P::NC + 1 + nin);
+      if (r == 0 && bEll)
+        tma_load_1d(s_ell, lp.heEll + lh.ellPtr, bEll, &bar[1]);
+      else if (r == 1 && bEnt)
+        tma_load_1d(s_ent, lp.entInfo + lh.entPtr, bEnt, &bar[1]);
+      else if (r == 2 && bEnt)
+        tma_load_1d(s_row, lp.entRhsRow + lh.entPtr, bEnt, &bar[1]);
+      else if (r == 3 && bEnt)
+        tma_load_1d(s_go, lp.entGo + lh.entPtr, bEnt, &bar[1]);
     }
-  }
+  });
   NW_PT_MARK(); /* 1: TMA issue */
   {
     const int nSl = (lh.nEnts + 31) >> 5;
-    const int t = (int)threadIdx.x - 32;
-    if (t >= 0 && t <= nSl)
-      s_slice[t] = __ldg(lp.sliceOff + lh.slicePtr + t);
+    if ((int)threadIdx.x <= nSl)
+      s_slice[threadIdx.x] = __ldg(lp.sliceOff + lh.slicePtr + threadIdx.x);
   }
-  stage_halo_gather<P::NC>(s_node, stride, nc, h, mp.haloNodes);
+  if (!(mp.dbgSkip & 1))
+    stage_halo_gather<P::NC>(s_node, stride, nc, h, mp.haloNodes);
   NW_PT_MARK(); /* 2: halo gather */
+  stage_halo_wait();
   mbar_wait(&bar[0], 0);
   __syncthreads();
   NW_PT_MARK(); /* 3: stage wait */
@@ -733,7 +801,12 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
       if (hasPec)
         pecfac = s_res[kPec * L.resStride + j];
       double res[P::NRES];
-      P::compute(ld, l, r, av, mdot, pecfac, o, res);
+      if (mp.dbgSkip & 2) {
+#pragma unroll
+        for (int k = 0; k < P::NRES; ++k)
+          res[k] = av[0] + (double)(l + r);
+      } else
+        P::compute(ld, l, r, av, mdot, pecfac, o, res);
       /* results overwrite this edge's own inputs (all read above) */
 #pragma unroll
       for (int k = 0; k < P::NRES; ++k)
@@ -752,7 +825,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
    * point to, are loaded before anything of the block is stored, so that the
    * shared-memory latencies of a block overlap (round-1 phase cycles: this
    * phase was a chain of dependent 30-cycle loads, 20 % of a CTA's life). ---- */
-  {
+  if (!(mp.dbgSkip & 4)) {
     const int lane = threadIdx.x & 31;
     for (int row0 = (int)threadIdx.x - lane; row0 < lh.nEnts;
          row0 += blockDim.x) {
@@ -1020,16 +1093,23 @@ __global__ void __launch_bounds__(kTileThreads) mdot_tile_kernel(
   const int estride = even_up_i(mp.maxTileEdges);
   double* s_area = smem + (size_t)P::NC * mp.maxStaged;
   uint32_t* s_lr = reinterpret_cast<uint32_t*>(s_area + ND * estride);
-  if (threadIdx.x == 0)
+  if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
+    mbar_expect_tx(&bar, node_copy_bytes(P::NC, h) + edge_stream_bytes(h, ND));
+  }
+  const EdgeCompSel<ND> ecomp{ec};
   __syncthreads();
   NW_PT_MARK();
-  stage_nodes_issue<P::NC>(smem, stride, nc, h, &bar, edge_stream_bytes(h, ND));
-  if (threadIdx.x == 0)
-    stage_edges_issue(s_lr, s_area, estride, mp, h, ec.area, ND, &bar);
+  issue_spread(P::NC + 1 + ND, [&](int q) {
+    if (q < P::NC)
+      node_copy<P::NC>(q, smem, stride, nc, h, &bar);
+    else
+      edge_copy(q - P::NC, s_lr, s_area, estride, mp, h, ecomp, &bar);
+  });
   NW_PT_MARK();
   stage_halo_gather<P::NC>(smem, stride, nc, h, mp.haloNodes);
   NW_PT_MARK();
+  stage_halo_wait();
   mbar_wait(&bar, 0);
   __syncthreads();
   NW_PT_MARK();
@@ -1066,16 +1146,24 @@ __global__ void __launch_bounds__(kTileThreads) peclet_tile_kernel(
   const TileHdr h = mp.tiles[blockIdx.x];
   const int stride = even_up_i(h.nOwnPad + h.nHalo);
   uint32_t* s_lr = reinterpret_cast<uint32_t*>(smem + (size_t)NC * mp.maxStaged);
-  if (threadIdx.x == 0)
+  if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
+    mbar_expect_tx(&bar, node_copy_bytes(NC, h) + edge_stream_bytes(h, 0));
+  }
+  const EdgeComps noEdge{};
+  const EdgeCompSel<ND> ecomp{noEdge};
   __syncthreads();
   NW_PT_MARK();
-  stage_nodes_issue<NC>(smem, stride, nc, h, &bar, edge_stream_bytes(h, 0));
-  if (threadIdx.x == 0)
-    stage_edges_issue(s_lr, nullptr, 0, mp, h, nullptr, 0, &bar);
+  issue_spread(NC + 1, [&](int q) {
+    if (q < NC)
+      node_copy<NC>(q, smem, stride, nc, h, &bar);
+    else
+      edge_copy(0, s_lr, (double*)nullptr, 0, mp, h, ecomp, &bar);
+  });
   NW_PT_MARK();
   stage_halo_gather<NC>(smem, stride, nc, h, mp.haloNodes);
   NW_PT_MARK();
+  stage_halo_wait();
   mbar_wait(&bar, 0);
   __syncthreads();
   NW_PT_MARK();
@@ -1227,7 +1315,7 @@ struct GradOut
  * walks the node's half-edges (sliced-ELL list, TMA-staged), sums in
  * registers in list order and writes the node's gradient once, coalesced. */
 template <int D1, int ND>
-__global__ void __launch_bounds__(kTileThreads, 4) grad_tile_kernel(
+__global__ void __launch_bounds__(kTileThreads, D1 == 1 ? 8 : 5) grad_tile_kernel(
   const MeshPlanDev mp,
   const NodeComps phi,
   const double* __restrict__ dualVol,
@@ -1250,25 +1338,31 @@ __global__ void __launch_bounds__(kTileThreads, 4) grad_tile_kernel(
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
   }
+  const EdgeCompSel<ND> ecomp{ec};
+  const uint32_t bEll = (uint32_t)h.ellLenNode * 4u;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar[0], node_copy_bytes(D1, h) + edge_stream_bytes(h, ND));
+    mbar_expect_tx(&bar[1], bEll);
+  }
   __syncthreads();
   NW_PT_MARK();
-  stage_nodes_issue<D1>(s_phi, stride, phi, h, &bar[0], edge_stream_bytes(h, ND));
-  if (threadIdx.x == 0) {
-    stage_edges_issue(s_lr, s_area, estride, mp, h, ec.area, ND, &bar[0]);
-    const uint32_t bEll = (uint32_t)h.ellLenNode * 4u;
-    mbar_expect_tx(&bar[1], bEll);
-    if (bEll)
+  issue_spread(D1 + 1 + ND + 1, [&](int q) {
+    if (q < D1)
+      node_copy<D1>(q, s_phi, stride, phi, h, &bar[0]);
+    else if (q <= D1 + ND)
+      edge_copy(q - D1, s_lr, s_area, estride, mp, h, ecomp, &bar[0]);
+    else if (bEll)
       tma_load_1d(s_ell, mp.heNodeEll + h.ellPtrNode, bEll, &bar[1]);
-  }
+  });
   NW_PT_MARK();
   {
     const int nSl = (h.nOwn + 31) >> 5;
-    const int t = (int)threadIdx.x - 32;
-    if (t >= 0 && t <= nSl)
-      s_slice[t] = __ldg(mp.sliceOffNode + h.slicePtrNode + t);
+    if ((int)threadIdx.x <= nSl)
+      s_slice[threadIdx.x] = __ldg(mp.sliceOffNode + h.slicePtrNode + threadIdx.x);
   }
   stage_halo_gather<D1>(s_phi, stride, phi, h, mp.haloNodes);
   NW_PT_MARK();
+  stage_halo_wait();
   mbar_wait(&bar[0], 0);
   mbar_wait(&bar[1], 0);
   __syncthreads();
@@ -1285,43 +1379,27 @@ __global__ void __launch_bounds__(kTileThreads, 4) grad_tile_kernel(
 #pragma unroll
     for (int k = 0; k < NV; ++k)
       acc[k] = 0.0;
-    /* blocked by four list steps: records, then (L,R) pairs, then areas and
-     * phi are loaded for the whole block before the sums (same order of
-     * additions as the plain walk); the block is sized so that four CTAs stay
-     * resident per SM */
-    constexpr int kBlk = D1 == 1 ? 4 : 2;
-    for (int w0 = 0; w0 < W; w0 += kBlk) {
-      uint32_t hv[kBlk], lrv[kBlk];
+    for (int w = 0; w < W; ++w) {
+      const uint32_t hv = hp[w * 32];
+      if (hv & kHeValid) {
+        const int j = (int)he_edge(hv);
+        const uint32_t v = s_lr[j];
+        const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
+        /* L node: += a_j phiIp ; R node: -= a_j phiIp (NodalGradEdgeAlg.C:100-106) */
+        const double sgn = he_side(hv) ? -1.0 : 1.0;
+        double av[ND];
 #pragma unroll
-      for (int u = 0; u < kBlk; ++u)
-        hv[u] = (w0 + u < W) ? hp[(w0 + u) * 32] : 0u;
+        for (int d = 0; d < ND; ++d)
+          av[d] = sgn * s_area[d * estride + j];
 #pragma unroll
-      for (int u = 0; u < kBlk; ++u)
-        lrv[u] = (hv[u] & kHeValid) ? s_lr[he_edge(hv[u])] : 0u;
-      double av[kBlk][ND], ph[kBlk][D1];
-#pragma unroll
-      for (int u = 0; u < kBlk; ++u)
-        if (hv[u] & kHeValid) {
-          const int j = (int)he_edge(hv[u]);
-          const int l = (int)(lrv[u] & 0xffffu), r = (int)(lrv[u] >> 16);
-          /* L node: += a_j phiIp ; R node: -= a_j phiIp (NodalGradEdgeAlg.C:100-106) */
-          const double sgn = he_side(hv[u]) ? -1.0 : 1.0;
+        for (int c = 0; c < D1; ++c) {
+          const double phiIp =
+            0.5 * (s_phi[c * stride + l] + s_phi[c * stride + r]);
 #pragma unroll
           for (int d = 0; d < ND; ++d)
-            av[u][d] = sgn * s_area[d * estride + j];
-#pragma unroll
-          for (int c = 0; c < D1; ++c)
-            ph[u][c] = 0.5 * (s_phi[c * stride + l] + s_phi[c * stride + r]);
+            acc[c * ND + d] += av[d] * phiIp;
         }
-#pragma unroll
-      for (int u = 0; u < kBlk; ++u)
-        if (hv[u] & kHeValid) {
-#pragma unroll
-          for (int c = 0; c < D1; ++c)
-#pragma unroll
-            for (int d = 0; d < ND; ++d)
-              acc[c * ND + d] += av[u][d] * ph[u][c];
-        }
+      }
     }
     /* the reference divides every edge term by the dual volume before summing;
      * scaling the node's sum once differs by rounding only (a few ulp) and
@@ -1400,38 +1478,6 @@ constexpr int kStreamThreads = 256;
 constexpr int kStreamWarps = kStreamThreads / 32;
 constexpr int kHdrRing = 4;
 constexpr int kListRing = 2;
-
-__device__ __forceinline__ void
-cp_async4(void* dstSmem, const void* src)
-{
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dstSmem)),
-               "l"(src)
-               : "memory");
-}
-__device__ __forceinline__ void
-cp_async8(void* dstSmem, const void* src)
-{
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dstSmem)),
-               "l"(src)
-               : "memory");
-}
-__device__ __forceinline__ void
-cp_async16(void* dstSmem, const void* src)
-{
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dstSmem)),
-               "l"(src)
-               : "memory");
-}
-__device__ __forceinline__ void
-cp_async_commit()
-{
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void
-cp_async_wait_all()
-{
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
 
 /* one warp copies `bytes` (multiple of 16, both ends 16-byte aligned) */
 __device__ __forceinline__ void
@@ -2629,6 +2675,17 @@ env_int(const char* name, int dflt)
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
 }
+/* NW_DBG_SKIP: timing experiments (see MeshPlanDev::dbgSkip) */
+template <class K>
+inline MeshPlanDev
+with_pf(const MeshPlanDev& mp, K, int, size_t)
+{
+  static const int dbgEnv = env_int("NW_DBG_SKIP", 0);
+  MeshPlanDev m = mp;
+  m.dbgSkip = dbgEnv;
+  return m;
+}
+
 inline bool
 stream_enabled()
 {
@@ -2683,7 +2740,8 @@ launch_ls_tile(
   e = set_smem(ls_tile_kernel<P, ND>, bytes);
   if (e != cudaSuccess)
     return e;
-  ls_tile_kernel<P, ND><<<mp.nTiles, kTileThreads, bytes, s>>>(mp, lp, nc, ec, o);
+  ls_tile_kernel<P, ND><<<mp.nTiles, kTileThreads, bytes, s>>>(
+    with_pf(mp, ls_tile_kernel<P, ND>, kTileThreads, bytes), lp, nc, ec, o);
   return cudaGetLastError();
 }
 
@@ -2791,14 +2849,14 @@ launch_mdot_tile(
     const size_t bytes = edge_kernel_smem(mp, ContinuityP<3>::NC, 3);
     if ((e = set_smem(mdot_tile_kernel<3>, bytes)) != cudaSuccess)
       return e;
-    mdot_tile_kernel<3>
-      <<<mp.nTiles, kTileThreads, bytes, s>>>(mp, nc, ec, mdotOut, o);
+    mdot_tile_kernel<3><<<mp.nTiles, kTileThreads, bytes, s>>>(
+      with_pf(mp, mdot_tile_kernel<3>, kTileThreads, bytes), nc, ec, mdotOut, o);
   } else {
     const size_t bytes = edge_kernel_smem(mp, ContinuityP<2>::NC, 2);
     if ((e = set_smem(mdot_tile_kernel<2>, bytes)) != cudaSuccess)
       return e;
-    mdot_tile_kernel<2>
-      <<<mp.nTiles, kTileThreads, bytes, s>>>(mp, nc, ec, mdotOut, o);
+    mdot_tile_kernel<2><<<mp.nTiles, kTileThreads, bytes, s>>>(
+      with_pf(mp, mdot_tile_kernel<2>, kTileThreads, bytes), nc, ec, mdotOut, o);
   }
   return cudaGetLastError();
 }
@@ -2843,14 +2901,14 @@ launch_peclet_tile(
     const size_t bytes = edge_kernel_smem(mp, 8, 0);
     if ((e = set_smem(peclet_tile_kernel<3>, bytes)) != cudaSuccess)
       return e;
-    peclet_tile_kernel<3>
-      <<<mp.nTiles, kTileThreads, bytes, s>>>(mp, nc, pecfacOut, o);
+    peclet_tile_kernel<3><<<mp.nTiles, kTileThreads, bytes, s>>>(
+      with_pf(mp, peclet_tile_kernel<3>, kTileThreads, bytes), nc, pecfacOut, o);
   } else {
     const size_t bytes = edge_kernel_smem(mp, 6, 0);
     if ((e = set_smem(peclet_tile_kernel<2>, bytes)) != cudaSuccess)
       return e;
-    peclet_tile_kernel<2>
-      <<<mp.nTiles, kTileThreads, bytes, s>>>(mp, nc, pecfacOut, o);
+    peclet_tile_kernel<2><<<mp.nTiles, kTileThreads, bytes, s>>>(
+      with_pf(mp, peclet_tile_kernel<2>, kTileThreads, bytes), nc, pecfacOut, o);
   }
   return cudaGetLastError();
 }
@@ -2873,8 +2931,9 @@ launch_grad_tile_t(
   cudaError_t e = set_smem(grad_tile_kernel<D1, ND>, bytes);
   if (e != cudaSuccess)
     return e;
-  grad_tile_kernel<D1, ND>
-    <<<mp.nTiles, kTileThreads, bytes, s>>>(mp, phi, dualVol, ec, go);
+  grad_tile_kernel<D1, ND><<<mp.nTiles, kTileThreads, bytes, s>>>(
+    with_pf(mp, grad_tile_kernel<D1, ND>, kTileThreads, bytes), phi, dualVol, ec,
+    go);
   return cudaGetLastError();
 }
 template <int D1, int ND>
@@ -3435,6 +3494,41 @@ launch_p2p_pull_accumulate(
   p2p_pull_accumulate_kernel<<<p2p_pull_grid(nDst * nc, beside), 256, 0, s>>>(
     bufOff, entStride, compStride, nc, dstIdx, ptr, pos, nDst, dst,
     dstCompStride, pp, wait ? 1 : 0);
+  return cudaGetLastError();
+}
+
+namespace {
+/* PeriodicManager add_slave_to_master + set_slave_to_master for one field:
+ * thread per (group, component) */
+__global__ void __launch_bounds__(256) periodic_update_kernel(
+  double* base, int64_t stride, int nc, const int32_t* __restrict__ ptr,
+  const int32_t* __restrict__ slots, int nGroups)
+{
+  const int64_t total = (int64_t)nGroups * nc;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(t / nc);
+    const int c = (int)(t - (int64_t)g * nc);
+    double* f = base + (int64_t)c * stride;
+    const int a = ptr[g], b = ptr[g + 1];
+    double v = f[slots[a]];
+    for (int q = a + 1; q < b; ++q)
+      v += f[slots[q]];
+    for (int q = a; q < b; ++q)
+      f[slots[q]] = v;
+  }
+}
+} // namespace
+
+cudaError_t
+launch_periodic_update(
+  double* base, int64_t stride, int nc, const int32_t* ptr,
+  const int32_t* slots, int nGroups, cudaStream_t s)
+{
+  if (nGroups == 0)
+    return cudaSuccess;
+  periodic_update_kernel<<<blocks_for((int64_t)nGroups * nc, 256), 256, 0, s>>>(
+    base, stride, nc, ptr, slots, nGroups);
   return cudaGetLastError();
 }
 

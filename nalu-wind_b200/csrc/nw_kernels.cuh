@@ -34,6 +34,10 @@ struct MeshPlanDev
   int maxTileEdges = 0;
   int maxTileNodes = 0;
   int maxTileEllNode = 0;
+  /* NW_DBG_SKIP (timing experiments only, results are wrong): bit 0 no halo
+   * gather, bit 1 no edge physics, bit 2 no row reduction / copy-out, bit 3
+   * no own-range node copies */
+  int dbgSkip = 0;
 };
 
 struct LsPlanDev
@@ -288,6 +292,10 @@ cudaError_t launch_accumulate_multi(
   const double* buf, int64_t entStride, int64_t compStride, int nc,
   const int64_t* dstIdx, const int64_t* ptr, const int64_t* pos, int64_t nDst,
   double* dst, int64_t dstCompStride, cudaStream_t s);
+/* periodic_field_update: groups in CSR form over slots, master first */
+cudaError_t launch_periodic_update(
+  double* base, int64_t stride, int nc, const int32_t* ptr,
+  const int32_t* slots, int nGroups, cudaStream_t s);
 cudaError_t launch_unpack_add(
   const double* src, const int64_t* idx, int64_t n, double* dst,
   cudaStream_t s);

@@ -127,6 +127,11 @@ def peclet(form="classic", a=0.0, b=1.0):
     return Peclet(0 if form == "classic" else 1, float(a), float(b))
 
 
+def peclet_eval(pf, pecnum):
+    """PecletFunction::execute (src/PecletFunction.C:41-45, 68-71)"""
+    return float(lib().orc_peclet_eval(C.byref(pf), float(pecnum)))
+
+
 class DenseSink:
     """TestLinearSystem (unit_tests/UnitTestLinearSystem.h)."""
 

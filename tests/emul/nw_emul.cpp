@@ -786,6 +786,17 @@ emu_geometry_cvfem(
   return 1;
 }
 
+/* the product's peclet_eval (edge_physics.h), host build */
+double
+emu_peclet_eval(int form, double a, double b, double pecnum)
+{
+  nw_peclet_fn f;
+  f.form = form;
+  f.a = a;
+  f.b = b;
+  return peclet_eval(f, pecnum);
+}
+
 /* The default-option paths of momentum_edge / scalar_edge (edge_physics.h,
  * template DEF) against the general paths on n seeded random edges with
  * alpha = 0, alpha_upw = 1, hoUpwind = 1: returns the number of result doubles

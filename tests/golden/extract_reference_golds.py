@@ -11,6 +11,7 @@ Only numbers are extracted (C++ brace initialisers), no code.  Sources:
   unit_tests/edge_kernels/UnitTestScalarAdvDiffEdge.C:24-143
   unit_tests/ngp_algorithms/UnitTestNodalGradAlg.C:52-54, 107-110
   unit_tests/ngp_algorithms/UnitTestMdotAlg.C:66-77   (every edge == 2.5)
+  unit_tests/UnitTestPecletFunction.C:36-100  (classic / tanh known answers)
 """
 import json
 import os
@@ -125,6 +126,37 @@ def main():
     out["nodal_grad_scalar"] = flat(f[i0:i1], "expectedValues")
     out["nodal_grad_vector_diag"] = flat(f[i1:], "expectedValues")
     out["mdot_edge_value"] = 2.5
+
+    # PecletFunction known answers (UnitTestPecletFunction.C:36-100; tolerance
+    # 1e-6 there).  The inputs are C++ expressions (std::sqrt(5.0), c1 + 10.0 *
+    # c2): the braces are extracted as text and evaluated with the test's own
+    # constants.
+    import math
+    f = strip_comments(open(os.path.join(
+        REF, "unit_tests/UnitTestPecletFunction.C")).read())
+
+    def case(test_name):
+        i0 = f.index(test_name + ")")
+        body = f[i0:f.index("TEST(", i0) if "TEST(" in f[i0:] else len(f)]
+        env = {"sqrt": math.sqrt}
+        for nm in ("A", "hybridFactor", "c1", "c2"):
+            m = re.search(r"\b" + nm + r"\s*=\s*([-+0-9.eE]+)\s*;", body)
+            if m:
+                env[nm] = float(m.group(1))
+
+        def ev(name):
+            blk = array_after(body, name)[1:-1].replace("std::sqrt", "sqrt")
+            return [float(eval(x, {"__builtins__": {}}, env))
+                    for x in blk.split(",")]
+        d = {"peclet_numbers": ev("pecletNumbers"),
+             "peclet_factors": ev("pecletFactors"), "tolerance": 1.0e-6}
+        d.update({k: v for k, v in env.items() if k != "sqrt"})
+        return d
+    out["peclet_function"] = {
+        "classic": case("NGP_classic_double"),
+        "tanh": case("NGP_tanh_double"),
+        "tanh_simd": case("NGP_tanh_simd"),
+    }
 
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)),
                        "reference_golds.json")

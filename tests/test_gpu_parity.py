@@ -987,6 +987,78 @@ def test_full_size_conservation(P, ctx, big):
     ls.close()
 
 
+def _report_plain(tag, res):
+    """plain relative worst errors beside the scaled ones; kept
+    as a file when the run has a gpurun_out/ to put it in"""
+    out = {"case": tag, "worst_scaled_error": max(res.values()),
+           "scaled": res, "plain_relative": dict(pu.LAST_PLAIN)}
+    print(json.dumps(out))
+    d = os.path.join(pu.ROOT, "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_%s.json" % tag), "w") as fh:
+            json.dump(out, fh, indent=1)
+
+
+def test_baseline_size_128_vs_oracle(P, ctx):
+    """BASELINE configs[1] at its full size -- 128^3 elements, default tile --
+    entry by entry against the oracle (not just properties): mdot, Peclet
+    factor, both gradients, continuity / scalar / momentum-UVW (separate and
+    fused Peclet) matrices and right-hand sides, |got - ref| <= 1e-12 max(|ref|,
+    sum |contributions|)"""
+    n = int(os.environ.get("NW_TEST_BIG", "128"))
+    res = pu.run_lowmach_case(P, ctx, dims=(n, n, n), tile_nodes=0)
+    _report_plain("box%d" % n, res)
+    assert max(res.values()) < 1.0, res
+
+
+def test_abl_neutral_edge_size_vs_oracle(P, ctx):
+    """BASELINE configs[0]: the ablNeutralEdge mesh size, 125 x 125 x 25
+    elements, laterally periodic (reg_tests/test_files/ablNeutralEdge), entry by
+    entry against the oracle"""
+    res = pu.run_lowmach_case(P, ctx, dims=(125, 125, 25), tile_nodes=0,
+                              periodic=(True, True),
+                              lengths=(5000.0, 5000.0, 1000.0))
+    _report_plain("abl_125x125x25_periodic", res)
+    assert max(res.values()) < 1.0, res
+
+
+def test_peclet_function_known_answers_on_device(P, ctx):
+    """UnitTestPecletFunction.C:36-100 through nw_peclet_edge: a box with uniform
+    velocity along x and uniform nu has Peclet number u dx / nu on every x-edge
+    and 0 on the others; the reference's known (Peclet number, factor) pairs
+    must come out within its tolerance of 1e-6"""
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden",
+                                    "reference_golds.json")))["peclet_function"]
+    case = pu.Case(dims=(4, 3, 2))
+    b = case.box
+    mesh = b.make_mesh(ctx)
+    nu, dx = 1.0e-3, 1.0
+    mesh.put("density", P.NW_NODE, np.ones(b.n_nodes))
+    mesh.put("viscosity", P.NW_NODE, np.full(b.n_nodes, nu))
+    mesh.register("peclet_factor", P.NW_EDGE, 1)
+    xedge = np.abs(b.coords[b.edges[:, 1], 0] - b.coords[b.edges[:, 0], 0]) > 0.5
+    assert xedge.sum() > 0 and (~xedge).sum() > 0
+    checked = 0
+    for tag, form, a, c2 in (("classic", "classic", G["classic"]["hybridFactor"], 1.0),
+                             ("tanh", "tanh", G["tanh"]["c1"], G["tanh"]["c2"]),
+                             ("tanh_simd", "tanh", G["tanh_simd"]["c1"],
+                              G["tanh_simd"]["c2"])):
+        for pec, want in zip(G[tag]["peclet_numbers"], G[tag]["peclet_factors"]):
+            if pec < 0:
+                continue  # |u.dx| / nu is never negative; the host-side test covers it
+            u = np.zeros((b.n_nodes, 3))
+            u[:, 0] = pec * nu / dx
+            mesh.put("velocity", P.NW_NODE, u)
+            mesh.peclet_edge("viscosity", P.peclet_fn(form, a, c2))
+            got = mesh.download("peclet_factor")
+            assert np.max(np.abs(got[xedge] - want)) <= G[tag]["tolerance"], (tag, pec)
+            zero = 0.0 if form == "classic" else 0.5 * (1.0 + np.tanh((0.0 - a) / c2))
+            assert np.max(np.abs(got[~xedge] - zero)) <= G[tag]["tolerance"], (tag, pec)
+            checked += 1
+    assert checked == 8
+    mesh.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("periodic", ["0", "1"])
 def test_two_gpu_partitioned_assembly_matches_serial_oracle(periodic):

@@ -349,3 +349,28 @@ def test_geometry_interior_quad4_properties():
     np.add.at(acc, g.edges[:, 1], -area)
     j = np.arange(g.n_nodes) // 48
     assert np.max(np.abs(acc[(j > 0) & (j < 19)])) <= 1e-14
+
+
+def test_gold_peclet_function():
+    """UnitTestPecletFunction.C:36-100: known answers of the classic and tanh
+    blending functions (tolerance 1e-6 as there) -- the oracle's restatement and
+    the host build of the product's peclet_eval (edge_physics.h)"""
+    import ctypes as C
+    g = G["peclet_function"]
+    L = pu.emu_lib()
+    L.emu_peclet_eval.restype = C.c_double
+    L.emu_peclet_eval.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
+    n = 0
+    for tag, form, a, b in (("classic", "classic", g["classic"]["hybridFactor"], 1.0),
+                            ("tanh", "tanh", g["tanh"]["c1"], g["tanh"]["c2"]),
+                            ("tanh_simd", "tanh", g["tanh_simd"]["c1"], g["tanh_simd"]["c2"])):
+        c = g[tag]
+        pf = orc.peclet(form, a, b)
+        for pec, want in zip(c["peclet_numbers"], c["peclet_factors"]):
+            assert abs(orc.peclet_eval(pf, pec) - want) <= c["tolerance"], (tag, pec)
+            got = L.emu_peclet_eval(0 if form == "classic" else 1, a, b, pec)
+            assert abs(got - want) <= c["tolerance"], (tag, pec, got)
+            # the two restatements agree far tighter than the reference's bar
+            assert abs(got - orc.peclet_eval(pf, pec)) <= 1e-15
+            n += 1
+    assert n == 10
