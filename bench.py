@@ -53,10 +53,13 @@ CONT_OPTS = dict(dt=DT, gamma1=GAMMA1, noc_fac=1.0, interp_together=1.0,
 # ALGORITHMIC bytes per edge on a hex mesh (r = 1/3, z = 7)
 # momentum_uvw_fused: the Peclet factor is computed in the kernel, so its 8 B /
 # edge read (and the whole K9 pass) drop out of the algorithmic traffic
+# grad_scalar_pair: two scalar gradients in one launch; charged as two (the
+# shared area vectors / dual volumes are read once, the figure is conservative
+# for the roofline fraction only in the sense that it is the un-fused one)
 ALG_BYTES = {"peclet": 69.3333, "momentum_uvw": 122.6667,
              "momentum_uvw_fused": 114.6667, "continuity": 85.3333,
              "mdot": 72.0, "grad_scalar": 45.3333, "grad_vector": 66.6667,
-             "scalar": 93.3333}
+             "scalar": 93.3333, "grad_scalar_pair": 2 * 45.3333}
 # what a solver changes between two sweeps of one nonlinear iteration and has
 # to hand over again (the solves update velocity and pressure, the momentum
 # system's diagonal gives momentum_diag); density / viscosity and the
@@ -448,7 +451,11 @@ class Sweep:
                     s.assemble_scalar_edge(q, dq, mu, pf=self.pf_scalar, **SCAL_OPTS)
                 timed("scalar", sc, detail)
                 timed("load_complete", s.loadComplete, detail)
-                timed("grad_scalar", lambda q=q, go=go: mesh.nodal_grad_edge(q, go), detail)
+            # dkdx and dwdx: one launch (both NodalGradEdgeAlg instances of the
+            # SST system see the same, unchanged inputs)
+            (_, qa, _, _, ga), (_, qb, _, _, gb) = SST_SCALARS
+            timed("grad_scalar_pair",
+                  lambda: mesh.nodal_grad_edge_pair(qa, ga, qb, gb), detail)
 
     def sweep_bytes(self):
         """algorithmic bytes per edge of one sweep as it runs here"""
@@ -465,7 +472,7 @@ class Sweep:
     def launches_per_step(self):
         n = 5 if self.args.fuse_peclet else 6
         if self.sst:
-            n += 2 * 2
+            n += 2 + 1  # two scalar assemblies + the paired gradient
         return n
 
     def norms(self, glob):

@@ -267,6 +267,14 @@ int nw_peclet_edge(
  * nw_field_periodic_update does.  phi has dim1 components (1 or ndim), grad
  * dim1*ndim. */
 int nw_nodal_grad_edge(nw_mesh* mesh, int phi_field, int grad_field);
+/* Two scalar nodal gradients in one launch (SST: dkdx and dwdx, the
+ * NodalGradEdgeAlg instances ShearStressTransportEquationSystem runs back to
+ * back on unchanged inputs, src/ShearStressTransportEquationSystem.C:247-320):
+ * same arithmetic and result as two nw_nodal_grad_edge calls; the (L,R)
+ * records, area vectors, half-edge lists and dual volumes are staged once.
+ * Both phi fields have one component, both grad fields ndim. */
+int nw_nodal_grad_edge_pair(
+  nw_mesh* mesh, int phi_a, int grad_a, int phi_b, int grad_b);
 
 /* ------------------------------------------------------------------ */
 /* linear system (LinearSystem / HypreLinearSystem / HypreUVWLinearSystem) */

@@ -123,7 +123,7 @@ ABI_SYMBOLS = [
     "nw_mesh_get_node_permutation", "nw_geometry_interior_hex8", "nw_geometry_interior_quad4",
     "nw_geometry_interior_tet4", "nw_geometry_interior_wed6", "nw_geometry_interior_pyr5", "nw_mdot_edge",
     "nw_mdot_edge_ext", "nw_assemble_continuity_edge_ext", "nw_peclet_edge",
-    "nw_nodal_grad_edge", "nw_linsys_create", "nw_linsys_destroy",
+    "nw_nodal_grad_edge", "nw_nodal_grad_edge_pair", "nw_linsys_create", "nw_linsys_destroy",
     "nw_linsys_set_skipped_rows", "nw_linsys_build_edge_to_node_graph",
     "nw_linsys_finalize", "nw_linsys_get_sizes", "nw_linsys_get_graph",
     "nw_linsys_get_edge_slots", "nw_linsys_zero",
@@ -199,6 +199,7 @@ def lib():
         vp, C.POINTER(ContinuityOpts), C.POINTER(MdotExtraOpts)]
     L.nw_peclet_edge.argtypes = [vp, C.c_int, C.POINTER(PecletOpts)]
     L.nw_nodal_grad_edge.argtypes = [vp, C.c_int, C.c_int]
+    L.nw_nodal_grad_edge_pair.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.nw_linsys_create.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
     L.nw_linsys_destroy.argtypes = [vp]
     L.nw_linsys_set_skipped_rows.argtypes = [vp, c_i64p, C.c_int64]
@@ -452,6 +453,12 @@ class Mesh:
     def nodal_grad_edge(self, phi, grad):
         _chk(lib().nw_nodal_grad_edge(self.h, self.field_id(phi),
                                       self.field_id(grad)))
+
+    def nodal_grad_edge_pair(self, phi_a, grad_a, phi_b, grad_b):
+        """two scalar gradients in one launch (SST: dkdx, dwdx)"""
+        _chk(lib().nw_nodal_grad_edge_pair(
+            self.h, self.field_id(phi_a), self.field_id(grad_a),
+            self.field_id(phi_b), self.field_id(grad_b)))
 
     # --- shared-node exchange lists (caller-side transport) ---
     def halo_send(self, peer):

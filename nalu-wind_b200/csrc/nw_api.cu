@@ -1071,6 +1071,49 @@ nw_nodal_grad_edge(nw_mesh* mesh, int phi_field, int grad_field)
   return periodic_update(mesh, grad);
 }
 
+extern "C" int
+nw_nodal_grad_edge_pair(
+  nw_mesh* mesh, int phi_a, int grad_a, int phi_b, int grad_b)
+{
+  if (!mesh)
+    return fail(NW_ERR_ARG, "nw_nodal_grad_edge_pair: NULL mesh");
+  if (int rc = need_device(mesh->ctx, "nw_nodal_grad_edge_pair"))
+    return rc;
+  nw_field_t* phi[2] = {get_field(mesh, phi_a), get_field(mesh, phi_b)};
+  nw_field_t* grad[2] = {get_field(mesh, grad_a), get_field(mesh, grad_b)};
+  const int nd = mesh->plan.ndim;
+  for (int k = 0; k < 2; ++k)
+    if (!phi[k] || !grad[k] || phi[k]->rank != NW_NODE ||
+        grad[k]->rank != NW_NODE || phi[k]->ncomp != 1 || grad[k]->ncomp != nd)
+      return fail(
+        NW_ERR_ARG, "nw_nodal_grad_edge_pair: phi must be scalar nodal fields "
+                    "and grad nodal fields of ndim components");
+  if (grad[0] == grad[1])
+    return fail(NW_ERR_ARG, "nw_nodal_grad_edge_pair: the two outputs coincide");
+  NodeComps nc;
+  nc.c[0] = phi[0]->buf.as<double>();
+  nc.c[1] = phi[1]->buf.as<double>();
+  const double* vol = nullptr;
+  EdgeComps ec;
+  int rc;
+  if ((rc = bind(mesh, "dual_nodal_volume", NW_NODE, 1, &vol)) ||
+      (rc = bind_edge_common(mesh, ec, false, false)))
+    return rc;
+  double* out[9];
+  for (int k = 0; k < 2; ++k)
+    for (int c = 0; c < nd; ++c)
+      out[k * nd + c] = grad[k]->buf.as<double>() + (int64_t)c * grad[k]->stride;
+  NW_CUDA(launch_grad_tile(mesh->dev, 2, nc, vol, ec, out, mesh->ctx->stream));
+  for (int k = 0; k < 2; ++k) {
+    if (mesh->plan.nranks > 1)
+      if (int rc2 = node_halo_sum(mesh, grad[k]))
+        return rc2;
+    if (int rc2 = periodic_update(mesh, grad[k]))
+      return rc2;
+  }
+  return NW_OK;
+}
+
 /* ------------------------------------------------------------------ */
 /*  linear system                                                      */
 /* ------------------------------------------------------------------ */

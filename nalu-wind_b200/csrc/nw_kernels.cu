@@ -2965,10 +2965,11 @@ launch_grad_tile(
   double* const* gradOut,
   cudaStream_t s)
 {
+  /* dim1 == 2 on a 3-D mesh: two scalar fields at once (nw_nodal_grad_edge_pair) */
   if (mp.ndim == 3)
-    return dim1 == 1
-             ? launch_grad_tile_t<1, 3>(mp, phi, dualVol, ec, gradOut, s)
-             : launch_grad_tile_t<3, 3>(mp, phi, dualVol, ec, gradOut, s);
+    return dim1 == 1   ? launch_grad_tile_t<1, 3>(mp, phi, dualVol, ec, gradOut, s)
+           : dim1 == 2 ? launch_grad_tile_t<2, 3>(mp, phi, dualVol, ec, gradOut, s)
+                       : launch_grad_tile_t<3, 3>(mp, phi, dualVol, ec, gradOut, s);
   return dim1 == 1 ? launch_grad_tile_t<1, 2>(mp, phi, dualVol, ec, gradOut, s)
                    : launch_grad_tile_t<2, 2>(mp, phi, dualVol, ec, gradOut, s);
 }

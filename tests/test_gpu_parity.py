@@ -1022,6 +1022,25 @@ def test_abl_neutral_edge_size_vs_oracle(P, ctx):
     assert max(res.values()) < 1.0, res
 
 
+def test_nodal_grad_pair_equals_two_calls(P, ctx):
+    """nw_nodal_grad_edge_pair (dkdx and dwdx in one launch) gives the bits of
+    two nw_nodal_grad_edge calls, on a periodic box (periodic_field_update
+    included) and on a plain one"""
+    for periodic in ((False, False), (True, True)):
+        case = pu.Case(dims=(9, 7, 6), periodic=periodic)
+        mesh = case.box.make_mesh(ctx, tile_nodes=40)
+        pu.upload_state(P, mesh, case)
+        for nm in ("ga", "gb", "pa", "pb"):
+            mesh.register(nm, P.NW_NODE, 3)
+        mesh.nodal_grad_edge("turbulent_ke", "ga")
+        mesh.nodal_grad_edge("specific_dissipation_rate", "gb")
+        mesh.nodal_grad_edge_pair("turbulent_ke", "pa",
+                                  "specific_dissipation_rate", "pb")
+        assert np.array_equal(mesh.download("ga"), mesh.download("pa"))
+        assert np.array_equal(mesh.download("gb"), mesh.download("pb"))
+        mesh.close()
+
+
 def test_peclet_function_known_answers_on_device(P, ctx):
     """UnitTestPecletFunction.C:36-100 through nw_peclet_edge: a box with uniform
     velocity along x and uniform nu has Peclet number u dx / nu on every x-edge
