@@ -59,7 +59,8 @@ CONT_OPTS = dict(dt=DT, gamma1=GAMMA1, noc_fac=1.0, interp_together=1.0,
 ALG_BYTES = {"peclet": 69.3333, "momentum_uvw": 122.6667,
              "momentum_uvw_fused": 114.6667, "continuity": 85.3333,
              "mdot": 72.0, "grad_scalar": 45.3333, "grad_vector": 66.6667,
-             "scalar": 93.3333, "grad_scalar_pair": 2 * 45.3333}
+             "scalar": 93.3333, "grad_scalar_pair": 2 * 45.3333,
+             "scalar_pair": 2 * 93.3333}
 # what a solver changes between two sweeps of one nonlinear iteration and has
 # to hand over again (the solves update velocity and pressure, the momentum
 # system's diagonal gives momentum_diag); density / viscosity and the
@@ -93,6 +94,9 @@ def parse():
                     help="e2e leg: nw_field_upload on the compute stream instead "
                          "of the pipelined nw_field_stage / nw_field_commit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fuse-scalars", action="store_true",
+                    help="--sst: assemble the TKE and SDR systems with two "
+                         "launches instead of nw_assemble_scalar_edge_pair")
     ap.add_argument("--north-star", default=os.environ.get("NW_BENCH_NORTH_STAR", "auto"),
                     choices=["auto", "on", "off"],
                     help="the 512^3 SST strong-scaling record (auto: when N > 1)")
@@ -442,7 +446,20 @@ class Sweep:
         timed("mdot", lambda: mesh.mdot_edge(), detail)
         timed("grad_scalar", lambda: mesh.nodal_grad_edge("pressure", "dpdx_new"), detail)
         timed("grad_vector", lambda: mesh.nodal_grad_edge("velocity", "dudx_new"), detail)
-        if self.sst:
+        if self.sst and not args.no_fuse_scalars:
+            # TKE + SDR assembled in one launch (same graph, same state)
+            (na, qa_, dqa, mua, _), (nb_, qb_, dqb, mub, _) = SST_SCALARS
+            sa, sb = systems[na], systems[nb_]
+            so = dict(SCAL_OPTS, pf=self.pf_scalar)
+
+            def pair():
+                sa.zeroSystem()
+                sb.zeroSystem()
+                sa.assemble_scalar_edge_pair(qa_, dqa, mua, sb, qb_, dqb, mub, opts=so)
+            timed("scalar_pair", pair, detail)
+            timed("load_complete", sa.loadComplete, detail)
+            timed("load_complete", sb.loadComplete, detail)
+        elif self.sst:
             for nm, q, dq, mu, go in SST_SCALARS:
                 s = systems[nm]
 
@@ -472,7 +489,8 @@ class Sweep:
     def launches_per_step(self):
         n = 5 if self.args.fuse_peclet else 6
         if self.sst:
-            n += 2 + 1  # two scalar assemblies + the paired gradient
+            # scalar assemblies (one fused launch or two) + the paired gradient
+            n += (2 if self.args.no_fuse_scalars else 1) + 1
         return n
 
     def norms(self, glob):

@@ -388,6 +388,22 @@ int nw_assemble_scalar_edge(
   int dqdx_field,
   int diff_flux_coeff_field,
   const nw_scalar_opts* opts);
+/* The TKE and SDR assemblies of ShearStressTransportEquationSystem::
+ * solve_and_update in one launch (src/ShearStressTransportEquationSystem.C:
+ * 247-320: both systems are assembled from the same state -- the solves write
+ * kTmp / wTmp, update_and_clip comes after both).  Equivalent to
+ * nw_assemble_scalar_edge(ls_a, ...) followed by nw_assemble_scalar_edge(ls_b,
+ * ...): same arithmetic, same results bit for bit; what the two share
+ * (coordinates, velocity, density, edge streams, the reduction plan) is staged
+ * once per tile.  Both systems must be 1-dof hypre systems of the same mesh
+ * with the same skipped rows; when the fused tile path does not apply
+ * (atomic scatter mode, accumulation onto a non-empty system, tile too large)
+ * the two assemblies run one after the other. */
+int nw_assemble_scalar_edge_pair(
+  nw_linsys* ls_a, int q_a, int dqdx_a, int diff_flux_coeff_a,
+  const nw_scalar_opts* opts_a,
+  nw_linsys* ls_b, int q_b, int dqdx_b, int diff_flux_coeff_b,
+  const nw_scalar_opts* opts_b);
 
 typedef struct {
   double include_divu, alpha, alpha_upw, ho_upwind, relax_fac;

@@ -128,7 +128,7 @@ ABI_SYMBOLS = [
     "nw_linsys_finalize", "nw_linsys_get_sizes", "nw_linsys_get_graph",
     "nw_linsys_get_edge_slots", "nw_linsys_zero",
     "nw_linsys_set_scatter_mode", "nw_assemble_continuity_edge",
-    "nw_assemble_scalar_edge", "nw_assemble_momentum_edge",
+    "nw_assemble_scalar_edge", "nw_assemble_scalar_edge_pair", "nw_assemble_momentum_edge",
     "nw_assemble_mass_bdf_node", "nw_assemble_wall_dist_edge",
     "nw_assemble_wall_dist_node", "nw_linsys_write_preassembly_files", "nw_linsys_sum_into", "nw_linsys_reset_rows",
     "nw_linsys_apply_dirichlet_bcs", "nw_linsys_load_complete",
@@ -215,6 +215,9 @@ def lib():
                                           C.POINTER(ScalarOpts)]
     L.nw_assemble_momentum_edge.argtypes = [vp, C.c_int,
                                             C.POINTER(MomentumOpts)]
+    L.nw_assemble_scalar_edge_pair.argtypes = [
+        vp, C.c_int, C.c_int, C.c_int, C.POINTER(ScalarOpts),
+        vp, C.c_int, C.c_int, C.c_int, C.POINTER(ScalarOpts)]
     L.nw_linsys_sum_into.argtypes = [vp, C.c_int64, C.c_int, vp, vp, vp]
     L.nw_linsys_reset_rows.argtypes = [vp, C.c_int64, vp, C.c_double, C.c_double]
     L.nw_assemble_mass_bdf_node.argtypes = [vp, C.c_int, C.POINTER(MassBdfOpts)]
@@ -575,6 +578,23 @@ class LinearSystem:
         _chk(lib().nw_assemble_scalar_edge(
             self.h, m.field_id(q), m.field_id(dqdx), m.field_id(dflux),
             C.byref(o)))
+
+    def assemble_scalar_edge_pair(self, q, dqdx, dflux, other, q_b, dqdx_b,
+                                  dflux_b, opts=None, opts_b=None):
+        """this system and `other` (same graph) in one launch; opts / opts_b:
+        dicts of assemble_scalar_edge keyword options"""
+        def mk(o):
+            o = dict(o or {})
+            return ScalarOpts(o.get("alpha", 0.0), o.get("alpha_upw", 1.0),
+                              o.get("ho_upwind", 1.0), o.get("relax_fac", 1.0),
+                              1 if o.get("use_limiter", False) else 0,
+                              o.get("eps", 1e-16), o.get("pf") or peclet_fn())
+        oa, ob = mk(opts), mk(opts_b if opts_b is not None else opts)
+        m = self.mesh
+        _chk(lib().nw_assemble_scalar_edge_pair(
+            self.h, m.field_id(q), m.field_id(dqdx), m.field_id(dflux),
+            C.byref(oa), other.h, m.field_id(q_b), m.field_id(dqdx_b),
+            m.field_id(dflux_b), C.byref(ob)))
 
     def assemble_momentum_edge(self, viscosity="viscosity", include_divu=0.0,
                                alpha=0.0, alpha_upw=1.0, ho_upwind=1.0,

@@ -1588,6 +1588,63 @@ nw_assemble_scalar_edge(
 }
 
 extern "C" int
+nw_assemble_scalar_edge_pair(
+  nw_linsys* la, int q_a, int dqdx_a, int dflux_a, const nw_scalar_opts* oa,
+  nw_linsys* lb, int q_b, int dqdx_b, int dflux_b, const nw_scalar_opts* ob)
+{
+  if (int rc = ls_ready(la, "nw_assemble_scalar_edge_pair"))
+    return rc;
+  if (int rc = ls_ready(lb, "nw_assemble_scalar_edge_pair"))
+    return rc;
+  if (!oa || !ob)
+    return fail(NW_ERR_ARG, "nw_assemble_scalar_edge_pair: NULL options");
+  if (la == lb || la->mesh != lb->mesh)
+    return fail(
+      NW_ERR_ARG, "nw_assemble_scalar_edge_pair: needs two distinct systems of "
+                  "one mesh");
+  for (nw_linsys* ls : {la, lb})
+    if (ls->numDof != 1 || ls->kind != NW_LINSYS_HYPRE)
+      return fail(
+        NW_ERR_ARG, "nw_assemble_scalar_edge_pair: needs 1-dof hypre systems");
+  nw_mesh* mesh = la->mesh;
+  const int nd = mesh->plan.ndim;
+  const bool fused = la->sh == lb->sh && la->sh->lp.usable &&
+                     la->mode == NW_SCATTER_SEGMENTED &&
+                     lb->mode == NW_SCATTER_SEGMENTED &&
+                     la->state == NW_LS_LAZY_ZERO && lb->state == NW_LS_LAZY_ZERO;
+  if (fused) {
+    NodeComps nc;
+    EdgeComps ec;
+    int rc;
+    /* x, vrtm, rho, then per system q, dqdx, dflux */
+    const int ca = 2 * nd + 1, cb = ca + nd + 2;
+    if ((rc = bind(mesh, "coordinates", NW_NODE, nd, &nc.c[0])) ||
+        (rc = bind(mesh, "velocity", NW_NODE, nd, &nc.c[nd])) ||
+        (rc = bind(mesh, "density", NW_NODE, 1, &nc.c[2 * nd])) ||
+        (rc = bind_id(mesh, q_a, NW_NODE, 1, &nc.c[ca])) ||
+        (rc = bind_id(mesh, dqdx_a, NW_NODE, nd, &nc.c[ca + 1])) ||
+        (rc = bind_id(mesh, dflux_a, NW_NODE, 1, &nc.c[ca + 1 + nd])) ||
+        (rc = bind_id(mesh, q_b, NW_NODE, 1, &nc.c[cb])) ||
+        (rc = bind_id(mesh, dqdx_b, NW_NODE, nd, &nc.c[cb + 1])) ||
+        (rc = bind_id(mesh, dflux_b, NW_NODE, 1, &nc.c[cb + 1 + nd])) ||
+        (rc = bind_edge_common(mesh, ec, true, false)))
+      return rc;
+    bool launched = false;
+    NW_CUDA(launch_scalar_pair_tile(
+      mesh->dev, la->dev, lb->dev.values, lb->dev.rhs, nc, ec, *oa, *ob,
+      &launched, mesh->ctx->stream));
+    if (launched) {
+      if (int rc2 = finish_tile_assembly(la))
+        return rc2;
+      return finish_tile_assembly(lb);
+    }
+  }
+  if (int rc = nw_assemble_scalar_edge(la, q_a, dqdx_a, dflux_a, oa))
+    return rc;
+  return nw_assemble_scalar_edge(lb, q_b, dqdx_b, dflux_b, ob);
+}
+
+extern "C" int
 nw_assemble_momentum_edge(
   nw_linsys* ls, int viscosity_field, const nw_momentum_opts* opts)
 {

@@ -895,6 +895,227 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
 }
 
 /* ------------------------------------------------------------------ */
+/*  two scalar systems of one graph in one launch (SST: TKE + SDR)      */
+/* ------------------------------------------------------------------ */
+
+/* ShearStressTransportEquationSystem assembles the TKE and the SDR system
+ * from the same state (src/ShearStressTransportEquationSystem.C:247-320: both
+ * assemble_and_solve calls precede update_and_clip), with the same
+ * ScalarEdgeSolverAlg arithmetic (src/edge_kernels/ScalarEdgeSolverAlg.C:
+ * 55-206) on the same mesh and the same graph.  This kernel stages what the
+ * two assemblies share -- coordinates, velocity, density, the (L,R) records,
+ * area vectors, mass flow rates and the whole reduction plan -- once per
+ * tile: 17 node components instead of 2 x 12, one set of edge / plan streams
+ * instead of two, one CTA start-up instead of two.  One CTA of 512 threads
+ * per tile; a work item of phase 1 is (edge, system), of phase 2 (row,
+ * system); every value and rhs entry of both systems is written once, in
+ * the same order of additions as ls_tile_kernel<ScalarP> (bit-identical
+ * results, tests/test_gpu_parity.py::test_scalar_pair_equals_two_calls).
+ * Staged node components: x[ND], v[ND], rho, then per system q, dqdx[ND],
+ * diffFluxCoeff. */
+constexpr int kPairThreads = 512;
+
+template <int ND>
+struct PairSmem
+{
+  static constexpr int NC = 2 * ND + 1 + 2 * (ND + 2);
+  static constexpr int NIN = ND + 1; /* area, mdot */
+  static constexpr int NRES = 5;     /* per system: a00 a01 a10 a11 flux */
+  int nodeRegion, resStride, valsLen, ellLen, entLen, lrLen;
+  __host__ __device__ PairSmem(const MeshPlanDev& mp, const LsPlanDev& lp)
+  {
+    resStride = (mp.maxTileEdges + 1) & ~1;
+    lrLen = (mp.maxTileEdges + 3) & ~3;
+    valsLen = (lp.maxTileNnz + 3) & ~3;
+    /* row staging: values of both systems (8 B each) + deltas (4 B) */
+    const int rowRegion = 2 * valsLen + valsLen / 2;
+    const int stage = NC * mp.maxStaged;
+    nodeRegion = stage > rowRegion ? stage : rowRegion;
+    ellLen = lp.maxTileEll;
+    entLen = (lp.maxTileEnts + 3) & ~3;
+  }
+  __host__ __device__ size_t bytes() const
+  {
+    return sizeof(double) *
+             ((size_t)nodeRegion + (size_t)(NIN + 2 * NRES) * resStride) +
+           4u * (size_t)ellLen + 12u * (size_t)entLen + 4u * (size_t)lrLen;
+  }
+};
+
+template <int ND>
+__global__ void __launch_bounds__(kPairThreads, 1) scalar_pair_tile_kernel(
+  const MeshPlanDev mp,
+  const LsPlanDev lp, /* plan; values / rhs of system A */
+  double* __restrict__ valuesB,
+  double* __restrict__ rhsB,
+  const NodeComps nc,
+  const EdgeComps ec,
+  const nw_scalar_opts oA,
+  const nw_scalar_opts oB)
+{
+  using S = PairSmem<ND>;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ int32_t s_slice[kMaxTileEnts / 32 + 2];
+
+  const TileHdr h = mp.tiles[blockIdx.x];
+  const LsTileHdr lh = lp.tiles[blockIdx.x];
+  const S L(mp, lp);
+  const int stride = even_up_i(h.nOwnPad + h.nHalo);
+  const int rs = L.resStride;
+
+  double* s_node = smem;
+  double* s_in = s_node + L.nodeRegion;  /* area[ND], mdot */
+  double* s_res = s_in + S::NIN * rs;    /* [system][5][edge] */
+  double* s_vals = s_node;               /* row staging of both systems */
+  int32_t* s_delta = reinterpret_cast<int32_t*>(s_vals + 2 * L.valsLen);
+  uint32_t* s_ell = reinterpret_cast<uint32_t*>(s_res + 2 * S::NRES * rs);
+  EntInfo* s_ent = reinterpret_cast<EntInfo*>(s_ell + L.ellLen);
+  int32_t* s_row = reinterpret_cast<int32_t*>(s_ent + L.entLen);
+  int32_t* s_go = s_row + L.entLen;
+  uint32_t* s_lr = reinterpret_cast<uint32_t*>(s_go + L.entLen);
+
+  const EdgeCompSel<ND> ecomp{ec};
+  const uint32_t bEll = (uint32_t)lh.ellLen * 4u;
+  const uint32_t bEnt = round16((uint32_t)lh.nEnts * 4u);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_expect_tx(
+      &bar[0], node_copy_bytes(S::NC, h) + edge_stream_bytes(h, S::NIN));
+    mbar_expect_tx(&bar[1], bEll + 3u * bEnt);
+  }
+  __syncthreads();
+  issue_spread(S::NC + 1 + S::NIN + 4, [&](int q) {
+    if (q < S::NC)
+      node_copy<S::NC>(q, s_node, stride, nc, h, &bar[0]);
+    else if (q <= S::NC + S::NIN)
+      edge_copy(q - S::NC, s_lr, s_in, rs, mp, h, ecomp, &bar[0]);
+    else {
+      const int r = q - (S::NC + 1 + S::NIN);
+      if (r == 0 && bEll)
+        tma_load_1d(s_ell, lp.heEll + lh.ellPtr, bEll, &bar[1]);
+      else if (r == 1 && bEnt)
+        tma_load_1d(s_ent, lp.entInfo + lh.entPtr, bEnt, &bar[1]);
+      else if (r == 2 && bEnt)
+        tma_load_1d(s_row, lp.entRhsRow + lh.entPtr, bEnt, &bar[1]);
+      else if (r == 3 && bEnt)
+        tma_load_1d(s_go, lp.entGo + lh.entPtr, bEnt, &bar[1]);
+    }
+  });
+  {
+    const int nSl = (lh.nEnts + 31) >> 5;
+    if ((int)threadIdx.x <= nSl)
+      s_slice[threadIdx.x] = __ldg(lp.sliceOff + lh.slicePtr + threadIdx.x);
+  }
+  stage_halo_gather<S::NC>(s_node, stride, nc, h, mp.haloNodes);
+  stage_halo_wait();
+  mbar_wait(&bar[0], 0);
+  __syncthreads();
+
+  /* ---- phase 1: work item = (edge j, system sys) ---- */
+  for (int it = threadIdx.x; it < 2 * h.nEdges; it += blockDim.x) {
+    const int sys = it >= h.nEdges ? 1 : 0;
+    const int j = it - sys * h.nEdges;
+    const uint32_t v = s_lr[j];
+    const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
+    double av[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+      av[d] = s_in[d * rs + j];
+    const double mdot = s_in[ND * rs + j];
+    const int cq = 2 * ND + 1 + sys * (ND + 2); /* first component of the system */
+    ScalNode<ND> Ln, Rn;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      Ln.x[d] = s_node[d * stride + l];
+      Rn.x[d] = s_node[d * stride + r];
+      Ln.v[d] = s_node[(ND + d) * stride + l];
+      Rn.v[d] = s_node[(ND + d) * stride + r];
+      Ln.dq[d] = s_node[(cq + 1 + d) * stride + l];
+      Rn.dq[d] = s_node[(cq + 1 + d) * stride + r];
+    }
+    Ln.rho = s_node[2 * ND * stride + l];
+    Rn.rho = s_node[2 * ND * stride + r];
+    Ln.q = s_node[cq * stride + l];
+    Rn.q = s_node[cq * stride + r];
+    Ln.mu = s_node[(cq + 1 + ND) * stride + l];
+    Rn.mu = s_node[(cq + 1 + ND) * stride + r];
+    double res[S::NRES];
+    scalar_edge<ND>(Ln, Rn, av, mdot, sys ? oB : oA, res, res[4]);
+    double* out = s_res + sys * S::NRES * rs + j;
+#pragma unroll
+    for (int k = 0; k < S::NRES; ++k)
+      out[k * rs] = res[k];
+  }
+  mbar_wait(&bar[1], 0);
+  __syncthreads();
+
+  /* ---- phases 2+3: work item = (32-row slice, system), warp by warp ---- */
+  {
+    const int lane = threadIdx.x & 31;
+    const int nWarps = blockDim.x >> 5;
+    const int nSl = (lh.nEnts + 31) >> 5;
+    for (int p = threadIdx.x >> 5; p < 2 * nSl; p += nWarps) {
+      const int sys = p >= nSl ? 1 : 0;
+      const int sl = p - sys * nSl;
+      const int row0 = sl << 5, row = row0 + lane;
+      const double* sres = s_res + sys * S::NRES * rs;
+      double* svals = s_vals + sys * L.valsLen;
+      double* gvals = sys ? valuesB : lp.values;
+      double* grhs = sys ? rhsB : lp.rhs;
+      if (row < lh.nEnts) {
+        const int o0 = s_slice[sl], o1 = s_slice[sl + 1];
+        const uint32_t* hp = s_ell + o0 + lane;
+        const int W = (o1 - o0) >> 5;
+        const EntInfo ei = s_ent[row];
+        double* vrow = svals + ei.base;
+        double diag = 0.0, rhs = 0.0;
+        constexpr int kBlk = 4;
+        for (int w0 = 0; w0 < W; w0 += kBlk) {
+          uint32_t hv[kBlk];
+#pragma unroll
+          for (int u = 0; u < kBlk; ++u)
+            hv[u] = (w0 + u < W) ? hp[(w0 + u) * 32] : 0u;
+          double dg[kBlk], off[kBlk], rr[kBlk][1];
+#pragma unroll
+          for (int u = 0; u < kBlk; ++u)
+            if (hv[u] & kHeValid)
+              ScalarP<ND>::contrib(
+                he_side(hv[u]), sres, rs, (int)he_edge(hv[u]), dg[u], off[u],
+                rr[u]);
+#pragma unroll
+          for (int u = 0; u < kBlk; ++u)
+            if (hv[u] & kHeValid) {
+              diag += dg[u];
+              rhs += rr[u][0];
+              double* dst = vrow + he_k(hv[u]);
+              if (hv[u] & kHeDup)
+                off[u] += *dst;
+              *dst = off[u];
+            }
+        }
+        vrow[ei.diagK] = diag;
+        /* both systems write the same deltas (same graph) */
+        const int32_t delta = s_go[row] - (int32_t)ei.base;
+        for (int k = 0; k < (int)ei.nnz; ++k)
+          s_delta[ei.base + k] = delta;
+        grhs[s_row[row]] = rhs;
+      }
+      __syncwarp();
+      {
+        const int last = min(row0 + 31, lh.nEnts - 1);
+        const EntInfo e0 = s_ent[row0], e1 = s_ent[last];
+        const int end = (int)e1.base + (int)e1.nnz;
+#pragma unroll 4
+        for (int e = (int)e0.base + lane; e < end; e += 32)
+          gvals[e + s_delta[e]] = svals[e];
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ */
 /*  linear-system atomic kernel (comparison variant)                   */
 /* ------------------------------------------------------------------ */
 
@@ -3039,6 +3260,35 @@ launch_scalar_tile(
 {
   return mp.ndim == 3 ? launch_ls_tile<ScalarP<3>, 3>(mp, lp, nc, ec, o, s)
                       : launch_ls_tile<ScalarP<2>, 2>(mp, lp, nc, ec, o, s);
+}
+
+cudaError_t
+launch_scalar_pair_tile(
+  const MeshPlanDev& mp, const LsPlanDev& lpA, double* valuesB, double* rhsB,
+  const NodeComps& nc, const EdgeComps& ec, nw_scalar_opts oA,
+  nw_scalar_opts oB, bool* launched, cudaStream_t s)
+{
+  *launched = false;
+  cudaError_t e;
+  if (mp.ndim == 3) {
+    const size_t bytes = PairSmem<3>(mp, lpA).bytes();
+    if (bytes > 226 * 1024)
+      return cudaSuccess; /* the caller assembles the systems one by one */
+    if ((e = set_smem(scalar_pair_tile_kernel<3>, bytes)) != cudaSuccess)
+      return e;
+    scalar_pair_tile_kernel<3><<<mp.nTiles, kPairThreads, bytes, s>>>(
+      mp, lpA, valuesB, rhsB, nc, ec, oA, oB);
+  } else {
+    const size_t bytes = PairSmem<2>(mp, lpA).bytes();
+    if (bytes > 226 * 1024)
+      return cudaSuccess;
+    if ((e = set_smem(scalar_pair_tile_kernel<2>, bytes)) != cudaSuccess)
+      return e;
+    scalar_pair_tile_kernel<2><<<mp.nTiles, kPairThreads, bytes, s>>>(
+      mp, lpA, valuesB, rhsB, nc, ec, oA, oB);
+  }
+  *launched = true;
+  return cudaGetLastError();
 }
 
 cudaError_t

@@ -124,6 +124,14 @@ cudaError_t launch_wall_dist_node(
 cudaError_t launch_scalar_tile(
   const MeshPlanDev& mp, const LsPlanDev& lp, const NodeComps& nc,
   const EdgeComps& ec, nw_scalar_opts o, cudaStream_t s);
+/* two scalar systems sharing graph and plan (lpA: plan + values / rhs of
+ * system A); nc: x, v, rho, then per system q, dqdx, diffFluxCoeff.
+ * *launched = false (and no error): the tile does not fit one CTA's shared
+ * memory, assemble the systems one by one */
+cudaError_t launch_scalar_pair_tile(
+  const MeshPlanDev& mp, const LsPlanDev& lpA, double* valuesB, double* rhsB,
+  const NodeComps& nc, const EdgeComps& ec, nw_scalar_opts oA,
+  nw_scalar_opts oB, bool* launched, cudaStream_t s);
 cudaError_t launch_momentum_uvw_tile(
   const MeshPlanDev& mp, const LsPlanDev& lp, const NodeComps& nc,
   const EdgeComps& ec, nw_momentum_opts o, double* diagOut, cudaStream_t s);

@@ -1022,6 +1022,53 @@ def test_abl_neutral_edge_size_vs_oracle(P, ctx):
     assert max(res.values()) < 1.0, res
 
 
+def test_scalar_pair_equals_two_calls(P, ctx):
+    """nw_assemble_scalar_edge_pair (TKE + SDR systems in one launch) against
+    two nw_assemble_scalar_edge calls: same plan, same arithmetic, same order of
+    additions -- the values and right-hand sides must agree bit for bit; also
+    the fall-back (atomic mode: one after the other) and different options per
+    system"""
+    for periodic, dims in (((False, False), (11, 9, 7)), ((True, True), (9, 7, 5))):
+        case = pu.Case(dims=dims, periodic=periodic)
+        mesh = case.box.make_mesh(ctx, tile_nodes=48)
+        pu.upload_state(P, mesh, case)
+        mesh.upload("mass_flow_rate", case.oracle_mdot())
+        oa = dict(pu.SCAL_OPTS, pf=P.peclet_fn("tanh", 2.0, 1.0))
+        ob = dict(pu.SCAL_OPTS, pf=P.peclet_fn("classic", 1.0), relax_fac=0.8)
+        fa = ("turbulent_ke", "dkdx", "effective_viscosity_tke")
+        fb = ("specific_dissipation_rate", "dwdx", "effective_viscosity_sdr")
+        sysm = []
+        for _ in range(4):
+            ls = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE, 1)
+            ls.buildEdgeToNodeGraph()
+            ls.finalizeLinearSystem()
+            ls.zeroSystem()
+            sysm.append(ls)
+        a1, b1, a2, b2 = sysm
+        a1.assemble_scalar_edge(*fa, **oa)
+        b1.assemble_scalar_edge(*fb, **ob)
+        a2.assemble_scalar_edge_pair(*fa, b2, *fb, opts=oa, opts_b=ob)
+        for x, y in ((a1, a2), (b1, b2)):
+            vx, rx = x.values()
+            vy, ry = y.values()
+            assert np.array_equal(vx, vy) and np.array_equal(rx, ry)
+        # fall-back: atomic scatter mode -> the two assemblies run in turn
+        for ls in (a2, b2):
+            ls.set_scatter_mode(P.NW_SCATTER_ATOMIC)
+            ls.zeroSystem()
+        a2.assemble_scalar_edge_pair(*fa, b2, *fb, opts=oa, opts_b=ob)
+        for x, y in ((a1, a2), (b1, b2)):
+            vx, rx = x.values()
+            vy, ry = y.values()
+            sc = np.maximum(np.abs(vx), 1e-3 * np.max(np.abs(vx)))
+            assert pu.scaled_err(vy, vx, sc) < 1
+            sr = np.maximum(np.abs(rx), 1e-3 * np.max(np.abs(rx)))
+            assert pu.scaled_err(ry, rx, sr) < 1
+        for ls in sysm:
+            ls.close()
+        mesh.close()
+
+
 def test_nodal_grad_pair_equals_two_calls(P, ctx):
     """nw_nodal_grad_edge_pair (dkdx and dwdx in one launch) gives the bits of
     two nw_nodal_grad_edge calls, on a periodic box (periodic_field_update
