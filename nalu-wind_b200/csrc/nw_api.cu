@@ -1682,9 +1682,10 @@ nw_assemble_momentum_edge(
   }
   cudaStream_t s = mesh->ctx->stream;
   if (uvw) {
-    if (use_tile_path(ls, diagOut != nullptr, &rc)) {
+    /* extract_diagonal rides on the tile kernel (node-keyed pass) */
+    if (use_tile_path(ls, false, &rc)) {
       NW_CUDA(launch_momentum_uvw_tile(
-        mesh->dev, ls->dev, nc, ec, *opts, nullptr, s));
+        mesh->dev, ls->dev, nc, ec, *opts, diagOut, s));
       return finish_tile_assembly(ls);
     }
     if (rc)

@@ -669,6 +669,7 @@ template <class P>
 struct LsSmem
 {
   int nodeRegion; /* doubles: node stage, reused as row staging after phase 1 */
+  int rowRegion;  /* doubles of the row staging inside it */
   int resStride;  /* doubles per result component */
   int valsLen;    /* staged matrix values (doubles) + their int32 deltas */
   int ellLen;     /* uint32 records */
@@ -685,10 +686,13 @@ struct LsSmem
     resStride = (mp.maxTileEdges + 1) & ~1;
     lrLen = (mp.maxTileEdges + 3) & ~3;
     valsLen = (lp.maxTileNnz + 3) & ~3;
-    /* row staging: values (8 B) + value-offset deltas (4 B) */
-    const int rowRegion = valsLen + valsLen / 2;
+    /* row staging: values (8 B) + value-offset deltas (4 B), and behind it the
+     * node-keyed half-edge list of extract_diagonal (4 B records) */
+    rowRegion = valsLen + valsLen / 2;
+    const int rowAll = rowRegion + (mp.maxTileEllNode + 1) / 2 + 2;
     const int stage = P::NC * mp.maxStaged;
-    nodeRegion = stage > rowRegion ? stage : rowRegion;
+    nodeRegion = stage > rowAll ? stage : rowAll;
+    nodeRegion = (nodeRegion + 1) & ~1;
     ellLen = lp.maxTileEll;
     entLen = (lp.maxTileEnts + 3) & ~3;
   }
@@ -708,10 +712,11 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
   const typename P::Opts o)
 {
   extern __shared__ __align__(16) double smem[];
-  __shared__ __align__(8) uint64_t bar[2];
-  /* slice offsets of the tile's sliced-ELL list (fetched during the stage: a
+  __shared__ __align__(8) uint64_t bar[3];
+  /* slice offsets of the tile's sliced-ELL lists (fetched during the stage: a
    * global load at the top of phase 2 would sit on the critical path) */
   __shared__ int32_t s_slice[kMaxTileEnts / 32 + 2];
+  __shared__ int32_t s_sliceN[kMaxTileEnts / 32 + 2]; /* node-keyed (diagOut) */
   NW_PT_BEGIN(P::kPhaseId);
 
   const TileHdr h = mp.tiles[blockIdx.x];
@@ -744,6 +749,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
   if (threadIdx.x == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
+    mbar_init(&bar[2], 1);
     mbar_expect_tx(
       &bar[0], node_copy_bytes(P::NC, h, skipOwn) + edge_stream_bytes(h, nin));
     mbar_expect_tx(&bar[1], bEll + 3u * bEnt);
@@ -776,6 +782,10 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
     const int nSl = (lh.nEnts + 31) >> 5;
     if ((int)threadIdx.x <= nSl)
       s_slice[threadIdx.x] = __ldg(lp.sliceOff + lh.slicePtr + threadIdx.x);
+    const int nSlN = (h.nOwn + 31) >> 5;
+    if (lp.diagOut && (int)threadIdx.x <= nSlN)
+      s_sliceN[threadIdx.x] =
+        __ldg(mp.sliceOffNode + h.slicePtrNode + threadIdx.x);
   }
   if (!(mp.dbgSkip & 1))
     stage_halo_gather<P::NC>(s_node, stride, nc, h, mp.haloNodes);
@@ -817,6 +827,18 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
   mbar_wait(&bar[1], 0);
   __syncthreads();
   NW_PT_MARK(); /* 5: phase-1 barrier */
+  /* extract_diagonal: the node stage is dead now; the tile's node-keyed
+   * half-edge list (the gradient kernel's list) lands behind the row staging
+   * while phases 2-3 run */
+  uint32_t* s_ellN = reinterpret_cast<uint32_t*>(s_node + L.rowRegion);
+  if (lp.diagOut && threadIdx.x == 0) {
+    const uint32_t bN = (uint32_t)h.ellLenNode * 4u;
+    /* the copy overwrites shared memory the threads have just read */
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&bar[2], bN);
+    if (bN)
+      tma_load_1d(s_ellN, mp.heNodeEll + h.ellPtrNode, bN, &bar[2]);
+  }
 
   /* ---- phases 2+3, warp by warp: one thread per row reduces the row's
    * half-edges in list order, then the warp copies the staging range of its
@@ -891,6 +913,32 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
     }
   }
   NW_PT_MARK(); /* 6: phases 2+3 */
+  if (lp.diagOut) {
+    /* NGPApplyCoeff::extract_diagonal (src/SolverAlgorithm.C:87-105):
+     * diagField(node) += lhs(ix, ix) for both nodes of every edge, i.e. per
+     * node the sum of its half-edges' diagonal-block entries -- node by node
+     * (periodic slaves and Dirichlet nodes included: the reference extracts
+     * before the row is skipped or redirected), summed in list order, one
+     * writer per node instead of the reference's atomic_add */
+    mbar_wait(&bar[2], 0);
+    for (int i = threadIdx.x; i < h.nOwn; i += blockDim.x) {
+      const int sl = i >> 5;
+      const int o0 = s_sliceN[sl], o1 = s_sliceN[sl + 1];
+      const uint32_t* hp = s_ellN + o0 + (i & 31);
+      const int W = (o1 - o0) >> 5;
+      double acc = 0.0;
+      for (int w = 0; w < W; ++w) {
+        const uint32_t hv = hp[w * 32];
+        if (hv & kHeValid) {
+          double dg, off, rr[P::NR];
+          P::contrib(
+            he_side(hv), s_res, L.resStride, (int)he_edge(hv), dg, off, rr);
+          acc += dg;
+        }
+      }
+      lp.diagOut[h.node0 + i] += acc;
+    }
+  }
   NW_PT_END();
 }
 
@@ -2924,40 +2972,24 @@ template <class P, int ND>
 cudaError_t
 launch_ls_tile(
   const MeshPlanDev& mp,
-  const LsPlanDev& lp,
+  const LsPlanDev& lpIn,
   const NodeComps& nc,
   const EdgeComps& ec,
   const typename P::Opts& o,
-  cudaStream_t s)
+  cudaStream_t s,
+  double* diagOut = nullptr)
 {
+  LsPlanDev lp = lpIn;
+  lp.diagOut = diagOut;
   bool launched = false;
-  cudaError_t e = launch_ls_stream<P, ND>(mp, lp, nc, ec, o, s, &launched);
+  cudaError_t e = cudaSuccess;
+  if (!diagOut) /* the stream variant has no extract_diagonal pass */
+    e = launch_ls_stream<P, ND>(mp, lp, nc, ec, o, s, &launched);
   if (e != cudaSuccess || launched)
     return e;
   const size_t bytes = ls_tile_smem<P>(mp, lp);
   if (bytes > 227 * 1024)
     return cudaErrorInvalidConfiguration;
-  /* diagnostic: NW_TILE_CTAS=3 forces the 3-CTA (<= 85 register) build when
-   * three copies of the tile's shared memory fit */
-  static const int ctasEnv = env_int("NW_TILE_CTAS", 0);
-  if (ctasEnv == 3 && 3 * (bytes + 1024) <= 228 * 1024) {
-    e = set_smem(ls_tile_kernel<P, ND, 3>, bytes);
-    if (e != cudaSuccess)
-      return e;
-    ls_tile_kernel<P, ND, 3>
-      <<<mp.nTiles, kTileThreads, bytes, s>>>(mp, lp, nc, ec, o);
-    return cudaGetLastError();
-  }
-  /* diagnostic: NW_TILE_THREADS=384 runs 12-warp CTAs (2 per SM, <= 85
-   * registers) instead of 8-warp ones */
-  static const int thrEnv = env_int("NW_TILE_THREADS", 0);
-  if (thrEnv == 384 && 2 * (bytes + 1024) <= 228 * 1024) {
-    e = set_smem(ls_tile_kernel<P, ND, 2, 384>, bytes);
-    if (e != cudaSuccess)
-      return e;
-    ls_tile_kernel<P, ND, 2, 384><<<mp.nTiles, 384, bytes, s>>>(mp, lp, nc, ec, o);
-    return cudaGetLastError();
-  }
   e = set_smem(ls_tile_kernel<P, ND>, bytes);
   if (e != cudaSuccess)
     return e;
@@ -3298,12 +3330,12 @@ launch_momentum_uvw_tile(
   const NodeComps& nc,
   const EdgeComps& ec,
   nw_momentum_opts o,
-  double* /*diagOut*/,
+  double* diagOut,
   cudaStream_t s)
 {
   return mp.ndim == 3
-           ? launch_ls_tile<MomentumUvwP<3>, 3>(mp, lp, nc, ec, o, s)
-           : launch_ls_tile<MomentumUvwP<2>, 2>(mp, lp, nc, ec, o, s);
+           ? launch_ls_tile<MomentumUvwP<3>, 3>(mp, lp, nc, ec, o, s, diagOut)
+           : launch_ls_tile<MomentumUvwP<2>, 2>(mp, lp, nc, ec, o, s, diagOut);
 }
 
 cudaError_t

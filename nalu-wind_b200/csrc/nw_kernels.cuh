@@ -54,6 +54,9 @@ struct LsPlanDev
   double* values = nullptr;
   double* rhs = nullptr;
   int64_t rhsStride = 0; /* rows_owned + rows_shared */
+  /* NGPApplyCoeff::extract_diagonal target (nodal field, internal slots) of
+   * the current launch, or null */
+  double* diagOut = nullptr;
 };
 
 /* atomic-variant slot map, per tile-edge slot */

@@ -403,6 +403,57 @@ def test_monolithic_momentum_vs_oracle(P, ctx):
     assert pu.scaled_err(got, ud, np.abs(ud) + np.max(np.abs(ud)) * 1e-2) < 1
 
 
+@pytest.mark.parametrize("periodic", [(False, False), (True, True)])
+def test_extract_diagonal_on_the_tile_path(P, ctx, periodic):
+    """NGPApplyCoeff::extract_diagonal (src/SolverAlgorithm.C:87-105) with the
+    segregated UVW system in segmented mode: the momentum tile kernel fills the
+    nodal diagonal field in a node-keyed pass (no atomics) while assembling the
+    same matrix as without it; Dirichlet rows and periodic slaves get their
+    node's sum like in the reference (it extracts before the row is skipped).
+    Checked against the oracle's per-node sums and against the atomic path;
+    a second assembly accumulates onto the field (+=)."""
+    case = pu.Case(dims=(9, 8, 6), periodic=periodic)
+    mesh = case.box.make_mesh(ctx, tile_nodes=56)
+    pu.upload_state(P, mesh, case)
+    omdot = case.oracle_mdot()
+    opec = case.oracle_pecfac(orc.peclet("classic", 1.0))
+    mesh.upload("mass_flow_rate", omdot)
+    mesh.upload("peclet_factor", opec)
+    skipped = np.array([3, 40, 77], dtype=np.int64) if not any(periodic) else \
+        np.zeros(0, dtype=np.int64)
+    g = case.oracle_graph(skipped=skipped)
+    ud = np.zeros(case.n_nodes)
+    o = pu.oracle_momentum(case, g, omdot, opec, uvw=True, udiag=ud)
+    ov, orhs = o.get()
+    av, arhs = o.get_abs()
+    scale = np.abs(ud) + np.max(np.abs(ud)) * 1e-2
+    out = {}
+    for mode in (P.NW_SCATTER_SEGMENTED, P.NW_SCATTER_ATOMIC):
+        name = "udiag_%d" % mode
+        mesh.register(name, P.NW_NODE, 1)
+        mesh.fill(name, 0.0)
+        ls = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE_UVW, 3)
+        ls.set_scatter_mode(mode)
+        if len(skipped):
+            ls.set_skipped_rows(skipped)
+        ls.buildEdgeToNodeGraph()
+        ls.finalizeLinearSystem()
+        ls.zeroSystem()
+        ls.assemble_momentum_edge("viscosity", diag_field=name, **pu.MOM_OPTS)
+        vals, rhs = ls.values()
+        assert pu.scaled_err(vals, ov, av) < 1
+        assert pu.scaled_err(rhs, orhs, arhs) < 1
+        out[mode] = mesh.download(name)
+        assert pu.scaled_err(out[mode], ud, scale) < 1, mode
+        if mode == P.NW_SCATTER_SEGMENTED:
+            ls.zeroSystem()
+            ls.assemble_momentum_edge("viscosity", diag_field=name, **pu.MOM_OPTS)
+            twice = mesh.download(name)
+            assert pu.scaled_err(twice, 2.0 * ud, 2.0 * scale) < 1
+        ls.close()
+    mesh.close()
+
+
 def test_skipped_rows_and_accumulation(P, ctx):
     """Dirichlet rows are left untouched; a second assembly without zeroSystem
     accumulates (HypreLinearSystem.C:1394-1405: values are zeroed once per
