@@ -79,6 +79,13 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=int(os.environ.get("NW_BENCH_N", "128")),
                     help="elements per box side per GPU (BASELINE config: 128)")
+    ap.add_argument("--mesh", default="box", choices=["box", "warped", "mixed"],
+                    help="box: BASELINE configs[1] (default); warped: configs[3]-"
+                         "style curvilinear (warped + stretched) hex box whose "
+                         "edges arrive in bucket-shuffled order; mixed: "
+                         "configs[4], the reference's multiElemTypeCylinder.g "
+                         "(tet / hex / wedge / pyramid) tiled to >= 10^7 edges "
+                         "(one GPU)")
     ap.add_argument("--tile", type=int,
                     default=int(os.environ.get("NW_TILE_NODES", "0")))
     ap.add_argument("--sst", action="store_true",
@@ -198,11 +205,70 @@ def bind_to_gpu_numa_node(local):
         return {"numa_node": None, "error": str(e)[:80]}
 
 
-def build_case(P, dims, nranks, rank):
-    """per-rank part of an nx x ny x nz box, z-slab decomposition"""
+class TiledMixedMesh:
+    """BASELINE configs[4]: the reference's multiElemTypeCylinder.g (TETRA4 /
+    HEX8 / WEDGE6 / PYRAMID5; fixture tests/golden/mesh_multiElemTypeCylinder.npz)
+    repeated on a lattice of translated copies until it has >= min_edges edges.
+    Connectivity, valence distribution (tets: ~14 neighbours per row) and edge
+    order are the mesh's own; the dual geometry the edge kernels read is
+    synthetic (edge-aligned area vectors + seeded transverse part, positive
+    volumes), as in the parity tests.  One rank."""
+
+    def __init__(self, P, min_edges=10_000_000, seed=20261017):
+        m = np.load(os.path.join(ROOT, "tests", "golden",
+                                 "mesh_multiElemTypeCylinder.npz"))
+        c0, e0 = m["coords"], m["edges"].astype(np.int64)
+        n0, ne0 = len(c0), len(e0)
+        k = int(math.ceil(min_edges / ne0))
+        side = int(math.ceil(k ** (1.0 / 3.0)))
+        ext = (c0.max(0) - c0.min(0)) * 1.05
+        self.copies = k
+        shifts = np.array([[i, j, l] for l in range(side) for j in range(side)
+                           for i in range(side)][:k], dtype=np.float64) * ext
+        self.coords = np.ascontiguousarray(
+            (c0[None, :, :] + shifts[:, None, :]).reshape(-1, 3))
+        self.edges = np.ascontiguousarray(
+            (e0[None, :, :] + (np.arange(k) * n0)[:, None, None]).reshape(-1, 2)
+            .astype(np.int32))
+        n = self.n_nodes = k * n0
+        self.n_edges = k * ne0
+        self.gid = np.arange(1, n + 1, dtype=np.int64)
+        self.hid = np.arange(n, dtype=np.int64)
+        self.own_hid = self.hid
+        self.offsets = np.array([0, n], dtype=np.int64)
+        rng = np.random.default_rng(seed)
+        dx = self.coords[self.edges[:, 1]] - self.coords[self.edges[:, 0]]
+        ln = np.linalg.norm(dx, axis=1, keepdims=True)
+        self.area = np.ascontiguousarray(
+            0.3 * ln * dx + 0.05 * ln * ln * rng.standard_normal(dx.shape))
+        self.vol = (0.5 + rng.random(n)) * float(np.mean(ln)) ** 3
+        self.lengths = tuple((self.coords.max(0) - self.coords.min(0)).tolist())
+        self.coords0 = self.coords.min(0)
+        self._P = P
+
+    def make_mesh(self, ctx, tile_nodes=0):
+        return self._P.Mesh(ctx, 3, self.edges, self.hid, self.coords,
+                            tile_nodes=tile_nodes)
+
+
+def build_case(P, dims, nranks, rank, kind="box"):
+    """per-rank part of an nx x ny x nz box, z-slab decomposition (kind "box" /
+    "warped"), or the tiled mixed-element mesh (kind "mixed", one rank)"""
     synth = __import__("nalu_wind_b200.synth", fromlist=["state"])
+    if kind == "mixed":
+        assert nranks == 1, "--mesh mixed runs on one GPU"
+        box = TiledMixedMesh(P)
+        fields = synth.state_chunked(
+            box.coords - box.coords0, box.gid, box.lengths, DT, GAMMA1,
+            threads=int(os.environ.get("NW_HOST_THREADS", "0")) or None)
+        fields["dual_nodal_volume"] = box.vol
+        return box, fields
     nx, ny, nz = dims
-    box = P.BoxMesh(nx, ny, nz, nranks=nranks, rank=rank)
+    if kind == "warped":
+        box = P.BoxMesh(nx, ny, nz, nranks=nranks, rank=rank, warp=0.15,
+                        zstretch=1.1, shuffle_bucket=512)
+    else:
+        box = P.BoxMesh(nx, ny, nz, nranks=nranks, rank=rank)
     fields = synth.state_chunked(box.coords, box.gid,
                                  (float(nx), float(ny), float(nz)), DT, GAMMA1,
                                  threads=int(os.environ.get("NW_HOST_THREADS", "0")) or None)
@@ -337,12 +403,19 @@ def main_reference(args):
 
 def workload_config(args, n_gpus):
     n = args.n
+    mesh = {"box": "generated %dx%dx%d hex box (BASELINE configs[1]: %d^3 per "
+                   "GPU)" % (n, n, n * n_gpus, n),
+            "warped": "generated %dx%dx%d curvilinear hex box (warp 0.15, "
+                      "z-stretch 1.1, edges delivered in bucket-shuffled order; "
+                      "BASELINE configs[3]-style)" % (n, n, n * n_gpus),
+            "mixed": "reg_tests/mesh/multiElemTypeCylinder.g (tet / hex / wedge "
+                     "/ pyramid) tiled to >= 10^7 edges, synthetic dual geometry "
+                     "(BASELINE configs[4])"}[getattr(args, "mesh", "box")]
     return {
-        "workload": "generated %dx%dx%d hex box (BASELINE configs[1]: %d^3 per "
-                    "GPU), low-Mach edge sweep: Peclet + momentum(UVW) + "
+        "workload": "%s, low-Mach edge sweep: Peclet + momentum(UVW) + "
                     "continuity + mdot + grad(p) + grad(u)%s; fp64; z-slab "
                     "partition over %d GPU(s)" % (
-                        n, n, n * n_gpus, n,
+                        mesh,
                         " + k/omega scalar assemblies + gradients" if args.sst else "",
                         n_gpus),
         "scatter": args.mode,
@@ -357,10 +430,10 @@ def workload_config(args, n_gpus):
 class Sweep:
     """one rank's mesh, fields, linear systems and the sweep over them"""
 
-    def __init__(self, P, ctx, args, dims, world, rank, sst, torch):
+    def __init__(self, P, ctx, args, dims, world, rank, sst, torch, kind="box"):
         self.P, self.ctx, self.args, self.sst, self.torch = P, ctx, args, sst, torch
         t0 = time.time()
-        self.box, self.fields = build_case(P, dims, world, rank)
+        self.box, self.fields = build_case(P, dims, world, rank, kind)
         t1 = time.time()
         box = self.box
         self.mesh = mesh = box.make_mesh(ctx, tile_nodes=args.tile)
@@ -397,6 +470,11 @@ class Sweep:
             ls.finalizeLinearSystem()
             self.systems[name] = ls
         t3 = time.time()
+        # r = nodes per edge, z = non-zeros per row: the mesh's own figures for
+        # the general byte formulas of BASELINE.md section 4
+        sz = self.systems["continuity"].sizes
+        self.r = box.n_nodes / max(1, box.n_edges)
+        self.z = sz.num_nonzeros_owned / max(1, sz.num_rows_owned)
         self.setup_s = {"mesh_generation_and_state": t1 - t0, "mesh_plan": t2 - t1,
                         "fields_and_linear_systems": t3 - t2}
         self.pf = P.peclet_fn("classic", 1.0)
@@ -474,16 +552,30 @@ class Sweep:
             timed("grad_scalar_pair",
                   lambda: mesh.nodal_grad_edge_pair(qa, ga, qb, gb), detail)
 
+    def alg_bytes(self):
+        """ALGORITHMIC bytes per edge of every kernel (BASELINE.md section 4,
+        general formulas with this mesh's r and z; a hex box gives ALG_BYTES)"""
+        r, z = self.r, self.z
+        b = {"mdot": 96 * r + 40, "grad_scalar": 40 * r + 32,
+             "grad_vector": 104 * r + 32, "peclet": 64 * r + 48,
+             "continuity": (96 + 8 * (z + 1)) * r + 32,
+             "scalar": (96 + 8 * (z + 1)) * r + 40,
+             "momentum_uvw": (144 + 8 * (z + 3)) * r + 48}
+        b["momentum_uvw_fused"] = b["momentum_uvw"] - 8.0
+        b["grad_scalar_pair"] = 2 * b["grad_scalar"]
+        b["scalar_pair"] = 2 * b["scalar"]
+        return b
+
     def sweep_bytes(self):
         """algorithmic bytes per edge of one sweep as it runs here"""
         a = self.args
-        b = (ALG_BYTES["momentum_uvw_fused" if a.fuse_peclet else "momentum_uvw"] +
-             ALG_BYTES["continuity"] + ALG_BYTES["mdot"] +
-             ALG_BYTES["grad_scalar"] + ALG_BYTES["grad_vector"])
+        B = self.alg_bytes()
+        b = (B["momentum_uvw_fused" if a.fuse_peclet else "momentum_uvw"] +
+             B["continuity"] + B["mdot"] + B["grad_scalar"] + B["grad_vector"])
         if not a.fuse_peclet:
-            b += ALG_BYTES["peclet"]
+            b += B["peclet"]
         if self.sst:
-            b += 2 * (ALG_BYTES["scalar"] + ALG_BYTES["grad_scalar"])
+            b += 2 * (B["scalar"] + B["grad_scalar"])
         return b
 
     def launches_per_step(self):
@@ -588,7 +680,10 @@ def main():
             raise SystemExit(3)
 
     n = args.n
-    sw = Sweep(P, ctx, args, (n, n, n * world), world, rank, args.sst, torch)
+    if args.mesh == "mixed" and world > 1:
+        raise SystemExit("bench.py: --mesh mixed runs on one GPU")
+    sw = Sweep(P, ctx, args, (n, n, n * world), world, rank, args.sst, torch,
+               kind=args.mesh)
     box, mesh, systems = sw.box, sw.mesh, sw.systems
 
     # ---------------- device-resident throughput ("value") ----------------
@@ -618,7 +713,8 @@ def main():
     mom_ms = float(np.mean([a.elapsed_time(b) for a, b in kev["momentum_uvw"]]))
     peak, peak_src = measured_peak()
     mom_key = "momentum_uvw_fused" if args.fuse_peclet else "momentum_uvw"
-    ALG_BYTES_RUN = dict(ALG_BYTES, momentum_uvw=ALG_BYTES[mom_key])
+    AB = sw.alg_bytes()
+    ALG_BYTES_RUN = dict(AB, momentum_uvw=AB[mom_key])
     ach = ALG_BYTES_RUN["momentum_uvw"] * edges_local / (mom_ms * 1e-3) / 1e9
     sweep_bytes = sw.sweep_bytes()
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel
@@ -626,7 +722,7 @@ def main():
     # default tile); null for any other configuration
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic_momentum_uvw.json")
-    if os.path.exists(tp) and args.n == 128 and not args.tile:
+    if os.path.exists(tp) and args.n == 128 and not args.tile and args.mesh == "box":
         try:
             traffic = json.load(open(tp)).get(mom_key, {}).get(
                 "dram_bytes_per_launch")

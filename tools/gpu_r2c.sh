@@ -10,7 +10,7 @@ TAG=${1:-r02c}; shift || true
 echo "=== pytest -m gpu"
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; tail -4 gpurun_out/${TAG}_pytest_gpu.log
 i=0
-for v in "" "$@"; do
+for v in "$@"; do
   name=${TAG}_bench_v$i
   echo "=== bench variant $i: [$v]"
   env $v timeout 300 python bench.py --steps 20 --warmup 5 --detail --sst --no-cpu-baseline > gpurun_out/$name.json 2> gpurun_out/$name.detail.txt
