@@ -398,15 +398,22 @@ struct ContinuityP
     n.p = ld(3 * ND + 1, i);
     n.ud = ld(3 * ND + 2, i);
   }
-  template <class LD>
-  __device__ __forceinline__ static void compute(
-    const LD& ld, int l, int r, const double* av, double, double,
+  using Node = ContNode<ND>;
+  __device__ __forceinline__ static void compute_n(
+    const Node& L, const Node& R, const double* av, double, double,
     const Opts& o, double* res)
   {
-    ContNode<ND> L, R;
+    continuity_edge<ND>(L, R, av, o, res[0], res[1]);
+  }
+  template <class LD>
+  __device__ __forceinline__ static void compute(
+    const LD& ld, int l, int r, const double* av, double m, double pf,
+    const Opts& o, double* res)
+  {
+    Node L, R;
     load(ld, l, L);
     load(ld, r, R);
-    continuity_edge<ND>(L, R, av, o, res[0], res[1]);
+    compute_n(L, R, av, m, pf, o, res);
   }
   /* contribution of edge j to the row of its `side` node, read from the
    * phase-1 results s_res[k * rs + j] */
@@ -452,20 +459,40 @@ struct WallDistP
   static constexpr bool kNeedsMdot = false;
   static constexpr bool kNeedsPec = false;
   using Opts = nw_wall_dist_opts_;
+  struct Node
+  {
+    double x[ND];
+  };
   template <class LD>
-  __device__ __forceinline__ static void compute(
-    const LD& ld, int l, int r, const double* av, double, double, const Opts&,
+  __device__ __forceinline__ static void load(const LD& ld, int i, Node& n)
+  {
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+      n.x[d] = ld(d, i);
+  }
+  __device__ __forceinline__ static void compute_n(
+    const Node& L, const Node& R, const double* av, double, double, const Opts&,
     double* res)
   {
     double asq = 0.0, axdx = 0.0;
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
-      const double dxj = ld(d, r) - ld(d, l);
+      const double dxj = R.x[d] - L.x[d];
       asq += av[d] * av[d];
       axdx += av[d] * dxj;
     }
     /* an exact divide: this kernel is nowhere near any arithmetic limit */
     res[0] = asq / axdx;
+  }
+  template <class LD>
+  __device__ __forceinline__ static void compute(
+    const LD& ld, int l, int r, const double* av, double m, double pf,
+    const Opts& o, double* res)
+  {
+    Node L, R;
+    load(ld, l, L);
+    load(ld, r, R);
+    compute_n(L, R, av, m, pf, o, res);
   }
   __device__ __forceinline__ static void contrib(
     uint32_t, const double* s_res, int, int j, double& diag, double& off,
@@ -515,15 +542,22 @@ struct ScalarP
     n.rho = ld(3 * ND + 1, i);
     n.mu = ld(3 * ND + 2, i);
   }
-  template <class LD>
-  __device__ __forceinline__ static void compute(
-    const LD& ld, int l, int r, const double* av, double mdot, double,
+  using Node = ScalNode<ND>;
+  __device__ __forceinline__ static void compute_n(
+    const Node& L, const Node& R, const double* av, double mdot, double,
     const Opts& o, double* res)
   {
-    ScalNode<ND> L, R;
+    scalar_edge<ND>(L, R, av, mdot, o, res, res[4]);
+  }
+  template <class LD>
+  __device__ __forceinline__ static void compute(
+    const LD& ld, int l, int r, const double* av, double mdot, double pf,
+    const Opts& o, double* res)
+  {
+    Node L, R;
     load(ld, l, L);
     load(ld, r, R);
-    scalar_edge<ND>(L, R, av, mdot, o, res, res[4]);
+    compute_n(L, R, av, mdot, pf, o, res);
   }
   __device__ __forceinline__ static void contrib(
     uint32_t side, const double* s_res, int rs, int j, double& diag,
@@ -578,14 +612,21 @@ struct MomentumUvwP
     n.rho = ld(2 * ND + ND * ND + 1, i);
     n.mask = ld(2 * ND + ND * ND + 2, i);
   }
+  using Node = MomNode<ND>;
   template <class LD>
   __device__ __forceinline__ static void compute(
     const LD& ld, int l, int r, const double* av, double mdot, double pecfac,
     const Opts& o, double* res)
   {
-    MomNode<ND> L, R;
+    Node L, R;
     load(ld, l, L);
     load(ld, r, R);
+    compute_n(L, R, av, mdot, pecfac, o, res);
+  }
+  __device__ __forceinline__ static void compute_n(
+    const Node& L, const Node& R, const double* av, double mdot, double pecfac,
+    const Opts& o, double* res)
+  {
     if (o.fuse_peclet) {
       /* MomentumEdgePecletAlg fused (src/edge_kernels/MomentumEdgePecletAlg.C:74-101) */
       PecNode<ND> pl, pr;
@@ -796,7 +837,44 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
   NW_PT_MARK(); /* 3: stage wait */
 
   /* ---- phase 1: per-edge physics, entirely out of shared memory ---- */
-  {
+  if (mp.dbgSkip & 16) {
+    /* experiment: three consecutive tile-edges per thread.  The list is sorted
+     * by (L, R), so the three usually share their L node, whose state is then
+     * read from shared memory once instead of three times */
+    const SmemLd ld{s_node, stride};
+    for (int base = 3 * (int)threadIdx.x; base < h.nEdges; base += 3 * blockDim.x) {
+      typename P::Node Ln;
+      int lprev = -1;
+#pragma unroll 1
+      for (int u = 0; u < 3; ++u) {
+        const int j = base + u;
+        if (j >= h.nEdges)
+          break;
+        const uint32_t v = s_lr[j];
+        const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
+        if (l != lprev) {
+          P::load(ld, l, Ln);
+          lprev = l;
+        }
+        typename P::Node Rn;
+        P::load(ld, r, Rn);
+        double av[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+          av[d] = s_res[d * L.resStride + j];
+        double mdot = 0.0, pecfac = 0.0;
+        if (P::kNeedsMdot)
+          mdot = s_res[kMdot * L.resStride + j];
+        if (hasPec)
+          pecfac = s_res[kPec * L.resStride + j];
+        double res[P::NRES];
+        P::compute_n(Ln, Rn, av, mdot, pecfac, o, res);
+#pragma unroll
+        for (int k = 0; k < P::NRES; ++k)
+          s_res[k * L.resStride + j] = res[k];
+      }
+    }
+  } else {
     const SmemLd ld{s_node, stride};
     for (int j = threadIdx.x; j < h.nEdges; j += blockDim.x) {
       const uint32_t v = s_lr[j];
