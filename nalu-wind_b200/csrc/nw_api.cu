@@ -1470,13 +1470,17 @@ finish_tile_assembly(nw_linsys* ls)
   return NW_OK;
 }
 
-/* decide the path for an edge assembly; returns 1 for the tile kernel */
+/* decide the path for an edge assembly; returns 1 for the tile kernel.
+ * policy: the kernel's policy id (ls_tile_fits): a user-chosen tile size or a
+ * high-valence mesh whose tile does not fit one CTA's shared memory takes the
+ * atomic path instead of failing at launch */
 static int
-use_tile_path(nw_linsys* ls, bool needsDiagExtract, int* rcOut)
+use_tile_path(nw_linsys* ls, bool needsDiagExtract, int* rcOut, int policy)
 {
   *rcOut = NW_OK;
   const bool tile = ls->mode == NW_SCATTER_SEGMENTED && ls->sh->lp.usable &&
-                    ls->state == NW_LS_LAZY_ZERO && !needsDiagExtract;
+                    ls->state == NW_LS_LAZY_ZERO && !needsDiagExtract &&
+                    ls_tile_fits(ls->mesh->dev, ls->dev, policy);
   if (tile)
     return 1;
   if (ls->state != NW_LS_ACCUM)
@@ -1504,7 +1508,7 @@ nw_assemble_continuity_edge(nw_linsys* ls, const nw_continuity_opts* opts)
       (rc = bind_edge_common(mesh, ec, false, false)))
     return rc;
   cudaStream_t s = mesh->ctx->stream;
-  if (use_tile_path(ls, false, &rc)) {
+  if (use_tile_path(ls, false, &rc, 0)) {
     NW_CUDA(launch_continuity_tile(mesh->dev, ls->dev, nc, ec, *opts, s));
     return finish_tile_assembly(ls);
   }
@@ -1576,7 +1580,7 @@ nw_assemble_scalar_edge(
       (rc = bind_edge_common(mesh, ec, true, false)))
     return rc;
   cudaStream_t s = mesh->ctx->stream;
-  if (use_tile_path(ls, false, &rc)) {
+  if (use_tile_path(ls, false, &rc, 1)) {
     NW_CUDA(launch_scalar_tile(mesh->dev, ls->dev, nc, ec, *opts, s));
     return finish_tile_assembly(ls);
   }
@@ -1683,7 +1687,7 @@ nw_assemble_momentum_edge(
   cudaStream_t s = mesh->ctx->stream;
   if (uvw) {
     /* extract_diagonal rides on the tile kernel (node-keyed pass) */
-    if (use_tile_path(ls, false, &rc)) {
+    if (use_tile_path(ls, false, &rc, 2)) {
       NW_CUDA(launch_momentum_uvw_tile(
         mesh->dev, ls->dev, nc, ec, *opts, diagOut, s));
       return finish_tile_assembly(ls);
@@ -1836,7 +1840,7 @@ nw_assemble_wall_dist_edge(nw_linsys* ls)
       (rc = bind_edge_common(mesh, ec, false, false)))
     return rc;
   cudaStream_t s = mesh->ctx->stream;
-  if (use_tile_path(ls, false, &rc)) {
+  if (use_tile_path(ls, false, &rc, 7)) {
     NW_CUDA(launch_wall_dist_tile(mesh->dev, ls->dev, nc, ec, s));
     return finish_tile_assembly(ls);
   }

@@ -3372,6 +3372,30 @@ launch_scalar_tile(
                       : launch_ls_tile<ScalarP<2>, 2>(mp, lp, nc, ec, o, s);
 }
 
+/* does the tile kernel of a policy fit one CTA's shared memory on this mesh /
+ * graph?  (0 continuity, 1 scalar, 2 momentum UVW, 7 wall distance; the
+ * kPhaseId of the policies) */
+bool
+ls_tile_fits(const MeshPlanDev& mp, const LsPlanDev& lp, int policy)
+{
+  size_t b = 0;
+  const bool d3 = mp.ndim == 3;
+  switch (policy) {
+  case 0:
+    b = d3 ? ls_tile_smem<ContinuityP<3>>(mp, lp) : ls_tile_smem<ContinuityP<2>>(mp, lp);
+    break;
+  case 1:
+    b = d3 ? ls_tile_smem<ScalarP<3>>(mp, lp) : ls_tile_smem<ScalarP<2>>(mp, lp);
+    break;
+  case 2:
+    b = d3 ? ls_tile_smem<MomentumUvwP<3>>(mp, lp) : ls_tile_smem<MomentumUvwP<2>>(mp, lp);
+    break;
+  default:
+    b = d3 ? ls_tile_smem<WallDistP<3>>(mp, lp) : ls_tile_smem<WallDistP<2>>(mp, lp);
+  }
+  return b <= 227 * 1024;
+}
+
 cudaError_t
 launch_scalar_pair_tile(
   const MeshPlanDev& mp, const LsPlanDev& lpA, double* valuesB, double* rhsB,

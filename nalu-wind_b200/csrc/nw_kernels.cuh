@@ -127,6 +127,9 @@ cudaError_t launch_wall_dist_node(
 cudaError_t launch_scalar_tile(
   const MeshPlanDev& mp, const LsPlanDev& lp, const NodeComps& nc,
   const EdgeComps& ec, nw_scalar_opts o, cudaStream_t s);
+/* shared-memory check of a policy's tile kernel (0 continuity, 1 scalar,
+ * 2 momentum UVW, 7 wall distance): false -> use the atomic path */
+bool ls_tile_fits(const MeshPlanDev& mp, const LsPlanDev& lp, int policy);
 /* two scalar systems sharing graph and plan (lpA: plan + values / rhs of
  * system A); nc: x, v, rho, then per system q, dqdx, diffFluxCoeff.
  * *launched = false (and no error): the tile does not fit one CTA's shared

@@ -94,6 +94,11 @@ public:
   Realm& operator=(const Realm&) = delete;
 
   int spatial_dimension() const { return ndim_; }
+  /* Realm::periodic_field_update (src/Realm.C:3090-3100) */
+  void periodic_field_update(const std::string& field)
+  {
+    nw_check(nw_field_periodic_update(mesh_, field_ordinal(field)));
+  }
   nw_mesh* mesh() { return mesh_; }
   nw_ctx* ctx() { return ctx_; }
 
@@ -423,7 +428,7 @@ public:
       diffFluxCoeff_(diffFluxCoeff)
   {
   }
-  void execute() override
+  nw_scalar_opts options() const
   {
     nw_scalar_opts o;
     o.alpha = realm_.get_alpha_factor(dofName_);
@@ -433,9 +438,27 @@ public:
     o.use_limiter = realm_.primitive_uses_limiter(dofName_) ? 1 : 0;
     o.eps = 1.0e-16;
     o.pf = realm_.peclet_function(dofName_);
+    return o;
+  }
+  void execute() override
+  {
+    const nw_scalar_opts o = options();
     nw_check(nw_assemble_scalar_edge(
       eqSystem_->linsys_->handle(), realm_.field_ordinal(dofName_),
       realm_.field_ordinal(dqdx_), realm_.field_ordinal(diffFluxCoeff_), &o));
+  }
+  /* this algorithm and `other` (another scalar of the same mesh and graph,
+   * assembled from the same state: SST's TKE + SDR) in one launch; same result
+   * as execute() on both */
+  void execute_with(ScalarEdgeSolverAlg& other)
+  {
+    const nw_scalar_opts oa = options(), ob = other.options();
+    nw_check(nw_assemble_scalar_edge_pair(
+      eqSystem_->linsys_->handle(), realm_.field_ordinal(dofName_),
+      realm_.field_ordinal(dqdx_), realm_.field_ordinal(diffFluxCoeff_), &oa,
+      other.eqSystem_->linsys_->handle(), realm_.field_ordinal(other.dofName_),
+      realm_.field_ordinal(other.dqdx_),
+      realm_.field_ordinal(other.diffFluxCoeff_), &ob));
   }
 
 private:
@@ -537,6 +560,17 @@ public:
   {
     nw_check(nw_nodal_grad_edge(
       realm_.mesh(), realm_.field_ordinal(phi_), realm_.field_ordinal(gradPhi_)));
+  }
+
+  /* the SST system's dkdx and dwdx drivers in one launch (same result as the
+   * two execute() calls; src/ShearStressTransportEquationSystem.C:247-320) */
+  static void execute_pair(
+    Realm& realm, const std::string& phiA, const std::string& gradA,
+    const std::string& phiB, const std::string& gradB)
+  {
+    nw_check(nw_nodal_grad_edge_pair(
+      realm.mesh(), realm.field_ordinal(phiA), realm.field_ordinal(gradA),
+      realm.field_ordinal(phiB), realm.field_ordinal(gradB)));
   }
 
 private:
