@@ -207,8 +207,14 @@ round16(uint32_t bytes)
  * different warps back to back (r02b_microbench_stage_layouts.txt, V4). */
 template <class F>
 __device__ __forceinline__ void
-issue_spread(int nCopies, F&& copy)
+issue_spread(int nCopies, F&& copy, int mode = 0)
 {
+  if (mode & 32) { /* experiment: all copies from thread 0 */
+    if (threadIdx.x == 0)
+      for (int q = 0; q < nCopies; ++q)
+        copy(q);
+    return;
+  }
   if ((threadIdx.x & 31) == 0)
     for (int q = threadIdx.x >> 5; q < nCopies; q += blockDim.x >> 5)
       copy(q);
@@ -245,10 +251,15 @@ stage_halo_gather(
   int stride,
   const NodeComps& nc,
   const TileHdr& h,
-  const int32_t* __restrict__ haloNodes)
+  const int32_t* __restrict__ haloNodes,
+  int mode = 0)
 {
   const int32_t* halo = haloNodes + h.haloPtr;
-  for (int k = threadIdx.x; k < h.nHalo; k += blockDim.x) {
+  /* experiment (mode & 64): warp 0 does not gather */
+  const int t0 = (mode & 64) ? 32 : 0;
+  if ((int)threadIdx.x < t0)
+    return;
+  for (int k = threadIdx.x - t0; k < h.nHalo; k += blockDim.x - t0) {
     const int32_t g = __ldg(halo + k);
 #pragma unroll
     for (int c = 0; c < NC; ++c)
@@ -817,7 +828,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
       else if (r == 3 && bEnt)
         tma_load_1d(s_go, lp.entGo + lh.entPtr, bEnt, &bar[1]);
     }
-  });
+  }, mp.dbgSkip);
   NW_PT_MARK(); /* 1: TMA issue */
   {
     const int nSl = (lh.nEnts + 31) >> 5;
@@ -829,7 +840,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
         __ldg(mp.sliceOffNode + h.slicePtrNode + threadIdx.x);
   }
   if (!(mp.dbgSkip & 1))
-    stage_halo_gather<P::NC>(s_node, stride, nc, h, mp.haloNodes);
+    stage_halo_gather<P::NC>(s_node, stride, nc, h, mp.haloNodes, mp.dbgSkip);
   NW_PT_MARK(); /* 2: halo gather */
   stage_halo_wait();
   mbar_wait(&bar[0], 0);
@@ -837,44 +848,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
   NW_PT_MARK(); /* 3: stage wait */
 
   /* ---- phase 1: per-edge physics, entirely out of shared memory ---- */
-  if (mp.dbgSkip & 16) {
-    /* experiment: three consecutive tile-edges per thread.  The list is sorted
-     * by (L, R), so the three usually share their L node, whose state is then
-     * read from shared memory once instead of three times */
-    const SmemLd ld{s_node, stride};
-    for (int base = 3 * (int)threadIdx.x; base < h.nEdges; base += 3 * blockDim.x) {
-      typename P::Node Ln;
-      int lprev = -1;
-#pragma unroll 1
-      for (int u = 0; u < 3; ++u) {
-        const int j = base + u;
-        if (j >= h.nEdges)
-          break;
-        const uint32_t v = s_lr[j];
-        const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
-        if (l != lprev) {
-          P::load(ld, l, Ln);
-          lprev = l;
-        }
-        typename P::Node Rn;
-        P::load(ld, r, Rn);
-        double av[ND];
-#pragma unroll
-        for (int d = 0; d < ND; ++d)
-          av[d] = s_res[d * L.resStride + j];
-        double mdot = 0.0, pecfac = 0.0;
-        if (P::kNeedsMdot)
-          mdot = s_res[kMdot * L.resStride + j];
-        if (hasPec)
-          pecfac = s_res[kPec * L.resStride + j];
-        double res[P::NRES];
-        P::compute_n(Ln, Rn, av, mdot, pecfac, o, res);
-#pragma unroll
-        for (int k = 0; k < P::NRES; ++k)
-          s_res[k * L.resStride + j] = res[k];
-      }
-    }
-  } else {
+  {
     const SmemLd ld{s_node, stride};
     for (int j = threadIdx.x; j < h.nEdges; j += blockDim.x) {
       const uint32_t v = s_lr[j];

@@ -313,6 +313,10 @@ def test_fuzz_random_graphs_on_device(P, ctx, seed):
     mag = np.abs(orc.nodal_grad_edge(
         3, 3, case.edges, np.abs(f["velocity"]), np.abs(case.area),
         f["dual_nodal_volume"], case.n_nodes)) + 1e-3 * (np.max(np.abs(ref)) + 1e-300)
+    if np.any(b.hid != b.own_hid):
+        # NodalGradAlgDriver::post_work: periodic_field_update on the aliases
+        ref = pu.periodic_field_update(ref, b.hid, b.own_hid)
+        mag = pu.periodic_field_update(mag, b.hid, b.own_hid)
     assert pu.scaled_err(got.reshape(ref.shape), ref, mag) < 1
     oc = pu.oracle_continuity(case, g)
     om = pu.oracle_momentum(case, g, omdot, opec, uvw=True)
