@@ -101,9 +101,13 @@ def parse():
                     help="e2e leg: nw_field_upload on the compute stream instead "
                          "of the pipelined nw_field_stage / nw_field_commit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-fuse-scalars", action="store_true",
-                    help="--sst: assemble the TKE and SDR systems with two "
-                         "launches instead of nw_assemble_scalar_edge_pair")
+    ap.add_argument("--fuse-scalars", dest="no_fuse_scalars", action="store_false",
+                    default=True,
+                    help="--sst: assemble the TKE and SDR systems through "
+                         "nw_assemble_scalar_edge_pair (one launch with "
+                         "NW_SCALAR_PAIR_FUSED=1; measured slower, see DESIGN.md)")
+    ap.add_argument("--no-fuse-scalars", dest="no_fuse_scalars", action="store_true",
+                    help="(default) two scalar assembly launches")
     ap.add_argument("--north-star", default=os.environ.get("NW_BENCH_NORTH_STAR", "auto"),
                     choices=["auto", "on", "off"],
                     help="the 512^3 SST strong-scaling record (auto: when N > 1)")

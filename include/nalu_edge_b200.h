@@ -396,9 +396,12 @@ int nw_assemble_scalar_edge(
  * ...): same arithmetic, same results bit for bit; what the two share
  * (coordinates, velocity, density, edge streams, the reduction plan) is staged
  * once per tile.  Both systems must be 1-dof hypre systems of the same mesh
- * with the same skipped rows; when the fused tile path does not apply
- * (atomic scatter mode, accumulation onto a non-empty system, tile too large)
- * the two assemblies run one after the other. */
+ * with the same skipped rows.  The fused kernel (one 512-thread CTA per tile,
+ * ~150 KB of shared memory) is opt-in, NW_SCALAR_PAIR_FUSED=1: on a B200 it
+ * measured slower than the two launches (one CTA per SM leaves the staging
+ * latency uncovered); by default, and whenever the fused
+ * path does not apply (atomic scatter mode, accumulation onto a non-empty
+ * system, tile too large), the two assemblies run one after the other. */
 int nw_assemble_scalar_edge_pair(
   nw_linsys* ls_a, int q_a, int dqdx_a, int diff_flux_coeff_a,
   const nw_scalar_opts* opts_a,

@@ -1612,7 +1612,18 @@ nw_assemble_scalar_edge_pair(
         NW_ERR_ARG, "nw_assemble_scalar_edge_pair: needs 1-dof hypre systems");
   nw_mesh* mesh = la->mesh;
   const int nd = mesh->plan.ndim;
-  const bool fused = la->sh == lb->sh && la->sh->lp.usable &&
+  /* The fused kernel stages 17 node components + both systems' results for
+   * one tile: ~150 KB of shared memory, one 512-thread CTA per SM.  Measured
+   * (profiles/r02f_bench_sst*.detail.txt, 128^3): 0.691 ms against 2 x 0.312
+   * ms for the two single launches -- with one CTA per SM nothing covers the
+   * staging latency of a tile, which costs more than the shared staging
+   * saves.  It therefore runs only on request (NW_SCALAR_PAIR_FUSED=1); the
+   * default is the two assemblies in turn. */
+  static const bool wantFused = [] {
+    const char* e = getenv("NW_SCALAR_PAIR_FUSED");
+    return e && e[0] == '1';
+  }();
+  const bool fused = wantFused && la->sh == lb->sh && la->sh->lp.usable &&
                      la->mode == NW_SCATTER_SEGMENTED &&
                      lb->mode == NW_SCATTER_SEGMENTED &&
                      la->state == NW_LS_LAZY_ZERO && lb->state == NW_LS_LAZY_ZERO;

@@ -259,6 +259,15 @@ stage_halo_gather(
   const int t0 = (mode & 64) ? 32 : 0;
   if ((int)threadIdx.x < t0)
     return;
+  if (mode & 128) { /* experiment: load + store through registers */
+    for (int k = threadIdx.x - t0; k < h.nHalo; k += blockDim.x - t0) {
+      const int32_t g = __ldg(halo + k);
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        s_node[c * stride + h.nOwnPad + k] = __ldg(nc.c[c] + g);
+    }
+    return;
+  }
   for (int k = threadIdx.x - t0; k < h.nHalo; k += blockDim.x - t0) {
     const int32_t g = __ldg(halo + k);
 #pragma unroll
@@ -3042,6 +3051,18 @@ launch_ls_tile(
   const size_t bytes = ls_tile_smem<P>(mp, lp);
   if (bytes > 227 * 1024)
     return cudaErrorInvalidConfiguration;
+  /* experiment: NW_TILE_THREADS=160 runs 5-warp CTAs, three per SM at 128
+   * registers (needs a tile whose shared memory fits three times, e.g.
+   * NW_TILE_NODES=128) */
+  static const int thrEnv = env_int("NW_TILE_THREADS", 0);
+  if (thrEnv == 160 && 3 * (bytes + 2048) <= 228 * 1024) {
+    e = set_smem(ls_tile_kernel<P, ND, 3, 160>, bytes);
+    if (e != cudaSuccess)
+      return e;
+    ls_tile_kernel<P, ND, 3, 160><<<mp.nTiles, 160, bytes, s>>>(
+      with_pf(mp, ls_tile_kernel<P, ND, 3, 160>, 160, bytes), lp, nc, ec, o);
+    return cudaGetLastError();
+  }
   e = set_smem(ls_tile_kernel<P, ND>, bytes);
   if (e != cudaSuccess)
     return e;

@@ -1077,12 +1077,14 @@ def test_abl_neutral_edge_size_vs_oracle(P, ctx):
     assert max(res.values()) < 1.0, res
 
 
-def test_scalar_pair_equals_two_calls(P, ctx):
+def test_scalar_pair_equals_two_calls(P, ctx, monkeypatch):
     """nw_assemble_scalar_edge_pair (TKE + SDR systems in one launch) against
     two nw_assemble_scalar_edge calls: same plan, same arithmetic, same order of
     additions -- the values and right-hand sides must agree bit for bit; also
     the fall-back (atomic mode: one after the other) and different options per
-    system"""
+    system.  The fused kernel is opt-in (NW_SCALAR_PAIR_FUSED=1, read once per
+    process: set before the first call)."""
+    monkeypatch.setenv("NW_SCALAR_PAIR_FUSED", "1")
     for periodic, dims in (((False, False), (11, 9, 7)), ((True, True), (9, 7, 5))):
         case = pu.Case(dims=dims, periodic=periodic)
         mesh = case.box.make_mesh(ctx, tile_nodes=48)
