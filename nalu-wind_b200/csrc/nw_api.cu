@@ -221,6 +221,7 @@ mesh_upload_plan(nw_mesh* m)
   int rc;
   if ((rc = upload(m->dTiles, p.tiles, s, &acc)) ||
       (rc = upload(m->dHalo, p.haloNodes, s, &acc)) ||
+      (rc = upload(m->dHaloBlock, p.haloBlock, s, &acc)) ||
       (rc = upload(m->dLr, p.lr, s, &acc)) ||
       (rc = upload(m->dHeNode, p.heNodeEll, s, &acc)) ||
       (rc = upload(m->dWarpNode, p.sliceOffNode, s, &acc)) ||
@@ -234,6 +235,7 @@ mesh_upload_plan(nw_mesh* m)
   MeshPlanDev& d = m->dev;
   d.tiles = m->dTiles.as<TileHdr>();
   d.haloNodes = m->dHalo.as<int32_t>();
+  d.haloBlock = m->dHaloBlock.as<int32_t>();
   d.lr = m->dLr.as<uint32_t>();
   d.heNodeEll = m->dHeNode.as<uint32_t>();
   d.sliceOffNode = m->dWarpNode.as<int32_t>();

@@ -198,7 +198,7 @@ struct nw_mesh
   nw_ctx* ctx = nullptr;
   nw::MeshPlan plan;
   nw::MeshPlanDev dev;
-  nw::DevBuf dTiles, dHalo, dLr, dHeNode, dWarpNode, dPrimary, dNodeOfSlot,
+  nw::DevBuf dTiles, dHalo, dHaloBlock, dLr, dHeNode, dWarpNode, dPrimary, dNodeOfSlot,
     dTileEdgeSrc, dPrimarySlot, dSecondSlot;
   nw::DevBuf scratch; /* staging for field upload / download */
   std::vector<std::unique_ptr<nw_field_t>> fields;

@@ -244,6 +244,16 @@ node_copy_bytes(int ncomp, const TileHdr& h, bool skip = false)
  * load/store-unit operation per value instead of a load and a store, no
  * register round trip); the issuing thread waits for its own copies with
  * stage_halo_wait() before the CTA barrier */
+/* the calling thread's halo slot of this tile from the fixed-stride block
+ * (issue it right after the header load: both travel together) */
+__device__ __forceinline__ int32_t
+halo_index_early(const MeshPlanDev& mp)
+{
+  return (int)threadIdx.x < kHaloBlock
+           ? __ldg(mp.haloBlock + (size_t)blockIdx.x * kHaloBlock + threadIdx.x)
+           : -1;
+}
+
 template <int NC>
 __device__ __forceinline__ void
 stage_halo_gather(
@@ -252,23 +262,20 @@ stage_halo_gather(
   const NodeComps& nc,
   const TileHdr& h,
   const int32_t* __restrict__ haloNodes,
-  int mode = 0)
+  int32_t g0 /* halo_index_early() */)
 {
-  const int32_t* halo = haloNodes + h.haloPtr;
-  /* experiment (mode & 64): warp 0 does not gather */
-  const int t0 = (mode & 64) ? 32 : 0;
-  if ((int)threadIdx.x < t0)
-    return;
-  if (mode & 128) { /* experiment: load + store through registers */
-    for (int k = threadIdx.x - t0; k < h.nHalo; k += blockDim.x - t0) {
-      const int32_t g = __ldg(halo + k);
+  /* halo node k < kHaloBlock by thread k, its index is already here */
+  if ((int)threadIdx.x < h.nHalo && (int)threadIdx.x < kHaloBlock) {
+    const int k = threadIdx.x;
 #pragma unroll
-      for (int c = 0; c < NC; ++c)
-        s_node[c * stride + h.nOwnPad + k] = __ldg(nc.c[c] + g);
-    }
-    return;
+    for (int c = 0; c < NC; ++c)
+      cp_async8(s_node + c * stride + h.nOwnPad + k, nc.c[c] + g0);
   }
-  for (int k = threadIdx.x - t0; k < h.nHalo; k += blockDim.x - t0) {
+  /* the rest (more halo nodes than threads, or a tile with more than
+   * kHaloBlock of them): through the list */
+  const int32_t* halo = haloNodes + h.haloPtr;
+  const int first = (int)blockDim.x < kHaloBlock ? (int)blockDim.x : kHaloBlock;
+  for (int k = first + threadIdx.x; k < h.nHalo; k += blockDim.x) {
     const int32_t g = __ldg(halo + k);
 #pragma unroll
     for (int c = 0; c < NC; ++c)
@@ -280,28 +287,6 @@ __device__ __forceinline__ void
 stage_halo_wait()
 {
   cp_async_wait_all();
-}
-
-template <int NC>
-__device__ __forceinline__ void
-stage_nodes(
-  double* s_node,
-  int stride,
-  const NodeComps& nc,
-  const TileHdr& h,
-  const int32_t* __restrict__ haloNodes,
-  uint64_t* bar)
-{
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    mbar_expect_tx(bar, node_copy_bytes(NC, h));
-  }
-  __syncthreads();
-  issue_spread(NC, [&](int q) { node_copy<NC>(q, s_node, stride, nc, h, bar); });
-  stage_halo_gather<NC>(s_node, stride, nc, h, haloNodes);
-  stage_halo_wait();
-  mbar_wait(bar, 0);
-  __syncthreads();
 }
 
 /* bytes the edge-stream bulk copies of one tile deliver: the packed (L,R)
@@ -782,6 +767,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
 
   const TileHdr h = mp.tiles[blockIdx.x];
   const LsTileHdr lh = lp.tiles[blockIdx.x];
+  const int32_t g0 = halo_index_early(mp);
   const LsSmem<P> L(mp, lp);
   const int stride = even_up_i(h.nOwnPad + h.nHalo);
 
@@ -849,7 +835,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
         __ldg(mp.sliceOffNode + h.slicePtrNode + threadIdx.x);
   }
   if (!(mp.dbgSkip & 1))
-    stage_halo_gather<P::NC>(s_node, stride, nc, h, mp.haloNodes, mp.dbgSkip);
+    stage_halo_gather<P::NC>(s_node, stride, nc, h, mp.haloNodes, g0);
   NW_PT_MARK(); /* 2: halo gather */
   stage_halo_wait();
   mbar_wait(&bar[0], 0);
@@ -1069,6 +1055,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) scalar_pair_tile_kernel(
 
   const TileHdr h = mp.tiles[blockIdx.x];
   const LsTileHdr lh = lp.tiles[blockIdx.x];
+  const int32_t g0 = halo_index_early(mp);
   const S L(mp, lp);
   const int stride = even_up_i(h.nOwnPad + h.nHalo);
   const int rs = L.resStride;
@@ -1117,7 +1104,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) scalar_pair_tile_kernel(
     if ((int)threadIdx.x <= nSl)
       s_slice[threadIdx.x] = __ldg(lp.sliceOff + lh.slicePtr + threadIdx.x);
   }
-  stage_halo_gather<S::NC>(s_node, stride, nc, h, mp.haloNodes);
+  stage_halo_gather<S::NC>(s_node, stride, nc, h, mp.haloNodes, g0);
   stage_halo_wait();
   mbar_wait(&bar[0], 0);
   __syncthreads();
@@ -1419,6 +1406,7 @@ __global__ void __launch_bounds__(kTileThreads) mdot_tile_kernel(
   __shared__ __align__(8) uint64_t bar;
   NW_PT_BEGIN(3);
   const TileHdr h = mp.tiles[blockIdx.x];
+  const int32_t g0 = halo_index_early(mp);
   const int stride = even_up_i(h.nOwnPad + h.nHalo);
   const int estride = even_up_i(mp.maxTileEdges);
   double* s_area = smem + (size_t)P::NC * mp.maxStaged;
@@ -1437,7 +1425,7 @@ __global__ void __launch_bounds__(kTileThreads) mdot_tile_kernel(
       edge_copy(q - P::NC, s_lr, s_area, estride, mp, h, ecomp, &bar);
   });
   NW_PT_MARK();
-  stage_halo_gather<P::NC>(smem, stride, nc, h, mp.haloNodes);
+  stage_halo_gather<P::NC>(smem, stride, nc, h, mp.haloNodes, g0);
   NW_PT_MARK();
   stage_halo_wait();
   mbar_wait(&bar, 0);
@@ -1474,6 +1462,7 @@ __global__ void __launch_bounds__(kTileThreads) peclet_tile_kernel(
   __shared__ __align__(8) uint64_t bar;
   NW_PT_BEGIN(4);
   const TileHdr h = mp.tiles[blockIdx.x];
+  const int32_t g0 = halo_index_early(mp);
   const int stride = even_up_i(h.nOwnPad + h.nHalo);
   uint32_t* s_lr = reinterpret_cast<uint32_t*>(smem + (size_t)NC * mp.maxStaged);
   if (threadIdx.x == 0) {
@@ -1491,7 +1480,7 @@ __global__ void __launch_bounds__(kTileThreads) peclet_tile_kernel(
       edge_copy(0, s_lr, (double*)nullptr, 0, mp, h, ecomp, &bar);
   });
   NW_PT_MARK();
-  stage_halo_gather<NC>(smem, stride, nc, h, mp.haloNodes);
+  stage_halo_gather<NC>(smem, stride, nc, h, mp.haloNodes, g0);
   NW_PT_MARK();
   stage_halo_wait();
   mbar_wait(&bar, 0);
@@ -1658,6 +1647,7 @@ __global__ void __launch_bounds__(kTileThreads, D1 == 1 ? 8 : 5) grad_tile_kerne
   __shared__ int32_t s_slice[kMaxTileEnts / 32 + 2];
   NW_PT_BEGIN(D1 == 1 ? 5 : 6);
   const TileHdr h = mp.tiles[blockIdx.x];
+  const int32_t g0 = halo_index_early(mp);
   const int stride = even_up_i(h.nOwnPad + h.nHalo);
   const int estride = even_up_i(mp.maxTileEdges);
   double* s_phi = smem;
@@ -1690,7 +1680,7 @@ __global__ void __launch_bounds__(kTileThreads, D1 == 1 ? 8 : 5) grad_tile_kerne
     if ((int)threadIdx.x <= nSl)
       s_slice[threadIdx.x] = __ldg(mp.sliceOffNode + h.slicePtrNode + threadIdx.x);
   }
-  stage_halo_gather<D1>(s_phi, stride, phi, h, mp.haloNodes);
+  stage_halo_gather<D1>(s_phi, stride, phi, h, mp.haloNodes, g0);
   NW_PT_MARK();
   stage_halo_wait();
   mbar_wait(&bar[0], 0);

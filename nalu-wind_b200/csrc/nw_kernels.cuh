@@ -24,6 +24,7 @@ struct MeshPlanDev
 {
   const TileHdr* tiles = nullptr;
   const int32_t* haloNodes = nullptr;
+  const int32_t* haloBlock = nullptr; /* [nTiles][kHaloBlock], -1 padded */
   const uint32_t* lr = nullptr;
   const uint32_t* heNodeEll = nullptr;   /* sliced-ELL node-keyed half-edges */
   const int32_t* sliceOffNode = nullptr;

@@ -18,6 +18,7 @@ constexpr int kMaxRowNnz = 128;         /* 7 bits: slot of an entry in its row *
 constexpr int kMaxTileStaged = 65535;   /* 16 bits per end in an lr record */
 constexpr int kMaxWarps = 8;            /* CTA = 256 threads */
 constexpr int kTileThreads = 256;
+constexpr int kHaloBlock = 256;         /* halo slots per tile stored at a fixed stride */
 
 /* half-edge record (32 bit):
  *   [0,12)  tile-edge index

@@ -482,11 +482,16 @@ build_mesh_plan(const MeshInput& in, MeshPlan& mp)
     fail("nw_mesh_create: plan arrays exceed 32-bit offsets");
   mp.totalHalo = hp;
   mp.haloNodes.assign(hp + 4, 0);
+  mp.haloBlock.assign(size_t(nTiles) * kHaloBlock, -1);
   mp.heNode.assign(qp + 4, 0u);
   for (int64_t t = 0; t < nTiles; ++t) {
     const TileHdr& h = mp.tiles[t];
     std::copy(haloPer[t].begin(), haloPer[t].end(),
               mp.haloNodes.begin() + h.haloPtr);
+    std::copy(
+      haloPer[t].begin(),
+      haloPer[t].begin() + std::min<size_t>(haloPer[t].size(), kHaloBlock),
+      mp.haloBlock.begin() + size_t(t) * kHaloBlock);
     std::copy(hePer[t].begin(), hePer[t].end(), mp.heNode.begin() + h.hePtrNode);
     split_half_edges(
       mp.heNode.data() + h.hePtrNode, h.nHalfNode, kMaxWarps,

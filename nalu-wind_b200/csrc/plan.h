@@ -58,6 +58,11 @@ struct MeshPlan
   int64_t nTiles = 0;
   std::vector<TileHdr> tiles;
   std::vector<int32_t> haloNodes; /* internal slots, per tile ascending */
+  /* the first kHaloBlock halo slots of every tile at a fixed stride (entry
+   * t * kHaloBlock + k, -1 = none): thread k of the tile's CTA loads its
+   * halo index together with the tile header, one dependent load less in the
+   * staging chain */
+  std::vector<int32_t> haloBlock;
 
   /* tile-edge arrays (slot index space, even-aligned tile starts) */
   int64_t nTileEdgeSlots = 0;

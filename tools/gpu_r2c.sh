@@ -9,7 +9,7 @@ mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 TAG=${1:-r02c}
 echo "=== pytest -m gpu"
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; tail -6 gpurun_out/${TAG}_pytest_gpu.log
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; tail -6 gpurun_out/${TAG}_pytest_gpu.log
 run() { # name, env, args
   local name=${TAG}_bench_$1
   echo "=== bench $1: [$2] $3"
@@ -22,10 +22,11 @@ print('value',round(d['value'],1),'ms/step',round(d['ms_per_step'],4),'sweep_fra
 }
 run default "" ""
 run sst "" "--sst --no-cpu-baseline"
-run sst_nofuse "" "--sst --no-fuse-scalars --no-cpu-baseline"
-run e3 "NW_DBG_SKIP=16" "--sst --no-fuse-scalars --no-cpu-baseline"
+if [ "${2:-}" = "all" ]; then
+run sst_fused "NW_SCALAR_PAIR_FUSED=1" "--sst --fuse-scalars --no-cpu-baseline"
 run warped "" "--mesh warped --sst --no-cpu-baseline"
 run mixed "" "--mesh mixed --sst --no-cpu-baseline"
+fi
 echo "=== phase cycles"
 make -C nalu-wind_b200 -s prof > /dev/null 2>&1 && NW_LIB_PATH=$PWD/nalu-wind_b200/libnalu_edge_b200_prof.so timeout 300 python tools/phase_times.py > gpurun_out/${TAG}_phase_cycles.txt 2>&1
 grep -A8 -E "^(continuity|momentum|mdot|grad_scalar) " gpurun_out/${TAG}_phase_cycles.txt
