@@ -990,6 +990,365 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
 }
 
 /* ------------------------------------------------------------------ */
+/*  pipelined linear-system kernel: warp-specialised, persistent        */
+/* ------------------------------------------------------------------ */
+
+/* profiles/r02d_ablation_timings.txt: in ls_tile_kernel the stage, the physics
+ * and the row reduction of a tile add up -- each is a chain of latencies and
+ * an SM holds only two or three tiles.  Here one persistent CTA per SM keeps
+ * three tiles in flight with different warps:
+ *
+ *   memory warps (kPipeMemWarps):  reduce tile k (phases 2-3 of
+ *       ls_tile_kernel: row walk, copy-out), then stage tile k+2 into the
+ *       slot tile k has just left (bulk copies + asynchronous halo gather:
+ *       issue only, the data lands while they reduce tile k+1);
+ *   compute warps (the rest):  the edge physics of tile k+1.
+ *
+ * Two slots (node stage, edge inputs / results, reduction plan); per slot an
+ * mbarrier `full` (bulk-copy bytes + one asynchronous arrival per memory
+ * thread for its cp.async gathers) and an mbarrier `done` (one arrival per
+ * compute thread after its results are in shared memory).  The FP64 pipe
+ * works while the two memory phases of the neighbouring tiles run.  Same plan
+ * data, same arithmetic, same order of additions as ls_tile_kernel: results
+ * are bit-identical (tests/test_gpu_parity.py::test_pipe_kernel_*). */
+constexpr int kPipeThreads = 512;
+constexpr int kPipeMemWarps = 4;
+constexpr int kPipeMemThreads = kPipeMemWarps * 32;
+constexpr int kPipeCmpThreads = kPipeThreads - kPipeMemThreads;
+constexpr int kPipeHdrRing = 4;
+
+__device__ __forceinline__ void
+mbar_arrive(uint64_t* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+/* arrival that fires when all prior cp.async of the calling thread have
+ * landed; does not change the barrier's pending count (counted at init) */
+__device__ __forceinline__ void
+mbar_arrive_cp_async(uint64_t* bar)
+{
+  asm volatile(
+    "cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar))
+    : "memory");
+}
+/* barrier among the memory warps only (barrier 1; 0 is __syncthreads) */
+__device__ __forceinline__ void
+mem_warps_sync()
+{
+  asm volatile("bar.sync 1, %0;" ::"n"(kPipeMemThreads) : "memory");
+}
+
+template <class P>
+struct PipeSmem
+{
+  static constexpr int NIN_MAX = LsSmem<P>::NIN_MAX;
+  static constexpr int NEDGE = LsSmem<P>::NEDGE;
+  int nodeLen, resStride, lrLen, valsLen, ellLen, entLen;
+  size_t slotBytes, rowBytes;
+  __host__ __device__ PipeSmem(const MeshPlanDev& mp, const LsPlanDev& lp)
+  {
+    nodeLen = P::NC * mp.maxStaged;
+    resStride = (mp.maxTileEdges + 1) & ~1;
+    lrLen = (mp.maxTileEdges + 3) & ~3;
+    valsLen = (lp.maxTileNnz + 3) & ~3;
+    ellLen = (lp.maxTileEll + 3) & ~3;
+    entLen = (lp.maxTileEnts + 3) & ~3;
+    slotBytes = sizeof(double) * ((size_t)nodeLen + (size_t)NEDGE * resStride) +
+                4u * (size_t)lrLen + 4u * (size_t)ellLen + 12u * (size_t)entLen;
+    slotBytes = (slotBytes + 15) & ~size_t(15);
+    rowBytes = 8u * (size_t)valsLen + 4u * (size_t)valsLen;
+  }
+  __host__ __device__ size_t bytes() const { return 2 * slotBytes + rowBytes; }
+};
+
+template <class P, int ND>
+__global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
+  const MeshPlanDev mp,
+  const LsPlanDev lp,
+  const NodeComps nc,
+  const EdgeComps ec,
+  const typename P::Opts o)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t barFull[2], barDone[2];
+  __shared__ __align__(16) TileHdr s_hdr[kPipeHdrRing];
+  __shared__ __align__(16) LsTileHdr s_lhdr[kPipeHdrRing];
+  __shared__ int32_t s_slice[2][kMaxTileEnts / 32 + 2];
+
+  using S = PipeSmem<P>;
+  const S L(mp, lp);
+  const int tid = threadIdx.x;
+  const int G = gridDim.x;
+  const int K = (mp.nTiles - (int)blockIdx.x + G - 1) / G; /* my tiles */
+  auto tile_of = [&](int k) { return (int)blockIdx.x + k * G; };
+
+  auto s_node_of = [&](int sl) {
+    return reinterpret_cast<double*>(smem_raw + (size_t)sl * L.slotBytes);
+  };
+  auto s_res_of = [&](int sl) { return s_node_of(sl) + L.nodeLen; };
+  auto s_lr_of = [&](int sl) {
+    return reinterpret_cast<uint32_t*>(s_res_of(sl) + S::NEDGE * L.resStride);
+  };
+  auto s_ell_of = [&](int sl) { return s_lr_of(sl) + L.lrLen; };
+  auto s_ent_of = [&](int sl) {
+    return reinterpret_cast<EntInfo*>(s_ell_of(sl) + L.ellLen);
+  };
+  double* s_vals = reinterpret_cast<double*>(smem_raw + 2 * L.slotBytes);
+  int32_t* s_delta = reinterpret_cast<int32_t*>(s_vals + L.valsLen);
+
+  constexpr int kMdot = ND;
+  constexpr int kPec = ND + 1;
+  const bool hasPec = P::kNeedsPec && ec.pecfac != nullptr;
+  const int nin = ND + (P::kNeedsMdot ? 1 : 0) + (hasPec ? 1 : 0);
+  const EdgeCompSel<ND> ecomp{ec};
+
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&barFull[b], 1 + kPipeMemThreads);
+      mbar_init(&barDone[b], kPipeCmpThreads);
+    }
+  }
+  __syncthreads();
+
+  if (tid < kPipeMemThreads) {
+    /* =========================== memory warps =========================== */
+    const int lane = tid & 31, warp = tid >> 5;
+
+    /* headers of tile k -> ring slot k % kPipeHdrRing (lane i of warp 0:
+     * word i of the 64-byte TileHdr, lanes 16..31: the LsTileHdr) */
+    auto hdr_load = [&](int k) -> int32_t {
+      if (warp != 0 || k >= K)
+        return 0;
+      return lane < 16
+               ? __ldg(reinterpret_cast<const int32_t*>(mp.tiles + tile_of(k)) + lane)
+               : __ldg(reinterpret_cast<const int32_t*>(lp.tiles + tile_of(k)) + (lane - 16));
+    };
+    auto hdr_store = [&](int k, int32_t w) {
+      if (warp != 0 || k >= K)
+        return;
+      if (lane < 16)
+        reinterpret_cast<int32_t*>(&s_hdr[k % kPipeHdrRing])[lane] = w;
+      else
+        reinterpret_cast<int32_t*>(&s_lhdr[k % kPipeHdrRing])[lane - 16] = w;
+    };
+    /* my halo slots of tile k out of the fixed-stride block */
+    auto halo_early = [&](int k, int32_t& ga, int32_t& gb) {
+      ga = gb = -1;
+      if (k < K) {
+        const int32_t* blk = mp.haloBlock + (size_t)tile_of(k) * kHaloBlock;
+        ga = __ldg(blk + tid);
+        gb = __ldg(blk + kPipeMemThreads + tid);
+      }
+    };
+    /* stage tile k into slot k & 1 (headers of k are in the ring and visible
+     * to the memory warps) */
+    auto stage = [&](int k, int32_t ga, int32_t gb) {
+      const int sl = k & 1;
+      const TileHdr h = s_hdr[k % kPipeHdrRing];
+      const LsTileHdr lh = s_lhdr[k % kPipeHdrRing];
+      const int stride = even_up_i(h.nOwnPad + h.nHalo);
+      double* s_node = s_node_of(sl);
+      double* s_res = s_res_of(sl);
+      const uint32_t bEll = (uint32_t)lh.ellLen * 4u;
+      const uint32_t bEnt = round16((uint32_t)lh.nEnts * 4u);
+      EntInfo* s_ent = s_ent_of(sl);
+      int32_t* s_row = reinterpret_cast<int32_t*>(s_ent + L.entLen);
+      int32_t* s_go = s_row + L.entLen;
+      uint64_t* bar = &barFull[sl];
+      if (tid == 0)
+        mbar_expect_tx(
+          bar, node_copy_bytes(P::NC, h) + edge_stream_bytes(h, nin) + bEll +
+                 3u * bEnt);
+      /* bulk copies: copy q from lane 0 of memory warp q mod kPipeMemWarps */
+      if (lane == 0)
+        for (int q = warp; q < P::NC + 1 + nin + 4; q += kPipeMemWarps) {
+          if (q < P::NC)
+            node_copy<P::NC>(q, s_node, stride, nc, h, bar);
+          else if (q <= P::NC + nin)
+            edge_copy(q - P::NC, s_lr_of(sl), s_res, L.resStride, mp, h, ecomp, bar);
+          else {
+            const int r = q - (P::NC + 1 + nin);
+            if (r == 0 && bEll)
+              tma_load_1d(s_ell_of(sl), lp.heEll + lh.ellPtr, bEll, bar);
+            else if (r == 1 && bEnt)
+              tma_load_1d(s_ent, lp.entInfo + lh.entPtr, bEnt, bar);
+            else if (r == 2 && bEnt)
+              tma_load_1d(s_row, lp.entRhsRow + lh.entPtr, bEnt, bar);
+            else if (r == 3 && bEnt)
+              tma_load_1d(s_go, lp.entGo + lh.entPtr, bEnt, bar);
+          }
+        }
+      /* slice offsets of the row-keyed list */
+      {
+        const int nSl = (lh.nEnts + 31) >> 5;
+        if (tid <= nSl)
+          s_slice[sl][tid] = __ldg(lp.sliceOff + lh.slicePtr + tid);
+      }
+      /* halo nodes: asynchronous gathers, two from the early indices, the rest
+       * through the list */
+      if (tid < h.nHalo) {
+#pragma unroll
+        for (int c = 0; c < P::NC; ++c)
+          cp_async8(s_node + c * stride + h.nOwnPad + tid, nc.c[c] + ga);
+      }
+      if (kPipeMemThreads + tid < h.nHalo) {
+#pragma unroll
+        for (int c = 0; c < P::NC; ++c)
+          cp_async8(
+            s_node + c * stride + h.nOwnPad + kPipeMemThreads + tid, nc.c[c] + gb);
+      }
+      const int32_t* halo = mp.haloNodes + h.haloPtr;
+      for (int q = 2 * kPipeMemThreads + tid; q < h.nHalo; q += kPipeMemThreads) {
+        const int32_t g = __ldg(halo + q);
+#pragma unroll
+        for (int c = 0; c < P::NC; ++c)
+          cp_async8(s_node + c * stride + h.nOwnPad + q, nc.c[c] + g);
+      }
+      /* the slice offsets (plain stores) and the header ring must be visible
+       * to whoever passes the barrier: every memory thread arrives after its
+       * own stores; the asynchronous arrival counts its gathers in */
+      __threadfence_block();
+      mbar_arrive_cp_async(bar);
+    };
+
+    /* prologue: headers of my first three tiles, tiles 0 and 1 staged */
+    {
+      const int32_t w0 = hdr_load(0), w1 = hdr_load(1), w2 = hdr_load(2);
+      hdr_store(0, w0);
+      hdr_store(1, w1);
+      hdr_store(2, w2);
+    }
+    int32_t ga, gb;
+    mem_warps_sync();
+    for (int k = 0; k < 2 && k < K; ++k) {
+      halo_early(k, ga, gb);
+      stage(k, ga, gb);
+    }
+
+    for (int k = 0; k < K; ++k) {
+      const int sl = k & 1;
+      const uint32_t par = (uint32_t)(k >> 1) & 1u;
+      /* issued now, needed after the reduction */
+      const int32_t wNext = hdr_load(k + 3);
+      halo_early(k + 2, ga, gb);
+
+      /* ---- reduce tile k (phases 2-3) ---- */
+      mbar_wait(&barFull[sl], par); /* the plan of tile k */
+      mbar_wait(&barDone[sl], par); /* its edge results */
+      {
+        const LsTileHdr lh = s_lhdr[k % kPipeHdrRing];
+        const double* s_res = s_res_of(sl);
+        const uint32_t* s_ell = s_ell_of(sl);
+        const EntInfo* s_ent = s_ent_of(sl);
+        const int32_t* s_row = reinterpret_cast<const int32_t*>(s_ent + L.entLen);
+        const int32_t* s_go = s_row + L.entLen;
+        for (int row0 = tid - lane; row0 < lh.nEnts; row0 += kPipeMemThreads) {
+          const int row = row0 + lane;
+          if (row < lh.nEnts) {
+            const int s = row0 >> 5;
+            const int o0 = s_slice[sl][s], o1 = s_slice[sl][s + 1];
+            const uint32_t* hp = s_ell + o0 + lane;
+            const int W = (o1 - o0) >> 5;
+            const EntInfo ei = s_ent[row];
+            double* vrow = s_vals + ei.base;
+            double diag = 0.0;
+            double rhs[P::NR];
+#pragma unroll
+            for (int d = 0; d < P::NR; ++d)
+              rhs[d] = 0.0;
+            constexpr int kBlk = 4;
+            for (int w0 = 0; w0 < W; w0 += kBlk) {
+              uint32_t hv[kBlk];
+#pragma unroll
+              for (int u = 0; u < kBlk; ++u)
+                hv[u] = (w0 + u < W) ? hp[(w0 + u) * 32] : 0u;
+              double dg[kBlk], off[kBlk], rr[kBlk][P::NR];
+#pragma unroll
+              for (int u = 0; u < kBlk; ++u)
+                if (hv[u] & kHeValid)
+                  P::contrib(
+                    he_side(hv[u]), s_res, L.resStride, (int)he_edge(hv[u]),
+                    dg[u], off[u], rr[u]);
+#pragma unroll
+              for (int u = 0; u < kBlk; ++u)
+                if (hv[u] & kHeValid) {
+                  diag += dg[u];
+#pragma unroll
+                  for (int d = 0; d < P::NR; ++d)
+                    rhs[d] += rr[u][d];
+                  double* dst = vrow + he_k(hv[u]);
+                  if (hv[u] & kHeDup)
+                    off[u] += *dst;
+                  *dst = off[u];
+                }
+            }
+            vrow[ei.diagK] = diag;
+            const int32_t delta = s_go[row] - (int32_t)ei.base;
+            for (int q = 0; q < (int)ei.nnz; ++q)
+              s_delta[ei.base + q] = delta;
+            const int64_t grow = s_row[row];
+#pragma unroll
+            for (int d = 0; d < P::NR; ++d)
+              lp.rhs[(int64_t)d * lp.rhsStride + grow] = rhs[d];
+          }
+          __syncwarp();
+          {
+            const int last = min(row0 + 31, lh.nEnts - 1);
+            const EntInfo e0 = s_ent[row0], e1 = s_ent[last];
+            const int end = (int)e1.base + (int)e1.nnz;
+#pragma unroll 4
+            for (int e = (int)e0.base + lane; e < end; e += 32)
+              lp.values[e + s_delta[e]] = s_vals[e];
+          }
+          __syncwarp();
+        }
+      }
+      /* every memory warp has left slot sl (and the row staging) */
+      hdr_store(k + 3, wNext);
+      mem_warps_sync();
+      /* the bulk copies of the next stage overwrite shared memory these
+       * threads have read through the generic proxy */
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (k + 2 < K)
+        stage(k + 2, ga, gb);
+    }
+  } else {
+    /* =========================== compute warps ========================== */
+    const int ct = tid - kPipeMemThreads;
+    for (int k = 0; k < K; ++k) {
+      const int sl = k & 1;
+      const uint32_t par = (uint32_t)(k >> 1) & 1u;
+      mbar_wait(&barFull[sl], par);
+      const TileHdr h = s_hdr[k % kPipeHdrRing];
+      const int stride = even_up_i(h.nOwnPad + h.nHalo);
+      double* s_res = s_res_of(sl);
+      const uint32_t* s_lr = s_lr_of(sl);
+      const SmemLd ld{s_node_of(sl), stride};
+      for (int j = ct; j < h.nEdges; j += kPipeCmpThreads) {
+        const uint32_t v = s_lr[j];
+        const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
+        double av[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+          av[d] = s_res[d * L.resStride + j];
+        double mdot = 0.0, pecfac = 0.0;
+        if (P::kNeedsMdot)
+          mdot = s_res[kMdot * L.resStride + j];
+        if (hasPec)
+          pecfac = s_res[kPec * L.resStride + j];
+        double res[P::NRES];
+        P::compute(ld, l, r, av, mdot, pecfac, o, res);
+#pragma unroll
+        for (int q = 0; q < P::NRES; ++q)
+          s_res[q * L.resStride + j] = res[q];
+      }
+      mbar_arrive(&barDone[sl]);
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ */
 /*  two scalar systems of one graph in one launch (SST: TKE + SDR)      */
 /* ------------------------------------------------------------------ */
 
@@ -3038,6 +3397,21 @@ launch_ls_tile(
     e = launch_ls_stream<P, ND>(mp, lp, nc, ec, o, s, &launched);
   if (e != cudaSuccess || launched)
     return e;
+  /* NW_PIPE=1: the warp-specialised persistent kernel, when two slots of this
+   * mesh's tiles fit one CTA's shared memory (tiles of <= ~160 nodes for
+   * momentum on a hex mesh) and no extract_diagonal pass is asked for */
+  const int pipeEnv = env_int("NW_PIPE", 0); /* read per call: tests toggle it */
+  if (pipeEnv && !diagOut && mp.nTiles > 0) {
+    const size_t pb = PipeSmem<P>(mp, lp).bytes();
+    if (pb + 2048 <= 227 * 1024) {
+      e = set_smem(ls_pipe_kernel<P, ND>, pb);
+      if (e != cudaSuccess)
+        return e;
+      const int grid = std::min(mp.nTiles, sm_count());
+      ls_pipe_kernel<P, ND><<<grid, kPipeThreads, pb, s>>>(mp, lp, nc, ec, o);
+      return cudaGetLastError();
+    }
+  }
   const size_t bytes = ls_tile_smem<P>(mp, lp);
   if (bytes > 227 * 1024)
     return cudaErrorInvalidConfiguration;

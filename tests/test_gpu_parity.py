@@ -1087,6 +1087,53 @@ def test_abl_neutral_edge_size_vs_oracle(P, ctx):
     assert max(res.values()) < 1.0, res
 
 
+@pytest.mark.parametrize("periodic,dims,tile", [
+    ((False, False), (13, 11, 9), 48), ((True, True), (9, 8, 6), 40),
+    ((False, False), (30, 28, 26), 144)])
+def test_pipe_kernel_matches_tile_kernel(P, ctx, monkeypatch, periodic, dims, tile):
+    """NW_PIPE=1: the warp-specialised persistent kernel (memory warps stage tile
+    k+2 and reduce tile k while compute warps run the physics of tile k+1) must
+    give the bits of ls_tile_kernel -- same plan, same arithmetic, same order of
+    additions -- for continuity, scalar and momentum (separate and fused
+    Peclet), on more tiles than SMs (third case: every CTA loops) and fewer"""
+    case = pu.Case(dims=dims, periodic=periodic)
+    mesh = case.box.make_mesh(ctx, tile_nodes=tile)
+    pu.upload_state(P, mesh, case)
+    mesh.upload("mass_flow_rate", case.oracle_mdot())
+    mesh.upload("peclet_factor", case.oracle_pecfac(orc.peclet("classic", 1.0)))
+    pf = P.peclet_fn("classic", 1.0)
+
+    def run(pipe):
+        monkeypatch.setenv("NW_PIPE", "1" if pipe else "0")
+        out = []
+        for kind, nd, fn in (
+                (P.NW_LINSYS_HYPRE, 1,
+                 lambda ls: ls.assemble_continuity_edge(**pu.CONT_OPTS)),
+                (P.NW_LINSYS_HYPRE, 1,
+                 lambda ls: ls.assemble_scalar_edge(
+                     "turbulent_ke", "dkdx", "effective_viscosity_tke",
+                     pf=P.peclet_fn("tanh", 2.0, 1.0), **pu.SCAL_OPTS)),
+                (P.NW_LINSYS_HYPRE_UVW, 3,
+                 lambda ls: ls.assemble_momentum_edge("viscosity", **pu.MOM_OPTS)),
+                (P.NW_LINSYS_HYPRE_UVW, 3,
+                 lambda ls: ls.assemble_momentum_edge(
+                     "viscosity", fuse_peclet=True, pf=pf, **pu.MOM_OPTS))):
+            ls = P.LinearSystem(mesh, kind, nd)
+            ls.buildEdgeToNodeGraph()
+            ls.finalizeLinearSystem()
+            for _ in range(2):  # twice: the second run reuses every buffer
+                ls.zeroSystem()
+                fn(ls)
+            out.append(ls.values())
+            ls.close()
+        return out
+    ref, got = run(False), run(True)
+    monkeypatch.setenv("NW_PIPE", "0")
+    for (v0, r0), (v1, r1) in zip(ref, got):
+        assert np.array_equal(v0, v1) and np.array_equal(r0, r1)
+    mesh.close()
+
+
 def test_scalar_pair_equals_two_calls(P, ctx, monkeypatch):
     """nw_assemble_scalar_edge_pair (TKE + SDR systems in one launch) against
     two nw_assemble_scalar_edge calls: same plan, same arithmetic, same order of
