@@ -1045,21 +1045,26 @@ struct PipeSmem
   static constexpr int NIN_MAX = LsSmem<P>::NIN_MAX;
   static constexpr int NEDGE = LsSmem<P>::NEDGE;
   int nodeLen, resStride, lrLen, valsLen, ellLen, entLen;
-  size_t slotBytes, rowBytes;
+  size_t nodeBytes, rslotBytes, rowBytes;
   __host__ __device__ PipeSmem(const MeshPlanDev& mp, const LsPlanDev& lp)
   {
-    nodeLen = P::NC * mp.maxStaged;
+    nodeLen = (P::NC * mp.maxStaged + 1) & ~1;
     resStride = (mp.maxTileEdges + 1) & ~1;
     lrLen = (mp.maxTileEdges + 3) & ~3;
     valsLen = (lp.maxTileNnz + 3) & ~3;
     ellLen = (lp.maxTileEll + 3) & ~3;
     entLen = (lp.maxTileEnts + 3) & ~3;
-    slotBytes = sizeof(double) * ((size_t)nodeLen + (size_t)NEDGE * resStride) +
-                4u * (size_t)lrLen + 4u * (size_t)ellLen + 12u * (size_t)entLen;
-    slotBytes = (slotBytes + 15) & ~size_t(15);
+    nodeBytes = sizeof(double) * (size_t)nodeLen;
+    rslotBytes = sizeof(double) * (size_t)NEDGE * resStride + 4u * (size_t)lrLen +
+                 4u * (size_t)ellLen + 12u * (size_t)entLen;
+    rslotBytes = (rslotBytes + 15) & ~size_t(15);
     rowBytes = 8u * (size_t)valsLen + 4u * (size_t)valsLen;
   }
-  __host__ __device__ size_t bytes() const { return 2 * slotBytes + rowBytes; }
+  /* two node slots, three result / plan slots, one row staging */
+  __host__ __device__ size_t bytes() const
+  {
+    return 2 * nodeBytes + 3 * rslotBytes + rowBytes;
+  }
 };
 
 template <class P, int ND>
@@ -1071,10 +1076,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
   const typename P::Opts o)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t barFull[2], barDone[2];
+  __shared__ __align__(8) uint64_t barFull[3], barDone[3];
   __shared__ __align__(16) TileHdr s_hdr[kPipeHdrRing];
   __shared__ __align__(16) LsTileHdr s_lhdr[kPipeHdrRing];
-  __shared__ int32_t s_slice[2][kMaxTileEnts / 32 + 2];
+  __shared__ int32_t s_slice[3][kMaxTileEnts / 32 + 2];
 
   using S = PipeSmem<P>;
   const S L(mp, lp);
@@ -1083,18 +1088,24 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
   const int K = (mp.nTiles - (int)blockIdx.x + G - 1) / G; /* my tiles */
   auto tile_of = [&](int k) { return (int)blockIdx.x + k * G; };
 
-  auto s_node_of = [&](int sl) {
-    return reinterpret_cast<double*>(smem_raw + (size_t)sl * L.slotBytes);
+  /* tile k: node slot k & 1 (free again when its physics is done), result /
+   * plan slot k % 3 (edge inputs -> edge results -> read by the reduction) */
+  auto s_node_of = [&](int k) {
+    return reinterpret_cast<double*>(smem_raw + (size_t)(k & 1) * L.nodeBytes);
   };
-  auto s_res_of = [&](int sl) { return s_node_of(sl) + L.nodeLen; };
-  auto s_lr_of = [&](int sl) {
-    return reinterpret_cast<uint32_t*>(s_res_of(sl) + S::NEDGE * L.resStride);
+  auto s_res_of = [&](int k) {
+    return reinterpret_cast<double*>(
+      smem_raw + 2 * L.nodeBytes + (size_t)(k % 3) * L.rslotBytes);
   };
-  auto s_ell_of = [&](int sl) { return s_lr_of(sl) + L.lrLen; };
-  auto s_ent_of = [&](int sl) {
-    return reinterpret_cast<EntInfo*>(s_ell_of(sl) + L.ellLen);
+  auto s_lr_of = [&](int k) {
+    return reinterpret_cast<uint32_t*>(s_res_of(k) + S::NEDGE * L.resStride);
   };
-  double* s_vals = reinterpret_cast<double*>(smem_raw + 2 * L.slotBytes);
+  auto s_ell_of = [&](int k) { return s_lr_of(k) + L.lrLen; };
+  auto s_ent_of = [&](int k) {
+    return reinterpret_cast<EntInfo*>(s_ell_of(k) + L.ellLen);
+  };
+  double* s_vals =
+    reinterpret_cast<double*>(smem_raw + 2 * L.nodeBytes + 3 * L.rslotBytes);
   int32_t* s_delta = reinterpret_cast<int32_t*>(s_vals + L.valsLen);
 
   constexpr int kMdot = ND;
@@ -1104,7 +1115,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
   const EdgeCompSel<ND> ecomp{ec};
 
   if (tid == 0) {
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 3; ++b) {
       mbar_init(&barFull[b], 1 + kPipeMemThreads);
       mbar_init(&barDone[b], kPipeCmpThreads);
     }
@@ -1141,21 +1152,20 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
         gb = __ldg(blk + kPipeMemThreads + tid);
       }
     };
-    /* stage tile k into slot k & 1 (headers of k are in the ring and visible
-     * to the memory warps) */
+    /* stage tile k (its headers are in the ring and visible to the memory
+     * warps): issue only, completion is barFull[k % 3] */
     auto stage = [&](int k, int32_t ga, int32_t gb) {
-      const int sl = k & 1;
       const TileHdr h = s_hdr[k % kPipeHdrRing];
       const LsTileHdr lh = s_lhdr[k % kPipeHdrRing];
       const int stride = even_up_i(h.nOwnPad + h.nHalo);
-      double* s_node = s_node_of(sl);
-      double* s_res = s_res_of(sl);
+      double* s_node = s_node_of(k);
+      double* s_res = s_res_of(k);
       const uint32_t bEll = (uint32_t)lh.ellLen * 4u;
       const uint32_t bEnt = round16((uint32_t)lh.nEnts * 4u);
-      EntInfo* s_ent = s_ent_of(sl);
+      EntInfo* s_ent = s_ent_of(k);
       int32_t* s_row = reinterpret_cast<int32_t*>(s_ent + L.entLen);
       int32_t* s_go = s_row + L.entLen;
-      uint64_t* bar = &barFull[sl];
+      uint64_t* bar = &barFull[k % 3];
       if (tid == 0)
         mbar_expect_tx(
           bar, node_copy_bytes(P::NC, h) + edge_stream_bytes(h, nin) + bEll +
@@ -1166,11 +1176,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
           if (q < P::NC)
             node_copy<P::NC>(q, s_node, stride, nc, h, bar);
           else if (q <= P::NC + nin)
-            edge_copy(q - P::NC, s_lr_of(sl), s_res, L.resStride, mp, h, ecomp, bar);
+            edge_copy(q - P::NC, s_lr_of(k), s_res, L.resStride, mp, h, ecomp, bar);
           else {
             const int r = q - (P::NC + 1 + nin);
             if (r == 0 && bEll)
-              tma_load_1d(s_ell_of(sl), lp.heEll + lh.ellPtr, bEll, bar);
+              tma_load_1d(s_ell_of(k), lp.heEll + lh.ellPtr, bEll, bar);
             else if (r == 1 && bEnt)
               tma_load_1d(s_ent, lp.entInfo + lh.entPtr, bEnt, bar);
             else if (r == 2 && bEnt)
@@ -1183,7 +1193,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
       {
         const int nSl = (lh.nEnts + 31) >> 5;
         if (tid <= nSl)
-          s_slice[sl][tid] = __ldg(lp.sliceOff + lh.slicePtr + tid);
+          s_slice[k % 3][tid] = __ldg(lp.sliceOff + lh.slicePtr + tid);
       }
       /* halo nodes: asynchronous gathers, two from the early indices, the rest
        * through the list */
@@ -1227,27 +1237,37 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
     }
 
     for (int k = 0; k < K; ++k) {
-      const int sl = k & 1;
-      const uint32_t par = (uint32_t)(k >> 1) & 1u;
-      /* issued now, needed after the reduction */
+      const uint32_t par = (uint32_t)(k / 3) & 1u;
+      /* issued now, needed further down */
       const int32_t wNext = hdr_load(k + 3);
       halo_early(k + 2, ga, gb);
 
+      /* the physics of tile k is done: its results are in place and its node
+       * slot is free -- stage tile k+2 into it first, so that the data has a
+       * whole iteration to land, then reduce tile k */
+      mbar_wait(&barDone[k % 3], par);
+      /* the bulk copies overwrite shared memory read through the generic
+       * proxy (node slot: compute warps; result slot: the reduction of tile
+       * k-1, ordered by the barrier at the end of the last iteration) */
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (k + 2 < K)
+        stage(k + 2, ga, gb);
+
       /* ---- reduce tile k (phases 2-3) ---- */
-      mbar_wait(&barFull[sl], par); /* the plan of tile k */
-      mbar_wait(&barDone[sl], par); /* its edge results */
+      mbar_wait(&barFull[k % 3], par); /* the plan of tile k (long landed) */
       {
         const LsTileHdr lh = s_lhdr[k % kPipeHdrRing];
-        const double* s_res = s_res_of(sl);
-        const uint32_t* s_ell = s_ell_of(sl);
-        const EntInfo* s_ent = s_ent_of(sl);
+        const double* s_res = s_res_of(k);
+        const uint32_t* s_ell = s_ell_of(k);
+        const EntInfo* s_ent = s_ent_of(k);
         const int32_t* s_row = reinterpret_cast<const int32_t*>(s_ent + L.entLen);
         const int32_t* s_go = s_row + L.entLen;
+        const int32_t* sliceOff = s_slice[k % 3];
         for (int row0 = tid - lane; row0 < lh.nEnts; row0 += kPipeMemThreads) {
           const int row = row0 + lane;
           if (row < lh.nEnts) {
             const int s = row0 >> 5;
-            const int o0 = s_slice[sl][s], o1 = s_slice[sl][s + 1];
+            const int o0 = sliceOff[s], o1 = sliceOff[s + 1];
             const uint32_t* hp = s_ell + o0 + lane;
             const int W = (o1 - o0) >> 5;
             const EntInfo ei = s_ent[row];
@@ -1304,27 +1324,21 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
           __syncwarp();
         }
       }
-      /* every memory warp has left slot sl (and the row staging) */
+      /* every memory warp has left the result slot and the row staging */
       hdr_store(k + 3, wNext);
       mem_warps_sync();
-      /* the bulk copies of the next stage overwrite shared memory these
-       * threads have read through the generic proxy */
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      if (k + 2 < K)
-        stage(k + 2, ga, gb);
     }
   } else {
     /* =========================== compute warps ========================== */
     const int ct = tid - kPipeMemThreads;
     for (int k = 0; k < K; ++k) {
-      const int sl = k & 1;
-      const uint32_t par = (uint32_t)(k >> 1) & 1u;
-      mbar_wait(&barFull[sl], par);
+      const uint32_t par = (uint32_t)(k / 3) & 1u;
+      mbar_wait(&barFull[k % 3], par);
       const TileHdr h = s_hdr[k % kPipeHdrRing];
       const int stride = even_up_i(h.nOwnPad + h.nHalo);
-      double* s_res = s_res_of(sl);
-      const uint32_t* s_lr = s_lr_of(sl);
-      const SmemLd ld{s_node_of(sl), stride};
+      double* s_res = s_res_of(k);
+      const uint32_t* s_lr = s_lr_of(k);
+      const SmemLd ld{s_node_of(k), stride};
       for (int j = ct; j < h.nEdges; j += kPipeCmpThreads) {
         const uint32_t v = s_lr[j];
         const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
@@ -1343,7 +1357,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
         for (int q = 0; q < P::NRES; ++q)
           s_res[q * L.resStride + j] = res[q];
       }
-      mbar_arrive(&barDone[sl]);
+      mbar_arrive(&barDone[k % 3]);
     }
   }
 }
