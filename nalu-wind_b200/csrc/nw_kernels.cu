@@ -1012,9 +1012,6 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
  * data, same arithmetic, same order of additions as ls_tile_kernel: results
  * are bit-identical (tests/test_gpu_parity.py::test_pipe_kernel_*). */
 constexpr int kPipeThreads = 512;
-constexpr int kPipeMemWarps = 4;
-constexpr int kPipeMemThreads = kPipeMemWarps * 32;
-constexpr int kPipeCmpThreads = kPipeThreads - kPipeMemThreads;
 constexpr int kPipeHdrRing = 4;
 
 __device__ __forceinline__ void
@@ -1033,10 +1030,11 @@ mbar_arrive_cp_async(uint64_t* bar)
     : "memory");
 }
 /* barrier among the memory warps only (barrier 1; 0 is __syncthreads) */
+template <int NTHREADS>
 __device__ __forceinline__ void
 mem_warps_sync()
 {
-  asm volatile("bar.sync 1, %0;" ::"n"(kPipeMemThreads) : "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");
 }
 
 template <class P>
@@ -1067,7 +1065,7 @@ struct PipeSmem
   }
 };
 
-template <class P, int ND>
+template <class P, int ND, int MEMW>
 __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
   const MeshPlanDev mp,
   const LsPlanDev lp,
@@ -1081,6 +1079,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
   __shared__ __align__(16) LsTileHdr s_lhdr[kPipeHdrRing];
   __shared__ int32_t s_slice[3][kMaxTileEnts / 32 + 2];
 
+  constexpr int kPipeMemWarps = MEMW;
+  constexpr int kPipeMemThreads = MEMW * 32;
+  constexpr int kPipeCmpThreads = kPipeThreads - kPipeMemThreads;
   using S = PipeSmem<P>;
   const S L(mp, lp);
   const int tid = threadIdx.x;
@@ -1148,13 +1149,25 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
       ga = gb = -1;
       if (k < K) {
         const int32_t* blk = mp.haloBlock + (size_t)tile_of(k) * kHaloBlock;
-        ga = __ldg(blk + tid);
-        gb = __ldg(blk + kPipeMemThreads + tid);
+        ga = tid < kHaloBlock ? __ldg(blk + tid) : -1;
+        gb = kPipeMemThreads + tid < kHaloBlock
+               ? __ldg(blk + kPipeMemThreads + tid)
+               : -1;
       }
     };
     /* stage tile k (its headers are in the ring and visible to the memory
      * warps): issue only, completion is barFull[k % 3] */
-    auto stage = [&](int k, int32_t ga, int32_t gb) {
+    /* slice offset `tid` of tile k's row-keyed list (its LsTileHdr is in the
+     * ring): loaded a phase ahead of stage(k), which only stores it */
+    auto slice_early = [&](int k) -> int32_t {
+      if (k >= K)
+        return 0;
+      const LsTileHdr lh = s_lhdr[k % kPipeHdrRing];
+      return tid <= ((lh.nEnts + 31) >> 5)
+               ? __ldg(lp.sliceOff + lh.slicePtr + tid)
+               : 0;
+    };
+    auto stage = [&](int k, int32_t ga, int32_t gb, int32_t so) {
       const TileHdr h = s_hdr[k % kPipeHdrRing];
       const LsTileHdr lh = s_lhdr[k % kPipeHdrRing];
       const int stride = even_up_i(h.nOwnPad + h.nHalo);
@@ -1189,36 +1202,34 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
               tma_load_1d(s_go, lp.entGo + lh.entPtr, bEnt, bar);
           }
         }
-      /* slice offsets of the row-keyed list */
-      {
-        const int nSl = (lh.nEnts + 31) >> 5;
-        if (tid <= nSl)
-          s_slice[k % 3][tid] = __ldg(lp.sliceOff + lh.slicePtr + tid);
-      }
+      /* slice offsets of the row-keyed list (read by the memory warps only:
+       * ordered by their barrier) */
+      if (tid <= ((lh.nEnts + 31) >> 5))
+        s_slice[k % 3][tid] = so;
       /* halo nodes: asynchronous gathers, two from the early indices, the rest
        * through the list */
-      if (tid < h.nHalo) {
+      static_assert(2 * kPipeMemThreads >= kHaloBlock, "block coverage");
+      if (tid < h.nHalo && tid < kHaloBlock) {
 #pragma unroll
         for (int c = 0; c < P::NC; ++c)
           cp_async8(s_node + c * stride + h.nOwnPad + tid, nc.c[c] + ga);
       }
-      if (kPipeMemThreads + tid < h.nHalo) {
+      if (kPipeMemThreads + tid < h.nHalo && kPipeMemThreads + tid < kHaloBlock) {
 #pragma unroll
         for (int c = 0; c < P::NC; ++c)
           cp_async8(
             s_node + c * stride + h.nOwnPad + kPipeMemThreads + tid, nc.c[c] + gb);
       }
       const int32_t* halo = mp.haloNodes + h.haloPtr;
-      for (int q = 2 * kPipeMemThreads + tid; q < h.nHalo; q += kPipeMemThreads) {
+      for (int q = kHaloBlock + tid; q < h.nHalo; q += kPipeMemThreads) {
         const int32_t g = __ldg(halo + q);
 #pragma unroll
         for (int c = 0; c < P::NC; ++c)
           cp_async8(s_node + c * stride + h.nOwnPad + q, nc.c[c] + g);
       }
-      /* the slice offsets (plain stores) and the header ring must be visible
-       * to whoever passes the barrier: every memory thread arrives after its
-       * own stores; the asynchronous arrival counts its gathers in */
-      __threadfence_block();
+      /* the asynchronous arrival counts this thread's gathers in (the header
+       * ring reaches the compute warps through thread 0's release-arrive
+       * above, which follows the memory warps' barrier) */
       mbar_arrive_cp_async(bar);
     };
 
@@ -1230,10 +1241,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
       hdr_store(2, w2);
     }
     int32_t ga, gb;
-    mem_warps_sync();
+    mem_warps_sync<kPipeMemThreads>();
     for (int k = 0; k < 2 && k < K; ++k) {
       halo_early(k, ga, gb);
-      stage(k, ga, gb);
+      stage(k, ga, gb, slice_early(k));
     }
 
     for (int k = 0; k < K; ++k) {
@@ -1241,6 +1252,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
       /* issued now, needed further down */
       const int32_t wNext = hdr_load(k + 3);
       halo_early(k + 2, ga, gb);
+      const int32_t so = slice_early(k + 2);
 
       /* the physics of tile k is done: its results are in place and its node
        * slot is free -- stage tile k+2 into it first, so that the data has a
@@ -1251,7 +1263,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
        * k-1, ordered by the barrier at the end of the last iteration) */
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       if (k + 2 < K)
-        stage(k + 2, ga, gb);
+        stage(k + 2, ga, gb, so);
 
       /* ---- reduce tile k (phases 2-3) ---- */
       mbar_wait(&barFull[k % 3], par); /* the plan of tile k (long landed) */
@@ -1326,7 +1338,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
       }
       /* every memory warp has left the result slot and the row staging */
       hdr_store(k + 3, wNext);
-      mem_warps_sync();
+      mem_warps_sync<kPipeMemThreads>();
     }
   } else {
     /* =========================== compute warps ========================== */
@@ -3418,11 +3430,18 @@ launch_ls_tile(
   if (pipeEnv && !diagOut && mp.nTiles > 0) {
     const size_t pb = PipeSmem<P>(mp, lp).bytes();
     if (pb + 2048 <= 227 * 1024) {
-      e = set_smem(ls_pipe_kernel<P, ND>, pb);
-      if (e != cudaSuccess)
-        return e;
       const int grid = std::min(mp.nTiles, sm_count());
-      ls_pipe_kernel<P, ND><<<grid, kPipeThreads, pb, s>>>(mp, lp, nc, ec, o);
+      if (pipeEnv == 8) { /* NW_PIPE=8: eight memory warps, eight compute warps */
+        e = set_smem(ls_pipe_kernel<P, ND, 8>, pb);
+        if (e != cudaSuccess)
+          return e;
+        ls_pipe_kernel<P, ND, 8><<<grid, kPipeThreads, pb, s>>>(mp, lp, nc, ec, o);
+      } else {
+        e = set_smem(ls_pipe_kernel<P, ND, 4>, pb);
+        if (e != cudaSuccess)
+          return e;
+        ls_pipe_kernel<P, ND, 4><<<grid, kPipeThreads, pb, s>>>(mp, lp, nc, ec, o);
+      }
       return cudaGetLastError();
     }
   }

@@ -1087,10 +1087,11 @@ def test_abl_neutral_edge_size_vs_oracle(P, ctx):
     assert max(res.values()) < 1.0, res
 
 
-@pytest.mark.parametrize("periodic,dims,tile", [
-    ((False, False), (13, 11, 9), 48), ((True, True), (9, 8, 6), 40),
-    ((False, False), (30, 28, 26), 144)])
-def test_pipe_kernel_matches_tile_kernel(P, ctx, monkeypatch, periodic, dims, tile):
+@pytest.mark.parametrize("periodic,dims,tile,memw", [
+    ((False, False), (13, 11, 9), 48, "1"), ((True, True), (9, 8, 6), 40, "8"),
+    ((False, False), (30, 28, 26), 128, "1"), ((False, False), (30, 28, 26), 128, "8")])
+def test_pipe_kernel_matches_tile_kernel(P, ctx, monkeypatch, periodic, dims, tile,
+                                         memw):
     """NW_PIPE=1: the warp-specialised persistent kernel (memory warps stage tile
     k+2 and reduce tile k while compute warps run the physics of tile k+1) must
     give the bits of ls_tile_kernel -- same plan, same arithmetic, same order of
@@ -1104,7 +1105,7 @@ def test_pipe_kernel_matches_tile_kernel(P, ctx, monkeypatch, periodic, dims, ti
     pf = P.peclet_fn("classic", 1.0)
 
     def run(pipe):
-        monkeypatch.setenv("NW_PIPE", "1" if pipe else "0")
+        monkeypatch.setenv("NW_PIPE", memw if pipe else "0")
         out = []
         for kind, nd, fn in (
                 (P.NW_LINSYS_HYPRE, 1,
