@@ -1065,7 +1065,20 @@ struct PipeSmem
   }
 };
 
-template <class P, int ND, int MEMW>
+/* Roles (warp index): 0 .. NRED-1 reducers, NRED the stager, the rest compute.
+ *   stager  : per tile k: wait until the physics of tile k is done (its node
+ *             slot is free) and the reduction of tile k-1 is done (its result
+ *             slot is free), then stage tile k+2 -- all bulk copies, the halo
+ *             gather (cp.async), slice offsets, header ring.  Issue only.
+ *   reducers: per tile k: wait for its results, row walk + copy-out.
+ *   compute : 32-edge units are dealt round-robin to the compute warps ACROSS
+ *             tiles (a warp that is done with its units of tile k goes on to
+ *             tile k+1 at once), so a tile whose edge count is not a multiple
+ *             of the compute threads costs no idle round.
+ * mbarriers per slot (three): full (bulk-copy bytes + stager lanes' cp.async
+ * arrivals + the stager's own arrive), done (one arrival per compute warp),
+ * red (one arrival per reducer warp). */
+template <class P, int ND, int NRED>
 __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
   const MeshPlanDev mp,
   const LsPlanDev lp,
@@ -1074,17 +1087,16 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
   const typename P::Opts o)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t barFull[3], barDone[3];
+  __shared__ __align__(8) uint64_t barFull[3], barDone[3], barRed[3];
   __shared__ __align__(16) TileHdr s_hdr[kPipeHdrRing];
   __shared__ __align__(16) LsTileHdr s_lhdr[kPipeHdrRing];
   __shared__ int32_t s_slice[3][kMaxTileEnts / 32 + 2];
 
-  constexpr int kPipeMemWarps = MEMW;
-  constexpr int kPipeMemThreads = MEMW * 32;
-  constexpr int kPipeCmpThreads = kPipeThreads - kPipeMemThreads;
+  constexpr int kRedThreads = NRED * 32;
+  constexpr int kCmpWarps = kPipeThreads / 32 - NRED - 1;
   using S = PipeSmem<P>;
   const S L(mp, lp);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x;
   const int K = (mp.nTiles - (int)blockIdx.x + G - 1) / G; /* my tiles */
   auto tile_of = [&](int k) { return (int)blockIdx.x + k * G; };
@@ -1117,57 +1129,34 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
 
   if (tid == 0) {
     for (int b = 0; b < 3; ++b) {
-      mbar_init(&barFull[b], 1 + kPipeMemThreads);
-      mbar_init(&barDone[b], kPipeCmpThreads);
+      mbar_init(&barFull[b], 1 + 32);
+      mbar_init(&barDone[b], kCmpWarps);
+      mbar_init(&barRed[b], NRED);
     }
   }
   __syncthreads();
 
-  if (tid < kPipeMemThreads) {
-    /* =========================== memory warps =========================== */
-    const int lane = tid & 31, warp = tid >> 5;
-
-    /* headers of tile k -> ring slot k % kPipeHdrRing (lane i of warp 0:
-     * word i of the 64-byte TileHdr, lanes 16..31: the LsTileHdr) */
+  if (warp == NRED) {
+    /* ============================== stager ============================== */
+    /* headers of tile k -> ring slot k % kPipeHdrRing (lane i: word i of the
+     * 64-byte TileHdr, lanes 16..31: the LsTileHdr) */
     auto hdr_load = [&](int k) -> int32_t {
-      if (warp != 0 || k >= K)
+      if (k >= K)
         return 0;
       return lane < 16
                ? __ldg(reinterpret_cast<const int32_t*>(mp.tiles + tile_of(k)) + lane)
                : __ldg(reinterpret_cast<const int32_t*>(lp.tiles + tile_of(k)) + (lane - 16));
     };
     auto hdr_store = [&](int k, int32_t w) {
-      if (warp != 0 || k >= K)
+      if (k >= K)
         return;
       if (lane < 16)
         reinterpret_cast<int32_t*>(&s_hdr[k % kPipeHdrRing])[lane] = w;
       else
         reinterpret_cast<int32_t*>(&s_lhdr[k % kPipeHdrRing])[lane - 16] = w;
     };
-    /* my halo slots of tile k out of the fixed-stride block */
-    auto halo_early = [&](int k, int32_t& ga, int32_t& gb) {
-      ga = gb = -1;
-      if (k < K) {
-        const int32_t* blk = mp.haloBlock + (size_t)tile_of(k) * kHaloBlock;
-        ga = tid < kHaloBlock ? __ldg(blk + tid) : -1;
-        gb = kPipeMemThreads + tid < kHaloBlock
-               ? __ldg(blk + kPipeMemThreads + tid)
-               : -1;
-      }
-    };
-    /* stage tile k (its headers are in the ring and visible to the memory
-     * warps): issue only, completion is barFull[k % 3] */
-    /* slice offset `tid` of tile k's row-keyed list (its LsTileHdr is in the
-     * ring): loaded a phase ahead of stage(k), which only stores it */
-    auto slice_early = [&](int k) -> int32_t {
-      if (k >= K)
-        return 0;
-      const LsTileHdr lh = s_lhdr[k % kPipeHdrRing];
-      return tid <= ((lh.nEnts + 31) >> 5)
-               ? __ldg(lp.sliceOff + lh.slicePtr + tid)
-               : 0;
-    };
-    auto stage = [&](int k, int32_t ga, int32_t gb, int32_t so) {
+    /* stage tile k (its headers are in the ring, stored by this warp) */
+    auto stage = [&](int k) {
       const TileHdr h = s_hdr[k % kPipeHdrRing];
       const LsTileHdr lh = s_lhdr[k % kPipeHdrRing];
       const int stride = even_up_i(h.nOwnPad + h.nHalo);
@@ -1179,13 +1168,39 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
       int32_t* s_row = reinterpret_cast<int32_t*>(s_ent + L.entLen);
       int32_t* s_go = s_row + L.entLen;
       uint64_t* bar = &barFull[k % 3];
-      if (tid == 0)
-        mbar_expect_tx(
-          bar, node_copy_bytes(P::NC, h) + edge_stream_bytes(h, nin) + bEll +
-                 3u * bEnt);
-      /* bulk copies: copy q from lane 0 of memory warp q mod kPipeMemWarps */
-      if (lane == 0)
-        for (int q = warp; q < P::NC + 1 + nin + 4; q += kPipeMemWarps) {
+      /* halo gather first (the longest chain: index -> data): lanes take
+       * halo nodes q = lane, lane + 32, ...; indices from the fixed-stride
+       * block, beyond it from the list */
+      {
+        const int32_t* blk = mp.haloBlock + (size_t)tile_of(k) * kHaloBlock;
+        const int32_t* halo = mp.haloNodes + h.haloPtr;
+        for (int q0 = 0; q0 < h.nHalo; q0 += 4 * 32) {
+          int32_t g[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int q = q0 + u * 32 + lane;
+            g[u] = q < h.nHalo ? (q < kHaloBlock ? __ldg(blk + q) : __ldg(halo + q))
+                               : -1;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int q = q0 + u * 32 + lane;
+            if (q < h.nHalo) {
+#pragma unroll
+              for (int c = 0; c < P::NC; ++c)
+                cp_async8(s_node + c * stride + h.nOwnPad + q, nc.c[c] + g[u]);
+            }
+          }
+        }
+      }
+      /* slice offsets of the row-keyed list */
+      if (lane <= ((lh.nEnts + 31) >> 5))
+        s_slice[k % 3][lane] = __ldg(lp.sliceOff + lh.slicePtr + lane);
+      if (lane + 32 <= ((lh.nEnts + 31) >> 5))
+        s_slice[k % 3][lane + 32] = __ldg(lp.sliceOff + lh.slicePtr + lane + 32);
+      /* bulk copies */
+      if (lane == 0) {
+        for (int q = 0; q < P::NC + 1 + nin + 4; ++q) {
           if (q < P::NC)
             node_copy<P::NC>(q, s_node, stride, nc, h, bar);
           else if (q <= P::NC + nin)
@@ -1202,147 +1217,125 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
               tma_load_1d(s_go, lp.entGo + lh.entPtr, bEnt, bar);
           }
         }
-      /* slice offsets of the row-keyed list (read by the memory warps only:
-       * ordered by their barrier) */
-      if (tid <= ((lh.nEnts + 31) >> 5))
-        s_slice[k % 3][tid] = so;
-      /* halo nodes: asynchronous gathers, two from the early indices, the rest
-       * through the list */
-      static_assert(2 * kPipeMemThreads >= kHaloBlock, "block coverage");
-      if (tid < h.nHalo && tid < kHaloBlock) {
-#pragma unroll
-        for (int c = 0; c < P::NC; ++c)
-          cp_async8(s_node + c * stride + h.nOwnPad + tid, nc.c[c] + ga);
       }
-      if (kPipeMemThreads + tid < h.nHalo && kPipeMemThreads + tid < kHaloBlock) {
-#pragma unroll
-        for (int c = 0; c < P::NC; ++c)
-          cp_async8(
-            s_node + c * stride + h.nOwnPad + kPipeMemThreads + tid, nc.c[c] + gb);
-      }
-      const int32_t* halo = mp.haloNodes + h.haloPtr;
-      for (int q = kHaloBlock + tid; q < h.nHalo; q += kPipeMemThreads) {
-        const int32_t g = __ldg(halo + q);
-#pragma unroll
-        for (int c = 0; c < P::NC; ++c)
-          cp_async8(s_node + c * stride + h.nOwnPad + q, nc.c[c] + g);
-      }
-      /* the asynchronous arrival counts this thread's gathers in (the header
-       * ring reaches the compute warps through thread 0's release-arrive
-       * above, which follows the memory warps' barrier) */
+      /* every lane: asynchronous arrival for its gathers; then, after the
+       * warp's plain stores (header ring, slice offsets), lane 0 posts the
+       * byte count with a release-arrive */
       mbar_arrive_cp_async(bar);
+      __syncwarp();
+      if (lane == 0)
+        mbar_expect_tx(
+          bar, node_copy_bytes(P::NC, h) + edge_stream_bytes(h, nin) + bEll +
+                 3u * bEnt);
     };
 
-    /* prologue: headers of my first three tiles, tiles 0 and 1 staged */
     {
       const int32_t w0 = hdr_load(0), w1 = hdr_load(1), w2 = hdr_load(2);
       hdr_store(0, w0);
       hdr_store(1, w1);
       hdr_store(2, w2);
+      __syncwarp();
     }
-    int32_t ga, gb;
-    mem_warps_sync<kPipeMemThreads>();
-    for (int k = 0; k < 2 && k < K; ++k) {
-      halo_early(k, ga, gb);
-      stage(k, ga, gb, slice_early(k));
+    for (int k = 0; k < 2 && k < K; ++k)
+      stage(k);
+    for (int k = 0; k + 2 < K; ++k) {
+      const int32_t wNext = hdr_load(k + 3);
+      /* node slot of tile k+2 = that of tile k: free when its physics is done */
+      mbar_wait(&barDone[k % 3], (uint32_t)(k / 3) & 1u);
+      /* result slot of tile k+2 = that of tile k-1: free when it is reduced */
+      if (k >= 1)
+        mbar_wait(&barRed[(k - 1) % 3], (uint32_t)((k - 1) / 3) & 1u);
+      /* the copies overwrite shared memory read through the generic proxy */
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      stage(k + 2);
+      hdr_store(k + 3, wNext);
+      __syncwarp();
     }
-
+  } else if (warp < NRED) {
+    /* ============================= reducers ============================= */
     for (int k = 0; k < K; ++k) {
       const uint32_t par = (uint32_t)(k / 3) & 1u;
-      /* issued now, needed further down */
-      const int32_t wNext = hdr_load(k + 3);
-      halo_early(k + 2, ga, gb);
-      const int32_t so = slice_early(k + 2);
-
-      /* the physics of tile k is done: its results are in place and its node
-       * slot is free -- stage tile k+2 into it first, so that the data has a
-       * whole iteration to land, then reduce tile k */
-      mbar_wait(&barDone[k % 3], par);
-      /* the bulk copies overwrite shared memory read through the generic
-       * proxy (node slot: compute warps; result slot: the reduction of tile
-       * k-1, ordered by the barrier at the end of the last iteration) */
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      if (k + 2 < K)
-        stage(k + 2, ga, gb, so);
-
-      /* ---- reduce tile k (phases 2-3) ---- */
-      mbar_wait(&barFull[k % 3], par); /* the plan of tile k (long landed) */
-      {
-        const LsTileHdr lh = s_lhdr[k % kPipeHdrRing];
-        const double* s_res = s_res_of(k);
-        const uint32_t* s_ell = s_ell_of(k);
-        const EntInfo* s_ent = s_ent_of(k);
-        const int32_t* s_row = reinterpret_cast<const int32_t*>(s_ent + L.entLen);
-        const int32_t* s_go = s_row + L.entLen;
-        const int32_t* sliceOff = s_slice[k % 3];
-        for (int row0 = tid - lane; row0 < lh.nEnts; row0 += kPipeMemThreads) {
-          const int row = row0 + lane;
-          if (row < lh.nEnts) {
-            const int s = row0 >> 5;
-            const int o0 = sliceOff[s], o1 = sliceOff[s + 1];
-            const uint32_t* hp = s_ell + o0 + lane;
-            const int W = (o1 - o0) >> 5;
-            const EntInfo ei = s_ent[row];
-            double* vrow = s_vals + ei.base;
-            double diag = 0.0;
-            double rhs[P::NR];
+      mbar_wait(&barFull[k % 3], par); /* plan, headers, slice offsets */
+      mbar_wait(&barDone[k % 3], par); /* edge results */
+      const LsTileHdr lh = s_lhdr[k % kPipeHdrRing];
+      const double* s_res = s_res_of(k);
+      const uint32_t* s_ell = s_ell_of(k);
+      const EntInfo* s_ent = s_ent_of(k);
+      const int32_t* s_row = reinterpret_cast<const int32_t*>(s_ent + L.entLen);
+      const int32_t* s_go = s_row + L.entLen;
+      const int32_t* sliceOff = s_slice[k % 3];
+      for (int row0 = tid - lane; row0 < lh.nEnts; row0 += kRedThreads) {
+        const int row = row0 + lane;
+        if (row < lh.nEnts) {
+          const int s = row0 >> 5;
+          const int o0 = sliceOff[s], o1 = sliceOff[s + 1];
+          const uint32_t* hp = s_ell + o0 + lane;
+          const int W = (o1 - o0) >> 5;
+          const EntInfo ei = s_ent[row];
+          double* vrow = s_vals + ei.base;
+          double diag = 0.0;
+          double rhs[P::NR];
 #pragma unroll
-            for (int d = 0; d < P::NR; ++d)
-              rhs[d] = 0.0;
-            constexpr int kBlk = 4;
-            for (int w0 = 0; w0 < W; w0 += kBlk) {
-              uint32_t hv[kBlk];
+          for (int d = 0; d < P::NR; ++d)
+            rhs[d] = 0.0;
+          constexpr int kBlk = 4;
+          for (int w0 = 0; w0 < W; w0 += kBlk) {
+            uint32_t hv[kBlk];
 #pragma unroll
-              for (int u = 0; u < kBlk; ++u)
-                hv[u] = (w0 + u < W) ? hp[(w0 + u) * 32] : 0u;
-              double dg[kBlk], off[kBlk], rr[kBlk][P::NR];
+            for (int u = 0; u < kBlk; ++u)
+              hv[u] = (w0 + u < W) ? hp[(w0 + u) * 32] : 0u;
+            double dg[kBlk], off[kBlk], rr[kBlk][P::NR];
 #pragma unroll
-              for (int u = 0; u < kBlk; ++u)
-                if (hv[u] & kHeValid)
-                  P::contrib(
-                    he_side(hv[u]), s_res, L.resStride, (int)he_edge(hv[u]),
-                    dg[u], off[u], rr[u]);
+            for (int u = 0; u < kBlk; ++u)
+              if (hv[u] & kHeValid)
+                P::contrib(
+                  he_side(hv[u]), s_res, L.resStride, (int)he_edge(hv[u]), dg[u],
+                  off[u], rr[u]);
 #pragma unroll
-              for (int u = 0; u < kBlk; ++u)
-                if (hv[u] & kHeValid) {
-                  diag += dg[u];
+            for (int u = 0; u < kBlk; ++u)
+              if (hv[u] & kHeValid) {
+                diag += dg[u];
 #pragma unroll
-                  for (int d = 0; d < P::NR; ++d)
-                    rhs[d] += rr[u][d];
-                  double* dst = vrow + he_k(hv[u]);
-                  if (hv[u] & kHeDup)
-                    off[u] += *dst;
-                  *dst = off[u];
-                }
-            }
-            vrow[ei.diagK] = diag;
-            const int32_t delta = s_go[row] - (int32_t)ei.base;
-            for (int q = 0; q < (int)ei.nnz; ++q)
-              s_delta[ei.base + q] = delta;
-            const int64_t grow = s_row[row];
-#pragma unroll
-            for (int d = 0; d < P::NR; ++d)
-              lp.rhs[(int64_t)d * lp.rhsStride + grow] = rhs[d];
+                for (int d = 0; d < P::NR; ++d)
+                  rhs[d] += rr[u][d];
+                double* dst = vrow + he_k(hv[u]);
+                if (hv[u] & kHeDup)
+                  off[u] += *dst;
+                *dst = off[u];
+              }
           }
-          __syncwarp();
-          {
-            const int last = min(row0 + 31, lh.nEnts - 1);
-            const EntInfo e0 = s_ent[row0], e1 = s_ent[last];
-            const int end = (int)e1.base + (int)e1.nnz;
-#pragma unroll 4
-            for (int e = (int)e0.base + lane; e < end; e += 32)
-              lp.values[e + s_delta[e]] = s_vals[e];
-          }
-          __syncwarp();
+          vrow[ei.diagK] = diag;
+          const int32_t delta = s_go[row] - (int32_t)ei.base;
+          for (int q = 0; q < (int)ei.nnz; ++q)
+            s_delta[ei.base + q] = delta;
+          const int64_t grow = s_row[row];
+#pragma unroll
+          for (int d = 0; d < P::NR; ++d)
+            lp.rhs[(int64_t)d * lp.rhsStride + grow] = rhs[d];
         }
+        __syncwarp();
+        {
+          const int last = min(row0 + 31, lh.nEnts - 1);
+          const EntInfo e0 = s_ent[row0], e1 = s_ent[last];
+          const int end = (int)e1.base + (int)e1.nnz;
+#pragma unroll 4
+          for (int e = (int)e0.base + lane; e < end; e += 32)
+            lp.values[e + s_delta[e]] = s_vals[e];
+        }
+        __syncwarp();
       }
-      /* every memory warp has left the result slot and the row staging */
-      hdr_store(k + 3, wNext);
-      mem_warps_sync<kPipeMemThreads>();
+      /* this warp has left the result slot; the row staging is shared by the
+       * reducer warps: all of them are through before the next tile's rows
+       * are written */
+      __syncwarp();
+      if (lane == 0)
+        mbar_arrive(&barRed[k % 3]);
+      asm volatile("bar.sync 1, %0;" ::"n"(kRedThreads) : "memory");
     }
   } else {
-    /* =========================== compute warps ========================== */
-    const int ct = tid - kPipeMemThreads;
+    /* ============================== compute ============================= */
+    const int cw = warp - NRED - 1; /* 0 .. kCmpWarps-1 */
+    int g0 = 0;                     /* units dealt before this tile, mod kCmpWarps */
     for (int k = 0; k < K; ++k) {
       const uint32_t par = (uint32_t)(k / 3) & 1u;
       mbar_wait(&barFull[k % 3], par);
@@ -1351,25 +1344,36 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
       double* s_res = s_res_of(k);
       const uint32_t* s_lr = s_lr_of(k);
       const SmemLd ld{s_node_of(k), stride};
-      for (int j = ct; j < h.nEdges; j += kPipeCmpThreads) {
-        const uint32_t v = s_lr[j];
-        const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
-        double av[ND];
+      const int nUnits = (h.nEdges + 31) >> 5;
+      /* my first unit of this tile: (g0 + u) % kCmpWarps == cw */
+      int u = cw - g0;
+      if (u < 0)
+        u += kCmpWarps;
+      for (; u < nUnits; u += kCmpWarps) {
+        const int j = u * 32 + lane;
+        if (j < h.nEdges) {
+          const uint32_t v = s_lr[j];
+          const int l = (int)(v & 0xffffu), r = (int)(v >> 16);
+          double av[ND];
 #pragma unroll
-        for (int d = 0; d < ND; ++d)
-          av[d] = s_res[d * L.resStride + j];
-        double mdot = 0.0, pecfac = 0.0;
-        if (P::kNeedsMdot)
-          mdot = s_res[kMdot * L.resStride + j];
-        if (hasPec)
-          pecfac = s_res[kPec * L.resStride + j];
-        double res[P::NRES];
-        P::compute(ld, l, r, av, mdot, pecfac, o, res);
+          for (int d = 0; d < ND; ++d)
+            av[d] = s_res[d * L.resStride + j];
+          double mdot = 0.0, pecfac = 0.0;
+          if (P::kNeedsMdot)
+            mdot = s_res[kMdot * L.resStride + j];
+          if (hasPec)
+            pecfac = s_res[kPec * L.resStride + j];
+          double res[P::NRES];
+          P::compute(ld, l, r, av, mdot, pecfac, o, res);
 #pragma unroll
-        for (int q = 0; q < P::NRES; ++q)
-          s_res[q * L.resStride + j] = res[q];
+          for (int q = 0; q < P::NRES; ++q)
+            s_res[q * L.resStride + j] = res[q];
+        }
       }
-      mbar_arrive(&barDone[k % 3]);
+      g0 = (g0 + nUnits) % kCmpWarps;
+      __syncwarp();
+      if (lane == 0)
+        mbar_arrive(&barDone[k % 3]);
     }
   }
 }
@@ -3431,12 +3435,12 @@ launch_ls_tile(
     const size_t pb = PipeSmem<P>(mp, lp).bytes();
     if (pb + 2048 <= 227 * 1024) {
       const int grid = std::min(mp.nTiles, sm_count());
-      if (pipeEnv == 8) { /* NW_PIPE=8: eight memory warps, eight compute warps */
-        e = set_smem(ls_pipe_kernel<P, ND, 8>, pb);
+      if (pipeEnv == 8) { /* NW_PIPE=8: six reducer warps, nine compute warps */
+        e = set_smem(ls_pipe_kernel<P, ND, 6>, pb);
         if (e != cudaSuccess)
           return e;
-        ls_pipe_kernel<P, ND, 8><<<grid, kPipeThreads, pb, s>>>(mp, lp, nc, ec, o);
-      } else {
+        ls_pipe_kernel<P, ND, 6><<<grid, kPipeThreads, pb, s>>>(mp, lp, nc, ec, o);
+      } else { /* four reducer warps, one stager, eleven compute warps */
         e = set_smem(ls_pipe_kernel<P, ND, 4>, pb);
         if (e != cudaSuccess)
           return e;
