@@ -1065,8 +1065,8 @@ struct PipeSmem
   }
 };
 
-/* Roles (warp index): 0 .. NRED-1 reducers, NRED the stager, the rest compute.
- *   stager  : per tile k: wait until the physics of tile k is done (its node
+/* Roles (warp index): 0 .. NRED-1 reducers, then NSTG stagers, the rest compute.
+ *   stagers : per tile k: wait until the physics of tile k is done (its node
  *             slot is free) and the reduction of tile k-1 is done (its result
  *             slot is free), then stage tile k+2 -- all bulk copies, the halo
  *             gather (cp.async), slice offsets, header ring.  Issue only.
@@ -1078,7 +1078,7 @@ struct PipeSmem
  * mbarriers per slot (three): full (bulk-copy bytes + stager lanes' cp.async
  * arrivals + the stager's own arrive), done (one arrival per compute warp),
  * red (one arrival per reducer warp). */
-template <class P, int ND, int NRED>
+template <class P, int ND, int NRED, int NSTG>
 __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
   const MeshPlanDev mp,
   const LsPlanDev lp,
@@ -1093,7 +1093,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
   __shared__ int32_t s_slice[3][kMaxTileEnts / 32 + 2];
 
   constexpr int kRedThreads = NRED * 32;
-  constexpr int kCmpWarps = kPipeThreads / 32 - NRED - 1;
+  constexpr int kCmpWarps = kPipeThreads / 32 - NRED - NSTG;
+  constexpr int kStgThreads = NSTG * 32;
   using S = PipeSmem<P>;
   const S L(mp, lp);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1129,26 +1130,34 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
 
   if (tid == 0) {
     for (int b = 0; b < 3; ++b) {
-      mbar_init(&barFull[b], 1 + 32);
+      mbar_init(&barFull[b], 1 + kStgThreads);
       mbar_init(&barDone[b], kCmpWarps);
       mbar_init(&barRed[b], NRED);
     }
   }
   __syncthreads();
 
-  if (warp == NRED) {
-    /* ============================== stager ============================== */
+  if (warp >= NRED && warp < NRED + NSTG) {
+    /* ============================== stagers ============================= */
+    const int sw = warp - NRED;        /* stager warp index */
+    const int st = sw * 32 + lane;     /* stager thread index */
+    auto stagers_sync = [&]() {
+      if (NSTG > 1)
+        asm volatile("bar.sync 2, %0;" ::"n"(kStgThreads) : "memory");
+      else
+        __syncwarp();
+    };
     /* headers of tile k -> ring slot k % kPipeHdrRing (lane i: word i of the
      * 64-byte TileHdr, lanes 16..31: the LsTileHdr) */
     auto hdr_load = [&](int k) -> int32_t {
-      if (k >= K)
+      if (k >= K || sw != 0)
         return 0;
       return lane < 16
                ? __ldg(reinterpret_cast<const int32_t*>(mp.tiles + tile_of(k)) + lane)
                : __ldg(reinterpret_cast<const int32_t*>(lp.tiles + tile_of(k)) + (lane - 16));
     };
     auto hdr_store = [&](int k, int32_t w) {
-      if (k >= K)
+      if (k >= K || sw != 0)
         return;
       if (lane < 16)
         reinterpret_cast<int32_t*>(&s_hdr[k % kPipeHdrRing])[lane] = w;
@@ -1174,17 +1183,17 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
       {
         const int32_t* blk = mp.haloBlock + (size_t)tile_of(k) * kHaloBlock;
         const int32_t* halo = mp.haloNodes + h.haloPtr;
-        for (int q0 = 0; q0 < h.nHalo; q0 += 4 * 32) {
+        for (int q0 = 0; q0 < h.nHalo; q0 += 4 * kStgThreads) {
           int32_t g[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int q = q0 + u * 32 + lane;
+            const int q = q0 + u * kStgThreads + st;
             g[u] = q < h.nHalo ? (q < kHaloBlock ? __ldg(blk + q) : __ldg(halo + q))
                                : -1;
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int q = q0 + u * 32 + lane;
+            const int q = q0 + u * kStgThreads + st;
             if (q < h.nHalo) {
 #pragma unroll
               for (int c = 0; c < P::NC; ++c)
@@ -1194,13 +1203,15 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
         }
       }
       /* slice offsets of the row-keyed list */
-      if (lane <= ((lh.nEnts + 31) >> 5))
-        s_slice[k % 3][lane] = __ldg(lp.sliceOff + lh.slicePtr + lane);
-      if (lane + 32 <= ((lh.nEnts + 31) >> 5))
-        s_slice[k % 3][lane + 32] = __ldg(lp.sliceOff + lh.slicePtr + lane + 32);
-      /* bulk copies */
+      if (sw == 0) {
+        if (lane <= ((lh.nEnts + 31) >> 5))
+          s_slice[k % 3][lane] = __ldg(lp.sliceOff + lh.slicePtr + lane);
+        if (lane + 32 <= ((lh.nEnts + 31) >> 5))
+          s_slice[k % 3][lane + 32] = __ldg(lp.sliceOff + lh.slicePtr + lane + 32);
+      }
+      /* bulk copies: copy q from lane 0 of stager warp q mod NSTG */
       if (lane == 0) {
-        for (int q = 0; q < P::NC + 1 + nin + 4; ++q) {
+        for (int q = sw; q < P::NC + 1 + nin + 4; q += NSTG) {
           if (q < P::NC)
             node_copy<P::NC>(q, s_node, stride, nc, h, bar);
           else if (q <= P::NC + nin)
@@ -1223,7 +1234,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
        * byte count with a release-arrive */
       mbar_arrive_cp_async(bar);
       __syncwarp();
-      if (lane == 0)
+      if (st == 0)
         mbar_expect_tx(
           bar, node_copy_bytes(P::NC, h) + edge_stream_bytes(h, nin) + bEll +
                  3u * bEnt);
@@ -1234,7 +1245,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
       hdr_store(0, w0);
       hdr_store(1, w1);
       hdr_store(2, w2);
-      __syncwarp();
+      stagers_sync();
     }
     for (int k = 0; k < 2 && k < K; ++k)
       stage(k);
@@ -1249,7 +1260,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       stage(k + 2);
       hdr_store(k + 3, wNext);
-      __syncwarp();
+      stagers_sync();
     }
   } else if (warp < NRED) {
     /* ============================= reducers ============================= */
@@ -1334,7 +1345,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) ls_pipe_kernel(
     }
   } else {
     /* ============================== compute ============================= */
-    const int cw = warp - NRED - 1; /* 0 .. kCmpWarps-1 */
+    const int cw = warp - NRED - NSTG; /* 0 .. kCmpWarps-1 */
     int g0 = 0;                     /* units dealt before this tile, mod kCmpWarps */
     for (int k = 0; k < K; ++k) {
       const uint32_t par = (uint32_t)(k / 3) & 1u;
@@ -3435,17 +3446,21 @@ launch_ls_tile(
     const size_t pb = PipeSmem<P>(mp, lp).bytes();
     if (pb + 2048 <= 227 * 1024) {
       const int grid = std::min(mp.nTiles, sm_count());
-      if (pipeEnv == 8) { /* NW_PIPE=8: six reducer warps, nine compute warps */
-        e = set_smem(ls_pipe_kernel<P, ND, 6>, pb);
-        if (e != cudaSuccess)
-          return e;
-        ls_pipe_kernel<P, ND, 6><<<grid, kPipeThreads, pb, s>>>(mp, lp, nc, ec, o);
-      } else { /* four reducer warps, one stager, eleven compute warps */
-        e = set_smem(ls_pipe_kernel<P, ND, 4>, pb);
-        if (e != cudaSuccess)
-          return e;
-        ls_pipe_kernel<P, ND, 4><<<grid, kPipeThreads, pb, s>>>(mp, lp, nc, ec, o);
-      }
+      /* NW_PIPE=<stagers><reducers>: 32 (default for 1), 43, 22 */
+#define NW_PIPE_LAUNCH(NR, NS)                                                   \
+  do {                                                                          \
+    e = set_smem(ls_pipe_kernel<P, ND, NR, NS>, pb);                            \
+    if (e != cudaSuccess)                                                       \
+      return e;                                                                 \
+    ls_pipe_kernel<P, ND, NR, NS><<<grid, kPipeThreads, pb, s>>>(mp, lp, nc, ec, o); \
+  } while (0)
+      if (pipeEnv == 43)
+        NW_PIPE_LAUNCH(3, 4);
+      else if (pipeEnv == 22)
+        NW_PIPE_LAUNCH(2, 2);
+      else
+        NW_PIPE_LAUNCH(2, 3);
+#undef NW_PIPE_LAUNCH
       return cudaGetLastError();
     }
   }
