@@ -1029,14 +1029,6 @@ mbar_arrive_cp_async(uint64_t* bar)
     "cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar))
     : "memory");
 }
-/* barrier among the memory warps only (barrier 1; 0 is __syncthreads) */
-template <int NTHREADS>
-__device__ __forceinline__ void
-mem_warps_sync()
-{
-  asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");
-}
-
 template <class P>
 struct PipeSmem
 {
@@ -3438,15 +3430,16 @@ launch_ls_tile(
     e = launch_ls_stream<P, ND>(mp, lp, nc, ec, o, s, &launched);
   if (e != cudaSuccess || launched)
     return e;
-  /* NW_PIPE=1: the warp-specialised persistent kernel, when two slots of this
-   * mesh's tiles fit one CTA's shared memory (tiles of <= ~160 nodes for
-   * momentum on a hex mesh) and no extract_diagonal pass is asked for */
+  /* NW_PIPE (experiment): the warp-specialised persistent
+   * kernel, when its slots fit one CTA's shared memory (tiles of <= ~136 nodes
+   * for momentum on a hex mesh) and no extract_diagonal pass is asked for.
+   * Bit-identical to the tile kernel, measured slower: not the default. */
   const int pipeEnv = env_int("NW_PIPE", 0); /* read per call: tests toggle it */
   if (pipeEnv && !diagOut && mp.nTiles > 0) {
     const size_t pb = PipeSmem<P>(mp, lp).bytes();
     if (pb + 2048 <= 227 * 1024) {
       const int grid = std::min(mp.nTiles, sm_count());
-      /* NW_PIPE=<stagers><reducers>: 32 (default for 1), 43, 22 */
+      /* NW_PIPE=<stagers><reducers>: 32 (also for any other non-zero value), 43 */
 #define NW_PIPE_LAUNCH(NR, NS)                                                   \
   do {                                                                          \
     e = set_smem(ls_pipe_kernel<P, ND, NR, NS>, pb);                            \
@@ -3456,8 +3449,6 @@ launch_ls_tile(
   } while (0)
       if (pipeEnv == 43)
         NW_PIPE_LAUNCH(3, 4);
-      else if (pipeEnv == 22)
-        NW_PIPE_LAUNCH(2, 2);
       else
         NW_PIPE_LAUNCH(2, 3);
 #undef NW_PIPE_LAUNCH
@@ -3467,18 +3458,6 @@ launch_ls_tile(
   const size_t bytes = ls_tile_smem<P>(mp, lp);
   if (bytes > 227 * 1024)
     return cudaErrorInvalidConfiguration;
-  /* experiment: NW_TILE_THREADS=160 runs 5-warp CTAs, three per SM at 128
-   * registers (needs a tile whose shared memory fits three times, e.g.
-   * NW_TILE_NODES=128) */
-  static const int thrEnv = env_int("NW_TILE_THREADS", 0);
-  if (thrEnv == 160 && 3 * (bytes + 2048) <= 228 * 1024) {
-    e = set_smem(ls_tile_kernel<P, ND, 3, 160>, bytes);
-    if (e != cudaSuccess)
-      return e;
-    ls_tile_kernel<P, ND, 3, 160><<<mp.nTiles, 160, bytes, s>>>(
-      with_pf(mp, ls_tile_kernel<P, ND, 3, 160>, 160, bytes), lp, nc, ec, o);
-    return cudaGetLastError();
-  }
   e = set_smem(ls_tile_kernel<P, ND>, bytes);
   if (e != cudaSuccess)
     return e;

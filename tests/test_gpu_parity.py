@@ -1089,7 +1089,7 @@ def test_abl_neutral_edge_size_vs_oracle(P, ctx):
 
 @pytest.mark.parametrize("periodic,dims,tile,memw", [
     ((False, False), (13, 11, 9), 48, "32"), ((True, True), (9, 8, 6), 40, "43"),
-    ((False, False), (30, 28, 26), 128, "32"), ((False, False), (30, 28, 26), 128, "22"),
+    ((False, False), (30, 28, 26), 128, "32"),
     ((False, False), (30, 28, 26), 128, "43")])
 def test_pipe_kernel_matches_tile_kernel(P, ctx, monkeypatch, periodic, dims, tile,
                                          memw):

@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "nalu-wind_b200", "libnalu_edge_b200.so")
-KEEP = ("ls_tile_kernel", "scalar_pair_tile_kernel", "mdot_tile_kernel",
+KEEP = ("ls_tile_kernel", "ls_pipe_kernel", "scalar_pair_tile_kernel", "mdot_tile_kernel",
         "peclet_tile_kernel", "grad_tile_kernel", "p2p_", "periodic_update",
         "momentum_mono_atomic", "ls_atomic_kernel")
 
