@@ -302,6 +302,122 @@ build_mesh_plan(const MeshInput& in, MeshPlan& mp)
   std::vector<int64_t> leafBegin;
   rcb(items, pts, nLeaves, leafBegin);
   tm.mark("mesh: rcb");
+  /* ---- cut refinement ----
+   * Coordinate bisection cuts a curvilinear or unstructured mesh obliquely:
+   * ragged tile boundaries, i.e. more cut edges (each is evaluated in both
+   * tiles) and more halo nodes (profiles/r02f_bench_warped: 1.8 halo nodes
+   * per node against 1.06 on the regular box).  When the cut is above what a
+   * lattice gives, a few greedy passes move a row group to the neighbouring
+   * tile that holds more of its edges than its own tile does (every move
+   * lowers the cut; tiles may grow by ~8 % and never run empty).  Serial and
+   * in group order, so the result is deterministic.  NW_TILE_REFINE=0
+   * switches it off. */
+  {
+    const int64_t nT = (int64_t)leafBegin.size() - 1;
+    const char* env = std::getenv("NW_TILE_REFINE");
+    const bool wanted = !(env && env[0] == '0');
+    if (wanted && nT > 1 && E > 0) {
+      std::vector<int32_t> tileOfGroup(G), groupOfNode(N);
+      for (int64_t t = 0; t < nT; ++t)
+        for (int64_t gi = leafBegin[t]; gi < leafBegin[t + 1]; ++gi)
+          tileOfGroup[items[gi]] = (int32_t)t;
+      for (int64_t g = 0; g < G; ++g)
+        for (int64_t i = gStart[g]; i < gStart[g + 1]; ++i)
+          groupOfNode[order[i]] = (int32_t)g;
+      int64_t cut = 0;
+#pragma omp parallel for reduction(+ : cut) schedule(static)
+      for (int64_t e = 0; e < E; ++e) {
+        const int32_t ga = groupOfNode[mp.edgeNodes[2 * e]];
+        const int32_t gb = groupOfNode[mp.edgeNodes[2 * e + 1]];
+        cut += tileOfGroup[ga] != tileOfGroup[gb];
+      }
+      /* a hex lattice in tiles of T nodes cuts ~ (2 / cbrt(T)) / 2 of its
+       * edges (0.19 at T = 192); start refining a fifth above that */
+      const double lattice = 1.0 / std::cbrt((double)std::max(T, 8));
+      if ((double)cut > 1.2 * lattice * (double)E) {
+        std::vector<int64_t> aptr(G + 1, 0);
+        for (int64_t e = 0; e < E; ++e) {
+          const int32_t ga = groupOfNode[mp.edgeNodes[2 * e]];
+          const int32_t gb = groupOfNode[mp.edgeNodes[2 * e + 1]];
+          if (ga != gb) {
+            aptr[ga + 1]++;
+            aptr[gb + 1]++;
+          }
+        }
+        for (int64_t g = 0; g < G; ++g)
+          aptr[g + 1] += aptr[g];
+        std::vector<int32_t> adj(aptr[G]);
+        {
+          std::vector<int64_t> fill(aptr.begin(), aptr.end() - 1);
+          for (int64_t e = 0; e < E; ++e) {
+            const int32_t ga = groupOfNode[mp.edgeNodes[2 * e]];
+            const int32_t gb = groupOfNode[mp.edgeNodes[2 * e + 1]];
+            if (ga != gb) {
+              adj[fill[ga]++] = gb;
+              adj[fill[gb]++] = ga;
+            }
+          }
+        }
+        std::vector<int32_t> tileSize(nT, 0);
+        for (int64_t g = 0; g < G; ++g)
+          tileSize[tileOfGroup[g]] += (int32_t)(gStart[g + 1] - gStart[g]);
+        const int32_t tMax =
+          (int32_t)std::min<int64_t>(kMaxTileEnts, T + std::max(2, T / 12));
+        std::vector<std::pair<int32_t, int32_t>> cnt; /* (tile, edges) */
+        for (int pass = 0; pass < 4; ++pass) {
+          int64_t moved = 0;
+          for (int64_t g = 0; g < G; ++g) {
+            const int32_t t = tileOfGroup[g];
+            cnt.clear();
+            int32_t own = 0;
+            for (int64_t q = aptr[g]; q < aptr[g + 1]; ++q) {
+              const int32_t tn = tileOfGroup[adj[q]];
+              if (tn == t) {
+                ++own;
+                continue;
+              }
+              bool found = false;
+              for (auto& c : cnt)
+                if (c.first == tn) {
+                  ++c.second;
+                  found = true;
+                  break;
+                }
+              if (!found)
+                cnt.push_back({tn, 1});
+            }
+            int32_t bestT = -1, bestC = own;
+            for (const auto& c : cnt)
+              if (c.second > bestC || (c.second == bestC && bestT >= 0 && c.first < bestT)) {
+                bestT = c.first;
+                bestC = c.second;
+              }
+            const int32_t gs = (int32_t)(gStart[g + 1] - gStart[g]);
+            if (bestT >= 0 && bestC > own && tileSize[bestT] + gs <= tMax &&
+                tileSize[t] - gs >= 1) {
+              tileOfGroup[g] = bestT;
+              tileSize[bestT] += gs;
+              tileSize[t] -= gs;
+              ++moved;
+            }
+          }
+          if (moved == 0)
+            break;
+        }
+        /* back to the leaf lists: groups of a tile in ascending group id */
+        std::vector<int64_t> lb(nT + 1, 0);
+        for (int64_t g = 0; g < G; ++g)
+          lb[tileOfGroup[g] + 1]++;
+        for (int64_t t = 0; t < nT; ++t)
+          lb[t + 1] += lb[t];
+        std::vector<int64_t> fill(lb.begin(), lb.end() - 1);
+        for (int64_t g = 0; g < G; ++g)
+          items[fill[tileOfGroup[g]]++] = (int32_t)g;
+        leafBegin = lb;
+      }
+    }
+  }
+  tm.mark("mesh: cut refinement");
   const int64_t nTiles = (int64_t)leafBegin.size() - 1;
   mp.nTiles = nTiles;
   mp.tiles.assign(nTiles, TileHdr());
