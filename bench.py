@@ -101,6 +101,12 @@ def parse():
                     help="e2e leg: nw_field_upload on the compute stream instead "
                          "of the pipelined nw_field_stage / nw_field_commit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="eager", choices=["eager", "plain"],
+                    help="N > 1: 'eager' (default) lets every edge assembly run "
+                         "its boundary tiles first and send the shared rows while "
+                         "the interior tiles are assembled (nw_linsys_set_eager_"
+                         "exchange; the sweep has no other contribution before "
+                         "loadComplete); 'plain' sends them in loadComplete")
     ap.add_argument("--fuse-scalars", dest="no_fuse_scalars", action="store_false",
                     default=True,
                     help="--sst: assemble the TKE and SDR systems through "
@@ -428,6 +434,12 @@ def workload_config(args, n_gpus):
               "126 MB L2), no explicit flush" % (
                   ((n + 1) ** 3 * 8 * 60) / 1e9),
         "tile_nodes": args.tile if args.tile else "default",
+        "exchange": ("n/a (one GPU)" if n_gpus == 1 else
+                     "boundary tiles first, shared rows / nodes pushed over NVLink "
+                     "behind them while the interior tiles run"
+                     if getattr(args, "exchange", "eager") == "eager" and
+                     os.environ.get("NW_HALO_OVERLAP", "1") != "0" else
+                     "after the full kernel (loadComplete / post_work)"),
     }
 
 
@@ -436,6 +448,7 @@ class Sweep:
 
     def __init__(self, P, ctx, args, dims, world, rank, sst, torch, kind="box"):
         self.P, self.ctx, self.args, self.sst, self.torch = P, ctx, args, sst, torch
+        self.world = world
         t0 = time.time()
         self.box, self.fields = build_case(P, dims, world, rank, kind)
         t1 = time.time()
@@ -472,6 +485,8 @@ class Sweep:
             ls.set_scatter_mode(mode)
             ls.buildEdgeToNodeGraph()
             ls.finalizeLinearSystem()
+            if world > 1:
+                ls.set_eager_exchange(args.exchange == "eager")
             self.systems[name] = ls
         t3 = time.time()
         # r = nodes per edge, z = non-zeros per row: the mesh's own figures for
@@ -587,6 +602,18 @@ class Sweep:
         if self.sst:
             # scalar assemblies (one fused launch or two) + the paired gradient
             n += (2 if self.args.no_fuse_scalars else 1) + 1
+        if self.world > 1:
+            # halo exchange kernels (peer-memory transport): a linear system
+            # pushes once and pulls twice (values, rhs), a nodal sum pushes and
+            # pulls once; boundary-tiles-first splits the producing launch
+            overlap = (self.args.exchange == "eager" and
+                       os.environ.get("NW_HALO_OVERLAP", "1") != "0")
+            n_ls = 2 + (2 if self.sst else 0)
+            n_grad_calls = 2 + (1 if self.sst else 0)
+            n_sums = 2 + (2 if self.sst else 0)
+            n += n_ls * 3 + n_sums * 2
+            if overlap:
+                n += n_ls + n_grad_calls
         return n
 
     def norms(self, glob):
@@ -712,6 +739,19 @@ def main():
     sustained = {"value": edges_total * ksus / (ms_sus * 1e-3) / 1e6,
                  "unit": "Medges/s", "steps": ksus, "seconds": ms_sus * 1e-3}
 
+    # N > 1: the same sweep with the halo exchanges switched off (the results
+    # are then wrong and are not used): what the exchanges cost in this line
+    exchange = None
+    if world > 1:
+        ctx.debug_skip_exchange(True)
+        for _ in range(2):
+            sw.run()
+        ms_skip = time_steps(sw, args.steps)
+        ctx.debug_skip_exchange(False)
+        sw.run()  # leave consistent state behind
+        exchange = {"ms_per_step_without_exchanges": ms_skip / args.steps,
+                    "share_of_step": 1.0 - ms_skip / ms_max}
+
     # dominant kernel: momentum UVW assembly, timed live inside the region
     kev = sw.kernel_events
     mom_ms = float(np.mean([a.elapsed_time(b) for a, b in kev["momentum_uvw"]]))
@@ -748,6 +788,10 @@ def main():
     per_kernel = {}
     for k, v in kev.items():
         if k == "load_complete":
+            if args.detail and rank == 0 and v:
+                print("  %-14s %8.3f ms x%.0f  (shared-row exchange)" % (
+                    k, float(np.mean([a.elapsed_time(b) for a, b in v])),
+                    len(v) / args.steps), file=sys.stderr)
             continue
         tms = float(np.mean([a.elapsed_time(b) for a, b in v]))
         gbs = ALG_BYTES_RUN[k] * edges_local / (tms * 1e-3) / 1e9
@@ -877,6 +921,8 @@ def main():
     }
     if gate is not None:
         line["parity_gate"] = gate
+    if exchange is not None:
+        line["halo_exchange"] = exchange
 
     # ---------------- BASELINE configs[2]: 512^3 SST over the N GPUs --------
     want_ns = args.north_star == "on" or (args.north_star == "auto" and world > 1)

@@ -127,7 +127,8 @@ ABI_SYMBOLS = [
     "nw_linsys_set_skipped_rows", "nw_linsys_build_edge_to_node_graph",
     "nw_linsys_finalize", "nw_linsys_get_sizes", "nw_linsys_get_graph",
     "nw_linsys_get_edge_slots", "nw_linsys_zero",
-    "nw_linsys_set_scatter_mode", "nw_assemble_continuity_edge",
+    "nw_linsys_set_scatter_mode", "nw_linsys_set_eager_exchange",
+    "nw_assemble_continuity_edge",
     "nw_assemble_scalar_edge", "nw_assemble_scalar_edge_pair", "nw_assemble_momentum_edge",
     "nw_assemble_mass_bdf_node", "nw_assemble_wall_dist_edge",
     "nw_assemble_wall_dist_node", "nw_linsys_write_preassembly_files", "nw_linsys_sum_into", "nw_linsys_reset_rows",
@@ -210,6 +211,7 @@ def lib():
     L.nw_linsys_get_edge_slots.argtypes = [vp, c_i64p, c_i64p]
     L.nw_linsys_zero.argtypes = [vp]
     L.nw_linsys_set_scatter_mode.argtypes = [vp, C.c_int]
+    L.nw_linsys_set_eager_exchange.argtypes = [vp, C.c_int]
     L.nw_assemble_continuity_edge.argtypes = [vp, C.POINTER(ContinuityOpts)]
     L.nw_assemble_scalar_edge.argtypes = [vp, C.c_int, C.c_int, C.c_int,
                                           C.POINTER(ScalarOpts)]
@@ -554,6 +556,11 @@ class LinearSystem:
 
     def set_scatter_mode(self, mode):
         _chk(lib().nw_linsys_set_scatter_mode(self.h, mode))
+
+    def set_eager_exchange(self, on=True):
+        """The edge assembly is the last contribution to shared rows before
+        loadComplete: send them from the assembly call (boundary tiles first)."""
+        _chk(lib().nw_linsys_set_eager_exchange(self.h, 1 if on else 0))
 
     def assemble_continuity_edge(self, dt=1.0, gamma1=1.0, noc_fac=1.0,
                                  interp_together=1.0, solve_incompressible=0.0):

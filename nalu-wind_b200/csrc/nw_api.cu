@@ -136,6 +136,7 @@ nw_ctx_create(int cuda_device, nw_ctx** out)
 }
 
 static int p2p_init(nw_ctx* ctx);
+static int p2p_complete_pending(nw_ctx* ctx);
 static int p2p_check_error(nw_ctx* ctx);
 static void p2p_queue_error_read(nw_ctx* ctx, cudaStream_t s);
 static int p2p_error_after_sync(nw_ctx* ctx);
@@ -996,6 +997,84 @@ nw_peclet_edge(nw_mesh* mesh, int viscosity_field, const nw_peclet_opts* opts)
 }
 
 static int node_halo_sum(nw_mesh* mesh, nw_field_t* f);
+static P2pDev p2p_next(nw_ctx* ctx);
+static int node_halo_sum_end(NodeHaloSum* st);
+static bool node_halo_overlap_applicable(nw_mesh* mesh);
+static int periodic_update(nw_mesh* mesh, nw_field_t* f);
+
+/* NodalGradEdgeAlg kernel + NodalGradAlgDriver::post_work
+ * (NodalGradAlgDriver.C:41-71: parallel sum, periodic update).  On several
+ * ranks over peer memory the exchange is fused into the kernel: the tiles
+ * that own shared nodes run first and store their partial sums straight into
+ * the other sharers' windows (the last of them publishes the epoch), the
+ * interior tiles are computed while the data travels, and one small kernel
+ * adds what has arrived.  The two fields of a pair travel as ONE exchange of
+ * 2 x ndim components. */
+static int
+grad_with_post_work(
+  nw_mesh* mesh, int dim1, const NodeComps& nc, const double* vol,
+  const EdgeComps& ec, double* const* out, nw_field_t* const* grads, int nGrads)
+{
+  nw_ctx* ctx = mesh->ctx;
+  cudaStream_t s = ctx->stream;
+  const bool multi = mesh->plan.nranks > 1;
+  int first = 0;
+  bool launched = false;
+  if (multi) {
+    if (int rc = mesh_halo_auto(mesh))
+      return rc;
+    nw_node_halo& H = mesh->halo;
+    const int ncomp = dim1 * mesh->plan.ndim;
+    if (node_halo_overlap_applicable(mesh) && ncomp <= 9 &&
+        (H.p2pMode == 1 || nGrads == 1)) {
+      NodePushDev pd;
+      pd.tilePtr = H.dPushTilePtr.as<int32_t>();
+      pd.slot = H.dPushSlot.as<int32_t>();
+      pd.peer = H.dPushPeer.as<int32_t>();
+      pd.dst = H.dPushDst.as<int64_t>();
+      pd.nc = ncomp;
+      pd.nSendTiles = H.nPushTiles;
+      pd.pp = p2p_next(ctx);
+      MeshPlanDev md = mesh->dev;
+      md.tiles = H.dTilesPerm.as<TileHdr>();
+      md.haloBlock = H.dHaloBlockPerm.as<int32_t>();
+      NW_CUDA(launch_grad_tile(md, dim1, nc, vol, ec, out, s, &pd));
+      launched = true;
+      if (H.p2pMode == 1) {
+        CompPtrs comps;
+        for (int c = 0; c < ncomp; ++c)
+          comps.c[c] = out[c];
+        NW_CUDA(launch_p2p_pull_nodal(
+          comps, ncomp, H.dRecvIdx.as<int64_t>(), H.nRecvP2p, pd.pp, false, s));
+        first = nGrads; /* every field of the call is summed */
+        for (int k = 0; k < nGrads; ++k)
+          if (int rc = periodic_update(mesh, grads[k]))
+            return rc;
+      } else {
+        NodeHaloSum st;
+        st.mesh = mesh;
+        st.f = grads[0];
+        st.pp = pd.pp;
+        st.mode = 2;
+        if (int rc = node_halo_sum_end(&st))
+          return rc;
+        if (int rc = periodic_update(mesh, grads[0]))
+          return rc;
+        first = 1;
+      }
+    }
+  }
+  if (!launched)
+    NW_CUDA(launch_grad_tile(mesh->dev, dim1, nc, vol, ec, out, s));
+  for (int k = first; k < nGrads; ++k) {
+    if (multi)
+      if (int rc = node_halo_sum(mesh, grads[k]))
+        return rc;
+    if (int rc = periodic_update(mesh, grads[k]))
+      return rc;
+  }
+  return NW_OK;
+}
 
 /* Realm::periodic_field_update on one nodal field (compute stream) */
 static int
@@ -1064,13 +1143,8 @@ nw_nodal_grad_edge(nw_mesh* mesh, int phi_field, int grad_field)
   double* out[9];
   for (int c = 0; c < grad->ncomp; ++c)
     out[c] = grad->buf.as<double>() + (int64_t)c * grad->stride;
-  NW_CUDA(launch_grad_tile(
-    mesh->dev, phi->ncomp, nc, vol, ec, out, mesh->ctx->stream));
-  /* NodalGradAlgDriver::post_work (NodalGradAlgDriver.C:41-71) */
-  if (mesh->plan.nranks > 1)
-    if (int rc2 = node_halo_sum(mesh, grad))
-      return rc2;
-  return periodic_update(mesh, grad);
+  nw_field_t* grads[1] = {grad};
+  return grad_with_post_work(mesh, phi->ncomp, nc, vol, ec, out, grads, 1);
 }
 
 extern "C" int
@@ -1105,15 +1179,7 @@ nw_nodal_grad_edge_pair(
   for (int k = 0; k < 2; ++k)
     for (int c = 0; c < nd; ++c)
       out[k * nd + c] = grad[k]->buf.as<double>() + (int64_t)c * grad[k]->stride;
-  NW_CUDA(launch_grad_tile(mesh->dev, 2, nc, vol, ec, out, mesh->ctx->stream));
-  for (int k = 0; k < 2; ++k) {
-    if (mesh->plan.nranks > 1)
-      if (int rc2 = node_halo_sum(mesh, grad[k]))
-        return rc2;
-    if (int rc2 = periodic_update(mesh, grad[k]))
-      return rc2;
-  }
-  return NW_OK;
+  return grad_with_post_work(mesh, 2, nc, vol, ec, out, grad, 2);
 }
 
 /* ------------------------------------------------------------------ */
@@ -1142,6 +1208,8 @@ nw_linsys_create(nw_mesh* mesh, int kind, int num_dof, nw_linsys** out)
 extern "C" int
 nw_linsys_destroy(nw_linsys* ls)
 {
+  if (ls && ls->mesh->ctx->p2p.pendingEager == ls)
+    p2p_complete_pending(ls->mesh->ctx); /* keep the neighbours' protocol intact */
   if (ls && ls->pullDone) {
     cudaEventSynchronize(ls->pullDone);
     if (ls->mesh->ctx->p2p.lastPull == ls->pullDone)
@@ -1355,8 +1423,11 @@ nw_linsys_get_edge_slots(
   return NW_OK;
 }
 
+/* kind: 0 reads the system (an outstanding eager exchange is completed
+ * first), 1 adds to it (an error while the shared rows are on their way: the
+ * contribution could not reach their owners any more), 2 load_complete */
 static int
-ls_ready(nw_linsys* ls, const char* what)
+ls_ready(nw_linsys* ls, const char* what, int kind = 0)
 {
   if (!ls)
     return fail(NW_ERR_ARG, std::string(what) + ": NULL linear system");
@@ -1366,6 +1437,15 @@ ls_ready(nw_linsys* ls, const char* what)
     return fail(
       NW_ERR_STATE,
       std::string(what) + ": finalizeLinearSystem has not been called");
+  if (ls->eagerState != 0 && kind == 1)
+    return fail(
+      NW_ERR_STATE,
+      std::string(what) + ": the shared rows of this system have already been "
+                          "sent (eager exchange); call nw_linsys_load_complete "
+                          "before adding to it");
+  if (ls->eagerState == 1 && kind == 0)
+    if (int rc = p2p_complete_pending(ls->mesh->ctx))
+      return rc;
   if (ls->pullPending) {
     /* the shared-row add of the last loadComplete may still be running on the
      * communication stream: every later use of the system comes after it */
@@ -1412,6 +1492,7 @@ nw_linsys_zero(nw_linsys* ls)
     return rc;
   /* The zero-fill is deferred: the tile kernels write every row exactly once,
    * so a following segmented assembly needs no memset at all. */
+  ls->eagerState = 0; /* ls_ready completed an outstanding eager exchange */
   ls->state = NW_LS_LAZY_ZERO;
   return NW_OK;
 }
@@ -1472,6 +1553,43 @@ finish_tile_assembly(nw_linsys* ls)
   return NW_OK;
 }
 
+static bool ls_eager_applicable(const nw_linsys* ls);
+static int ls_eager_begin(nw_linsys* ls, LsPushDev* out);
+static bool ls_fused_push_possible(const nw_linsys* ls);
+static int ls_eager_push_separately(nw_linsys* ls);
+
+/* One tile assembly: launch(MeshPlanDev, LsPlanDev) runs the policy's tile
+ * kernel.  Eager exchange (several ranks, peer memory,
+ * nw_linsys_set_eager_exchange): the tiles that own shared or receiving rows
+ * come first in the launch and store the shared tail straight into the
+ * owners' windows; the neighbours' rows travel while the interior tiles are
+ * assembled and nw_linsys_load_complete only adds them. */
+template <class Launch>
+static int
+tile_assembly(nw_linsys* ls, Launch&& launch)
+{
+  nw_mesh* mesh = ls->mesh;
+  if (!ls_eager_applicable(ls)) {
+    NW_CUDA(launch(mesh->dev, ls->dev));
+    return finish_tile_assembly(ls);
+  }
+  if (!ls_fused_push_possible(ls)) {
+    NW_CUDA(launch(mesh->dev, ls->dev));
+    if (int rc = finish_tile_assembly(ls))
+      return rc;
+    return ls_eager_push_separately(ls);
+  }
+  LsPlanDev lpd = ls->dev;
+  if (int rc = ls_eager_begin(ls, &lpd.push))
+    return rc;
+  MeshPlanDev md = mesh->dev;
+  md.tiles = mesh->halo.dTilesPerm.as<TileHdr>();
+  md.haloBlock = mesh->halo.dHaloBlockPerm.as<int32_t>();
+  lpd.tiles = ls->sh->dLsTilesPerm.as<LsTileHdr>();
+  NW_CUDA(launch(md, lpd));
+  return finish_tile_assembly(ls);
+}
+
 /* decide the path for an edge assembly; returns 1 for the tile kernel.
  * policy: the kernel's policy id (ls_tile_fits): a user-chosen tile size or a
  * high-valence mesh whose tile does not fit one CTA's shared memory takes the
@@ -1495,7 +1613,7 @@ use_tile_path(nw_linsys* ls, bool needsDiagExtract, int* rcOut, int policy)
 extern "C" int
 nw_assemble_continuity_edge(nw_linsys* ls, const nw_continuity_opts* opts)
 {
-  if (int rc = ls_ready(ls, "nw_assemble_continuity_edge"))
+  if (int rc = ls_ready(ls, "nw_assemble_continuity_edge", 1))
     return rc;
   if (!opts)
     return fail(NW_ERR_ARG, "nw_assemble_continuity_edge: NULL options");
@@ -1511,8 +1629,9 @@ nw_assemble_continuity_edge(nw_linsys* ls, const nw_continuity_opts* opts)
     return rc;
   cudaStream_t s = mesh->ctx->stream;
   if (use_tile_path(ls, false, &rc, 0)) {
-    NW_CUDA(launch_continuity_tile(mesh->dev, ls->dev, nc, ec, *opts, s));
-    return finish_tile_assembly(ls);
+    return tile_assembly(ls, [&](const MeshPlanDev& md, const LsPlanDev& ld) {
+      return launch_continuity_tile(md, ld, nc, ec, *opts, s);
+    });
   }
   if (rc)
     return rc;
@@ -1525,7 +1644,7 @@ extern "C" int
 nw_assemble_continuity_edge_ext(
   nw_linsys* ls, const nw_continuity_opts* opts, const nw_mdot_extra_opts* extra)
 {
-  if (int rc = ls_ready(ls, "nw_assemble_continuity_edge_ext"))
+  if (int rc = ls_ready(ls, "nw_assemble_continuity_edge_ext", 1))
     return rc;
   if (!opts)
     return fail(NW_ERR_ARG, "nw_assemble_continuity_edge_ext: NULL options");
@@ -1560,7 +1679,7 @@ nw_assemble_scalar_edge(
   int diff_flux_coeff_field,
   const nw_scalar_opts* opts)
 {
-  if (int rc = ls_ready(ls, "nw_assemble_scalar_edge"))
+  if (int rc = ls_ready(ls, "nw_assemble_scalar_edge", 1))
     return rc;
   if (!opts)
     return fail(NW_ERR_ARG, "nw_assemble_scalar_edge: NULL options");
@@ -1583,8 +1702,9 @@ nw_assemble_scalar_edge(
     return rc;
   cudaStream_t s = mesh->ctx->stream;
   if (use_tile_path(ls, false, &rc, 1)) {
-    NW_CUDA(launch_scalar_tile(mesh->dev, ls->dev, nc, ec, *opts, s));
-    return finish_tile_assembly(ls);
+    return tile_assembly(ls, [&](const MeshPlanDev& md, const LsPlanDev& ld) {
+      return launch_scalar_tile(md, ld, nc, ec, *opts, s);
+    });
   }
   if (rc)
     return rc;
@@ -1598,9 +1718,9 @@ nw_assemble_scalar_edge_pair(
   nw_linsys* la, int q_a, int dqdx_a, int dflux_a, const nw_scalar_opts* oa,
   nw_linsys* lb, int q_b, int dqdx_b, int dflux_b, const nw_scalar_opts* ob)
 {
-  if (int rc = ls_ready(la, "nw_assemble_scalar_edge_pair"))
+  if (int rc = ls_ready(la, "nw_assemble_scalar_edge_pair", 1))
     return rc;
-  if (int rc = ls_ready(lb, "nw_assemble_scalar_edge_pair"))
+  if (int rc = ls_ready(lb, "nw_assemble_scalar_edge_pair", 1))
     return rc;
   if (!oa || !ob)
     return fail(NW_ERR_ARG, "nw_assemble_scalar_edge_pair: NULL options");
@@ -1665,7 +1785,7 @@ extern "C" int
 nw_assemble_momentum_edge(
   nw_linsys* ls, int viscosity_field, const nw_momentum_opts* opts)
 {
-  if (int rc = ls_ready(ls, "nw_assemble_momentum_edge"))
+  if (int rc = ls_ready(ls, "nw_assemble_momentum_edge", 1))
     return rc;
   if (!opts)
     return fail(NW_ERR_ARG, "nw_assemble_momentum_edge: NULL options");
@@ -1701,9 +1821,9 @@ nw_assemble_momentum_edge(
   if (uvw) {
     /* extract_diagonal rides on the tile kernel (node-keyed pass) */
     if (use_tile_path(ls, false, &rc, 2)) {
-      NW_CUDA(launch_momentum_uvw_tile(
-        mesh->dev, ls->dev, nc, ec, *opts, diagOut, s));
-      return finish_tile_assembly(ls);
+      return tile_assembly(ls, [&](const MeshPlanDev& md, const LsPlanDev& ld) {
+        return launch_momentum_uvw_tile(md, ld, nc, ec, *opts, diagOut, s);
+      });
     }
     if (rc)
       return rc;
@@ -1786,7 +1906,7 @@ build_node_rows(nw_linsys* ls)
 extern "C" int
 nw_assemble_mass_bdf_node(nw_linsys* ls, int kind, const nw_mass_bdf_opts* opts)
 {
-  if (int rc = ls_ready(ls, "nw_assemble_mass_bdf_node"))
+  if (int rc = ls_ready(ls, "nw_assemble_mass_bdf_node", 1))
     return rc;
   if (!opts || kind < NW_MASS_SCALAR || kind > NW_MASS_CONTINUITY)
     return fail(NW_ERR_ARG, "nw_assemble_mass_bdf_node: bad argument");
@@ -1840,7 +1960,7 @@ nw_assemble_mass_bdf_node(nw_linsys* ls, int kind, const nw_mass_bdf_opts* opts)
 extern "C" int
 nw_assemble_wall_dist_edge(nw_linsys* ls)
 {
-  if (int rc = ls_ready(ls, "nw_assemble_wall_dist_edge"))
+  if (int rc = ls_ready(ls, "nw_assemble_wall_dist_edge", 1))
     return rc;
   if (ls->numDof != 1 || ls->kind != NW_LINSYS_HYPRE)
     return fail(
@@ -1854,8 +1974,9 @@ nw_assemble_wall_dist_edge(nw_linsys* ls)
     return rc;
   cudaStream_t s = mesh->ctx->stream;
   if (use_tile_path(ls, false, &rc, 7)) {
-    NW_CUDA(launch_wall_dist_tile(mesh->dev, ls->dev, nc, ec, s));
-    return finish_tile_assembly(ls);
+    return tile_assembly(ls, [&](const MeshPlanDev& md, const LsPlanDev& ld) {
+      return launch_wall_dist_tile(md, ld, nc, ec, s);
+    });
   }
   if (rc)
     return rc;
@@ -1867,7 +1988,7 @@ nw_assemble_wall_dist_edge(nw_linsys* ls)
 extern "C" int
 nw_assemble_wall_dist_node(nw_linsys* ls, int dual_nodal_volume_field)
 {
-  if (int rc = ls_ready(ls, "nw_assemble_wall_dist_node"))
+  if (int rc = ls_ready(ls, "nw_assemble_wall_dist_node", 1))
     return rc;
   if (ls->numDof != 1 || ls->kind != NW_LINSYS_HYPRE)
     return fail(
@@ -2021,7 +2142,7 @@ nw_linsys_sum_into(
   const double* d_lhs,
   const double* d_rhs)
 {
-  if (int rc = ls_ready(ls, "nw_linsys_sum_into"))
+  if (int rc = ls_ready(ls, "nw_linsys_sum_into", 1))
     return rc;
   if (n_entities < 0 || nodes_per_entity < 1 || nodes_per_entity > 8 ||
       (n_entities > 0 && (!d_entity_nodes || !d_lhs || !d_rhs)))

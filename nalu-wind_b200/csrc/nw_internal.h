@@ -113,6 +113,10 @@ struct nw_p2p
   cudaStream_t commStream = nullptr;
   cudaEvent_t pushDone = nullptr; /* compute stream: producer + push issued */
   cudaEvent_t lastPull = nullptr; /* completion event of the latest pull (not owned) */
+  /* a linear system whose shared rows were pushed from its assembly call
+   * (eager exchange) and not yet pulled: the next exchange of the context
+   * completes it first (the window protocol wants pull(e) before push(e+1)) */
+  struct nw_linsys* pendingEager = nullptr;
 };
 
 struct nw_ctx
@@ -190,6 +194,28 @@ struct nw_node_halo
   nw::DevBuf dSendIdx, dSendDst, dRecvIdx; /* int64 */
   nw::DevBuf dSendPeer, dPeerList;         /* int32 */
   nw::DevBuf dRecvIsGhost;                 /* uint8: receive entry is a ghost of mine */
+  /* boundary tiles first: the tiles holding a node of any exchange list, then
+   * the others, each group in plan order.  The gradient kernels run the first
+   * group, push, and run the second group while the neighbours' data travels */
+  std::vector<int32_t> tileOrder;
+  int nBoundaryTiles = 0;
+  /* the per-tile arrays of the mesh plan in that order (a CTA finds its tile
+   * by block index: no indirection on the critical path) */
+  nw::DevBuf dTilesPerm, dHaloBlockPerm;
+  /* fused push (NodePushDev): first send list of the mode, grouped by tile
+   * (launch order) */
+  int nPushTiles = 0;
+  nw::DevBuf dPushTilePtr, dPushSlot, dPushPeer, dPushDst;
+};
+
+struct nw_mesh;
+/* a nodal halo sum between its two halves (nw_halo.inc) */
+struct NodeHaloSum
+{
+  nw_mesh* mesh = nullptr;
+  nw_field_t* f = nullptr;
+  nw::P2pDev pp;
+  int mode = 0; /* 0: nothing sent yet (NCCL path / exchange skipped) */
 };
 
 struct nw_ls_shared;
@@ -247,6 +273,9 @@ struct nw_ls_shared
   nw::DevBuf dLsTiles, dEntInfo, dEntRhsRow, dHe, dWarp, dRuns;
   nw::DevBuf dUncovered, dUncoveredPeriodic, dRowPtr;
   nw::DevBuf dPeriodicRows;
+  /* lp.tiles in the mesh's boundary-tiles-first order (eager exchange) */
+  nw::DevBuf dLsTilesPerm;
+  bool permUploaded = false;
 };
 
 struct nw_linsys
@@ -308,6 +337,19 @@ struct nw_linsys
    * (row, col) pairs appended after the reference-layout arrays */
   int64_t nExtra = 0;
   std::vector<int64_t> extraRows, extraCols;
+  /* eager exchange (nw_linsys_set_eager_exchange): the tile assembly runs the
+   * tiles that own shared or receiving rows first, pushes the shared tail and
+   * assembles the interior tiles behind the push; load_complete only pulls.
+   * eagerState: 0 nothing outstanding, 1 pushed (pull outstanding), 2 pulled
+   * by a later exchange of the context (load_complete is a no-op) */
+  bool eager = false;
+  int eagerState = 0;
+  nw::P2pDev eagerPP;
+  int nSendTiles = 0;      /* tiles with rows of the shared tail */
+  bool fusedPushOk = false;
+  int nPushSeg = 0;
+  bool p2pNothingToSend = false; /* no shared rows at all on this rank */
+  nw::DevBuf dPushSeg;     /* PushSeg per owner */
 };
 
 #endif

@@ -247,12 +247,74 @@ node_copy_bytes(int ncomp, const TileHdr& h, bool skip = false)
 /* the calling thread's halo slot of this tile from the fixed-stride block
  * (issue it right after the header load: both travel together) */
 __device__ __forceinline__ int32_t
-halo_index_early(const MeshPlanDev& mp)
+halo_index_early(const MeshPlanDev& mp, int tile)
 {
   return (int)threadIdx.x < kHaloBlock
-           ? __ldg(mp.haloBlock + (size_t)blockIdx.x * kHaloBlock + threadIdx.x)
+           ? __ldg(mp.haloBlock + (size_t)tile * kHaloBlock + threadIdx.x)
            : -1;
 }
+__device__ __forceinline__ int32_t
+halo_index_early(const MeshPlanDev& mp)
+{
+  return halo_index_early(mp, (int)blockIdx.x);
+}
+
+/* ---- fused push (eager exchange): a boundary tile stores what other ranks
+ * need straight into their windows; the last such tile of the launch
+ * publishes the epoch.  pp.sync[0] counts the tiles (kernels of one stream
+ * run one after the other, and the word is back at zero when the launch
+ * ends). ---- */
+__device__ __forceinline__ void
+st_release_sys_u64(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void
+tile_push_signal(const P2pDev& pp, int nSendTiles)
+{
+  /* the CTA's remote stores are ordered before thread 0's fence by the
+   * barrier; the fence is cumulative (one system fence per tile instead of
+   * one per thread: the tile leaves its SM slot sooner) */
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned done = atomicAdd(pp.sync, 1u) + 1u;
+    if (done == (unsigned)nSendTiles) {
+      pp.sync[0] = 0u;
+      __threadfence_system();
+      for (int i = 0; i < pp.nPeers; ++i)
+        st_release_sys_u64(pp.peerFlags[pp.peers[i]] + pp.myRank, pp.epoch);
+    }
+  }
+}
+/* a rank with nothing to send still tells its neighbours that the epoch is
+ * complete: the first CTA of the launch does it straight away */
+__device__ __forceinline__ void
+tile_push_signal_empty(const P2pDev& pp)
+{
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    __threadfence_system();
+    for (int i = 0; i < pp.nPeers; ++i)
+      st_release_sys_u64(pp.peerFlags[pp.peers[i]] + pp.myRank, pp.epoch);
+  }
+}
+__device__ __forceinline__ const PushSeg*
+push_seg_of_value(const LsPushDev& pd, int64_t k /* index in the shared tail */)
+{
+  for (int i = 0; i < pd.nSeg; ++i)
+    if (k >= pd.seg[i].val0 && k < pd.seg[i].val0 + pd.seg[i].valN)
+      return pd.seg + i;
+  return nullptr;
+}
+__device__ __forceinline__ const PushSeg*
+push_seg_of_row(const LsPushDev& pd, int64_t r /* row index in the shared tail */)
+{
+  for (int i = 0; i < pd.nSeg; ++i)
+    if (r >= pd.seg[i].row0 && r < pd.seg[i].row0 + pd.seg[i].rowN)
+      return pd.seg + i;
+  return nullptr;
+}
+
 
 template <int NC>
 __device__ __forceinline__ void
@@ -765,9 +827,10 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
   __shared__ int32_t s_sliceN[kMaxTileEnts / 32 + 2]; /* node-keyed (diagOut) */
   NW_PT_BEGIN(P::kPhaseId);
 
-  const TileHdr h = mp.tiles[blockIdx.x];
-  const LsTileHdr lh = lp.tiles[blockIdx.x];
-  const int32_t g0 = halo_index_early(mp);
+  const int tile = (int)blockIdx.x;
+  const TileHdr h = mp.tiles[tile];
+  const LsTileHdr lh = lp.tiles[tile];
+  const int32_t g0 = halo_index_early(mp, tile);
   const LsSmem<P> L(mp, lp);
   const int stride = even_up_i(h.nOwnPad + h.nHalo);
 
@@ -894,6 +957,10 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
    * point to, are loaded before anything of the block is stored, so that the
    * shared-memory latencies of a block overlap (round-1 phase cycles: this
    * phase was a chain of dependent 30-cycle loads, 20 % of a CTA's life). ---- */
+  /* eager exchange: this tile holds rows of the shared tail */
+  const bool pushing = lp.push.seg != nullptr && lh.hasShared != 0;
+  if (lp.push.enabled && lp.push.nSendTiles == 0)
+    tile_push_signal_empty(lp.push.pp);
   if (!(mp.dbgSkip & 4)) {
     const int lane = threadIdx.x & 31;
     for (int row0 = (int)threadIdx.x - lane; row0 < lh.nEnts;
@@ -946,6 +1013,17 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
 #pragma unroll
         for (int d = 0; d < P::NR; ++d)
           lp.rhs[(int64_t)d * lp.rhsStride + grow] = rhs[d];
+        if (pushing && grow >= lp.push.numRowsOwned) {
+          /* a row another rank owns: its rhs goes to the owner's window too */
+          const int64_t tr = grow - lp.push.numRowsOwned;
+          if (const PushSeg* sg = push_seg_of_row(lp.push, tr)) {
+            double* w = lp.push.pp.peerWindow[sg->peer] + lp.push.pp.winOff +
+                        sg->rowDst + (tr - sg->row0);
+#pragma unroll
+            for (int d = 0; d < P::NR; ++d)
+              w[(int64_t)d * sg->rowStride] = rhs[d];
+          }
+        }
       }
       __syncwarp();
       /* copy-out of this warp's rows: every value written exactly once */
@@ -956,6 +1034,15 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
 #pragma unroll 4
         for (int e = (int)e0.base + lane; e < end; e += 32)
           lp.values[e + s_delta[e]] = s_vals[e];
+        if (pushing)
+          for (int e = (int)e0.base + lane; e < end; e += 32) {
+            const int64_t tk = (int64_t)e + s_delta[e] - lp.push.nnzOwned;
+            if (tk >= 0)
+              if (const PushSeg* sg = push_seg_of_value(lp.push, tk))
+                lp.push.pp.peerWindow[sg->peer]
+                                     [lp.push.pp.winOff + sg->valDst + (tk - sg->val0)] =
+                  s_vals[e];
+          }
       }
     }
   }
@@ -986,6 +1073,8 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
       lp.diagOut[h.node0 + i] += acc;
     }
   }
+  if (pushing)
+    tile_push_signal(lp.push.pp, lp.push.nSendTiles);
   NW_PT_END();
 }
 
@@ -2016,10 +2105,7 @@ __global__ void __launch_bounds__(kTileThreads) continuity_ext_atomic_kernel(
 /*  nodal gradient                                                     */
 /* ------------------------------------------------------------------ */
 
-struct GradOut
-{
-  double* c[9];
-};
+using GradOut = CompPtrs;
 
 /* NodalGradEdgeAlg (src/ngp_algorithms/NodalGradEdgeAlg.C:85-109) with the
  * zero-fill of NodalGradAlgDriver::pre_work fused: one thread per owned node
@@ -2031,15 +2117,17 @@ __global__ void __launch_bounds__(kTileThreads, D1 == 1 ? 8 : 5) grad_tile_kerne
   const NodeComps phi,
   const double* __restrict__ dualVol,
   const EdgeComps ec,
-  const GradOut out)
+  const GradOut out,
+  const NodePushDev push)
 {
   constexpr int NV = D1 * ND;
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t bar[2];
   __shared__ int32_t s_slice[kMaxTileEnts / 32 + 2];
   NW_PT_BEGIN(D1 == 1 ? 5 : 6);
-  const TileHdr h = mp.tiles[blockIdx.x];
-  const int32_t g0 = halo_index_early(mp);
+  const int tile = (int)blockIdx.x;
+  const TileHdr h = mp.tiles[tile];
+  const int32_t g0 = halo_index_early(mp, tile);
   const int stride = even_up_i(h.nOwnPad + h.nHalo);
   const int estride = even_up_i(mp.maxTileEdges);
   double* s_phi = smem;
@@ -2122,6 +2210,26 @@ __global__ void __launch_bounds__(kTileThreads, D1 == 1 ? 8 : 5) grad_tile_kerne
       out.c[k][h.node0 + i] = acc[k] * invVol;
   }
   NW_PT_MARK();
+  if (push.tilePtr && push.nSendTiles == 0)
+    tile_push_signal_empty(push.pp);
+  if (push.tilePtr) {
+    /* eager exchange: the partial sums of this tile's shared nodes go straight
+     * to the other sharers' windows (the values were written by this CTA: the
+     * barrier makes them visible to all of its threads) */
+    const int p0 = __ldg(push.tilePtr + tile), p1 = __ldg(push.tilePtr + tile + 1);
+    if (p1 > p0) { /* uniform over the CTA */
+      __syncthreads();
+      for (int g = p0 + (int)threadIdx.x; g < p1; g += blockDim.x) {
+        const int slot = __ldg(push.slot + g);
+        double* w = push.pp.peerWindow[__ldg(push.peer + g)] + push.pp.winOff +
+                    __ldg(push.dst + g) * NV;
+#pragma unroll
+        for (int c = 0; c < NV; ++c) /* constant indices: no local copy of `out` */
+          w[c] = out.c[c][slot];
+      }
+      tile_push_signal(push.pp, push.nSendTiles);
+    }
+  }
   NW_PT_END();
 }
 
@@ -3255,7 +3363,7 @@ __global__ void __launch_bounds__(256) p2p_push_nodal_kernel(
 /* nodal pull: own partial + the other sharer's partial (two sharers per node:
  * a + b on one side, b + a on the other -- the same bits) */
 __global__ void __launch_bounds__(256) p2p_pull_nodal_kernel(
-  double* base, int64_t stride, int nc, const int64_t* __restrict__ recvIdx,
+  const CompPtrs comps, int nc, const int64_t* __restrict__ recvIdx,
   int64_t n, const P2pDev pp)
 {
   if (!p2p_wait(pp))
@@ -3266,7 +3374,7 @@ __global__ void __launch_bounds__(256) p2p_pull_nodal_kernel(
        t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t g = t / nc;
     const int c = (int)(t - g * nc);
-    double* d = base + (int64_t)c * stride + recvIdx[g];
+    double* d = comps.c[c] + recvIdx[g];
     *d += __ldcg(win + t);
   }
 }
@@ -3333,6 +3441,43 @@ __global__ void __launch_bounds__(256) p2p_pull_accumulate_kernel(
     for (int64_t q = ptr[u]; q < ptr[u + 1]; ++q)
       v += __ldcg(buf + pos[q] * entStride + c * compStride);
     *d = v;
+  }
+}
+
+/* both accumulate plans of a linear system in one launch: the matrix values
+ * (window offset 0) and the rhs columns (window offset rhsOff, column c at
+ * + c * rhsColStride) -- same order of additions as two
+ * p2p_pull_accumulate_kernel launches */
+__global__ void __launch_bounds__(256) p2p_pull_accumulate2_kernel(
+  const int64_t* __restrict__ valDst, const int64_t* __restrict__ valPtr,
+  const int64_t* __restrict__ valPos, int64_t nVal, double* values,
+  int64_t rhsOff, int64_t rhsColStride, int nR,
+  const int64_t* __restrict__ rhsDst, const int64_t* __restrict__ rhsPtr,
+  const int64_t* __restrict__ rhsPos, int64_t nRhs, double* rhs,
+  int64_t rhsStride, const P2pDev pp)
+{
+  if (!p2p_wait(pp))
+    return;
+  const double* buf = pp.myWindow + pp.winOff;
+  const int64_t total = nVal + nRhs * nR;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    if (t < nVal) {
+      double* d = values + valDst[t];
+      double v = *d;
+      for (int64_t q = valPtr[t]; q < valPtr[t + 1]; ++q)
+        v += __ldcg(buf + valPos[q]);
+      *d = v;
+    } else {
+      const int64_t t2 = t - nVal;
+      const int64_t u = t2 / nR;
+      const int c = (int)(t2 - u * nR);
+      double* d = rhs + (int64_t)c * rhsStride + rhsDst[u];
+      double v = *d;
+      for (int64_t q = rhsPtr[u]; q < rhsPtr[u + 1]; ++q)
+        v += __ldcg(buf + rhsOff + rhsPos[q] + (int64_t)c * rhsColStride);
+      *d = v;
+    }
   }
 }
 
@@ -3426,7 +3571,9 @@ launch_ls_tile(
   lp.diagOut = diagOut;
   bool launched = false;
   cudaError_t e = cudaSuccess;
-  if (!diagOut) /* the stream variant has no extract_diagonal pass */
+  /* the stream variant has no extract_diagonal pass; neither experimental
+   * variant knows the fused push */
+  if (!diagOut && !lp.push.enabled)
     e = launch_ls_stream<P, ND>(mp, lp, nc, ec, o, s, &launched);
   if (e != cudaSuccess || launched)
     return e;
@@ -3435,7 +3582,7 @@ launch_ls_tile(
    * for momentum on a hex mesh) and no extract_diagonal pass is asked for.
    * Bit-identical to the tile kernel, measured slower: not the default. */
   const int pipeEnv = env_int("NW_PIPE", 0); /* read per call: tests toggle it */
-  if (pipeEnv && !diagOut && mp.nTiles > 0) {
+  if (pipeEnv && !diagOut && !lp.push.enabled && mp.nTiles > 0) {
     const size_t pb = PipeSmem<P>(mp, lp).bytes();
     if (pb + 2048 <= 227 * 1024) {
       const int grid = std::min(mp.nTiles, sm_count());
@@ -3461,6 +3608,8 @@ launch_ls_tile(
   e = set_smem(ls_tile_kernel<P, ND>, bytes);
   if (e != cudaSuccess)
     return e;
+  if (mp.nTiles == 0)
+    return cudaSuccess;
   ls_tile_kernel<P, ND><<<mp.nTiles, kTileThreads, bytes, s>>>(
     with_pf(mp, ls_tile_kernel<P, ND>, kTileThreads, bytes), lp, nc, ec, o);
   return cudaGetLastError();
@@ -3643,18 +3792,27 @@ launch_grad_tile_t(
   const double* dualVol,
   const EdgeComps& ec,
   double* const* gradOut,
-  cudaStream_t s)
+  cudaStream_t s,
+  const NodePushDev* push)
 {
   GradOut go;
   for (int k = 0; k < D1 * ND; ++k)
     go.c[k] = gradOut[k];
+  NodePushDev pd;
+  if (push) {
+    if (push->nc != D1 * ND)
+      return cudaErrorInvalidValue;
+    pd = *push;
+  }
   const size_t bytes = edge_kernel_smem(mp, D1, ND) + 4u * (size_t)mp.maxTileEllNode;
   cudaError_t e = set_smem(grad_tile_kernel<D1, ND>, bytes);
   if (e != cudaSuccess)
     return e;
+  if (mp.nTiles == 0)
+    return cudaSuccess;
   grad_tile_kernel<D1, ND><<<mp.nTiles, kTileThreads, bytes, s>>>(
     with_pf(mp, grad_tile_kernel<D1, ND>, kTileThreads, bytes), phi, dualVol, ec,
-    go);
+    go, pd);
   return cudaGetLastError();
 }
 template <int D1, int ND>
@@ -3684,15 +3842,16 @@ launch_grad_tile(
   const double* dualVol,
   const EdgeComps& ec,
   double* const* gradOut,
-  cudaStream_t s)
+  cudaStream_t s,
+  const NodePushDev* push)
 {
   /* dim1 == 2 on a 3-D mesh: two scalar fields at once (nw_nodal_grad_edge_pair) */
   if (mp.ndim == 3)
-    return dim1 == 1   ? launch_grad_tile_t<1, 3>(mp, phi, dualVol, ec, gradOut, s)
-           : dim1 == 2 ? launch_grad_tile_t<2, 3>(mp, phi, dualVol, ec, gradOut, s)
-                       : launch_grad_tile_t<3, 3>(mp, phi, dualVol, ec, gradOut, s);
-  return dim1 == 1 ? launch_grad_tile_t<1, 2>(mp, phi, dualVol, ec, gradOut, s)
-                   : launch_grad_tile_t<2, 2>(mp, phi, dualVol, ec, gradOut, s);
+    return dim1 == 1   ? launch_grad_tile_t<1, 3>(mp, phi, dualVol, ec, gradOut, s, push)
+           : dim1 == 2 ? launch_grad_tile_t<2, 3>(mp, phi, dualVol, ec, gradOut, s, push)
+                       : launch_grad_tile_t<3, 3>(mp, phi, dualVol, ec, gradOut, s, push);
+  return dim1 == 1 ? launch_grad_tile_t<1, 2>(mp, phi, dualVol, ec, gradOut, s, push)
+                   : launch_grad_tile_t<2, 2>(mp, phi, dualVol, ec, gradOut, s, push);
 }
 
 cudaError_t
@@ -4229,11 +4388,11 @@ launch_p2p_push_nodal(
 
 cudaError_t
 launch_p2p_pull_nodal(
-  double* base, int64_t stride, int nc, const int64_t* recvIdx, int64_t n,
+  const CompPtrs& comps, int nc, const int64_t* recvIdx, int64_t n,
   const P2pDev& pp, bool beside, cudaStream_t s)
 {
   p2p_pull_nodal_kernel<<<p2p_pull_grid(n * nc, beside), 256, 0, s>>>(
-    base, stride, nc, recvIdx, n, pp);
+    comps, nc, recvIdx, n, pp);
   return cudaGetLastError();
 }
 
@@ -4269,6 +4428,20 @@ launch_p2p_pull_accumulate(
   p2p_pull_accumulate_kernel<<<p2p_pull_grid(nDst * nc, beside), 256, 0, s>>>(
     bufOff, entStride, compStride, nc, dstIdx, ptr, pos, nDst, dst,
     dstCompStride, pp, wait ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_p2p_pull_accumulate2(
+  const int64_t* valDst, const int64_t* valPtr, const int64_t* valPos,
+  int64_t nVal, double* values, int64_t rhsOff, int64_t rhsColStride, int nR,
+  const int64_t* rhsDst, const int64_t* rhsPtr, const int64_t* rhsPos,
+  int64_t nRhs, double* rhs, int64_t rhsStride, const P2pDev& pp, bool beside,
+  cudaStream_t s)
+{
+  p2p_pull_accumulate2_kernel<<<p2p_pull_grid(nVal + nRhs * nR, beside), 256, 0, s>>>(
+    valDst, valPtr, valPos, nVal, values, rhsOff, rhsColStride, nR, rhsDst,
+    rhsPtr, rhsPos, nRhs, rhs, rhsStride, pp);
   return cudaGetLastError();
 }
 

@@ -20,6 +20,63 @@ constexpr int kPhaseKernels = 16; /* 8.. : stream kernels */
 constexpr int kPhaseSlots = 12;
 cudaError_t phase_times_read(unsigned long long* out, bool reset);
 
+/* peer-memory mailbox as the kernels see it (nw_p2p in nw_internal.h) */
+struct P2pDev
+{
+  double* const* peerWindow = nullptr;            /* [nranks] window base of rank r */
+  unsigned long long* const* peerFlags = nullptr; /* [nranks] flag array of rank r */
+  double* myWindow = nullptr;
+  const unsigned long long* myFlags = nullptr;
+  unsigned* sync = nullptr; /* [0] block counter, [1] error word */
+  /* ranks signalled / waited for: the union of the neighbours of every
+   * exchange object of the context (see p2p_register_peers) */
+  const int32_t* peers = nullptr;
+  int nPeers = 0;
+  int myRank = 0;
+  int64_t winOff = 0; /* parity * winDoubles */
+  unsigned long long epoch = 0;
+  long long timeoutCycles = 40000000000ll; /* bounded spin of the pull kernels */
+};
+
+/* component arrays of one or more nodal fields */
+struct CompPtrs
+{
+  double* c[9];
+};
+
+/* fused push of a tile kernel (eager exchange, nw_halo.inc): the shared tail
+ * is one contiguous segment per owner; segment k of the tail values / rows
+ * lands in that owner's window */
+struct PushSeg
+{
+  int64_t val0 = 0, valN = 0, valDst = 0; /* tail value range -> window offset */
+  int64_t row0 = 0, rowN = 0, rowDst = 0; /* tail row range -> window offset ... */
+  int64_t rowStride = 0;                  /* ... of rhs column 0; next column + rowStride */
+  int32_t peer = 0;
+  int32_t pad = 0;
+};
+struct LsPushDev
+{
+  const PushSeg* seg = nullptr; /* null: nothing to send */
+  int enabled = 0;              /* 0: no fused push in this launch */
+  int nSeg = 0;
+  int nSendTiles = 0; /* tiles with hasShared: the last one publishes the epoch */
+  int64_t nnzOwned = 0, numRowsOwned = 0;
+  P2pDev pp;
+};
+
+/* fused push of the gradient kernel: the nodal send list grouped by tile */
+struct NodePushDev
+{
+  const int32_t* tilePtr = nullptr; /* [nTiles + 1], launch order; null: no fused push */
+  const int32_t* slot = nullptr;    /* internal node slot of entry g */
+  const int32_t* peer = nullptr;
+  const int64_t* dst = nullptr;     /* window entry (x nc components) */
+  int nc = 0;                       /* components per window entry */
+  int nSendTiles = 0;
+  P2pDev pp;
+};
+
 struct MeshPlanDev
 {
   const TileHdr* tiles = nullptr;
@@ -58,6 +115,7 @@ struct LsPlanDev
   /* NGPApplyCoeff::extract_diagonal target (nodal field, internal slots) of
    * the current launch, or null */
   double* diagOut = nullptr;
+  LsPushDev push;
 };
 
 /* atomic-variant slot map, per tile-edge slot */
@@ -110,7 +168,7 @@ cudaError_t launch_peclet_tile(
 cudaError_t launch_grad_tile(
   const MeshPlanDev& mp, int dim1, const NodeComps& phi, const double* dualVol,
   const EdgeComps& ec, double* const* gradOut /* dim1*ndim comps */,
-  cudaStream_t s);
+  cudaStream_t s, const NodePushDev* push = nullptr);
 
 cudaError_t launch_continuity_tile(
   const MeshPlanDev& mp, const LsPlanDev& lp, const NodeComps& nc,
@@ -252,23 +310,6 @@ cudaError_t launch_pack(
 cudaError_t launch_scatter_assign(
   const double* src, const int64_t* idx, int64_t n, double* dst,
   cudaStream_t s);
-/* peer-memory mailbox as the kernels see it (nw_p2p in nw_internal.h) */
-struct P2pDev
-{
-  double* const* peerWindow = nullptr;            /* [nranks] window base of rank r */
-  unsigned long long* const* peerFlags = nullptr; /* [nranks] flag array of rank r */
-  double* myWindow = nullptr;
-  const unsigned long long* myFlags = nullptr;
-  unsigned* sync = nullptr; /* [0] block counter, [1] error word */
-  /* ranks signalled / waited for: the union of the neighbours of every
-   * exchange object of the context (see p2p_register_peers) */
-  const int32_t* peers = nullptr;
-  int nPeers = 0;
-  int myRank = 0;
-  int64_t winOff = 0; /* parity * winDoubles */
-  unsigned long long epoch = 0;
-  long long timeoutCycles = 40000000000ll; /* bounded spin of the pull kernels */
-};
 cudaError_t launch_p2p_push_nodal(
   const double* base, int64_t stride, int nc, const int64_t* sendIdx,
   const int32_t* sendPeer, const int64_t* sendDst, int64_t n, const P2pDev& pp,
@@ -276,8 +317,9 @@ cudaError_t launch_p2p_push_nodal(
 /* beside: the launch shares the GPU with compute kernels of another stream
  * (asynchronous completion) -- small grid */
 cudaError_t launch_p2p_pull_nodal(
-  double* base, int64_t stride, int nc, const int64_t* recvIdx, int64_t n,
-  const P2pDev& pp, bool beside, cudaStream_t s);
+  const CompPtrs& comps /* nc component arrays, internal slots */, int nc,
+  const int64_t* recvIdx, int64_t n, const P2pDev& pp, bool beside,
+  cudaStream_t s);
 cudaError_t launch_p2p_pull_assign_nodal(
   double* base, int64_t stride, int nc, const int64_t* recvIdx,
   const unsigned char* recvIsGhost, int64_t n, const P2pDev& pp, bool beside,
@@ -285,6 +327,12 @@ cudaError_t launch_p2p_pull_assign_nodal(
 cudaError_t launch_p2p_push_segments(
   const double* const* segSrc, const int64_t* segStart, const int64_t* segDst,
   const int32_t* segPeer, int nSeg, int64_t total, const P2pDev& pp,
+  cudaStream_t s);
+cudaError_t launch_p2p_pull_accumulate2(
+  const int64_t* valDst, const int64_t* valPtr, const int64_t* valPos,
+  int64_t nVal, double* values, int64_t rhsOff, int64_t rhsColStride, int nR,
+  const int64_t* rhsDst, const int64_t* rhsPtr, const int64_t* rhsPos,
+  int64_t nRhs, double* rhs, int64_t rhsStride, const P2pDev& pp, bool beside,
   cudaStream_t s);
 cudaError_t launch_p2p_pull_accumulate(
   int64_t bufOff, int64_t entStride, int64_t compStride, int nc,

@@ -87,7 +87,9 @@ struct LsTileHdr
   int32_t ellPtr;     /* offset into heEll[] (multiple of 32) */
   int32_t ellLen;     /* records incl. padding (multiple of 32) */
   int32_t slicePtr;   /* offset into sliceOff[]: nSlices+1 entries */
-  int32_t pad[5];
+  int32_t hasShared;  /* 1: some row of this tile lies in the shared tail
+                         (another rank owns it): fused push of the tile kernel */
+  int32_t pad[4];
 };
 
 /* per tile row: where its values sit in the staging buffer */

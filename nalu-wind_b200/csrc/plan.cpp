@@ -310,12 +310,17 @@ build_mesh_plan(const MeshInput& in, MeshPlan& mp)
    * lattice gives, a few greedy passes move a row group to the neighbouring
    * tile that holds more of its edges than its own tile does (every move
    * lowers the cut; tiles may grow by ~8 % and never run empty).  Serial and
-   * in group order, so the result is deterministic.  NW_TILE_REFINE=0
-   * switches it off. */
+   * in group order, so the result is deterministic.
+   * Opt-in (NW_TILE_REFINE=1).  Measured (profiles/r02s_bench_*): the tet /
+   * wedge / pyramid mesh gains 4 % (halo nodes per node 1.49 -> 1.39, largest
+   * staged tile 428 -> 363 nodes), the warped hex box LOSES 15 %: its cut
+   * barely moves (1.392 -> 1.389: an oblique cut through a lattice is a
+   * staircase no local move removes) while the grown tiles (208 nodes, 824
+   * edges) cost the scalar kernel a resident CTA. */
   {
     const int64_t nT = (int64_t)leafBegin.size() - 1;
     const char* env = std::getenv("NW_TILE_REFINE");
-    const bool wanted = !(env && env[0] == '0');
+    const bool wanted = env && env[0] == '1';
     if (wanted && nT > 1 && E > 0) {
       std::vector<int32_t> tileOfGroup(G), groupOfNode(N);
       for (int64_t t = 0; t < nT; ++t)
@@ -956,6 +961,10 @@ build_ls_plan(const MeshPlan& mp, const Graph& g, LsPlan& lp)
     }
     LsTileHdr& lh = lp.tiles[t];
     lh.nEnts = (int32_t)rows.size();
+    lh.hasShared = 0;
+    for (const auto r : rows)
+      if ((int64_t)r >= g.numRowsOwned)
+        lh.hasShared = 1;
     lh.nnz = (int32_t)so;
     lh.nRuns = (int32_t)runs.size();
 

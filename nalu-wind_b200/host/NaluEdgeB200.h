@@ -267,6 +267,13 @@ public:
   virtual void finalizeLinearSystem() { nw_check(nw_linsys_finalize(ls_)); }
   virtual void zeroSystem() { nw_check(nw_linsys_zero(ls_)); }
   virtual void loadComplete() { nw_check(nw_linsys_load_complete(ls_)); }
+  /* not in the reference: the edge algorithm is the last contribution to rows
+   * shared with other ranks before loadComplete, so their exchange may start
+   * from inside its execute() (nw_linsys_set_eager_exchange) */
+  void eagerExchange(bool on = true)
+  {
+    nw_check(nw_linsys_set_eager_exchange(ls_, on ? 1 : 0));
+  }
   void skipRows(const std::vector<int64_t>& rows)
   {
     nw_check(nw_linsys_set_skipped_rows(ls_, rows.data(), (int64_t)rows.size()));

@@ -194,6 +194,38 @@ def main():
     keep = np.array([r not in pr for r in range(gfull.num_rows_owned)])
     ref2 = float(np.sum(fr[0, :gfull.num_rows_owned][keep] ** 2))
     res["norm2_global"] = abs(n2[0] - ref2) / (1e-10 * ref2)
+    # eager exchange (boundary tiles first, push from the assembly call): bit-
+    # identical to the default order; a reader completes the exchange, a
+    # writer is refused while the shared rows travel
+    eager = {}
+    v0, r0 = ls.values()
+    ls.set_eager_exchange(True)
+    ls.zeroSystem()
+    ls.assemble_continuity_edge(**pu.CONT_OPTS)
+    ls.loadComplete()
+    v1, r1 = ls.values()
+    eager["continuity_bit_identical"] = bool(
+        np.array_equal(v0, v1) and np.array_equal(r0, r1))
+    ls.zeroSystem()
+    ls.assemble_continuity_edge(**pu.CONT_OPTS)
+    refused = False
+    if ls.halo_transport() == "peer_memory":
+        try:
+            ls.assemble_continuity_edge(**pu.CONT_OPTS)
+        except Exception:
+            refused = True
+    else:
+        refused = None
+    v2, r2 = ls.values()  # no loadComplete: the read completes the exchange
+    ls.loadComplete()     # ... and this is then a no-op
+    v3, r3 = ls.values()
+    # (NCCL transport: no eager exchange, the read sees the un-summed rows)
+    eager["reader_completes"] = bool(
+        (refused is None or
+         (np.array_equal(v0, v2) and np.array_equal(r0, r2))) and
+        np.array_equal(v0, v3) and np.array_equal(r0, r3))
+    eager["writer_refused"] = refused
+    ls.set_eager_exchange(False)
     ls.close()
 
     ls = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE_UVW, 3)
@@ -205,14 +237,28 @@ def main():
     check_system("momentum_uvw", ls,
                  pu.oracle_momentum(full, gfull, fmdot, fpec, uvw=True), 3)
     linsys_transport = ls.halo_transport()
+    v0, r0 = ls.values()
+    ls.set_eager_exchange(True)
+    ls.zeroSystem()
+    ls.assemble_momentum_edge("viscosity", **pu.MOM_OPTS)
+    ls.loadComplete()
+    v1, r1 = ls.values()
+    eager["momentum_bit_identical"] = bool(
+        np.array_equal(v0, v1) and np.array_equal(r0, r1))
     ls.close()
 
     # nodal gradients incl. the shared-node sum over NCCL
     gid2loc_full = {int(g): l for l, g in enumerate(full.box.gid)}
     for phi, d1 in (("pressure", 1), ("velocity", 3)):
         mesh.register("g_" + phi, P.NW_NODE, d1 * 3)
+        os.environ["NW_HALO_OVERLAP"] = "0"  # read per call
         mesh.nodal_grad_edge(phi, "g_" + phi)
+        plain_order = mesh.download("g_" + phi).copy()
+        del os.environ["NW_HALO_OVERLAP"]
+        mesh.nodal_grad_edge(phi, "g_" + phi)  # boundary tiles first
         got = mesh.download("g_" + phi).reshape(b.n_nodes, d1 * 3)
+        eager["grad_%s_bit_identical" % phi] = bool(
+            np.array_equal(plain_order.reshape(got.shape), got))
         ref = orc.nodal_grad_edge(d1, 3, full.edges, full.fields[phi], full.area,
                                   full.fields["dual_nodal_volume"], full.n_nodes)
         ref = ref.reshape(full.n_nodes, d1 * 3)
@@ -224,6 +270,17 @@ def main():
             worst = max(worst, float(np.max(np.abs(
                 got[l] - ref[gid2loc_full[int(b.gid[l])]])) / scale))
         res["grad_" + phi] = worst
+
+    # the pair gradient travels as one 6-component exchange: same bits as two
+    # single calls
+    mesh.register("g_density", P.NW_NODE, 3)
+    mesh.register("g_pair_a", P.NW_NODE, 3)
+    mesh.register("g_pair_b", P.NW_NODE, 3)
+    mesh.nodal_grad_edge("density", "g_density")
+    mesh.nodal_grad_edge_pair("pressure", "g_pair_a", "density", "g_pair_b")
+    eager["grad_pair_bit_identical"] = bool(
+        np.array_equal(mesh.download("g_pair_a"), mesh.download("g_pressure")) and
+        np.array_equal(mesh.download("g_pair_b"), mesh.download("g_density")))
 
     # copy_owned_to_shared: poison the non-owned copies, every copy must come
     # back equal to the serial field (bit-exact: a pure copy)
@@ -252,6 +309,8 @@ def main():
     dist.all_gather_object(allplain, plain)
     alldelay = [None] * world
     dist.all_gather_object(alldelay, delay)
+    alleager = [None] * world
+    dist.all_gather_object(alleager, eager)
     if rank == 0:
         worst = max(max(r.values()) for r in allres)
         out = {"world": world, "mesh": which, "dims": dims, "periodic": periodic,
@@ -259,6 +318,7 @@ def main():
                "linsys_transport": linsys_transport,
                "tolerance": "scaled: |got-ref| <= 1e-12 max(|ref|, sum |contributions|)",
                "worst_scaled_error": worst,
+               "eager_exchange": alleager,
                "worst_plain_relative_error": {
                    k: max(p_[k] for p_ in allplain) for k in allplain[0]},
                "per_rank": allres}
@@ -266,6 +326,7 @@ def main():
             out["delayed_rank_test"] = alldelay
         print(json.dumps(out))
         assert worst < 1.0, allres
+        assert all(v is not False for e in alleager for v in e.values()), alleager
         if delay is not None:
             assert all(d["ok"] for d in alldelay), alldelay
             assert any(d["error"] for d in alldelay if d["rank"] != 1), alldelay

@@ -26,6 +26,7 @@ if [ "${2:-}" = "all" ]; then
 run sst_fused "NW_SCALAR_PAIR_FUSED=1" "--sst --fuse-scalars --no-cpu-baseline"
 run warped "" "--mesh warped --sst --no-cpu-baseline"
 run mixed "" "--mesh mixed --sst --no-cpu-baseline"
+run mixed_refine "NW_TILE_REFINE=1" "--mesh mixed --sst --no-cpu-baseline"
 fi
 echo "=== phase cycles"
 make -C nalu-wind_b200 -s prof > /dev/null 2>&1 && NW_LIB_PATH=$PWD/nalu-wind_b200/libnalu_edge_b200_prof.so timeout 300 python tools/phase_times.py > gpurun_out/${TAG}_phase_cycles.txt 2>&1
