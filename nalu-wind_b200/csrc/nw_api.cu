@@ -1035,17 +1035,15 @@ grad_with_post_work(
       pd.nc = ncomp;
       pd.nSendTiles = H.nPushTiles;
       pd.pp = p2p_next(ctx);
-      MeshPlanDev md = mesh->dev;
-      md.tiles = H.dTilesPerm.as<TileHdr>();
-      md.haloBlock = H.dHaloBlockPerm.as<int32_t>();
-      NW_CUDA(launch_grad_tile(md, dim1, nc, vol, ec, out, s, &pd));
+      NW_CUDA(launch_grad_tile(mesh->dev, dim1, nc, vol, ec, out, s, &pd));
       launched = true;
       if (H.p2pMode == 1) {
         CompPtrs comps;
         for (int c = 0; c < ncomp; ++c)
           comps.c[c] = out[c];
         NW_CUDA(launch_p2p_pull_nodal(
-          comps, ncomp, H.dRecvIdx.as<int64_t>(), H.nRecvP2p, pd.pp, false, s));
+          comps, ncomp, H.dRecvIdx.as<int64_t>(), H.nRecvP2p, pd.pp, false, s,
+          true));
         first = nGrads; /* every field of the call is summed */
         for (int k = 0; k < nGrads; ++k)
           if (int rc = periodic_update(mesh, grads[k]))
@@ -1056,6 +1054,7 @@ grad_with_post_work(
         st.f = grads[0];
         st.pp = pd.pp;
         st.mode = 2;
+        st.signal = true;
         if (int rc = node_halo_sum_end(&st))
           return rc;
         if (int rc = periodic_update(mesh, grads[0]))
@@ -1582,11 +1581,7 @@ tile_assembly(nw_linsys* ls, Launch&& launch)
   LsPlanDev lpd = ls->dev;
   if (int rc = ls_eager_begin(ls, &lpd.push))
     return rc;
-  MeshPlanDev md = mesh->dev;
-  md.tiles = mesh->halo.dTilesPerm.as<TileHdr>();
-  md.haloBlock = mesh->halo.dHaloBlockPerm.as<int32_t>();
-  lpd.tiles = ls->sh->dLsTilesPerm.as<LsTileHdr>();
-  NW_CUDA(launch(md, lpd));
+  NW_CUDA(launch(mesh->dev, lpd));
   return finish_tile_assembly(ls);
 }
 

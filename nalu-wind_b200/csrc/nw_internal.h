@@ -194,16 +194,8 @@ struct nw_node_halo
   nw::DevBuf dSendIdx, dSendDst, dRecvIdx; /* int64 */
   nw::DevBuf dSendPeer, dPeerList;         /* int32 */
   nw::DevBuf dRecvIsGhost;                 /* uint8: receive entry is a ghost of mine */
-  /* boundary tiles first: the tiles holding a node of any exchange list, then
-   * the others, each group in plan order.  The gradient kernels run the first
-   * group, push, and run the second group while the neighbours' data travels */
-  std::vector<int32_t> tileOrder;
-  int nBoundaryTiles = 0;
-  /* the per-tile arrays of the mesh plan in that order (a CTA finds its tile
-   * by block index: no indirection on the critical path) */
-  nw::DevBuf dTilesPerm, dHaloBlockPerm;
-  /* fused push (NodePushDev): first send list of the mode, grouped by tile
-   * (launch order) */
+  /* fused push of the gradient kernels (NodePushDev): the first send list of
+   * the mode grouped by tile */
   int nPushTiles = 0;
   nw::DevBuf dPushTilePtr, dPushSlot, dPushPeer, dPushDst;
 };
@@ -216,6 +208,8 @@ struct NodeHaloSum
   nw_field_t* f = nullptr;
   nw::P2pDev pp;
   int mode = 0; /* 0: nothing sent yet (NCCL path / exchange skipped) */
+  bool signal = false; /* the push was fused into the producing kernel: the
+                          first pull kernel publishes the epoch */
 };
 
 struct nw_ls_shared;
@@ -273,9 +267,6 @@ struct nw_ls_shared
   nw::DevBuf dLsTiles, dEntInfo, dEntRhsRow, dHe, dWarp, dRuns;
   nw::DevBuf dUncovered, dUncoveredPeriodic, dRowPtr;
   nw::DevBuf dPeriodicRows;
-  /* lp.tiles in the mesh's boundary-tiles-first order (eager exchange) */
-  nw::DevBuf dLsTilesPerm;
-  bool permUploaded = false;
 };
 
 struct nw_linsys
@@ -343,6 +334,7 @@ struct nw_linsys
    * eagerState: 0 nothing outstanding, 1 pushed (pull outstanding), 2 pulled
    * by a later exchange of the context (load_complete is a no-op) */
   bool eager = false;
+  bool eagerFused = false; /* the outstanding push was done by the tile kernel */
   int eagerState = 0;
   nw::P2pDev eagerPP;
   int nSendTiles = 0;      /* tiles with rows of the shared tail */

@@ -260,44 +260,13 @@ halo_index_early(const MeshPlanDev& mp)
 }
 
 /* ---- fused push (eager exchange): a boundary tile stores what other ranks
- * need straight into their windows; the last such tile of the launch
- * publishes the epoch.  pp.sync[0] counts the tiles (kernels of one stream
- * run one after the other, and the word is back at zero when the launch
- * ends). ---- */
-__device__ __forceinline__ void
-st_release_sys_u64(unsigned long long* p, unsigned long long v)
-{
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void
-tile_push_signal(const P2pDev& pp, int nSendTiles)
-{
-  /* the CTA's remote stores are ordered before thread 0's fence by the
-   * barrier; the fence is cumulative (one system fence per tile instead of
-   * one per thread: the tile leaves its SM slot sooner) */
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    const unsigned done = atomicAdd(pp.sync, 1u) + 1u;
-    if (done == (unsigned)nSendTiles) {
-      pp.sync[0] = 0u;
-      __threadfence_system();
-      for (int i = 0; i < pp.nPeers; ++i)
-        st_release_sys_u64(pp.peerFlags[pp.peers[i]] + pp.myRank, pp.epoch);
-    }
-  }
-}
-/* a rank with nothing to send still tells its neighbours that the epoch is
- * complete: the first CTA of the launch does it straight away */
-__device__ __forceinline__ void
-tile_push_signal_empty(const P2pDev& pp)
-{
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    __threadfence_system();
-    for (int i = 0; i < pp.nPeers; ++i)
-      st_release_sys_u64(pp.peerFlags[pp.peers[i]] + pp.myRank, pp.epoch);
-  }
-}
+ * need straight into their windows and is done -- no fence, no counter: a
+ * system fence per tile holds the tile's SM slot for an NVLink round trip
+ * (measured at 512^3 over 8 GPUs, 14.6 k boundary tiles per rank:
+ * +1.5 ms per sweep, profiles/r02v_bench_n8_fence_per_tile.json).  The
+ * stores have landed when the kernel has completed; the epoch is published
+ * by the first block of the pull kernel that follows on the stream
+ * (p2p_signal_then_wait). ---- */
 __device__ __forceinline__ const PushSeg*
 push_seg_of_value(const LsPushDev& pd, int64_t k /* index in the shared tail */)
 {
@@ -959,8 +928,6 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
    * phase was a chain of dependent 30-cycle loads, 20 % of a CTA's life). ---- */
   /* eager exchange: this tile holds rows of the shared tail */
   const bool pushing = lp.push.seg != nullptr && lh.hasShared != 0;
-  if (lp.push.enabled && lp.push.nSendTiles == 0)
-    tile_push_signal_empty(lp.push.pp);
   if (!(mp.dbgSkip & 4)) {
     const int lane = threadIdx.x & 31;
     for (int row0 = (int)threadIdx.x - lane; row0 < lh.nEnts;
@@ -1073,8 +1040,6 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
       lp.diagOut[h.node0 + i] += acc;
     }
   }
-  if (pushing)
-    tile_push_signal(lp.push.pp, lp.push.nSendTiles);
   NW_PT_END();
 }
 
@@ -2210,8 +2175,6 @@ __global__ void __launch_bounds__(kTileThreads, D1 == 1 ? 8 : 5) grad_tile_kerne
       out.c[k][h.node0 + i] = acc[k] * invVol;
   }
   NW_PT_MARK();
-  if (push.tilePtr && push.nSendTiles == 0)
-    tile_push_signal_empty(push.pp);
   if (push.tilePtr) {
     /* eager exchange: the partial sums of this tile's shared nodes go straight
      * to the other sharers' windows (the values were written by this CTA: the
@@ -2227,7 +2190,6 @@ __global__ void __launch_bounds__(kTileThreads, D1 == 1 ? 8 : 5) grad_tile_kerne
         for (int c = 0; c < NV; ++c) /* constant indices: no local copy of `out` */
           w[c] = out.c[c][slot];
       }
-      tile_push_signal(push.pp, push.nSendTiles);
     }
   }
   NW_PT_END();
@@ -3342,6 +3304,20 @@ p2p_wait(const P2pDev& pp)
   return __syncthreads_or(bad) == 0;
 }
 
+/* pull kernel behind a kernel with a fused push: that kernel has completed,
+ * its remote stores have landed -- the first block publishes the epoch, then
+ * everybody waits for the neighbours' */
+__device__ __forceinline__ bool
+p2p_signal_then_wait(const P2pDev& pp, int signal)
+{
+  if (signal && blockIdx.x == 0 && threadIdx.x == 0) {
+    __threadfence_system();
+    for (int i = 0; i < pp.nPeers; ++i)
+      st_release_sys(pp.peerFlags[pp.peers[i]] + pp.myRank, pp.epoch);
+  }
+  return p2p_wait(pp);
+}
+
 /* nodal push: entry g of the concatenated send list, component c ->
  * window of rank sendPeer[g] at entry sendDst[g] */
 __global__ void __launch_bounds__(256) p2p_push_nodal_kernel(
@@ -3364,9 +3340,9 @@ __global__ void __launch_bounds__(256) p2p_push_nodal_kernel(
  * a + b on one side, b + a on the other -- the same bits) */
 __global__ void __launch_bounds__(256) p2p_pull_nodal_kernel(
   const CompPtrs comps, int nc, const int64_t* __restrict__ recvIdx,
-  int64_t n, const P2pDev pp)
+  int64_t n, const P2pDev pp, int signal)
 {
-  if (!p2p_wait(pp))
+  if (!p2p_signal_then_wait(pp, signal))
     return;
   const double* win = pp.myWindow + pp.winOff;
   const int64_t total = n * nc;
@@ -3422,10 +3398,10 @@ __global__ void __launch_bounds__(256) p2p_pull_accumulate_kernel(
   int64_t bufOff, int64_t entStride, int64_t compStride, int nc,
   const int64_t* __restrict__ dstIdx, const int64_t* __restrict__ ptr,
   const int64_t* __restrict__ pos, int64_t nDst, double* dst,
-  int64_t dstCompStride, const P2pDev pp, int wait)
+  int64_t dstCompStride, const P2pDev pp, int wait, int signal)
 {
   if (wait) {
-    if (!p2p_wait(pp))
+    if (!p2p_signal_then_wait(pp, signal))
       return;
   } else if (*(volatile unsigned*)(pp.sync + 1) != 0u) {
     return; /* the launch that waited for this epoch timed out */
@@ -3454,9 +3430,9 @@ __global__ void __launch_bounds__(256) p2p_pull_accumulate2_kernel(
   int64_t rhsOff, int64_t rhsColStride, int nR,
   const int64_t* __restrict__ rhsDst, const int64_t* __restrict__ rhsPtr,
   const int64_t* __restrict__ rhsPos, int64_t nRhs, double* rhs,
-  int64_t rhsStride, const P2pDev pp)
+  int64_t rhsStride, const P2pDev pp, int signal)
 {
-  if (!p2p_wait(pp))
+  if (!p2p_signal_then_wait(pp, signal))
     return;
   const double* buf = pp.myWindow + pp.winOff;
   const int64_t total = nVal + nRhs * nR;
@@ -4389,10 +4365,10 @@ launch_p2p_push_nodal(
 cudaError_t
 launch_p2p_pull_nodal(
   const CompPtrs& comps, int nc, const int64_t* recvIdx, int64_t n,
-  const P2pDev& pp, bool beside, cudaStream_t s)
+  const P2pDev& pp, bool beside, cudaStream_t s, bool signal)
 {
   p2p_pull_nodal_kernel<<<p2p_pull_grid(n * nc, beside), 256, 0, s>>>(
-    comps, nc, recvIdx, n, pp);
+    comps, nc, recvIdx, n, pp, signal ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -4423,11 +4399,11 @@ launch_p2p_pull_accumulate(
   int64_t bufOff, int64_t entStride, int64_t compStride, int nc,
   const int64_t* dstIdx, const int64_t* ptr, const int64_t* pos, int64_t nDst,
   double* dst, int64_t dstCompStride, const P2pDev& pp, bool wait, bool beside,
-  cudaStream_t s)
+  cudaStream_t s, bool signal)
 {
   p2p_pull_accumulate_kernel<<<p2p_pull_grid(nDst * nc, beside), 256, 0, s>>>(
     bufOff, entStride, compStride, nc, dstIdx, ptr, pos, nDst, dst,
-    dstCompStride, pp, wait ? 1 : 0);
+    dstCompStride, pp, wait ? 1 : 0, signal ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -4437,11 +4413,11 @@ launch_p2p_pull_accumulate2(
   int64_t nVal, double* values, int64_t rhsOff, int64_t rhsColStride, int nR,
   const int64_t* rhsDst, const int64_t* rhsPtr, const int64_t* rhsPos,
   int64_t nRhs, double* rhs, int64_t rhsStride, const P2pDev& pp, bool beside,
-  cudaStream_t s)
+  cudaStream_t s, bool signal)
 {
   p2p_pull_accumulate2_kernel<<<p2p_pull_grid(nVal + nRhs * nR, beside), 256, 0, s>>>(
     valDst, valPtr, valPos, nVal, values, rhsOff, rhsColStride, nR, rhsDst,
-    rhsPtr, rhsPos, nRhs, rhs, rhsStride, pp);
+    rhsPtr, rhsPos, nRhs, rhs, rhsStride, pp, signal ? 1 : 0);
   return cudaGetLastError();
 }
 

@@ -60,7 +60,7 @@ struct LsPushDev
   const PushSeg* seg = nullptr; /* null: nothing to send */
   int enabled = 0;              /* 0: no fused push in this launch */
   int nSeg = 0;
-  int nSendTiles = 0; /* tiles with hasShared: the last one publishes the epoch */
+  int nSendTiles = 0; /* tiles with hasShared */
   int64_t nnzOwned = 0, numRowsOwned = 0;
   P2pDev pp;
 };
@@ -319,7 +319,7 @@ cudaError_t launch_p2p_push_nodal(
 cudaError_t launch_p2p_pull_nodal(
   const CompPtrs& comps /* nc component arrays, internal slots */, int nc,
   const int64_t* recvIdx, int64_t n, const P2pDev& pp, bool beside,
-  cudaStream_t s);
+  cudaStream_t s, bool signal = false);
 cudaError_t launch_p2p_pull_assign_nodal(
   double* base, int64_t stride, int nc, const int64_t* recvIdx,
   const unsigned char* recvIsGhost, int64_t n, const P2pDev& pp, bool beside,
@@ -333,12 +333,12 @@ cudaError_t launch_p2p_pull_accumulate2(
   int64_t nVal, double* values, int64_t rhsOff, int64_t rhsColStride, int nR,
   const int64_t* rhsDst, const int64_t* rhsPtr, const int64_t* rhsPos,
   int64_t nRhs, double* rhs, int64_t rhsStride, const P2pDev& pp, bool beside,
-  cudaStream_t s);
+  cudaStream_t s, bool signal = false);
 cudaError_t launch_p2p_pull_accumulate(
   int64_t bufOff, int64_t entStride, int64_t compStride, int nc,
   const int64_t* dstIdx, const int64_t* ptr, const int64_t* pos, int64_t nDst,
   double* dst, int64_t dstCompStride, const P2pDev& pp, bool wait, bool beside,
-  cudaStream_t s);
+  cudaStream_t s, bool signal = false);
 
 /* all peers + all components in one launch; buffer element of concatenated
  * entry g, component c at buf[g * entStride + c * compStride] */
