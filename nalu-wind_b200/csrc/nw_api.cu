@@ -997,7 +997,9 @@ nw_peclet_edge(nw_mesh* mesh, int viscosity_field, const nw_peclet_opts* opts)
 }
 
 static int node_halo_sum(nw_mesh* mesh, nw_field_t* f);
-static P2pDev p2p_next(nw_ctx* ctx);
+static P2pDev p2p_next(nw_ctx* ctx, bool fusedPush);
+static int p2p_pull_begin(nw_ctx* ctx, cudaStream_t* out);
+static int p2p_pull_end(nw_ctx* ctx, cudaEvent_t* objEvent, bool* objPending);
 static int node_halo_sum_end(NodeHaloSum* st);
 static bool node_halo_overlap_applicable(nw_mesh* mesh);
 static int periodic_update(nw_mesh* mesh, nw_field_t* f);
@@ -1034,16 +1036,22 @@ grad_with_post_work(
       pd.dst = H.dPushDst.as<int64_t>();
       pd.nc = ncomp;
       pd.nSendTiles = H.nPushTiles;
-      pd.pp = p2p_next(ctx);
+      pd.pp = p2p_next(ctx, true);
       NW_CUDA(launch_grad_tile(mesh->dev, dim1, nc, vol, ec, out, s, &pd));
       launched = true;
       if (H.p2pMode == 1) {
         CompPtrs comps;
         for (int c = 0; c < ncomp; ++c)
           comps.c[c] = out[c];
+        cudaStream_t ps;
+        if (int rc = p2p_pull_begin(ctx, &ps))
+          return rc;
         NW_CUDA(launch_p2p_pull_nodal(
-          comps, ncomp, H.dRecvIdx.as<int64_t>(), H.nRecvP2p, pd.pp, false, s,
-          true));
+          comps, ncomp, H.dRecvIdx.as<int64_t>(), H.nRecvP2p, pd.pp,
+          ctx->p2p.async, ps, true));
+        for (int k = 0; k < nGrads; ++k)
+          if (int rc = p2p_pull_end(ctx, &grads[k]->pullDone, &grads[k]->pullPending))
+            return rc;
         first = nGrads; /* every field of the call is summed */
         for (int k = 0; k < nGrads; ++k)
           if (int rc = periodic_update(mesh, grads[k]))

@@ -89,7 +89,7 @@ struct nw_p2p
 {
   bool ok = false;
   int64_t winDoubles = 0; /* doubles per parity half of the window */
-  nw::DevBuf window;      /* [2][winDoubles] */
+  nw::DevBuf window;      /* [3][winDoubles] */
   nw::DevBuf flags;       /* unsigned long long [nranks]: epoch written by rank r */
   nw::DevBuf sync;        /* [0] block counter, [1] timeout/error word */
   std::vector<void*> mappedWindow, mappedFlags; /* per rank, opened IPC handles */
@@ -113,6 +113,10 @@ struct nw_p2p
   cudaStream_t commStream = nullptr;
   cudaEvent_t pushDone = nullptr; /* compute stream: producer + push issued */
   cudaEvent_t lastPull = nullptr; /* completion event of the latest pull (not owned) */
+  /* "the pull of epoch e is done", slot e mod 3 (p2p_next: a kernel with a
+   * fused push waits for the pull two exchanges back only) */
+  cudaEvent_t pullRing[3] = {nullptr, nullptr, nullptr};
+  unsigned long long pullRingEpoch[3] = {0, 0, 0};
   /* a linear system whose shared rows were pushed from its assembly call
    * (eager exchange) and not yet pulled: the next exchange of the context
    * completes it first (the window protocol wants pull(e) before push(e+1)) */
