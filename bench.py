@@ -102,11 +102,11 @@ def parse():
                          "of the pipelined nw_field_stage / nw_field_commit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="eager", choices=["eager", "plain"],
-                    help="N > 1: 'eager' (default) lets every edge assembly run "
-                         "its boundary tiles first and send the shared rows while "
-                         "the interior tiles are assembled (nw_linsys_set_eager_"
-                         "exchange; the sweep has no other contribution before "
-                         "loadComplete); 'plain' sends them in loadComplete")
+                    help="N > 1: 'eager' (default) lets every edge assembly "
+                         "store its shared rows straight into the owners' windows "
+                         "(nw_linsys_set_eager_exchange; the sweep has no other "
+                         "contribution before loadComplete); 'plain' sends them "
+                         "in loadComplete")
     ap.add_argument("--fuse-scalars", dest="no_fuse_scalars", action="store_false",
                     default=True,
                     help="--sst: assemble the TKE and SDR systems through "
@@ -435,8 +435,9 @@ def workload_config(args, n_gpus):
                   ((n + 1) ** 3 * 8 * 60) / 1e9),
         "tile_nodes": args.tile if args.tile else "default",
         "exchange": ("n/a (one GPU)" if n_gpus == 1 else
-                     "boundary tiles first, shared rows / nodes pushed over NVLink "
-                     "behind them while the interior tiles run"
+                     "fused: the tile kernels store shared rows / nodal partial "
+                     "sums straight into the neighbours' windows over NVLink, "
+                     "one pull kernel per exchange on a communication stream"
                      if getattr(args, "exchange", "eager") == "eager" and
                      os.environ.get("NW_HALO_OVERLAP", "1") != "0" else
                      "after the full kernel (loadComplete / post_work)"),
@@ -603,17 +604,16 @@ class Sweep:
             # scalar assemblies (one fused launch or two) + the paired gradient
             n += (2 if self.args.no_fuse_scalars else 1) + 1
         if self.world > 1:
-            # halo exchange kernels (peer-memory transport): a linear system
-            # pushes once and pulls twice (values, rhs), a nodal sum pushes and
-            # pulls once; boundary-tiles-first splits the producing launch
-            overlap = (self.args.exchange == "eager" and
-                       os.environ.get("NW_HALO_OVERLAP", "1") != "0")
+            # halo exchange kernels (peer-memory transport).  Fused: the
+            # producing kernel stores into the neighbours' windows, one pull
+            # kernel per exchange (the pair gradient is one exchange).  Plain:
+            # a push and a pull kernel per exchange, one exchange per field.
+            fused = (self.args.exchange == "eager" and
+                     os.environ.get("NW_HALO_OVERLAP", "1") != "0")
             n_ls = 2 + (2 if self.sst else 0)
             n_grad_calls = 2 + (1 if self.sst else 0)
             n_sums = 2 + (2 if self.sst else 0)
-            n += n_ls * 3 + n_sums * 2
-            if overlap:
-                n += n_ls + n_grad_calls
+            n += (n_ls + n_grad_calls) if fused else 2 * (n_ls + n_sums)
         return n
 
     def norms(self, glob):

@@ -345,10 +345,9 @@ int nw_linsys_set_scatter_mode(nw_linsys* ls, int mode);
  * src/HypreLinearSystem.C:1236-1385), after every algorithm has contributed.
  * With on != 0 the caller promises that the edge assembly
  * (nw_assemble_*_edge) is the LAST contribution to rows shared with other
- * ranks before nw_linsys_load_complete: the assembly then runs the tiles
- * that own shared or receiving rows first, sends the shared rows to their
- * owners and assembles the interior tiles while they travel;
- * nw_linsys_load_complete only adds what has arrived.  Until then any call
+ * ranks before nw_linsys_load_complete: the assembly kernel then stores the
+ * shared rows straight into their owners' memory while it runs (no separate
+ * send); nw_linsys_load_complete only adds what has arrived.  Until then any call
  * that adds to the system returns NW_ERR_STATE (the addition could not reach
  * the owners any more); calls that read it complete the exchange first.
  * Results are bit-identical to the default order. */

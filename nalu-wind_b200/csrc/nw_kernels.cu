@@ -4339,15 +4339,20 @@ p2p_grid(int64_t elems)
   return (int)std::max<int64_t>(1, std::min(b, cap));
 }
 /* pull kernels run on the communication stream beside the compute kernels of
- * the main stream and spin until the neighbour's push has landed: keep them
- * small so that they hold few SM resources while they wait */
+ * the main stream and spin until the neighbour's epoch has arrived: keep them
+ * small so that they hold few SM resources while they wait -- but not so
+ * small that a large exchange (512^3 over 8 GPUs: 5 M values per system)
+ * becomes a millisecond of serial work the next-but-one kernel has to wait
+ * for: at most ~8 grid-stride iterations per thread */
 inline int
 p2p_pull_grid(int64_t elems, bool beside)
 {
   if (!beside)
     return p2p_grid(elems);
   const int64_t b = (elems + 255) / 256;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(b, 32));
+  const int64_t want = std::max<int64_t>(32, (b + 7) / 8);
+  return (int)std::max<int64_t>(
+    1, std::min<int64_t>(std::min(b, want), 2 * (int64_t)sm_count()));
 }
 } // namespace
 
