@@ -804,39 +804,49 @@ def main():
     if args.detail:
         # the monolithic 3-dof momentum system (HypreLinearSystem, 6x6 blocks;
         # not part of the sweep: every deck of SURVEY 8 runs the segregated UVW
-        # system): fp64-atomic scatter through the slot map, timed on its own
+        # system), timed on its own: the tile kernel (node graph's plan, three
+        # rows per node, no atomics) and the fp64-atomic scatter through the
+        # slot map (zero fill + atomics)
         try:
             mono = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE, 3)
             mono.buildEdgeToNodeGraph()
             mono.finalizeLinearSystem()
             mesh.peclet_edge("viscosity", sw.pf)
-
-            def mono_asm():
-                mono.zeroSystem()
-                mono.assemble_momentum_edge("viscosity", **MOM_OPTS)
-            for _ in range(2):
-                mono_asm()
-            barrier()
-            a, b = sw.ev(), sw.ev()
-            a.record(sw.stream)
-            for _ in range(5):
-                mono_asm()
-            b.record(sw.stream)
-            barrier()
-            tms = a.elapsed_time(b) / 5
             bpe = (144 + 8 * (9 * sw.z + 3)) * sw.r + 48
-            gbs = bpe * edges_local / (tms * 1e-3) / 1e9
-            per_kernel["momentum_monolithic_atomic"] = {
-                "ms": tms, "calls_per_step": 0, "algorithmic_gbs": gbs,
-                "frac": gbs / peak, "algorithmic_bytes_per_edge": bpe,
-                "note": "zero fill (memset of 9 z N values) + atomic scatter"}
-            if rank == 0:
-                print("  %-14s %8.3f ms (not in the sweep) %8.1f GB/s algorithmic  "
-                      "%5.1f%% of peak" % ("momentum_mono", tms, gbs,
-                                           100 * gbs / peak), file=sys.stderr)
+            for key, smode, note in (
+                    ("momentum_monolithic_tile", P.NW_SCATTER_SEGMENTED,
+                     "ls_tile_kernel<MomentumMonoP>: rows written once, no zero fill"),
+                    ("momentum_monolithic_atomic", P.NW_SCATTER_ATOMIC,
+                     "zero fill (memset of 9 z N values) + atomic scatter")):
+                if smode == P.NW_SCATTER_SEGMENTED and not mono.uses_tile_path():
+                    continue
+                mono.set_scatter_mode(smode)
+
+                def mono_asm():
+                    mono.zeroSystem()
+                    mono.assemble_momentum_edge("viscosity", **MOM_OPTS)
+                for _ in range(2):
+                    mono_asm()
+                barrier()
+                a, b = sw.ev(), sw.ev()
+                a.record(sw.stream)
+                for _ in range(5):
+                    mono_asm()
+                b.record(sw.stream)
+                barrier()
+                tms = a.elapsed_time(b) / 5
+                gbs = bpe * edges_local / (tms * 1e-3) / 1e9
+                per_kernel[key] = {
+                    "ms": tms, "calls_per_step": 0, "algorithmic_gbs": gbs,
+                    "frac": gbs / peak, "algorithmic_bytes_per_edge": bpe,
+                    "note": note}
+                if rank == 0:
+                    print("  %-26s %8.3f ms (not in the sweep) %8.1f GB/s algorithmic  "
+                          "%5.1f%% of peak" % (key, tms, gbs, 100 * gbs / peak),
+                          file=sys.stderr)
             mono.close()
         except P.NwError as e:  # e.g. > 2^31 non-zeros on a large partition
-            per_kernel["momentum_monolithic_atomic"] = {"error": str(e)[:160]}
+            per_kernel["momentum_monolithic"] = {"error": str(e)[:160]}
         roofline["per_kernel"] = per_kernel
 
     # ---------------- end to end through the C ABI with host buffers -------

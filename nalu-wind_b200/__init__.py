@@ -128,6 +128,7 @@ ABI_SYMBOLS = [
     "nw_linsys_finalize", "nw_linsys_get_sizes", "nw_linsys_get_graph",
     "nw_linsys_get_edge_slots", "nw_linsys_zero",
     "nw_linsys_set_scatter_mode", "nw_linsys_set_eager_exchange",
+    "nw_linsys_uses_tile_path",
     "nw_assemble_continuity_edge",
     "nw_assemble_scalar_edge", "nw_assemble_scalar_edge_pair", "nw_assemble_momentum_edge",
     "nw_assemble_mass_bdf_node", "nw_assemble_wall_dist_edge",
@@ -212,6 +213,7 @@ def lib():
     L.nw_linsys_zero.argtypes = [vp]
     L.nw_linsys_set_scatter_mode.argtypes = [vp, C.c_int]
     L.nw_linsys_set_eager_exchange.argtypes = [vp, C.c_int]
+    L.nw_linsys_uses_tile_path.argtypes = [vp]
     L.nw_assemble_continuity_edge.argtypes = [vp, C.POINTER(ContinuityOpts)]
     L.nw_assemble_scalar_edge.argtypes = [vp, C.c_int, C.c_int, C.c_int,
                                           C.POINTER(ScalarOpts)]
@@ -556,6 +558,9 @@ class LinearSystem:
 
     def set_scatter_mode(self, mode):
         _chk(lib().nw_linsys_set_scatter_mode(self.h, mode))
+
+    def uses_tile_path(self):
+        return bool(lib().nw_linsys_uses_tile_path(self.h))
 
     def set_eager_exchange(self, on=True):
         """The edge assembly is the last contribution to shared rows before

@@ -1248,23 +1248,13 @@ nw_linsys_build_edge_to_node_graph(nw_linsys* ls)
   return NW_OK;
 }
 
+/* the integer plan of a shared graph goes to the device once */
 static int
-linsys_upload(nw_linsys* ls)
+shared_upload(nw_ls_shared& sh, cudaStream_t s)
 {
-  nw_mesh* m = ls->mesh;
-  cudaStream_t s = m->ctx->stream;
-  NW_CUDA(cudaSetDevice(m->ctx->device));
-  nw_ls_shared& sh = *ls->sh;
   const Graph& g = sh.g;
-  const int64_t nnz = g.nnzOwned + g.nnzShared + ls->nExtra;
   const int64_t rows = g.numRowsLocal();
-  NW_CUDA(ls->dValues.alloc(sizeof(double) * (nnz + 2)));
-  NW_CUDA(ls->dRhs.alloc(sizeof(double) * (rows * ls->nRhs + 2)));
-  ls->dev.values = ls->dValues.as<double>();
-  ls->dev.rhs = ls->dRhs.as<double>();
-  ls->dev.rhsStride = rows;
   int rc;
-  /* the integer plan is uploaded once per shared graph */
   if (!sh.uploaded) {
     if (sh.lp.usable) {
       if ((rc = upload(sh.dLsTiles, sh.lp.tiles, s, nullptr)) ||
@@ -1300,6 +1290,35 @@ linsys_upload(nw_linsys* ls)
       return rc;
     sh.uploaded = true;
   }
+  return NW_OK;
+}
+
+static int
+linsys_upload(nw_linsys* ls)
+{
+  nw_mesh* m = ls->mesh;
+  cudaStream_t s = m->ctx->stream;
+  NW_CUDA(cudaSetDevice(m->ctx->device));
+  nw_ls_shared& sh = *ls->sh;
+  const Graph& g = sh.g;
+  const int64_t nnz = g.nnzOwned + g.nnzShared + ls->nExtra;
+  const int64_t rows = g.numRowsLocal();
+  NW_CUDA(ls->dValues.alloc(sizeof(double) * (nnz + 2)));
+  NW_CUDA(ls->dRhs.alloc(sizeof(double) * (rows * ls->nRhs + 2)));
+  ls->dev.values = ls->dValues.as<double>();
+  ls->dev.rhs = ls->dRhs.as<double>();
+  ls->dev.rhsStride = rows;
+  int rc;
+  if ((rc = shared_upload(sh, s)))
+    return rc;
+  if (ls->monoOk) {
+    if ((rc = shared_upload(*ls->twin, s)) ||
+        (rc = upload(ls->dMonoGo, ls->monoGo, s, nullptr)) ||
+        (rc = upload(ls->dMonoRow, ls->monoRow, s, nullptr)) ||
+        (rc = upload(ls->dMonoUncovered, ls->monoUncovered, s, nullptr)) ||
+        (rc = upload(ls->dMonoUncoveredPer, ls->monoUncoveredPer, s, nullptr)))
+      return rc;
+  }
   if (sh.lp.usable) {
     ls->dev.tiles = sh.dLsTiles.as<LsTileHdr>();
     ls->dev.entInfo = sh.dEntInfo.as<EntInfo>();
@@ -1315,6 +1334,101 @@ linsys_upload(nw_linsys* ls)
   NW_CUDA(ls->dNormPartial.alloc(sizeof(double) * nPartial * ls->nRhs));
   NW_CUDA(ls->dNormOut.alloc(sizeof(double) * 8));
   NW_CUDA(cudaStreamSynchronize(s));
+  return NW_OK;
+}
+
+/* Monolithic system on the tile path: find (or build) the node graph of this
+ * mesh and check that the ndim-dof graph is its exact blow-up -- row nd r + i
+ * of node row r has nd entries per node-row entry, in the same column order,
+ * and the nd rows of a node are contiguous.  Anything else (skipped rows, a
+ * graph the builder laid out differently) keeps the atomic kernel. */
+static int
+build_mono_twin(nw_linsys* ls)
+{
+  ls->monoOk = false;
+  ls->twin.reset();
+  const int nd = ls->numDof;
+  if (ls->kind != NW_LINSYS_HYPRE || nd < 2 || !ls->skipped.empty())
+    return NW_OK;
+  std::shared_ptr<nw_ls_shared> tw;
+  for (auto& c : ls->mesh->lsCache)
+    if (c->numDof == 1 && c->skipped.empty())
+      tw = c;
+  if (!tw) {
+    tw = std::make_shared<nw_ls_shared>();
+    NW_TRY(build_graph(ls->mesh->plan, NW_LINSYS_HYPRE, 1, {}, tw->g);
+           build_ls_plan(ls->mesh->plan, tw->g, tw->lp);)
+    tw->numDof = 1;
+    ls->mesh->lsCache.push_back(tw);
+  }
+  const Graph& g1 = tw->g;
+  const Graph& g3 = ls->sh->g;
+  const LsPlan& lp = tw->lp;
+  if (!lp.usable || g3.numRowsOwned != nd * g1.numRowsOwned ||
+      g3.numRowsShared != nd * g1.numRowsShared)
+    return NW_OK;
+  auto row3 = [&](int64_t r1) {
+    return r1 < g1.numRowsOwned
+             ? nd * r1
+             : g3.numRowsOwned + nd * (r1 - g1.numRowsOwned);
+  };
+  /* checked for the rows the tiles write (a periodic slave row is a lone
+   * diagonal in both graphs and is left to the row initialisation) */
+  /* (the per-tile lists are padded: only the first nEnts of a tile count) */
+  std::vector<uint8_t> live(lp.entRhsRow.size(), 0);
+  for (const LsTileHdr& lh : lp.tiles)
+    for (int32_t e = lh.entPtr; e < lh.entPtr + lh.nEnts; ++e)
+      live[(size_t)e] = 1;
+  const int64_t nE = (int64_t)lp.entRhsRow.size();
+  bool ok = true;
+#pragma omp parallel for schedule(static) reduction(&& : ok)
+  for (int64_t e = 0; e < nE; ++e) {
+    if (!live[(size_t)e])
+      continue;
+    const int64_t r1 = lp.entRhsRow[(size_t)e];
+    const int64_t len1 = g1.rowLen(r1), p1 = g1.rowPtr(r1);
+    const int64_t r3 = row3(r1);
+    for (int i = 0; i < nd && ok; ++i) {
+      if (g3.rowLen(r3 + i) != nd * len1 ||
+          g3.rowPtr(r3 + i) != g3.rowPtr(r3) + (int64_t)i * nd * len1) {
+        ok = false;
+        break;
+      }
+      const int64_t p3 = g3.rowPtr(r3 + i);
+      for (int64_t k = 0; k < len1 && ok; ++k)
+        for (int c = 0; c < nd; ++c)
+          if (g3.cols[p3 + nd * k + c] != nd * g1.cols[p1 + k] + c)
+            ok = false;
+    }
+  }
+  if (!ok)
+    return NW_OK;
+  const size_t nEnt = lp.entRhsRow.size();
+  ls->monoGo.resize(nEnt);
+  ls->monoRow.resize(nEnt);
+  for (size_t e = 0; e < nEnt; ++e) {
+    if (!live[e]) {
+      ls->monoRow[e] = 0;
+      ls->monoGo[e] = 0;
+      continue;
+    }
+    const int64_t r3 = row3(lp.entRhsRow[e]);
+    ls->monoRow[e] = (int32_t)r3;
+    ls->monoGo[e] = (int32_t)g3.rowPtr(r3);
+  }
+  ls->monoUncovered.clear();
+  ls->monoUncoveredPer.clear();
+  for (int32_t r1 : lp.uncoveredRows)
+    for (int i = 0; i < nd; ++i) {
+      const int64_t r3 = row3(r1) + i;
+      ls->monoUncovered.push_back((int32_t)r3);
+      ls->monoUncoveredPer.push_back(
+        r3 < g3.numRowsOwned &&
+        std::binary_search(
+          g3.periodicRowsOwned.begin(), g3.periodicRowsOwned.end(), g3.iLower + r3));
+    }
+  ls->twin = tw;
+  ls->monoOk = true;
   return NW_OK;
 }
 
@@ -1354,6 +1468,8 @@ nw_linsys_finalize(nw_linsys* ls)
   if (ls->sh->g.nnzOwned + ls->sh->g.nnzShared >= (int64_t(1) << 31) - 8)
     return fail(
       NW_ERR_LIMIT, "nw_linsys_finalize: more than 2^31 nonzeros per rank");
+  if (int rc = build_mono_twin(ls))
+    return rc;
   if (ls->mesh->plan.nranks > 1)
     if (int rc = linsys_build_halo(ls))
       return rc;
@@ -1511,6 +1627,25 @@ nw_linsys_set_scatter_mode(nw_linsys* ls, int mode)
     return fail(NW_ERR_ARG, "nw_linsys_set_scatter_mode: bad argument");
   ls->mode = mode;
   return NW_OK;
+}
+
+extern "C" int
+nw_linsys_uses_tile_path(const nw_linsys* ls)
+{
+  if (!ls || !ls->finalized)
+    return 0;
+  if (ls->kind == NW_LINSYS_HYPRE && ls->numDof > 1) {
+    if (!ls->monoOk)
+      return 0;
+    if (ls->mesh->ctx->device < 0)
+      return 1;
+    LsPlanDev ld = ls->dev; /* shared-memory need of the monolithic policy */
+    ld.maxTileNnz = (int)ls->twin->lp.maxTileNnz;
+    ld.maxTileEnts = (int)ls->twin->lp.maxTileEnts;
+    ld.maxTileEll = (int)ls->twin->lp.maxTileEll;
+    return ls_tile_fits(ls->mesh->dev, ld, 3) ? 1 : 0;
+  }
+  return ls->sh->lp.usable ? 1 : 0;
 }
 
 static int
@@ -1835,7 +1970,36 @@ nw_assemble_momentum_edge(
       mesh->dev, ls->dev, am, nc, ec, *opts, diagOut, s));
     return NW_OK;
   }
-  /* monolithic: atomic scatter of the full block */
+  /* monolithic on the tile path: the node graph's plan, ndim rows per node */
+  if (ls->monoOk && ls->mode == NW_SCATTER_SEGMENTED &&
+      ls->state == NW_LS_LAZY_ZERO) {
+    const nw_ls_shared& tw = *ls->twin;
+    LsPlanDev ld = ls->dev; /* values, rhs of THIS system */
+    ld.tiles = tw.dLsTiles.as<LsTileHdr>();
+    ld.entInfo = tw.dEntInfo.as<EntInfo>();
+    ld.heEll = tw.dHe.as<uint32_t>();
+    ld.sliceOff = tw.dWarp.as<int32_t>();
+    ld.entRhsRow = ls->dMonoRow.as<int32_t>();
+    ld.entGo = ls->dMonoGo.as<int32_t>();
+    ld.maxTileNnz = (int)tw.lp.maxTileNnz;
+    ld.maxTileEnts = (int)tw.lp.maxTileEnts;
+    ld.maxTileEll = (int)tw.lp.maxTileEll;
+    if (ls_tile_fits(mesh->dev, ld, 3)) {
+      NW_CUDA(launch_momentum_mono_tile(mesh->dev, ld, nc, ec, *opts, diagOut, s));
+      /* rows no tile writes (periodic slaves: diag 1), the COO extension */
+      NW_CUDA(launch_row_init(
+        ls->dMonoUncovered.as<int32_t>(), (int)ls->monoUncovered.size(),
+        ls->sh->dRowPtr.as<int64_t>(), ls->dMonoUncoveredPer.as<uint8_t>(),
+        ls->dev.values, ls->dev.rhs, ls->dev.rhsStride, ls->nRhs, s));
+      if (ls->nExtra > 0)
+        NW_CUDA(cudaMemsetAsync(
+          ls->dev.values + ls->sh->g.nnzOwned + ls->sh->g.nnzShared, 0,
+          sizeof(double) * ls->nExtra, s));
+      ls->state = NW_LS_ACCUM;
+      return NW_OK;
+    }
+  }
+  /* otherwise: atomic scatter of the full block */
   if (ls->state != NW_LS_ACCUM)
     if ((rc = materialize_zero(ls)))
       return rc;

@@ -332,6 +332,14 @@ struct nw_linsys
    * (row, col) pairs appended after the reference-layout arrays */
   int64_t nExtra = 0;
   std::vector<int64_t> extraRows, extraCols;
+  /* monolithic ndim-dof system on the tile path: the node graph's plan (the
+   * 1-dof twin, shared with the scalar systems of the mesh) plus, per tile
+   * row, the value offset and the local row of the node's first dof */
+  std::shared_ptr<nw_ls_shared> twin;
+  bool monoOk = false;
+  std::vector<int32_t> monoGo, monoRow, monoUncovered;
+  std::vector<uint8_t> monoUncoveredPer;
+  nw::DevBuf dMonoGo, dMonoRow, dMonoUncovered, dMonoUncoveredPer;
   /* eager exchange (nw_linsys_set_eager_exchange): the tile assembly runs the
    * tiles that own shared or receiving rows first, pushes the shared tail and
    * assembles the interior tiles behind the push; load_complete only pulls.

@@ -742,6 +742,87 @@ struct GmemLd
 
 /* shared-memory carve-up of ls_tile_kernel, shared by the kernel and the
  * host-side size computation (all region sizes are multiples of 16 bytes) */
+/* Monolithic 3-dof momentum (HypreLinearSystem with numDof = ndim: the full
+ * 2ND x 2ND block of MomentumEdgeSolverAlg.C:275-310 through sum_into,
+ * src/HypreLinearSystem.C:2059-2161).  Same staging and physics as the UVW
+ * policy; an edge keeps the four same-component scalars, the flux, and the
+ * three factors of the cross-component term -viscIp a_i a_j / axdx, from which
+ * the row walk forms the ND x ND blocks (momentum_block_entry's expression and
+ * order).  The reduction runs on the NODE graph's plan (the 1-dof twin of the
+ * 3-dof graph: row 3r+i of node r holds the entries of the node row, three
+ * columns each) and writes straight to the CSR arrays -- no staging. */
+template <int ND>
+struct MomentumMonoP : MomentumUvwP<ND>
+{
+  using Base = MomentumUvwP<ND>;
+  using Opts = nw_momentum_opts;
+  using Node = MomNode<ND>;
+  static constexpr int kMinBlocks = 1;
+  static constexpr int NRES = 4 + ND + 2 + ND;
+  static constexpr int kSame = 0, kFlux = 4, kVisc = 4 + ND, kInv = 5 + ND, kArea = 6 + ND;
+  __device__ __forceinline__ static void compute_n(
+    const Node& L, const Node& R, const double* av, double mdot, double pecfac,
+    const Opts& o, double* res)
+  {
+    if (o.fuse_peclet) {
+      PecNode<ND> pl, pr;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        pl.x[d] = L.x[d];
+        pr.x[d] = R.x[d];
+        pl.v[d] = L.u[d];
+        pr.v[d] = R.u[d];
+      }
+      pl.rho = L.rho;
+      pr.rho = R.rho;
+      pl.mu = L.mu;
+      pr.mu = R.mu;
+      pecfac = peclet_eval(o.pf, peclet_number<ND>(pl, pr, o.pec_eps));
+    }
+    MomResult<ND> m;
+    momentum_edge<ND>(L, R, av, mdot, pecfac, o, m);
+    res[0] = m.sLL;
+    res[1] = m.sLR;
+    res[2] = m.sRL;
+    res[3] = m.sRR;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      res[kFlux + d] = m.flux[d];
+      res[kArea + d] = av[d];
+    }
+    res[kVisc] = m.viscIp;
+    res[kInv] = m.inv_axdx;
+  }
+  template <class LD>
+  __device__ __forceinline__ static void compute(
+    const LD& ld, int l, int r, const double* av, double mdot, double pecfac,
+    const Opts& o, double* res)
+  {
+    Node L, R;
+    Base::load(ld, l, L);
+    Base::load(ld, r, R);
+    compute_n(L, R, av, mdot, pecfac, o, res);
+  }
+  /* entry (0,0) of the diagonal block of this half-edge (extract_diagonal) */
+  __device__ __forceinline__ static double diag00(
+    uint32_t side, const double* s_res, int rs, int j, const Opts& o)
+  {
+    const double* p = s_res + j;
+    const double ns = -p[kVisc * rs] * p[kArea * rs] * p[kArea * rs] * p[kInv * rs];
+    return p[side ? 3 * rs : 0] - ns * nw_rcp(o.relax_fac);
+  }
+};
+template <class P>
+struct IsMonoPolicy
+{
+  static constexpr bool value = false;
+};
+template <int ND>
+struct IsMonoPolicy<MomentumMonoP<ND>>
+{
+  static constexpr bool value = true;
+};
+
 template <class P>
 struct LsSmem
 {
@@ -764,8 +845,11 @@ struct LsSmem
     lrLen = (mp.maxTileEdges + 3) & ~3;
     valsLen = (lp.maxTileNnz + 3) & ~3;
     /* row staging: values (8 B) + value-offset deltas (4 B), and behind it the
-     * node-keyed half-edge list of extract_diagonal (4 B records) */
-    rowRegion = valsLen + valsLen / 2;
+     * node-keyed half-edge list of extract_diagonal (4 B records); the
+     * monolithic policy stages ND x ND values per node-row entry and copies
+     * out node by node (no deltas) */
+    rowRegion = IsMonoPolicy<P>::value ? valsLen * P::kND * P::kND
+                                       : valsLen + valsLen / 2;
     const int rowAll = rowRegion + (mp.maxTileEllNode + 1) / 2 + 2;
     const int stage = P::NC * mp.maxStaged;
     nodeRegion = stage > rowAll ? stage : rowAll;
@@ -926,6 +1010,87 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
    * point to, are loaded before anything of the block is stored, so that the
    * shared-memory latencies of a block overlap (round-1 phase cycles: this
    * phase was a chain of dependent 30-cycle loads, 20 % of a CTA's life). ---- */
+  if constexpr (IsMonoPolicy<P>::value) {
+    /* ---- monolithic rows: one thread per node walks the node's half-edges
+     * and writes its ND rows (ND x ND block per neighbour) in place; s_go is
+     * the value offset of row ND r, s_row its local row ---- */
+    const double invRelax = nw_rcp(o.relax_fac);
+    const int rs = L.resStride;
+    const int lane = threadIdx.x & 31;
+    for (int row0 = (int)threadIdx.x - lane; row0 < lh.nEnts; row0 += blockDim.x) {
+      const int row = row0 + lane;
+      if (row < lh.nEnts) {
+        const int sl = row0 >> 5;
+        const int o0 = s_slice[sl], o1 = s_slice[sl + 1];
+        const uint32_t* hp = s_ell + o0 + lane;
+        const int W = (o1 - o0) >> 5;
+        const EntInfo ei = s_ent[row];
+        const int rowLen = ND * (int)ei.nnz;
+        double* vbase = s_vals + ND * ND * (int)ei.base; /* staged: ND rows */
+        double dg[ND][ND], rhs[ND];
+#pragma unroll
+        for (int i = 0; i < ND; ++i) {
+          rhs[i] = 0.0;
+#pragma unroll
+          for (int c = 0; c < ND; ++c)
+            dg[i][c] = 0.0;
+        }
+        for (int w = 0; w < W; ++w) {
+          const uint32_t hv = hp[w * 32];
+          if (!(hv & kHeValid))
+            continue;
+          const double* p = s_res + he_edge(hv);
+          const bool side = he_side(hv) != 0;
+          const double sXX = p[side ? 3 * rs : 0];
+          const double sXY = p[side ? 2 * rs : rs];
+          const double visc = p[P::kVisc * rs], inv = p[P::kInv * rs];
+          double a[ND];
+#pragma unroll
+          for (int d = 0; d < ND; ++d)
+            a[d] = p[(P::kArea + d) * rs];
+          double* dst = vbase + ND * (int)he_k(hv);
+          const bool dup = (hv & kHeDup) != 0;
+#pragma unroll
+          for (int i = 0; i < ND; ++i) {
+            const double f = p[(P::kFlux + i) * rs];
+            rhs[i] += side ? f : -f;
+#pragma unroll
+            for (int c = 0; c < ND; ++c) {
+              /* momentum_block_entry (edge_physics.h) */
+              const double ns = -visc * a[i] * a[c] * inv;
+              const double s = (i == c) ? 1.0 : 0.0;
+              dg[i][c] += s * sXX - ns * invRelax;
+              double off = s * sXY + ns;
+              double* q = dst + i * rowLen + c;
+              if (dup)
+                off += *q;
+              *q = off;
+            }
+          }
+        }
+        double* dd = vbase + ND * (int)ei.diagK;
+        const int64_t grow = s_row[row];
+#pragma unroll
+        for (int i = 0; i < ND; ++i) {
+#pragma unroll
+          for (int c = 0; c < ND; ++c)
+            dd[i * rowLen + c] = dg[i][c];
+          lp.rhs[grow + i] = rhs[i];
+        }
+      }
+      __syncwarp();
+      /* copy-out: the ND rows of a node are contiguous in the CSR arrays */
+      const int last = min(row0 + 31, lh.nEnts - 1);
+      for (int r = row0; r <= last; ++r) {
+        const EntInfo er = s_ent[r];
+        const int n = ND * ND * (int)er.nnz;
+        const double* src = s_vals + ND * ND * (int)er.base;
+        double* dstg = lp.values + s_go[r];
+        for (int t = lane; t < n; t += 32)
+          dstg[t] = src[t];
+      }
+    }
+  } else {
   /* eager exchange: this tile holds rows of the shared tail */
   const bool pushing = lp.push.seg != nullptr && lh.hasShared != 0;
   if (!(mp.dbgSkip & 4)) {
@@ -1013,6 +1178,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
       }
     }
   }
+  } /* !mono */
   NW_PT_MARK(); /* 6: phases 2+3 */
   if (lp.diagOut) {
     /* NGPApplyCoeff::extract_diagonal (src/SolverAlgorithm.C:87-105):
@@ -1031,10 +1197,14 @@ __global__ void __launch_bounds__(THREADS, MINB) ls_tile_kernel(
       for (int w = 0; w < W; ++w) {
         const uint32_t hv = hp[w * 32];
         if (hv & kHeValid) {
-          double dg, off, rr[P::NR];
-          P::contrib(
-            he_side(hv), s_res, L.resStride, (int)he_edge(hv), dg, off, rr);
-          acc += dg;
+          if constexpr (IsMonoPolicy<P>::value) {
+            acc += P::diag00(he_side(hv), s_res, L.resStride, (int)he_edge(hv), o);
+          } else {
+            double dg, off, rr[P::NR];
+            P::contrib(
+              he_side(hv), s_res, L.resStride, (int)he_edge(hv), dg, off, rr);
+            acc += dg;
+          }
         }
       }
       lp.diagOut[h.node0 + i] += acc;
@@ -3915,6 +4085,9 @@ ls_tile_fits(const MeshPlanDev& mp, const LsPlanDev& lp, int policy)
   case 2:
     b = d3 ? ls_tile_smem<MomentumUvwP<3>>(mp, lp) : ls_tile_smem<MomentumUvwP<2>>(mp, lp);
     break;
+  case 3:
+    b = d3 ? ls_tile_smem<MomentumMonoP<3>>(mp, lp) : ls_tile_smem<MomentumMonoP<2>>(mp, lp);
+    break;
   default:
     b = d3 ? ls_tile_smem<WallDistP<3>>(mp, lp) : ls_tile_smem<WallDistP<2>>(mp, lp);
   }
@@ -3963,6 +4136,43 @@ launch_momentum_uvw_tile(
   return mp.ndim == 3
            ? launch_ls_tile<MomentumUvwP<3>, 3>(mp, lp, nc, ec, o, s, diagOut)
            : launch_ls_tile<MomentumUvwP<2>, 2>(mp, lp, nc, ec, o, s, diagOut);
+}
+
+namespace {
+constexpr int kMonoThreads = 512; /* one CTA per SM (145 KB of shared memory) */
+template <int ND>
+cudaError_t
+launch_momentum_mono_tile_t(
+  const MeshPlanDev& mp, const LsPlanDev& lpIn, const NodeComps& nc,
+  const EdgeComps& ec, const nw_momentum_opts& o, double* diagOut, cudaStream_t s)
+{
+  using P = MomentumMonoP<ND>;
+  LsPlanDev lp = lpIn;
+  lp.diagOut = diagOut;
+  lp.push = LsPushDev(); /* shared rows of a monolithic system go through load_complete */
+  const size_t bytes = ls_tile_smem<P>(mp, lp);
+  if (bytes > 227 * 1024)
+    return cudaErrorInvalidConfiguration;
+  cudaError_t e = set_smem(ls_tile_kernel<P, ND, 1, kMonoThreads>, bytes);
+  if (e != cudaSuccess)
+    return e;
+  if (mp.nTiles == 0)
+    return cudaSuccess;
+  ls_tile_kernel<P, ND, 1, kMonoThreads><<<mp.nTiles, kMonoThreads, bytes, s>>>(
+    with_pf(mp, ls_tile_kernel<P, ND, 1, kMonoThreads>, kMonoThreads, bytes), lp,
+    nc, ec, o);
+  return cudaGetLastError();
+}
+} // namespace
+
+cudaError_t
+launch_momentum_mono_tile(
+  const MeshPlanDev& mp, const LsPlanDev& lp, const NodeComps& nc,
+  const EdgeComps& ec, nw_momentum_opts o, double* diagOut, cudaStream_t s)
+{
+  return mp.ndim == 3
+           ? launch_momentum_mono_tile_t<3>(mp, lp, nc, ec, o, diagOut, s)
+           : launch_momentum_mono_tile_t<2>(mp, lp, nc, ec, o, diagOut, s);
 }
 
 cudaError_t

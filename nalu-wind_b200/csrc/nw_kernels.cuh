@@ -197,6 +197,12 @@ cudaError_t launch_scalar_pair_tile(
   const MeshPlanDev& mp, const LsPlanDev& lpA, double* valuesB, double* rhsB,
   const NodeComps& nc, const EdgeComps& ec, nw_scalar_opts oA,
   nw_scalar_opts oB, bool* launched, cudaStream_t s);
+/* monolithic ndim-dof momentum on the tile path: lp carries the node graph's
+ * plan with entGo / entRhsRow = value offset / local row of each node's first
+ * dof (nw_api.cu: build_mono_twin) */
+cudaError_t launch_momentum_mono_tile(
+  const MeshPlanDev& mp, const LsPlanDev& lp, const NodeComps& nc,
+  const EdgeComps& ec, nw_momentum_opts o, double* diagOut, cudaStream_t s);
 cudaError_t launch_momentum_uvw_tile(
   const MeshPlanDev& mp, const LsPlanDev& lp, const NodeComps& nc,
   const EdgeComps& ec, nw_momentum_opts o, double* diagOut, cudaStream_t s);

@@ -380,8 +380,15 @@ def test_reference_airfoil_mesh_2d(P, ctx):
     assert not bad, bad
 
 
-def test_monolithic_momentum_vs_oracle(P, ctx):
-    case = pu.Case(dims=(10, 9, 7))
+@pytest.mark.parametrize("periodic", [(False, False), (True, True)])
+@pytest.mark.parametrize("mode", ["segmented", "atomic"])
+def test_monolithic_momentum_vs_oracle(P, ctx, mode, periodic):
+    """HypreLinearSystem with numDof = ndim (sum_into of the full 6x6 block,
+    src/HypreLinearSystem.C:2059-2161).  Segmented: the tile kernel walks the
+    node graph's plan and writes three rows per node (no atomics); atomic:
+    the slot-map kernel.  Both against the oracle, entry by entry, incl. the
+    extract_diagonal side channel; on a periodic box too (aliased rows)."""
+    case = pu.Case(dims=(10, 9, 7), periodic=periodic)
     mesh = case.box.make_mesh(ctx, tile_nodes=64)
     pu.upload_state(P, mesh, case)
     omdot = case.oracle_mdot()
@@ -392,6 +399,9 @@ def test_monolithic_momentum_vs_oracle(P, ctx):
     ls = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE, 3)
     ls.buildEdgeToNodeGraph()
     ls.finalizeLinearSystem()
+    assert ls.uses_tile_path()
+    ls.set_scatter_mode(P.NW_SCATTER_SEGMENTED if mode == "segmented"
+                        else P.NW_SCATTER_ATOMIC)
     ls.zeroSystem()
     ls.assemble_momentum_edge("viscosity", diag_field="udiag_out", **pu.MOM_OPTS)
     vals, rhs = ls.values()
@@ -405,6 +415,26 @@ def test_monolithic_momentum_vs_oracle(P, ctx):
     # NGPApplyCoeff::extract_diagonal side channel
     got = mesh.download("udiag_out")
     assert pu.scaled_err(got, ud, np.abs(ud) + np.max(np.abs(ud)) * 1e-2) < 1
+    if mode == "segmented":
+        # deterministic: a second assembly gives the same bits
+        ls.zeroSystem()
+        ls.assemble_momentum_edge("viscosity", **pu.MOM_OPTS)
+        v2, r2 = ls.values()
+        assert np.array_equal(vals, v2) and np.array_equal(rhs, r2)
+    ls.close()
+    mesh.close()
+
+
+def test_monolithic_momentum_skipped_rows_take_the_atomic_path(P, ctx):
+    case = pu.Case(dims=(6, 5, 4))
+    mesh = case.box.make_mesh(ctx, tile_nodes=48)
+    ls = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE, 3)
+    ls.set_skipped_rows(np.array([3, 4, 5], dtype=np.int64))
+    ls.buildEdgeToNodeGraph()
+    ls.finalizeLinearSystem()
+    assert not ls.uses_tile_path()
+    ls.close()
+    mesh.close()
 
 
 @pytest.mark.parametrize("periodic", [(False, False), (True, True)])
