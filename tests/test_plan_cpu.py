@@ -171,6 +171,48 @@ def test_tile_plan_walkthrough_matches_oracle(kw):
         assert pu.scaled_err(got, ref, mag) < 1
 
 
+@pytest.mark.parametrize("kw", CASES, ids=_ids)
+def test_monolithic_system_shares_the_node_graph_plan(kw):
+    """The numDof = ndim system (src/HypreLinearSystem.C:2059-2161) takes the tile
+    path when its graph is the exact blow-up of the node graph (checked row by
+    row by the builder: ndim entries per node-row entry, same column order, the
+    ndim rows of a node contiguous); skipped rows keep the atomic kernel."""
+    P = pu.pkg()
+    case = pu.Case(**kw)
+    ctx = P.Context(-1)
+    mesh = case.box.make_mesh(ctx, tile_nodes=48)
+    one = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE, 1)
+    one.buildEdgeToNodeGraph()
+    one.finalizeLinearSystem()
+    mono = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE, 3)
+    mono.buildEdgeToNodeGraph()
+    mono.finalizeLinearSystem()
+    assert one.uses_tile_path() and mono.uses_tile_path()
+    # the blow-up the builder relies on, restated with the exported graphs
+    g1, g3 = one.graph(), mono.graph()
+    s1, s3 = one.sizes, mono.sizes
+    assert s3.num_rows_owned == 3 * s1.num_rows_owned
+    assert s3.num_rows_shared == 3 * s1.num_rows_shared
+    per3 = set(int(r) - s3.i_lower for r in g3["periodic_rows"])
+    rs1, rs3 = g1["row_start_owned"], g3["row_start_owned"]
+    for r in range(s1.num_rows_owned):
+        if 3 * r in per3:
+            continue  # periodic slave: a lone diagonal in both graphs
+        c1 = g1["cols"][rs1[r]:rs1[r + 1]]
+        for i in range(3):
+            c3 = g3["cols"][rs3[3 * r + i]:rs3[3 * r + i + 1]]
+            assert np.array_equal(c3, (3 * c1[:, None] + np.arange(3)).ravel())
+    skip = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE, 3)
+    lo = int(case.box.offsets[case.box.rank]) * 3
+    skip.set_skipped_rows(np.array([lo, lo + 1, lo + 2], dtype=np.int64))
+    skip.buildEdgeToNodeGraph()
+    skip.finalizeLinearSystem()
+    assert not skip.uses_tile_path()
+    for ls in (one, mono, skip):
+        ls.close()
+    mesh.close()
+
+
 def test_abi_library_exports_every_declared_symbol():
     """the C-ABI library loads without a GPU and exports every function that
     include/nalu_edge_b200.h declares; compute calls fail loudly (no fallback)"""
