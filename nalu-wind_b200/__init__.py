@@ -564,7 +564,7 @@ class LinearSystem:
 
     def set_eager_exchange(self, on=True):
         """The edge assembly is the last contribution to shared rows before
-        loadComplete: send them from the assembly call (boundary tiles first)."""
+        loadComplete: the assembly kernel stores them into the owners' windows."""
         _chk(lib().nw_linsys_set_eager_exchange(self.h, 1 if on else 0))
 
     def assemble_continuity_edge(self, dt=1.0, gamma1=1.0, noc_fac=1.0,

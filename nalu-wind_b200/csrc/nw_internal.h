@@ -88,7 +88,7 @@ struct Comm
 struct nw_p2p
 {
   bool ok = false;
-  int64_t winDoubles = 0; /* doubles per parity half of the window */
+  int64_t winDoubles = 0; /* doubles per window slot (three slots) */
   nw::DevBuf window;      /* [3][winDoubles] */
   nw::DevBuf flags;       /* unsigned long long [nranks]: epoch written by rank r */
   nw::DevBuf sync;        /* [0] block counter, [1] timeout/error word */
@@ -104,11 +104,13 @@ struct nw_p2p
   nw::DevBuf dUnionPeers;          /* int32 [nranks] */
   long long timeoutCycles = 40000000000ll; /* NW_P2P_TIMEOUT_S, default 20 s */
   unsigned* hErr = nullptr; /* pinned host copy of sync[1] (p2p_queue_error_read) */
-  /* asynchronous completion (NW_P2P_ASYNC=1): pushes run on the compute stream, pulls on
-   * `commStream` beside whatever the compute stream does next.  An object with
-   * a pull in flight carries its completion event; every later use of the
-   * object (and every later push: the window protocol needs pull(e) before
-   * push(e+1)) first makes the compute stream wait for it. */
+  /* asynchronous completion (default, NW_P2P_ASYNC=0 switches it off): pushes
+   * run on the compute stream (fused into the producing kernel, or a push
+   * kernel), pulls on `commStream` beside whatever the compute stream does
+   * next.  An object with a pull in flight carries its completion event; every
+   * later use of the object first makes the compute stream wait for it, and so
+   * does every later push kernel (p2p_next has the protocol; a kernel with a
+   * fused push waits for the pull two exchanges back only). */
   bool async = false;
   cudaStream_t commStream = nullptr;
   cudaEvent_t pushDone = nullptr; /* compute stream: producer + push issued */

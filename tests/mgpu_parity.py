@@ -194,7 +194,7 @@ def main():
     keep = np.array([r not in pr for r in range(gfull.num_rows_owned)])
     ref2 = float(np.sum(fr[0, :gfull.num_rows_owned][keep] ** 2))
     res["norm2_global"] = abs(n2[0] - ref2) / (1e-10 * ref2)
-    # eager exchange (boundary tiles first, push from the assembly call): bit-
+    # eager exchange (push fused into the assembly kernel): bit-
     # identical to the default order; a reader completes the exchange, a
     # writer is refused while the shared rows travel
     eager = {}
@@ -255,7 +255,7 @@ def main():
         mesh.nodal_grad_edge(phi, "g_" + phi)
         plain_order = mesh.download("g_" + phi).copy()
         del os.environ["NW_HALO_OVERLAP"]
-        mesh.nodal_grad_edge(phi, "g_" + phi)  # boundary tiles first
+        mesh.nodal_grad_edge(phi, "g_" + phi)  # push fused into the kernel
         got = mesh.download("g_" + phi).reshape(b.n_nodes, d1 * 3)
         eager["grad_%s_bit_identical" % phi] = bool(
             np.array_equal(plain_order.reshape(got.shape), got))
