@@ -595,6 +595,161 @@ emu_assemble(
   return 0;
 }
 
+/* Monolithic ndim-dof momentum system on the tile path (product:
+ * build_mono_twin in nw_api.cu + the MomentumMonoP branch of ls_tile_kernel):
+ * the emulator's linear system is the NODE graph (numDof 1, no skipped rows);
+ * the 3-dof graph is built here, row nd r + i of node row r.  values / rhs
+ * sized for the 3-dof graph (rhs: one column).  Node fields: x, u, dudx, visc,
+ * rho, mask as for emu_assemble kind 2. */
+int
+emu_assemble_mono(
+  void* h,
+  const double* const* nodeFields,
+  const int* nodeNcomp,
+  int nNodeFields,
+  const double* area,
+  const double* mdot,
+  const double* pecfac,
+  const void* opts,
+  double* values,
+  double* rhs)
+{
+  Emu* e = static_cast<Emu*>(h);
+  if (!e->hasLs || !e->lp.usable || e->g.numDof != 1) {
+    e->err = "emu_assemble_mono needs the node graph's plan (numDof 1)";
+    return 1;
+  }
+  const MeshPlan& mp = e->mp;
+  const Graph& g1 = e->g;
+  const LsPlan& lp = e->lp;
+  constexpr int ND = 3;
+  Graph g3;
+  try {
+    build_graph(mp, NW_LINSYS_HYPRE, ND, {}, g3);
+  } catch (const std::exception& ex) {
+    e->err = ex.what();
+    return 1;
+  }
+  auto row3 = [&](int64_t r1) {
+    return r1 < g1.numRowsOwned ? ND * r1
+                                : g3.numRowsOwned + ND * (r1 - g1.numRowsOwned);
+  };
+  const nw_momentum_opts& o = *static_cast<const nw_momentum_opts*>(opts);
+  std::vector<std::vector<double>> store;
+  std::vector<const double*> comps;
+  for (int f = 0; f < nNodeFields; ++f)
+    store.push_back(to_slots(mp, nodeFields[f], nodeNcomp[f]));
+  for (int f = 0; f < nNodeFields; ++f)
+    for (int c = 0; c < nodeNcomp[f]; ++c)
+      comps.push_back(store[f].data() + size_t(c) * mp.nSlots);
+  const std::vector<double> sArea = edge_to_slots(mp, area, ND);
+  const std::vector<double> sMdot = edge_to_slots(mp, mdot, 1);
+  std::vector<double> sPec;
+  if (pecfac)
+    sPec = edge_to_slots(mp, pecfac, 1);
+  const int64_t S = mp.nTileEdgeSlots;
+  const int64_t nnz = g3.nnzOwned + g3.nnzShared, rows = g3.numRowsLocal();
+  for (int64_t i = 0; i < nnz; ++i)
+    values[i] = NAN;
+  for (int64_t i = 0; i < rows; ++i)
+    rhs[i] = NAN;
+  const double invRelax = 1.0 / o.relax_fac;
+  for (int64_t t = 0; t < mp.nTiles; ++t) {
+    const TileHdr& hd = mp.tiles[t];
+    const LsTileHdr& lh = lp.tiles[t];
+    Staged st = stage(mp, hd, comps);
+    std::vector<MomResult<ND>> res(hd.nEdges);
+    std::vector<double> av(size_t(ND) * hd.nEdges);
+    for (int j = 0; j < hd.nEdges; ++j) {
+      const uint32_t v = mp.lr[hd.edge0 + j];
+      const int l = v & 0xffff, r = v >> 16;
+      double a[ND];
+      for (int d = 0; d < ND; ++d)
+        a[d] = av[size_t(d) * hd.nEdges + j] = sArea[size_t(d) * S + hd.edge0 + j];
+      MomNode<ND> L, R;
+      auto ld = [&](int i, MomNode<ND>& n) {
+        for (int d = 0; d < ND; ++d) {
+          n.x[d] = st(d, i);
+          n.u[d] = st(ND + d, i);
+        }
+        for (int d = 0; d < ND * ND; ++d)
+          n.g[d] = st(2 * ND + d, i);
+        n.mu = st(2 * ND + ND * ND, i);
+        n.rho = st(2 * ND + ND * ND + 1, i);
+        n.mask = st(2 * ND + ND * ND + 2, i);
+      };
+      ld(l, L);
+      ld(r, R);
+      const double pf = pecfac ? sPec[hd.edge0 + j] : 0.0;
+      momentum_edge<ND>(L, R, a, sMdot[hd.edge0 + j], pf, o, res[j]);
+    }
+    /* row walk: ND rows per node, blocks written in place (the device stages
+     * them and copies out; same values, same order of additions) */
+    bool bad = false;
+    std::vector<double> dg(size_t(ND) * ND * lh.nEnts, 0.0), rr(size_t(ND) * lh.nEnts, 0.0);
+    const bool okWalk = walk_ell(
+      lp.heEll.data() + lh.ellPtr, lp.sliceOff.data() + lh.slicePtr, lh.nEnts,
+      lh.ellLen, [&](int ent, uint32_t hv) {
+        const int j = he_edge(hv), side = he_side(hv), k = he_k(hv);
+        const EntInfo& ei = lp.entInfo[lh.entPtr + ent];
+        if (k >= ei.nnz || k == ei.diagK) {
+          bad = true;
+          return;
+        }
+        const MomResult<ND>& m = res[j];
+        const int64_t r3 = row3(lp.entRhsRow[lh.entPtr + ent]);
+        const int64_t rowLen = ND * (int64_t)ei.nnz;
+        if (g3.rowLen(r3) != rowLen) {
+          bad = true;
+          return;
+        }
+        const double sXX = side ? m.sRR : m.sLL, sXY = side ? m.sRL : m.sLR;
+        for (int i = 0; i < ND; ++i) {
+          rr[size_t(ent) * ND + i] += side ? m.flux[i] : -m.flux[i];
+          for (int c = 0; c < ND; ++c) {
+            const double ns = -m.viscIp * av[size_t(i) * hd.nEdges + j] *
+                              av[size_t(c) * hd.nEdges + j] * m.inv_axdx;
+            const double s_ = (i == c) ? 1.0 : 0.0;
+            dg[(size_t(ent) * ND + i) * ND + c] += s_ * sXX - ns * invRelax;
+            double off = s_ * sXY + ns;
+            double& dst = values[g3.rowPtr(r3 + i) + ND * k + c];
+            if (hv & kHeDup)
+              off += dst;
+            dst = off;
+          }
+        }
+      });
+    if (!okWalk || bad) {
+      e->err = "row ELL list malformed, slot out of row, or 3-dof row is not "
+               "the blow-up of the node row";
+      return 1;
+    }
+    for (int ent = 0; ent < lh.nEnts; ++ent) {
+      const EntInfo& ei = lp.entInfo[lh.entPtr + ent];
+      const int64_t r3 = row3(lp.entRhsRow[lh.entPtr + ent]);
+      for (int i = 0; i < ND; ++i) {
+        for (int c = 0; c < ND; ++c)
+          values[g3.rowPtr(r3 + i) + ND * ei.diagK + c] =
+            dg[(size_t(ent) * ND + i) * ND + c];
+        rhs[r3 + i] = rr[size_t(ent) * ND + i];
+      }
+    }
+  }
+  for (int32_t r1 : lp.uncoveredRows)
+    for (int i = 0; i < ND; ++i) {
+      const int64_t r = row3(r1) + i;
+      const int64_t a = g3.rowPtr(r), len = g3.rowLen(r);
+      for (int64_t k = 0; k < len; ++k)
+        values[a + k] = 0.0;
+      if (r < g3.numRowsOwned &&
+          std::binary_search(
+            g3.periodicRowsOwned.begin(), g3.periodicRowsOwned.end(), g3.iLower + r))
+        values[a] = 1.0;
+      rhs[r] = 0.0;
+    }
+  return 0;
+}
+
 /* nodal gradient through the node-keyed half-edge lists; grad AoS out */
 int
 emu_nodal_grad(

@@ -160,6 +160,20 @@ def test_tile_plan_walkthrough_matches_oracle(kw):
         assert pu.scaled_err(vals, ov, av) < 1
         assert pu.scaled_err(rhs, orhs, arhs) < 1
 
+    # monolithic 3-dof momentum (src/HypreLinearSystem.C:2059-2161) through the
+    # same node-graph plan: three rows per node, blocks formed in the row walk
+    g3 = case.oracle_graph(num_dof=3)
+    o3 = pu.oracle_momentum(case, g3, omdot, opec, uvw=False)
+    vals, rhs = emu.assemble_mono(pu.MOM_FIELDS, P.MomentumOpts(
+        mo["include_divu"], mo["alpha"], mo["alpha_upw"], mo["ho_upwind"],
+        mo["relax_fac"], 1, 1e-16, 0, P.peclet_fn("classic", 1.0), 1e-16, -1),
+        g3.nnz_owned + g3.nnz_shared, g3.num_rows_owned + g3.num_rows_shared,
+        mdot=omdot, pecfac=opec)
+    ov, orhs = o3.get()
+    av, arhs = o3.get_abs()
+    assert pu.scaled_err(vals, ov, av) < 1
+    assert pu.scaled_err(rhs, orhs.ravel(), arhs.ravel()) < 1
+
     f = case.fields
     for phi, d1 in (("pressure", 1), ("velocity", 3)):
         got = emu.nodal_grad(f[phi], d1)
