@@ -342,9 +342,9 @@ int nw_linsys_set_scatter_mode(nw_linsys* ls, int mode);
  * deterministic tile kernels: 1-dof and UVW systems whose reduction plan fits
  * the per-tile limits; the monolithic ndim-dof system (HypreLinearSystem with
  * numDof = ndim, sum_into of the full 2 ndim x 2 ndim block,
- * src/HypreLinearSystem.C:2059-2161) when it has no skipped rows -- it then
- * walks the node graph's plan and writes ndim rows per node.  0: the
- * warp-aggregated atomic kernels. */
+ * src/HypreLinearSystem.C:2059-2161) when its skipped rows cover whole nodes
+ * (as applyDirichletBCs lists them) -- it then walks the node graph's plan
+ * and writes ndim rows per node.  0: the warp-aggregated atomic kernels. */
 int nw_linsys_uses_tile_path(const nw_linsys* ls);
 
 /* Eager exchange of the shared rows (several ranks, peer-memory transport,

@@ -1340,25 +1340,47 @@ linsys_upload(nw_linsys* ls)
 /* Monolithic system on the tile path: find (or build) the node graph of this
  * mesh and check that the ndim-dof graph is its exact blow-up -- row nd r + i
  * of node row r has nd entries per node-row entry, in the same column order,
- * and the nd rows of a node are contiguous.  Anything else (skipped rows, a
- * graph the builder laid out differently) keeps the atomic kernel. */
+ * and the nd rows of a node are contiguous.  Anything else (skipped rows that
+ * do not cover whole nodes, a graph the builder laid out differently) keeps
+ * the atomic kernel. */
 static int
 build_mono_twin(nw_linsys* ls)
 {
   ls->monoOk = false;
   ls->twin.reset();
   const int nd = ls->numDof;
-  if (ls->kind != NW_LINSYS_HYPRE || nd < 2 || !ls->skipped.empty())
+  if (ls->kind != NW_LINSYS_HYPRE || nd < 2)
     return NW_OK;
+  /* skipped rows (Dirichlet nodes) become skipped NODE rows of the twin when
+   * they cover all dofs of their nodes -- sum_into tests the first dof's row
+   * id only (src/HypreLinearSystem.C:2095-2099), applyDirichletBCs lists all
+   * of them; a partial list keeps the atomic kernel */
+  std::vector<int64_t> key1;
+  {
+    std::vector<int64_t> sk = ls->skipped;
+    std::sort(sk.begin(), sk.end());
+    sk.erase(std::unique(sk.begin(), sk.end()), sk.end());
+    if (sk.size() % (size_t)nd != 0)
+      return NW_OK;
+    for (size_t i = 0; i < sk.size(); i += (size_t)nd) {
+      if (sk[i] % nd != 0)
+        return NW_OK;
+      for (int d = 1; d < nd; ++d)
+        if (sk[i + d] != sk[i] + d)
+          return NW_OK;
+      key1.push_back(sk[i] / nd);
+    }
+  }
   std::shared_ptr<nw_ls_shared> tw;
   for (auto& c : ls->mesh->lsCache)
-    if (c->numDof == 1 && c->skipped.empty())
+    if (c->numDof == 1 && c->skipped == key1)
       tw = c;
   if (!tw) {
     tw = std::make_shared<nw_ls_shared>();
-    NW_TRY(build_graph(ls->mesh->plan, NW_LINSYS_HYPRE, 1, {}, tw->g);
+    NW_TRY(build_graph(ls->mesh->plan, NW_LINSYS_HYPRE, 1, key1, tw->g);
            build_ls_plan(ls->mesh->plan, tw->g, tw->lp);)
     tw->numDof = 1;
+    tw->skipped = key1;
     ls->mesh->lsCache.push_back(tw);
   }
   const Graph& g1 = tw->g;

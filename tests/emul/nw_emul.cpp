@@ -597,7 +597,8 @@ emu_assemble(
 
 /* Monolithic ndim-dof momentum system on the tile path (product:
  * build_mono_twin in nw_api.cu + the MomentumMonoP branch of ls_tile_kernel):
- * the emulator's linear system is the NODE graph (numDof 1, no skipped rows);
+ * the emulator's linear system is the NODE graph (numDof 1, the skipped nodes
+ * of the 3-dof system as its skipped rows);
  * the 3-dof graph is built here, row nd r + i of node row r.  values / rhs
  * sized for the 3-dof graph (rhs: one column).  Node fields: x, u, dudx, visc,
  * rho, mask as for emu_assemble kind 2. */
@@ -611,6 +612,8 @@ emu_assemble_mono(
   const double* mdot,
   const double* pecfac,
   const void* opts,
+  const int64_t* skipped3, /* skipped rows of the 3-dof system (whole nodes) */
+  int64_t nSkipped3,
   double* values,
   double* rhs)
 {
@@ -625,7 +628,8 @@ emu_assemble_mono(
   constexpr int ND = 3;
   Graph g3;
   try {
-    build_graph(mp, NW_LINSYS_HYPRE, ND, {}, g3);
+    build_graph(
+      mp, NW_LINSYS_HYPRE, ND, std::vector<int64_t>(skipped3, skipped3 + nSkipped3), g3);
   } catch (const std::exception& ex) {
     e->err = ex.what();
     return 1;

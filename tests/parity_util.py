@@ -261,7 +261,8 @@ def emu_lib():
         L.emu_destroy.argtypes = [vp]
         L.emu_build_linsys.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int64]
         L.emu_check_plan.argtypes = [vp]
-        L.emu_assemble_mono.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
+        L.emu_assemble_mono.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp,
+                                        C.c_int64, vp, vp]
         L.emu_assemble.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, vp,
                                    vp, vp, vp]
         L.emu_nodal_grad.argtypes = [vp, C.c_int, vp, vp, vp, vp]
@@ -305,16 +306,18 @@ class Emu:
                       dtype=np.int32)
         return arrs, ptrs, nc
 
-    def assemble_mono(self, names, opts, nnz, rows, mdot, pecfac=None):
+    def assemble_mono(self, names, opts, nnz, rows, mdot, pecfac=None,
+                      skipped3=()):
         """monolithic 3-dof momentum through the node graph's plan"""
+        sk = np.ascontiguousarray(skipped3, dtype=np.int64)
         arrs, ptrs, nc = self._fields(names)
         vals = np.zeros(nnz)
         rhs = np.zeros(rows)
         area = np.ascontiguousarray(self.case.area)
         rc = emu_lib().emu_assemble_mono(
             self.h, C.cast(ptrs, C.c_void_p), _p(nc), len(arrs), _p(area),
-            _p(mdot), _p(pecfac), C.cast(C.byref(opts), C.c_void_p), _p(vals),
-            _p(rhs))
+            _p(mdot), _p(pecfac), C.cast(C.byref(opts), C.c_void_p), _p(sk),
+            sk.size, _p(vals), _p(rhs))
         assert rc == 0, emu_lib().emu_error(self.h).decode()
         return vals, rhs
 

@@ -425,15 +425,37 @@ def test_monolithic_momentum_vs_oracle(P, ctx, mode, periodic):
     mesh.close()
 
 
-def test_monolithic_momentum_skipped_rows_take_the_atomic_path(P, ctx):
-    case = pu.Case(dims=(6, 5, 4))
-    mesh = case.box.make_mesh(ctx, tile_nodes=48)
-    ls = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE, 3)
-    ls.set_skipped_rows(np.array([3, 4, 5], dtype=np.int64))
-    ls.buildEdgeToNodeGraph()
-    ls.finalizeLinearSystem()
-    assert not ls.uses_tile_path()
-    ls.close()
+def test_monolithic_momentum_with_dirichlet_nodes(P, ctx):
+    """Skipped rows that cover whole nodes (applyDirichletBCs lists every dof of
+    a Dirichlet node; sum_into tests the first dof's row id,
+    src/HypreLinearSystem.C:2095-2099): the monolithic system stays on the tile
+    path, the twin plan skips the node rows.  A list with only the first dof of
+    a node keeps the atomic kernel.  Both against the oracle."""
+    case = pu.Case(dims=(9, 8, 6))
+    mesh = case.box.make_mesh(ctx, tile_nodes=56)
+    pu.upload_state(P, mesh, case)
+    omdot = case.oracle_mdot()
+    opec = case.oracle_pecfac(orc.peclet("classic", 1.0))
+    mesh.upload("mass_flow_rate", omdot)
+    mesh.upload("peclet_factor", opec)
+    nodes = np.array([3, 40, 77, 150], dtype=np.int64)
+    for skipped, tile in (((3 * nodes[:, None] + np.arange(3)).ravel(), True),
+                          (3 * nodes[:1], False)):
+        ls = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE, 3)
+        ls.set_skipped_rows(skipped)
+        ls.buildEdgeToNodeGraph()
+        ls.finalizeLinearSystem()
+        assert ls.uses_tile_path() == tile
+        ls.zeroSystem()
+        ls.assemble_momentum_edge("viscosity", **pu.MOM_OPTS)
+        vals, rhs = ls.values()
+        g = case.oracle_graph(num_dof=3, skipped=skipped)
+        o = pu.oracle_momentum(case, g, omdot, opec, uvw=False)
+        ov, orhs = o.get()
+        av, arhs = o.get_abs()
+        assert pu.scaled_err(vals, ov, av) < 1
+        assert pu.scaled_err(rhs, orhs, arhs) < 1
+        ls.close()
     mesh.close()
 
 

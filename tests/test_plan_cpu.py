@@ -173,6 +173,24 @@ def test_tile_plan_walkthrough_matches_oracle(kw):
     av, arhs = o3.get_abs()
     assert pu.scaled_err(vals, ov, av) < 1
     assert pu.scaled_err(rhs, orhs.ravel(), arhs.ravel()) < 1
+    if not kw.get("periodic") and kw.get("nranks", 1) == 1:
+        # with Dirichlet nodes: the twin skips their node rows
+        nodes = np.array([2, 11, 30], dtype=np.int64)
+        sk3 = (3 * nodes[:, None] + np.arange(3)).ravel()
+        emu_s = pu.Emu(case, tile_nodes=40)
+        emu_s.build_linsys(0, 1, skipped=nodes)
+        g3s = case.oracle_graph(num_dof=3, skipped=sk3)
+        o3s = pu.oracle_momentum(case, g3s, omdot, opec, uvw=False)
+        vals, rhs = emu_s.assemble_mono(pu.MOM_FIELDS, P.MomentumOpts(
+            mo["include_divu"], mo["alpha"], mo["alpha_upw"], mo["ho_upwind"],
+            mo["relax_fac"], 1, 1e-16, 0, P.peclet_fn("classic", 1.0), 1e-16, -1),
+            g3s.nnz_owned + g3s.nnz_shared,
+            g3s.num_rows_owned + g3s.num_rows_shared, mdot=omdot, pecfac=opec,
+            skipped3=sk3)
+        ov, orhs = o3s.get()
+        av, arhs = o3s.get_abs()
+        assert pu.scaled_err(vals, ov, av) < 1
+        assert pu.scaled_err(rhs, orhs.ravel(), arhs.ravel()) < 1
 
     f = case.fields
     for phi, d1 in (("pressure", 1), ("velocity", 3)):
@@ -216,13 +234,22 @@ def test_monolithic_system_shares_the_node_graph_plan(kw):
         for i in range(3):
             c3 = g3["cols"][rs3[3 * r + i]:rs3[3 * r + i + 1]]
             assert np.array_equal(c3, (3 * c1[:, None] + np.arange(3)).ravel())
-    skip = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE, 3)
+    # Dirichlet nodes (all dofs of a node, as applyDirichletBCs lists them):
+    # skipped node rows of the twin -- still the tile path; a list that covers
+    # only the first dof of a node keeps the atomic kernel
     lo = int(case.box.offsets[case.box.rank]) * 3
-    skip.set_skipped_rows(np.array([lo, lo + 1, lo + 2], dtype=np.int64))
+    skip = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE, 3)
+    skip.set_skipped_rows(np.array([lo, lo + 1, lo + 2, lo + 9, lo + 10, lo + 11],
+                                   dtype=np.int64))
     skip.buildEdgeToNodeGraph()
     skip.finalizeLinearSystem()
-    assert not skip.uses_tile_path()
-    for ls in (one, mono, skip):
+    assert skip.uses_tile_path()
+    part = P.LinearSystem(mesh, P.NW_LINSYS_HYPRE, 3)
+    part.set_skipped_rows(np.array([lo], dtype=np.int64))
+    part.buildEdgeToNodeGraph()
+    part.finalizeLinearSystem()
+    assert not part.uses_tile_path()
+    for ls in (one, mono, skip, part):
         ls.close()
     mesh.close()
 
