@@ -203,6 +203,36 @@ def test_tile_plan_walkthrough_matches_oracle(kw):
         assert pu.scaled_err(got, ref, mag) < 1
 
 
+@pytest.mark.parametrize("kw", [CASES[2], CASES[6], CASES[4]], ids=_ids)
+def test_tile_cut_refinement_keeps_the_plan_valid(kw, monkeypatch):
+    """NW_TILE_REFINE=1 (opt-in greedy cut refinement after the RCB,
+    plan.cpp): tiles change, the plan invariants and the assembled systems do
+    not; the cut never grows."""
+    P = pu.pkg()
+    case = pu.Case(**kw)
+    stats = {}
+    for on in ("0", "1"):
+        monkeypatch.setenv("NW_TILE_REFINE", on)
+        emu = pu.Emu(case, tile_nodes=40)
+        emu.build_linsys(0, 1)
+        emu.check_plan()
+        g = case.oracle_graph()
+        nnz = g.nnz_owned + g.nnz_shared
+        rows = g.num_rows_owned + g.num_rows_shared
+        o = pu.oracle_continuity(case, g)
+        vals, rhs = emu.assemble(0, pu.CONT_FIELDS, P.ContinuityOpts(
+            pu.DT, pu.GAMMA1, 1.0, 1.0, 0.0), nnz, rows, 1)
+        ov, orhs = o.get()
+        av, arhs = o.get_abs()
+        assert pu.scaled_err(vals, ov, av) < 1
+        assert pu.scaled_err(rhs, orhs, arhs) < 1
+        ctx = P.Context(-1)
+        mesh = case.box.make_mesh(ctx, tile_nodes=40)
+        stats[on] = mesh.stats()
+        mesh.close()
+    assert stats["1"]["n_tile_edges"] <= stats["0"]["n_tile_edges"]
+
+
 @pytest.mark.parametrize("kw", CASES, ids=_ids)
 def test_monolithic_system_shares_the_node_graph_plan(kw):
     """The numDof = ndim system (src/HypreLinearSystem.C:2059-2161) takes the tile
