@@ -86,26 +86,31 @@ int nw_ctx_comm_init(nw_ctx* ctx, const void* unique_id, int nranks, int rank);
 /* Transport of the two halo exchanges (shared-row add of loadComplete,
  * shared-node sum of the nodal gradient).  nw_ctx_comm_init also tries to set
  * up a peer-memory mailbox over NVLink (CUDA IPC windows; NW_P2P=0 disables
- * it): an exchange is then a push kernel (pack + remote stores + release flag)
- * and a pull kernel (acquire wait + ordered add) instead of pack / ncclSend /
- * ncclRecv / unpack.  All ranks use the same transport (agreed collectively);
- * results are bit-identical between the two.  The mailbox's window reuse
- * assumes that all exchanges of a context involve the same neighbour ranks
- * (slab-type decompositions); otherwise run with NW_P2P=0. */
+ * it): the sender stores straight into the receiver's window -- from inside
+ * the producing kernel (gradient kernels; edge assemblies after
+ * nw_linsys_set_eager_exchange) or from a push kernel -- and a pull kernel
+ * publishes / waits for the epoch flags and does the ordered add, instead of
+ * pack / ncclSend / ncclRecv / unpack.  All ranks use the same transport
+ * (agreed collectively); results are bit-identical between the two.  Any
+ * decomposition works: every exchange signals and waits for the union of the
+ * neighbour ranks of all exchange objects of the context.  A neighbour that
+ * does not arrive within NW_P2P_TIMEOUT_S (default 20 s) makes the next call
+ * that returns data to the host fail with NW_ERR_COMM; nothing stale is ever
+ * added. */
 typedef enum {
   NW_TRANSPORT_NONE = 0,       /* single rank / structure not built yet */
   NW_TRANSPORT_NCCL = 1,
   NW_TRANSPORT_PEER_MEMORY = 2
 } nw_halo_transport;
 int nw_ctx_peer_memory(const nw_ctx* ctx); /* 1 if the mailbox is up */
-/* With NW_P2P_ASYNC=1 the receiving half of a peer-memory exchange (wait for
- * the neighbour + add) runs on a separate high-priority communication stream,
- * so that it overlaps whatever the caller enqueues next; every nw_* call that
- * touches the exchanged field / linear system again is ordered after it
- * automatically.  nw_ctx_join_comm orders the context's compute stream after
- * all exchanges issued so far (no host synchronisation) -- for callers that
- * hand raw device pointers (nw_field_device_view, nw_linsys_device_arrays) to
- * their own kernels on nw_ctx_stream.  A no-op in the default one-stream mode. */
+/* The receiving half of a peer-memory exchange (wait for the neighbours +
+ * add) runs on a separate high-priority communication stream, so that it
+ * overlaps whatever the caller enqueues next (NW_P2P_ASYNC=0: on the compute
+ * stream); every nw_* call that touches the exchanged field / linear system
+ * again -- nw_field_device_view and nw_linsys_device_arrays included -- is
+ * ordered after it automatically.  nw_ctx_join_comm orders the context's
+ * compute stream after ALL exchanges issued so far (no host
+ * synchronisation); nw_ctx_sync waits for both streams. */
 int nw_ctx_join_comm(nw_ctx* ctx);
 
 /* ------------------------------------------------------------------ */
