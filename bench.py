@@ -335,66 +335,134 @@ def oracle_mod():
     return orc
 
 
-def cpu_sample_case(P, orc, n):
-    """bounded sample of the workload for the CPU legs: a box of n_s^3 elements
-    with the same fields (same edges-per-node ratio); throughput is per edge"""
-    ns = min(n, 96)
-    box, fields = build_case(P, (ns, ns, ns), 1, 0)
-    g = orc.Graph(1, 0, box.n_nodes - 1)
-    g.add_edges(box.edges, box.hid)
-    g.finalize()
-    return ns, box, fields, g
+def host_threads():
+    """threads this process may use (the affinity mask, not the machine)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+class CpuSample:
+    """Bounded sample of the workload for the CPU legs: a box of n_s^3 elements
+    with the same fields (same edges-per-node ratio; throughput is per edge),
+    timed the two ways the reference uses host cores:
+
+      * rank per core -- how nalu-wind is run on CPUs: one MPI rank per core,
+        Kokkos Serial inside (plain adds, no atomics).  The box is cut into one
+        z-slab per thread with STK ownership semantics (the same partitioner the
+        GPU arm uses at N > 1); every thread sweeps its own part with the
+        serial oracle into its own owned + shared rows.  The MPI exchanges
+        (loadComplete, the shared-node gradient sum) are NOT timed, which
+        favours the CPU;
+      * OpenMP threads over one rank's edges with an atomic on every add (the
+        reference's Kokkos OpenMP build).
+    """
+
+    def __init__(self, P, orc, n, threads):
+        from concurrent.futures import ThreadPoolExecutor
+        self.orc = orc
+        self.ns = ns = min(n, 96)
+        self.threads = threads
+        self.nparts = max(1, min(threads, ns // 2))
+        self.parts = []
+        for r in range(self.nparts):
+            box, fields = build_case(P, (ns, ns, ns), self.nparts, r)
+            g = orc.Graph(1, int(box.offsets[r]), int(box.offsets[r + 1]) - 1)
+            g.add_edges(box.edges, box.hid)
+            g.finalize()
+            self.parts.append((box, fields, g))
+        self.n_edges = sum(p[0].n_edges for p in self.parts)
+        self.pool = ThreadPoolExecutor(self.nparts)
+        self._serial = None
+
+    def sweep_rank_per_core(self, sst):
+        """one sweep of every part, all parts at once; wall seconds (= the
+        slowest rank, as a solver step would see it)"""
+        self.orc.set_num_threads(1)
+        t0 = time.perf_counter()
+        list(self.pool.map(
+            lambda p: cpu_sweep(self.orc, p[0], p[1], p[2], sst), self.parts))
+        return time.perf_counter() - t0
+
+    def serial_case(self, P):
+        if self._serial is None:
+            box, fields = build_case(P, (self.ns,) * 3, 1, 0)
+            g = self.orc.Graph(1, 0, box.n_nodes - 1)
+            g.add_edges(box.edges, box.hid)
+            g.finalize()
+            self._serial = (box, fields, g)
+        return self._serial
+
+    def sweep_one_rank(self, P, sst, threads):
+        """the whole sample as one rank on `threads` OpenMP threads (atomics
+        when threads > 1); seconds"""
+        box, fields, g = self.serial_case(P)
+        self.orc.set_num_threads(threads)
+        t = cpu_sweep(self.orc, box, fields, g, sst)
+        self.orc.set_num_threads(1)
+        return t
+
+    def describe(self):
+        return ("%d^3-element box (%d edges) cut into %d z-slabs, one serial "
+                "oracle sweep per slab and host thread at once (the reference's "
+                "rank-per-core CPU deployment, Kokkos Serial; MPI exchanges not "
+                "timed)" % (self.ns, self.n_edges, self.nparts))
+
+    def extras(self, P, sst):
+        """the two other figures SURVEY 8(d) asks for: one thread, and all
+        threads under OpenMP with atomic adds"""
+        box = self.serial_case(P)[0]
+        self.sweep_one_rank(P, sst, self.threads)  # warm-up
+        ta = min(self.sweep_one_rank(P, sst, self.threads) for _ in range(2))
+        t1 = min(self.sweep_one_rank(P, sst, 1) for _ in range(2))
+        return {"single_thread_value": box.n_edges / t1 / 1e6,
+                "openmp_atomic_value": box.n_edges / ta / 1e6,
+                "openmp_atomic_threads": self.threads}
 
 
 def run_cpu_baseline(P, n, sst):
-    """CPU oracle timed on the host cores (all of them, then one) on a bounded
-    sample of the workload"""
+    """CPU oracle timed on the host cores on a bounded sample of the workload"""
     orc = oracle_mod()
-    threads = os.cpu_count() or 1
-    ns, box, fields, g = cpu_sample_case(P, orc, n)
-    orc.set_num_threads(threads)
-    cpu_sweep(orc, box, fields, g, sst)  # warm-up (page faults, caches)
+    cs = CpuSample(P, orc, n, host_threads())
+    cs.sweep_rank_per_core(sst)  # warm-up (page faults, caches)
     reps, tot = 0, 0.0
-    while tot < 8.0 and reps < 20:
-        tot += cpu_sweep(orc, box, fields, g, sst)
+    while tot < 8.0 and reps < 40:
+        tot += cs.sweep_rank_per_core(sst)
         reps += 1
-    orc.set_num_threads(1)
-    t1 = min(cpu_sweep(orc, box, fields, g, sst) for _ in range(2))
-    return {"value": box.n_edges * reps / tot / 1e6, "unit": "Medges/s",
-            "cores": threads, "kind": "port",
-            "single_thread_value": box.n_edges / t1 / 1e6,
-            "sample": "%d^3-element box (%d edges): %d full sweeps on %d threads "
-                      "in %.1f s, then 2 sweeps on one thread; "
-                      "oracle/edge_oracle.cpp (the reference cannot be compiled "
-                      "here: no Kokkos/STK/hypre)" % (
-                          ns, box.n_edges, reps, threads, tot)}
+    out = {"value": cs.n_edges * reps / tot / 1e6, "unit": "Medges/s",
+           "cores": cs.nparts, "kind": "port",
+           "sample": "%s: %d sweeps in %.1f s; oracle/edge_oracle.cpp (the "
+                     "reference cannot be compiled here: no Kokkos/STK/hypre)" % (
+                         cs.describe(), reps, tot)}
+    out.update(cs.extras(P, sst))
+    return out
 
 
 def main_reference(args):
     """--impl reference: the reference's CPU implementation of the path (here
     the oracle port: the reference itself needs Trilinos/Kokkos/hypre, absent)
-    on all host cores; rank 0 only."""
+    on all host cores, one rank per core; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     P = graft.load_package()
-    threads = os.cpu_count() or 1
     orc = oracle_mod()
-    ns, box, fields, g = cpu_sample_case(P, orc, args.n)
-    orc.set_num_threads(threads)
+    cs = CpuSample(P, orc, args.n, host_threads())
     for _ in range(max(args.warmup, 1)):
-        cpu_sweep(orc, box, fields, g, args.sst)
+        cs.sweep_rank_per_core(args.sst)
     t = 0.0
     for _ in range(args.steps):
-        t += cpu_sweep(orc, box, fields, g, args.sst)
-    val = box.n_edges * args.steps / t / 1e6
-    orc.set_num_threads(1)
-    t1 = cpu_sweep(orc, box, fields, g, args.sst)  # SURVEY 8(d): also single-thread
-    sample = ("each step = one full sweep over a %dx%dx%d-element box (%d edges) "
-              "-- a bounded sample of the workload, same fields / options as the "
-              "GPU arm; the metric is per edge" % (ns, ns, ns, box.n_edges))
+        t += cs.sweep_rank_per_core(args.sst)
+    val = cs.n_edges * args.steps / t / 1e6
+    sample = ("each step = one full sweep over a " + cs.describe() +
+              " -- a bounded sample of the workload, same fields / options as "
+              "the GPU arm; the metric is per edge")
     cfg = workload_config(args, args.gpus)
     cfg["reference_sample"] = sample
+    cpu = {"value": val, "unit": "Medges/s", "cores": cs.nparts, "kind": "port",
+           "sample": sample}
+    cpu.update(cs.extras(P, args.sst))
     line = {
         "impl": "reference", "metric": "edge_assembly_throughput",
         "value": val, "unit": "Medges/s", "n_gpus": args.gpus,
@@ -402,9 +470,7 @@ def main_reference(args):
         "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": cfg,
-        "cpu_baseline": {"value": val, "unit": "Medges/s", "cores": threads,
-                         "kind": "port", "single_thread_value": box.n_edges / t1 / 1e6,
-                         "sample": sample},
+        "cpu_baseline": cpu,
         "e2e": {"value": val, "unit": "Medges/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
