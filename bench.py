@@ -364,10 +364,13 @@ class CpuSample:
         self.orc = orc
         self.ns = ns = min(n, 96)
         self.threads = threads
-        self.nparts = max(1, min(threads, ns // 2))
+        self.nparts = max(1, min(threads, 64))
+        # slabs at least 6 element layers thick, so that a part is mostly
+        # interior like a production rank (throughput is per edge)
+        self.nz = nz = max(ns, 6 * self.nparts)
         self.parts = []
         for r in range(self.nparts):
-            box, fields = build_case(P, (ns, ns, ns), self.nparts, r)
+            box, fields = build_case(P, (ns, ns, nz), self.nparts, r)
             g = orc.Graph(1, int(box.offsets[r]), int(box.offsets[r + 1]) - 1)
             g.add_edges(box.edges, box.hid)
             g.finalize()
@@ -387,7 +390,7 @@ class CpuSample:
 
     def serial_case(self, P):
         if self._serial is None:
-            box, fields = build_case(P, (self.ns,) * 3, 1, 0)
+            box, fields = build_case(P, (self.ns, self.ns, self.nz), 1, 0)
             g = self.orc.Graph(1, 0, box.n_nodes - 1)
             g.add_edges(box.edges, box.hid)
             g.finalize()
@@ -404,10 +407,10 @@ class CpuSample:
         return t
 
     def describe(self):
-        return ("%d^3-element box (%d edges) cut into %d z-slabs, one serial "
+        return ("%dx%dx%d-element box (%d edges) cut into %d z-slabs, one serial "
                 "oracle sweep per slab and host thread at once (the reference's "
                 "rank-per-core CPU deployment, Kokkos Serial; MPI exchanges not "
-                "timed)" % (self.ns, self.n_edges, self.nparts))
+                "timed)" % (self.ns, self.ns, self.nz, self.n_edges, self.nparts))
 
     def extras(self, P, sst):
         """the two other figures SURVEY 8(d) asks for: one thread, and all
