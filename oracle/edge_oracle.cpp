@@ -60,6 +60,13 @@ van_leer(double dqm, double dqp, double eps)
 
 } // namespace
 
+/* the limiter by itself, for tests/test_option_matrix_cpu.py */
+extern "C" double
+orc_van_leer(double dqm, double dqp, double eps)
+{
+  return van_leer(dqm, dqp, eps);
+}
+
 /* ------------------------------------------------------------------ */
 /*  sinks                                                              */
 /* ------------------------------------------------------------------ */

@@ -43,6 +43,8 @@ typedef struct {
 } orc_peclet;
 
 double orc_peclet_eval(const orc_peclet* f, double pecnum);
+/* include/edge_kernels/EdgeKernelUtils.h:18-24 */
+double orc_van_leer(double dqm, double dqp, double eps);
 
 /* ---- linear-system sinks ("CoeffApplier", include/LinearSystem.h:44-74) ---- */
 typedef struct orc_applier orc_applier;
