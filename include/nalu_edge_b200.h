@@ -447,6 +447,14 @@ typedef struct {
   /* NGPApplyCoeff::extract_diagonal (src/SolverAlgorithm.C:87-105): nodal
    * field that accumulates lhs(i*ndim, i*ndim) of both end nodes, or -1 */
   int32_t diag_field;
+  /* solutionOptions_->realm_has_vof_ (src/edge_kernels/MomentumEdgeSolverAlg.C:
+   * 52-64, 88, 124-125, 174-192): the edge mass flow is mass_flow_rate +
+   * mass_vof_balanced_flow_rate (edge field of that name, 1 component, must be
+   * registered) and alphaUpw, the Peclet factor and the limited extrapolation
+   * are pushed to full upwinding across a density jump,
+   * 1 - erf(6 |rhoL - rhoR| / min(rhoL, rhoR)).  0: off (both fields alias
+   * mass_flow_rate in the reference, the factor is exactly 1). */
+  int32_t has_vof;
 } nw_momentum_opts;
 /* MomentumEdgeSolverAlg::execute (src/edge_kernels/MomentumEdgeSolverAlg.C:70-313)
  * into a NW_LINSYS_HYPRE_UVW system (x-x entries + ndim RHS,

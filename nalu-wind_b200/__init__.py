@@ -82,7 +82,7 @@ class MomentumOpts(C.Structure):
                 ("relax_fac", C.c_double), ("use_limiter", C.c_int32),
                 ("eps", C.c_double), ("fuse_peclet", C.c_int32),
                 ("pf", PecletFn), ("pec_eps", C.c_double),
-                ("diag_field", C.c_int32)]
+                ("diag_field", C.c_int32), ("has_vof", C.c_int32)]
 
 
 class MdotExtraOpts(C.Structure):
@@ -612,12 +612,13 @@ class LinearSystem:
                                alpha=0.0, alpha_upw=1.0, ho_upwind=1.0,
                                relax_fac=1.0, use_limiter=False, eps=1e-16,
                                fuse_peclet=False, pf=None, pec_eps=1e-16,
-                               diag_field=None):
+                               diag_field=None, has_vof=False):
         m = self.mesh
         o = MomentumOpts(include_divu, alpha, alpha_upw, ho_upwind, relax_fac,
                          1 if use_limiter else 0, eps, 1 if fuse_peclet else 0,
                          pf or peclet_fn(), pec_eps,
-                         m.field_id(diag_field) if diag_field else -1)
+                         m.field_id(diag_field) if diag_field else -1,
+                         1 if has_vof else 0)
         _chk(lib().nw_assemble_momentum_edge(
             self.h, m.field_id(viscosity), C.byref(o)))
 

@@ -450,7 +450,7 @@ struct MomResult
  * finite y, a != 0 -- so the specialised path gives the same bits as the
  * general one (at most the sign of an exact zero differs) with ~10 % fewer
  * FP64 instructions; momentum_edge_any picks the path (warp-uniform). */
-template <int ND, bool DEF>
+template <int ND, bool DEF, bool VOF = false>
 NW_HD void
 momentum_edge_t(
   const MomNode<ND>& L,
@@ -461,15 +461,16 @@ momentum_edge_t(
   const nw_momentum_opts& o,
   MomResult<ND>& res)
 {
+  static_assert(!(DEF && VOF), "the VOF branch changes alphaUpw per edge");
   const double eps = o.eps;
   const double includeDivU = o.include_divu;
   const double alpha = o.alpha;
-  const double alphaUpw = o.alpha_upw;
+  double alphaUpw = o.alpha_upw;
   const double hoUpwind = o.ho_upwind;
   const double invRelaxU = nw_rcp(o.relax_fac); /* warp-uniform */
   const double om_alpha = 1.0 - alpha;
-  const double om_alphaUpw = 1.0 - alphaUpw;
-  const double density_upwinding_factor = 1.0; /* has_vof == 0 */
+  double om_alphaUpw = 1.0 - alphaUpw;
+  double density_upwinding_factor = 1.0; /* has_vof == 0 */
 
   const double viscIp = 0.5 * (L.mu + R.mu);
 
@@ -512,7 +513,18 @@ momentum_edge_t(
     }
   }
 
-  const double om_pecfac = 1.0 - pecfac;
+  double om_pecfac = 1.0 - pecfac;
+  if (VOF) {
+    /* upwinding switch for multiphase cases: full upwinding across an
+     * interface (src/edge_kernels/MomentumEdgeSolverAlg.C:174-192) */
+    const double min_density = fmin(L.rho, R.rho);
+    const double density_differential = fabs(L.rho - R.rho) / min_density;
+    density_upwinding_factor = 1.0 - erf(6.0 * density_differential);
+    alphaUpw = density_upwinding_factor * alphaUpw + (1.0 - density_upwinding_factor);
+    om_alphaUpw = 1.0 - alphaUpw;
+    pecfac = 1.0 - density_upwinding_factor + density_upwinding_factor * pecfac;
+    om_pecfac = 1.0 - pecfac;
+  }
 
   double uIpL[ND], uIpR[ND];
 #pragma unroll
@@ -614,6 +626,23 @@ momentum_edge_t(
   res.sRR = sRR;
   res.viscIp = viscIp;
   res.inv_axdx = inv_axdx;
+}
+
+/* realm_has_vof_: mdot is massFlowRate + massVofBalancedFlowRate (summed by the
+ * caller of the kernel, MomentumEdgeSolverAlg.C:124-125), the upwinding factors
+ * depend on the density jump of the edge */
+template <int ND>
+NW_HD void
+momentum_edge_vof(
+  const MomNode<ND>& L,
+  const MomNode<ND>& R,
+  const double* av,
+  double mdot,
+  double pecfac,
+  const nw_momentum_opts& o,
+  MomResult<ND>& res)
+{
+  momentum_edge_t<ND, false, true>(L, R, av, mdot, pecfac, o, res);
 }
 
 template <int ND>

@@ -1978,6 +1978,19 @@ nw_assemble_momentum_edge(
     diagOut = const_cast<double*>(dp);
   }
   cudaStream_t s = mesh->ctx->stream;
+  if (opts->has_vof) {
+    /* mdot = massFlowRate + has_vof * massVofBalancedFlowRate
+     * (src/edge_kernels/MomentumEdgeSolverAlg.C:124-125), summed once per
+     * assembly over the tile-edge slots; the VOF kernels read the sum */
+    const double* mv = nullptr;
+    if ((rc = bind(mesh, "mass_vof_balanced_flow_rate", NW_EDGE, 1, &mv)))
+      return rc;
+    const int64_t n = mesh->plan.nTileEdgeSlots;
+    if (mesh->dVofMdot.bytes < sizeof(double) * (size_t)n)
+      NW_CUDA(mesh->dVofMdot.alloc(sizeof(double) * (size_t)n));
+    NW_CUDA(launch_edge_sum(ec.mdot, mv, n, mesh->dVofMdot.as<double>(), s));
+    ec.mdot = mesh->dVofMdot.as<double>();
+  }
   if (uvw) {
     /* extract_diagonal rides on the tile kernel (node-keyed pass) */
     if (use_tile_path(ls, false, &rc, 2)) {

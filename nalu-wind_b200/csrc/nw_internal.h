@@ -227,6 +227,9 @@ struct nw_mesh
   nw::DevBuf dTiles, dHalo, dHaloBlock, dLr, dHeNode, dWarpNode, dPrimary, dNodeOfSlot,
     dTileEdgeSrc, dPrimarySlot, dSecondSlot;
   nw::DevBuf scratch; /* staging for field upload / download */
+  /* mass_flow_rate + mass_vof_balanced_flow_rate over the tile-edge slots: the
+   * mdot stream of the VOF momentum kernels (nw_momentum_opts::has_vof) */
+  nw::DevBuf dVofMdot;
   std::vector<std::unique_ptr<nw_field_t>> fields;
   std::map<std::string, int> fieldByName;
   nw_node_halo halo;

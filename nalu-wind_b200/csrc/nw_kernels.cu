@@ -663,6 +663,14 @@ struct MomentumUvwP
     const Node& L, const Node& R, const double* av, double mdot, double pecfac,
     const Opts& o, double* res)
   {
+    compute_n_t<false>(L, R, av, mdot, pecfac, o, res);
+  }
+  /* VOF: the realm_has_vof_ branch of the physics (MomentumUvwVofP) */
+  template <bool VOF>
+  __device__ __forceinline__ static void compute_n_t(
+    const Node& L, const Node& R, const double* av, double mdot, double pecfac,
+    const Opts& o, double* res)
+  {
     if (o.fuse_peclet) {
       /* MomentumEdgePecletAlg fused (src/edge_kernels/MomentumEdgePecletAlg.C:74-101) */
       PecNode<ND> pl, pr;
@@ -680,7 +688,10 @@ struct MomentumUvwP
       pecfac = peclet_eval(o.pf, peclet_number<ND>(pl, pr, o.pec_eps));
     }
     MomResult<ND> m;
-    momentum_edge<ND>(L, R, av, mdot, pecfac, o, m);
+    if (VOF)
+      momentum_edge_vof<ND>(L, R, av, mdot, pecfac, o, m);
+    else
+      momentum_edge<ND>(L, R, av, mdot, pecfac, o, m);
     /* HypreUVWLinSysCoeffApplier keeps only the x-x entries
      * (src/HypreUVWLinearSystem.C:738) */
     momentum_block_entry<ND>(
@@ -764,6 +775,13 @@ struct MomentumMonoP : MomentumUvwP<ND>
     const Node& L, const Node& R, const double* av, double mdot, double pecfac,
     const Opts& o, double* res)
   {
+    compute_n_t<false>(L, R, av, mdot, pecfac, o, res);
+  }
+  template <bool VOF>
+  __device__ __forceinline__ static void compute_n_t(
+    const Node& L, const Node& R, const double* av, double mdot, double pecfac,
+    const Opts& o, double* res)
+  {
     if (o.fuse_peclet) {
       PecNode<ND> pl, pr;
 #pragma unroll
@@ -780,7 +798,10 @@ struct MomentumMonoP : MomentumUvwP<ND>
       pecfac = peclet_eval(o.pf, peclet_number<ND>(pl, pr, o.pec_eps));
     }
     MomResult<ND> m;
-    momentum_edge<ND>(L, R, av, mdot, pecfac, o, m);
+    if (VOF)
+      momentum_edge_vof<ND>(L, R, av, mdot, pecfac, o, m);
+    else
+      momentum_edge<ND>(L, R, av, mdot, pecfac, o, m);
     res[0] = m.sLL;
     res[1] = m.sLR;
     res[2] = m.sRL;
@@ -819,6 +840,63 @@ struct IsMonoPolicy
 };
 template <int ND>
 struct IsMonoPolicy<MomentumMonoP<ND>>
+{
+  static constexpr bool value = true;
+};
+
+/* realm_has_vof_ (src/edge_kernels/MomentumEdgeSolverAlg.C:88, 174-192): the
+ * same kernels with the VOF branch of the physics compiled in, as policies of
+ * their own so that the kernels of every other deck stay as they are.  The
+ * edge stream they read as mdot is mass_flow_rate +
+ * mass_vof_balanced_flow_rate (edge_sum_kernel, nw_assemble_momentum_edge). */
+template <int ND>
+struct MomentumUvwVofP : MomentumUvwP<ND>
+{
+  using Base = MomentumUvwP<ND>;
+  using Opts = nw_momentum_opts;
+  using Node = MomNode<ND>;
+  __device__ __forceinline__ static void compute_n(
+    const Node& L, const Node& R, const double* av, double mdot, double pecfac,
+    const Opts& o, double* res)
+  {
+    Base::template compute_n_t<true>(L, R, av, mdot, pecfac, o, res);
+  }
+  template <class LD>
+  __device__ __forceinline__ static void compute(
+    const LD& ld, int l, int r, const double* av, double mdot, double pecfac,
+    const Opts& o, double* res)
+  {
+    Node L, R;
+    Base::load(ld, l, L);
+    Base::load(ld, r, R);
+    compute_n(L, R, av, mdot, pecfac, o, res);
+  }
+};
+template <int ND>
+struct MomentumMonoVofP : MomentumMonoP<ND>
+{
+  using Base = MomentumMonoP<ND>;
+  using Opts = nw_momentum_opts;
+  using Node = MomNode<ND>;
+  __device__ __forceinline__ static void compute_n(
+    const Node& L, const Node& R, const double* av, double mdot, double pecfac,
+    const Opts& o, double* res)
+  {
+    Base::template compute_n_t<true>(L, R, av, mdot, pecfac, o, res);
+  }
+  template <class LD>
+  __device__ __forceinline__ static void compute(
+    const LD& ld, int l, int r, const double* av, double mdot, double pecfac,
+    const Opts& o, double* res)
+  {
+    Node L, R;
+    Base::load(ld, l, L);
+    Base::load(ld, r, R);
+    compute_n(L, R, av, mdot, pecfac, o, res);
+  }
+};
+template <int ND>
+struct IsMonoPolicy<MomentumMonoVofP<ND>>
 {
   static constexpr bool value = true;
 };
@@ -1925,7 +2003,7 @@ __global__ void __launch_bounds__(kTileThreads) ls_atomic_kernel(
 }
 
 /* monolithic momentum: full 2ND x 2ND block through the slot map */
-template <int ND>
+template <int ND, bool VOF = false>
 __global__ void __launch_bounds__(kTileThreads) momentum_mono_atomic_kernel(
   const MeshPlanDev mp,
   const int32_t* __restrict__ slots,
@@ -1973,7 +2051,10 @@ __global__ void __launch_bounds__(kTileThreads) momentum_mono_atomic_kernel(
       pecfac = peclet_eval(o.pf, peclet_number<ND>(pl, pr, o.pec_eps));
     }
     MomResult<ND> m;
-    momentum_edge<ND>(L, R, av, mdot, pecfac, o, m);
+    if (VOF)
+      momentum_edge_vof<ND>(L, R, av, mdot, pecfac, o, m);
+    else
+      momentum_edge<ND>(L, R, av, mdot, pecfac, o, m);
     const int32_t* sl = slots + es * (NB * NB);
     const int32_t* rr = rhsRows + es * NB;
 #pragma unroll
@@ -3761,6 +3842,33 @@ launch_ls_tile(
   return cudaGetLastError();
 }
 
+/* the tile kernel only (no comparison variants): the VOF policies */
+template <class P, int ND>
+cudaError_t
+launch_ls_tile_plain(
+  const MeshPlanDev& mp,
+  const LsPlanDev& lpIn,
+  const NodeComps& nc,
+  const EdgeComps& ec,
+  const typename P::Opts& o,
+  cudaStream_t s,
+  double* diagOut)
+{
+  LsPlanDev lp = lpIn;
+  lp.diagOut = diagOut;
+  const size_t bytes = ls_tile_smem<P>(mp, lp);
+  if (bytes > 227 * 1024)
+    return cudaErrorInvalidConfiguration;
+  cudaError_t e = set_smem(ls_tile_kernel<P, ND>, bytes);
+  if (e != cudaSuccess)
+    return e;
+  if (mp.nTiles == 0)
+    return cudaSuccess;
+  ls_tile_kernel<P, ND><<<mp.nTiles, kTileThreads, bytes, s>>>(
+    with_pf(mp, ls_tile_kernel<P, ND>, kTileThreads, bytes), lp, nc, ec, o);
+  return cudaGetLastError();
+}
+
 template <class P, int ND>
 cudaError_t
 launch_ls_stream(
@@ -4133,6 +4241,10 @@ launch_momentum_uvw_tile(
   double* diagOut,
   cudaStream_t s)
 {
+  if (o.has_vof)
+    return mp.ndim == 3
+             ? launch_ls_tile_plain<MomentumUvwVofP<3>, 3>(mp, lp, nc, ec, o, s, diagOut)
+             : launch_ls_tile_plain<MomentumUvwVofP<2>, 2>(mp, lp, nc, ec, o, s, diagOut);
   return mp.ndim == 3
            ? launch_ls_tile<MomentumUvwP<3>, 3>(mp, lp, nc, ec, o, s, diagOut)
            : launch_ls_tile<MomentumUvwP<2>, 2>(mp, lp, nc, ec, o, s, diagOut);
@@ -4140,13 +4252,12 @@ launch_momentum_uvw_tile(
 
 namespace {
 constexpr int kMonoThreads = 512; /* one CTA per SM (145 KB of shared memory) */
-template <int ND>
+template <int ND, class P = MomentumMonoP<ND>>
 cudaError_t
 launch_momentum_mono_tile_t(
   const MeshPlanDev& mp, const LsPlanDev& lpIn, const NodeComps& nc,
   const EdgeComps& ec, const nw_momentum_opts& o, double* diagOut, cudaStream_t s)
 {
-  using P = MomentumMonoP<ND>;
   LsPlanDev lp = lpIn;
   lp.diagOut = diagOut;
   lp.push = LsPushDev(); /* shared rows of a monolithic system go through load_complete */
@@ -4170,6 +4281,10 @@ launch_momentum_mono_tile(
   const MeshPlanDev& mp, const LsPlanDev& lp, const NodeComps& nc,
   const EdgeComps& ec, nw_momentum_opts o, double* diagOut, cudaStream_t s)
 {
+  if (o.has_vof)
+    return mp.ndim == 3
+             ? launch_momentum_mono_tile_t<3, MomentumMonoVofP<3>>(mp, lp, nc, ec, o, diagOut, s)
+             : launch_momentum_mono_tile_t<2, MomentumMonoVofP<2>>(mp, lp, nc, ec, o, diagOut, s);
   return mp.ndim == 3
            ? launch_momentum_mono_tile_t<3>(mp, lp, nc, ec, o, diagOut, s)
            : launch_momentum_mono_tile_t<2>(mp, lp, nc, ec, o, diagOut, s);
@@ -4216,6 +4331,10 @@ launch_momentum_uvw_atomic(
   double* diagOut,
   cudaStream_t s)
 {
+  if (o.has_vof)
+    return mp.ndim == 3
+             ? launch_ls_atomic<MomentumUvwVofP<3>, 3>(mp, lp, am, nc, ec, o, diagOut, s)
+             : launch_ls_atomic<MomentumUvwVofP<2>, 2>(mp, lp, am, nc, ec, o, diagOut, s);
   return mp.ndim == 3
            ? launch_ls_atomic<MomentumUvwP<3>, 3>(mp, lp, am, nc, ec, o, diagOut, s)
            : launch_ls_atomic<MomentumUvwP<2>, 2>(mp, lp, am, nc, ec, o, diagOut, s);
@@ -4234,6 +4353,15 @@ launch_momentum_mono_atomic(
   double* diagOut,
   cudaStream_t s)
 {
+  if (o.has_vof) {
+    if (mp.ndim == 3)
+      momentum_mono_atomic_kernel<3, true><<<mp.nTiles, kTileThreads, 0, s>>>(
+        mp, slots, rhsRows, values, rhs, nc, ec, o, diagOut);
+    else
+      momentum_mono_atomic_kernel<2, true><<<mp.nTiles, kTileThreads, 0, s>>>(
+        mp, slots, rhsRows, values, rhs, nc, ec, o, diagOut);
+    return cudaGetLastError();
+  }
   if (mp.ndim == 3)
     momentum_mono_atomic_kernel<3><<<mp.nTiles, kTileThreads, 0, s>>>(
       mp, slots, rhsRows, values, rhs, nc, ec, o, diagOut);
@@ -4300,6 +4428,29 @@ launch_edge_scatter(
     return cudaSuccess;
   edge_scatter_kernel<<<blocks_for(nEdges, 256), 256, 0, s>>>(
     srcSoa, ncomp, primarySlotOfEdge, nEdges, slotStride, dstAos);
+  return cudaGetLastError();
+}
+
+/* out[i] = a[i] + b[i]: the VOF momentum kernels' edge mass flow,
+ * massFlowRate + has_vof * massVofBalancedFlowRate with has_vof == 1.0
+ * (src/edge_kernels/MomentumEdgeSolverAlg.C:124-125; 1.0 * b is b exactly) */
+__global__ void
+edge_sum_kernel(
+  const double* __restrict__ a, const double* __restrict__ b, int64_t n,
+  double* __restrict__ out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = a[i] + b[i];
+}
+
+cudaError_t
+launch_edge_sum(
+  const double* a, const double* b, int64_t n, double* out, cudaStream_t s)
+{
+  if (n == 0)
+    return cudaSuccess;
+  edge_sum_kernel<<<blocks_for(n, 256), 256, 0, s>>>(a, b, n, out);
   return cudaGetLastError();
 }
 

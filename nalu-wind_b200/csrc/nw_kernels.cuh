@@ -243,6 +243,8 @@ cudaError_t launch_edge_scatter(
   const double* srcSoa, int ncomp, const int32_t* primarySlotOfEdge,
   int64_t nEdges, int64_t slotStride, double* dstAos, cudaStream_t s);
 cudaError_t launch_fill(double* p, int64_t n, double v, cudaStream_t s);
+cudaError_t launch_edge_sum(
+  const double* a, const double* b, int64_t n, double* out, cudaStream_t s);
 /* rows no tile writes: values zero (periodic rows: diagonal 1), rhs zero */
 cudaError_t launch_row_init(
   const int32_t* rows, int nRows, const int64_t* rowPtr /* [R+1] */,

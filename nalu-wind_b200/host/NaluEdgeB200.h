@@ -58,6 +58,10 @@ struct SolutionOptions
   double includeDivU_ = 0.0;
   bool mdotInterpRhoUTogether_ = true;
   bool solveIncompressibleContinuity_ = false;
+  /* SolutionOptions::realm_has_vof_: MomentumEdgeSolverAlg then reads the edge
+   * field "mass_vof_balanced_flow_rate" as well
+   * (src/edge_kernels/MomentumEdgeSolverAlg.C:52-64, 88) */
+  bool realm_has_vof_ = false;
   std::map<std::string, double> hybridMap_, alphaMap_, alphaUpwMap_, upwMap_,
     relaxFactorMap_, tanhTransMap_, tanhWidthMap_;
   std::map<std::string, bool> nocMap_, limiterMap_;
@@ -501,6 +505,7 @@ public:
     o.pf = realm_.peclet_function(dof);
     o.pec_eps = 1.0e-16;
     o.diag_field = diagField_.empty() ? -1 : realm_.field_ordinal(diagField_);
+    o.has_vof = realm_.solutionOptions_.realm_has_vof_ ? 1 : 0;
     nw_check(nw_assemble_momentum_edge(
       eqSystem_->linsys_->handle(), realm_.field_ordinal(viscName_), &o));
   }

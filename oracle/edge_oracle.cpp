@@ -2018,8 +2018,11 @@ orc_scalar_edge(
 /*  MomentumEdgeSolverAlg                                              */
 /* ------------------------------------------------------------------ */
 
-extern "C" void
-orc_momentum_edge(
+/* mass_vof_f: massVofBalancedFlowRate; the reference aliases it to
+ * massFlowRate when realm_has_vof_ is off (:52-56) and multiplies it by
+ * has_vof = 0.0 -- here a null pointer. */
+static void
+momentum_edge_impl(
   int ndim,
   int64_t n_edges,
   const int32_t* edge_nodes,
@@ -2031,25 +2034,24 @@ orc_momentum_edge(
   const double* node_mask,
   const double* edge_area,
   const double* mdot_f,
+  const double* mass_vof_f,
   const double* pecfac_f,
   const orc_momentum_opts* o,
   orc_applier* sink,
   double* udiag_accum)
 {
-  /* src/edge_kernels/MomentumEdgeSolverAlg.C:70-88, 105-312 with
-   * has_vof == 0 (mdot == massFlowRate, density_upwinding_factor == 1). */
+  /* src/edge_kernels/MomentumEdgeSolverAlg.C:70-88, 105-312 */
   const double eps = o->eps;
   const double includeDivU = o->include_divu;
   const double alpha = o->alpha;
-  const double alphaUpw = o->alpha_upw;
+  const double alphaUpw_input = o->alpha_upw;
   const double hoUpwind = o->ho_upwind;
   const double relaxFacU = o->relax_fac;
   const bool useLimiter = o->use_limiter != 0;
   const double om_alpha = 1.0 - alpha;
-  const double om_alphaUpw = 1.0 - alphaUpw;
-  const double density_upwinding_factor = 1.0;
+  const double om_alphaUpw_input = 1.0 - alphaUpw_input;
+  const double has_vof = mass_vof_f ? 1.0 : 0.0; /* (double)realm_has_vof_, :88 */
   const int n = 2 * ndim;
-  (void)density; /* only read by the VOF branch (:178-192), has_vof == 0 */
 
   ORC_EDGE_LOOP
   for (int64_t e = 0; e < n_edges; ++e) {
@@ -2073,7 +2075,13 @@ orc_momentum_edge(
     const double* gL = &dudx[nL * ndim * ndim];
     const double* gR = &dudx[nR * ndim * ndim];
 
-    const double mdot = mdot_f[e];
+    /* :110-111: per-edge copies the VOF branch modifies */
+    double alphaUpw = alphaUpw_input;
+    double om_alphaUpw = om_alphaUpw_input;
+    /* :124-125 */
+    const double mdot =
+      mdot_f[e] + has_vof * (mass_vof_f ? mass_vof_f[e] : mdot_f[e]);
+    const double densityL = density[nL], densityR = density[nR];
     const double viscosityL = viscosity[nL], viscosityR = viscosity[nR];
     const double viscIp = 0.5 * (viscosityL + viscosityR);
 
@@ -2109,8 +2117,23 @@ orc_momentum_edge(
       }
     }
 
-    const double pecfac = pecfac_f[e];
-    const double om_pecfac = 1.0 - pecfac;
+    /* :174-192 upwinding switch for multiphase cases */
+    double pecfac = pecfac_f[e];
+    double om_pecfac = 1.0 - pecfac;
+    double density_upwinding_factor = 1.0;
+    if (has_vof > 0.5) {
+      const double min_density = std::fmin(densityL, densityR);
+      const double density_differential =
+        std::fabs(densityL - densityR) / min_density;
+      density_upwinding_factor = 1.0 - std::erf(6.0 * density_differential);
+
+      alphaUpw = density_upwinding_factor * alphaUpw +
+                 (1.0 - density_upwinding_factor);
+      om_alphaUpw = 1.0 - alphaUpw;
+      pecfac =
+        1.0 - density_upwinding_factor + density_upwinding_factor * pecfac;
+      om_pecfac = 1.0 - pecfac;
+    }
 
     double uIpL[kMaxDim], uIpR[kMaxDim];
     for (int d = 0; d < ndim; ++d) {
@@ -2205,4 +2228,31 @@ orc_momentum_edge(
     sink->apply(2, nodes, rhs, lhs, n);
 #undef LHS
   }
+}
+
+extern "C" void
+orc_momentum_edge(
+  int ndim, int64_t n_edges, const int32_t* edge_nodes, const double* coords,
+  const double* vel, const double* dudx, const double* viscosity,
+  const double* density, const double* node_mask, const double* edge_area,
+  const double* mdot_f, const double* pecfac_f, const orc_momentum_opts* o,
+  orc_applier* sink, double* udiag_accum)
+{
+  momentum_edge_impl(
+    ndim, n_edges, edge_nodes, coords, vel, dudx, viscosity, density, node_mask,
+    edge_area, mdot_f, nullptr, pecfac_f, o, sink, udiag_accum);
+}
+
+/* realm_has_vof_ on: mass_vof = the mass_vof_balanced_flow_rate edge field */
+extern "C" void
+orc_momentum_edge_vof(
+  int ndim, int64_t n_edges, const int32_t* edge_nodes, const double* coords,
+  const double* vel, const double* dudx, const double* viscosity,
+  const double* density, const double* node_mask, const double* edge_area,
+  const double* mdot_f, const double* mass_vof, const double* pecfac_f,
+  const orc_momentum_opts* o, orc_applier* sink, double* udiag_accum)
+{
+  momentum_edge_impl(
+    ndim, n_edges, edge_nodes, coords, vel, dudx, viscosity, density, node_mask,
+    edge_area, mdot_f, mass_vof, pecfac_f, o, sink, udiag_accum);
 }

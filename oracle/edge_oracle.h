@@ -264,7 +264,8 @@ typedef struct {
   int use_limiter;
   double eps; /* 1e-16 */
 } orc_momentum_opts;
-/* src/edge_kernels/MomentumEdgeSolverAlg.C:105-312 (has_vof = 0).
+/* src/edge_kernels/MomentumEdgeSolverAlg.C:105-312 (has_vof = 0;
+ * orc_momentum_edge_vof below: has_vof = 1).
  * udiag_accum (nullable): NGPApplyCoeff::extract_diagonal,
  * src/SolverAlgorithm.C:87-105, adds lhs(i*ndim,i*ndim) per end node. */
 void orc_momentum_edge(
@@ -273,6 +274,14 @@ void orc_momentum_edge(
   const double* density, const double* node_mask, const double* edge_area,
   const double* mdot, const double* pecfac, const orc_momentum_opts* o,
   orc_applier* sink, double* udiag_accum);
+/* the same with solutionOptions_->realm_has_vof_ set (:88, 124-125, 174-192):
+ * mdot + mass_vof_balanced_flow_rate, density-jump upwinding factors */
+void orc_momentum_edge_vof(
+  int ndim, int64_t n_edges, const int32_t* edge_nodes, const double* coords,
+  const double* velocity, const double* dudx, const double* viscosity,
+  const double* density, const double* node_mask, const double* edge_area,
+  const double* mdot, const double* mass_vof_balanced, const double* pecfac,
+  const orc_momentum_opts* o, orc_applier* sink, double* udiag_accum);
 
 #ifdef __cplusplus
 }

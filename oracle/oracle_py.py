@@ -341,7 +341,10 @@ def scalar_edge(ndim, edge_nodes, coords, vrtm, q, dqdx, rho, dflux, area,
 def momentum_edge(ndim, edge_nodes, coords, vel, dudx, visc, rho, mask, area,
                   mdot, pecfac, sink, include_divu=0.0, alpha=0.0,
                   alpha_upw=1.0, ho_upwind=1.0, relax_fac=1.0,
-                  use_limiter=False, eps=1e-16, udiag_accum=None):
+                  use_limiter=False, eps=1e-16, udiag_accum=None,
+                  mass_vof=None):
+    """mass_vof: the mass_vof_balanced_flow_rate edge field; given = the
+    realm_has_vof_ branch (MomentumEdgeSolverAlg.C:88, 124-125, 174-192)"""
     en, pe = _i32(edge_nodes)
     arrs = [_f(x) for x in (coords, vel, dudx, visc, rho, mask, area, mdot,
                             pecfac)]
@@ -351,6 +354,15 @@ def momentum_edge(ndim, edge_nodes, coords, vel, dudx, visc, rho, mask, area,
     if udiag_accum is not None:
         assert udiag_accum.dtype == np.float64 and udiag_accum.flags.c_contiguous
         ud = udiag_accum.ctypes.data_as(c_f64p)
+    if mass_vof is not None:
+        mv = _f(mass_vof)
+        f = lib().orc_momentum_edge_vof
+        f.argtypes = [C.c_int, C.c_int64, c_i32p] + [c_f64p] * 10 + [
+            C.POINTER(MomentumOpts), C.c_void_p, c_f64p]
+        f.restype = None
+        ptrs = [a[1] for a in arrs]
+        f(ndim, en.size // 2, pe, *ptrs[:8], mv[1], ptrs[8], C.byref(o), sink.h, ud)
+        return
     lib().orc_momentum_edge(ndim, en.size // 2, pe, *[a[1] for a in arrs],
                             C.byref(o), sink.h, ud)
 

@@ -509,7 +509,12 @@ emu_assemble(
           pf = peclet_eval(o.pf, peclet_number<ND>(pl, pr, o.pec_eps));
         }
         MomResult<ND> m;
-        momentum_edge<ND>(L, R, av, sMdot[hd.edge0 + j], pf, o, m);
+        /* has_vof: the caller hands mass_flow_rate + mass_vof_balanced_flow_rate
+         * as the mdot stream, as nw_assemble_momentum_edge's edge_sum_kernel does */
+        if (o.has_vof)
+          momentum_edge_vof<ND>(L, R, av, sMdot[hd.edge0 + j], pf, o, m);
+        else
+          momentum_edge<ND>(L, R, av, sMdot[hd.edge0 + j], pf, o, m);
         momentum_block_entry<ND>(
           m, av, o.relax_fac, 0, 0, out[0], out[1], out[2], out[3]);
         for (int d = 0; d < ND; ++d)
@@ -685,7 +690,10 @@ emu_assemble_mono(
       ld(l, L);
       ld(r, R);
       const double pf = pecfac ? sPec[hd.edge0 + j] : 0.0;
-      momentum_edge<ND>(L, R, a, sMdot[hd.edge0 + j], pf, o, res[j]);
+      if (o.has_vof)
+        momentum_edge_vof<ND>(L, R, a, sMdot[hd.edge0 + j], pf, o, res[j]);
+      else
+        momentum_edge<ND>(L, R, a, sMdot[hd.edge0 + j], pf, o, res[j]);
     }
     /* row walk: ND rows per node, blocks written in place (the device stages
      * them and copies out; same values, same order of additions) */

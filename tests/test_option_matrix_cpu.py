@@ -259,3 +259,111 @@ def test_momentum_option_matrix_product_header_vs_oracle(o):
     av, arhs = s3.get_abs()
     assert pu.scaled_err(vals, ov, av) < 1
     assert pu.scaled_err(rhs, orhs.ravel(), arhs.ravel()) < 1
+
+
+# ---------------------------------------------------------------------------
+# realm_has_vof_ (src/edge_kernels/MomentumEdgeSolverAlg.C:88, 124-125, 174-192)
+# ---------------------------------------------------------------------------
+
+def _two_phase_density(c, seed=5):
+    """water / air with a band of intermediate densities: the density jump
+    |rhoL - rhoR| / min spans 0 ... ~1000, erf(6 x) spans 0 ... 1"""
+    x = c.box.coords.reshape(-1, 3)
+    rng = np.random.default_rng(seed)
+    s = (x[:, 2] - 0.5 * x[:, 2].max()) / max(1.0, 0.25 * x[:, 2].max())
+    rho = 1.2 + 0.5 * (1.0 + np.tanh(s)) * 998.8
+    # a few nodes with tiny relative differences (erf in its linear range)
+    rho *= 1.0 + 0.02 * rng.random(rho.size)
+    return rho
+
+
+@pytest.mark.parametrize("o", [
+    dict(include_divu=0.0, alpha=0.0, alpha_upw=1.0, ho_upwind=1.0,
+         relax_fac=0.7, use_limiter=True),
+    dict(include_divu=1.0, alpha=0.4, alpha_upw=0.6, ho_upwind=0.5,
+         relax_fac=1.0, use_limiter=False),
+    dict(include_divu=0.0, alpha=0.0, alpha_upw=0.0, ho_upwind=0.0,
+         relax_fac=1.0, use_limiter=False)],
+    ids=["deck", "mixed", "gold"])
+def test_vof_branch_product_header_vs_oracle(o):
+    P = pu.pkg()
+    c = _case(dims=(6, 5, 6))
+    f, b = c.fields, c.box
+    f["density"] = _two_phase_density(c)
+    emu = pu.Emu(c, tile_nodes=40)
+    emu.build_linsys(0, 1)
+    g = c.oracle_graph()
+    nnz, rows = _graph_sizes(g)
+    mdot = c.oracle_mdot()
+    rng = np.random.default_rng(11)
+    mvof = 0.3 * np.abs(mdot).mean() * rng.standard_normal(c.n_edges)
+    pec = c.oracle_pecfac(orc.peclet("classic", 1.0))
+
+    def oracle(graph, uvw, vof=True):
+        s = orc.HypreSink(graph, b.hid, uvw_ndim=3 if uvw else 0)
+        orc.momentum_edge(3, c.edges, b.coords, f["velocity"], f["dudx"],
+                          f["viscosity"], f["density"],
+                          f["abl_wall_no_slip_wall_func_node_mask"], c.area,
+                          mdot, pec, s, mass_vof=mvof if vof else None, **o)
+        return s
+
+    def popts(fuse, vof=1):
+        return P.MomentumOpts(
+            o["include_divu"], o["alpha"], o["alpha_upw"], o["ho_upwind"],
+            o["relax_fac"], 1 if o["use_limiter"] else 0, 1e-16, fuse,
+            P.peclet_fn("classic", 1.0), 1e-16, -1, vof)
+
+    s = oracle(g, True)
+    ov, orhs = s.get()
+    av, arhs = s.get_abs()
+    # the branch must matter on this case, else the comparison says nothing
+    s0 = oracle(g, True, vof=False)
+    assert pu.scaled_err(s0.get()[0], ov, av) > 1e6
+    for fuse in (0, 1):
+        vals, rhs = emu.assemble(2, pu.MOM_FIELDS, popts(fuse), nnz, rows, 3,
+                                 mdot=mdot + mvof, pecfac=pec)
+        assert pu.scaled_err(vals, ov, av) < 1
+        assert pu.scaled_err(rhs, orhs, arhs) < 1
+    g3 = c.oracle_graph(num_dof=3)
+    s3 = oracle(g3, False)
+    vals, rhs = emu.assemble_mono(pu.MOM_FIELDS, popts(0), *_graph_sizes(g3),
+                                  mdot=mdot + mvof, pecfac=pec)
+    ov, orhs = s3.get()
+    av, arhs = s3.get_abs()
+    assert pu.scaled_err(vals, ov, av) < 1
+    assert pu.scaled_err(rhs, orhs.ravel(), arhs.ravel()) < 1
+
+
+def test_vof_branch_is_the_identity_for_uniform_density():
+    """rhoL == rhoR: the jump is 0, erf(0) = 0, the factor exactly 1, alphaUpw
+    and the Peclet factor unchanged -- with a zero mass_vof_balanced_flow_rate
+    the VOF branch must return the non-VOF result bit for bit (oracle and
+    product header; an answer that does not depend on either's VOF lines)"""
+    P = pu.pkg()
+    c = _case(dims=(5, 4, 4))
+    f, b = c.fields, c.box
+    f["density"] = np.full(c.n_nodes, 1.178037722969475)
+    g = c.oracle_graph()
+    nnz, rows = _graph_sizes(g)
+    mdot = c.oracle_mdot()
+    pec = c.oracle_pecfac(orc.peclet("classic", 1.0))
+    o = dict(include_divu=1.0, alpha=0.4, alpha_upw=0.6, ho_upwind=0.5,
+             relax_fac=0.7, use_limiter=True)
+    out = []
+    for mv in (None, np.zeros(c.n_edges)):
+        s = orc.HypreSink(g, b.hid, uvw_ndim=3)
+        orc.momentum_edge(3, c.edges, b.coords, f["velocity"], f["dudx"],
+                          f["viscosity"], f["density"],
+                          f["abl_wall_no_slip_wall_func_node_mask"], c.area,
+                          mdot, pec, s, mass_vof=mv, **o)
+        out.append(s.get())
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    emu = pu.Emu(c, tile_nodes=40)
+    emu.build_linsys(0, 1)
+    got = []
+    for vof in (0, 1):
+        got.append(emu.assemble(2, pu.MOM_FIELDS, P.MomentumOpts(
+            o["include_divu"], o["alpha"], o["alpha_upw"], o["ho_upwind"],
+            o["relax_fac"], 1, 1e-16, 0, P.peclet_fn("classic", 1.0), 1e-16,
+            -1, vof), nnz, rows, 3, mdot=mdot, pecfac=pec))
+    assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1])
