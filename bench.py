@@ -1016,7 +1016,10 @@ def main():
             line["north_star"] = {"error": str(e)[:300]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = run_cpu_baseline(P, args.n, args.sst)
+        try:
+            line["cpu_baseline"] = run_cpu_baseline(P, args.n, args.sst)
+        except Exception as e:  # the GPU line must not be lost to the CPU leg
+            line["cpu_baseline"] = {"error": str(e)[:300]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
