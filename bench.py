@@ -790,9 +790,9 @@ def main():
     # Warm-up in two parts around the start of the clock sampler (nvidia-smi
     # needs ~0.3 s to spawn): the last three warm-up sweeps run immediately
     # ahead of the timed region, so that it does not begin on a GPU that has
-    # just idled for 0.3 s.  W (>= 3) sweeps in total, at least 2 before.
+    # just idled for 0.3 s.  W (>= 3) sweeps in total.
     warm = max(args.warmup, 3)
-    for _ in range(max(warm - 3, 2)):
+    for _ in range(warm - 3):
         sw.run()
     barrier()
     sampler = ClockSampler(local)
