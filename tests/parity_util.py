@@ -245,10 +245,33 @@ def oracle_momentum(case, g, mdot, pecfac, uvw=True, udiag=None):
 # CPU plan walk-through (tests/emul)
 # ---------------------------------------------------------------------------
 _emu = None
+_emu_variants = {}
 
 
-def emu_lib():
+def host_has_fma():
+    try:
+        return " fma " in open("/proc/cpuinfo").read().replace("\n", " ")
+    except OSError:
+        return False
+
+
+def emu_lib(fma=False):
+    """fma: the build whose a*b+c are contracted into fused multiply-adds (as
+    nvcc contracts them on the device) -- a CPU stand-in for device rounding"""
     global _emu
+    if fma:
+        if "fma" not in _emu_variants:
+            subprocess.check_call(["make", "-C", os.path.join(HERE, "emul"), "-s",
+                                   "libnw_emul_fma.so"])
+            L = C.CDLL(os.path.join(HERE, "emul", "libnw_emul_fma.so"))
+            base = emu_lib()
+            for name in ("emu_create", "emu_error", "emu_destroy",
+                         "emu_build_linsys", "emu_check_plan", "emu_assemble_mono",
+                         "emu_assemble", "emu_nodal_grad", "emu_mdot"):
+                getattr(L, name).argtypes = getattr(base, name).argtypes
+                getattr(L, name).restype = getattr(base, name).restype
+            _emu_variants["fma"] = L
+        return _emu_variants["fma"]
     if _emu is None:
         subprocess.check_call(["make", "-C", os.path.join(HERE, "emul"), "-s"])
         L = C.CDLL(os.path.join(HERE, "emul", "libnw_emul.so"))
@@ -277,10 +300,10 @@ def _p(a):
 
 
 class Emu:
-    def __init__(self, case, tile_nodes=64):
+    def __init__(self, case, tile_nodes=64, fma=False):
         b = case.box
         self.case = case
-        L = emu_lib()
+        self.L = L = emu_lib(fma)
         self._keep = [np.ascontiguousarray(b.edges), b.hid, b.own_hid,
                       b.offsets, b.coords]
         self.h = L.emu_create(3, b.rank, b.nranks, b.n_nodes, b.n_edges,
@@ -290,12 +313,12 @@ class Emu:
 
     def build_linsys(self, kind=0, num_dof=1, skipped=()):
         sk = np.ascontiguousarray(skipped, dtype=np.int64)
-        rc = emu_lib().emu_build_linsys(self.h, kind, num_dof, _p(sk), sk.size)
-        assert rc == 0, emu_lib().emu_error(self.h).decode()
+        rc = self.L.emu_build_linsys(self.h, kind, num_dof, _p(sk), sk.size)
+        assert rc == 0, self.L.emu_error(self.h).decode()
 
     def check_plan(self):
-        rc = emu_lib().emu_check_plan(self.h)
-        assert rc == 0, emu_lib().emu_error(self.h).decode()
+        rc = self.L.emu_check_plan(self.h)
+        assert rc == 0, self.L.emu_error(self.h).decode()
 
     def _fields(self, names):
         arrs = [np.ascontiguousarray(self.case.fields[n] if n != "coordinates"
@@ -314,11 +337,11 @@ class Emu:
         vals = np.zeros(nnz)
         rhs = np.zeros(rows)
         area = np.ascontiguousarray(self.case.area)
-        rc = emu_lib().emu_assemble_mono(
+        rc = self.L.emu_assemble_mono(
             self.h, C.cast(ptrs, C.c_void_p), _p(nc), len(arrs), _p(area),
             _p(mdot), _p(pecfac), C.cast(C.byref(opts), C.c_void_p), _p(sk),
             sk.size, _p(vals), _p(rhs))
-        assert rc == 0, emu_lib().emu_error(self.h).decode()
+        assert rc == 0, self.L.emu_error(self.h).decode()
         return vals, rhs
 
     def assemble(self, kind, names, opts, nnz, rows, nrhs, mdot=None,
@@ -327,11 +350,11 @@ class Emu:
         vals = np.zeros(nnz)
         rhs = np.zeros((nrhs, rows))
         area = np.ascontiguousarray(self.case.area)
-        rc = emu_lib().emu_assemble(
+        rc = self.L.emu_assemble(
             self.h, kind, C.cast(ptrs, C.c_void_p), _p(nc), len(arrs),
             _p(area), _p(mdot), _p(pecfac), C.cast(C.byref(opts), C.c_void_p),
             _p(vals), _p(rhs))
-        assert rc == 0, emu_lib().emu_error(self.h).decode()
+        assert rc == 0, self.L.emu_error(self.h).decode()
         return vals, rhs
 
     def nodal_grad(self, phi, dim1):
@@ -339,7 +362,7 @@ class Emu:
         out = np.zeros((self.case.n_nodes, dim1 * 3))
         area = np.ascontiguousarray(self.case.area)
         vol = np.ascontiguousarray(self.case.fields["dual_nodal_volume"])
-        rc = emu_lib().emu_nodal_grad(self.h, dim1, _p(phi), _p(area), _p(vol),
+        rc = self.L.emu_nodal_grad(self.h, dim1, _p(phi), _p(area), _p(vol),
                                       _p(out))
         assert rc == 0
         return out
@@ -348,14 +371,14 @@ class Emu:
         arrs, ptrs, nc = self._fields(CONT_FIELDS)
         out = np.zeros(self.case.n_edges)
         area = np.ascontiguousarray(self.case.area)
-        rc = emu_lib().emu_mdot(self.h, C.cast(ptrs, C.c_void_p), _p(nc),
+        rc = self.L.emu_mdot(self.h, C.cast(ptrs, C.c_void_p), _p(nc),
                                 len(arrs), _p(area), 1.0, 1.0, _p(out))
-        assert rc == 0, emu_lib().emu_error(self.h).decode()
+        assert rc == 0, self.L.emu_error(self.h).decode()
         return out
 
     def __del__(self):
         if getattr(self, "h", None):
-            emu_lib().emu_destroy(self.h)
+            self.L.emu_destroy(self.h)
             self.h = None
 
 

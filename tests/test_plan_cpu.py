@@ -112,14 +112,18 @@ def test_skipped_rows_graph():
     assert np.array_equal(rows, orows)
 
 
+@pytest.mark.parametrize("fma", [False, pytest.param(True, marks=pytest.mark.skipif(
+    not pu.host_has_fma(), reason="host CPU without FMA"))], ids=["plain", "fma"])
 @pytest.mark.parametrize("kw", CASES, ids=_ids)
-def test_tile_plan_walkthrough_matches_oracle(kw):
+def test_tile_plan_walkthrough_matches_oracle(kw, fma):
     """Replay the tile kernels' phases on the CPU from the same plan arrays and
     the same physics header; every matrix / rhs entry within 1e-12 of the
-    oracle (scaled by the entry's sum of |contributions|)."""
+    oracle (scaled by the entry's sum of |contributions|).  fma: the header
+    compiled with fused multiply-add contraction, as nvcc compiles it for the
+    device (the oracle is compiled -ffp-contract=off)."""
     P = pu.pkg()
     case = pu.Case(**kw)
-    emu = pu.Emu(case, tile_nodes=40)
+    emu = pu.Emu(case, tile_nodes=40, fma=fma)
     emu.build_linsys(0, 1)
     emu.check_plan()
     g = case.oracle_graph()
@@ -177,7 +181,7 @@ def test_tile_plan_walkthrough_matches_oracle(kw):
         # with Dirichlet nodes: the twin skips their node rows
         nodes = np.array([2, 11, 30], dtype=np.int64)
         sk3 = (3 * nodes[:, None] + np.arange(3)).ravel()
-        emu_s = pu.Emu(case, tile_nodes=40)
+        emu_s = pu.Emu(case, tile_nodes=40, fma=fma)
         emu_s.build_linsys(0, 1, skipped=nodes)
         g3s = case.oracle_graph(num_dof=3, skipped=sk3)
         o3s = pu.oracle_momentum(case, g3s, omdot, opec, uvw=False)

@@ -77,7 +77,13 @@ def test_vof_momentum_vs_oracle(P, ctx, system, mode, o):
                       omdot, opec, s, mass_vof=mvof, **o)
     ov, orhs = s.get()
     av, arhs = s.get_abs()
-    assert pu.scaled_err(vals, ov, av) < 1
+    # matrix entries: 1e-12 of max(sum of |contributions|, 1e-4 of the row's
+    # largest entry) -- across an interface the branch leaves 0.5 mdot (1 -
+    # pecfac') with pecfac' = 1 - O(1e-16) beside the viscous term, a
+    # cancellation remainder that FMA contraction moves by 1e-9 of the entry
+    # and 1e-18 of its row (tests/test_option_matrix_cpu.py, the fma build)
+    lsc = pu.lhs_scale(g.rows - g.i_lower, ov, av)
+    assert pu.scaled_err(vals, ov, lsc) < 1
     assert pu.scaled_err(rhs, orhs, arhs) < 1
     # and the branch is not a no-op on this case
     s0 = orc.HypreSink(g, b.hid, uvw_ndim=3 if uvw else 0)
@@ -85,7 +91,7 @@ def test_vof_momentum_vs_oracle(P, ctx, system, mode, o):
                       f["viscosity"], f["density"],
                       f["abl_wall_no_slip_wall_func_node_mask"], case.area,
                       omdot, opec, s0, **o)
-    assert pu.scaled_err(vals, s0.get()[0], av) > 1e6
+    assert pu.scaled_err(vals, s0.get()[0], lsc) > 1e6
     # has_vof off again: the ordinary kernels, the ordinary answer
     ls.zeroSystem()
     ls.assemble_momentum_edge("viscosity", **o)
