@@ -153,6 +153,46 @@ def lhs_scale(g_rows, ov, av, floor=1e-4):
     return np.maximum(av, floor * rowmax[rows])
 
 
+def momentum_flux_scale(edges, mdot, velocity, n_nodes):
+    """per node: sum over its edges of |mdot| * max(|u_L|_inf, |u_R|_inf) -- the
+    magnitude of the advective momentum flux VECTOR through the node's dual
+    faces.  Floor for the rhs tolerance of the VOF branch (same idea as
+    lhs_scale): a component whose own flux sum is below 1e-4 of this is held to
+    that fraction of it."""
+    e = np.asarray(edges).reshape(-1, 2)
+    u = np.abs(np.asarray(velocity).reshape(n_nodes, -1)).max(axis=1)
+    w = np.abs(np.asarray(mdot)) * np.maximum(u[e[:, 0]], u[e[:, 1]])
+    out = np.zeros(n_nodes)
+    np.add.at(out, e[:, 0], w)
+    np.add.at(out, e[:, 1], w)
+    return out
+
+
+def vof_scales(c, g, mdot_total, ov, av, arhs, num_dof):
+    """Tolerance scales of the VOF comparisons.  The
+    branch evaluates erf, the one function of the path the device does not
+    compute bit for bit like the host (CUDA: <= 2 ulp), and with the decks'
+    alphaUpw = 1 it forms  1 - (f + (1 - f))  and  1 - (1 - f + f pecfac):  0 or
+    +-1 ulp depending on the last bit of f.  That ulp, times mdot, is the whole
+    error of an entry (or rhs component) whose own magnitude is a cancellation
+    remainder -- the viscous 2e-5 beside mdot ~ 1e4, the w-momentum flux at a
+    node whose upwind w is exactly 0 -- so:
+      matrix entries  1e-12 max(sum |contributions|, 1e-3 row max)
+      rhs components  1e-12 max(sum |contributions|, 1e-4 sum_e |mdot| |u|_inf)
+    (measured with the +-2 ulp build: 0.35 and 0.01 of these; 5e4 and 9e2 of
+    the plain scale)."""
+    lsc = lhs_scale(g.rows - g.i_lower, ov, av, floor=1e-3)
+    flux = momentum_flux_scale(c.edges, mdot_total, c.fields["velocity"],
+                                  c.n_nodes)
+    per_row = np.zeros(g.num_rows_owned // num_dof)
+    per_row[c.box.hid - g.i_lower // num_dof] = flux
+    if num_dof == 1:   # UVW: rhs[d][row]
+        rsc = np.maximum(arhs, 1e-4 * per_row[None, :arhs.shape[1]])
+    else:              # monolithic: rhs[row * ndof + d]
+        rsc = np.maximum(arhs.ravel(), 1e-4 * np.repeat(per_row, num_dof))
+    return lsc, rsc
+
+
 class Case:
     """generated hex box + synthetic state (one rank)"""
 
@@ -260,18 +300,20 @@ def emu_lib(fma=False):
     nvcc contracts them on the device) -- a CPU stand-in for device rounding"""
     global _emu
     if fma:
-        if "fma" not in _emu_variants:
-            subprocess.check_call(["make", "-C", os.path.join(HERE, "emul"), "-s",
-                                   "libnw_emul_fma.so"])
-            L = C.CDLL(os.path.join(HERE, "emul", "libnw_emul_fma.so"))
+        # fma == "erf": additionally erf moved by up to +-2 ulp (emul/erf_perturb.h)
+        key = "erf" if fma == "erf" else "fma"
+        if key not in _emu_variants:
+            so = "libnw_emul_%s.so" % key
+            subprocess.check_call(["make", "-C", os.path.join(HERE, "emul"), "-s", so])
+            L = C.CDLL(os.path.join(HERE, "emul", so))
             base = emu_lib()
             for name in ("emu_create", "emu_error", "emu_destroy",
                          "emu_build_linsys", "emu_check_plan", "emu_assemble_mono",
                          "emu_assemble", "emu_nodal_grad", "emu_mdot"):
                 getattr(L, name).argtypes = getattr(base, name).argtypes
                 getattr(L, name).restype = getattr(base, name).restype
-            _emu_variants["fma"] = L
-        return _emu_variants["fma"]
+            _emu_variants[key] = L
+        return _emu_variants[key]
     if _emu is None:
         subprocess.check_call(["make", "-C", os.path.join(HERE, "emul"), "-s"])
         L = C.CDLL(os.path.join(HERE, "emul", "libnw_emul.so"))

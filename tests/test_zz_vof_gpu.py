@@ -77,14 +77,14 @@ def test_vof_momentum_vs_oracle(P, ctx, system, mode, o):
                       omdot, opec, s, mass_vof=mvof, **o)
     ov, orhs = s.get()
     av, arhs = s.get_abs()
-    # matrix entries: 1e-12 of max(sum of |contributions|, 1e-4 of the row's
-    # largest entry) -- across an interface the branch leaves 0.5 mdot (1 -
-    # pecfac') with pecfac' = 1 - O(1e-16) beside the viscous term, a
-    # cancellation remainder that FMA contraction moves by 1e-9 of the entry
-    # and 1e-18 of its row (tests/test_option_matrix_cpu.py, the fma build)
-    lsc = pu.lhs_scale(g.rows - g.i_lower, ov, av)
+    # tolerance scales of the VOF branch (parity_util.vof_scales: the device's
+    # erf is not bit-identical to the host's, and with alphaUpw = 1 one ulp of
+    # it is the whole error of entries that are cancellation remainders; sized
+    # on the CPU with the fma / +-2 ulp builds, tests/test_option_matrix_cpu.py)
+    lsc, rsc = pu.vof_scales(case, g, omdot + mvof, ov, av, arhs, 1 if uvw else 3)
     assert pu.scaled_err(vals, ov, lsc) < 1
-    assert pu.scaled_err(rhs, orhs, arhs) < 1
+    assert pu.scaled_err(rhs.ravel() if not uvw else rhs,
+                         orhs.ravel() if not uvw else orhs, rsc) < 1
     # and the branch is not a no-op on this case
     s0 = orc.HypreSink(g, b.hid, uvw_ndim=3 if uvw else 0)
     orc.momentum_edge(3, case.edges, b.coords, f["velocity"], f["dudx"],
