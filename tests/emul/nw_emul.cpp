@@ -964,6 +964,13 @@ emu_peclet_eval(int form, double a, double b, double pecnum)
   return peclet_eval(f, pecnum);
 }
 
+/* the product's van_leer (edge_physics.h), host build */
+double
+emu_van_leer(double dqm, double dqp, double eps)
+{
+  return van_leer(dqm, dqp, eps);
+}
+
 /* The default-option paths of momentum_edge / scalar_edge (edge_physics.h,
  * template DEF) against the general paths on n seeded random edges with
  * alpha = 0, alpha_upw = 1, hoUpwind = 1: returns the number of result doubles
