@@ -155,6 +155,33 @@ ref_scs_areav(int topo, const double* coords, int simd, double* areav)
   return 0;
 }
 
+/* one element block of a mesh: conn[nElems][npe] into coords[nNodes][ndim];
+ * volume[nElems][numScvIp], areav[nElems][numScsIp][ndim] (DoubleType overloads) */
+int
+ref_geometry_block(
+  int topo, long nElems, const int* conn, const double* coords, double* volume,
+  double* areav)
+{
+  auto v = make_scv(topo);
+  auto s = make_scs(topo);
+  if (!v || !s)
+    return 1;
+  const int npe = v->nodesPerElement_, nd = v->nDim_;
+  const int nscv = v->num_integration_points();
+  const int nscs = s->num_integration_points();
+  std::vector<double> x(npe * nd);
+  for (long e = 0; e < nElems; ++e) {
+    for (int n = 0; n < npe; ++n)
+      for (int d = 0; d < nd; ++d)
+        x[n * nd + d] = coords[(long)conn[e * npe + n] * nd + d];
+    if (int rc = ref_scv_volume(topo, x.data(), 1, volume + e * nscv))
+      return rc;
+    if (int rc = ref_scs_areav(topo, x.data(), 1, areav + e * nscs * nd))
+      return rc;
+  }
+  return 0;
+}
+
 /* ipNodeMap of the SCV (numScvIp ints) and adjacentNodes of the SCS
  * (2 numScsIp ints: left, right) */
 int

@@ -17,7 +17,8 @@ seeded inputs.  This pins what no in-tree gold of the reference pins:
   * the Peclet blending functions and the limiter over a sweep of arguments,
     bit for bit.
 
-`-m gpu` part: the device kernels (nw_geometry_interior_*) on the same elements.
+The device kernels (nw_geometry_interior_*) run on the same elements in
+tests/test_zzz_reference_runs_gpu.py (`-m gpu`).
 """
 import ctypes as C
 import json
@@ -121,19 +122,73 @@ def test_fixture_is_what_the_reference_build_gives_now():
         assert L.ref_peclet_tanh(FH(c1), FH(c2), FH(p)) == FH(want)
 
 
+@pytest.mark.parametrize("name", ["multiElemTypeCylinder", "hybrid_g_8_0"])
+def test_oracle_geometry_vs_reference_on_its_own_meshes(name):
+    """every element of the reference's mixed tet / pyramid / wedge / hex
+    regression meshes through the reference's master elements, live (needs
+    oracle/_ref: skipped where the reference tree never was)"""
+    so = os.path.join(HERE, "..", "oracle", "_ref", "libnalu_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    L = C.CDLL(so)
+    vp = C.c_void_p
+    L.ref_geometry_block.argtypes = [C.c_int, C.c_long, vp, vp, vp, vp]
+    ids = {"hex": 0, "tet": 1, "pyr": 2, "wed": 3}
+    msh = pu.load_reference_mesh(name)
+    coords = np.ascontiguousarray(msh["coords"])
+    edges = np.ascontiguousarray(msh["edges"])
+    n = len(coords)
+    blocks = pu.mesh_blocks(msh)
+    odnv, oarea, oev = pu.oracle_mesh_geometry(blocks, coords, edges)
+    ekey = {}
+    for e, (a, b) in enumerate(edges):
+        ekey[(int(a), int(b))] = (e, 1.0)
+        ekey[(int(b), int(a))] = (e, -1.0)
+    dnv, area = np.zeros(n), np.zeros((len(edges), 3))
+    dmag, amag = np.zeros(n), np.zeros(len(edges))
+    total = 0
+    for t, conn in blocks.items():
+        m = R["master_elements"][t]
+        nscv, nscs = m["num_scv_ip"], m["num_scs_ip"]
+        conn = np.ascontiguousarray(conn, dtype=np.int32)
+        vol = np.zeros((len(conn), nscv))
+        av = np.zeros((len(conn), nscs, 3))
+        assert L.ref_geometry_block(ids[t], len(conn), conn.ctypes.data,
+                                    coords.ctypes.data, vol.ctypes.data,
+                                    av.ctypes.data) == 0
+        # element volumes: the same sum in the same order, bit for bit
+        ev = np.zeros(len(conn))
+        for ip in range(nscv):
+            ev += vol[:, ip]
+        assert np.array_equal(ev, oev[t]), t
+        ipn = np.array(m["ip_node_map"])
+        np.add.at(dnv, conn[:, ipn].ravel(), vol.ravel())
+        np.add.at(dmag, conn[:, ipn].ravel(), np.abs(vol).ravel())
+        lr = np.array(m["adjacent_nodes"]).reshape(nscs, 2)
+        for ip in range(nscs):
+            L_, R_ = conn[:, lr[ip, 0]], conn[:, lr[ip, 1]]
+            es = np.array([ekey[(int(a), int(b))] for a, b in zip(L_, R_)])
+            idx, sgn = es[:, 0].astype(np.int64), es[:, 1]
+            np.add.at(area, idx, sgn[:, None] * av[:, ip, :])
+            np.add.at(amag, idx, np.abs(av[:, ip, :]).max(axis=1))
+        total += len(conn)
+    assert total > 20000 or name != "multiElemTypeCylinder"
+    # sums over the elements around a node / an edge, accumulated in another
+    # order than the oracle's: a few ulp of the sum of magnitudes
+    assert np.max(np.abs(dnv - odnv) / dmag) <= 1e-15
+    assert np.max(np.abs(area - oarea) / amag[:, None]) <= 1e-15
+
+
 @pytest.mark.parametrize("topo", TOPOS_3D + ["quad"])
 def test_oracle_geometry_vs_reference_master_elements(topo):
     m, coords, conn, edges, dnv, ev, area = _block(topo)
     n = len(coords)
     odnv, oev, oarea = _oracle_geometry(topo, conn, coords, edges, n)
-    # same formulas in the same order: agreement to the last few bits of each
-    # value (a sub-control volume is a sum of signed terms; its error is
-    # measured against the element's own size)
-    vscale = np.repeat(ev, m["nodes_per_element"])
-    assert np.max(np.abs(odnv - dnv) / vscale) <= 4e-16, topo
-    assert np.max(np.abs(oev - ev) / ev) <= 4e-16, topo
-    ascale = np.max(np.abs(area))
-    assert np.max(np.abs(oarea - area)) <= 4e-16 * ascale, topo
+    # same formulas in the same operation order, no contraction on either side
+    # (-ffp-contract=off): the oracle reproduces the reference's bits
+    assert np.array_equal(odnv, dnv), topo
+    assert np.array_equal(oev, ev), topo
+    assert np.array_equal(oarea, area), topo
     # reversed mesh-edge orientation flips the sign (GeometryInteriorAlg.C:213)
     _, _, orev = _oracle_geometry(topo, conn, coords, edges[:, ::-1].copy(), n)
     assert np.array_equal(orev, -oarea)
@@ -214,33 +269,3 @@ def test_van_leer_bitwise_vs_reference():
             # the product multiplies by a reciprocal where the reference divides
             worst = max(worst, abs(gp - want) / max(abs(want), 1e-300))
     assert worst <= 4.5e-16, worst
-
-
-# ---------------------------------------------------------------------------
-# device kernels on the same elements
-# ---------------------------------------------------------------------------
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("topo", TOPOS_3D + ["quad"])
-def test_device_geometry_vs_reference_master_elements(topo):
-    P = pu.pkg()
-    m, coords, conn, edges, dnv, ev, area = _block(topo)
-    nd = m["ndim"]
-    ctx = P.Context(0)
-    try:
-        mesh = P.Mesh(ctx, nd, edges, np.arange(len(coords), dtype=np.int64), coords)
-        mesh.register("dual_nodal_volume", P.NW_NODE, 1)
-        mesh.register("edge_area_vector", P.NW_EDGE, nd)
-        mesh.fill("dual_nodal_volume", 0.0)
-        mesh.fill("edge_area_vector", 0.0)
-        mesh.geometry_interior(conn, dnv="dual_nodal_volume", area="edge_area_vector")
-        got_dnv = mesh.download("dual_nodal_volume")
-        got_area = mesh.download("edge_area_vector").reshape(-1, nd)
-        # FMA contraction on the device moves single ulps of the terms: 1e-13 of
-        # the element's volume / of the largest area component
-        vscale = np.repeat(ev, m["nodes_per_element"])
-        assert np.max(np.abs(got_dnv - dnv) / vscale) <= 1e-13, topo
-        assert np.max(np.abs(got_area - area)) <= 1e-13 * np.max(np.abs(area)), topo
-        mesh.close()
-    finally:
-        ctx.close()
