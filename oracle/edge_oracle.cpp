@@ -719,6 +719,46 @@ orc_applier_dense_get(const orc_applier* a, double* lhs, double* rhs)
   std::memcpy(rhs, d->rhs_.data(), d->rhs_.size() * sizeof(double));
 }
 
+/* records the local blocks in call order (one thread: edge order) -- for the
+ * edge-by-edge comparison with the reference's own lambdas, oracle/_ref */
+namespace {
+struct RecordApplier : orc_applier
+{
+  int n_ = 0;
+  std::vector<double> lhs_, rhs_;
+  void apply(
+    int, const int32_t*, const double* rhs, const double* lhs, int n) override
+  {
+    n_ = n;
+    lhs_.insert(lhs_.end(), lhs, lhs + size_t(n) * n);
+    rhs_.insert(rhs_.end(), rhs, rhs + n);
+  }
+};
+} // namespace
+
+extern "C" orc_applier*
+orc_applier_record_create()
+{
+  return new RecordApplier();
+}
+
+/* number of recorded calls; *n = block size of the last call */
+extern "C" int64_t
+orc_applier_record_count(const orc_applier* a, int* n)
+{
+  auto* r = static_cast<const RecordApplier*>(a);
+  *n = r->n_;
+  return r->n_ ? int64_t(r->rhs_.size()) / r->n_ : 0;
+}
+
+extern "C" void
+orc_applier_record_get(const orc_applier* a, double* lhs, double* rhs)
+{
+  auto* r = static_cast<const RecordApplier*>(a);
+  std::memcpy(lhs, r->lhs_.data(), r->lhs_.size() * sizeof(double));
+  std::memcpy(rhs, r->rhs_.data(), r->rhs_.size() * sizeof(double));
+}
+
 extern "C" orc_applier*
 orc_applier_hypre_create(
   const orc_graph* g, const int64_t* node_hid, int64_t n_nodes, int uvw_ndim)

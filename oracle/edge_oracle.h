@@ -55,6 +55,13 @@ orc_applier* orc_applier_dense_create(int64_t n_nodes, int num_dof);
 /* copies out lhs (n*n row-major) and rhs (n), n = n_nodes*num_dof */
 void orc_applier_dense_get(const orc_applier*, double* lhs, double* rhs);
 
+/* recorder: keeps every local block in call order (single-threaded runs: edge
+ * order); test infrastructure for the edge-by-edge comparison with the
+ * reference's own lambdas (oracle/_ref) */
+orc_applier* orc_applier_record_create(void);
+int64_t orc_applier_record_count(const orc_applier*, int* n);
+void orc_applier_record_get(const orc_applier*, double* lhs, double* rhs);
+
 /* hypre-IJ style CSR graph: src/HypreLinearSystem.C:97-208 (begin),
  * :211-269 (fill), :412-478 (edge graph), :999-1236 (CSR build),
  * :883-993 (rows/cols arrays). */

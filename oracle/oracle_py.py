@@ -152,6 +152,34 @@ class DenseSink:
             self.h = None
 
 
+class RecordSink:
+    """keeps every local block (lhs n x n, rhs n) in call order; run the oracle
+    on one thread so that call order == edge order"""
+
+    def __init__(self):
+        L = lib()
+        L.orc_applier_record_create.restype = C.c_void_p
+        L.orc_applier_record_count.restype = C.c_int64
+        L.orc_applier_record_count.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        L.orc_applier_record_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self.h = L.orc_applier_record_create()
+
+    def get(self):
+        n = C.c_int(0)
+        cnt = int(lib().orc_applier_record_count(self.h, C.byref(n)))
+        n = n.value
+        lhs = np.zeros((cnt, n, n))
+        rhs = np.zeros((cnt, n))
+        if cnt:
+            lib().orc_applier_record_get(self.h, lhs.ctypes.data, rhs.ctypes.data)
+        return lhs, rhs
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_applier_destroy(C.c_void_p(self.h))
+            self.h = None
+
+
 class Graph:
     """HypreLinearSystem graph (oracle restatement)."""
 

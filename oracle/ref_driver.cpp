@@ -234,7 +234,22 @@ NaluEnv::self()
   static NaluEnv e;
   return e;
 }
-std::ostream& NaluEnv::naluOutputP0() { return std::cerr; }
-std::ostream& NaluEnv::naluOutput() { return std::cerr; }
+namespace {
+/* swallows the reference's log lines (e.g. the VOF warning of the
+ * MomentumEdgeSolverAlg constructor) */
+struct NullBuf : std::streambuf
+{
+  int overflow(int c) override { return c; }
+};
+std::ostream&
+null_stream()
+{
+  static NullBuf b;
+  static std::ostream s(&b);
+  return s;
+}
+} // namespace
+std::ostream& NaluEnv::naluOutputP0() { return null_stream(); }
+std::ostream& NaluEnv::naluOutput() { return null_stream(); }
 } // namespace nalu
 } // namespace sierra

@@ -1,0 +1,321 @@
+/*
+ * oracle/ref_shim/nalu/RefHarness.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Stand-ins for the parts of nalu-wind that surround the edge algorithms, so
+ * that the reference's OWN source files
+ *     src/edge_kernels/{Momentum,Scalar,Continuity}EdgeSolverAlg.C
+ *     src/ngp_algorithms/MdotEdgeAlg.C
+ * compile unmodified, from where they lie, and their constructors and
+ * execute() bodies -- the per-edge lambdas SURVEY.md 8(a) rows a1, a4, a5, a6
+ * cite -- run here on arrays handed in from Python.
+ *
+ * What is the reference's: every line of those four .C files and of the
+ * headers they own (edge_kernels/*.h, ngp_algorithms/MdotEdgeAlg.h,
+ * PecletFunction.h/.C, EdgeKernelUtils.h, Enums.h, FieldTypeDef.h,
+ * KokkosInterface.h, SimdInterface.h).
+ * What is a stand-in (this file and its one-line forwarding headers, which
+ * shadow the reference's headers of the same name on the include path):
+ * Realm, SolutionOptions, EquationSystem, Algorithm, the loop shell
+ * AssembleEdgeSolverAlgorithm::run_algorithm / nalu_ngp::run_edge_algorithm
+ * (here: a serial loop over the edge list that zeroes the local block, calls
+ * the reference's lambda and records the block instead of scattering it), the
+ * field manager and get_field_ordinal.  Written for this repo.
+ */
+#ifndef NW_REF_HARNESS_H
+#define NW_REF_HARNESS_H
+
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <KokkosInterface.h>
+#include <SimdInterface.h>
+#include <Enums.h>
+#include <FieldTypeDef.h>
+#include <PecletFunction.h>
+#include <stk_mesh/base/Types.hpp>
+#include <stk_mesh/base/NgpMesh.hpp>
+#include <stk_mesh/base/NgpField.hpp>
+#include <stk_util/util/ReportHandler.hpp>
+
+namespace nwref {
+
+struct FieldRec
+{
+  std::string name;
+  int rank; /* stk::topology::NODE_RANK / EDGE_RANK */
+  int ncomp;
+  double* data;
+};
+
+/* everything the stand-in Realm answers from */
+struct World
+{
+  int ndim = 3;
+  long nNodes = 0, nEdges = 0;
+  const int* edgeNodes = nullptr; /* [nEdges][2] */
+  std::vector<FieldRec> fields;
+  std::vector<stk::mesh::FieldBase*> fieldHandles;
+  std::map<std::string, double> opt; /* "alpha:velocity", "dt", ... */
+  double gravity[3] = {0, 0, 0};
+  int pecletForm = 0; /* 0 classic(hybridFactor = pecletA), 1 tanh(c1, c2) */
+  double pecletA = 1.0, pecletB = 1.0;
+  /* where run_algorithm records the local blocks */
+  double* lhsOut = nullptr;
+  double* rhsOut = nullptr;
+
+  static World& self()
+  {
+    static World w;
+    return w;
+  }
+  double get(const std::string& key) const
+  {
+    auto it = opt.find(key);
+    if (it == opt.end())
+      throw std::runtime_error("ref harness: option not set: " + key);
+    return it->second;
+  }
+  double get(const std::string& key, double dflt) const
+  {
+    auto it = opt.find(key);
+    return it == opt.end() ? dflt : it->second;
+  }
+  unsigned ordinal(const std::string& name, int rank) const
+  {
+    for (size_t i = 0; i < fields.size(); ++i)
+      if (fields[i].name == name && fields[i].rank == rank)
+        return (unsigned)i;
+    throw std::runtime_error("ref harness: no such field: " + name);
+  }
+};
+
+} // namespace nwref
+
+namespace stk {
+namespace mesh {
+class MetaData
+{
+public:
+  unsigned spatial_dimension() const { return nwref::World::self().ndim; }
+  Part& locally_owned_part() const
+  {
+    static Part p;
+    return p;
+  }
+  const std::vector<FieldBase*>& get_fields() const
+  {
+    return nwref::World::self().fieldHandles;
+  }
+};
+class BulkData
+{
+public:
+  const MetaData& mesh_meta_data() const
+  {
+    static MetaData m;
+    return m;
+  }
+};
+} // namespace mesh
+} // namespace stk
+
+namespace sierra {
+namespace nalu {
+
+/* utils/StkHelpers.h */
+inline unsigned
+get_field_ordinal(
+  const stk::mesh::MetaData&, const std::string& name,
+  const stk::mesh::EntityRank rank = stk::topology::NODE_RANK)
+{
+  return nwref::World::self().ordinal(name, rank);
+}
+inline unsigned
+get_field_ordinal(
+  const stk::mesh::MetaData&, const std::string& name,
+  const stk::mesh::FieldState state,
+  const stk::mesh::EntityRank rank = stk::topology::NODE_RANK)
+{
+  /* only the NP1 state is ever asked for by the files compiled here */
+  STK_ThrowRequireMsg(state == stk::mesh::StateNP1, "ref harness: state of " << name);
+  return nwref::World::self().ordinal(name, rank);
+}
+
+namespace nalu_ngp {
+/* ngp_utils/NgpFieldManager.h */
+class FieldManager
+{
+public:
+  template <class T>
+  stk::mesh::NgpField<T> get_field(unsigned ord) const
+  {
+    const auto& f = nwref::World::self().fields.at(ord);
+    return stk::mesh::NgpField<T>(f.data, f.ncomp);
+  }
+};
+
+/* ngp_utils/NgpLoopUtils.h: EntityInfo and the edge loop shell */
+template <class Mesh>
+struct EntityInfo
+{
+  stk::mesh::FastMeshIndex meshIdx;
+  stk::mesh::Entity entity;
+  stk::mesh::Entity entityNodes[2];
+};
+
+template <class Mesh, class Lambda>
+void
+run_edge_algorithm(
+  const std::string&, const Mesh&, const stk::mesh::Selector&, const Lambda& f)
+{
+  const auto& w = nwref::World::self();
+  for (long e = 0; e < w.nEdges; ++e) {
+    EntityInfo<Mesh> info;
+    info.meshIdx = stk::mesh::FastMeshIndex{0u, (unsigned)e};
+    info.entity.m_value = (uint64_t)e;
+    info.entityNodes[0].m_value = (uint64_t)w.edgeNodes[2 * e];
+    info.entityNodes[1].m_value = (uint64_t)w.edgeNodes[2 * e + 1];
+    f(info);
+  }
+}
+} // namespace nalu_ngp
+
+class SolutionOptions
+{
+public:
+  bool realm_has_vof_ = false;
+  bool use_balanced_buoyancy_force_ = false;
+  TurbulenceModel turbulenceModel_ = TurbulenceModel::LAMINAR;
+  double get_relaxation_factor(const std::string& dof) const
+  {
+    return nwref::World::self().get("relax:" + dof);
+  }
+  std::vector<double> get_gravity_vector(const unsigned nDim) const
+  {
+    const auto& w = nwref::World::self();
+    return std::vector<double>(w.gravity, w.gravity + nDim);
+  }
+  std::string get_coordinates_name() const { return "coordinates"; }
+};
+
+class Realm
+{
+public:
+  Realm() : solutionOptions_(&so_) {}
+  const stk::mesh::MetaData& meta_data() const { return bulk_.mesh_meta_data(); }
+  stk::mesh::BulkData& bulk_data() { return bulk_; }
+  const stk::mesh::NgpMesh& ngp_mesh() const { return ngpMesh_; }
+  const nalu_ngp::FieldManager& ngp_field_manager() const { return fm_; }
+  std::string get_coordinates_name() const { return "coordinates"; }
+  bool does_mesh_move() const { return false; }
+  bool has_mesh_deformation() const { return w().get("mesh_deformation", 0.0) != 0.0; }
+  bool is_turbulent() const { return false; }
+  double get_divU() const { return w().get("divU"); }
+  double get_alpha_factor(const std::string d) const { return w().get("alpha:" + d); }
+  double get_alpha_upw_factor(const std::string d) const { return w().get("alpha_upw:" + d); }
+  double get_upw_factor(const std::string d) const { return w().get("upw:" + d); }
+  bool primitive_uses_limiter(const std::string d) const { return w().get("limiter:" + d) != 0.0; }
+  bool get_noc_usage(const std::string d) const { return w().get("noc:" + d) != 0.0; }
+  double get_mdot_interp() const { return w().get("mdot_interp"); }
+  double get_incompressible_solve() const { return w().get("solve_incompressible"); }
+  double get_time_step() const { return w().get("dt"); }
+  double get_gamma1() const { return w().get("gamma1"); }
+  stk::mesh::Selector get_inactive_selector() const { return stk::mesh::Selector(); }
+
+  SolutionOptions so_;
+  SolutionOptions* solutionOptions_;
+
+private:
+  static const nwref::World& w() { return nwref::World::self(); }
+  stk::mesh::BulkData bulk_;
+  stk::mesh::NgpMesh ngpMesh_;
+  nalu_ngp::FieldManager fm_;
+};
+
+class EquationSystem
+{
+public:
+  explicit EquationSystem(int numDof) : numDof_(numDof) {}
+  /* src/EquationSystem.C: builds the blending function the input file names */
+  template <class T>
+  PecletFunction<T>* ngp_create_peclet_function(const std::string&)
+  {
+    const auto& w = nwref::World::self();
+    if (w.pecletForm == 0)
+      return new ClassicPecletFunction<T>((T)5.0, (T)w.pecletA);
+    return new TanhFunction<T>((T)w.pecletA, (T)w.pecletB);
+  }
+  int numDof_;
+};
+
+/* Algorithm.h */
+class Algorithm
+{
+public:
+  Algorithm(Realm& realm, stk::mesh::Part* part) : realm_(realm), partVec_(1, part) {}
+  virtual ~Algorithm() {}
+  virtual void execute() = 0;
+  Realm& realm_;
+  stk::mesh::PartVector partVec_;
+};
+
+/* SharedMemData.h: the edge scratch the lambdas write */
+struct SharedMemData_EdgeShim
+{
+  SharedMemView<double*, DeviceShmem> rhs;
+  SharedMemView<double**, DeviceShmem> lhs;
+};
+
+/* AssembleEdgeSolverAlgorithm.h: same members the derived classes use; the loop
+ * shell (include/AssembleEdgeSolverAlgorithm.h:47-100) as a serial loop that
+ * records the local block where the reference hands it to the CoeffApplier */
+class AssembleEdgeSolverAlgorithm : public Algorithm
+{
+public:
+  using DblType = double;
+  using ShmemDataType = SharedMemData_EdgeShim;
+
+  AssembleEdgeSolverAlgorithm(
+    Realm& realm, stk::mesh::Part* part, EquationSystem* eqSystem)
+    : Algorithm(realm, part), eqSystem_(eqSystem), rhsSize_(2 * eqSystem->numDof_)
+  {
+  }
+  virtual ~AssembleEdgeSolverAlgorithm() = default;
+
+  template <typename LambdaFunction>
+  void run_algorithm(stk::mesh::BulkData&, LambdaFunction lambdaFunc)
+  {
+    auto& w = nwref::World::self();
+    const int n = rhsSize_;
+    std::vector<double> l((size_t)n * n), r(n);
+    ShmemDataType smdata;
+    smdata.lhs = SharedMemView<double**, DeviceShmem>(l.data(), n, n);
+    smdata.rhs = SharedMemView<double*, DeviceShmem>(r.data(), n);
+    for (long e = 0; e < w.nEdges; ++e) {
+      const stk::mesh::FastMeshIndex edge{0u, (unsigned)e};
+      const stk::mesh::FastMeshIndex nodeL{0u, (unsigned)w.edgeNodes[2 * e]};
+      const stk::mesh::FastMeshIndex nodeR{0u, (unsigned)w.edgeNodes[2 * e + 1]};
+      set_vals(smdata.rhs, 0.0);
+      set_vals(smdata.lhs, 0.0);
+      lambdaFunc(smdata, edge, nodeL, nodeR);
+      for (int i = 0; i < n * n; ++i)
+        w.lhsOut[(size_t)e * n * n + i] = l[i];
+      for (int i = 0; i < n; ++i)
+        w.rhsOut[(size_t)e * n + i] = r[i];
+    }
+  }
+
+  EquationSystem* eqSystem_;
+
+protected:
+  static constexpr stk::mesh::EntityRank entityRank_{stk::topology::EDGE_RANK};
+  static constexpr int nodesPerEntity_{2};
+  static constexpr int NDimMax_{3};
+  const int rhsSize_;
+};
+
+} // namespace nalu
+} // namespace sierra
+#endif

@@ -1,15 +1,32 @@
 /* oracle/ref_shim: TEST INFRASTRUCTURE.  Stand-in for <stk_mesh/base/FieldBase.hpp>:
- * the type names FieldTypeDef.h aliases; never instantiated here. */
+ * a named field handle (ordinal into the harness' field table). */
 #ifndef NW_REF_SHIM_STK_FIELDBASE_HPP
 #define NW_REF_SHIM_STK_FIELDBASE_HPP
-#include <cstdint>
-#include "Entity.hpp"
+#include <string>
+#include "Types.hpp"
 namespace stk {
 namespace mesh {
-typedef uint64_t EntityId;
-class FieldBase {};
+class FieldBase
+{
+public:
+  FieldBase() {}
+  FieldBase(const std::string& n, unsigned ord, int ncomp)
+    : name_(n), ordinal_(ord), ncomp_(ncomp)
+  {
+  }
+  const std::string& name() const { return name_; }
+  unsigned mesh_meta_data_ordinal() const { return ordinal_; }
+  int max_size() const { return ncomp_; }
+  std::string name_;
+  unsigned ordinal_ = InvalidOrdinal;
+  int ncomp_ = 0;
+};
 template <class T>
-class Field : public FieldBase {};
+class Field : public FieldBase
+{
+public:
+  using FieldBase::FieldBase;
+};
 } // namespace mesh
 } // namespace stk
 #endif

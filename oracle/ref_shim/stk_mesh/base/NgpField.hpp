@@ -1,10 +1,29 @@
-/* oracle/ref_shim: TEST INFRASTRUCTURE.  Stand-in for <stk_mesh/base/NgpField.hpp>. */
+/* oracle/ref_shim: TEST INFRASTRUCTURE.  Stand-in for stk::mesh::NgpField: a
+ * view of a plain [entity][component] array. */
 #ifndef NW_REF_SHIM_STK_NGPFIELD_HPP
 #define NW_REF_SHIM_STK_NGPFIELD_HPP
+#include "Types.hpp"
 namespace stk {
 namespace mesh {
 template <class T>
-class NgpField {};
+class NgpField
+{
+public:
+  NgpField() {}
+  NgpField(T* d, int nc) : data_(d), ncomp_(nc) {}
+  T& get(const FastMeshIndex& i, int c) const
+  {
+    return data_[(size_t)i.bucket_ord * ncomp_ + c];
+  }
+  T& operator()(const FastMeshIndex& i, int c) const { return get(i, c); }
+  void sync_to_device() const {}
+  void sync_to_host() const {}
+  void modify_on_device() const {}
+  void modify_on_host() const {}
+  void clear_sync_state() const {}
+  T* data_ = nullptr;
+  int ncomp_ = 0;
+};
 } // namespace mesh
 } // namespace stk
 #endif

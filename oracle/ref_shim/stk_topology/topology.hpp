@@ -36,6 +36,17 @@ struct topology
     SUPERFACE_START = 200,
     SUPERELEMENT_START = 300
   };
+  enum rank_t {
+    BEGIN_RANK = 0,
+    NODE_RANK = 0,
+    EDGE_RANK = 1,
+    FACE_RANK = 2,
+    ELEM_RANK = 3,
+    ELEMENT_RANK = 3,
+    CONSTRAINT_RANK = 4,
+    END_RANK = 5,
+    INVALID_RANK = 256
+  };
   topology_t m_value;
   constexpr topology() : m_value(INVALID_TOPOLOGY) {}
   constexpr topology(topology_t t) : m_value(t) {}

@@ -18,6 +18,11 @@ Output (all doubles as C99 hex strings, so the file holds the exact bits):
       checked to give the same bits before anything is written)
   peclet_classic / peclet_tanh / van_leer: argument tuples with the
       reference's return values
+and tests/golden/reference_edge_runs.npz: a 2x2x2-element warped two-phase case
+(27 nodes, 54 edges) with all inputs and, for the option matrices of
+tests/test_reference_edge_runs.py, the local lhs / rhs blocks of every edge as
+the reference's own MomentumEdgeSolverAlg / ScalarEdgeSolverAlg /
+ContinuityEdgeSolverAlg leave them, and MdotEdgeAlg's mass_flow_rate.
 """
 import ctypes as C
 import json
@@ -148,6 +153,14 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes;",
           {k: len(v["elements"]) for k, v in me.items()},
           len(classic), len(tanh), len(vl))
+
+    # the reference's own edge algorithms (oracle/ref_edge_driver.cpp) on a small
+    # two-phase case: inputs and the local blocks of every edge
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import test_reference_edge_runs as T
+    epath = os.path.join(HERE, "reference_edge_runs.npz")
+    print("wrote", epath, T.write_fixture(epath), os.path.getsize(epath), "bytes")
 
 
 if __name__ == "__main__":
