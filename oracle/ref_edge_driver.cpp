@@ -6,6 +6,9 @@
  *   ScalarEdgeSolverAlg      src/edge_kernels/ScalarEdgeSolverAlg.C
  *   ContinuityEdgeSolverAlg  src/edge_kernels/ContinuityEdgeSolverAlg.C
  *   MdotEdgeAlg              src/ngp_algorithms/MdotEdgeAlg.C
+ *   NodalGradEdgeAlg         src/ngp_algorithms/NodalGradEdgeAlg.C
+ *   MomentumEdgePecletAlg    src/edge_kernels/MomentumEdgePecletAlg.C
+ *   WallDistEdgeSolverAlg    src/edge_kernels/WallDistEdgeSolverAlg.C
  * (compiled unmodified from /root/reference, oracle/Makefile.ref) over the
  * stand-in Realm of oracle/ref_shim/nalu/RefHarness.h and call execute():
  * the per-edge arithmetic that runs is the reference's, the local 2x2 /
@@ -16,7 +19,10 @@
 #include <edge_kernels/MomentumEdgeSolverAlg.h>
 #include <edge_kernels/ScalarEdgeSolverAlg.h>
 #include <edge_kernels/ContinuityEdgeSolverAlg.h>
+#include <edge_kernels/WallDistEdgeSolverAlg.h>
+#include <edge_kernels/MomentumEdgePecletAlg.h>
 #include <ngp_algorithms/MdotEdgeAlg.h>
+#include <ngp_algorithms/NodalGradEdgeAlg.h>
 
 #include <cstring>
 #include <string>
@@ -176,6 +182,57 @@ ref_run_mdot()
     configure(realm);
     stk::mesh::Part part;
     MdotEdgeAlg alg(realm, &part);
+    alg.execute();
+  });
+}
+
+/* NodalGradEdgeAlg: adds into the nodal field `grad` (dim1 x ndim components;
+ * the caller zero-fills it, NodalGradAlgDriver::pre_work) */
+int
+ref_run_nodal_grad(const char* phi, const char* grad)
+{
+  return guarded([&] {
+    auto& w = World::self();
+    Realm realm;
+    configure(realm);
+    stk::mesh::Part part;
+    auto handle = [&](const char* n) {
+      return static_cast<stk::mesh::Field<double>*>(
+        w.fieldHandles.at(w.ordinal(n, stk::topology::NODE_RANK)));
+    };
+    ScalarNodalGradEdgeAlg alg(realm, &part, handle(phi), handle(grad));
+    alg.execute();
+  });
+}
+
+/* MomentumEdgePecletAlg: writes the edge fields peclet_number, peclet_factor */
+int
+ref_run_peclet()
+{
+  return guarded([&] {
+    auto& w = World::self();
+    Realm realm;
+    configure(realm);
+    EquationSystem eq(w.ndim);
+    stk::mesh::Part part;
+    MomentumEdgePecletAlg alg(realm, &part, &eq);
+    alg.execute();
+  });
+}
+
+/* WallDistEdgeSolverAlg: lhsOut[nEdges][2][2], rhsOut[nEdges][2] */
+int
+ref_run_wall_dist(double* lhsOut, double* rhsOut)
+{
+  return guarded([&] {
+    auto& w = World::self();
+    w.lhsOut = lhsOut;
+    w.rhsOut = rhsOut;
+    Realm realm;
+    configure(realm);
+    EquationSystem eq(1);
+    stk::mesh::Part part;
+    WallDistEdgeSolverAlg alg(realm, &part, &eq);
     alg.execute();
   });
 }

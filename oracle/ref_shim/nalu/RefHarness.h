@@ -4,10 +4,11 @@
  * Stand-ins for the parts of nalu-wind that surround the edge algorithms, so
  * that the reference's OWN source files
  *     src/edge_kernels/{Momentum,Scalar,Continuity}EdgeSolverAlg.C
- *     src/ngp_algorithms/MdotEdgeAlg.C
+ *     src/edge_kernels/{WallDistEdgeSolverAlg,MomentumEdgePecletAlg}.C
+ *     src/ngp_algorithms/{MdotEdgeAlg,NodalGradEdgeAlg}.C
  * compile unmodified, from where they lie, and their constructors and
- * execute() bodies -- the per-edge lambdas SURVEY.md 8(a) rows a1, a4, a5, a6
- * cite -- run here on arrays handed in from Python.
+ * execute() bodies -- the per-edge lambdas SURVEY.md 8(a) rows a1, a2, a4, a5, a6 and
+ * 8(f) rows 1, 3 cite -- run here on arrays handed in from Python.
  *
  * What is the reference's: every line of those four .C files and of the
  * headers they own (edge_kernels/*.h, ngp_algorithms/MdotEdgeAlg.h,
@@ -25,6 +26,7 @@
 #define NW_REF_HARNESS_H
 
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -108,7 +110,28 @@ public:
   {
     return nwref::World::self().fieldHandles;
   }
+  template <class T>
+  Field<T>* get_field(EntityRank rank, const std::string& name) const
+  {
+    const auto& w = nwref::World::self();
+    return static_cast<Field<T>*>(w.fieldHandles.at(w.ordinal(name, rank)));
+  }
 };
+/* one bucket holding every entity of a rank */
+class Bucket
+{
+public:
+  explicit Bucket(size_t n) : n_(n) {}
+  size_t size() const { return n_; }
+  Entity operator[](size_t k) const
+  {
+    Entity e;
+    e.m_value = k;
+    return e;
+  }
+  size_t n_;
+};
+typedef std::vector<const Bucket*> BucketVector;
 class BulkData
 {
 public:
@@ -117,7 +140,47 @@ public:
     static MetaData m;
     return m;
   }
+  const BucketVector& get_buckets(EntityRank rank, const Selector&) const
+  {
+    const auto& w = nwref::World::self();
+    bucket_[rank].reset(new Bucket(rank == stk::topology::EDGE_RANK ? w.nEdges : w.nNodes));
+    vec_[rank].assign(1, bucket_[rank].get());
+    return vec_[rank];
+  }
+  const Entity* begin_nodes(Entity edge) const
+  {
+    const auto& w = nwref::World::self();
+    nodes_[0].m_value = (uint64_t)w.edgeNodes[2 * edge.m_value];
+    nodes_[1].m_value = (uint64_t)w.edgeNodes[2 * edge.m_value + 1];
+    return nodes_;
+  }
+
+private:
+  mutable std::unique_ptr<Bucket> bucket_[4];
+  mutable BucketVector vec_[4];
+  mutable Entity nodes_[2];
 };
+inline Selector selectField(const FieldBase&) { return Selector(); }
+inline double*
+field_data(const FieldBase& f, Entity e)
+{
+  const auto& r = nwref::World::self().fields.at(f.mesh_meta_data_ordinal());
+  return r.data + (size_t)e.m_value * r.ncomp;
+}
+inline void
+field_fill(double v, const FieldBase& f)
+{
+  const auto& w = nwref::World::self();
+  const auto& r = w.fields.at(f.mesh_meta_data_ordinal());
+  const size_t n =
+    (size_t)(r.rank == stk::topology::EDGE_RANK ? w.nEdges : w.nNodes) * r.ncomp;
+  for (size_t i = 0; i < n; ++i)
+    r.data[i] = v;
+}
+inline void
+copy_owned_to_shared(const BulkData&, const std::vector<const FieldBase*>&)
+{
+}
 } // namespace mesh
 } // namespace stk
 
@@ -141,6 +204,12 @@ get_field_ordinal(
   /* only the NP1 state is ever asked for by the files compiled here */
   STK_ThrowRequireMsg(state == stk::mesh::StateNP1, "ref harness: state of " << name);
   return nwref::World::self().ordinal(name, rank);
+}
+
+inline unsigned
+max_extent(const stk::mesh::FieldBase& field, unsigned)
+{
+  return (unsigned)field.max_size();
 }
 
 namespace nalu_ngp {
@@ -180,6 +249,45 @@ run_edge_algorithm(
     f(info);
   }
 }
+
+/* ngp_utils/NgpFieldOps.h, edge_nodal_field_updater: the reference adds with
+ * Kokkos::atomic_add from a parallel loop; the serial loop here adds in edge
+ * order (what the oracle does, edge_oracle.cpp orc_nodal_grad_edge) */
+template <class Mesh, class Field>
+struct EdgeNodalUpdaterShim
+{
+  struct Ops
+  {
+    double& ref;
+    void operator=(const double& v) const { ref = v; }
+    void operator+=(const double& v) const { ref += v; }
+    void operator-=(const double& v) const { ref += -v; }
+  };
+  Ops operator()(const EntityInfo<Mesh>& einfo, unsigned ni, unsigned ic) const
+  {
+    const stk::mesh::FastMeshIndex i{0u, (unsigned)einfo.entityNodes[ni].m_value};
+    return Ops{fld.get(i, ic)};
+  }
+  Field fld;
+};
+template <class Mesh, class Field>
+EdgeNodalUpdaterShim<Mesh, Field>
+edge_nodal_field_updater(const Mesh&, const Field& fld)
+{
+  return EdgeNodalUpdaterShim<Mesh, Field>{fld};
+}
+
+/* ngp_utils/NgpMeshInfo.h */
+class MeshInfoShim
+{
+public:
+  const stk::mesh::MetaData& meta() const { return bulk_.mesh_meta_data(); }
+  const stk::mesh::NgpMesh& ngp_mesh() const { return mesh_; }
+  const FieldManager& ngp_field_manager() const { return fm_; }
+  stk::mesh::BulkData bulk_;
+  stk::mesh::NgpMesh mesh_;
+  FieldManager fm_;
+};
 } // namespace nalu_ngp
 
 class SolutionOptions
@@ -208,6 +316,7 @@ public:
   stk::mesh::BulkData& bulk_data() { return bulk_; }
   const stk::mesh::NgpMesh& ngp_mesh() const { return ngpMesh_; }
   const nalu_ngp::FieldManager& ngp_field_manager() const { return fm_; }
+  const nalu_ngp::MeshInfoShim& mesh_info() const { return meshInfo_; }
   std::string get_coordinates_name() const { return "coordinates"; }
   bool does_mesh_move() const { return false; }
   bool has_mesh_deformation() const { return w().get("mesh_deformation", 0.0) != 0.0; }
@@ -232,6 +341,7 @@ private:
   stk::mesh::BulkData bulk_;
   stk::mesh::NgpMesh ngpMesh_;
   nalu_ngp::FieldManager fm_;
+  nalu_ngp::MeshInfoShim meshInfo_;
 };
 
 class EquationSystem

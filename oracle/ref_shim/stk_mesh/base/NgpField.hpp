@@ -9,7 +9,9 @@ template <class T>
 class NgpField
 {
 public:
+  using value_type = T;
   NgpField() {}
+  stk::topology::rank_t get_rank() const { return stk::topology::NODE_RANK; }
   NgpField(T* d, int nc) : data_(d), ncomp_(nc) {}
   T& get(const FastMeshIndex& i, int c) const
   {

@@ -35,6 +35,8 @@ def lib():
         L.ref_run_momentum.argtypes = [vp, vp]
         L.ref_run_scalar.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, vp, vp]
         L.ref_run_continuity.argtypes = [vp, vp]
+        L.ref_run_wall_dist.argtypes = [vp, vp]
+        L.ref_run_nodal_grad.argtypes = [C.c_char_p, C.c_char_p]
         _L = L
     return _L
 
@@ -89,6 +91,21 @@ class World:
 
     def continuity(self):
         return self._run(lib().ref_run_continuity, 2)
+
+    def wall_dist(self):
+        return self._run(lib().ref_run_wall_dist, 2)
+
+    def nodal_grad(self, phi, grad):
+        """NodalGradEdgeAlg adds into the registered field `grad`"""
+        if lib().ref_run_nodal_grad(phi.encode(), grad.encode()):
+            raise RuntimeError(lib().ref_last_error().decode())
+        return self._keep[(grad, NODE)].copy()
+
+    def peclet_alg(self):
+        if lib().ref_run_peclet():
+            raise RuntimeError(lib().ref_last_error().decode())
+        return (self._keep[("peclet_number", EDGE)].ravel().copy(),
+                self._keep[("peclet_factor", EDGE)].ravel().copy())
 
     def mdot(self):
         if lib().ref_run_mdot():

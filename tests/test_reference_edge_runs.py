@@ -2,6 +2,7 @@
 
 oracle/Makefile.ref compiles src/edge_kernels/{Momentum,Scalar,Continuity}
 EdgeSolverAlg.C and src/ngp_algorithms/MdotEdgeAlg.C of the reference --
+(and NodalGradEdgeAlg.C, MomentumEdgePecletAlg.C, WallDistEdgeSolverAlg.C) --
 unmodified, from where they lie -- over stand-ins for Realm / STK / Kokkos
 (oracle/ref_shim; DESIGN.md section 4 says exactly what is the reference's and
 what is a stand-in).  Their constructors and execute() bodies, i.e. the per-edge
@@ -101,6 +102,7 @@ class State:
         self.source = rng.standard_normal((n, d))
         self.source_mask = (rng.random(n) > 0.3).astype(np.float64)
         self.efvm = 0.1 * rng.standard_normal(self.n_edges)
+        self.vol = 0.5 + rng.random(n)
 
     def world(self):
         d = self.ndim
@@ -124,6 +126,10 @@ class State:
         w.field("mass_vof_balanced_flow_rate", R.EDGE, self.mvof, 1)
         w.field("peclet_factor", R.EDGE, self.pecfac, 1)
         w.field("edge_face_velocity_mag", R.EDGE, self.efvm, 1)
+        w.field("dual_nodal_volume", R.NODE, self.vol, 1)
+        w.field("peclet_number", R.EDGE, np.zeros(self.n_edges), 1)
+        w.field("dpdx_new", R.NODE, np.zeros((self.n_nodes, d)), d)
+        w.field("dudx_new", R.NODE, np.zeros((self.n_nodes, d * d)), d * d)
         return w
 
 
@@ -273,6 +279,53 @@ def test_continuity_and_mdot_lambdas_bitwise(key, o, buoyancy, gcl):
     assert np.abs(mdot).max() > 0
 
 
+def ref_grads(st):
+    return (st.world().nodal_grad("pressure", "dpdx_new"),
+            st.world().nodal_grad("velocity", "dudx_new"))
+
+
+def orc_grads(st):
+    orc.set_num_threads(1)
+    d = st.ndim
+    return (orc.nodal_grad_edge(1, d, st.edges, st.pressure, st.area, st.vol, st.n_nodes),
+            orc.nodal_grad_edge(d, d, st.edges, st.velocity, st.area, st.vol, st.n_nodes))
+
+
+def ref_peclet_alg(st, pec):
+    w = st.world()
+    w.peclet(*pec)
+    return w.peclet_alg()
+
+
+def orc_peclet_alg(st, pec):
+    orc.set_num_threads(1)
+    return orc.peclet_edge(st.ndim, st.edges, st.coords, st.velocity, st.density,
+                           st.viscosity, orc.peclet(*pec))
+
+
+def orc_wall_dist(st):
+    orc.set_num_threads(1)
+    s = orc.RecordSink()
+    orc.wall_dist_edge(st.ndim, st.edges, st.coords, st.area, s)
+    return s.get()
+
+
+@live
+@pytest.mark.parametrize("key", ["3d", "2d"])
+def test_nodal_grad_peclet_alg_wall_dist_bitwise(key):
+    """NodalGradEdgeAlg (scalar -> vector, vector -> tensor; the serial edge
+    order of the stand-in loop is the oracle's), MomentumEdgePecletAlg with all
+    four blending functions, WallDistEdgeSolverAlg"""
+    st = state(key)
+    for got, want in zip(ref_grads(st), orc_grads(st)):
+        assert np.abs(got).max() > 0 and same_bits(got, want)
+    for pec in PECLETS:
+        (pn, pf), (opn, opf) = ref_peclet_alg(st, pec), orc_peclet_alg(st, pec)
+        assert np.array_equal(pn, opn) and np.array_equal(pf, opf), pec
+    (lhs, rhs), (ol, orh) = st.world().wall_dist(), orc_wall_dist(st)
+    assert same_bits(lhs, ol) and same_bits(rhs, orh)
+
+
 # ------------------------------ fixture -------------------------------------
 
 def _fixture():
@@ -284,7 +337,7 @@ def _fixture_state(z):
     st.ndim = int(z["ndim"])
     for k in ("edges", "coords", "velocity", "dudx", "dpdx", "dkdx", "area",
               "viscosity", "density", "pressure", "udiag", "tke", "dflux", "mask",
-              "mdot", "mvof", "pecfac", "source", "source_mask", "efvm"):
+              "mdot", "mvof", "pecfac", "source", "source_mask", "efvm", "vol"):
         setattr(st, k, np.ascontiguousarray(z["in_" + k]))
     st.n_nodes, st.n_edges = len(st.coords), len(st.edges)
     return st
@@ -318,6 +371,14 @@ def test_fixture_momentum_scalar_continuity_mdot():
             assert np.array_equal(orc_cont(st, o, bu, gcl, None), z[tag + "_mdot"]), tag
             n += 1
     assert n == 2 * len(MOM_POINTS) + len(SCAL_POINTS) * len(PECLETS) + 2 * len(CONT_POINTS)
+    gs, gv = orc_grads(st)
+    assert same_bits(gs, z["grad_scalar"]) and same_bits(gv, z["grad_vector"])
+    for j, pec in enumerate(PECLETS):
+        pn, pf = orc_peclet_alg(st, pec)
+        assert np.array_equal(pn, z["pecalg%d_number" % j])
+        assert np.array_equal(pf, z["pecalg%d_factor" % j])
+    ol, orh = orc_wall_dist(st)
+    assert same_bits(ol, z["walldist_lhs"]) and same_bits(orh, z["walldist_rhs"])
 
 
 @live
@@ -336,7 +397,7 @@ def write_fixture(path):
     out = {"ndim": np.int32(3)}
     for k in ("edges", "coords", "velocity", "dudx", "dpdx", "dkdx", "area",
               "viscosity", "density", "pressure", "udiag", "tke", "dflux", "mask",
-              "mdot", "mvof", "pecfac", "source", "source_mask", "efvm"):
+              "mdot", "mvof", "pecfac", "source", "source_mask", "efvm", "vol"):
         out["in_" + k] = getattr(st, k)
     for i, o in enumerate(MOM_POINTS):
         for vof in (False, True):
@@ -351,5 +412,9 @@ def write_fixture(path):
             tag = "cont%d_%d" % (i, j)
             out[tag + "_lhs"], out[tag + "_rhs"] = ref_cont_world(st, o, bu, gcl).continuity()
             out[tag + "_mdot"] = ref_cont_world(st, o, bu, gcl).mdot()
+    out["grad_scalar"], out["grad_vector"] = ref_grads(st)
+    for j, pec in enumerate(PECLETS):
+        out["pecalg%d_number" % j], out["pecalg%d_factor" % j] = ref_peclet_alg(st, pec)
+    out["walldist_lhs"], out["walldist_rhs"] = st.world().wall_dist()
     np.savez_compressed(path, **out)
     return st.n_nodes, st.n_edges
