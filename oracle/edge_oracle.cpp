@@ -6,6 +6,14 @@
  * relative to /root/reference.  Build: `make -C oracle` (g++ -O2
  * -ffp-contract=off so results are plain IEEE double, reproducible across
  * hosts).
+ *
+ * Pinned (a) to every golden vector the reference's unit tests hold for the
+ * path (tests/test_oracle_golds.py) and (b) to the reference's own edge
+ * algorithm, master-element and Peclet sources, compiled unmodified against
+ * stand-in Kokkos / STK / Realm headers and run in the build container
+ * (oracle/Makefile.ref -> oracle/_ref; tests/test_reference_edge_runs.py,
+ * tests/test_reference_runs.py): the kernels below reproduce the reference's
+ * per-edge blocks, edge fields, gradients and geometry bit for bit.
  */
 #include "edge_oracle.h"
 
