@@ -224,6 +224,11 @@ ref_van_leer(double dqm, double dqp, double eps)
 
 /* NaluEnv is declared by the reference (include/NaluEnv.h); its definition
  * (src/NaluEnv.C) needs MPI.  The master elements only use it to print. */
+/* rank / size as the stand-in world of the other drivers sets them */
+int g_nwref_rank = 0, g_nwref_size = 1;
+static int nwref_rank() { return g_nwref_rank; }
+static int nwref_size() { return g_nwref_size; }
+
 namespace sierra {
 namespace nalu {
 NaluEnv::NaluEnv() : parallelCommunicator_(0), pSize_(1), pRank_(0) {}
@@ -249,6 +254,10 @@ null_stream()
   return s;
 }
 } // namespace
+int NaluEnv::parallel_rank() { return nwref_rank(); }
+int NaluEnv::parallel_size() { return nwref_size(); }
+MPI_Comm NaluEnv::parallel_comm() { return 0; }
+double NaluEnv::nalu_time() { return 0.0; }
 std::ostream& NaluEnv::naluOutputP0() { return null_stream(); }
 std::ostream& NaluEnv::naluOutput() { return null_stream(); }
 } // namespace nalu

@@ -30,6 +30,8 @@
 using namespace sierra::nalu;
 using nwref::World;
 
+extern int g_nwref_rank, g_nwref_size; /* ref_driver.cpp: NaluEnv */
+
 namespace {
 std::string g_err;
 bool g_has_vof = false, g_buoyancy = false;
@@ -75,6 +77,8 @@ ref_world_reset(int ndim, long nNodes, long nEdges, const int* edgeNodes)
   w.nEdges = nEdges;
   w.edgeNodes = edgeNodes;
   g_has_vof = g_buoyancy = false;
+  g_nwref_rank = 0;
+  g_nwref_size = 1;
 }
 
 /* rank: 0 node, 1 edge; data[entity][ncomp] stays owned by the caller */

@@ -87,11 +87,27 @@ struct data_type<T[N]>
 };
 } // namespace shim
 
-/* row-major (LayoutRight) view; the property pack is accepted and ignored */
+namespace shim {
+template <class... P>
+struct has_layout_left : std::false_type {};
+template <class P0, class... P>
+struct has_layout_left<P0, P...>
+  : std::conditional_t<std::is_same<P0, LayoutLeft>::value, std::true_type, has_layout_left<P...>> {};
+} // namespace shim
+
+/* row-major view, column-major when LayoutLeft is among the properties; the
+ * rest of the property pack is accepted and ignored */
 template <class DataType, class... Props>
 class View
 {
 public:
+  using HostMirror = View;
+  using memory_space = HostSpace;
+  using execution_space = Serial;
+  using size_type = size_t;
+  static constexpr bool layout_left = shim::has_layout_left<Props...>::value;
+  std::string label() const { return "view"; }
+  bool is_allocated() const { return ptr_ != nullptr; }
   using value_type = typename shim::data_type<DataType>::value_type;
   using non_const_value_type = std::remove_const_t<value_type>;
   using pointer_type = value_type*;
@@ -128,10 +144,15 @@ public:
   KOKKOS_INLINE_FUNCTION value_type& operator()(I... idx) const
   {
     static_assert(sizeof...(I) == rank, "index count != rank");
-    const size_t ii[] = {static_cast<size_t>(idx)...};
+    const size_t ii[] = {static_cast<size_t>(idx)..., 0};
     size_t off = 0;
-    for (int d = 0; d < rank; ++d)
-      off = off * ext_[d] + ii[d];
+    if (layout_left) {
+      for (int d = rank - 1; d >= 0; --d)
+        off = off * ext_[d] + ii[d];
+    } else {
+      for (int d = 0; d < rank; ++d)
+        off = off * ext_[d] + ii[d];
+    }
     return ptr_[off];
   }
   KOKKOS_INLINE_FUNCTION value_type& operator[](size_t i) const { return ptr_[i]; }
@@ -218,6 +239,20 @@ parallel_for(const std::string&, const RangePolicy<P...>& r, const F& f)
   for (size_t i = r.b; i < r.e; ++i)
     f(i);
 }
+template <class... P, class F>
+void
+parallel_for(const RangePolicy<P...>& r, const F& f)
+{
+  for (size_t i = r.b; i < r.e; ++i)
+    f(i);
+}
+template <class F>
+void
+parallel_for(const std::string&, size_t n, const F& f)
+{
+  for (size_t i = 0; i < n; ++i)
+    f(i);
+}
 template <class... P, class F, class R>
 void
 parallel_reduce(const std::string&, const RangePolicy<P...>& r, const F& f, R& red)
@@ -245,6 +280,54 @@ deep_copy(const V& v, const typename V::non_const_value_type& x)
 {
   for (size_t i = 0; i < v.size(); ++i)
     v.data()[i] = x;
+}
+template <class D1, class... P1, class D2, class... P2>
+void
+deep_copy(const View<D1, P1...>& dst, const View<D2, P2...>& src)
+{
+  if ((const void*)dst.data() == (const void*)src.data())
+    return;
+  for (size_t i = 0; i < dst.size() && i < src.size(); ++i)
+    dst.data()[i] = src.data()[i];
+}
+/* host build: a mirror view is the view itself */
+template <class D, class... P>
+View<D, P...>
+create_mirror_view(const View<D, P...>& v)
+{
+  return v;
+}
+template <class Space, class D, class... P>
+View<D, P...>
+create_mirror_view(const Space&, const View<D, P...>& v)
+{
+  return v;
+}
+template <class T>
+inline void
+atomic_add(T* p, const T& v)
+{
+  *p += v;
+}
+template <class D, class... P>
+void
+resize(View<D, P...>& v, size_t n0 = 0, size_t n1 = 0, size_t n2 = 0)
+{
+  View<D, P...> w("resized", n0, n1, n2);
+  deep_copy(w, v);
+  v = w;
+}
+struct WithoutInitializing_t {};
+constexpr WithoutInitializing_t WithoutInitializing{};
+inline std::string
+view_alloc(WithoutInitializing_t, const std::string& s)
+{
+  return s;
+}
+inline std::string
+view_alloc(const std::string& s, WithoutInitializing_t)
+{
+  return s;
 }
 
 } // namespace Kokkos

@@ -25,8 +25,10 @@
 #ifndef NW_REF_HARNESS_H
 #define NW_REF_HARNESS_H
 
+#include <cstring>
 #include <map>
 #include <memory>
+#include <mpi.h>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -49,6 +51,7 @@ struct FieldRec
   int rank; /* stk::topology::NODE_RANK / EDGE_RANK */
   int ncomp;
   double* data;
+  int* idata = nullptr; /* integer fields (hypre_global_id, nalu_global_id) */
 };
 
 /* everything the stand-in Realm answers from */
@@ -63,6 +66,15 @@ struct World
   double gravity[3] = {0, 0, 0};
   int pecletForm = 0; /* 0 classic(hybridFactor = pecletA), 1 tanh(c1, c2) */
   double pecletA = 1.0, pecletB = 1.0;
+  /* parallel decomposition as seen by this "rank" (one process plays one
+   * rank at a time): STK identifier, owner and periodic master id per local
+   * node; the hypre row range of this rank */
+  int rank = 0, nranks = 1;
+  const long* nodeIdentifier = nullptr; /* [nNodes], STK global ids (1-based) */
+  const int* nodeOwner = nullptr;       /* [nNodes] */
+  std::map<long, long> nodeOfIdentifier;
+  long hypreILower = 0, hypreIUpper = 0, hypreNumNodes = 0;
+  std::vector<int> hypreOffsets;
   /* where run_algorithm records the local blocks */
   double* lhsOut = nullptr;
   double* rhsOut = nullptr;
@@ -106,6 +118,9 @@ public:
     static Part p;
     return p;
   }
+  Part& universal_part() const { return locally_owned_part(); }
+  Part& globally_shared_part() const { return locally_owned_part(); }
+  EntityRank side_rank() const { return stk::topology::FACE_RANK; }
   const std::vector<FieldBase*>& get_fields() const
   {
     return nwref::World::self().fieldHandles;
@@ -117,11 +132,13 @@ public:
     return static_cast<Field<T>*>(w.fieldHandles.at(w.ordinal(name, rank)));
   }
 };
-/* one bucket holding every entity of a rank */
+/* one bucket holding every entity of a rank: all nodes, or the locally-owned
+ * edges (the edge list handed in is the owned one) */
 class Bucket
 {
 public:
-  explicit Bucket(size_t n) : n_(n) {}
+  typedef size_t size_type;
+  Bucket(EntityRank r, size_t n) : rank_(r), n_(n) {}
   size_t size() const { return n_; }
   Entity operator[](size_t k) const
   {
@@ -129,7 +146,26 @@ public:
     e.m_value = k;
     return e;
   }
+  stk::topology topology() const
+  {
+    return rank_ == stk::topology::EDGE_RANK ? stk::topology::LINE_2
+                                             : stk::topology::NODE;
+  }
+  const Entity* begin_nodes(size_t k) const
+  {
+    const auto& w = nwref::World::self();
+    if (rank_ == stk::topology::EDGE_RANK) {
+      nodes_[0].m_value = (uint64_t)w.edgeNodes[2 * k];
+      nodes_[1].m_value = (uint64_t)w.edgeNodes[2 * k + 1];
+    } else {
+      nodes_[0].m_value = k;
+    }
+    return nodes_;
+  }
+  unsigned num_nodes(size_t) const { return rank_ == stk::topology::EDGE_RANK ? 2 : 1; }
+  EntityRank rank_;
   size_t n_;
+  mutable Entity nodes_[2];
 };
 typedef std::vector<const Bucket*> BucketVector;
 class BulkData
@@ -140,11 +176,19 @@ public:
     static MetaData m;
     return m;
   }
+  MPI_Comm parallel() const { return 0; }
+  int parallel_size() const { return nwref::World::self().nranks; }
+  int parallel_rank() const { return nwref::World::self().rank; }
+  /* nodes and edges only: there are no elements or faces in this mesh view */
   const BucketVector& get_buckets(EntityRank rank, const Selector&) const
   {
     const auto& w = nwref::World::self();
-    bucket_[rank].reset(new Bucket(rank == stk::topology::EDGE_RANK ? w.nEdges : w.nNodes));
-    vec_[rank].assign(1, bucket_[rank].get());
+    vec_[rank].clear();
+    if (rank == stk::topology::EDGE_RANK || rank == stk::topology::NODE_RANK) {
+      bucket_[rank].reset(new Bucket(
+        rank, rank == stk::topology::EDGE_RANK ? w.nEdges : w.nNodes));
+      vec_[rank].push_back(bucket_[rank].get());
+    }
     return vec_[rank];
   }
   const Entity* begin_nodes(Entity edge) const
@@ -154,18 +198,72 @@ public:
     nodes_[1].m_value = (uint64_t)w.edgeNodes[2 * edge.m_value + 1];
     return nodes_;
   }
+  unsigned num_nodes(Entity) const { return 2; }
+  unsigned num_elements(Entity) const { return 0; }
+  const Entity* begin_elements(Entity) const { return nullptr; }
+  EntityId identifier(Entity node) const
+  {
+    const auto& w = nwref::World::self();
+    return w.nodeIdentifier ? (EntityId)w.nodeIdentifier[node.m_value]
+                            : (EntityId)node.m_value + 1;
+  }
+  Entity get_entity(EntityRank, EntityId id) const
+  {
+    const auto& w = nwref::World::self();
+    Entity e;
+    if (!w.nodeIdentifier) {
+      e.m_value = id - 1;
+      return e;
+    }
+    auto it = w.nodeOfIdentifier.find((long)id);
+    e.m_value = it == w.nodeOfIdentifier.end() ? ~uint64_t(0) : (uint64_t)it->second;
+    return e;
+  }
+  bool is_valid(Entity e) const { return e.m_value != ~uint64_t(0); }
+  int parallel_owner_rank(Entity node) const
+  {
+    const auto& w = nwref::World::self();
+    return w.nodeOwner ? w.nodeOwner[node.m_value] : w.rank;
+  }
 
 private:
-  mutable std::unique_ptr<Bucket> bucket_[4];
-  mutable BucketVector vec_[4];
+  mutable std::unique_ptr<Bucket> bucket_[6];
+  mutable BucketVector vec_[6];
   mutable Entity nodes_[2];
 };
+class Ghosting
+{
+};
+inline void
+communicate_field_data(const Ghosting&, const std::vector<const FieldBase*>&)
+{
+}
 inline Selector selectField(const FieldBase&) { return Selector(); }
 inline double*
 field_data(const FieldBase& f, Entity e)
 {
   const auto& r = nwref::World::self().fields.at(f.mesh_meta_data_ordinal());
   return r.data + (size_t)e.m_value * r.ncomp;
+}
+inline double*
+field_data(const Field<double>& f, Entity e)
+{
+  return field_data(static_cast<const FieldBase&>(f), e);
+}
+inline int*
+field_data(const Field<int>& f, Entity e)
+{
+  const auto& r = nwref::World::self().fields.at(f.mesh_meta_data_ordinal());
+  return r.idata + (size_t)e.m_value * r.ncomp;
+}
+/* nalu_global_id is a Field<EntityId>; kept as int here */
+inline EntityId*
+field_data(const Field<EntityId>& f, Entity e)
+{
+  static thread_local EntityId v;
+  const auto& r = nwref::World::self().fields.at(f.mesh_meta_data_ordinal());
+  v = (EntityId)r.idata[(size_t)e.m_value * r.ncomp];
+  return &v;
 }
 inline void
 field_fill(double v, const FieldBase& f)
@@ -221,7 +319,10 @@ public:
   stk::mesh::NgpField<T> get_field(unsigned ord) const
   {
     const auto& f = nwref::World::self().fields.at(ord);
-    return stk::mesh::NgpField<T>(f.data, f.ncomp);
+    if constexpr (std::is_same<T, double>::value)
+      return stk::mesh::NgpField<T>(f.data, f.ncomp);
+    else
+      return stk::mesh::NgpField<T>(reinterpret_cast<T*>(f.idata), f.ncomp);
   }
 };
 
@@ -248,6 +349,24 @@ run_edge_algorithm(
     info.entityNodes[1].m_value = (uint64_t)w.edgeNodes[2 * e + 1];
     f(info);
   }
+}
+
+/* ngp_utils/NgpTypes.h, NgpLoopUtils.h: node loop */
+template <class Mesh = stk::mesh::NgpMesh>
+struct NGPMeshTraits
+{
+  using MeshIndex = stk::mesh::FastMeshIndex;
+};
+template <class Mesh, class Lambda>
+void
+run_entity_algorithm(
+  const std::string&, const Mesh&, stk::topology::rank_t rank,
+  const stk::mesh::Selector&, const Lambda& f)
+{
+  const auto& w = nwref::World::self();
+  const long n = rank == stk::topology::EDGE_RANK ? w.nEdges : w.nNodes;
+  for (long i = 0; i < n; ++i)
+    f(stk::mesh::FastMeshIndex{0u, (unsigned)i});
 }
 
 /* ngp_utils/NgpFieldOps.h, edge_nodal_field_updater: the reference adds with
@@ -308,11 +427,61 @@ public:
   std::string get_coordinates_name() const { return "coordinates"; }
 };
 
+class OversetInfo;
+class OversetManager
+{
+public:
+  stk::mesh::Ghosting* oversetGhosting_ = nullptr;
+  std::vector<OversetInfo*> oversetInfoVec_;
+};
+class OversetInfo
+{
+public:
+  stk::mesh::Entity orphanNode_;
+  stk::mesh::Entity owningElement_;
+};
+class NonConformalManager
+{
+public:
+  stk::mesh::Ghosting* nonConformalGhosting_ = nullptr;
+};
+
 class Realm
 {
 public:
-  Realm() : solutionOptions_(&so_) {}
-  const stk::mesh::MetaData& meta_data() const { return bulk_.mesh_meta_data(); }
+  Realm() : solutionOptions_(&so_)
+  {
+    const auto& w = nwref::World::self();
+    hypreILower_ = (HypreIntType)w.hypreILower;
+    hypreIUpper_ = (HypreIntType)w.hypreIUpper;
+    hypreNumNodes_ = (HypreIntType)w.hypreNumNodes;
+    hypreOffsets_.assign(w.hypreOffsets.begin(), w.hypreOffsets.end());
+    for (size_t i = 0; i < w.fields.size(); ++i) {
+      if (w.fields[i].name == "hypre_global_id")
+        hypreGlobalId_ = static_cast<HypreIDFieldType*>(w.fieldHandles[i]);
+      if (w.fields[i].name == "nalu_global_id")
+        naluGlobalId_ = static_cast<GlobalIdFieldType*>(w.fieldHandles[i]);
+    }
+  }
+  stk::mesh::MetaData& meta_data() const
+  {
+    return const_cast<stk::mesh::MetaData&>(bulk_.mesh_meta_data());
+  }
+  const stk::mesh::BucketVector&
+  get_buckets(stk::mesh::EntityRank rank, const stk::mesh::Selector& s) const
+  {
+    return bulk_.get_buckets(rank, s);
+  }
+  stk::mesh::PartVector get_slave_part_vector() const { return stk::mesh::PartVector(); }
+  HypreIDFieldType* hypreGlobalId_ = nullptr;
+  GlobalIdFieldType* naluGlobalId_ = nullptr;
+  HypreIntType hypreILower_ = 0, hypreIUpper_ = 0, hypreNumNodes_ = 0;
+  std::vector<HypreIntType> hypreOffsets_;
+  OversetManager* oversetManager_ = nullptr;
+  NonConformalManager* nonConformalManager_ = nullptr;
+  bool isFinalOuterIter_ = false;
+  double l2Scaling_ = 1.0;
+  bool hasPeriodic_ = false;
   stk::mesh::BulkData& bulk_data() { return bulk_; }
   const stk::mesh::NgpMesh& ngp_mesh() const { return ngpMesh_; }
   const nalu_ngp::FieldManager& ngp_field_manager() const { return fm_; }
@@ -358,6 +527,10 @@ public:
     return new TanhFunction<T>((T)w.pecletA, (T)w.pecletB);
   }
   int numDof_;
+  std::string name_ = "EqSys";
+  std::string userSuppliedName_ = "EqSys";
+  int linsysWriteCounter_ = 0;
+  bool firstTimeStepSolve_ = true;
 };
 
 /* Algorithm.h */

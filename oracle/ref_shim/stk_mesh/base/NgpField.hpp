@@ -18,6 +18,11 @@ public:
     return data_[(size_t)i.bucket_ord * ncomp_ + c];
   }
   T& operator()(const FastMeshIndex& i, int c) const { return get(i, c); }
+  template <class Mesh>
+  T& get(const Mesh&, const Entity& e, int c) const
+  {
+    return data_[(size_t)e.m_value * ncomp_ + c];
+  }
   void sync_to_device() const {}
   void sync_to_host() const {}
   void modify_on_device() const {}
