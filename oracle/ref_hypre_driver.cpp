@@ -14,6 +14,9 @@
  */
 #include <HypreLinearSystem.h>
 #include <HypreUVWLinearSystem.h>
+#include <edge_kernels/MomentumEdgeSolverAlg.h>
+#include <edge_kernels/ScalarEdgeSolverAlg.h>
+#include <edge_kernels/ContinuityEdgeSolverAlg.h>
 
 #include <cstring>
 #include <memory>
@@ -271,6 +274,58 @@ ref_hypre_assemble(void* p, const double* lhs, const double* rhs, int n)
       SharedMemView<const double**, DeviceShmem> lv(lhs + (size_t)e * n * n, n, n);
       (*dev)(2, cn, idv, pv, rv, lv, "ref_hypre_assemble");
     }
+  });
+}
+
+/* One assembly as the reference runs it: zeroSystem, get_coeff_applier, the
+ * edge algorithm's execute() whose shell hands every local block straight to
+ * the reference's CoeffApplier (no recording), loadComplete.  alg: 0 momentum
+ * (system created with numDof = ndim, UVW or monolithic), 1 continuity,
+ * 2 scalar (q, dqdx, dflux name the fields).  For timing the reference's own
+ * code (tools/cpu_reference_code_timing.py) and as an end-to-end check. */
+int
+ref_hypre_sweep(void* p, int alg, const char* q, const char* dqdx, const char* dflux)
+{
+  auto* h = static_cast<Handle*>(p);
+  return guarded([&] {
+    auto& w = World::self();
+    h->ls().zeroSystem();
+    auto* dev = dynamic_cast<HypreLinearSystem::HypreLinSysCoeffApplier*>(
+      h->ls().get_coeff_applier());
+    const int nmax = 2 * 3;
+    std::vector<int> ids(nmax), perm(nmax);
+    stk::mesh::Entity nodes[2];
+    w.applyHook = [&](long e, const double* lhs, const double* rhs, int n) {
+      nodes[0].m_value = (uint64_t)w.edgeNodes[2 * e];
+      nodes[1].m_value = (uint64_t)w.edgeNodes[2 * e + 1];
+      stk::mesh::NgpMesh::ConnectedNodes cn(nodes, 2);
+      SharedMemView<int*, DeviceShmem> idv(ids.data(), n), pv(perm.data(), n);
+      SharedMemView<const double*, DeviceShmem> rv(rhs, n);
+      SharedMemView<const double**, DeviceShmem> lv(lhs, n, n);
+      (*dev)(2, cn, idv, pv, rv, lv, "ref_hypre_sweep");
+    };
+    try {
+      auto handle = [&](const char* nm) {
+        return static_cast<stk::mesh::Field<double>*>(
+          w.fieldHandles.at(w.ordinal(nm, stk::topology::NODE_RANK)));
+      };
+      if (alg == 0) {
+        MomentumEdgeSolverAlg a(h->realm, &h->part, &h->eq);
+        a.execute();
+      } else if (alg == 1) {
+        ContinuityEdgeSolverAlg a(h->realm, &h->part, &h->eq);
+        a.execute();
+      } else {
+        ScalarEdgeSolverAlg a(
+          h->realm, &h->part, &h->eq, handle(q), handle(dqdx), handle(dflux));
+        a.execute();
+      }
+    } catch (...) {
+      w.applyHook = nullptr;
+      throw;
+    }
+    w.applyHook = nullptr;
+    h->ls().loadComplete();
   });
 }
 

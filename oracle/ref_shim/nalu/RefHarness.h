@@ -26,6 +26,7 @@
 #define NW_REF_HARNESS_H
 
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mpi.h>
@@ -78,6 +79,9 @@ struct World
   /* where run_algorithm records the local blocks */
   double* lhsOut = nullptr;
   double* rhsOut = nullptr;
+  /* ... or, when set, hands them on (to the reference's own CoeffApplier,
+   * oracle/ref_hypre_driver.cpp: ref_hypre_sweep) as the reference's shell does */
+  std::function<void(long, const double*, const double*, int)> applyHook;
 
   static World& self()
   {
@@ -583,6 +587,10 @@ public:
       set_vals(smdata.rhs, 0.0);
       set_vals(smdata.lhs, 0.0);
       lambdaFunc(smdata, edge, nodeL, nodeR);
+      if (w.applyHook) {
+        w.applyHook(e, l.data(), r.data(), n);
+        continue;
+      }
       for (int i = 0; i < n * n; ++i)
         w.lhsOut[(size_t)e * n * n + i] = l[i];
       for (int i = 0; i < n; ++i)

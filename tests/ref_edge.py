@@ -140,6 +140,7 @@ class HypreRef:
         L.ref_hypre_graph.argtypes = [vp] * 7
         L.ref_hypre_assemble.argtypes = [vp, vp, vp, C.c_int]
         L.ref_hypre_values.argtypes = [vp, vp, vp]
+        L.ref_hypre_sweep.argtypes = [vp, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p]
         L.ref_hypre_rhs_shape.argtypes = [vp, vp]
         L.ref_hypre_ij_calls.argtypes = [vp, C.c_int]
         L.ref_hypre_ij_call_sizes.argtypes = [vp, C.c_int, C.c_int, vp]
@@ -201,6 +202,23 @@ class HypreRef:
         rhs = np.ascontiguousarray(rhs, dtype=np.float64)
         n = rhs.shape[1]
         self._chk(lib().ref_hypre_assemble(self.h, lhs.ctypes.data, rhs.ctypes.data, n))
+        sh = (C.c_long * 3)()
+        lib().ref_hypre_rhs_shape(self.h, sh)
+        vals = np.zeros(sh[2])
+        r = np.zeros((sh[1], sh[0]))
+        lib().ref_hypre_values(self.h, vals.ctypes.data, r.ctypes.data)
+        return vals, r
+
+    def sweep(self, alg, q="", dqdx="", dflux=""):
+        """one assembly as the reference runs it (zeroSystem, the edge
+        algorithm's execute() feeding the reference's CoeffApplier,
+        loadComplete); alg: 'momentum' | 'continuity' | 'scalar'"""
+        k = {"momentum": 0, "continuity": 1, "scalar": 2}[alg]
+        self._chk(lib().ref_hypre_sweep(self.h, k, q.encode(), dqdx.encode(),
+                                        dflux.encode()))
+        return self.values()
+
+    def values(self):
         sh = (C.c_long * 3)()
         lib().ref_hypre_rhs_shape(self.h, sh)
         vals = np.zeros(sh[2])

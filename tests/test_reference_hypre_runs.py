@@ -208,3 +208,41 @@ def test_momentum_systems(system, tag, dims, nranks, periodic):
         assert np.array_equal(r.reshape(orh.shape) if r.size == orh.size else r, orh)
         check_handoff(h, g, vals, r)
         h.close()
+
+
+def _momentum_options(w, o):
+    for k, v in (("divU", o["include_divu"]), ("alpha:velocity", o["alpha"]),
+                 ("alpha_upw:velocity", o["alpha_upw"]), ("upw:velocity", o["ho_upwind"]),
+                 ("relax:velocity", o["relax_fac"]),
+                 ("limiter:velocity", 1.0 if o["use_limiter"] else 0.0)):
+        w.option(k, v)
+
+
+@pytest.mark.parametrize("system", ["monolithic", "uvw"])
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_end_to_end_reference_assembly(system, nranks):
+    """the path as the reference runs it, nothing recorded in between:
+    zeroSystem, MomentumEdgeSolverAlg::execute whose loop shell hands every
+    local block to the reference's CoeffApplier, loadComplete -- against the
+    oracle's momentum kernel + sink, with the bench's (decks') options"""
+    uvw = system == "uvw"
+    o = T.MOM_POINTS[1]
+    for rank in range(nranks):
+        rc = RankCase((4, 3, 6), nranks, rank, (True, False))
+        st = rc.st
+        w = st.world()
+        _momentum_options(w, o)
+        b = rc.b
+        h = R.HypreRef(w, b.own_hid, uvw=uvw, num_dof=3, rank=rank, nranks=nranks,
+                       node_identifier=rc.ident, node_owner=b.owner,
+                       nalu_id=rc.nalu, offsets=b.offsets)
+        vals, r = h.sweep("momentum")
+        g = rc.oracle_graph(1 if uvw else 3)
+        s = orc.HypreSink(g, b.hid, uvw_ndim=3 if uvw else 0)
+        orc.set_num_threads(1)
+        orc.momentum_edge(3, st.edges, st.coords, st.velocity, st.dudx, st.viscosity,
+                          st.density, st.mask, st.area, st.mdot, st.pecfac, s, **o)
+        ov, orh = s.get()
+        assert np.array_equal(vals, ov)
+        assert np.array_equal(r.ravel(), np.asarray(orh).ravel())
+        h.close()
