@@ -329,6 +329,46 @@ ref_hypre_sweep(void* p, int alg, const char* q, const char* dqdx, const char* d
   });
 }
 
+/* CoeffApplier::resetRows (FixPressureAtNodeAlgorithm, include/LinearSystem.h:53-60)
+ * on the system as it stands after ref_hypre_assemble */
+int
+ref_hypre_reset_rows(void* p, const int* nodes, int n, double diag, double rhs)
+{
+  auto* h = static_cast<Handle*>(p);
+  return guarded([&] {
+    std::vector<stk::mesh::Entity> v(n);
+    for (int i = 0; i < n; ++i)
+      v[i].m_value = (uint64_t)nodes[i];
+    h->app()->resetRows((unsigned)n, v.data(), 0, h->numDof, diag, rhs);
+  });
+}
+
+/* HypreLinearSystem::applyDirichletBCs over the given nodes (the part selector
+ * of the reference becomes a node list) */
+int
+ref_hypre_apply_dirichlet(
+  void* p, const char* solution, const char* bcValues, const int* nodes, int n)
+{
+  auto* h = static_cast<Handle*>(p);
+  return guarded([&] {
+    auto& w = World::self();
+    w.nodeSelected.assign((size_t)w.nNodes, 0);
+    for (int i = 0; i < n; ++i)
+      w.nodeSelected[nodes[i]] = 1;
+    auto handle = [&](const char* nm) {
+      return w.fieldHandles.at(w.ordinal(nm, stk::topology::NODE_RANK));
+    };
+    stk::mesh::PartVector parts(1, &h->part);
+    try {
+      h->ls().applyDirichletBCs(handle(solution), handle(bcValues), parts, 0, h->numDof);
+    } catch (...) {
+      w.nodeSelected.clear();
+      throw;
+    }
+    w.nodeSelected.clear();
+  });
+}
+
 /* values[nnzOwned + nnzShared]; rhs[nrhs][numRowsOwned + numRowsShared rows x
  * numDof] as the applier holds them (rhs_dev_ is LayoutLeft: one column per
  * right-hand side) */

@@ -76,6 +76,8 @@ struct World
   std::map<long, long> nodeOfIdentifier;
   long hypreILower = 0, hypreIUpper = 0, hypreNumNodes = 0;
   std::vector<int> hypreOffsets;
+  /* node selector of run_entity_algorithm (empty: every node) */
+  std::vector<char> nodeSelected;
   /* where run_algorithm records the local blocks */
   double* lhsOut = nullptr;
   double* rhsOut = nullptr;
@@ -369,8 +371,10 @@ run_entity_algorithm(
 {
   const auto& w = nwref::World::self();
   const long n = rank == stk::topology::EDGE_RANK ? w.nEdges : w.nNodes;
+  const bool sel = rank == stk::topology::NODE_RANK && !w.nodeSelected.empty();
   for (long i = 0; i < n; ++i)
-    f(stk::mesh::FastMeshIndex{0u, (unsigned)i});
+    if (!sel || w.nodeSelected[i])
+      f(stk::mesh::FastMeshIndex{0u, (unsigned)i});
 }
 
 /* ngp_utils/NgpFieldOps.h, edge_nodal_field_updater: the reference adds with

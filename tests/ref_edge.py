@@ -140,6 +140,8 @@ class HypreRef:
         L.ref_hypre_graph.argtypes = [vp] * 7
         L.ref_hypre_assemble.argtypes = [vp, vp, vp, C.c_int]
         L.ref_hypre_values.argtypes = [vp, vp, vp]
+        L.ref_hypre_reset_rows.argtypes = [vp, vp, C.c_int, C.c_double, C.c_double]
+        L.ref_hypre_apply_dirichlet.argtypes = [vp, C.c_char_p, C.c_char_p, vp, C.c_int]
         L.ref_hypre_sweep.argtypes = [vp, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p]
         L.ref_hypre_rhs_shape.argtypes = [vp, vp]
         L.ref_hypre_ij_calls.argtypes = [vp, C.c_int]
@@ -216,6 +218,18 @@ class HypreRef:
         k = {"momentum": 0, "continuity": 1, "scalar": 2}[alg]
         self._chk(lib().ref_hypre_sweep(self.h, k, q.encode(), dqdx.encode(),
                                         dflux.encode()))
+        return self.values()
+
+    def reset_rows(self, nodes, diag_value, rhs_residual):
+        nd = np.ascontiguousarray(nodes, dtype=np.int32)
+        self._chk(lib().ref_hypre_reset_rows(self.h, nd.ctypes.data, len(nd),
+                                             float(diag_value), float(rhs_residual)))
+        return self.values()
+
+    def apply_dirichlet(self, solution, bc_values, nodes):
+        nd = np.ascontiguousarray(nodes, dtype=np.int32)
+        self._chk(lib().ref_hypre_apply_dirichlet(
+            self.h, solution.encode(), bc_values.encode(), nd.ctypes.data, len(nd)))
         return self.values()
 
     def values(self):

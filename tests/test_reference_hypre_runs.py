@@ -246,3 +246,42 @@ def test_end_to_end_reference_assembly(system, nranks):
         assert np.array_equal(vals, ov)
         assert np.array_equal(r.ravel(), np.asarray(orh).ravel())
         h.close()
+
+
+@pytest.mark.parametrize("tag,dims,nranks,periodic", CASES[:2] + CASES[3:4],
+                         ids=[c[0] for c in CASES[:2] + CASES[3:4]])
+def test_reset_rows_and_dirichlet_bcs(tag, dims, nranks, periodic):
+    """CoeffApplier::resetRows (FixPressureAtNode) and applyDirichletBCs of the
+    reference on an assembled system, against the oracle's sink"""
+    for rank in range(nranks):
+        rc = RankCase(dims, nranks, rank, periodic)
+        st, b = rc.st, rc.b
+        z = st.coords[:, 2]
+        owned = (b.owner == rank) & ~rc.slave
+        wall = np.nonzero((z <= z.min() + 1e-9) & owned)[0][::2].astype(np.int32)
+        lhs, rhs = T.ref_scalar(st, T.SCAL_POINTS[1], T.PECLETS[0])
+        rng = np.random.default_rng(9)
+        bc = rng.standard_normal(st.n_nodes)
+        w = st.world()
+        w.field("tke_bc", R.NODE, bc, 1)
+        h = R.HypreRef(w, b.own_hid, rank=rank, nranks=nranks, node_identifier=rc.ident,
+                       node_owner=b.owner, nalu_id=rc.nalu, offsets=b.offsets,
+                       dirichlet_nodes=wall)
+        g = rc.oracle_graph(skipped_nodes=wall)
+        s = orc.HypreSink(g, b.hid)
+        h.assemble(lhs, rhs)
+        s.apply(st.edges, lhs, rhs)
+        # FixPressureAtNode-style reset of a few rows: any node this rank holds,
+        # owned or shared
+        some = np.arange(st.n_nodes)[3::7].astype(np.int32)
+        vals, r = h.reset_rows(some, 2.5, -0.75)
+        s.reset_rows(some, 2.5, -0.75)
+        ov, orh = s.get()
+        assert np.array_equal(vals, ov) and np.array_equal(r.ravel(), np.asarray(orh).ravel())
+        if len(wall):
+            vals, r = h.apply_dirichlet("turbulent_ke", "tke_bc", wall)
+            s.apply_dirichlet(wall, st.tke, bc)
+            ov, orh = s.get()
+            assert np.array_equal(vals, ov)
+            assert np.array_equal(r.ravel(), np.asarray(orh).ravel())
+        h.close()
