@@ -9,6 +9,10 @@
  *   NodalGradEdgeAlg         src/ngp_algorithms/NodalGradEdgeAlg.C
  *   MomentumEdgePecletAlg    src/edge_kernels/MomentumEdgePecletAlg.C
  *   WallDistEdgeSolverAlg    src/edge_kernels/WallDistEdgeSolverAlg.C
+ *   {Scalar,Momentum,Continuity}MassBDFNodeKernel, WallDistNodeKernel
+ *                            src/node_kernels/*.C (setup + execute per node;
+ *                            the shell AssembleNGPNodeSolverAlgorithm.C:85-146
+ *                            is the serial loop of run_node_kernel below)
  * (compiled unmodified from /root/reference, oracle/Makefile.ref) over the
  * stand-in Realm of oracle/ref_shim/nalu/RefHarness.h and call execute():
  * the per-edge arithmetic that runs is the reference's, the local 2x2 /
@@ -23,6 +27,10 @@
 #include <edge_kernels/MomentumEdgePecletAlg.h>
 #include <ngp_algorithms/MdotEdgeAlg.h>
 #include <ngp_algorithms/NodalGradEdgeAlg.h>
+#include <node_kernels/ScalarMassBDFNodeKernel.h>
+#include <node_kernels/MomentumMassBDFNodeKernel.h>
+#include <node_kernels/ContinuityMassBDFNodeKernel.h>
+#include <node_kernels/WallDistNodeKernel.h>
 
 #include <cstring>
 #include <string>
@@ -238,6 +246,50 @@ ref_run_wall_dist(double* lhsOut, double* rhsOut)
     stk::mesh::Part part;
     WallDistEdgeSolverAlg alg(realm, &part, &eq);
     alg.execute();
+  });
+}
+
+/* node kernels: which = 0 ScalarMassBDF(q), 1 MomentumMassBDF, 2 ContinuityMassBDF,
+ * 3 WallDist; lhsOut[nNodes][n][n], rhsOut[nNodes][n] with n = numDof.  Time
+ * states of a field F are the registered fields F, F_n, F_nm1. */
+int
+ref_run_node_kernel(int which, const char* q, double* lhsOut, double* rhsOut)
+{
+  return guarded([&] {
+    auto& w = World::self();
+    Realm realm;
+    configure(realm);
+    const int n = which == 1 ? w.ndim : 1;
+    std::vector<double> l((size_t)n * n), r(n);
+    NodeKernelTraits::LhsType lhs(l.data(), n, n);
+    NodeKernelTraits::RhsType rhs(r.data(), n);
+    auto run = [&](NodeKernel& k) {
+      k.setup(realm);
+      for (long i = 0; i < w.nNodes; ++i) {
+        set_vals(rhs, 0.0);
+        set_vals(lhs, 0.0);
+        k.execute(lhs, rhs, stk::mesh::FastMeshIndex{0u, (unsigned)i});
+        for (int j = 0; j < n * n; ++j)
+          lhsOut[(size_t)i * n * n + j] = l[j];
+        for (int j = 0; j < n; ++j)
+          rhsOut[(size_t)i * n + j] = r[j];
+      }
+    };
+    if (which == 0) {
+      auto* f = static_cast<stk::mesh::Field<double>*>(
+        w.fieldHandles.at(w.ordinal(q, stk::topology::NODE_RANK)));
+      ScalarMassBDFNodeKernel k(realm.bulk_data(), f);
+      run(k);
+    } else if (which == 1) {
+      MomentumMassBDFNodeKernel k(realm.bulk_data());
+      run(k);
+    } else if (which == 2) {
+      ContinuityMassBDFNodeKernel k(realm.bulk_data());
+      run(k);
+    } else {
+      WallDistNodeKernel k(realm.bulk_data());
+      run(k);
+    }
   });
 }
 

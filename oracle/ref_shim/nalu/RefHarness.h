@@ -102,6 +102,17 @@ struct World
     auto it = opt.find(key);
     return it == opt.end() ? dflt : it->second;
   }
+  bool has(const std::string& name, int rank) const
+  {
+    for (const auto& f : fields)
+      if (f.name == name && f.rank == rank)
+        return true;
+    return false;
+  }
+  static std::string state_name(const std::string& name, int state)
+  {
+    return state == 0 ? name : name + (state == 1 ? "_n" : "_nm1");
+  }
   unsigned ordinal(const std::string& name, int rank) const
   {
     for (size_t i = 0; i < fields.size(); ++i)
@@ -288,6 +299,26 @@ copy_owned_to_shared(const BulkData&, const std::vector<const FieldBase*>&)
 } // namespace mesh
 } // namespace stk
 
+namespace stk {
+namespace mesh {
+inline unsigned
+FieldBase::number_of_states() const
+{
+  const auto& w = nwref::World::self();
+  const int rank = w.fields.at(ordinal_).rank;
+  return 1u + (w.has(name_ + "_n", rank) ? 1u : 0u) +
+         (w.has(name_ + "_nm1", rank) ? 1u : 0u);
+}
+inline FieldBase&
+FieldBase::field_of_state(FieldState s) const
+{
+  const auto& w = nwref::World::self();
+  const int rank = w.fields.at(ordinal_).rank;
+  return *w.fieldHandles.at(w.ordinal(nwref::World::state_name(name_, s), rank));
+}
+} // namespace mesh
+} // namespace stk
+
 namespace sierra {
 namespace nalu {
 
@@ -305,9 +336,7 @@ get_field_ordinal(
   const stk::mesh::FieldState state,
   const stk::mesh::EntityRank rank = stk::topology::NODE_RANK)
 {
-  /* only the NP1 state is ever asked for by the files compiled here */
-  STK_ThrowRequireMsg(state == stk::mesh::StateNP1, "ref harness: state of " << name);
-  return nwref::World::self().ordinal(name, rank);
+  return nwref::World::self().ordinal(nwref::World::state_name(name, state), rank);
 }
 
 inline unsigned
@@ -508,6 +537,8 @@ public:
   double get_incompressible_solve() const { return w().get("solve_incompressible"); }
   double get_time_step() const { return w().get("dt"); }
   double get_gamma1() const { return w().get("gamma1"); }
+  double get_gamma2() const { return w().get("gamma2"); }
+  double get_gamma3() const { return w().get("gamma3"); }
   stk::mesh::Selector get_inactive_selector() const { return stk::mesh::Selector(); }
 
   SolutionOptions so_;

@@ -17,6 +17,10 @@ public:
   const std::string& name() const { return name_; }
   unsigned mesh_meta_data_ordinal() const { return ordinal_; }
   int max_size() const { return ncomp_; }
+  /* states: "F" is NP1, "F_n" is N, "F_nm1" is NM1 where registered (the
+   * look-up lives with the field table, nalu/RefHarness.h) */
+  unsigned number_of_states() const;
+  FieldBase& field_of_state(FieldState s) const;
   std::string name_;
   unsigned ordinal_ = InvalidOrdinal;
   int ncomp_ = 0;

@@ -27,6 +27,8 @@ struct FastMeshIndex
   unsigned bucket_id;
   unsigned bucket_ord;
 };
+class BulkData; /* defined with the stand-in mesh, nalu/RefHarness.h */
+class MetaData;
 class Part
 {
 };

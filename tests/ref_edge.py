@@ -37,6 +37,7 @@ def lib():
         L.ref_run_continuity.argtypes = [vp, vp]
         L.ref_run_wall_dist.argtypes = [vp, vp]
         L.ref_run_nodal_grad.argtypes = [C.c_char_p, C.c_char_p]
+        L.ref_run_node_kernel.argtypes = [C.c_int, C.c_char_p, vp, vp]
         _L = L
     return _L
 
@@ -91,6 +92,18 @@ class World:
 
     def continuity(self):
         return self._run(lib().ref_run_continuity, 2)
+
+    def node_kernel(self, which, q=""):
+        """{Scalar,Momentum,Continuity}MassBDFNodeKernel / WallDistNodeKernel:
+        local lhs [nNodes][n][n] and rhs [nNodes][n] of every node"""
+        k = {"scalar_mass": 0, "momentum_mass": 1, "continuity_mass": 2,
+             "wall_dist": 3}[which]
+        n = self.ndim if k == 1 else 1
+        lhs = np.zeros((self.n_nodes, n, n))
+        rhs = np.zeros((self.n_nodes, n))
+        if lib().ref_run_node_kernel(k, q.encode(), lhs.ctypes.data, rhs.ctypes.data):
+            raise RuntimeError(lib().ref_last_error().decode())
+        return lhs, rhs
 
     def wall_dist(self):
         return self._run(lib().ref_run_wall_dist, 2)

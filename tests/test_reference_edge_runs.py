@@ -326,6 +326,58 @@ def test_nodal_grad_peclet_alg_wall_dist_bitwise(key):
     assert same_bits(lhs, ol) and same_bits(rhs, orh)
 
 
+@live
+@pytest.mark.parametrize("key", ["3d", "2d"])
+@pytest.mark.parametrize("states", [3, 2])
+def test_node_kernels_bitwise(key, states):
+    """ScalarMassBDFNodeKernel, MomentumMassBDFNodeKernel,
+    ContinuityMassBDFNodeKernel (BDF2 with three states, BDF1 with two),
+    WallDistNodeKernel of the reference (src/node_kernels/*.C: constructor,
+    setup, execute per node) against the oracle's node kernels"""
+    st = state(key)
+    d, n = st.ndim, st.n_nodes
+    rng = np.random.default_rng(17)
+    q3 = [st.tke * (1.0 + 0.1 * rng.standard_normal(n)) for _ in range(2)] + [st.tke]
+    rho3 = [st.density * (1.0 + 0.05 * rng.random(n)) for _ in range(2)] + [st.density]
+    u3 = [st.velocity + 0.1 * rng.standard_normal((n, d)) for _ in range(2)] + [st.velocity]
+    dnv3 = [st.vol * (1.0 + 0.02 * rng.random(n)) for _ in range(2)] + [st.vol]
+    if states == 2:  # no NM1 state registered: the kernels alias it to N
+        q3[0], rho3[0], u3[0] = q3[1], rho3[1], u3[1]
+        dnv3[0] = dnv3[2]  # populate_dnv_states, two states: nm1 = np1
+    dt, g1, g2, g3 = 0.25, 1.5, -2.0, 0.5
+    w = st.world()
+    for name, arrs, nc in (("turbulent_ke", q3, 1), ("density", rho3, 1),
+                           ("velocity", u3, d), ("dual_nodal_volume", dnv3, 1)):
+        w.field(name + "_n", R.NODE, arrs[1], nc)
+        if states == 3:
+            w.field(name + "_nm1", R.NODE, arrs[0], nc)
+    w.option("dt", dt)
+    w.option("gamma1", g1)
+    w.option("gamma2", g2)
+    w.option("gamma3", g3)
+    nodes = np.arange(n, dtype=np.int32)
+    orc.set_num_threads(1)
+
+    def rec(f, *a):
+        s = orc.RecordSink()
+        f(*a, s)
+        return s.get()
+
+    lhs, rhs = w.node_kernel("scalar_mass", "turbulent_ke")
+    ol, orh = rec(orc.scalar_mass_bdf_node, nodes, q3, rho3, dnv3, dt, g1, g2, g3)
+    assert same_bits(lhs, ol) and same_bits(rhs, orh)
+    lhs, rhs = w.node_kernel("momentum_mass")
+    ol, orh = rec(orc.momentum_mass_bdf_node, d, nodes, u3, rho3, dnv3, st.dpdx,
+                  dt, g1, g2, g3)
+    assert same_bits(lhs, ol) and same_bits(rhs, orh)
+    lhs, rhs = w.node_kernel("continuity_mass")
+    ol, orh = rec(orc.continuity_mass_bdf_node, nodes, rho3, dnv3, dt, g1, g2, g3)
+    assert same_bits(lhs, ol) and same_bits(rhs, orh)
+    lhs, rhs = w.node_kernel("wall_dist")
+    ol, orh = rec(orc.wall_dist_node, nodes, st.vol)
+    assert same_bits(lhs, ol) and same_bits(rhs, orh)
+
+
 # ------------------------------ fixture -------------------------------------
 
 def _fixture():
