@@ -421,7 +421,35 @@ class CpuSample:
         t1 = min(self.sweep_one_rank(P, sst, 1) for _ in range(2))
         return {"single_thread_value": box.n_edges / t1 / 1e6,
                 "openmp_atomic_value": box.n_edges / ta / 1e6,
-                "openmp_atomic_threads": self.threads}
+                "openmp_atomic_threads": self.threads,
+                "reference_code": reference_code_leg()}
+
+
+def reference_code_leg(n=40):
+    """Calibration of the port, beside it: one momentum (UVW) and one continuity
+    assembly through the REFERENCE'S OWN edge algorithm + HypreLinearSystem code
+    (oracle/_ref: compiled unmodified against stand-in Kokkos / STK / hypre
+    headers) and through the oracle port on the same small
+    box, one thread each, results compared bit for bit.  The stand-in Realm
+    reads flat arrays where nalu-wind reads STK buckets, so this is not the
+    baseline (`value` stays the port, the faster of the two); never fatal."""
+    try:
+        so = os.path.join(ROOT, "oracle", "_ref", "libnalu_ref.so")
+        if not os.path.exists(so):
+            return {"unavailable": "oracle/_ref/libnalu_ref.so not built"}
+        for d in ("tools", "tests", "oracle"):
+            p = os.path.join(ROOT, d)
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        import cpu_reference_code_timing as crt
+        out = crt.measure(n, reps=2)
+        out["what"] = ("Medges/s of one assembly, one thread: the reference's own "
+                       "MomentumEdgeSolverAlg / ContinuityEdgeSolverAlg + "
+                       "HypreLinearSystem code run over stand-in infrastructure "
+                       "(oracle/_ref) vs the oracle port")
+        return out
+    except Exception as e:  # calibration only
+        return {"unavailable": str(e)[:200]}
 
 
 def run_cpu_baseline(P, n, sst):

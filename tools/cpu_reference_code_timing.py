@@ -36,20 +36,21 @@ def best(f, reps=3):
     return min(ts)
 
 
-def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+def measure(n=40, reps=3):
+    """one momentum (UVW) and one continuity assembly through the reference's
+    own code and through the oracle port, one thread each; Medges/s"""
     rc = H.RankCase((n, n, n), 1, 0)
     st, b = rc.st, rc.b
     orc.set_num_threads(1)
     o = T.MOM_POINTS[1]
-    print("box %d^3: %d nodes, %d edges; one thread" % (n, st.n_nodes, st.n_edges))
-    rows = []
+    out = {"box": "%d^3 elements, %d edges" % (n, st.n_edges), "cores": 1,
+           "unit": "Medges/s", "identical_results": True}
     # momentum (UVW)
     w = st.world()
     H._momentum_options(w, o)
     h = R.HypreRef(w, b.own_hid, uvw=True, num_dof=3, node_identifier=rc.ident,
                    node_owner=b.owner, nalu_id=rc.nalu, offsets=b.offsets)
-    t_ref = best(lambda: h.sweep("momentum"))
+    t_ref = best(lambda: h.sweep("momentum"), reps)
     g = rc.oracle_graph(1)
     s = orc.HypreSink(g, b.hid, uvw_ndim=3)
 
@@ -57,34 +58,45 @@ def main():
         s.reset()
         orc.momentum_edge(3, st.edges, st.coords, st.velocity, st.dudx, st.viscosity,
                           st.density, st.mask, st.area, st.mdot, st.pecfac, s, **o)
-    t_orc = best(orc_mom)
+    t_orc = best(orc_mom, reps)
     vals, r = h.values()
     ov, orh = s.get()
-    assert np.array_equal(vals, ov) and np.array_equal(r.ravel(), np.asarray(orh).ravel())
-    rows.append(("momentum (UVW)", t_ref, t_orc))
+    same = np.array_equal(vals, ov) and np.array_equal(r.ravel(), np.asarray(orh).ravel())
+    out["momentum_uvw"] = {"reference_code": st.n_edges / t_ref / 1e6,
+                           "port": st.n_edges / t_orc / 1e6}
     h.close()
     # continuity
     c = T.CONT_POINTS[0]
     w = T.ref_cont_world(st, c, False, False)
     h = R.HypreRef(w, b.own_hid, num_dof=1, node_identifier=rc.ident,
                    node_owner=b.owner, nalu_id=rc.nalu, offsets=b.offsets)
-    t_ref = best(lambda: h.sweep("continuity"))
+    t_ref = best(lambda: h.sweep("continuity"), reps)
     s1 = orc.HypreSink(g, b.hid)
 
     def orc_cont():
         s1.reset()
         T.orc_cont(st, c, False, False, s1)
-    t_orc = best(orc_cont)
+    t_orc = best(orc_cont, reps)
     vals, r = h.values()
     ov, orh = s1.get()
-    assert np.array_equal(vals, ov) and np.array_equal(r.ravel(), np.asarray(orh).ravel())
-    rows.append(("continuity", t_ref, t_orc))
+    same = same and np.array_equal(vals, ov) and np.array_equal(
+        r.ravel(), np.asarray(orh).ravel())
+    out["continuity"] = {"reference_code": st.n_edges / t_ref / 1e6,
+                         "port": st.n_edges / t_orc / 1e6}
     h.close()
-    print("%-16s %28s %28s" % ("assembly", "reference's own code", "oracle port"))
-    for name, a, p in rows:
-        print("%-16s %10.3f s %9.2f Medges/s %10.3f s %9.2f Medges/s" % (
-            name, a, st.n_edges / a / 1e6, p, st.n_edges / p / 1e6))
-    print("results identical bit for bit: yes")
+    out["identical_results"] = bool(same)
+    return out
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    m = measure(n)
+    print("box %s; one thread" % m["box"])
+    print("%-16s %24s %24s" % ("assembly", "reference's own code", "oracle port"))
+    for name in ("momentum_uvw", "continuity"):
+        print("%-16s %14.2f Medges/s %14.2f Medges/s" % (
+            name, m[name]["reference_code"], m[name]["port"]))
+    print("results identical bit for bit:", "yes" if m["identical_results"] else "NO")
 
 
 if __name__ == "__main__":
