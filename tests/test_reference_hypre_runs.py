@@ -41,9 +41,10 @@ class RankCase:
     """rank `rank` of an `nranks` z-slab decomposition of a (periodic) box with
     the state of test_reference_edge_runs.State"""
 
-    def __init__(self, dims, nranks, rank, periodic=(False, False), seed=3):
-        self.c = c = pu.Case(dims=dims, warp=0.1, nranks=nranks, rank=rank,
-                             periodic=periodic)
+    def __init__(self, dims, nranks, rank, periodic=(False, False), seed=3,
+                 case=None):
+        self.c = c = case if case is not None else pu.Case(
+            dims=dims, warp=0.1, nranks=nranks, rank=rank, periodic=periodic)
         b = c.box
         self.b = b
         st = T.State.__new__(T.State)
@@ -285,3 +286,27 @@ def test_reset_rows_and_dirichlet_bcs(tag, dims, nranks, periodic):
             assert np.array_equal(vals, ov)
             assert np.array_equal(r.ravel(), np.asarray(orh).ravel())
         h.close()
+
+
+def test_reference_decomposition_hybrid_g_8():
+    """the reference's own 8-way STK decomposition of hybrid.g (tet / pyramid /
+    hex; nodes shared by up to several ranks): every rank's graph, CoeffApplier
+    sums and hand-off through the reference's HypreLinearSystem vs the oracle"""
+    shared_total = 0
+    for rank in range(8):
+        case = pu.DecomposedRealMesh(rank=rank)
+        rc = RankCase(None, 8, rank, case=case)
+        lhs, rhs = T.ref_scalar(rc.st, T.SCAL_POINTS[1], T.PECLETS[2])
+        h = rc.hypre()
+        g = rc.oracle_graph()
+        check_graph(h, g)
+        shared_total += g.num_rows_shared
+        vals, r = h.assemble(lhs, rhs)
+        s = orc.HypreSink(g, rc.b.hid)
+        s.apply(rc.st.edges, lhs, rhs)
+        ov, orh = s.get()
+        assert np.array_equal(vals, ov)
+        assert np.array_equal(r.ravel(), np.asarray(orh).ravel())
+        check_handoff(h, g, vals, r)
+        h.close()
+    assert shared_total > 500
