@@ -17,6 +17,7 @@
 #include <edge_kernels/MomentumEdgeSolverAlg.h>
 #include <edge_kernels/ScalarEdgeSolverAlg.h>
 #include <edge_kernels/ContinuityEdgeSolverAlg.h>
+#include <SolverAlgorithm.h>
 
 #include <cstring>
 #include <memory>
@@ -281,28 +282,41 @@ ref_hypre_assemble(void* p, const double* lhs, const double* rhs, int n)
  * edge algorithm's execute() whose shell hands every local block straight to
  * the reference's CoeffApplier (no recording), loadComplete.  alg: 0 momentum
  * (system created with numDof = ndim, UVW or monolithic), 1 continuity,
- * 2 scalar (q, dqdx, dflux name the fields).  For timing the reference's own
+ * 2 scalar (q, dqdx, dflux name the fields); diagField non-empty: the
+ * extract_diagonal side channel of NGPApplyCoeff.  For timing the reference's own
  * code (tools/cpu_reference_code_timing.py) and as an end-to-end check. */
 int
-ref_hypre_sweep(void* p, int alg, const char* q, const char* dqdx, const char* dflux)
+ref_hypre_sweep(
+  void* p, int alg, const char* q, const char* dqdx, const char* dflux,
+  const char* diagField)
 {
   auto* h = static_cast<Handle*>(p);
   return guarded([&] {
     auto& w = World::self();
     h->ls().zeroSystem();
-    auto* dev = dynamic_cast<HypreLinearSystem::HypreLinSysCoeffApplier*>(
-      h->ls().get_coeff_applier());
+    /* the applier the reference's loop shell calls: NGPApplyCoeff
+     * (SolverAlgorithm.h:89, src/SolverAlgorithm.C:49-151) -- extract_diagonal
+     * into `diagField` when given, then the linear system's CoeffApplier,
+     * which its constructor fetches with get_coeff_applier() */
+    h->eq.linsys_ = &h->ls();
+    h->eq.extractDiagonal_ = diagField && diagField[0];
+    if (h->eq.extractDiagonal_)
+      h->eq.diagonalFieldName_ = diagField;
+    NGPApplyCoeff applier(&h->eq);
     const int nmax = 2 * 3;
     std::vector<int> ids(nmax), perm(nmax);
+    std::vector<double> lbuf(nmax * nmax), rbuf(nmax);
     stk::mesh::Entity nodes[2];
     w.applyHook = [&](long e, const double* lhs, const double* rhs, int n) {
       nodes[0].m_value = (uint64_t)w.edgeNodes[2 * e];
       nodes[1].m_value = (uint64_t)w.edgeNodes[2 * e + 1];
       stk::mesh::NgpMesh::ConnectedNodes cn(nodes, 2);
+      std::memcpy(lbuf.data(), lhs, sizeof(double) * n * n);
+      std::memcpy(rbuf.data(), rhs, sizeof(double) * n);
       SharedMemView<int*, DeviceShmem> idv(ids.data(), n), pv(perm.data(), n);
-      SharedMemView<const double*, DeviceShmem> rv(rhs, n);
-      SharedMemView<const double**, DeviceShmem> lv(lhs, n, n);
-      (*dev)(2, cn, idv, pv, rv, lv, "ref_hypre_sweep");
+      SharedMemView<double*, DeviceShmem> rv(rbuf.data(), n);
+      SharedMemView<double**, DeviceShmem> lv(lbuf.data(), n, n);
+      applier(2, cn, idv, pv, rv, lv, "ref_hypre_sweep");
     };
     try {
       auto handle = [&](const char* nm) {

@@ -444,6 +444,16 @@ public:
   stk::mesh::NgpMesh mesh_;
   FieldManager fm_;
 };
+/* ngp_utils/NgpFieldUtils.h */
+template <class T = double>
+inline stk::mesh::NgpField<T>
+get_ngp_field(
+  const MeshInfoShim& meshInfo, const std::string& fieldName,
+  const stk::mesh::EntityRank& rank = stk::topology::NODE_RANK)
+{
+  return meshInfo.ngp_field_manager().template get_field<T>(
+    nwref::World::self().ordinal(fieldName, rank));
+}
 } // namespace nalu_ngp
 
 class SolutionOptions
@@ -519,6 +529,7 @@ public:
   bool isFinalOuterIter_ = false;
   double l2Scaling_ = 1.0;
   bool hasPeriodic_ = false;
+  bool hasOverset_ = false;
   stk::mesh::BulkData& bulk_data() { return bulk_; }
   const stk::mesh::NgpMesh& ngp_mesh() const { return ngpMesh_; }
   const nalu_ngp::FieldManager& ngp_field_manager() const { return fm_; }
@@ -552,10 +563,35 @@ private:
   nalu_ngp::MeshInfoShim meshInfo_;
 };
 
+class LinearSystem;
 class EquationSystem
 {
 public:
-  explicit EquationSystem(int numDof) : numDof_(numDof) {}
+  explicit EquationSystem(int numDof) : realm_(default_realm()), numDof_(numDof) {}
+  EquationSystem(int numDof, Realm& realm) : realm_(realm), numDof_(numDof) {}
+  static Realm& default_realm()
+  {
+    static Realm r;
+    return r;
+  }
+  /* what NGPApplyCoeff (src/SolverAlgorithm.C) asks of its equation system */
+  Realm& realm_;
+  LinearSystem* linsys_ = nullptr;
+  bool extractDiagonal_ = false;
+  bool resetOversetRows_ = true;
+  /* host-side twin of extract_diagonal (src/EquationSystem.C); not on the NGP path */
+  void save_diagonal_term(
+    const std::vector<stk::mesh::Entity>&, const std::vector<int>&,
+    const std::vector<double>&)
+  {
+  }
+  std::string diagonalFieldName_ = "momentum_diag";
+  ScalarFieldType* get_diagonal_field() const
+  {
+    const auto& w = nwref::World::self();
+    return static_cast<ScalarFieldType*>(
+      w.fieldHandles.at(w.ordinal(diagonalFieldName_, stk::topology::NODE_RANK)));
+  }
   /* src/EquationSystem.C: builds the blending function the input file names */
   template <class T>
   PecletFunction<T>* ngp_create_peclet_function(const std::string&)

@@ -155,7 +155,8 @@ class HypreRef:
         L.ref_hypre_values.argtypes = [vp, vp, vp]
         L.ref_hypre_reset_rows.argtypes = [vp, vp, C.c_int, C.c_double, C.c_double]
         L.ref_hypre_apply_dirichlet.argtypes = [vp, C.c_char_p, C.c_char_p, vp, C.c_int]
-        L.ref_hypre_sweep.argtypes = [vp, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p]
+        L.ref_hypre_sweep.argtypes = [vp, C.c_int, C.c_char_p, C.c_char_p,
+                                      C.c_char_p, C.c_char_p]
         L.ref_hypre_rhs_shape.argtypes = [vp, vp]
         L.ref_hypre_ij_calls.argtypes = [vp, C.c_int]
         L.ref_hypre_ij_call_sizes.argtypes = [vp, C.c_int, C.c_int, vp]
@@ -224,13 +225,14 @@ class HypreRef:
         lib().ref_hypre_values(self.h, vals.ctypes.data, r.ctypes.data)
         return vals, r
 
-    def sweep(self, alg, q="", dqdx="", dflux=""):
+    def sweep(self, alg, q="", dqdx="", dflux="", diag_field=""):
         """one assembly as the reference runs it (zeroSystem, the edge
         algorithm's execute() feeding the reference's CoeffApplier,
-        loadComplete); alg: 'momentum' | 'continuity' | 'scalar'"""
+        loadComplete); alg: 'momentum' | 'continuity' | 'scalar'; diag_field:
+        NGPApplyCoeff::extract_diagonal adds lhs(ix, ix) of every node into it"""
         k = {"momentum": 0, "continuity": 1, "scalar": 2}[alg]
         self._chk(lib().ref_hypre_sweep(self.h, k, q.encode(), dqdx.encode(),
-                                        dflux.encode()))
+                                        dflux.encode(), diag_field.encode()))
         return self.values()
 
     def reset_rows(self, nodes, diag_value, rhs_residual):

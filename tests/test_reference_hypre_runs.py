@@ -310,3 +310,33 @@ def test_reference_decomposition_hybrid_g_8():
         check_handoff(h, g, vals, r)
         h.close()
     assert shared_total > 500
+
+
+@pytest.mark.parametrize("system", ["monolithic", "uvw"])
+def test_extract_diagonal_side_channel(system):
+    """NGPApplyCoeff::extract_diagonal (src/SolverAlgorithm.C:87-105): with
+    projected_timescale_type momentum_diag_inv the momentum assembly adds
+    lhs(ix, ix), the first dof's diagonal entry of each of the two nodes, into
+    momentum_diag before the block goes to the CoeffApplier"""
+    uvw = system == "uvw"
+    o = T.MOM_POINTS[1]
+    rc = RankCase((5, 4, 3), 1, 0, (True, False))
+    st, b = rc.st, rc.b
+    w = st.world()
+    _momentum_options(w, o)
+    diag = w.field("extracted_diag", R.NODE, np.zeros(st.n_nodes), 1)
+    h = R.HypreRef(w, b.own_hid, uvw=uvw, num_dof=3, node_identifier=rc.ident,
+                   node_owner=b.owner, nalu_id=rc.nalu, offsets=b.offsets)
+    vals, r = h.sweep("momentum", diag_field="extracted_diag")
+    g = rc.oracle_graph(1 if uvw else 3)
+    s = orc.HypreSink(g, b.hid, uvw_ndim=3 if uvw else 0)
+    od = np.zeros(st.n_nodes)
+    orc.set_num_threads(1)
+    orc.momentum_edge(3, st.edges, st.coords, st.velocity, st.dudx, st.viscosity,
+                      st.density, st.mask, st.area, st.mdot, st.pecfac, s,
+                      udiag_accum=od, **o)
+    ov, orh = s.get()
+    assert np.array_equal(vals, ov)
+    assert np.array_equal(r.ravel(), np.asarray(orh).ravel())
+    assert np.abs(od).max() > 0 and np.array_equal(diag.ravel(), od)
+    h.close()
