@@ -396,3 +396,40 @@ def test_vof_branch_is_the_identity_for_uniform_density():
             o["relax_fac"], 1, 1e-16, 0, P.peclet_fn("classic", 1.0), 1e-16,
             -1, vof), nnz, rows, 3, mdot=mdot, pecfac=pec))
     assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1])
+
+
+@FMA
+def test_wall_mask_with_zeros_product_header_vs_oracle(fma):
+    """abl_wall_no_slip_wall_func_node_mask with zeros (the synthetic state sets
+    it to one everywhere): the masked viscous terms of MomentumEdgeSolverAlg.C:
+    267-269 through the product header's default and general paths"""
+    P = pu.pkg()
+    c = _case(dims=(6, 5, 6))
+    f, b = c.fields, c.box
+    rng = np.random.default_rng(4)
+    f["abl_wall_no_slip_wall_func_node_mask"] = (rng.random(c.n_nodes) > 0.3).astype(float)
+    emu = pu.Emu(c, tile_nodes=40, fma=fma)
+    emu.build_linsys(0, 1)
+    g = c.oracle_graph()
+    nnz, rows = _graph_sizes(g)
+    mdot = c.oracle_mdot()
+    pec = c.oracle_pecfac(orc.peclet("classic", 1.0))
+    for o in (dict(include_divu=0.0, alpha=0.0, alpha_upw=1.0, ho_upwind=1.0,
+                   relax_fac=0.7, use_limiter=True),
+              dict(include_divu=1.0, alpha=0.4, alpha_upw=0.6, ho_upwind=0.5,
+                   relax_fac=0.7, use_limiter=True)):
+        s = orc.HypreSink(g, b.hid, uvw_ndim=3)
+        orc.momentum_edge(3, c.edges, b.coords, f["velocity"], f["dudx"],
+                          f["viscosity"], f["density"],
+                          f["abl_wall_no_slip_wall_func_node_mask"], c.area, mdot,
+                          pec, s, **o)
+        ov, orh = s.get()
+        av, arhs = s.get_abs()
+        for fuse in (0, 1):
+            po = P.MomentumOpts(o["include_divu"], o["alpha"], o["alpha_upw"],
+                                o["ho_upwind"], o["relax_fac"], 1, 1e-16, fuse,
+                                P.peclet_fn("classic", 1.0), 1e-16, -1, 0)
+            vals, rhs = emu.assemble(2, pu.MOM_FIELDS, po, nnz, rows, 3, mdot=mdot,
+                                     pecfac=pec)
+            assert pu.scaled_err(vals, ov, av) < 1
+            assert pu.scaled_err(rhs, orh, arhs) < 1
