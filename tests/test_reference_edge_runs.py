@@ -378,6 +378,30 @@ def test_node_kernels_bitwise(key, states):
     assert same_bits(lhs, ol) and same_bits(rhs, orh)
 
 
+@live
+@pytest.mark.parametrize("seed", range(6))
+def test_random_option_points_bitwise(seed):
+    """30 random points of the option space per seed (momentum with and without
+    VOF on the two-phase state, scalar with random blending functions)"""
+    rng = np.random.default_rng(1000 + seed)
+    st = state("3d-two-phase")
+    for _ in range(5):
+        o = dict(include_divu=float(rng.integers(0, 2)), alpha=float(rng.random()),
+                 alpha_upw=float(rng.random()), ho_upwind=float(rng.random()),
+                 relax_fac=float(0.3 + 0.7 * rng.random()),
+                 use_limiter=bool(rng.integers(0, 2)))
+        for vof in (False, True):
+            lhs, rhs = ref_momentum(st, o, vof=vof)
+            ol, orh = orc_momentum(st, o, vof=vof)
+            assert same_bits(lhs, ol) and same_bits(rhs, orh), (o, vof)
+        so = {k: o[k] for k in ("alpha", "alpha_upw", "ho_upwind", "relax_fac", "use_limiter")}
+        pec = (("classic", float(rng.random()), 1.0) if rng.integers(0, 2)
+               else ("tanh", float(10.0 ** rng.uniform(-1, 3)), float(10.0 ** rng.uniform(-1, 2))))
+        lhs, rhs = ref_scalar(st, so, pec)
+        ol, orh = orc_scalar(st, so, pec)
+        assert same_bits(lhs, ol) and same_bits(rhs, orh), (so, pec)
+
+
 # ------------------------------ fixture -------------------------------------
 
 def _fixture():
