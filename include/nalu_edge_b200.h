@@ -229,6 +229,23 @@ int nw_field_periodic_update(nw_mesh* mesh, int field_id);
  * 161-169, so that the next sweep reads current values on shared nodes): every
  * non-owned copy takes its owner's value.  Single rank: no-op. */
 int nw_field_copy_owned_to_shared(nw_mesh* mesh, int field_id);
+/* The consumer of extract_diagonal: the part of
+ * MomentumEquationSystem::assemble_and_solve that follows the momentum
+ * assembly when projected_timescale_type is momentum_diag_inv
+ * (src/LowMachEquationSystem.C:2759-2821).  In the reference's order:
+ * stk::mesh::parallel_sum of the shared-node copies of udiag (:2770-2774);
+ * on every locally owned node that is not a periodic slave
+ *     udiag = (udiag / (density * dual_nodal_volume) - gamma1/dt) * alpha_u
+ *             + gamma1/dt                                     (:2776-2790)
+ * (alpha_u: the velocity relaxation factor the assembly divided the diagonal
+ * by); copy_owned_to_shared (:2795-2800); periodic slaves take their master's
+ * value (apply_constraints with setSlaves only, :2802-2808).  All on the
+ * device, no host round trip; the non-conformal / overset updates of :2809-2817
+ * are out of scope.  The caller resets udiag before the assembly
+ * (nw_field_fill, :2741-2751) and passes it as nw_momentum_opts.diag_field. */
+int nw_momentum_diag_post_process(
+  nw_mesh* mesh, int udiag_field, int density_field,
+  int dual_nodal_volume_field, double dt, double gamma1, double alpha_u);
 /* transport the nodal halo sum of this mesh uses (nw_halo_transport) */
 int nw_mesh_halo_transport(const nw_mesh* mesh);
 

@@ -136,7 +136,7 @@ ABI_SYMBOLS = [
     "nw_linsys_apply_dirichlet_bcs", "nw_linsys_load_complete",
     "nw_linsys_device_arrays", "nw_linsys_get_values", "nw_linsys_rhs_norm2", "nw_linsys_rhs_norm2_global",
     "nw_mesh_halo_send_count", "nw_mesh_halo_get_send", "nw_mesh_halo_set_recv",
-    "nw_mesh_halo_commit", "nw_field_parallel_sum", "nw_field_periodic_update", "nw_field_copy_owned_to_shared", "nw_linsys_halo_send_info",
+    "nw_mesh_halo_commit", "nw_field_parallel_sum", "nw_field_periodic_update", "nw_momentum_diag_post_process", "nw_field_copy_owned_to_shared", "nw_linsys_halo_send_info",
     "nw_linsys_halo_get_send", "nw_linsys_halo_set_recv",
     "nw_linsys_halo_commit", "nw_linsys_halo_get_recv_slots",
     "nw_linsys_get_extra",
@@ -242,6 +242,8 @@ def lib():
     L.nw_mesh_halo_commit.argtypes = [vp]
     L.nw_field_parallel_sum.argtypes = [vp, C.c_int]
     L.nw_field_periodic_update.argtypes = [vp, C.c_int]
+    L.nw_momentum_diag_post_process.argtypes = [
+        vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
     L.nw_field_copy_owned_to_shared.argtypes = [vp, C.c_int]
     L.nw_linsys_halo_send_info.argtypes = [vp, C.c_int, c_i64p, c_i64p]
     L.nw_linsys_halo_get_send.argtypes = [vp, C.c_int, c_i64p, c_i64p, c_i64p]
@@ -493,6 +495,15 @@ class Mesh:
 
     def copy_owned_to_shared(self, name):
         _chk(lib().nw_field_copy_owned_to_shared(self.h, self.field_id(name)))
+
+    def momentum_diag_post_process(self, dt, gamma1, alpha_u,
+                                   udiag="momentum_diag", density="density",
+                                   dnv="dual_nodal_volume"):
+        """udiag post-processing of MomentumEquationSystem::assemble_and_solve
+        (src/LowMachEquationSystem.C:2759-2821)"""
+        _chk(lib().nw_momentum_diag_post_process(
+            self.h, self.field_id(udiag), self.field_id(density),
+            self.field_id(dnv), dt, gamma1, alpha_u))
 
     def halo_transport(self):
         return ["none", "nccl", "peer_memory"][lib().nw_mesh_halo_transport(self.h)]

@@ -69,6 +69,18 @@ nw_rcp(double x)
 #define NW_XDIV(a, b) ((a) / (b))
 #endif
 
+/* LowMach::udiag_post_processing, one node (src/LowMachEquationSystem.C:
+ * 2783-2790): the extracted momentum diagonal per unit mass with the velocity
+ * relaxation taken out again; every operation rounded on its own */
+NW_HD double
+udiag_post_value(
+  double udiag, double rho, double dualVol, double projTimeScale, double alphaU)
+{
+  const double udiagTmp = NW_XDIV(udiag, NW_XMUL(rho, dualVol));
+  return NW_XADD(
+    NW_XMUL(NW_XADD(udiagTmp, -projTimeScale), alphaU), projTimeScale);
+}
+
 NW_HD double
 peclet_eval(const nw_peclet_fn& f, double pecnum)
 {

@@ -254,6 +254,9 @@ struct nw_mesh
   nw::DevBuf dPerPtr, dPerSlots;
   /* node-kernel selector: locally owned and not a periodic slave */
   std::vector<uint8_t> nodeKernelActive;
+  /* slots of the selected nodes on the device (udiag post-processing) */
+  nw::DevBuf dActiveSlots;
+  int64_t nActiveSlots = -1;
   int64_t planBytes = 0;
   /* finalized graphs / plans of this mesh's linear systems (see nw_ls_shared) */
   std::vector<std::shared_ptr<nw_ls_shared>> lsCache;

@@ -4822,6 +4822,67 @@ launch_periodic_update(
   return cudaGetLastError();
 }
 
+namespace {
+/* LowMach::udiag_post_processing (src/LowMachEquationSystem.C:2783-2790):
+ * thread per selected node (locally owned, not a periodic slave); arithmetic
+ * in edge_physics.h (udiag_post_value) */
+__global__ void __launch_bounds__(256) udiag_post_kernel(
+  double* udiag, const double* __restrict__ rho,
+  const double* __restrict__ dvol, const int32_t* __restrict__ slots, int64_t n,
+  double projTimeScale, double alphaU)
+{
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t k = slots[t];
+    udiag[k] = udiag_post_value(udiag[k], rho[k], dvol[k], projTimeScale, alphaU);
+  }
+}
+
+/* PeriodicManager::apply_constraints with setSlaves only
+ * (src/LowMachEquationSystem.C:2802-2808): every slave takes its master's
+ * value; thread per (group, component) */
+__global__ void __launch_bounds__(256) periodic_set_kernel(
+  double* base, int64_t stride, int nc, const int32_t* __restrict__ ptr,
+  const int32_t* __restrict__ slots, int nGroups)
+{
+  const int64_t total = (int64_t)nGroups * nc;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(t / nc);
+    const int c = (int)(t - (int64_t)g * nc);
+    double* f = base + (int64_t)c * stride;
+    const int a = ptr[g], b = ptr[g + 1];
+    const double v = f[slots[a]];
+    for (int q = a + 1; q < b; ++q)
+      f[slots[q]] = v;
+  }
+}
+} // namespace
+
+cudaError_t
+launch_udiag_post(
+  double* udiag, const double* rho, const double* dvol, const int32_t* slots,
+  int64_t n, double projTimeScale, double alphaU, cudaStream_t s)
+{
+  if (n == 0)
+    return cudaSuccess;
+  udiag_post_kernel<<<blocks_for(n, 256), 256, 0, s>>>(
+    udiag, rho, dvol, slots, n, projTimeScale, alphaU);
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_periodic_set(
+  double* base, int64_t stride, int nc, const int32_t* ptr,
+  const int32_t* slots, int nGroups, cudaStream_t s)
+{
+  if (nGroups == 0)
+    return cudaSuccess;
+  periodic_set_kernel<<<blocks_for((int64_t)nGroups * nc, 256), 256, 0, s>>>(
+    base, stride, nc, ptr, slots, nGroups);
+  return cudaGetLastError();
+}
+
 cudaError_t
 launch_unpack_add(
   const double* src, const int64_t* idx, int64_t n, double* dst, cudaStream_t s)

@@ -367,6 +367,15 @@ cudaError_t launch_accumulate_multi(
 cudaError_t launch_periodic_update(
   double* base, int64_t stride, int nc, const int32_t* ptr,
   const int32_t* slots, int nGroups, cudaStream_t s);
+/* apply_constraints with setSlaves only: slaves take the master's value */
+cudaError_t launch_periodic_set(
+  double* base, int64_t stride, int nc, const int32_t* ptr,
+  const int32_t* slots, int nGroups, cudaStream_t s);
+/* LowMach::udiag_post_processing over the selected node slots
+ * (src/LowMachEquationSystem.C:2783-2790) */
+cudaError_t launch_udiag_post(
+  double* udiag, const double* rho, const double* dvol, const int32_t* slots,
+  int64_t n, double projTimeScale, double alphaU, cudaStream_t s);
 cudaError_t launch_unpack_add(
   const double* src, const int64_t* idx, int64_t n, double* dst,
   cudaStream_t s);

@@ -103,6 +103,16 @@ public:
   {
     nw_check(nw_field_periodic_update(mesh_, field_ordinal(field)));
   }
+  /* the udiag post-processing of MomentumEquationSystem::assemble_and_solve
+   * (src/LowMachEquationSystem.C:2759-2821) */
+  void momentum_diag_post_process(
+    double dt, double gamma1, double alphaU,
+    const std::string& udiag = "momentum_diag")
+  {
+    nw_check(nw_momentum_diag_post_process(
+      mesh_, field_ordinal(udiag), field_ordinal("density"),
+      field_ordinal("dual_nodal_volume"), dt, gamma1, alphaU));
+  }
   nw_mesh* mesh() { return mesh_; }
   nw_ctx* ctx() { return ctx_; }
 

@@ -1062,4 +1062,15 @@ emu_default_path_mismatches(int64_t n, uint64_t seed)
   return bad;
 }
 
+/* udiag_post_kernel's arithmetic over a list of nodes (csrc/edge_physics.h:
+ * udiag_post_value) */
+void
+emu_udiag_post(
+  int64_t n, double* udiag, const double* rho, const double* dvol,
+  double projTimeScale, double alphaU)
+{
+  for (int64_t i = 0; i < n; ++i)
+    udiag[i] = udiag_post_value(udiag[i], rho[i], dvol[i], projTimeScale, alphaU);
+}
+
 } // extern "C"

@@ -84,6 +84,30 @@ def periodic_field_update(field, hid, own_hid):
     return f.reshape(np.shape(field))
 
 
+def momentum_diag_post_process(udiag, rho, dvol, hid, own_hid, dt, gamma1,
+                               alpha_u, lo=None, hi=None):
+    """The udiag post-processing of MomentumEquationSystem::assemble_and_solve
+    (src/LowMachEquationSystem.C:2776-2808) restated for the checker, one rank
+    (the parallel_sum / copy_owned_to_shared around it are exchanges): on the
+    locally owned nodes that are not periodic slaves
+        udiag = (udiag / (rho * dualVol) - gamma1/dt) * alphaU + gamma1/dt,
+    then every periodic slave takes its master's value (apply_constraints with
+    setSlaves only).  numpy rounds every operation on its own, like the
+    reference's builds."""
+    u = np.array(udiag, dtype=np.float64)
+    hid, own = np.asarray(hid), np.asarray(own_hid)
+    sel = own == hid
+    if lo is not None:
+        sel &= (own >= lo) & (own <= hi)
+    pts = gamma1 / dt
+    tmp = u[sel] / (np.asarray(rho)[sel] * np.asarray(dvol)[sel])
+    u[sel] = (tmp - pts) * alpha_u + pts
+    master = {int(hid[n]): n for n in np.nonzero(own == hid)[0]}
+    for n in np.nonzero(own != hid)[0]:
+        u[n] = u[master[int(hid[n])]]
+    return u
+
+
 def add_tet_split_edges(b, seed=20261017):
     """Turn the hex box's edge graph into that of its 6-tet (Kuhn) split: every
     cell gains its three face diagonals towards (+,+,0), (+,0,+), (0,+,+) and
@@ -309,7 +333,8 @@ def emu_lib(fma=False):
             base = emu_lib()
             for name in ("emu_create", "emu_error", "emu_destroy",
                          "emu_build_linsys", "emu_check_plan", "emu_assemble_mono",
-                         "emu_assemble", "emu_nodal_grad", "emu_mdot"):
+                         "emu_assemble", "emu_nodal_grad", "emu_mdot",
+                         "emu_udiag_post"):
                 getattr(L, name).argtypes = getattr(base, name).argtypes
                 getattr(L, name).restype = getattr(base, name).restype
             _emu_variants[key] = L
@@ -333,6 +358,8 @@ def emu_lib(fma=False):
         L.emu_nodal_grad.argtypes = [vp, C.c_int, vp, vp, vp, vp]
         L.emu_mdot.argtypes = [vp, vp, vp, C.c_int, vp, C.c_double,
                                C.c_double, vp]
+        L.emu_udiag_post.restype = None
+        L.emu_udiag_post.argtypes = [C.c_int64, vp, vp, vp, C.c_double, C.c_double]
         _emu = L
     return _emu
 

@@ -71,6 +71,8 @@ def test_every_compute_entry_refuses_without_device(env):
         "nw_field_fill": lambda: mesh.fill("density", 0.0),
         "nw_field_parallel_sum": lambda: mesh.parallel_sum("dual_nodal_volume"),
         "nw_field_copy_owned_to_shared": lambda: mesh.copy_owned_to_shared("density"),
+        "nw_momentum_diag_post_process": lambda: mesh.momentum_diag_post_process(
+            0.5, 1.5, 0.7),
         "nw_mdot_edge": lambda: mesh.mdot_edge(1.0, 1.0),
         "nw_mdot_edge_ext": lambda: mesh.mdot_edge_ext(mesh.extra_opts(
             edge_face_vel_mag="mass_flow_rate")),
@@ -127,6 +129,19 @@ def test_bad_arguments_are_refused(env):
     assert L.nw_mdot_edge(None, None) == 1          # NW_ERR_ARG
     assert b"nw_mdot_edge" in L.nw_last_error()
     assert L.nw_linsys_zero(None) == 1
+    fid = mesh.field_id
+    assert L.nw_momentum_diag_post_process(None, 0, 0, 0, 0.5, 1.5, 0.7) == 1
+    # three distinct scalar nodal fields, dt > 0
+    assert L.nw_momentum_diag_post_process(
+        mesh.h, fid("velocity"), fid("density"), fid("dual_nodal_volume"),
+        0.5, 1.5, 0.7) == 1
+    assert L.nw_momentum_diag_post_process(
+        mesh.h, fid("density"), fid("density"), fid("dual_nodal_volume"),
+        0.5, 1.5, 0.7) == 1
+    assert L.nw_momentum_diag_post_process(
+        mesh.h, fid("momentum_diag"), fid("density"), fid("dual_nodal_volume"),
+        0.0, 1.5, 0.7) == 1
+    assert b"nw_momentum_diag_post_process" in L.nw_last_error()
     assert L.nw_field_fill(mesh.h, 10_000, 0.0) != 0
     with pytest.raises(P.NwError):
         mesh.field_id("no_such_field")

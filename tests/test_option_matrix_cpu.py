@@ -433,3 +433,38 @@ def test_wall_mask_with_zeros_product_header_vs_oracle(fma):
                                      pecfac=pec)
             assert pu.scaled_err(vals, ov, av) < 1
             assert pu.scaled_err(rhs, orh, arhs) < 1
+
+
+@FMA
+def test_udiag_post_processing_product_header_vs_restatement(fma):
+    """udiag_post_value (the arithmetic of nw_momentum_diag_post_process,
+    src/LowMachEquationSystem.C:2783-2790) against the numpy restatement on the
+    oracle's extracted diagonal: bit-identical in the plain build; the
+    contracted build may fuse (tmp - pts) * alphaU + pts, one rounding less"""
+    c = _case(dims=(7, 6, 5))
+    f, b = c.fields, c.box
+    g = c.oracle_graph()
+    ud = np.zeros(c.n_nodes)
+    pu.oracle_momentum(c, g, c.oracle_mdot(),
+                       c.oracle_pecfac(orc.peclet("classic", 1.0)), uvw=True, udiag=ud)
+    for alpha_u in (0.7, 1.0):
+        ref = pu.momentum_diag_post_process(
+            ud, f["density"], f["dual_nodal_volume"], b.hid, b.own_hid, pu.DT,
+            pu.GAMMA1, alpha_u)
+        got = np.ascontiguousarray(ud.copy())
+        rho = np.ascontiguousarray(f["density"], dtype=np.float64)
+        vol = np.ascontiguousarray(f["dual_nodal_volume"], dtype=np.float64)
+        pu.emu_lib(fma).emu_udiag_post(
+            c.n_nodes, got.ctypes.data, rho.ctypes.data, vol.ctypes.data,
+            pu.GAMMA1 / pu.DT, alpha_u)
+        if fma:
+            tmp = ud / (rho * vol)
+            assert np.all(np.abs(got - ref) <= 2.3e-16 * (np.abs(tmp) + pu.GAMMA1 / pu.DT))
+        else:
+            assert np.array_equal(got, ref)
+        # what the step undoes: udiag = rho vol ((x - pts) / alphaU + pts) gives x back
+        x = 3.0 + np.arange(c.n_nodes) * 1e-3
+        back = pu.momentum_diag_post_process(
+            rho * vol * ((x - pu.GAMMA1 / pu.DT) / alpha_u + pu.GAMMA1 / pu.DT),
+            rho, vol, b.hid, b.own_hid, pu.DT, pu.GAMMA1, alpha_u)
+        assert np.allclose(back, x, rtol=1e-14, atol=0)

@@ -8,7 +8,8 @@
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-python -m pytest tests/test_zy_option_matrix_gpu.py tests/test_zz_vof_gpu.py -m gpu -q \
+python -m pytest tests/test_zy_option_matrix_gpu.py tests/test_zz_vof_gpu.py \
+  tests/test_zzz_reference_runs_gpu.py tests/test_zzzz_udiag_post_gpu.py -m gpu -q \
   > gpurun_out/next_new_gpu_tests.log 2>&1
 echo "new GPU tests rc=$?"; tail -5 gpurun_out/next_new_gpu_tests.log
 python -m pytest tests -m gpu -x -q > gpurun_out/next_pytest_gpu.log 2>&1
